@@ -1,0 +1,427 @@
+"""ctypes front end of the CPU oracle (oracle/gap_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / ``--impl reference`` legs of bench.py.  Nothing under quip_b200/
+imports this module.
+
+Besides the bindings it holds an *independent* (Python, ElementTree) reading of
+the GAP XML format and of QUIP's ``key=value`` descriptor strings, so that the
+product's C++ loader (quip_b200/csrc/gap_model.cpp) is checked against a second
+implementation rather than against itself.  Reference lines followed:
+  * XML tags/attributes: src/GAP/gp_predict.f95:4584-5057, 5200-5273;
+    src/Potentials/IPModel_GAP.f95:618-700
+  * sparseX side files: src/libAtoms/cutil.c:195-214
+  * argument grammar: src/libAtoms/ParamReader.f95:393-518
+  * SOAP string defaults / version switches: src/GAP/descriptors.f95:2502-2596
+  * distance_2b defaults: src/GAP/descriptors.f95:1771-1782
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+def build():
+    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libgaporacle.so")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "gap_oracle.c")):
+            build()
+        L = C.CDLL(path)
+        L.orc_connect_new.restype = C.c_void_p
+        L.orc_connect_new.argtypes = [C.c_int, c_dp, c_dp, c_ip, C.c_double]
+        L.orc_connect_free.argtypes = [C.c_void_p]
+        L.orc_connect_total.argtypes = [C.c_void_p]
+        L.orc_connect_cells.argtypes = [C.c_void_p, c_ip]
+        L.orc_connect_get.argtypes = [C.c_void_p, c_ip, c_ip, c_ip, c_dp]
+        L.orc_soap_new.restype = C.c_void_p
+        L.orc_soap_new.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                   C.c_double, C.c_int, C.c_int, c_ip, C.c_int, c_ip, C.c_int, C.c_int, C.c_double,
+                                   C.c_double, C.c_double]
+        L.orc_soap_free.argtypes = [C.c_void_p]
+        L.orc_soap_dim.argtypes = [C.c_void_p]
+        L.orc_soap_get_basis.argtypes = [C.c_void_p, c_dp, c_dp, c_dp]
+        L.orc_soap_calc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_ip, c_dp, C.c_int, c_ip, c_dp, c_ip, c_ip,
+                                    c_dp, c_ip, c_dp, c_ip]
+        L.orc_model_new.restype = C.c_void_p
+        L.orc_model_free.argtypes = [C.c_void_p]
+        L.orc_model_set_e0.argtypes = [C.c_void_p, c_dp, C.c_int]
+        L.orc_model_set_E_scale.argtypes = [C.c_void_p, C.c_double]
+        L.orc_model_cutoff.restype = C.c_double
+        L.orc_model_cutoff.argtypes = [C.c_void_p]
+        L.orc_model_add_soap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, c_dp, C.c_double, C.c_double]
+        L.orc_model_add_distance_2b.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp,
+                                                c_dp, c_dp, C.c_double, C.c_double, C.c_double]
+        L.orc_model_calc.argtypes = [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_double, C.c_int, C.c_int, C.c_int,
+                                     c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+        L.orc_model_predict.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip) if a is not None else None
+
+
+# ----------------------------------------------------------------------
+# key=value strings (ParamReader.f95:393-518)
+# ----------------------------------------------------------------------
+def split_fields(line):
+    """split on space/comma with {} "" '' grouping (split_string(..., matching=.true.))"""
+    fields, cur, depth, quote = [], "", 0, None
+    for ch in line:
+        if quote:
+            if ch == quote:
+                quote = None
+            else:
+                cur += ch
+        elif ch in "\"'" and depth == 0:
+            quote = ch
+        elif ch == "{":
+            if depth > 0:
+                cur += ch
+            depth += 1
+        elif ch == "}":
+            depth -= 1
+            if depth > 0:
+                cur += ch
+        elif ch in " ," and depth == 0:
+            if cur:
+                fields.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur:
+        fields.append(cur)
+    return fields
+
+
+def parse_args(line):
+    out = {}
+    for fld in split_fields(line):
+        if "=" in fld:
+            k, v = fld.split("=", 1)
+            out[k] = v
+        else:
+            out[fld] = "T"  # bare key => true (:447-449)
+    return out
+
+
+def _f(v):
+    return float(str(v).strip().lower().replace("d", "e"))
+
+
+def _b(v):
+    return str(v).strip().upper() in ("T", "TRUE", ".TRUE.", "1")
+
+
+def _ilist(v):
+    return [int(t) for t in str(v).replace(",", " ").split()]
+
+
+def soap_params(desc_str, calc_xml_version=None):
+    """soap_initialise argument handling, descriptors.f95:2502-2596.
+
+    ``calc_xml_version`` is the ``xml_version`` soap_calc sees in its args_str
+    (IPModel_GAP.f95:361); None = the descriptor-only default 1423143769 (:7800)."""
+    a = parse_args(desc_str)
+    p = {}
+    p["cutoff"] = _f(a["cutoff"])
+    p["cutoff_transition_width"] = _f(a.get("cutoff_transition_width", 0.5))
+    p["cutoff_dexp"] = int(a.get("cutoff_dexp", 0))
+    p["cutoff_scale"] = _f(a.get("cutoff_scale", 1.0))
+    p["cutoff_rate"] = _f(a.get("cutoff_rate", 1.0))
+    p["l_max"] = int(a["l_max"])
+    p["n_max"] = int(a["n_max"])
+    p["atom_sigma"] = _f(a["atom_gaussian_width"] if "atom_gaussian_width" in a else a["atom_sigma"])
+    p["central_weight"] = _f(a.get("central_weight", 1.0))
+    has_cras = "central_reference_all_species" in a
+    p["central_reference_all_species"] = _b(a.get("central_reference_all_species", "F"))
+    p["covariance_sigma0"] = _f(a.get("covariance_sigma0", 0.0))
+    p["normalise"] = _b(a.get("normalise", a.get("normalize", "T")))
+    p["basis_error_exponent"] = _f(a.get("basis_error_exponent", 10.0))
+    p["n_Z"] = int(a.get("n_Z", 1))
+    has_n_species = "n_species" in a
+    p["n_species"] = int(a.get("n_species", 1))
+    xml_version = int(a.get("xml_version", 1426512068))
+    if xml_version < 1426512068:
+        p["central_reference_all_species"] = True
+    if p["n_species"] == 1:
+        p["species_Z"] = [int(a.get("species_Z", "0").split()[0])] if a.get("species_Z", "").strip() else [0]
+    else:
+        p["species_Z"] = _ilist(a["species_Z"])
+    if not has_n_species and "species_Z" in a and a["species_Z"].strip():
+        raise ValueError("soap: species_Z given without n_species")
+    if not has_cras and p["n_species"] == 1:
+        p["central_reference_all_species"] = True
+    p["Z"] = _ilist(a.get("Z", "0")) if p["n_Z"] > 1 else [int(str(a.get("Z", "0")).split()[0])]
+    for key in ("average", "diagonal_radial", "Z_mix", "R_mix", "sym_mix"):
+        if _b(a.get(key, "F")):
+            raise NotImplementedError("soap option %s is outside the oracle's scope" % key)
+    if a.get("radial_basis", "EQUISPACED_GAUSS") not in ("", "EQUISPACED_GAUSS"):
+        raise NotImplementedError("radial_basis")
+    if int(a.get("nu_R", 2)) != 2 or int(a.get("nu_S", 2)) != 2 or not _b(a.get("coupling", "T")):
+        raise NotImplementedError("nu_R/nu_S/coupling")
+    cv = 1423143769 if calc_xml_version is None else calc_xml_version
+    p["do_two_l_plus_one"] = cv >= 1423143769
+    return p
+
+
+def new_soap(p):
+    Z = np.array(p["Z"], dtype=np.int32)
+    sZ = np.array(p["species_Z"], dtype=np.int32)
+    h = lib().orc_soap_new(p["cutoff"], p["cutoff_transition_width"], p["l_max"], p["n_max"], p["atom_sigma"],
+                           p["central_weight"], int(p["central_reference_all_species"]), p["covariance_sigma0"],
+                           int(p["normalise"]), len(Z), _ip(Z), len(sZ), _ip(sZ), int(p["do_two_l_plus_one"]),
+                           p["cutoff_dexp"], p["cutoff_scale"], p["cutoff_rate"], p["basis_error_exponent"])
+    if not h:
+        raise RuntimeError("orc_soap_new failed")
+    return h
+
+
+def soap_basis(p):
+    h = new_soap(p)
+    n = p["n_max"]
+    r, t, ch = np.zeros(n), np.zeros((n, n), order="F"), np.zeros((n, n), order="F")
+    lib().orc_soap_get_basis(h, _dp(r), _dp(t), _dp(ch))
+    lib().orc_soap_free(h)
+    return r, t, ch
+
+
+# ----------------------------------------------------------------------
+# geometry helpers
+# ----------------------------------------------------------------------
+def _geom(atoms):
+    pos = np.ascontiguousarray(atoms.get_positions(), dtype=np.float64)
+    Z = np.ascontiguousarray(atoms.get_atomic_numbers(), dtype=np.int32)
+    lat = np.ascontiguousarray(np.asarray(atoms.get_cell(), dtype=np.float64).reshape(9))
+    pbc = np.ascontiguousarray(np.asarray(atoms.get_pbc(), dtype=bool).astype(np.int32))
+    return pos, Z, lat, pbc
+
+
+class Connect:
+    def __init__(self, atoms, cutoff):
+        self.pos, self.Z, self.lat, self.pbc = _geom(atoms)
+        self.N = len(self.Z)
+        self.h = lib().orc_connect_new(self.N, _dp(self.pos), _dp(self.lat), _ip(self.pbc), float(cutoff))
+
+    def arrays(self):
+        tot = lib().orc_connect_total(self.h)
+        off = np.zeros(self.N + 1, dtype=np.int32)
+        j = np.zeros(max(tot, 1), dtype=np.int32)
+        s = np.zeros((max(tot, 1), 3), dtype=np.int32)
+        d = np.zeros(max(tot, 1))
+        lib().orc_connect_get(self.h, _ip(off), _ip(j), _ip(s), _dp(d))
+        return off, j[:tot], s[:tot], d[:tot]
+
+    def cells(self):
+        out = np.zeros(6, dtype=np.int32)
+        lib().orc_connect_cells(self.h, _ip(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_connect_free(self.h)
+            self.h = None
+
+
+def soap_descriptor(desc_str, atoms, grad=False, cutoff=None):
+    """quippy ``Descriptor(desc_str).calc(atoms, grad=...)`` analogue (quippy/descriptors.py:141-235):
+    the neighbour list is built with ``descriptor cutoff + 1`` unless ``cutoff`` is given."""
+    p = soap_params(desc_str)
+    hs = new_soap(p)
+    con = Connect(atoms, p["cutoff"] + 1.0 if cutoff is None else cutoff)
+    d = lib().orc_soap_dim(hs)
+    nrows = C.c_int(0)
+    nd = lib().orc_soap_calc(hs, con.h, con.N, _dp(con.pos), _ip(con.Z), _dp(con.lat), int(grad), C.byref(nrows),
+                             None, None, None, None, None, None, None)
+    rows = nrows.value
+    x = np.zeros((nd, d))
+    ci = np.zeros(nd, dtype=np.int32)
+    row_off = np.zeros(nd + 1, dtype=np.int32)
+    out = {}
+    if grad:
+        g = np.zeros((rows, 3, d))
+        ii = np.zeros(rows, dtype=np.int32)
+        gpos = np.zeros((rows, 3))
+        hg = np.zeros(rows, dtype=np.int32)
+        lib().orc_soap_calc(hs, con.h, con.N, _dp(con.pos), _ip(con.Z), _dp(con.lat), 1, C.byref(nrows), _dp(x), _ip(ci),
+                            _ip(row_off), _dp(g), _ip(ii), _dp(gpos), _ip(hg))
+        out.update(grad_data=g, ii=ii, pos=gpos, has_grad_data=hg.astype(bool))
+        out["grad_index_0based"] = np.stack([np.repeat(ci, np.diff(row_off)), ii], axis=1)
+    else:
+        lib().orc_soap_calc(hs, con.h, con.N, _dp(con.pos), _ip(con.Z), _dp(con.lat), 0, C.byref(nrows), _dp(x), _ip(ci),
+                            _ip(row_off), None, None, None, None)
+    out.update(data=x, ci=ci, row_off=row_off)
+    lib().orc_soap_free(hs)
+    return out
+
+
+# ----------------------------------------------------------------------
+# GAP XML (independent reading)
+# ----------------------------------------------------------------------
+def _floats(text):
+    return np.array([_f(t) for t in text.split()], dtype=np.float64) if text and text.strip() else np.zeros(0)
+
+
+def load_gap_xml(path=None, xml_string=None, label=None):
+    if xml_string is None:
+        with open(path) as fh:
+            xml_string = fh.read()
+    base = os.path.dirname(os.path.abspath(path)) if path else os.getcwd()
+    root = ET.fromstring(xml_string)
+    params = None
+    cands = [root] if root.tag == "GAP_params" else list(root.iter("GAP_params"))
+    for gp in cands:  # first exact label match, else the first stanza (IPModel_GAP.f95:629-653)
+        if label and gp.get("label") == label:
+            params = gp
+            break
+    if params is None:
+        if label and not any(True for _ in cands):
+            raise ValueError("no GAP_params")
+        params = cands[0] if (not label) else None
+    if params is None:
+        raise ValueError("GAP_params label %r not found" % label)
+    model = {"label": params.get("label", ""), "xml_version": int(params.get("gap_version", 0)), "e0": np.zeros(128),
+             "coordinates": []}
+    gd = params.find("GAP_data")
+    if gd is not None:
+        if gd.get("e0") is not None:
+            model["e0"][:] = _f(gd.get("e0"))
+        for e in gd.findall("e0"):
+            model["e0"][int(e.get("Z"))] = _f(e.get("value"))
+    gs = params.find("gpSparse")
+    if gs is None:
+        raise ValueError("no gpSparse")
+    if gs.get("fitted") is not None and not _b(gs.get("fitted")):
+        raise ValueError("GAP model has not been fitted")
+    n_coord = int(gs.get("n_coordinate"))
+    coords = {c.get("label"): c for c in gs.findall("gpCoordinates")}
+    for i in range(1, n_coord + 1):
+        c = coords[gs.get("label") + str(i)]
+        d, M = int(c.get("dimensions")), int(c.get("n_sparseX"))
+        co = {"d": d, "M": M, "delta": _f(c.get("signal_variance")), "f0": _f(c.get("signal_mean")),
+              "covariance_type": int(c.get("covariance_type")), "n_permutations": int(c.get("n_permutations")),
+              "descriptor": "".join(c.find("descriptor").itertext()).strip(), "zeta": None}
+        if c.get("zeta") is not None:
+            co["zeta"] = _f(c.get("zeta"))
+        th = c.find("theta")
+        co["theta"] = _floats(th.text) if th is not None else np.zeros(0)
+        if co["covariance_type"] == 2 and co["zeta"] is None:  # legacy: theta holds zeta (:4972-4977)
+            co["zeta"] = float(co["theta"][0])
+        alpha, cut = np.zeros(M), np.zeros(M)
+        X = np.zeros((d, M), order="F")
+        fn = c.get("sparseX_filename")
+        if fn is not None:
+            with open(os.path.join(base, fn)) as fh:
+                X[:] = np.array([_f(t) for t in fh.read().split()]).reshape((d, M), order="F")
+        for sx in c.findall("sparseX"):
+            k = int(sx.get("i")) - 1
+            alpha[k], cut[k] = _f(sx.get("alpha")), _f(sx.get("sparseCutoff"))
+            if fn is None:
+                if sx.get("sliced") is not None and _b(sx.get("sliced")):
+                    for sl in sx.findall("sparseX_slice"):
+                        X[int(sl.get("start")) - 1:int(sl.get("end")), k] = _floats(sl.text)
+                else:
+                    X[:, k] = _floats(sx.text)
+        co.update(sparseX=X, alpha=alpha, sparseCutoff=cut)
+        model["coordinates"].append(co)
+    return model
+
+
+class Model:
+    """Oracle GAP model: ``Potential('IP GAP', param_filename=...)`` + ``calc`` analogue."""
+
+    def __init__(self, path=None, xml_string=None, label=None, E_scale=1.0, model=None):
+        self.spec = model if model is not None else load_gap_xml(path, xml_string, label)
+        L = lib()
+        self.h = L.orc_model_new()
+        e0 = np.ascontiguousarray(self.spec["e0"], dtype=np.float64)
+        L.orc_model_set_e0(self.h, _dp(e0), len(e0))
+        L.orc_model_set_E_scale(self.h, float(E_scale))
+        v = self.spec["xml_version"]
+        for co in self.spec["coordinates"]:
+            desc = co["descriptor"] + " xml_version=%d" % v  # IPModel_GAP.f95:184
+            kind = split_fields(desc)[0]
+            X = np.asfortranarray(co["sparseX"], dtype=np.float64)
+            al = np.ascontiguousarray(co["alpha"])
+            cu = np.ascontiguousarray(co["sparseCutoff"])
+            if kind == "soap":
+                if co["covariance_type"] != 2:
+                    raise NotImplementedError("soap with covariance_type %d" % co["covariance_type"])
+                p = soap_params(desc, calc_xml_version=v)
+                hs = new_soap(p)
+                assert L.orc_soap_dim(hs) == co["d"], (L.orc_soap_dim(hs), co["d"])
+                L.orc_model_add_soap(self.h, hs, co["M"], _dp(X), _dp(al), _dp(cu), co["delta"], co["zeta"])
+            elif kind == "distance_2b":
+                if co["covariance_type"] != 1 or co["n_permutations"] != 1 or co["d"] != 1:
+                    raise NotImplementedError("distance_2b variant")
+                a = parse_args(desc)
+                if int(a.get("n_exponents", 1)) != 1 or _f(a.get("exponents", 1)) != 1.0 or int(a.get("tail_exponent", 0)) != 0:
+                    raise NotImplementedError("distance_2b exponents/tail")
+                L.orc_model_add_distance_2b(self.h, _f(a.get("cutoff", 0.0)), _f(a.get("cutoff_transition_width", 0.5)),
+                                            int(a.get("Z1", 0)), int(a.get("Z2", 0)), co["M"], _dp(X), _dp(al), _dp(cu),
+                                            co["delta"], co["f0"], float(co["theta"][0]))
+            else:
+                raise NotImplementedError("descriptor %s" % kind)
+
+    @property
+    def cutoff(self):
+        return lib().orc_model_cutoff(self.h)
+
+    def calc(self, atoms, energy=True, force=True, virial=True, local_energy=False, local_virial=False,
+             connect_cutoff=None, first=0, last=None, nthreads=0):
+        pos, Z, lat, pbc = _geom(atoms)
+        N = len(Z)
+        last = N if last is None else last
+        e = np.zeros(1)
+        f = np.zeros((N, 3)) if force else None
+        v = np.zeros((3, 3), order="F") if virial else None
+        le = np.zeros(N) if local_energy else None
+        lv = np.zeros((N, 9)) if local_virial else None
+        t = np.zeros(3)
+        rc = lib().orc_model_calc(self.h, N, _dp(pos), _ip(Z), _dp(lat), _ip(pbc),
+                                  float(connect_cutoff if connect_cutoff is not None else self.cutoff), first, last,
+                                  nthreads, _dp(e), _dp(le), _dp(f), _dp(v), _dp(lv), _dp(t))
+        if rc:
+            raise RuntimeError("orc_model_calc failed")
+        out = {"energy": float(e[0]), "timings": t}
+        if force:
+            out["force"] = f
+        if virial:
+            out["virial"] = np.array(v)
+        if local_energy:
+            out["local_energy"] = le
+        if local_virial:
+            out["local_virial"] = lv
+        return out
+
+    def predict(self, icoord, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n, d = x.shape
+        e, g = np.zeros(n), np.zeros((n, d))
+        lib().orc_model_predict(self.h, icoord, n, _dp(x), _dp(e), _dp(g))
+        return e, g
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_model_free(self.h)
+            self.h = None

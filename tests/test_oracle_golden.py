@@ -1,0 +1,95 @@
+"""Pin the CPU oracle (oracle/gap_oracle.c) against the reference's own known answers.
+
+Every expected number here is a fixture taken from /root/reference/tests by
+tools/make_golden.py (see that file for the provenance of each item)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from quip_b200.atoms import Atoms, read_xyz
+
+SI_SOAP = ("soap atom_sigma=0.5 central_weight=1.0 cutoff=4.0 cutoff_transition_width=1.0 l_max=8 n_max=8 "
+           "n_species=1 Z=14 species_Z={14}")
+
+
+def test_gap_xml_energy_forces(golden):
+    # tests/test_gappot.py:30-48 : E to 1e-5, forces to 1e-6 (we hold 1e-8: the xyz has 8 decimals)
+    at = read_xyz(os.path.join(golden, "gap_sample.xyz"), 0)
+    m = orc.Model(os.path.join(golden, "GAP.xml"))
+    assert m.cutoff == 4.0
+    r = m.calc(at, local_energy=True, local_virial=True)
+    assert abs(r["energy"] - at.info["energy"]) < 1e-8
+    assert np.abs(r["force"] - at.arrays["force"]).max() < 1e-8
+    assert abs(r["local_energy"].sum() - r["energy"]) < 1e-10
+    assert np.abs(r["local_virial"].sum(axis=0).reshape(3, 3, order="F") - r["virial"]).max() < 1e-10
+    assert np.abs(r["virial"] - r["virial"].T).max() < 1e-9
+    assert np.abs(r["force"].sum(axis=0)).max() < 1e-9
+
+
+def test_h2_cell_energies(golden):
+    # tests/test_potential_cell.py:30-54 (multi-image neighbour lists), tol 1e-6 there
+    h = json.load(open(os.path.join(golden, "h2_cell_energies.json")))
+    m = orc.Model(os.path.join(golden, "GAP.xml"))
+    for c, e in zip(h["cell_sizes"], h["ref_energies"]):
+        a = Atoms(h["numbers"], h["positions"], [c, c, c], True)
+        assert abs(m.calc(a)["energy"] - e) < 1e-8
+
+
+def test_si_soap_sparse_vectors(golden):
+    # tests/test_gapfit.py: sparseX rows are SOAP vectors of known atoms of Si.np1.xyz (tol 1e-8 there)
+    frames = read_xyz(os.path.join(golden, "Si.np1.xyz"))
+    z = np.load(os.path.join(golden, "si_two_descriptors.npz"))
+    X = np.concatenate([orc.soap_descriptor(SI_SOAP, a)["data"] for a in frames])
+    assert X.shape == (439, 325)
+    assert np.abs(X[z["index_soap"] - 1] - z["sparsex_soap"]).max() < 1e-14
+    assert np.abs(np.linalg.norm(X[:, :-1], axis=1) - 1).max() < 1e-14
+
+
+@pytest.mark.parametrize("case", ["112", "114", "116", "119"])
+def test_soap_reference_data(golden, case):
+    # tests/test_SOAP.py:50-77 (np.allclose there); non-periodic triclinic cells, up to 4 species
+    S = json.load(open(os.path.join(golden, "soap_reference_cases.json")))
+    c = S["cases"][case]
+    ds = [Atoms(d["numbers"], np.array(d["scaled_positions"]) @ np.array(d["cell"]), d["cell"], False)
+          for d in S["datasets"][c["dataset_name"]]]
+    outs = [orc.soap_descriptor(c["quippy_str"], a, grad=True) for a in ds]
+    X = np.concatenate([o["data"] for o in outs])[np.array(c["perm"])]
+    assert np.abs(X - np.array(c["X"])).max() < 1e-13
+    gp = np.array(c["grad_perm"])
+    assert np.array_equal(outs[0]["grad_index_0based"][gp], np.array(c["grad_index_0based"]))
+    assert np.abs(outs[0]["grad_data"][gp] - np.array(c["grad_data"])).max() < 1e-13
+
+
+def test_c2h_descriptor_gradients(golden):
+    # tests/test_descriptor.py:63-226 (tol 1e-7 there; stored with 9 significant digits)
+    c = json.load(open(os.path.join(golden, "c2h_descriptor.json")))
+    a = Atoms(c["numbers"], c["positions"], c["cell"], True)
+    o = orc.soap_descriptor(c["descriptor"], a, grad=True, cutoff=3.0)
+    assert list(o["data"].shape) == c["shapes"]["descriptor"]
+    assert list(o["grad_data"].shape) == c["shapes"]["grad"]
+    assert np.array_equal(o["grad_index_0based"], np.array(c["ref_grad_index_0based"]))
+    assert np.abs(o["grad_data"][:2] - np.array(c["ref_grad_array"])).max() < 2e-9
+
+
+def test_soap_gradient_finite_difference(golden):
+    # the reference's own self-consistency idea (Potential.f95:1374 test_gradient) at descriptor level
+    frames = read_xyz(os.path.join(golden, "Si.np1.xyz"))
+    a = frames[3]
+    o = orc.soap_descriptor(SI_SOAP, a, grad=True)
+    row = 1
+    ci, jj = o["grad_index_0based"][row]
+    # total derivative of x(ci) wrt atom jj sums all periodic-image rows of (ci, jj)
+    rows = [r for r in range(o["row_off"][ci], o["row_off"][ci + 1]) if o["ii"][r] == jj]
+    g = o["grad_data"][rows].sum(axis=0)
+    h = 1e-5
+    for k in range(3):
+        xp = []
+        for s in (+1, -1):
+            p = a.positions.copy()
+            p[jj, k] += s * h
+            xp.append(orc.soap_descriptor(SI_SOAP, Atoms(a.numbers, p, a.cell, a.pbc))["data"][ci])
+        fd = (xp[0] - xp[1]) / (2 * h)
+        assert np.abs(fd - g[k]).max() < 5e-9
