@@ -1,0 +1,111 @@
+/* gap_b200.h -- C ABI of libgapb200.so: the B200-native drop-in for QUIP's "IP GAP" evaluation path.
+ *
+ * Plain C types only (no torch, no C++): this is what a Fortran host binds through ISO_C_BINDING (see
+ * quip_b200/fortran/gap_b200_iface.f90 and INTEGRATION.md) and what quip_b200/potential.py binds with ctypes.
+ *
+ * Conventions (identical to the Fortran side, so arrays can be passed without copies):
+ *   pos      real(dp) pos(3,N)        -> const double[3*N], xyz of atom 0, xyz of atom 1, ...
+ *   Z        integer Z(N)             -> const int[N]
+ *   lattice  real(dp) lattice(3,3)    -> const double[9], column-major: columns are the cell vectors a, b, c
+ *   pbc      logical is_periodic(3)   -> const int[3] (0/1)
+ *   force    real(dp) f(3,N)          -> double[3*N]
+ *   virial   real(dp) virial(3,3)     -> double[9] column-major
+ *   local_e  real(dp) local_e(N)      -> double[N]
+ *   local_virial real(dp) (9,N)       -> double[9*N]
+ * Output pointers may be NULL = Fortran "optional argument absent": the quantity is not computed
+ * (force, virial and local_virial all absent => no gradients at all, IPModel_GAP.f95:416-424).
+ * Every function returns 0 (ERROR_NONE) on success; otherwise non-zero, and gap_last_error() describes the
+ * failure (the reference's RAISE_ERROR/system_abort conditions are reported this way; the library never exits).
+ * There is no CPU fallback: without a usable CUDA device initialise fails.
+ */
+#ifndef GAP_B200_H
+#define GAP_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gap_potential gap_potential;
+
+/* Potential_Filename_Initialise (src/Potentials/Potential.f95:438): args_str e.g. "IP GAP" or
+ * "IP GAP label=..." or "" (take init_args from the XML); sparseX side files are resolved relative to the
+ * XML's directory (:455-466).  device = CUDA ordinal. */
+int gap_potential_filename_initialise(gap_potential** pot, const char* args_str, const char* param_filename, int device);
+
+/* potential_initialise with param_str (Potential.f95:499) -> IPModel_GAP_Initialise_str
+ * (src/Potentials/IPModel_GAP.f95:149): param_str is the entire XML text; base_dir (may be NULL = ".")
+ * is where sparseX_filename side files are looked up. */
+int gap_potential_initialise(gap_potential** pot, const char* args_str, const char* param_str, const char* base_dir, int device);
+
+/* finalise (IPModel_GAP_Finalise, IPModel_GAP.f95:194) */
+void gap_potential_finalise(gap_potential* pot);
+
+/* cutoff(pot) (Potential.f95:1044 -> IP_cutoff, IP.f95:704-705) */
+double gap_potential_cutoff(const gap_potential* pot);
+
+/* Print (IPModel_GAP_Print, IPModel_GAP.f95:952): writes a description into buf (NUL terminated, truncated to n) */
+int gap_potential_print(const gap_potential* pot, char* buf, size_t n);
+
+/* Data-parallel partition = the reference's MPI atom mask (descriptor_atomic_MPI_setup, descriptors.f95:1036-1051),
+ * as contiguous blocks of central atoms: this handle evaluates only centres [rank*N/n_ranks, (rank+1)*N/n_ranks).
+ * Outputs are then PARTIAL sums; the host reduces them (the reference's sum_in_place calls, IPModel_GAP.f95:538-556). */
+int gap_potential_set_partition(gap_potential* pot, int rank, int n_ranks);
+
+/* calc(pot, at, energy, force, virial, local_energy, local_virial, args_str) (Potential.f95:803 ->
+ * IPModel_GAP_Calc, IPModel_GAP.f95:233), including the neighbour-list build the reference does in
+ * potential_calc (:844-859 -> calc_connect, src/libAtoms/Connection.f95:1035).  All pointers are HOST pointers. */
+int gap_potential_calc(gap_potential* pot, int N, const double* pos, const int* Z, const double* lattice, const int* pbc,
+                       const char* args_str, double* energy, double* local_e, double* force, double* virial,
+                       double* local_virial);
+
+/* Same, GPU-resident: d_pos/d_Z are DEVICE pointers, results stay on the device.
+ *   d_packed  : device double[10 + 3*N] = [ E | virial(9) | F(3,N) ]  (the buffer the host all-reduces when the
+ *               partition is active: one collective instead of the reference's five); never NULL
+ *   d_local_e : device double[N] or NULL ; d_local_virial : device double[9*N] or NULL
+ *   want_grad : 0 = energy only
+ *   stream    : cudaStream_t (as void*) the work is enqueued on; NULL = the handle's own stream.
+ * Returns after enqueueing except for two small device->host reads (neighbour count, centre count). */
+int gap_potential_calc_device(gap_potential* pot, int N, const double* d_pos, const int* d_Z, const double* lattice,
+                              const int* pbc, const char* args_str, int want_grad, double* d_packed, double* d_local_e,
+                              double* d_local_virial, void* stream);
+
+/* F77-style one-shot entry point, same argument list as quip_wrapper_simple_
+ * (src/Potentials/quip_unified_wrapper.f95:311-332) plus the XML file name; pbc = T T T. */
+int gap_b200_wrapper_simple(const char* param_filename, const int* N, const double* lattice, const int* Z, const double* pos,
+                            double* energy, double* force, double* virial);
+
+/* ---- stage-level entry points (descriptors_wrapper.f95 analogue; used by the parity tests) ---- */
+
+/* calc_connect (Connection.f95:1035) with an explicit cutoff; returns the number of list entries in *n_entries.
+ * The list is the FULL list (both i->j and j->i), atom indices 0-based. */
+int gap_calc_connect(gap_potential* pot, int N, const double* pos, const double* lattice, const int* pbc, double cutoff,
+                     int* n_entries);
+/* copy out the last list: offsets[N+1], neighbour j[n], shift[3*n], distance[n] (host pointers) */
+int gap_get_connect(gap_potential* pot, int* offsets, int* j, int* shift, double* distance);
+
+/* descriptor_calc for SOAP coordinate i_coord (0-based): two-call protocol.  With x == NULL only *n_desc and *d are
+ * returned; otherwise x[n_desc*d] (row per centre) and ci[n_desc] (0-based centre atom) are filled. */
+int gap_descriptor_calc(gap_potential* pot, int i_coord, int N, const double* pos, const int* Z, const double* lattice,
+                        const int* pbc, int* n_desc, int* d, double* x, int* ci);
+
+/* gp_predict for coordinate i_coord on n descriptor vectors x[n*d] (gpCoordinates_Predict, gp_predict.f95:3627):
+ * e[n], grad[n*d] (grad may be NULL). dot_product coordinates only. */
+int gap_gp_predict(gap_potential* pot, int i_coord, int n, const double* x, double* e, double* grad);
+
+int gap_potential_n_coordinate(const gap_potential* pot);
+/* number of CUDA kernels this handle has launched since initialise */
+long gap_potential_launch_count(const gap_potential* pot);
+/* device milliseconds of the last calc, by stage: [0] connect [1] soap forward [2] covariance [3] soap adjoint
+ * [4] distance_2b [5] whole calc (CUDA events on the handle's stream; valid after gap_potential_calc) */
+int gap_potential_last_timings(const gap_potential* pot, double* ms6);
+
+/* Host-only: parse a model exactly as initialise would (XML + descriptor strings + SOAP radial-basis set-up) and
+ * write a text description with all derived numbers (%.17g) into buf.  Needs no GPU; used to check the loader. */
+int gap_model_describe(const char* args_str, const char* param_str, const char* base_dir, char* buf, size_t n);
+
+const char* gap_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

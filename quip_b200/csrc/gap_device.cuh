@@ -1,0 +1,143 @@
+// gap_device.cuh -- device-side data layout and kernel launchers of the B200 GAP path.
+//
+// HBM layout (all FP64 / int32):
+//   pos[N][3], Z[N]                      inputs (xyz per atom = Fortran pos(3,N))
+//   nbr_off[N+1], nbr_j[nnz], nbr_s[nnz] full neighbour list in CSR; shift packed 3 x int8
+//   x[Nc_pad][d_pad]                     normalised SOAP vectors, one row per centre
+//   xlm[Nc][nlm*K1]                      real-harmonic density expansion kept for the adjoint
+//   acoef[Nc_pad][M_pad]                 alpha_s * dk_s/dc  (GEMM-1 epilogue output)
+//   gvec[Nc_pad][dn_pad]                 dE_i/dx (GEMM-2 output = the reference's gradPredict)
+//   out_force[N][3], out_le[N], vir_part[slots][9]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gapb200 {
+
+constexpr int SOAP_NMAX_CAP = 16;   // n_max
+constexpr int SOAP_LMAX_CAP = 12;   // l_max
+constexpr int SOAP_SPECIES_CAP = 8; // n_species, n_Z
+
+struct SoapDev {
+  double cutoff, ctw, alpha, central_weight, sigma0, chol00;
+  double cutoff_scale, cutoff_rate, norm_radial_decay;
+  int cutoff_dexp;
+  int l_max, n_max, n_species, n_Z, K1, d, d_pad, nlm;
+  int normalise, cras, two_lp1;
+  int species_Z[SOAP_SPECIES_CAP];
+  int centre_Z[SOAP_SPECIES_CAP];
+  double r_basis[SOAP_NMAX_CAP];
+  double T[SOAP_NMAX_CAP * SOAP_NMAX_CAP];                            // T[a + n_max*a'] (column-major)
+  double ynorm[(SOAP_LMAX_CAP + 1) * (SOAP_LMAX_CAP + 2) / 2];        // N_lm * (m>0 ? sqrt2 : 1), index l(l+1)/2+m
+  double tlpo[SOAP_LMAX_CAP + 1];                                     // 1/sqrt(2l+1) or 1
+};
+
+struct CellGrid {
+  double lat[9];   // column-major lattice(k,m) = lat[k+3m]
+  double g[9];     // inverse: frac_r = sum_c g[r+3c] * pos_c
+  double toff[3];  // non-periodic directions: minimum fractional coordinate
+  double tscale[3];// non-periodic directions: 1/extent
+  int n[3], R[3], pbc[3];
+  double cutoff;
+};
+
+struct Lattice9 {
+  double v[9];
+};
+
+__host__ __device__ inline int pack_shift(int a, int b, int c) { return (a & 0xff) | ((b & 0xff) << 8) | ((c & 0xff) << 16); }
+__host__ __device__ inline void unpack_shift(int p, int& a, int& b, int& c) {
+  a = (int)(int8_t)(p & 0xff);
+  b = (int)(int8_t)((p >> 8) & 0xff);
+  c = (int)(int8_t)((p >> 16) & 0xff);
+}
+
+// Displacement pos_j - pos_i + lattice*shift with the reference's operation order and NO fused
+// multiply-add (Connection.f95:486-489, 2120-2125), so distances are bit-identical to the oracle.
+__device__ __forceinline__ void image_diff(const double* __restrict__ pi, const double* __restrict__ pj, const double* lat, int s0,
+                                           int s1, int s2, double* dd) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double t = __dsub_rn(pj[k], pi[k]);
+    t = __dadd_rn(t, __dmul_rn(lat[k + 0], (double)s0));
+    t = __dadd_rn(t, __dmul_rn(lat[k + 3], (double)s1));
+    t = __dadd_rn(t, __dmul_rn(lat[k + 6], (double)s2));
+    dd[k] = t;
+  }
+}
+__device__ __forceinline__ double norm_nofma(const double* dd) {
+  return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dd[0], dd[0]), __dmul_rn(dd[1], dd[1])), __dmul_rn(dd[2], dd[2])));
+}
+
+// ---- neighbour.cu ------------------------------------------------------------------------
+struct NeighbourWork {  // device scratch owned by the potential handle; sized for N atoms / ncell cells
+  int* cell_of = nullptr;      // [N]
+  int* mshift = nullptr;       // [N] packed map_shift
+  int* sort_keys = nullptr;    // [N]
+  int* sort_idx = nullptr;     // [N] atom ids sorted by cell (stable)
+  int* iota = nullptr;         // [N]
+  int* keys_tmp = nullptr;     // [N]
+  int* cell_count = nullptr;   // [ncell+1]
+  int* cell_start = nullptr;   // [ncell+1]
+  double* spos = nullptr;      // [N][3] positions in sorted order
+  int* smshift = nullptr;      // [N]
+  int* nn = nullptr;           // [N+1] neighbour counts (original atom order)
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  double* minmax = nullptr;    // [6]
+};
+size_t neighbour_cub_bytes(int N, int ncell);
+void launch_frac_minmax(const double* pos, int N, const double* g9_dev_unused, const CellGrid& grid, double* minmax6, cudaStream_t st, int* launches);
+void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell, NeighbourWork& w, cudaStream_t st, int* launches);
+void launch_neigh_count(const double* pos, int N, const CellGrid& grid, NeighbourWork& w, int* nbr_off, cudaStream_t st, int* launches);
+void launch_neigh_fill(const double* pos, int N, const CellGrid& grid, NeighbourWork& w, const int* nbr_off, int* nbr_j, int* nbr_s,
+                       double* nbr_d, cudaStream_t st, int* launches);
+
+// ---- soap.cu -------------------------------------------------------------------------------
+void launch_select_centres(const int* Z, int first, int last, const SoapDev* sp, int* flags, cudaStream_t st, int* launches);
+void launch_compact(const int* flags_scan, const int* flags, int first, int n, int* centres, cudaStream_t st, int* launches);
+size_t soap_forward_smem(const SoapDev& h);
+size_t soap_adjoint_smem(const SoapDev& h);
+void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres, int n_centres, const int* nbr_off, const int* nbr_j,
+                         const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, double* x, double* xlm, double* pnorm,
+                         cudaStream_t st, int* launches);
+void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, int n_centres, const int* nbr_off, const int* nbr_j,
+                         const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
+                         const double* pnorm, const double* gvec, int ldg, double e_scale, double* force, double* vir_part,
+                         double* local_virial, cudaStream_t st, int* launches);
+
+// ---- covariance.cu -------------------------------------------------------------------------
+struct CovParams {
+  double delta2;   // delta^2
+  double zeta;
+  int zeta_int;    // >=0: integer fast path (fast_pow_1d), -1: general pow
+};
+constexpr int COV_BM = 128, COV_BN = 128, COV_BK = 16;
+// GEMM-1 + epilogue: c = X S^T ; k = delta^2 c^zeta cutoff_s ; acoef = alpha_s delta^2 zeta c^(zeta-1) cutoff_s ;
+// epart[row][n_tile] = sum over the tile's columns of alpha_s k
+void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int M, int M_pad, int K_pad, const double* alpha,
+                      const double* cutoff, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n, cudaStream_t st,
+                      int* launches);
+// GEMM-2: gvec = acoef S   (S given transposed: st_rows[q][s])
+void launch_cov_gemm2(const double* acoef, int lda, const double* st_rows, int ldst, int n_rows_pad, int dn_pad, int K_pad, double* gvec,
+                      int ldg, cudaStream_t st, int* launches);
+void launch_energy_rows(const double* epart, int n_tiles_n, const int* centres, int n_centres, double e_scale, double* local_e,
+                        cudaStream_t st, int* launches);
+
+// ---- pair2b.cu -----------------------------------------------------------------------------
+struct Pair2bDev {
+  double cutoff, ctw, delta2, f02, inv_theta;
+  int Z1, Z2, M;
+  const double* sparseX;  // [M]
+  const double* alpha;    // [M]
+  const double* scut;     // [M]
+};
+void launch_pair2b(Pair2bDev p, int first, int last, const int* nbr_off, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z,
+                   Lattice9 lat, double e_scale, int do_grad, double* local_e, double* force, double* vir_part, double* local_virial,
+                   cudaStream_t st, int* launches, int* n_blocks_out);
+
+// ---- finalize (potential.cu) ----------------------------------------------------------------
+void launch_finalize(const int* Z, int N, int first, int last, const double* e0_dev, double e_scale, double* local_e, const double* vir_part,
+                     int n_vir_slots, double* packed_out /* [E, virial(9)] */, cudaStream_t st, int* launches);
+
+}  // namespace gapb200

@@ -1,0 +1,205 @@
+// neighbour.cu -- device neighbour list (replaces the serial connection_calc_connect,
+// src/libAtoms/Connection.f95:1035-1310, and the accessor connection_neighbour :2011-2138).
+//
+// Design (B200-first, not the reference's linked lists): atoms are binned into a cell grid with
+// cell width >= cutoff, sorted by cell with a stable radix sort (order inside a cell = ascending atom
+// index, so everything downstream is deterministic), and one thread per atom -- in sorted order, so
+// that the threads of a warp walk the same candidate cells and their loads coalesce/broadcast --
+// scans the (2R+1)^3 surrounding cells twice (count, exclusive scan, fill) into a CSR list holding
+// the FULL list (both directions; the reference stores a half list plus back references).
+//
+// Bit-exactness: the accept test d < cutoff uses the reference's operation order without FMA
+// (image_diff/norm_nofma in gap_device.cuh), on the ORIGINAL positions and the total integer shift
+// (cell image - map_shift(i) + map_shift(j), Connection.f95:1275), so the set of (i, j, shift, d)
+// equals the reference's whatever the binning details are.
+#include <cub/cub.cuh>
+
+#include "gap_device.cuh"
+
+namespace gapb200 {
+
+namespace {
+
+__device__ __forceinline__ void frac_coords(const double* g, const double* p, double* t) {
+#pragma unroll
+  for (int r = 0; r < 3; r++) t[r] = g[r] * p[0] + g[r + 3] * p[1] + g[r + 6] * p[2];
+}
+
+__global__ void k_frac_minmax(const double* __restrict__ pos, int N, CellGrid grid, double* __restrict__ part /* [gridDim][6] */) {
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    double t[3];
+    frac_coords(grid.g, pos + 3 * (size_t)i, t);
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      mn[r] = fmin(mn[r], t[r]);
+      mx[r] = fmax(mx[r], t[r]);
+    }
+  }
+  typedef cub::BlockReduce<double, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  for (int r = 0; r < 3; r++) {
+    double a = BR(tmp).Reduce(mn[r], cub::Min());
+    __syncthreads();
+    double b = BR(tmp).Reduce(mx[r], cub::Max());
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      part[6 * blockIdx.x + r] = a;
+      part[6 * blockIdx.x + 3 + r] = b;
+    }
+  }
+}
+__global__ void k_minmax_final(const double* __restrict__ part, int nb, double* __restrict__ out6) {
+  int r = threadIdx.x;
+  if (r >= 6) return;
+  double v = part[r];
+  for (int b = 1; b < nb; b++) v = r < 3 ? fmin(v, part[6 * b + r]) : fmax(v, part[6 * b + r]);
+  out6[r] = v;
+}
+
+__global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int* __restrict__ cell_of, int* __restrict__ mshift,
+                      int* __restrict__ cell_count, int* __restrict__ iota) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double t[3];
+  frac_coords(grid.g, pos + 3 * (size_t)i, t);
+  int c[3], ms[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    double u;
+    if (grid.pbc[r]) {
+      ms[r] = -(int)floor(t[r] + 0.5);  // map_shift, Connection.f95:1574
+      u = t[r] + (double)ms[r] + 0.5;
+    } else {
+      ms[r] = 0;
+      u = (t[r] - grid.toff[r]) * grid.tscale[r];
+    }
+    int ci = (int)floor((double)grid.n[r] * u);
+    c[r] = ci < 0 ? 0 : (ci >= grid.n[r] ? grid.n[r] - 1 : ci);
+  }
+  int cell = (c[2] * grid.n[1] + c[1]) * grid.n[0] + c[0];
+  cell_of[i] = cell;
+  mshift[i] = pack_shift(ms[0], ms[1], ms[2]);
+  iota[i] = i;
+  atomicAdd(&cell_count[cell], 1);
+}
+
+__global__ void k_gather_sorted(const double* __restrict__ pos, const int* __restrict__ mshift, const int* __restrict__ sort_idx, int N,
+                                double* __restrict__ spos, int* __restrict__ smshift) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  int i = sort_idx[p];
+  spos[3 * (size_t)p + 0] = pos[3 * (size_t)i + 0];
+  spos[3 * (size_t)p + 1] = pos[3 * (size_t)i + 1];
+  spos[3 * (size_t)p + 2] = pos[3 * (size_t)i + 2];
+  smshift[p] = mshift[i];
+}
+
+__device__ __forceinline__ int floor_div(int a, int n) { return (a >= 0) ? a / n : -((-a + n - 1) / n); }
+
+template <bool FILL>
+__global__ void k_neigh(int N, CellGrid grid, const int* __restrict__ sort_idx, const int* __restrict__ sort_keys,
+                        const double* __restrict__ spos, const int* __restrict__ smshift, const int* __restrict__ cell_start,
+                        int* __restrict__ nn, const int* __restrict__ nbr_off, int* __restrict__ nbr_j, int* __restrict__ nbr_s,
+                        double* __restrict__ nbr_d) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int i = sort_idx[p];
+  const int cell = sort_keys[p];
+  int c0 = cell % grid.n[0], c1 = (cell / grid.n[0]) % grid.n[1], c2 = cell / (grid.n[0] * grid.n[1]);
+  double pi[3] = {spos[3 * (size_t)p], spos[3 * (size_t)p + 1], spos[3 * (size_t)p + 2]};
+  int mi0, mi1, mi2;
+  unpack_shift(smshift[p], mi0, mi1, mi2);
+  int count = 0;
+  int w = FILL ? nbr_off[i] : 0;
+  const double cutoff = grid.cutoff;
+  for (int o2 = -grid.R[2]; o2 <= grid.R[2]; o2++) {
+    int z = c2 + o2, s2 = 0;
+    if (grid.pbc[2]) { s2 = floor_div(z, grid.n[2]); z -= s2 * grid.n[2]; } else if (z < 0 || z >= grid.n[2]) continue;
+    for (int o1 = -grid.R[1]; o1 <= grid.R[1]; o1++) {
+      int y = c1 + o1, s1 = 0;
+      if (grid.pbc[1]) { s1 = floor_div(y, grid.n[1]); y -= s1 * grid.n[1]; } else if (y < 0 || y >= grid.n[1]) continue;
+      for (int o0 = -grid.R[0]; o0 <= grid.R[0]; o0++) {
+        int x = c0 + o0, s0 = 0;
+        if (grid.pbc[0]) { s0 = floor_div(x, grid.n[0]); x -= s0 * grid.n[0]; } else if (x < 0 || x >= grid.n[0]) continue;
+        int nc = (z * grid.n[1] + y) * grid.n[0] + x;
+        int qb = cell_start[nc], qe = cell_start[nc + 1];
+        for (int q = qb; q < qe; q++) {
+          int mj0, mj1, mj2;
+          unpack_shift(smshift[q], mj0, mj1, mj2);
+          int t0 = s0 - mi0 + mj0, t1 = s1 - mi1 + mj1, t2 = s2 - mi2 + mj2;
+          if (q == p && t0 == 0 && t1 == 0 && t2 == 0) continue;  // self, zero shift (:1266-1272)
+          double dd[3];
+          image_diff(pi, spos + 3 * (size_t)q, grid.lat, t0, t1, t2, dd);
+          double d = norm_nofma(dd);
+          if (d < cutoff) {  // strict, Connection.f95:517
+            if (FILL) {
+              nbr_j[w] = sort_idx[q];
+              nbr_s[w] = pack_shift(t0, t1, t2);
+              if (nbr_d) nbr_d[w] = d;
+              w++;
+            }
+            count++;
+          }
+        }
+      }
+    }
+  }
+  if (!FILL) nn[i] = count;
+}
+
+}  // namespace
+
+size_t neighbour_cub_bytes(int N, int ncell) {
+  size_t a = 0, b = 0, c = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, N);
+  cub::DeviceScan::ExclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, ncell + 1);
+  cub::DeviceScan::ExclusiveSum(nullptr, c, (int*)nullptr, (int*)nullptr, N + 1);
+  size_t m = a > b ? a : b;
+  return (m > c ? m : c) + 256;
+}
+
+void launch_frac_minmax(const double* pos, int N, const double*, const CellGrid& grid, double* minmax6, cudaStream_t st, int* launches) {
+  // scratch for block partials is carved from the tail of minmax6 (allocated as 6 + 6*64 doubles)
+  int nb = (N + 255) / 256;
+  if (nb > 64) nb = 64;
+  if (nb < 1) nb = 1;
+  k_frac_minmax<<<nb, 256, 0, st>>>(pos, N, grid, minmax6 + 6);
+  k_minmax_final<<<1, 32, 0, st>>>(minmax6 + 6, nb, minmax6);
+  *launches += 2;
+}
+
+void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell, NeighbourWork& w, cudaStream_t st, int* launches) {
+  cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (ncell + 1), st);
+  int nb = (N + 255) / 256;
+  k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.cell_count, w.iota);
+  size_t bytes = w.cub_bytes;
+  cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.cell_count, w.cell_start, ncell + 1, st);
+  int bits = 1;
+  while ((1 << bits) < ncell && bits < 31) bits++;
+  bytes = w.cub_bytes;
+  cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.cell_of, w.sort_keys, w.iota, w.sort_idx, N, 0, bits, st);
+  k_gather_sorted<<<nb, 256, 0, st>>>(pos, w.mshift, w.sort_idx, N, w.spos, w.smshift);
+  *launches += 4;
+}
+
+void launch_neigh_count(const double* pos, int N, const CellGrid& grid, NeighbourWork& w, int* nbr_off, cudaStream_t st, int* launches) {
+  (void)pos;
+  int nb = (N + 127) / 128;
+  k_neigh<false><<<nb, 128, 0, st>>>(N, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nullptr, nullptr, nullptr,
+                                     nullptr);
+  cudaMemsetAsync(w.nn + N, 0, sizeof(int), st);
+  size_t bytes = w.cub_bytes;
+  cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.nn, nbr_off, N + 1, st);
+  *launches += 2;
+}
+
+void launch_neigh_fill(const double* pos, int N, const CellGrid& grid, NeighbourWork& w, const int* nbr_off, int* nbr_j, int* nbr_s,
+                       double* nbr_d, cudaStream_t st, int* launches) {
+  (void)pos;
+  int nb = (N + 127) / 128;
+  k_neigh<true><<<nb, 128, 0, st>>>(N, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nbr_off, nbr_j, nbr_s, nbr_d);
+  *launches += 1;
+}
+
+}  // namespace gapb200

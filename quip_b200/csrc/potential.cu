@@ -1,0 +1,889 @@
+// potential.cu -- the gap_potential handle: device-resident model, workspaces, the calc pipeline and the C ABI
+// declared in include/gap_b200.h.
+//
+// Orchestration replaced: potential_calc's automatic calc_connect (src/Potentials/Potential.f95:844-859) and
+// IPModel_GAP_Calc (src/Potentials/IPModel_GAP.f95:233-605): loop over coordinates -> descriptor -> gp_predict ->
+// scatter -> totals -> e0 -> E_scale.  Everything between the H2D copy of (pos, Z) and the D2H copy of the results
+// runs on one CUDA stream; the host only reads back two integers per call (neighbour-entry count, centre count).
+#include <cub/cub.cuh>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <fstream>
+#include <functional>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/gap_b200.h"
+#include "gap_device.cuh"
+#include "gap_model.h"
+
+using namespace gapb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define CUDA_OK(expr)                                                                                               \
+  do {                                                                                                              \
+    cudaError_t _e = (expr);                                                                                        \
+    if (_e != cudaSuccess)                                                                                          \
+      throw GapError(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T>
+  T* as() const { return (T*)p; }
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cap = 0;
+      throw GapError(std::string("cudaMalloc of ") + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct CoordDev {
+  int kind = 0;
+  // soap
+  SoapDev h;
+  SoapDev* d_sp = nullptr;
+  double *sp_rows = nullptr, *st_rows = nullptr, *alpha = nullptr, *scut = nullptr;
+  int M = 0, M_pad = 0, d_pad = 0, dn_pad = 0;
+  CovParams cp;
+  // distance_2b
+  Pair2bDev p2;
+  double *x2 = nullptr, *a2 = nullptr, *c2 = nullptr;
+};
+
+}  // namespace
+
+struct gap_potential {
+  GapModel model;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<CoordDev> cd;
+  double* d_e0 = nullptr;
+  int rank = 0, n_ranks = 1;
+  long launches = 0;
+  double last_ms[6] = {0, 0, 0, 0, 0, 0};
+
+  // neighbour list state
+  NeighbourWork nw;
+  DevBuf b_cell_of, b_mshift, b_keys, b_idx, b_iota, b_ccount, b_cstart, b_spos, b_smshift, b_nn, b_cub, b_minmax;
+  DevBuf b_off, b_j, b_s, b_d;
+  int conn_N = 0, conn_nnz = 0;
+  // inputs / outputs owned for the host-pointer API
+  DevBuf b_pos, b_Z, b_packed, b_le, b_lv;
+  // per-coordinate workspaces
+  DevBuf b_flags, b_scan, b_centres, b_x, b_xlm, b_pnorm, b_acoef, b_gvec, b_epart, b_vir, b_fin;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_stage;
+  size_t ev_used = 0;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// finalize kernels: local_e += e0 ; E = sum local_e ; virial = sum vir_part  (IPModel_GAP.f95:523-532, 576-596)
+// ---------------------------------------------------------------------------------------------------
+constexpr int FIN_BLOCKS = 128, FIN_THREADS = 256;
+
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize_partial(const int* __restrict__ Z, int N, int first, int last,
+                                                                  const double* __restrict__ e0, double e_scale, double* __restrict__ local_e,
+                                                                  const double* __restrict__ vir_part, int n_slots,
+                                                                  double* __restrict__ part /* [FIN_BLOCKS][10] */) {
+  typedef cub::BlockReduce<double, FIN_THREADS> BR;
+  __shared__ typename BR::TempStorage tmp;
+  double v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * FIN_THREADS + threadIdx.x; i < N; i += FIN_BLOCKS * FIN_THREADS) {
+    double le = local_e[i];
+    if (i >= first && i < last) {
+      int z = Z[i];
+      le += e_scale * ((z >= 0 && z < 128) ? e0[z] : 0.0);
+      local_e[i] = le;
+    }
+    v[0] += le;
+  }
+  for (int s = blockIdx.x * FIN_THREADS + threadIdx.x; s < n_slots; s += FIN_BLOCKS * FIN_THREADS)
+#pragma unroll
+    for (int k = 0; k < 9; k++) v[1 + k] += vir_part[9 * (size_t)s + k];
+  for (int k = 0; k < 10; k++) {
+    double t = BR(tmp).Sum(v[k]);
+    __syncthreads();
+    if (threadIdx.x == 0) part[10 * blockIdx.x + k] = t;
+  }
+}
+__global__ void k_finalize_final(const double* __restrict__ part, double* __restrict__ packed) {
+  int k = threadIdx.x;
+  if (k >= 10) return;
+  double t = 0.0;
+  for (int b = 0; b < FIN_BLOCKS; b++) t += part[10 * b + k];
+  packed[k] = t;
+}
+__global__ void k_iota(int* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+void mark(gap_potential* P, cudaStream_t st, int stage) {
+  if (P->ev_used == P->ev.size()) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreate(&e));
+    P->ev.push_back(e);
+    P->ev_stage.push_back(0);
+  }
+  P->ev_stage[P->ev_used] = stage;
+  CUDA_OK(cudaEventRecord(P->ev[P->ev_used], st));
+  P->ev_used++;
+}
+void collect_timings(gap_potential* P) {
+  for (double& v : P->last_ms) v = 0.0;
+  if (P->ev_used < 2) return;
+  for (size_t k = 1; k < P->ev_used; k++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, P->ev[k - 1], P->ev[k]) == cudaSuccess) {
+      int st = P->ev_stage[k];
+      if (st >= 0 && st < 5) P->last_ms[st] += ms;
+    }
+  }
+  float tot = 0.f;
+  if (cudaEventElapsedTime(&tot, P->ev[0], P->ev[P->ev_used - 1]) == cudaSuccess) P->last_ms[5] = tot;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// geometry on the host: inverse lattice, cell grid
+// ---------------------------------------------------------------------------------------------------
+inline double det3(const double* a) {
+  return a[0] * (a[4] * a[8] - a[7] * a[5]) - a[3] * (a[1] * a[8] - a[7] * a[2]) + a[6] * (a[1] * a[5] - a[4] * a[2]);
+}
+void inv3(const double* a, double* g) {  // column-major both
+  double det = det3(a);
+  auto A = [&](int r, int c) { return a[r + 3 * c]; };
+  g[0 + 3 * 0] = (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1)) / det;
+  g[0 + 3 * 1] = (A(0, 2) * A(2, 1) - A(0, 1) * A(2, 2)) / det;
+  g[0 + 3 * 2] = (A(0, 1) * A(1, 2) - A(0, 2) * A(1, 1)) / det;
+  g[1 + 3 * 0] = (A(1, 2) * A(2, 0) - A(1, 0) * A(2, 2)) / det;
+  g[1 + 3 * 1] = (A(0, 0) * A(2, 2) - A(0, 2) * A(2, 0)) / det;
+  g[1 + 3 * 2] = (A(0, 2) * A(1, 0) - A(0, 0) * A(1, 2)) / det;
+  g[2 + 3 * 0] = (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0)) / det;
+  g[2 + 3 * 1] = (A(0, 1) * A(2, 0) - A(0, 0) * A(2, 1)) / det;
+  g[2 + 3 * 2] = (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0)) / det;
+}
+
+void build_connect(gap_potential* P, int N, const double* d_pos, const double* lattice, const int* pbc, double cutoff, bool want_dist,
+                   cudaStream_t st) {
+  if (N < 0) throw GapError("calc_connect: negative number of atoms");
+  if (cutoff < 0.0) throw GapError("calc_connect: Negative cutoff radius " + std::to_string(cutoff));  // Connection.f95:1069
+  P->conn_N = N;
+  P->conn_nnz = 0;
+  P->b_off.ensure(sizeof(int) * (N + 2));
+  if (N == 0 || cutoff == 0.0) {  // cutoff == 0: "don't compute neighbours" (:1079)
+    CUDA_OK(cudaMemsetAsync(P->b_off.p, 0, sizeof(int) * (N + 2), st));
+    return;
+  }
+  CellGrid grid;
+  memset(&grid, 0, sizeof(grid));
+  grid.cutoff = cutoff;
+  double lat[9];
+  for (int k = 0; k < 9; k++) {
+    lat[k] = lattice[k];
+    if (!std::isfinite(lat[k])) throw GapError("calc_connect: lattice is not finite");
+  }
+  for (int k = 0; k < 3; k++) grid.pbc[k] = pbc[k] ? 1 : 0;
+  // non-periodic directions with a missing (zero) cell vector get a unit vector that completes the basis; it never
+  // multiplies a non-zero shift
+  for (int k = 0; k < 3; k++) {
+    double nrm = std::sqrt(lat[3 * k] * lat[3 * k] + lat[3 * k + 1] * lat[3 * k + 1] + lat[3 * k + 2] * lat[3 * k + 2]);
+    if (nrm < 1e-12) {
+      if (grid.pbc[k]) throw GapError("calc_connect: periodic direction with zero-length lattice vector");
+      lat[3 * k] = lat[3 * k + 1] = lat[3 * k + 2] = 0.0;
+    }
+  }
+  auto col_norm = [&](int k) { return std::sqrt(lat[3 * k] * lat[3 * k] + lat[3 * k + 1] * lat[3 * k + 1] + lat[3 * k + 2] * lat[3 * k + 2]); };
+  for (int k = 0; k < 3; k++) {
+    if (col_norm(k) >= 1e-12) continue;
+    double best = -1.0;
+    int bi = 0;
+    for (int c = 0; c < 3; c++) {
+      double trial[9];
+      memcpy(trial, lat, sizeof(trial));
+      trial[3 * k + c] = 1.0;
+      // temporarily fill the other empty columns so that det is meaningful
+      for (int k2 = 0; k2 < 3; k2++)
+        if (k2 != k && std::sqrt(trial[3 * k2] * trial[3 * k2] + trial[3 * k2 + 1] * trial[3 * k2 + 1] + trial[3 * k2 + 2] * trial[3 * k2 + 2]) < 1e-12)
+          trial[3 * k2 + ((c + 1 + (k2 > k ? 1 : 0)) % 3)] = 1.0;
+      double dv = std::fabs(det3(trial));
+      if (dv > best) { best = dv; bi = c; }
+    }
+    lat[3 * k + bi] = 1.0;
+  }
+  double det = det3(lat);
+  double scale = col_norm(0) * col_norm(1) * col_norm(2);
+  if (!(std::fabs(det) > 1e-10 * scale)) throw GapError("calc_connect: singular lattice");
+  memcpy(grid.lat, lat, sizeof(lat));
+  inv3(lat, grid.g);
+  // heights of the cell along each reciprocal direction: V / |b x c| etc. = 1 / |row k of g|
+  double height[3];
+  for (int k = 0; k < 3; k++) height[k] = 1.0 / std::sqrt(grid.g[k] * grid.g[k] + grid.g[k + 3] * grid.g[k + 3] + grid.g[k + 6] * grid.g[k + 6]);
+
+  P->b_minmax.ensure(sizeof(double) * (6 + 6 * 64));
+  int launches = 0;
+  double mm[6] = {0, 0, 0, 0, 0, 0};
+  if (!grid.pbc[0] || !grid.pbc[1] || !grid.pbc[2]) {
+    launch_frac_minmax(d_pos, N, nullptr, grid, P->b_minmax.as<double>(), st, &launches);
+    CUDA_OK(cudaMemcpyAsync(mm, P->b_minmax.p, sizeof(mm), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    for (int k = 0; k < 6; k++)
+      if (!std::isfinite(mm[k])) throw GapError("calc_connect: atomic positions are not finite");
+  }
+  double width[3];
+  for (int k = 0; k < 3; k++) {
+    if (grid.pbc[k]) {
+      int n = (int)std::floor(height[k] / cutoff);
+      grid.n[k] = n < 1 ? 1 : n;
+    } else {
+      double ext = mm[3 + k] - mm[k];
+      grid.toff[k] = mm[k];
+      grid.tscale[k] = ext > 0 ? 1.0 / ext : 0.0;
+      int n = (int)std::floor(ext * height[k] / cutoff);
+      grid.n[k] = n < 1 ? 1 : n;
+      height[k] = ext * height[k];
+    }
+  }
+  // bound the number of cells by the number of atoms (dilute systems / vacuum)
+  {
+    double cap = 4.0 * N + 1024.0;
+    while ((double)grid.n[0] * grid.n[1] * grid.n[2] > cap) {
+      int kmax = 0;
+      for (int k = 1; k < 3; k++)
+        if (grid.n[k] > grid.n[kmax]) kmax = k;
+      grid.n[kmax] = (grid.n[kmax] + 1) / 2;
+    }
+  }
+  for (int k = 0; k < 3; k++) {
+    width[k] = height[k] / grid.n[k];
+    if (grid.pbc[k]) {
+      grid.R[k] = (int)std::ceil(cutoff / width[k] + 1e-9);
+      if (grid.R[k] < 1) grid.R[k] = 1;
+      if ((grid.R[k] + grid.n[k] - 1) / grid.n[k] + 2 > 120) throw GapError("calc_connect: cutoff is too large for this cell (more than 120 images)");
+    } else {
+      grid.R[k] = grid.n[k] > 1 ? (int)std::ceil(cutoff / width[k] + 1e-9) : 0;
+      if (grid.R[k] > grid.n[k] - 1) grid.R[k] = grid.n[k] - 1;
+    }
+  }
+  const int ncell = grid.n[0] * grid.n[1] * grid.n[2];
+
+  NeighbourWork& w = P->nw;
+  P->b_cell_of.ensure(sizeof(int) * N); w.cell_of = P->b_cell_of.as<int>();
+  P->b_mshift.ensure(sizeof(int) * N); w.mshift = P->b_mshift.as<int>();
+  P->b_keys.ensure(sizeof(int) * N); w.sort_keys = P->b_keys.as<int>();
+  P->b_idx.ensure(sizeof(int) * N); w.sort_idx = P->b_idx.as<int>();
+  P->b_iota.ensure(sizeof(int) * N); w.iota = P->b_iota.as<int>();
+  P->b_ccount.ensure(sizeof(int) * (ncell + 2)); w.cell_count = P->b_ccount.as<int>();
+  P->b_cstart.ensure(sizeof(int) * (ncell + 2)); w.cell_start = P->b_cstart.as<int>();
+  P->b_spos.ensure(sizeof(double) * 3 * N); w.spos = P->b_spos.as<double>();
+  P->b_smshift.ensure(sizeof(int) * N); w.smshift = P->b_smshift.as<int>();
+  P->b_nn.ensure(sizeof(int) * (N + 2)); w.nn = P->b_nn.as<int>();
+  size_t cb = neighbour_cub_bytes(N, ncell);
+  P->b_cub.ensure(cb); w.cub_tmp = P->b_cub.p; w.cub_bytes = P->b_cub.cap;
+
+  launch_bin_atoms(d_pos, N, grid, ncell, w, st, &launches);
+  launch_neigh_count(d_pos, N, grid, w, P->b_off.as<int>(), st, &launches);
+  int nnz = 0;
+  CUDA_OK(cudaMemcpyAsync(&nnz, P->b_off.as<int>() + N, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (nnz < 0) throw GapError("calc_connect: neighbour list exceeds 2^31 entries");
+  P->conn_nnz = nnz;
+  P->b_j.ensure(sizeof(int) * (size_t)(nnz + 1));
+  P->b_s.ensure(sizeof(int) * (size_t)(nnz + 1));
+  if (want_dist) P->b_d.ensure(sizeof(double) * (size_t)(nnz + 1));
+  launch_neigh_fill(d_pos, N, grid, w, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), want_dist ? P->b_d.as<double>() : nullptr, st,
+                    &launches);
+  P->launches += launches;
+  CUDA_OK(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------
+// model upload
+// ---------------------------------------------------------------------------------------------------
+double factorial_d(int n) {
+  double f = 1.0;
+  for (int i = 2; i <= n; i++) f *= i;
+  return f;
+}
+
+void upload_model(gap_potential* P) {
+  const double pi = 3.14159265358979323846264338327950288;
+  CUDA_OK(cudaMalloc(&P->d_e0, sizeof(double) * 128));
+  CUDA_OK(cudaMemcpy(P->d_e0, P->model.e0, sizeof(double) * 128, cudaMemcpyHostToDevice));
+  for (const Coordinate& c : P->model.coord) {
+    CoordDev cd;
+    cd.kind = c.kind;
+    if (c.kind == DESC_SOAP) {
+      const SoapSpec& s = c.soap;
+      if (s.n_max > SOAP_NMAX_CAP) throw GapError("soap n_max > " + std::to_string(SOAP_NMAX_CAP) + " is not supported by the B200 path");
+      if (s.l_max > SOAP_LMAX_CAP) throw GapError("soap l_max > " + std::to_string(SOAP_LMAX_CAP) + " is not supported by the B200 path");
+      if (s.n_species > SOAP_SPECIES_CAP || s.n_Z > SOAP_SPECIES_CAP)
+        throw GapError("soap n_species/n_Z > " + std::to_string(SOAP_SPECIES_CAP) + " is not supported by the B200 path");
+      SoapDev& h = cd.h;
+      memset(&h, 0, sizeof(h));
+      h.cutoff = s.cutoff; h.ctw = s.cutoff_transition_width; h.alpha = s.alpha; h.central_weight = s.central_weight;
+      h.sigma0 = s.covariance_sigma0; h.chol00 = s.cholesky_overlap[0];
+      h.cutoff_scale = s.cutoff_scale; h.cutoff_rate = s.cutoff_rate; h.cutoff_dexp = s.cutoff_dexp;
+      h.norm_radial_decay = (s.cutoff_dexp > 0 && s.cutoff_rate != 0.0) ? s.cutoff_rate / (1.0 + s.cutoff_rate) : 1.0;
+      h.l_max = s.l_max; h.n_max = s.n_max; h.n_species = s.n_species; h.n_Z = s.n_Z; h.K1 = s.K1(); h.d = s.d;
+      h.d_pad = round_up(s.d, COV_BK); h.nlm = (s.l_max + 1) * (s.l_max + 1);
+      h.normalise = s.normalise; h.cras = s.central_reference_all_species; h.two_lp1 = s.do_two_l_plus_one;
+      for (int k = 0; k < s.n_species; k++) h.species_Z[k] = s.species_Z[k];
+      for (int k = 0; k < s.n_Z; k++) h.centre_Z[k] = s.Z[k];
+      for (int k = 0; k < s.n_max; k++) h.r_basis[k] = s.r_basis[k];
+      for (int k = 0; k < s.n_max * s.n_max; k++) h.T[k] = s.transform_basis[k];
+      for (int l = 0; l <= s.l_max; l++) {
+        h.tlpo[l] = s.do_two_l_plus_one ? 1.0 / std::sqrt(2.0 * l + 1.0) : 1.0;
+        for (int m = 0; m <= l; m++)
+          h.ynorm[l * (l + 1) / 2 + m] = std::sqrt((2.0 * l + 1.0) / (4.0 * pi) * factorial_d(l - m) / factorial_d(l + m)) * (m > 0 ? std::sqrt(2.0) : 1.0);
+      }
+      cudaDeviceProp prop;
+      CUDA_OK(cudaGetDeviceProperties(&prop, P->device));
+      if (soap_adjoint_smem(h) > prop.sharedMemPerBlockOptin || soap_forward_smem(h) > prop.sharedMemPerBlockOptin)
+        throw GapError("soap descriptor too large for the shared memory of this device");
+      CUDA_OK(cudaMalloc(&cd.d_sp, sizeof(SoapDev)));
+      CUDA_OK(cudaMemcpy(cd.d_sp, &h, sizeof(SoapDev), cudaMemcpyHostToDevice));
+      cd.M = c.M;
+      cd.M_pad = round_up(c.M > 0 ? c.M : 1, COV_BN);
+      cd.d_pad = h.d_pad;
+      cd.dn_pad = round_up(s.d, COV_BN);
+      // sparse points: rows [M_pad][d_pad] (GEMM-1 B operand) and transposed [dn_pad][M_pad] (GEMM-2 B operand)
+      std::vector<double> rows((size_t)cd.M_pad * cd.d_pad, 0.0), trn((size_t)cd.dn_pad * cd.M_pad, 0.0), al(cd.M_pad, 0.0), cu(cd.M_pad, 0.0);
+      for (int m = 0; m < c.M; m++) {
+        for (int q = 0; q < s.d; q++) {
+          double v = c.sparseX[(size_t)m * s.d + q];
+          rows[(size_t)m * cd.d_pad + q] = v;
+          trn[(size_t)q * cd.M_pad + m] = v;
+        }
+        al[m] = c.alpha[m];
+        cu[m] = c.sparseCutoff[m];
+      }
+      CUDA_OK(cudaMalloc(&cd.sp_rows, rows.size() * sizeof(double)));
+      CUDA_OK(cudaMalloc(&cd.st_rows, trn.size() * sizeof(double)));
+      CUDA_OK(cudaMalloc(&cd.alpha, al.size() * sizeof(double)));
+      CUDA_OK(cudaMalloc(&cd.scut, cu.size() * sizeof(double)));
+      CUDA_OK(cudaMemcpy(cd.sp_rows, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(cd.st_rows, trn.data(), trn.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(cd.alpha, al.data(), al.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(cd.scut, cu.data(), cu.size() * sizeof(double), cudaMemcpyHostToDevice));
+      cd.cp.delta2 = c.delta * c.delta;
+      cd.cp.zeta = c.zeta;
+      double zi = std::nearbyint(c.zeta);
+      cd.cp.zeta_int = (std::fabs(c.zeta - zi) < 1e-12 * std::fmax(1.0, std::fabs(c.zeta)) && zi >= 0 && zi <= 64) ? (int)zi : -1;
+    } else {
+      std::vector<double> xs(c.M > 0 ? c.M : 1, 0.0), al(xs.size(), 0.0), cu(xs.size(), 0.0);
+      for (int m = 0; m < c.M; m++) { xs[m] = c.sparseX[m]; al[m] = c.alpha[m]; cu[m] = c.sparseCutoff[m]; }
+      CUDA_OK(cudaMalloc(&cd.x2, xs.size() * sizeof(double)));
+      CUDA_OK(cudaMalloc(&cd.a2, xs.size() * sizeof(double)));
+      CUDA_OK(cudaMalloc(&cd.c2, xs.size() * sizeof(double)));
+      CUDA_OK(cudaMemcpy(cd.x2, xs.data(), xs.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(cd.a2, al.data(), xs.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(cd.c2, cu.data(), xs.size() * sizeof(double), cudaMemcpyHostToDevice));
+      cd.p2.cutoff = c.d2b.cutoff; cd.p2.ctw = c.d2b.cutoff_transition_width; cd.p2.delta2 = c.delta * c.delta; cd.p2.f02 = c.f0 * c.f0;
+      cd.p2.inv_theta = 1.0 / c.theta[0]; cd.p2.Z1 = c.d2b.Z1; cd.p2.Z2 = c.d2b.Z2; cd.p2.M = c.M;
+      cd.p2.sparseX = cd.x2; cd.p2.alpha = cd.a2; cd.p2.scut = cd.c2;
+    }
+    P->cd.push_back(cd);
+  }
+}
+
+gap_potential* create_potential(const std::string& args, const std::string& xml, const std::string& base_dir, int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw GapError(std::string("gap_potential_initialise: no usable CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+  if (device < 0 || device >= ndev) throw GapError("gap_potential_initialise: CUDA device " + std::to_string(device) + " out of range");
+  GapModel m = load_gap_model(args, xml, base_dir);
+  CUDA_OK(cudaSetDevice(device));
+  gap_potential* P = new gap_potential();
+  try {
+    P->model = std::move(m);
+    P->device = device;
+    CUDA_OK(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    upload_model(P);
+  } catch (...) {
+    gap_potential_finalise(P);
+    throw;
+  }
+  return P;
+}
+
+struct CalcArgs {
+  int only_descriptor = 0;  // 1-based, 0 = all
+};
+CalcArgs parse_calc_args(const gap_potential* P, const char* args_str) {
+  CalcArgs a;
+  if (!args_str || !*args_str) return a;
+  ArgDict d(args_str);
+  if (d.has("r_scale") || d.has("E_scale"))  // IPModel_GAP.f95:348-350
+    throw GapError("IPModel_GAP_Calc: rescaling of potential at the calc() stage with r_scale and E_scale not yet implemented!");
+  if (d.has("atom_mask_name") && d.str("atom_mask_name", "NONE") != "NONE")
+    throw GapError("IPModel_GAP_Calc: atom_mask_name is not supported by the B200 path (use gap_potential_set_partition)");
+  if (!d.str("local_gap_variance", "").empty() || d.logical("print_gap_variance", false))
+    throw GapError("IPModel_GAP_Calc: GAP variance estimates are not supported by the B200 path");
+  if (!d.str("energy_per_coordinate", "").empty()) throw GapError("IPModel_GAP_Calc: energy_per_coordinate is not supported by the B200 path");
+  if (d.has("only_descriptor")) {
+    a.only_descriptor = (int)d.integer("only_descriptor", 0);
+    if (P->model.coord.size() <= 1) a.only_descriptor = 0;  // :399
+  }
+  return a;
+}
+
+struct SoapRun {
+  int nc = 0, nc_pad = 0;
+};
+
+// select + compact the centres of SOAP coordinate cd among atoms [first,last)
+int select_centres(gap_potential* P, const CoordDev& cd, const int* d_Z, int first, int last, cudaStream_t st) {
+  int n = last - first;
+  if (n <= 0) return 0;
+  int launches = 0;
+  P->b_flags.ensure(sizeof(int) * (n + 1));
+  P->b_scan.ensure(sizeof(int) * (n + 1));
+  P->b_centres.ensure(sizeof(int) * (n + 1));
+  launch_select_centres(d_Z, first, last, cd.d_sp, P->b_flags.as<int>(), st, &launches);
+  size_t cb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cb, (int*)nullptr, (int*)nullptr, n + 1);
+  P->b_cub.ensure(cb + 256);
+  size_t bytes = P->b_cub.cap;
+  cub::DeviceScan::ExclusiveSum(P->b_cub.p, bytes, P->b_flags.as<int>(), P->b_scan.as<int>(), n + 1, st);
+  launches++;
+  int nc = 0;
+  CUDA_OK(cudaMemcpyAsync(&nc, P->b_scan.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  launch_compact(P->b_scan.as<int>(), P->b_flags.as<int>(), first, n, P->b_centres.as<int>(), st, &launches);
+  P->launches += launches;
+  return nc;
+}
+
+void soap_forward_stage(gap_potential* P, const CoordDev& cd, int nc, const double* d_pos, const int* d_Z, const Lattice9& lat, cudaStream_t st) {
+  int launches = 0;
+  int nc_pad = round_up(nc > 0 ? nc : 1, COV_BM);
+  P->b_x.ensure(sizeof(double) * (size_t)nc_pad * cd.d_pad);
+  P->b_xlm.ensure(sizeof(double) * (size_t)(nc > 0 ? nc : 1) * cd.h.nlm * cd.h.K1);
+  P->b_pnorm.ensure(sizeof(double) * (size_t)nc_pad);
+  if (nc_pad > nc) CUDA_OK(cudaMemsetAsync(P->b_x.as<double>() + (size_t)nc * cd.d_pad, 0, sizeof(double) * (size_t)(nc_pad - nc) * cd.d_pad, st));
+  launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos, d_Z, lat,
+                      P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
+  P->launches += launches;
+}
+
+// covariance for rows [0, nc_pad) of b_x: epart (all rows) and, if want_grad, gvec (all rows)
+void covariance_stage(gap_potential* P, const CoordDev& cd, int nc, bool want_grad, cudaStream_t st) {
+  int launches = 0;
+  int nc_pad = round_up(nc > 0 ? nc : 1, COV_BM);
+  int n_tiles_n = cd.M_pad / COV_BN;
+  size_t budget = (size_t)1 << 30;  // bytes of acoef kept live at once
+  int chunk = (int)(budget / ((size_t)cd.M_pad * sizeof(double)) / COV_BM) * COV_BM;
+  if (chunk < COV_BM) chunk = COV_BM;
+  if (chunk > nc_pad) chunk = nc_pad;
+  P->b_acoef.ensure(sizeof(double) * (size_t)chunk * cd.M_pad);
+  P->b_epart.ensure(sizeof(double) * (size_t)nc_pad * n_tiles_n);
+  if (want_grad) P->b_gvec.ensure(sizeof(double) * (size_t)nc_pad * cd.dn_pad);
+  for (int r0 = 0; r0 < nc_pad; r0 += chunk) {
+    int rows = std::min(chunk, nc_pad - r0);
+    launch_cov_gemm1(P->b_x.as<double>() + (size_t)r0 * cd.d_pad, cd.d_pad, cd.sp_rows, cd.d_pad, rows, cd.M, cd.M_pad, cd.d_pad, cd.alpha, cd.scut,
+                     cd.cp, P->b_acoef.as<double>(), cd.M_pad, P->b_epart.as<double>() + (size_t)r0 * n_tiles_n, n_tiles_n, st, &launches);
+    if (want_grad)
+      launch_cov_gemm2(P->b_acoef.as<double>(), cd.M_pad, cd.st_rows, cd.M_pad, rows, cd.dn_pad, cd.M_pad, P->b_gvec.as<double>() + (size_t)r0 * cd.dn_pad,
+                       cd.dn_pad, st, &launches);
+  }
+  P->launches += launches;
+}
+
+void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d_Z, const double* lattice, const int* pbc,
+                      const char* args_str, bool want_grad, double* d_packed, double* d_le_user, double* d_lv, cudaStream_t st) {
+  CUDA_OK(cudaSetDevice(P->device));
+  CalcArgs ca = parse_calc_args(P, args_str);
+  if (!lattice || !pbc) throw GapError("gap_potential_calc: lattice and pbc are required");
+  const int first = (int)((long long)P->rank * N / P->n_ranks), last = (int)((long long)(P->rank + 1) * N / P->n_ranks);
+  P->ev_used = 0;
+  mark(P, st, -1);
+  build_connect(P, N, d_pos, lattice, pbc, P->model.cutoff, false, st);
+  mark(P, st, 0);
+  Lattice9 lat;
+  for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
+
+  double* d_le = d_le_user;
+  if (!d_le) {
+    P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
+    d_le = P->b_le.as<double>();
+  }
+  CUDA_OK(cudaMemsetAsync(d_packed, 0, sizeof(double) * (10 + 3 * (size_t)N), st));
+  CUDA_OK(cudaMemsetAsync(d_le, 0, sizeof(double) * (size_t)(N + 1), st));
+  if (d_lv) CUDA_OK(cudaMemsetAsync(d_lv, 0, sizeof(double) * 9 * (size_t)N, st));
+  double* d_force = d_packed + 10;
+  const double es = P->model.E_scale;
+
+  // virial partial slots
+  size_t slots_cap = 0;
+  for (const CoordDev& cd : P->cd) slots_cap += cd.kind == DESC_SOAP ? (size_t)(last - first) : (size_t)((last - first + 3) / 4);
+  if (want_grad) P->b_vir.ensure(sizeof(double) * 9 * (slots_cap + 1));
+  size_t slot = 0;
+
+  for (size_t ic = 0; ic < P->cd.size(); ic++) {
+    if (ca.only_descriptor && (int)ic + 1 != ca.only_descriptor) continue;
+    const CoordDev& cd = P->cd[ic];
+    int launches = 0;
+    if (cd.kind == DESC_SOAP) {
+      int nc = select_centres(P, cd, d_Z, first, last, st);
+      if (nc > 0) {
+        soap_forward_stage(P, cd, nc, d_pos, d_Z, lat, st);
+        mark(P, st, 1);
+        covariance_stage(P, cd, nc, want_grad, st);
+        launch_energy_rows(P->b_epart.as<double>(), cd.M_pad / COV_BN, P->b_centres.as<int>(), nc, es, d_le, st, &launches);
+        mark(P, st, 2);
+        if (want_grad) {
+          launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), nc, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos, d_Z, lat,
+                              P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, es, d_force,
+                              P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches);
+          slot += nc;
+          mark(P, st, 3);
+        }
+      }
+    } else {
+      int nb = 0;
+      launch_pair2b(cd.p2, first, last, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos, d_Z, lat, es, want_grad ? 1 : 0, d_le,
+                    want_grad ? d_force : nullptr, want_grad ? P->b_vir.as<double>() + 9 * slot : nullptr, want_grad ? d_lv : nullptr, st, &launches,
+                    &nb);
+      if (want_grad) slot += nb;
+      mark(P, st, 4);
+    }
+    P->launches += launches;
+  }
+  // totals
+  P->b_fin.ensure(sizeof(double) * 10 * FIN_BLOCKS);
+  k_finalize_partial<<<FIN_BLOCKS, FIN_THREADS, 0, st>>>(d_Z, N, first, last, P->d_e0, es, d_le, want_grad ? P->b_vir.as<double>() : nullptr,
+                                                        want_grad ? (int)slot : 0, P->b_fin.as<double>());
+  k_finalize_final<<<1, 32, 0, st>>>(P->b_fin.as<double>(), d_packed);
+  P->launches += 2;
+  mark(P, st, -1);
+  CUDA_OK(cudaGetLastError());
+}
+
+int guard(const std::function<void()>& fn) {
+  try {
+    fn();
+    return 0;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return 1;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return 2;
+  }
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* gap_last_error(void) { return g_last_error.c_str(); }
+
+int gap_potential_initialise(gap_potential** pot, const char* args_str, const char* param_str, const char* base_dir, int device) {
+  return guard([&] {
+    if (!pot) throw GapError("gap_potential_initialise: pot is NULL");
+    *pot = nullptr;
+    if (!param_str) throw GapError("gap_potential_initialise: param_str is NULL");
+    *pot = create_potential(args_str ? args_str : "", param_str, base_dir && *base_dir ? base_dir : ".", device);
+  });
+}
+
+int gap_potential_filename_initialise(gap_potential** pot, const char* args_str, const char* param_filename, int device) {
+  return guard([&] {
+    if (!pot) throw GapError("gap_potential_filename_initialise: pot is NULL");
+    *pot = nullptr;
+    if (!param_filename) throw GapError("gap_potential_filename_initialise: param_filename is NULL");
+    std::ifstream f(param_filename, std::ios::binary);
+    if (!f) throw GapError(std::string("Potential_Filename_Initialise: cannot open ") + param_filename);
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    std::string path(param_filename);
+    size_t sl = path.find_last_of('/');
+    std::string dir = sl == std::string::npos ? "." : (sl == 0 ? "/" : path.substr(0, sl));
+    *pot = create_potential(args_str ? args_str : "", ss.str(), dir, device);
+  });
+}
+
+void gap_potential_finalise(gap_potential* P) {
+  if (!P) return;
+  cudaSetDevice(P->device);
+  if (P->stream) cudaStreamSynchronize(P->stream);
+  for (CoordDev& cd : P->cd) {
+    cudaFree(cd.d_sp); cudaFree(cd.sp_rows); cudaFree(cd.st_rows); cudaFree(cd.alpha); cudaFree(cd.scut);
+    cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2);
+  }
+  cudaFree(P->d_e0);
+  DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_ccount, &P->b_cstart, &P->b_spos, &P->b_smshift,
+                    &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
+                    &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
+                    &P->b_vir, &P->b_fin};
+  for (DevBuf* b : bufs) b->release();
+  for (cudaEvent_t e : P->ev) cudaEventDestroy(e);
+  if (P->stream) cudaStreamDestroy(P->stream);
+  delete P;
+}
+
+double gap_potential_cutoff(const gap_potential* P) { return P ? P->model.cutoff : 0.0; }
+int gap_potential_n_coordinate(const gap_potential* P) { return P ? (int)P->model.coord.size() : 0; }
+long gap_potential_launch_count(const gap_potential* P) { return P ? P->launches : 0; }
+
+int gap_potential_print(const gap_potential* P, char* buf, size_t n) {
+  return guard([&] {
+    if (!P || !buf || n == 0) throw GapError("gap_potential_print: bad arguments");
+    std::ostringstream os;
+    os << "IPModel_GAP : Gaussian Approximation Potential (B200 path)\n";
+    os << "IPModel_GAP : label = " << P->model.label << "\n";
+    os << "IPModel_GAP : cutoff = " << P->model.cutoff << "\n";
+    os << "IPModel_GAP : E_scale = " << P->model.E_scale << "\n";
+    os << "IPModel_GAP : gap_version = " << P->model.xml_version << "\n";
+    for (size_t i = 0; i < P->model.coord.size(); i++) {
+      const Coordinate& c = P->model.coord[i];
+      os << "IPModel_GAP : coordinate " << (i + 1) << " : " << c.descriptor_str << " | dimensions=" << c.d << " n_sparseX=" << c.M
+         << " covariance_type=" << c.covariance_type << " delta=" << c.delta << " zeta=" << c.zeta << "\n";
+    }
+    std::string s = os.str();
+    size_t k = s.size() < n - 1 ? s.size() : n - 1;
+    memcpy(buf, s.data(), k);
+    buf[k] = 0;
+  });
+}
+
+int gap_potential_set_partition(gap_potential* P, int rank, int n_ranks) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_set_partition: pot is NULL");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw GapError("gap_potential_set_partition: need 0 <= rank < n_ranks");
+    P->rank = rank;
+    P->n_ranks = n_ranks;
+  });
+}
+
+int gap_potential_calc_device(gap_potential* P, int N, const double* d_pos, const int* d_Z, const double* lattice, const int* pbc,
+                              const char* args_str, int want_grad, double* d_packed, double* d_local_e, double* d_local_virial, void* stream) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_calc_device: pot is NULL");
+    if (N < 0) throw GapError("gap_potential_calc_device: N < 0");
+    if (!d_packed) throw GapError("gap_potential_calc_device: d_packed is NULL");
+    cudaStream_t st = stream ? (cudaStream_t)stream : P->stream;
+    calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad != 0 || d_local_virial != nullptr, d_packed, d_local_e, d_local_virial, st);
+  });
+}
+
+int gap_potential_calc(gap_potential* P, int N, const double* pos, const int* Z, const double* lattice, const int* pbc, const char* args_str,
+                       double* energy, double* local_e, double* force, double* virial, double* local_virial) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_calc: pot is NULL");
+    if (N < 0) throw GapError("gap_potential_calc: N < 0");
+    if (N > 0 && (!pos || !Z)) throw GapError("gap_potential_calc: pos/Z are NULL");
+    CUDA_OK(cudaSetDevice(P->device));
+    cudaStream_t st = P->stream;
+    P->b_pos.ensure(sizeof(double) * 3 * (size_t)(N + 1));
+    P->b_Z.ensure(sizeof(int) * (size_t)(N + 1));
+    P->b_packed.ensure(sizeof(double) * (10 + 3 * (size_t)N));
+    P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
+    if (local_virial) P->b_lv.ensure(sizeof(double) * 9 * (size_t)(N + 1));
+    if (N > 0) {
+      CUDA_OK(cudaMemcpyAsync(P->b_pos.p, pos, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaMemcpyAsync(P->b_Z.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+    }
+    bool want_grad = force || virial || local_virial;  // IPModel_GAP.f95:416-424
+    calc_device_impl(P, N, P->b_pos.as<double>(), P->b_Z.as<int>(), lattice, pbc, args_str, want_grad, P->b_packed.as<double>(),
+                     P->b_le.as<double>(), local_virial ? P->b_lv.as<double>() : nullptr, st);
+    double head[10];
+    CUDA_OK(cudaMemcpyAsync(head, P->b_packed.p, sizeof(head), cudaMemcpyDeviceToHost, st));
+    if (force && N > 0) CUDA_OK(cudaMemcpyAsync(force, P->b_packed.as<double>() + 10, sizeof(double) * 3 * (size_t)N, cudaMemcpyDeviceToHost, st));
+    if (local_e && N > 0) CUDA_OK(cudaMemcpyAsync(local_e, P->b_le.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
+    if (local_virial && N > 0) CUDA_OK(cudaMemcpyAsync(local_virial, P->b_lv.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (energy) *energy = head[0];
+    if (virial)
+      for (int k = 0; k < 9; k++) virial[k] = head[1 + k];
+    collect_timings(P);
+  });
+}
+
+int gap_potential_last_timings(const gap_potential* P, double* ms6) {
+  if (!P || !ms6) return 1;
+  for (int k = 0; k < 6; k++) ms6[k] = P->last_ms[k];
+  return 0;
+}
+
+int gap_b200_wrapper_simple(const char* param_filename, const int* N, const double* lattice, const int* Z, const double* pos, double* energy,
+                            double* force, double* virial) {
+  gap_potential* P = nullptr;
+  int rc = gap_potential_filename_initialise(&P, "", param_filename, 0);
+  if (rc) return rc;
+  int pbc[3] = {1, 1, 1};
+  rc = gap_potential_calc(P, *N, pos, Z, lattice, pbc, "", energy, nullptr, force, virial, nullptr);
+  gap_potential_finalise(P);
+  return rc;
+}
+
+int gap_calc_connect(gap_potential* P, int N, const double* pos, const double* lattice, const int* pbc, double cutoff, int* n_entries) {
+  return guard([&] {
+    if (!P) throw GapError("gap_calc_connect: pot is NULL");
+    CUDA_OK(cudaSetDevice(P->device));
+    P->b_pos.ensure(sizeof(double) * 3 * (size_t)(N + 1));
+    if (N > 0) CUDA_OK(cudaMemcpyAsync(P->b_pos.p, pos, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, P->stream));
+    build_connect(P, N, P->b_pos.as<double>(), lattice, pbc, cutoff, true, P->stream);
+    CUDA_OK(cudaStreamSynchronize(P->stream));
+    if (n_entries) *n_entries = P->conn_nnz;
+  });
+}
+
+int gap_get_connect(gap_potential* P, int* offsets, int* j, int* shift, double* distance) {
+  return guard([&] {
+    if (!P) throw GapError("gap_get_connect: pot is NULL");
+    CUDA_OK(cudaSetDevice(P->device));
+    int N = P->conn_N, nnz = P->conn_nnz;
+    if (offsets) CUDA_OK(cudaMemcpy(offsets, P->b_off.p, sizeof(int) * (N + 1), cudaMemcpyDeviceToHost));
+    if (nnz > 0) {
+      if (j) CUDA_OK(cudaMemcpy(j, P->b_j.p, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost));
+      if (shift) {
+        std::vector<int> packed(nnz);
+        CUDA_OK(cudaMemcpy(packed.data(), P->b_s.p, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < nnz; k++) unpack_shift(packed[k], shift[3 * k], shift[3 * k + 1], shift[3 * k + 2]);
+      }
+      if (distance) {
+        if (P->b_d.cap < sizeof(double) * (size_t)nnz) throw GapError("gap_get_connect: distances were not stored (call gap_calc_connect first)");
+        CUDA_OK(cudaMemcpy(distance, P->b_d.p, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost));
+      }
+    }
+  });
+}
+
+int gap_descriptor_calc(gap_potential* P, int i_coord, int N, const double* pos, const int* Z, const double* lattice, const int* pbc, int* n_desc,
+                        int* d_out, double* x, int* ci) {
+  return guard([&] {
+    if (!P) throw GapError("gap_descriptor_calc: pot is NULL");
+    if (i_coord < 0 || i_coord >= (int)P->cd.size()) throw GapError("gap_descriptor_calc: coordinate index out of range");
+    const CoordDev& cd = P->cd[i_coord];
+    if (cd.kind != DESC_SOAP) throw GapError("gap_descriptor_calc: only soap coordinates have a descriptor-level entry point");
+    CUDA_OK(cudaSetDevice(P->device));
+    cudaStream_t st = P->stream;
+    P->b_pos.ensure(sizeof(double) * 3 * (size_t)(N + 1));
+    P->b_Z.ensure(sizeof(int) * (size_t)(N + 1));
+    if (N > 0) {
+      CUDA_OK(cudaMemcpyAsync(P->b_pos.p, pos, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaMemcpyAsync(P->b_Z.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+    }
+    int nc = select_centres(P, cd, P->b_Z.as<int>(), 0, N, st);
+    if (n_desc) *n_desc = nc;
+    if (d_out) *d_out = cd.h.d;
+    if (!x) return;
+    build_connect(P, N, P->b_pos.as<double>(), lattice, pbc, cd.h.cutoff, false, st);
+    Lattice9 lat;
+    for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
+    soap_forward_stage(P, cd, nc, P->b_pos.as<double>(), P->b_Z.as<int>(), lat, st);
+    if (nc > 0) {
+      CUDA_OK(cudaMemcpy2DAsync(x, sizeof(double) * cd.h.d, P->b_x.p, sizeof(double) * cd.d_pad, sizeof(double) * cd.h.d, nc, cudaMemcpyDeviceToHost, st));
+      if (ci) CUDA_OK(cudaMemcpyAsync(ci, P->b_centres.p, sizeof(int) * nc, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_OK(cudaStreamSynchronize(st));
+  });
+}
+
+int gap_gp_predict(gap_potential* P, int i_coord, int n, const double* x, double* e, double* grad) {
+  return guard([&] {
+    if (!P) throw GapError("gap_gp_predict: pot is NULL");
+    if (i_coord < 0 || i_coord >= (int)P->cd.size()) throw GapError("gap_gp_predict: coordinate index out of range");
+    const CoordDev& cd = P->cd[i_coord];
+    if (cd.kind != DESC_SOAP) throw GapError("gap_gp_predict: dot_product (soap) coordinates only");
+    if (n <= 0) return;
+    CUDA_OK(cudaSetDevice(P->device));
+    cudaStream_t st = P->stream;
+    int n_pad = round_up(n, COV_BM);
+    P->b_x.ensure(sizeof(double) * (size_t)n_pad * cd.d_pad);
+    CUDA_OK(cudaMemsetAsync(P->b_x.p, 0, sizeof(double) * (size_t)n_pad * cd.d_pad, st));
+    CUDA_OK(cudaMemcpy2DAsync(P->b_x.p, sizeof(double) * cd.d_pad, x, sizeof(double) * cd.h.d, sizeof(double) * cd.h.d, n, cudaMemcpyHostToDevice, st));
+    P->b_centres.ensure(sizeof(int) * (size_t)(n + 1));
+    k_iota<<<(n + 255) / 256, 256, 0, st>>>(P->b_centres.as<int>(), n);
+    P->b_le.ensure(sizeof(double) * (size_t)(n + 1));
+    CUDA_OK(cudaMemsetAsync(P->b_le.p, 0, sizeof(double) * (size_t)(n + 1), st));
+    covariance_stage(P, cd, n, grad != nullptr, st);
+    int launches = 1;
+    launch_energy_rows(P->b_epart.as<double>(), cd.M_pad / COV_BN, P->b_centres.as<int>(), n, 1.0, P->b_le.as<double>(), st, &launches);
+    P->launches += launches;
+    if (e) CUDA_OK(cudaMemcpyAsync(e, P->b_le.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (grad)
+      CUDA_OK(cudaMemcpy2DAsync(grad, sizeof(double) * cd.h.d, P->b_gvec.p, sizeof(double) * cd.dn_pad, sizeof(double) * cd.h.d, n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int gap_model_describe(const char* args_str, const char* param_str, const char* base_dir, char* buf, size_t n) {
+  return guard([&] {
+    if (!param_str || !buf || n == 0) throw GapError("gap_model_describe: bad arguments");
+    GapModel m = load_gap_model(args_str ? args_str : "", param_str, base_dir && *base_dir ? base_dir : ".");
+    std::ostringstream os;
+    os.precision(17);
+    os << "label " << m.label << "\nxml_version " << m.xml_version << "\ncutoff " << m.cutoff << "\nE_scale " << m.E_scale << "\nn_coordinate "
+       << m.coord.size() << "\n";
+    os << "e0";
+    for (int z = 0; z < 128; z++)
+      if (m.e0[z] != 0.0) os << " " << z << ":" << m.e0[z];
+    os << "\n";
+    for (size_t i = 0; i < m.coord.size(); i++) {
+      const Coordinate& c = m.coord[i];
+      double sx = 0, sa = 0, sc = 0;
+      for (size_t k = 0; k < c.sparseX.size(); k++) sx += c.sparseX[k] * (double)((k % 7) + 1);
+      for (double v : c.alpha) sa += v;
+      for (double v : c.sparseCutoff) sc += v;
+      os << "coordinate " << i << " kind " << c.kind << " covariance_type " << c.covariance_type << " d " << c.d << " M " << c.M << " delta " << c.delta
+         << " f0 " << c.f0 << " zeta " << c.zeta << " theta0 " << (c.theta.empty() ? 0.0 : c.theta[0]) << " cutoff " << c.cutoff() << " sparseX_wsum " << sx
+         << " alpha_sum " << sa << " sparseCutoff_sum " << sc << "\n";
+      if (c.kind == DESC_SOAP) {
+        const SoapSpec& s = c.soap;
+        os << "soap " << i << " l_max " << s.l_max << " n_max " << s.n_max << " n_species " << s.n_species << " n_Z " << s.n_Z << " cras "
+           << (int)s.central_reference_all_species << " normalise " << (int)s.normalise << " two_lp1 " << (int)s.do_two_l_plus_one << " alpha " << s.alpha
+           << " ctw " << s.cutoff_transition_width << " central_weight " << s.central_weight << " sigma0 " << s.covariance_sigma0 << "\n";
+        os << "species_Z";
+        for (int v : s.species_Z) os << " " << v;
+        os << "\nZ";
+        for (int v : s.Z) os << " " << v;
+        os << "\nr_basis";
+        for (double v : s.r_basis) os << " " << v;
+        os << "\ntransform_basis";
+        for (double v : s.transform_basis) os << " " << v;
+        os << "\ncholesky_overlap";
+        for (double v : s.cholesky_overlap) os << " " << v;
+        os << "\n";
+      } else {
+        os << "distance_2b " << i << " Z1 " << c.d2b.Z1 << " Z2 " << c.d2b.Z2 << " ctw " << c.d2b.cutoff_transition_width << "\n";
+      }
+    }
+    std::string s = os.str();
+    if (s.size() + 1 > n) throw GapError("gap_model_describe: buffer too small (need " + std::to_string(s.size() + 1) + ")");
+    memcpy(buf, s.c_str(), s.size() + 1);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+"""``Potential`` -- host-side mirror of ``quippy.potential.Potential`` over libgapb200.so.
+
+Mirrors the reference's Python interface for the GAP path (quippy/quippy/potential.py:64-331):
+same constructor arguments (``args_str``, ``param_str`` / ``param_filename``, ``calc_args``), the ASE
+``Calculator``-style ``calculate(atoms, properties)`` filling ``results`` with ``energy``, ``forces``
+(N,3), ``stress`` (Voigt, ``-virial/V``, :281-284), ``energies``, ``stresses``, and the extras in
+``extra_results``; errors surface as ``RuntimeError`` (quippy maps Fortran aborts the same way).
+
+All arithmetic happens in the CUDA library behind the C ABI of include/gap_b200.h; this module only
+marshals numpy arrays into the Fortran-compatible layouts.  There is no CPU fallback: if the shared
+library or a CUDA device is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBNAME = os.path.join(_HERE, "libgapb200.so")
+_lib = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+# every symbol include/gap_b200.h declares: (restype, argtypes)
+ABI = {
+    "gap_potential_filename_initialise": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_char_p, C.c_int]),
+    "gap_potential_initialise": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "gap_potential_finalise": (None, [C.c_void_p]),
+    "gap_potential_cutoff": (C.c_double, [C.c_void_p]),
+    "gap_potential_print": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "gap_potential_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "gap_potential_calc": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "gap_potential_calc_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_dp, c_ip, C.c_char_p, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gap_b200_wrapper_simple": (C.c_int, [C.c_char_p, c_ip, c_dp, c_ip, c_dp, c_dp, c_dp, c_dp]),
+    "gap_calc_connect": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip, C.c_double, c_ip]),
+    "gap_get_connect": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_dp]),
+    "gap_descriptor_calc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_ip, c_ip, c_ip, c_dp, c_ip]),
+    "gap_gp_predict": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp]),
+    "gap_potential_n_coordinate": (C.c_int, [C.c_void_p]),
+    "gap_potential_launch_count": (C.c_long, [C.c_void_p]),
+    "gap_potential_last_timings": (C.c_int, [C.c_void_p, c_dp]),
+    "gap_model_describe": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
+    "gap_last_error": (C.c_char_p, []),
+}
+
+
+def load_library():
+    """Load libgapb200.so (built in-tree by ``__graft_entry__.build()``); fail loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBNAME):
+            raise RuntimeError("libgapb200.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                               "quip_b200 has no CPU fallback" % _LIBNAME)
+        lib = C.CDLL(_LIBNAME)
+        for name, (res, args) in ABI.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip) if a is not None else None
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(load_library().gap_last_error().decode("utf-8", "replace"))
+
+
+def model_describe(param_str=None, param_filename=None, args_str="", base_dir="."):
+    """Host-only parse of a GAP model through the product's C++ loader (no GPU needed); returns the description text."""
+    if param_filename is not None:
+        with open(param_filename) as fh:
+            param_str = fh.read()
+        base_dir = os.path.dirname(os.path.abspath(param_filename))
+    buf = C.create_string_buffer(1 << 20)
+    _check(load_library().gap_model_describe(args_str.encode(), param_str.encode(), base_dir.encode(), buf, len(buf)))
+    return buf.value.decode()
+
+
+def key_val_dict_to_str(d):
+    return " ".join("%s=%s" % (k, v) if v is not None else str(k) for k, v in d.items())
+
+
+def _geometry(atoms):
+    pos = np.ascontiguousarray(atoms.get_positions(), dtype=np.float64)
+    Z = np.ascontiguousarray(atoms.get_atomic_numbers(), dtype=np.int32)
+    lat = np.ascontiguousarray(np.asarray(atoms.get_cell(), dtype=np.float64).reshape(9))  # rows = vectors = Fortran columns
+    pbc = np.ascontiguousarray(np.asarray(atoms.get_pbc(), dtype=bool).astype(np.int32))
+    return pos, Z, lat, pbc
+
+
+class Potential:
+    implemented_properties = ["energy", "free_energy", "forces", "stress", "energies", "stresses", "virial", "local_energy",
+                              "local_virial", "force"]
+
+    def __init__(self, args_str="", pot1=None, pot2=None, param_str=None, param_filename=None, atoms=None,
+                 calculation_always_required=False, calc_args=None, device=0, **kwargs):
+        if pot1 is not None or pot2 is not None:
+            raise RuntimeError("Potential: Sum potentials (pot1/pot2) are outside the scope of the B200 GAP path")
+        lib = load_library()
+        self._h = C.c_void_p()
+        if param_filename is not None:
+            _check(lib.gap_potential_filename_initialise(C.byref(self._h), args_str.encode(), os.fspath(param_filename).encode(),
+                                                         int(device)))
+        elif param_str is not None:
+            _check(lib.gap_potential_initialise(C.byref(self._h), args_str.encode(), param_str.encode(),
+                                                kwargs.pop("base_dir", ".").encode(), int(device)))
+        else:
+            raise RuntimeError("Potential: one of param_filename / param_str is required")
+        self.args_str = args_str
+        if isinstance(calc_args, dict):
+            calc_args = key_val_dict_to_str(calc_args)
+        self.calc_args = calc_args or ""
+        self.calculation_always_required = calculation_always_required
+        self.results = {}
+        self.extra_results = {"config": {}, "atoms": {}}
+        self.atoms = None
+        if atoms is not None:
+            atoms.calc = self
+
+    # ---- reference API ------------------------------------------------------------------------
+    def cutoff(self):
+        return load_library().gap_potential_cutoff(self._h)
+
+    def print_(self):
+        buf = C.create_string_buffer(16384)
+        _check(load_library().gap_potential_print(self._h, buf, len(buf)))
+        return buf.value.decode()
+
+    def set_partition(self, rank, n_ranks):
+        _check(load_library().gap_potential_set_partition(self._h, int(rank), int(n_ranks)))
+
+    def calc(self, atoms, energy=True, force=False, virial=False, local_energy=False, local_virial=False, args_str=""):
+        """``calc(pot, at, energy, force, virial, local_energy, local_virial, args_str)`` (Potential.f95:803).
+        Returns a dict with the requested quantities; ``force`` is (N,3), ``virial`` (3,3), ``local_virial`` (N,9)."""
+        pos, Z, lat, pbc = _geometry(atoms)
+        N = len(Z)
+        e = np.zeros(1)
+        f = np.zeros((N, 3)) if force else None
+        v = np.zeros((3, 3), order="F") if virial else None
+        le = np.zeros(N) if local_energy else None
+        lv = np.zeros((N, 9)) if local_virial else None
+        full_args = (self.calc_args + " " + (args_str or "")).strip()
+        _check(load_library().gap_potential_calc(self._h, N, _dp(pos), _ip(Z), _dp(lat), _ip(pbc), full_args.encode(), _dp(e),
+                                                 _dp(le), _dp(f), _dp(v), _dp(lv)))
+        out = {"energy": float(e[0])}
+        if force:
+            out["force"] = f
+        if virial:
+            out["virial"] = np.array(v)
+        if local_energy:
+            out["local_energy"] = le
+        if local_virial:
+            out["local_virial"] = lv
+        return out
+
+    def calculate(self, atoms=None, properties=None, system_changes=None, forces=None, virial=None, local_energy=None,
+                  local_virial=None, vol_per_atom=None, calc_args=None, **kwargs):
+        """ASE-calculator entry point (quippy/quippy/potential.py:177-331)."""
+        properties = list(set(["energy", "forces"] + list(properties or [])))
+        for p in properties:
+            if p not in self.implemented_properties:
+                raise RuntimeError("Don't know how to calculate property '%s'" % p)
+        if atoms is not None:
+            self.atoms = atoms
+        args_str = ""
+        if calc_args is not None:
+            args_str += " " + (key_val_dict_to_str(calc_args) if isinstance(calc_args, dict) else calc_args)
+        if kwargs:
+            args_str += " " + key_val_dict_to_str(kwargs)
+        want_v = "virial" in properties or "stress" in properties or virial is not None
+        want_lv = "local_virial" in properties or "stresses" in properties or local_virial is not None
+        want_le = "energies" in properties or "local_energy" in properties or local_energy is not None
+        r = self.calc(self.atoms, energy=True, force=True, virial=want_v, local_energy=want_le, local_virial=want_lv,
+                      args_str=args_str)
+        self.results = {"energy": r["energy"], "free_energy": r["energy"], "forces": r["force"]}
+        self.extra_results = {"config": {}, "atoms": {}}
+        if want_v:
+            stress = -r["virial"] / self.atoms.get_volume()
+            self.results["stress"] = np.array([stress[0, 0], stress[1, 1], stress[2, 2], stress[1, 2], stress[0, 2], stress[0, 1]])
+            self.extra_results["config"]["virial"] = r["virial"].copy()
+        if want_le:
+            self.results["energies"] = r["local_energy"].copy()
+            self.extra_results["atoms"]["local_energy"] = r["local_energy"].copy()
+        if want_lv:
+            self.extra_results["atoms"]["local_virial"] = r["local_virial"].copy()
+            if "stresses" in properties:
+                v_atom = self.atoms.get_volume() / len(self.atoms) if vol_per_atom is None else float(vol_per_atom)
+                self.results["stresses"] = -r["local_virial"].reshape((len(self.atoms), 3, 3), order="F") / v_atom
+        return self.results
+
+    def get_potential_energy(self, atoms=None):
+        return self.calculate(atoms, ["energy"])["energy"]
+
+    def get_forces(self, atoms=None):
+        return self.calculate(atoms, ["forces"])["forces"]
+
+    def get_stress(self, atoms=None):
+        return self.calculate(atoms, ["stress"])["stress"]
+
+    def get_virial(self, atoms=None):
+        self.calculate(atoms, ["stress"])
+        return self.extra_results["config"]["virial"]
+
+    # ---- stage-level entry points (parity tests, profiling) ---------------------------------------
+    def calc_connect(self, atoms, cutoff=None):
+        """Full neighbour list of ``atoms`` as (offsets[N+1], j[n], shift[n,3], distance[n])."""
+        pos, Z, lat, pbc = _geometry(atoms)
+        N = len(Z)
+        n = C.c_int(0)
+        cutoff = self.cutoff() if cutoff is None else float(cutoff)
+        _check(load_library().gap_calc_connect(self._h, N, _dp(pos), _dp(lat), _ip(pbc), cutoff, C.byref(n)))
+        off = np.zeros(N + 1, dtype=np.int32)
+        j = np.zeros(max(n.value, 1), dtype=np.int32)
+        s = np.zeros((max(n.value, 1), 3), dtype=np.int32)
+        d = np.zeros(max(n.value, 1))
+        _check(load_library().gap_get_connect(self._h, _ip(off), _ip(j), _ip(s), _dp(d)))
+        return off, j[:n.value], s[:n.value], d[:n.value]
+
+    def descriptor_calc(self, atoms, i_coord=0):
+        pos, Z, lat, pbc = _geometry(atoms)
+        N = len(Z)
+        nd, d = C.c_int(0), C.c_int(0)
+        lib = load_library()
+        _check(lib.gap_descriptor_calc(self._h, i_coord, N, _dp(pos), _ip(Z), _dp(lat), _ip(pbc), C.byref(nd), C.byref(d), None, None))
+        x = np.zeros((max(nd.value, 1), d.value))
+        ci = np.zeros(max(nd.value, 1), dtype=np.int32)
+        _check(lib.gap_descriptor_calc(self._h, i_coord, N, _dp(pos), _ip(Z), _dp(lat), _ip(pbc), C.byref(nd), C.byref(d), _dp(x), _ip(ci)))
+        return x[:nd.value], ci[:nd.value]
+
+    def gp_predict(self, i_coord, x, grad=True):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n, d = x.shape
+        e = np.zeros(n)
+        g = np.zeros((n, d)) if grad else None
+        _check(load_library().gap_gp_predict(self._h, i_coord, n, _dp(x), _dp(e), _dp(g)))
+        return e, g
+
+    def calc_device(self, N, d_pos_ptr, d_Z_ptr, lattice9, pbc3, d_packed_ptr, want_grad=True, d_local_e_ptr=None,
+                    d_local_virial_ptr=None, stream_ptr=None, args_str=""):
+        """GPU-resident evaluation: all ``*_ptr`` are raw device addresses (e.g. ``tensor.data_ptr()``)."""
+        lat = np.ascontiguousarray(lattice9, dtype=np.float64).reshape(9)
+        pbc = np.ascontiguousarray(np.asarray(pbc3, dtype=bool).astype(np.int32))
+        _check(load_library().gap_potential_calc_device(self._h, int(N), C.c_void_p(d_pos_ptr), C.c_void_p(d_Z_ptr), _dp(lat), _ip(pbc),
+                                                        args_str.encode(), int(bool(want_grad)), C.c_void_p(d_packed_ptr),
+                                                        C.c_void_p(d_local_e_ptr) if d_local_e_ptr else None,
+                                                        C.c_void_p(d_local_virial_ptr) if d_local_virial_ptr else None,
+                                                        C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    @property
+    def n_coordinate(self):
+        return load_library().gap_potential_n_coordinate(self._h)
+
+    @property
+    def launch_count(self):
+        return load_library().gap_potential_launch_count(self._h)
+
+    def last_timings(self):
+        t = np.zeros(6)
+        load_library().gap_potential_last_timings(self._h, _dp(t))
+        return dict(zip(["connect", "soap_forward", "covariance", "soap_adjoint", "distance_2b", "total"], t))
+
+    def finalise(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            load_library().gap_potential_finalise(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.finalise()
+        except Exception:
+            pass

@@ -1,0 +1,325 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference's golden fixtures.
+
+Bars (BASELINE.json north_star): neighbour lists bit-exact (identical (i, j, shift) sets AND identical FP64 distances);
+energies within 1e-8 eV/atom, forces within 1e-6 eV/A, virials within 1e-6 eV, all FP64."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402
+from quip_b200 import Atoms, Potential, read_xyz  # noqa: E402
+from quip_b200 import synthetic as syn  # noqa: E402
+from quip_b200.gap_xml import write_gap_xml  # noqa: E402
+from tests.models import SI_SOAP, si_two_descriptor_model  # noqa: E402
+
+TOL_E_PER_ATOM = 1e-8
+TOL_F = 1e-6
+TOL_V = 1e-6
+
+
+@pytest.fixture(scope="module")
+def gap_xml_pot(golden):
+    return Potential("IP GAP", param_filename=os.path.join(golden, "GAP.xml"))
+
+
+@pytest.fixture(scope="module")
+def si_model(tmp_path_factory):
+    d = tmp_path_factory.mktemp("si_model")
+    xml = si_two_descriptor_model(str(d))
+    return Potential("IP GAP", param_filename=xml), orc.Model(xml), xml
+
+
+@pytest.fixture(scope="module")
+def si_frames(golden):
+    return read_xyz(os.path.join(golden, "Si.np1.xyz"))
+
+
+def canon(off, j, s, d):
+    i = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    key = np.lexsort((s[:, 2], s[:, 1], s[:, 0], j, i))
+    return np.stack([i[key], j[key], s[key, 0], s[key, 1], s[key, 2]], axis=1), d[key]
+
+
+def assert_same_list(pot, atoms, cutoff):
+    g = canon(*pot.calc_connect(atoms, cutoff))
+    o = canon(*orc.Connect(atoms, cutoff).arrays())
+    assert g[0].shape == o[0].shape, (g[0].shape, o[0].shape)
+    assert np.array_equal(g[0], o[0])
+    assert np.array_equal(g[1], o[1])  # bit-exact FP64 distances
+    return len(g[1])
+
+
+# ----------------------------------------------------------------------------------------------------
+# neighbour list
+# ----------------------------------------------------------------------------------------------------
+def test_neighbour_list_bit_exact_fixtures(gap_xml_pot, golden, si_frames):
+    n = assert_same_list(gap_xml_pot, read_xyz(os.path.join(golden, "gap_sample.xyz"), 0), 4.0)
+    assert n > 0
+    for a in si_frames:  # 1..96 atoms, triclinic cells smaller than the cutoff (many periodic images)
+        for rc in (4.0, 6.0):
+            assert_same_list(gap_xml_pot, a, rc)
+
+
+def test_neighbour_list_pbc_variants_and_offsets(gap_xml_pot, si_frames):
+    # tests/test_neighbour_list.py idea: every pbc combination, and invariance under lattice-vector offsets
+    a = si_frames[8]
+    for pbc in ([1, 1, 1], [1, 1, 0], [1, 0, 0], [0, 0, 0], [0, 1, 1], [0, 1, 0]):
+        b = Atoms(a.numbers, a.positions, a.cell, pbc)
+        assert_same_list(gap_xml_pot, b, 5.0)
+    rng = np.random.default_rng(5)
+    shifts = rng.integers(-3, 4, size=(len(a), 3))
+    moved = Atoms(a.numbers, a.positions + shifts @ a.cell, a.cell, True)
+    assert_same_list(gap_xml_pot, moved, 5.0)
+    off0 = gap_xml_pot.calc_connect(a, 5.0)[0]
+    off1 = gap_xml_pot.calc_connect(moved, 5.0)[0]
+    assert np.array_equal(off0, off1)
+
+
+def test_neighbour_list_edge_cases(gap_xml_pot, golden):
+    S = json.load(open(os.path.join(golden, "soap_reference_cases.json")))
+    for name in ("mono_3", "quad_3"):  # non-periodic triclinic
+        for d in S["datasets"][name]:
+            a = Atoms(d["numbers"], np.array(d["scaled_positions"]) @ np.array(d["cell"]), d["cell"], False)
+            assert_same_list(gap_xml_pot, a, 6.0)
+    one = Atoms([14], [[0.1, 0.2, 0.3]], np.eye(3) * 3.0, True)  # single atom, only self images
+    assert assert_same_list(gap_xml_pot, one, 5.0) > 0
+    assert assert_same_list(gap_xml_pot, Atoms([14], [[0.1, 0.2, 0.3]], np.eye(3) * 30.0, True), 5.0) == 0
+    off, j, s, d = gap_xml_pot.calc_connect(Atoms(np.zeros(0, dtype=np.int32), np.zeros((0, 3)), np.eye(3), True), 5.0)
+    assert len(off) == 1 and len(j) == 0
+
+
+def test_neighbour_list_config_A_size(gap_xml_pot):
+    a = syn.si_diamond(8, 8, 8)  # 4,096 atoms
+    n = assert_same_list(gap_xml_pot, a, 5.0)
+    assert 27.5 < n / len(a) < 28.5
+    b = syn.sic_zincblende(6)
+    assert_same_list(gap_xml_pot, b, 5.0)
+    slab = syn.si_slab(4, 4, 3, vacuum=20.0)
+    assert_same_list(gap_xml_pot, slab, 5.0)
+    assert_same_list(gap_xml_pot, Atoms(slab.numbers, slab.positions, slab.cell, [1, 1, 0]), 5.0)
+
+
+# ----------------------------------------------------------------------------------------------------
+# SOAP descriptor
+# ----------------------------------------------------------------------------------------------------
+def test_soap_vectors_vs_golden_and_oracle(si_model, si_frames, golden):
+    pot, om, _ = si_model
+    z = np.load(os.path.join(golden, "si_two_descriptors.npz"))
+    X = np.concatenate([pot.descriptor_calc(a, 1)[0] for a in si_frames])
+    assert X.shape == (439, 325)
+    assert np.abs(X[z["index_soap"] - 1] - z["sparsex_soap"]).max() < 1e-12  # reference fixture (tol 1e-8 there)
+    Xo = np.concatenate([orc.soap_descriptor(SI_SOAP, a)["data"] for a in si_frames])
+    assert np.abs(X - Xo).max() < 1e-12
+
+
+def multi_species_model(tmpdir, desc, datasets, M, seed, delta=1.3, zeta=4.0, extra=()):
+    X = np.concatenate([orc.soap_descriptor(desc, a)["data"] for a in datasets])
+    rng = np.random.default_rng(seed)
+    rows = rng.choice(len(X), size=min(M, len(X)), replace=False)
+    coord = {"descriptor": desc, "covariance_type": 2, "delta": delta, "zeta": zeta, "sparseX": X[rows],
+             "alpha": rng.normal(size=len(rows)), "sparseCutoff": rng.uniform(0.5, 1.0, size=len(rows))}
+    return write_gap_xml(os.path.join(tmpdir, "ms_%d.xml" % seed), [coord] + list(extra), e0={23: 0.1, 41: -0.2, 42: 0.3, 73: 0.4, 6: -1.0})
+
+
+def quad_datasets(golden, pbc):
+    S = json.load(open(os.path.join(golden, "soap_reference_cases.json")))
+    return [Atoms(d["numbers"], np.array(d["scaled_positions"]) @ np.array(d["cell"]), d["cell"], pbc) for d in S["datasets"]["quad_3"]]
+
+
+def test_soap_multispecies_descriptor(golden, tmp_path):
+    desc = "soap n_Z=4 n_species=4 Z={23 41 42 73} species_Z={23 41 42 73} n_max=4 l_max=2 cutoff=5 atom_sigma=0.4 cutoff_transition_width=0.5 central_weight=1"
+    for pbc in (False, True):
+        ds = quad_datasets(golden, pbc)
+        xml = multi_species_model(str(tmp_path), desc, ds, 8, seed=7 + pbc)
+        pot = Potential("", param_filename=xml)
+        for a in ds:
+            x, ci = pot.descriptor_calc(a, 0)
+            o = orc.soap_descriptor(desc, a)
+            assert np.array_equal(ci, o["ci"])
+            assert np.abs(x - o["data"]).max() < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------------
+# covariance stage
+# ----------------------------------------------------------------------------------------------------
+def test_gp_predict_vs_oracle(si_model, si_frames):
+    pot, om, _ = si_model
+    X = np.concatenate([orc.soap_descriptor(SI_SOAP, a)["data"] for a in si_frames[:9]])
+    e, g = pot.gp_predict(1, X)
+    eo, go = om.predict(1, X)
+    assert np.abs(e - eo).max() < 1e-10 * max(1.0, np.abs(eo).max())
+    assert np.abs(g - go).max() < 1e-10 * max(1.0, np.abs(go).max())
+
+
+# ----------------------------------------------------------------------------------------------------
+# full energy / force / virial
+# ----------------------------------------------------------------------------------------------------
+def check_efv(pot, om, atoms, connect_cutoff=None):
+    r = pot.calc(atoms, force=True, virial=True, local_energy=True, local_virial=True)
+    o = om.calc(atoms, local_energy=True, local_virial=True, connect_cutoff=connect_cutoff)
+    n = max(len(atoms), 1)
+    assert abs(r["energy"] - o["energy"]) / n < TOL_E_PER_ATOM, (r["energy"], o["energy"])
+    assert np.abs(r["local_energy"] - o["local_energy"]).max() < 1e-8
+    assert np.abs(r["force"] - o["force"]).max() < TOL_F
+    assert np.abs(r["virial"] - o["virial"]).max() < TOL_V
+    assert np.abs(r["local_virial"] - o["local_virial"]).max() < TOL_V
+    # energy-only call must agree with the gradient call (do_grad_descriptor = .false. path)
+    assert abs(pot.calc(atoms)["energy"] - r["energy"]) < 1e-9 * max(1.0, abs(r["energy"]))
+    return r, o
+
+
+def test_gap_xml_known_answer(gap_xml_pot, golden):
+    # tests/test_gappot.py:30-48
+    at = read_xyz(os.path.join(golden, "gap_sample.xyz"), 0)
+    assert gap_xml_pot.cutoff() == 4.0
+    om = orc.Model(os.path.join(golden, "GAP.xml"))
+    r, _ = check_efv(gap_xml_pot, om, at)
+    assert abs(r["energy"] - at.info["energy"]) < 1e-8
+    assert np.abs(r["force"] - at.arrays["force"]).max() < 1e-8
+    # ASE-calculator semantics (potential.py:281-288)
+    res = gap_xml_pot.calculate(at, ["energy", "forces", "stress"])
+    assert res["forces"].shape == (81, 3) and res["stress"].shape == (6,)
+    assert abs(res["stress"][0] + r["virial"][0, 0] / at.get_volume()) < 1e-12
+
+
+def test_h2_cell_energies(gap_xml_pot, golden):
+    # tests/test_potential_cell.py:30-54
+    h = json.load(open(os.path.join(golden, "h2_cell_energies.json")))
+    for c, e in zip(h["cell_sizes"], h["ref_energies"]):
+        a = Atoms(h["numbers"], h["positions"], [c, c, c], True)
+        assert abs(gap_xml_pot.calc(a)["energy"] - e) < 1e-8
+
+
+def test_si_two_descriptor_model_all_frames(si_model, si_frames):
+    # BASELINE config[0]: distance_2b + SOAP on Si.np1.xyz
+    pot, om, _ = si_model
+    assert pot.cutoff() == 6.0 and pot.n_coordinate == 2
+    for a in si_frames:
+        check_efv(pot, om, a)
+    # only_descriptor selects one coordinate (IPModel_GAP.f95:399-404); the two parts add up (minus the double e0)
+    a = si_frames[7]
+    e1 = pot.calc(a, args_str="only_descriptor=1")["energy"]
+    e2 = pot.calc(a, args_str="only_descriptor=2")["energy"]
+    e0 = len(a) * (-158.54496821 + 2.0)
+    assert abs((e1 - e0) + (e2 - e0) + e0 - pot.calc(a)["energy"]) < 1e-8
+
+
+def test_multispecies_soap_plus_2b_efv(golden, tmp_path):
+    desc = ("soap n_Z=2 n_species=4 Z={23 42} species_Z={23 41 42 73} n_max=5 l_max=3 cutoff=4.5 atom_sigma=0.45 "
+            "cutoff_transition_width=0.7 central_weight=0.8")
+    extra = [syn.random_2b_coordinate("distance_2b cutoff=5.0 covariance_type=ard_se delta=0.5 theta_uniform=1.0 Z1=23 Z2=41", 1.5, 5.0, M=12,
+                                      seed=3)]
+    for pbc in (True, False, [1, 0, 1]):
+        ds = quad_datasets(golden, pbc)
+        xml = multi_species_model(str(tmp_path), desc, ds, 10, seed=11, zeta=2.0, extra=extra)
+        pot, om = Potential("", param_filename=xml), orc.Model(xml)
+        for a in ds:
+            check_efv(pot, om, a)
+
+
+def test_species_outside_map_and_unnormalised(golden, tmp_path):
+    # neighbours whose species is not in species_Z are ignored (descriptors.f95:8194-8195); normalise=F; zeta non-integer
+    desc = "soap n_Z=1 n_species=2 Z=23 species_Z={23 73} n_max=4 l_max=4 cutoff=5.0 atom_sigma=0.5 normalise=F covariance_sigma0=0.1"
+    ds = quad_datasets(golden, True)
+    xml = multi_species_model(str(tmp_path), desc, ds, 6, seed=13, zeta=2.5, delta=0.2)
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    for a in ds:
+        check_efv(pot, om, a)
+
+
+def test_config_A_reduced_vs_oracle(tmp_path):
+    # same shape as BASELINE config A (n_max=8 l_max=8 cutoff 5, zeta=4) at a size the oracle finishes in seconds
+    atoms, xml = syn.build_config_A(str(tmp_path), lambda desc, at: orc.soap_descriptor(desc, at)["data"], n_cells=3, M=150, seed=1)
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    r, o = check_efv(pot, om, atoms)
+    assert np.abs(r["force"]).max() > 1e-3  # a non-trivial configuration
+
+
+def test_partition_partials_sum_to_total(si_model, si_frames):
+    # the reference's MPI atom mask + Allreduce (descriptors.f95:1036-1051, IPModel_GAP.f95:538-556)
+    pot, om, xml = si_model
+    a = si_frames[8]
+    full = pot.calc(a, force=True, virial=True, local_energy=True)
+    parts = []
+    for r in range(3):
+        p = Potential("IP GAP", param_filename=xml)
+        p.set_partition(r, 3)
+        parts.append(p.calc(a, force=True, virial=True, local_energy=True))
+    for k, tol in (("energy", 1e-9), ("force", 1e-10), ("virial", 1e-9), ("local_energy", 1e-10)):
+        tot = sum(np.asarray(p[k]) for p in parts)
+        assert np.abs(tot - np.asarray(full[k])).max() < tol * max(1.0, np.abs(np.asarray(full[k])).max())
+
+
+def test_device_resident_entry_point(si_model, si_frames):
+    import torch
+
+    pot, om, _ = si_model
+    a = si_frames[8]
+    ref = pot.calc(a, force=True, virial=True)
+    pos = torch.tensor(a.positions, dtype=torch.float64, device="cuda")
+    Z = torch.tensor(a.numbers, dtype=torch.int32, device="cuda")
+    packed = torch.empty(10 + 3 * len(a), dtype=torch.float64, device="cuda")
+    pot.calc_device(len(a), pos.data_ptr(), Z.data_ptr(), a.lattice_fortran, a.pbc, packed.data_ptr(), want_grad=True,
+                    stream_ptr=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    out = packed.cpu().numpy()
+    assert abs(out[0] - ref["energy"]) < 1e-9 * abs(ref["energy"])
+    assert np.abs(out[1:10].reshape(3, 3, order="F") - ref["virial"]).max() < 1e-9
+    assert np.abs(out[10:].reshape(-1, 3) - ref["force"]).max() < 1e-9
+
+
+# ----------------------------------------------------------------------------------------------------
+# full-size config A: size-independent properties
+# ----------------------------------------------------------------------------------------------------
+def test_config_A_full_size_properties(tmp_path):
+    boot = syn.bootstrap_xml(str(tmp_path / "boot.xml"), [(syn.SOAP_A, syn.soap_dimension(8, 8))])
+    bp = Potential("", param_filename=boot)
+    atoms, xml = syn.build_config_A(str(tmp_path), lambda desc, at: bp.descriptor_calc(at, 0)[0], n_cells=8, M=2000, seed=1)
+    assert len(atoms) == 4096
+    pot = Potential("", param_filename=xml)
+    r = pot.calc(atoms, force=True, virial=True, local_energy=True, local_virial=True)
+    assert abs(r["local_energy"].sum() - r["energy"]) < 1e-7
+    assert np.abs(r["force"].sum(axis=0)).max() < 1e-8          # translation invariance
+    assert np.abs(r["virial"] - r["virial"].T).max() < 1e-7     # rotation invariance
+    assert np.abs(r["local_virial"].sum(axis=0).reshape(3, 3, order="F") - r["virial"]).max() < 1e-8
+    # central finite difference of the energy along a random displacement direction (Potential.f95:1374 idea)
+    rng = np.random.default_rng(0)
+    dirn = rng.normal(size=atoms.positions.shape)
+    dirn /= np.linalg.norm(dirn)
+    h = 1e-4
+    ep = pot.calc(Atoms(atoms.numbers, atoms.positions + h * dirn, atoms.cell, True))["energy"]
+    em = pot.calc(Atoms(atoms.numbers, atoms.positions - h * dirn, atoms.cell, True))["energy"]
+    assert abs((ep - em) / (2 * h) + np.sum(r["force"] * dirn)) < 1e-6
+    # strain derivative = virial (dE/d eps_ab = -virial_ab)
+    eps = 1e-5
+    for (aa, bb) in ((0, 0), (1, 2)):
+        F = np.eye(3)
+        F[aa, bb] += eps
+        Fm = np.eye(3)
+        Fm[aa, bb] -= eps
+        ep = pot.calc(Atoms(atoms.numbers, atoms.positions @ F.T, atoms.cell @ F.T, True))["energy"]
+        em = pot.calc(Atoms(atoms.numbers, atoms.positions @ Fm.T, atoms.cell @ Fm.T, True))["energy"]
+        assert abs((ep - em) / (2 * eps) + r["virial"][aa, bb]) < 1e-5
+    # oracle on a bounded sample of centres of the SAME configuration: partial sums must agree
+    om = orc.Model(xml)
+    first, last = 1000, 1064
+    o = om.calc(atoms, first=first, last=last, local_energy=True)
+    p = Potential("", param_filename=xml)
+    # the library partitions in equal blocks: 4096/64 = 64 atoms per block -> block index 1000/64 is not integral;
+    # compare local energies of the sample instead (they only depend on the centre)
+    assert np.abs(r["local_energy"][first:last] - o["local_energy"][first:last]).max() < 1e-8
+
+
+def test_error_reporting(golden):
+    with pytest.raises(RuntimeError, match="could not initialise GAP potential"):
+        Potential("IP GAP label=nonexistent", param_filename=os.path.join(golden, "GAP.xml"))
+    pot = Potential("IP GAP", param_filename=os.path.join(golden, "GAP.xml"))
+    at = read_xyz(os.path.join(golden, "gap_sample.xyz"), 0)
+    with pytest.raises(RuntimeError, match="not yet implemented"):  # IPModel_GAP.f95:348-350
+        pot.calc(at, args_str="E_scale=2.0")
+    with pytest.raises(RuntimeError, match="singular lattice|zero-length"):
+        pot.calc(Atoms(at.numbers, at.positions, np.zeros((3, 3)), True))

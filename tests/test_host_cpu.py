@@ -1,0 +1,135 @@
+"""CPU-side checks of the product's host logic (no compute, no GPU): the C ABI exports what include/gap_b200.h
+declares, the C++ model loader agrees with the independent Python reading used by the oracle, the XML writer
+round-trips, and the reference's error conditions are reported."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from quip_b200 import potential as P
+from quip_b200.gap_xml import write_gap_xml
+from tests.models import si_two_descriptor_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def parse_describe(text):
+    out = {"coordinate": {}, "soap": {}, "distance_2b": {}, "vec": []}
+    cur = None
+    for line in text.splitlines():
+        t = line.split()
+        if t[0] in ("coordinate", "soap", "distance_2b"):
+            cur = int(t[1])
+            out[t[0]][cur] = {t[k]: float(t[k + 1]) for k in range(2, len(t) - 1, 2)}
+        elif t[0] in ("species_Z", "Z", "r_basis", "transform_basis", "cholesky_overlap"):
+            out["soap"][cur][t[0]] = np.array([float(v) for v in t[1:]])
+        elif t[0] == "e0":
+            out["e0"] = {int(a.split(":")[0]): float(a.split(":")[1]) for a in t[1:]}
+        else:
+            out[t[0]] = t[1] if len(t) > 1 else ""
+    return out
+
+
+def test_abi_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "gap_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gap_\w+)\s*\(", hdr))
+    assert declared == set(P.ABI), declared ^ set(P.ABI)
+    lib = P.load_library()
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_initialise_fails_loudly_without_gpu(golden):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        P.Potential("IP GAP", param_filename=os.path.join(golden, "GAP.xml"))
+
+
+def test_loader_matches_independent_reader(golden, tmp_path):
+    for xml in (os.path.join(golden, "GAP.xml"), si_two_descriptor_model(str(tmp_path)),
+                si_two_descriptor_model(str(tmp_path / "inline"), separate_files=False) if (tmp_path / "inline").mkdir() is None else None):
+        d = parse_describe(P.model_describe(param_filename=xml))
+        m = orc.load_gap_xml(xml)
+        assert d["label"] == m["label"]
+        assert int(d["xml_version"]) == m["xml_version"]
+        assert int(d["n_coordinate"]) == len(m["coordinates"])
+        for z, v in d["e0"].items():
+            assert m["e0"][z] == v
+        assert np.count_nonzero(m["e0"]) == len(d["e0"])
+        for i, co in enumerate(m["coordinates"]):
+            c = d["coordinate"][i]
+            assert c["d"] == co["d"] and c["M"] == co["M"] and c["covariance_type"] == co["covariance_type"]
+            assert c["delta"] == co["delta"] and c["f0"] == co["f0"]
+            w = (np.arange(co["sparseX"].size) % 7 + 1.0)
+            assert abs(c["sparseX_wsum"] - float(np.sum(co["sparseX"].reshape(-1, order="F") * w))) <= 1e-9 * abs(c["sparseX_wsum"])
+            assert abs(c["alpha_sum"] - co["alpha"].sum()) <= 1e-9 * max(1.0, abs(c["alpha_sum"]))
+            assert abs(c["sparseCutoff_sum"] - co["sparseCutoff"].sum()) < 1e-12
+            if co["covariance_type"] == 2:
+                assert c["zeta"] == co["zeta"]
+                sp = orc.soap_params(co["descriptor"] + " xml_version=%d" % m["xml_version"], calc_xml_version=m["xml_version"])
+                s = d["soap"][i]
+                for k in ("l_max", "n_max", "n_species", "n_Z"):
+                    assert s[k] == sp[k]
+                assert bool(s["cras"]) == sp["central_reference_all_species"] and bool(s["two_lp1"]) == sp["do_two_l_plus_one"]
+                r, T, ch = orc.soap_basis(sp)
+                assert np.abs(s["r_basis"] - r).max() < 1e-14
+                assert np.abs(s["transform_basis"] - T.reshape(-1, order="F")).max() < 1e-11 * np.abs(T).max()
+                assert np.abs(s["cholesky_overlap"] - ch.reshape(-1, order="F")).max() < 1e-13
+            else:
+                assert c["theta0"] == co["theta"][0]
+                a = orc.parse_args(co["descriptor"])
+                assert d["distance_2b"][i]["Z1"] == int(a["Z1"]) and d["distance_2b"][i]["Z2"] == int(a["Z2"])
+                assert c["cutoff"] == float(a["cutoff"])
+
+
+def test_writer_roundtrip_sliced_inline(tmp_path):
+    rng = np.random.default_rng(0)
+    X = rng.random((7, 51))
+    c = {"descriptor": "soap cutoff=3.0 l_max=4 n_max=4 atom_sigma=0.5 n_Z=1 Z=6 n_species=1 species_Z={6}", "covariance_type": 2,
+         "delta": 0.7, "zeta": 2.0, "sparseX": X, "alpha": rng.normal(size=7), "sparseCutoff": rng.random(7)}
+    for sep in (True, False):
+        xml = write_gap_xml(str(tmp_path / ("m%d.xml" % sep)), [c], e0={6: -1.5}, separate_files=sep)
+        m = orc.load_gap_xml(xml)
+        assert np.array_equal(m["coordinates"][0]["sparseX"].T, X)
+        assert np.array_equal(m["coordinates"][0]["alpha"], c["alpha"])
+        d = parse_describe(P.model_describe(param_filename=xml))
+        w = (np.arange(X.size) % 7 + 1.0)
+        assert abs(d["coordinate"][0]["sparseX_wsum"] - float(np.sum(X.reshape(-1) * w))) < 1e-10
+        assert d["e0"] == {6: -1.5}
+
+
+def test_reference_error_conditions(golden, tmp_path):
+    xml = open(os.path.join(golden, "GAP.xml")).read()
+    with pytest.raises(RuntimeError, match="could not initialise GAP potential"):  # IPModel_GAP.f95:939-940
+        P.model_describe(param_str=xml, args_str="IP GAP label=nonexistent", base_dir=golden)
+    with pytest.raises(RuntimeError, match="does not exist"):  # gp_predict.f95:4719
+        P.model_describe(param_str=xml, args_str="IP GAP", base_dir=str(tmp_path))
+    with pytest.raises(RuntimeError, match="IP GAP"):
+        P.model_describe(param_str=xml, args_str="IP SW", base_dir=golden)
+    bad = si_two_descriptor_model(str(tmp_path))
+    side = [f for f in os.listdir(tmp_path) if "sparseX" in f][0]
+    with open(tmp_path / side, "a") as fh:
+        fh.write("1.0\n")
+    with pytest.raises(RuntimeError, match="md5 check sum failed"):  # gp_predict.f95:4736-4739
+        P.model_describe(param_filename=bad)
+    unfitted = xml.replace('n_coordinate="3"', 'n_coordinate="3" fitted="F"')
+    with pytest.raises(RuntimeError, match="has not been fitted"):  # IPModel_GAP.f95:179
+        P.model_describe(param_str=unfitted, base_dir=golden)
+    other = xml.replace("distance_2b cutoff=4.0", "angle_3b cutoff=4.0", 1)
+    with pytest.raises(RuntimeError, match="not supported"):
+        P.model_describe(param_str=other, base_dir=golden)
+
+
+def test_key_value_grammar_agrees():
+    # ParamReader.f95:393-518 grouping rules, product (via describe of a soap string) vs oracle splitter
+    s = "soap cutoff=4.0 l_max=2 n_max=3 atom_sigma=0.5 n_Z=2 Z={1 8} n_species=2 species_Z={8 1} normalise=F"
+    assert orc.split_fields(s) == ["soap", "cutoff=4.0", "l_max=2", "n_max=3", "atom_sigma=0.5", "n_Z=2", "Z=1 8", "n_species=2",
+                                   "species_Z=8 1", "normalise=F"]
+    sp = orc.soap_params(s)
+    assert sp["Z"] == [1, 8] and sp["species_Z"] == [8, 1] and not sp["normalise"] and not sp["central_reference_all_species"]
