@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- GAP-SOAP energy + force + virial throughput (atoms/s) of the B200 path, with its roofline and the CPU
+baseline timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md 8(d) "A"): Si diamond, 8x8x8 cubic cells = 4,096 atoms per GPU, rattled
+0.05 A, SOAP n_max=8 l_max=8 cutoff 5 A, zeta=4, 2,000 random-init sparse points; one step = one full E+F+V evaluation
+INCLUDING the neighbour-list build.  At N GPUs the cell is 8 x 8 x 8N (4,096 N atoms, weak scaling): positions are
+replicated, every rank evaluates its block of centres, and the one collective is the all-reduce of [E | virial | F].
+
+value  : inputs resident in HBM, timed with CUDA events per step (L2 flushed between steps), max over ranks.
+e2e    : through the host-pointer API (pinned host buffers, H2D and D2H inside the timed region), wall clock.
+roofline: the dominant kernel of the step (by CUDA-event time on the launching stream).
+cpu_baseline / --impl reference: the CPU restatement of QUIP's algorithm (oracle/, OpenMP over atoms) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "GAP-SOAP energy+force+virial atoms/sec (incl. neighbour-list build)"
+UNIT = "atoms/s"
+N_MAX, L_MAX, M_SPARSE, CELLS = 8, 8, 2000, 8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j.get("hbm_gbs", 6650.0), "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(tmp, n_gpus, descriptor_fn):
+    """Config A (x n_gpus along z for weak scaling) + its random-init model, written as a reference-format GAP XML."""
+    from quip_b200 import synthetic as syn
+    from quip_b200.gap_xml import write_gap_xml
+
+    atoms = syn.si_diamond(CELLS, CELLS, CELLS * n_gpus, seed=1)
+    src = syn.si_diamond(CELLS, CELLS, CELLS, rattle=0.08, seed=101, strain=0.01)
+    X = descriptor_fn(syn.SOAP_A, src)
+    coord = syn.random_soap_coordinate(syn.SOAP_A, X, M_SPARSE, delta=1.0, zeta=4.0, seed=101)
+    xml = write_gap_xml(os.path.join(tmp, "gap_config_A.xml"), [coord], e0={14: -158.54496821}, label="GAP_b200_config_A")
+    return atoms, xml
+
+
+def workload_name(n_gpus):
+    return ("Si diamond %d atoms (8x8x%d cells, rattled 0.05 A), SOAP n_max=8 l_max=8 cutoff=5.0 zeta=4, 2000 sparse points, "
+            "single-step E/F/V incl. neighbour list" % (4096 * n_gpus, 8 * n_gpus))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle = restatement of the reference's algorithm; the reference itself is Fortran and cannot be built here)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample(om, atoms, n_centres):
+    t = time.perf_counter()
+    om.calc(atoms, force=True, virial=True, first=0, last=n_centres)
+    return time.perf_counter() - t
+
+
+def cpu_baseline_leg(xml, atoms, budget_s=15.0):
+    from oracle import oracle as orc
+
+    om = orc.Model(xml)
+    cores = int(orc.lib().orc_num_threads())
+    n = min(len(atoms), 256)
+    dt = cpu_sample(om, atoms, n)
+    n2 = int(min(len(atoms), max(n, n / dt * budget_s)))
+    dt2 = cpu_sample(om, atoms, n2)
+    return {"value": n2 / dt2, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of %d centres of the same configuration (full neighbour list of all atoms built serially as in calc_connect), "
+                      "%.1f s, OpenMP over atoms with %d threads" % (n2, len(atoms), dt2, cores)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: the Fortran cannot be compiled in this image) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    orc.build()
+    n_gpus = args.gpus
+    with tempfile.TemporaryDirectory() as tmp:
+        atoms, xml = build_workload(tmp, n_gpus, lambda desc, at: orc.soap_descriptor(desc, at)["data"])
+        om = orc.Model(xml)
+        cores = int(orc.lib().orc_num_threads())
+        n = min(len(atoms), 128)
+        rate = n / cpu_sample(om, atoms, n)
+        # each step = a bounded sample of centres sized so that warmup + steps take about two minutes at most
+        per_step = int(max(64, min(len(atoms), rate * 120.0 / max(1, args.steps + args.warmup))))
+        for _ in range(args.warmup):
+            cpu_sample(om, atoms, per_step)
+        times = [cpu_sample(om, atoms, per_step) for _ in range(args.steps)]
+    tot = float(np.sum(times))
+    value = per_step * args.steps / tot
+    sample = "%d of %d centres per step, full neighbour list rebuilt each step, %d OpenMP threads" % (per_step, len(atoms), cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(n_gpus), "parallelism": "cpu-openmp-%d" % cores},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "QUIP's Fortran GAP path cannot be compiled in this image (no Fortran compiler); this is oracle/gap_oracle.c, a C/OpenMP "
+                    "restatement with the reference's loop structure (serial linked-cell list, forward-mode grad_data, per-atom BLAS-2)"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def measure_fp64_peak(torch, dev):
+    """cuBLAS DGEMM 4096^3, best of 5: the FP64 (DMMA) yardstick MEASURED_PEAKS.json does not carry."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    if args.gpus != world and rank == 0:
+        print("bench.py: --gpus %d but WORLD_SIZE=%d; using %d" % (args.gpus, world, world), file=sys.stderr)
+
+    from quip_b200 import Potential, ShardedPotential
+    from quip_b200 import synthetic as syn
+
+    tmp = tempfile.mkdtemp(prefix="gapb200_bench_r%d_" % rank)
+    boot = syn.bootstrap_xml(os.path.join(tmp, "boot.xml"), [(syn.SOAP_A, syn.soap_dimension(N_MAX, L_MAX))])
+    bp = Potential("", param_filename=boot, device=local)
+    atoms, xml = build_workload(tmp, n_gpus, lambda desc, at: bp.descriptor_calc(at, 0)[0])
+    bp.finalise()
+    N = len(atoms)
+    sp = ShardedPotential("", param_filename=xml, device=local, rank=rank, world_size=world)
+    pot = sp.pot
+    lat = atoms.lattice_fortran
+    pbc = atoms.pbc
+    d_pos = torch.tensor(atoms.positions, dtype=torch.float64, device=dev)
+    d_Z = torch.tensor(atoms.numbers, dtype=torch.int32, device=dev)
+    d_packed = torch.empty(10 + 3 * N, dtype=torch.float64, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.int8, device=dev)  # > 126 MB L2
+
+    fp64_peak = measure_fp64_peak(torch, dev) if rank == 0 else 0.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        sp.calc_resident(N, d_pos, d_Z, lat, pbc, d_packed, want_grad=True)
+
+    # ---- value: HBM-resident inputs, CUDA events per step, L2 flushed between steps ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = pot.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    stage_sum = {}
+    barrier()
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step_resident()
+        ev[k][1].record()
+        for name, ms in pot.last_timings().items():  # waits for this step's last kernel; per-stage CUDA events on the same stream
+            stage_sum[name] = stage_sum.get(name, 0.0) + ms
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = pot.launch_count - launches0
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = N / (ms_per_step * 1e-3)
+    result = d_packed[:10].cpu().numpy()
+
+    # ---- e2e: host-pointer API, pinned host buffers, H2D + D2H inside the timed region, wall clock ----
+    for _ in range(3):
+        r = sp.calc(atoms, force=True, virial=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = sp.calc(atoms, force=True, virial=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = N * args.steps / float(t.item())
+    assert abs(r["energy"] - result[0]) <= 1e-9 * abs(result[0]), (r["energy"], result[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per launch, averaged over the timed steps) ----
+    pk = peaks()
+    st = {k: v / args.steps for k, v in stage_sum.items()}
+    nc = N // world  # centres of this rank
+    d = syn.soap_dimension(N_MAX, L_MAX)
+    nn = 28.0
+    nlmK1 = (L_MAX + 1) ** 2 * N_MAX
+    kernels = {
+        # FP64 tensor-core GEMMs: 2 d M flops per centre each (F_cov = 4 d M per atom for the pair)
+        "cov_gemm1": {"bound": "tensor", "work": 2.0 * d * M_SPARSE * nc, "unit": "TFLOP/s"},
+        "cov_gemm2": {"bound": "tensor", "work": 2.0 * d * M_SPARSE * nc, "unit": "TFLOP/s"},
+        # HBM-side algorithmic bytes per centre: CSR read (8 B / entry) + pos/Z of the shell + x, X_lm, |p| written (forward);
+        # CSR + x + g + X_lm read, forces written (adjoint)
+        "soap_forward": {"bound": "hbm", "work": nc * (8.0 * nn + 28.0 * nn + 8.0 * (d + nlmK1 + 1)), "unit": "GB/s"},
+        "soap_adjoint": {"bound": "hbm", "work": nc * (8.0 * nn + 28.0 * nn + 8.0 * (2 * d + nlmK1 + 1) + 24.0 * (nn + 1)), "unit": "GB/s"},
+        "connect": {"bound": "hbm", "work": N * (24.0 + 4.0) * 2 + nc * nn * 8.0, "unit": "GB/s"},
+    }
+    dom = max(kernels, key=lambda k: st.get(k, 0.0))
+    kd = kernels[dom]
+    secs = st[dom] * 1e-3
+    if kd["bound"] == "tensor":
+        achieved, peak, peak_src = kd["work"] / secs / 1e12, fp64_peak, "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"
+    else:
+        achieved, peak, peak_src = kd["work"] / secs / 1e9, pk["hbm_gbs"], pk["source"]
+    roofline = {"kernel": dom, "bound": kd["bound"], "achieved": achieved, "peak": peak, "unit": kd["unit"], "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "ms_per_launch": st[dom],
+                "stage_ms": {k: round(v, 4) for k, v in st.items()}, "fp64_dgemm_tflops_measured": fp64_peak,
+                "cov_pair_tflops": 4.0 * d * M_SPARSE * nc / ((st["cov_gemm1"] + st["cov_gemm2"]) * 1e-3) / 1e12}
+
+    cpu = cpu_baseline_leg(xml, atoms) if (world == 1 and not args.no_cpu_baseline) else None
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n_gpus), "atoms": N, "atoms_per_gpu": N // world, "sparse_points": M_SPARSE, "descriptor_dim": d,
+                       "parallelism": "centre-block x%d, positions replicated, one all-reduce of [E|virial|F]" % world,
+                       "l2": "flushed between timed steps (512 MiB memset)", "timing": "CUDA events per step on the launching stream, max over ranks"},
+            "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 28 * N, "d2h_bytes_per_step": 8 * (10 + 3 * N)},
+            "gpu_launches": int(launches), "roofline": roofline, "wall_s_timed_region": t_wall,
+            "energy_eV": float(result[0])}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

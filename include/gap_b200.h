@@ -95,9 +95,10 @@ int gap_gp_predict(gap_potential* pot, int i_coord, int n, const double* x, doub
 int gap_potential_n_coordinate(const gap_potential* pot);
 /* number of CUDA kernels this handle has launched since initialise */
 long gap_potential_launch_count(const gap_potential* pot);
-/* device milliseconds of the last calc, by stage: [0] connect [1] soap forward [2] covariance [3] soap adjoint
- * [4] distance_2b [5] whole calc (CUDA events on the handle's stream; valid after gap_potential_calc) */
-int gap_potential_last_timings(const gap_potential* pot, double* ms6);
+/* device milliseconds of the last calc, by stage: [0] connect [1] soap forward [2] covariance GEMM-1 [3] covariance
+ * GEMM-2 [4] soap adjoint + scatter [5] distance_2b [6] everything else (centre selection, memsets, energy rows,
+ * totals) [7] whole calc.  CUDA events on the stream the calc was enqueued on; waits for the last calc. */
+int gap_potential_last_timings(gap_potential* pot, double* ms8);
 
 /* Host-only: parse a model exactly as initialise would (XML + descriptor strings + SOAP radial-basis set-up) and
  * write a text description with all derived numbers (%.17g) into buf.  Needs no GPU; used to check the loader. */

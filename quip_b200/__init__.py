@@ -5,4 +5,4 @@ into ``libgapb200.so``) and the host-side mirror of the reference's Python inter
 ext-XYZ reader, GAP XML writer, synthetic configurations).  There is no CPU fallback.
 """
 from .atoms import Atoms, read_xyz  # noqa: F401
-from .potential import Potential, load_library  # noqa: F401
+from .potential import Potential, ShardedPotential, load_library  # noqa: F401

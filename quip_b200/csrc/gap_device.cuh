@@ -89,9 +89,11 @@ struct NeighbourWork {  // device scratch owned by the potential handle; sized f
 size_t neighbour_cub_bytes(int N, int ncell);
 void launch_frac_minmax(const double* pos, int N, const double* g9_dev_unused, const CellGrid& grid, double* minmax6, cudaStream_t st, int* launches);
 void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell, NeighbourWork& w, cudaStream_t st, int* launches);
-void launch_neigh_count(const double* pos, int N, const CellGrid& grid, NeighbourWork& w, int* nbr_off, cudaStream_t st, int* launches);
-void launch_neigh_fill(const double* pos, int N, const CellGrid& grid, NeighbourWork& w, const int* nbr_off, int* nbr_j, int* nbr_s,
-                       double* nbr_d, cudaStream_t st, int* launches);
+// rows are built only for the centres [first, last) (the partition of this handle); other rows are empty
+void launch_neigh_count(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, cudaStream_t st,
+                        int* launches);
+void launch_neigh_fill(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, const int* nbr_off, int* nbr_j,
+                       int* nbr_s, double* nbr_d, cudaStream_t st, int* launches);
 
 // ---- soap.cu -------------------------------------------------------------------------------
 void launch_select_centres(const int* Z, int first, int last, const SoapDev* sp, int* flags, cudaStream_t st, int* launches);

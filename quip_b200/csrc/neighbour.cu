@@ -98,13 +98,17 @@ __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __res
 __device__ __forceinline__ int floor_div(int a, int n) { return (a >= 0) ? a / n : -((-a + n - 1) / n); }
 
 template <bool FILL>
-__global__ void k_neigh(int N, CellGrid grid, const int* __restrict__ sort_idx, const int* __restrict__ sort_keys,
+__global__ void k_neigh(int N, int first, int last, CellGrid grid, const int* __restrict__ sort_idx, const int* __restrict__ sort_keys,
                         const double* __restrict__ spos, const int* __restrict__ smshift, const int* __restrict__ cell_start,
                         int* __restrict__ nn, const int* __restrict__ nbr_off, int* __restrict__ nbr_j, int* __restrict__ nbr_s,
                         double* __restrict__ nbr_d) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
   const int i = sort_idx[p];
+  if (i < first || i >= last) {  // not a centre of this partition (descriptor_atomic_MPI_setup mask): empty row
+    if (!FILL) nn[i] = 0;
+    return;
+  }
   const int cell = sort_keys[p];
   int c0 = cell % grid.n[0], c1 = (cell / grid.n[0]) % grid.n[1], c2 = cell / (grid.n[0] * grid.n[1]);
   double pi[3] = {spos[3 * (size_t)p], spos[3 * (size_t)p + 1], spos[3 * (size_t)p + 2]};
@@ -183,10 +187,11 @@ void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell,
   *launches += 4;
 }
 
-void launch_neigh_count(const double* pos, int N, const CellGrid& grid, NeighbourWork& w, int* nbr_off, cudaStream_t st, int* launches) {
+void launch_neigh_count(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, cudaStream_t st,
+                        int* launches) {
   (void)pos;
   int nb = (N + 127) / 128;
-  k_neigh<false><<<nb, 128, 0, st>>>(N, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nullptr, nullptr, nullptr,
+  k_neigh<false><<<nb, 128, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nullptr, nullptr, nullptr,
                                      nullptr);
   cudaMemsetAsync(w.nn + N, 0, sizeof(int), st);
   size_t bytes = w.cub_bytes;
@@ -194,11 +199,11 @@ void launch_neigh_count(const double* pos, int N, const CellGrid& grid, Neighbou
   *launches += 2;
 }
 
-void launch_neigh_fill(const double* pos, int N, const CellGrid& grid, NeighbourWork& w, const int* nbr_off, int* nbr_j, int* nbr_s,
-                       double* nbr_d, cudaStream_t st, int* launches) {
+void launch_neigh_fill(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, const int* nbr_off, int* nbr_j,
+                       int* nbr_s, double* nbr_d, cudaStream_t st, int* launches) {
   (void)pos;
   int nb = (N + 127) / 128;
-  k_neigh<true><<<nb, 128, 0, st>>>(N, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nbr_off, nbr_j, nbr_s, nbr_d);
+  k_neigh<true><<<nb, 128, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nbr_off, nbr_j, nbr_s, nbr_d);
   *launches += 1;
 }
 

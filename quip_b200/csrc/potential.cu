@@ -83,7 +83,7 @@ struct gap_potential {
   double* d_e0 = nullptr;
   int rank = 0, n_ranks = 1;
   long launches = 0;
-  double last_ms[6] = {0, 0, 0, 0, 0, 0};
+  double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   // neighbour list state
   NeighbourWork nw;
@@ -143,6 +143,9 @@ __global__ void k_iota(int* p, int n) {
   if (i < n) p[i] = i;
 }
 
+// stage slots of gap_potential_last_timings
+enum { ST_CONNECT = 0, ST_SOAP_FWD = 1, ST_COV_GEMM1 = 2, ST_COV_GEMM2 = 3, ST_SOAP_ADJ = 4, ST_PAIR2B = 5, ST_OTHER = 6, ST_TOTAL = 7 };
+
 void mark(gap_potential* P, cudaStream_t st, int stage) {
   if (P->ev_used == P->ev.size()) {
     cudaEvent_t e;
@@ -161,11 +164,11 @@ void collect_timings(gap_potential* P) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, P->ev[k - 1], P->ev[k]) == cudaSuccess) {
       int st = P->ev_stage[k];
-      if (st >= 0 && st < 5) P->last_ms[st] += ms;
+      if (st >= 0 && st < 7) P->last_ms[st] += ms;
     }
   }
   float tot = 0.f;
-  if (cudaEventElapsedTime(&tot, P->ev[0], P->ev[P->ev_used - 1]) == cudaSuccess) P->last_ms[5] = tot;
+  if (cudaEventElapsedTime(&tot, P->ev[0], P->ev[P->ev_used - 1]) == cudaSuccess) P->last_ms[7] = tot;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -188,8 +191,8 @@ void inv3(const double* a, double* g) {  // column-major both
   g[2 + 3 * 2] = (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0)) / det;
 }
 
-void build_connect(gap_potential* P, int N, const double* d_pos, const double* lattice, const int* pbc, double cutoff, bool want_dist,
-                   cudaStream_t st) {
+void build_connect(gap_potential* P, int N, int first, int last, const double* d_pos, const double* lattice, const int* pbc, double cutoff,
+                   bool want_dist, cudaStream_t st) {
   if (N < 0) throw GapError("calc_connect: negative number of atoms");
   if (cutoff < 0.0) throw GapError("calc_connect: Negative cutoff radius " + std::to_string(cutoff));  // Connection.f95:1069
   P->conn_N = N;
@@ -306,7 +309,7 @@ void build_connect(gap_potential* P, int N, const double* d_pos, const double* l
   P->b_cub.ensure(cb); w.cub_tmp = P->b_cub.p; w.cub_bytes = P->b_cub.cap;
 
   launch_bin_atoms(d_pos, N, grid, ncell, w, st, &launches);
-  launch_neigh_count(d_pos, N, grid, w, P->b_off.as<int>(), st, &launches);
+  launch_neigh_count(d_pos, N, first, last, grid, w, P->b_off.as<int>(), st, &launches);
   int nnz = 0;
   CUDA_OK(cudaMemcpyAsync(&nnz, P->b_off.as<int>() + N, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
@@ -315,7 +318,7 @@ void build_connect(gap_potential* P, int N, const double* d_pos, const double* l
   P->b_j.ensure(sizeof(int) * (size_t)(nnz + 1));
   P->b_s.ensure(sizeof(int) * (size_t)(nnz + 1));
   if (want_dist) P->b_d.ensure(sizeof(double) * (size_t)(nnz + 1));
-  launch_neigh_fill(d_pos, N, grid, w, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), want_dist ? P->b_d.as<double>() : nullptr, st,
+  launch_neigh_fill(d_pos, N, first, last, grid, w, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), want_dist ? P->b_d.as<double>() : nullptr, st,
                     &launches);
   P->launches += launches;
   CUDA_OK(cudaGetLastError());
@@ -508,9 +511,12 @@ void covariance_stage(gap_potential* P, const CoordDev& cd, int nc, bool want_gr
     int rows = std::min(chunk, nc_pad - r0);
     launch_cov_gemm1(P->b_x.as<double>() + (size_t)r0 * cd.d_pad, cd.d_pad, cd.sp_rows, cd.d_pad, rows, cd.M, cd.M_pad, cd.d_pad, cd.alpha, cd.scut,
                      cd.cp, P->b_acoef.as<double>(), cd.M_pad, P->b_epart.as<double>() + (size_t)r0 * n_tiles_n, n_tiles_n, st, &launches);
-    if (want_grad)
+    mark(P, st, ST_COV_GEMM1);
+    if (want_grad) {
       launch_cov_gemm2(P->b_acoef.as<double>(), cd.M_pad, cd.st_rows, cd.M_pad, rows, cd.dn_pad, cd.M_pad, P->b_gvec.as<double>() + (size_t)r0 * cd.dn_pad,
                        cd.dn_pad, st, &launches);
+      mark(P, st, ST_COV_GEMM2);
+    }
   }
   P->launches += launches;
 }
@@ -523,8 +529,8 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   const int first = (int)((long long)P->rank * N / P->n_ranks), last = (int)((long long)(P->rank + 1) * N / P->n_ranks);
   P->ev_used = 0;
   mark(P, st, -1);
-  build_connect(P, N, d_pos, lattice, pbc, P->model.cutoff, false, st);
-  mark(P, st, 0);
+  build_connect(P, N, first, last, d_pos, lattice, pbc, P->model.cutoff, false, st);
+  mark(P, st, ST_CONNECT);
   Lattice9 lat;
   for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
 
@@ -551,18 +557,19 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
     int launches = 0;
     if (cd.kind == DESC_SOAP) {
       int nc = select_centres(P, cd, d_Z, first, last, st);
+      mark(P, st, ST_OTHER);
       if (nc > 0) {
         soap_forward_stage(P, cd, nc, d_pos, d_Z, lat, st);
-        mark(P, st, 1);
+        mark(P, st, ST_SOAP_FWD);
         covariance_stage(P, cd, nc, want_grad, st);
         launch_energy_rows(P->b_epart.as<double>(), cd.M_pad / COV_BN, P->b_centres.as<int>(), nc, es, d_le, st, &launches);
-        mark(P, st, 2);
+        mark(P, st, ST_OTHER);
         if (want_grad) {
           launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), nc, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos, d_Z, lat,
                               P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, es, d_force,
                               P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches);
           slot += nc;
-          mark(P, st, 3);
+          mark(P, st, ST_SOAP_ADJ);
         }
       }
     } else {
@@ -571,7 +578,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
                     want_grad ? d_force : nullptr, want_grad ? P->b_vir.as<double>() + 9 * slot : nullptr, want_grad ? d_lv : nullptr, st, &launches,
                     &nb);
       if (want_grad) slot += nb;
-      mark(P, st, 4);
+      mark(P, st, ST_PAIR2B);
     }
     P->launches += launches;
   }
@@ -581,7 +588,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
                                                         want_grad ? (int)slot : 0, P->b_fin.as<double>());
   k_finalize_final<<<1, 32, 0, st>>>(P->b_fin.as<double>(), d_packed);
   P->launches += 2;
-  mark(P, st, -1);
+  mark(P, st, ST_OTHER);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -729,9 +736,14 @@ int gap_potential_calc(gap_potential* P, int N, const double* pos, const int* Z,
   });
 }
 
-int gap_potential_last_timings(const gap_potential* P, double* ms6) {
-  if (!P || !ms6) return 1;
-  for (int k = 0; k < 6; k++) ms6[k] = P->last_ms[k];
+int gap_potential_last_timings(gap_potential* P, double* ms8) {
+  if (!P || !ms8) return 1;
+  if (P->ev_used >= 2) {  // events of the last calc (host- or device-pointer entry): wait for the last one, then read
+    cudaSetDevice(P->device);
+    cudaEventSynchronize(P->ev[P->ev_used - 1]);
+    collect_timings(P);
+  }
+  for (int k = 0; k < 8; k++) ms8[k] = P->last_ms[k];
   return 0;
 }
 
@@ -752,7 +764,7 @@ int gap_calc_connect(gap_potential* P, int N, const double* pos, const double* l
     CUDA_OK(cudaSetDevice(P->device));
     P->b_pos.ensure(sizeof(double) * 3 * (size_t)(N + 1));
     if (N > 0) CUDA_OK(cudaMemcpyAsync(P->b_pos.p, pos, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, P->stream));
-    build_connect(P, N, P->b_pos.as<double>(), lattice, pbc, cutoff, true, P->stream);
+    build_connect(P, N, 0, N, P->b_pos.as<double>(), lattice, pbc, cutoff, true, P->stream);
     CUDA_OK(cudaStreamSynchronize(P->stream));
     if (n_entries) *n_entries = P->conn_nnz;
   });
@@ -798,7 +810,7 @@ int gap_descriptor_calc(gap_potential* P, int i_coord, int N, const double* pos,
     if (n_desc) *n_desc = nc;
     if (d_out) *d_out = cd.h.d;
     if (!x) return;
-    build_connect(P, N, P->b_pos.as<double>(), lattice, pbc, cd.h.cutoff, false, st);
+    build_connect(P, N, 0, N, P->b_pos.as<double>(), lattice, pbc, cd.h.cutoff, false, st);
     Lattice9 lat;
     for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
     soap_forward_stage(P, cd, nc, P->b_pos.as<double>(), P->b_Z.as<int>(), lat, st);
@@ -819,6 +831,8 @@ int gap_gp_predict(gap_potential* P, int i_coord, int n, const double* x, double
     if (n <= 0) return;
     CUDA_OK(cudaSetDevice(P->device));
     cudaStream_t st = P->stream;
+    P->ev_used = 0;
+    mark(P, st, -1);
     int n_pad = round_up(n, COV_BM);
     P->b_x.ensure(sizeof(double) * (size_t)n_pad * cd.d_pad);
     CUDA_OK(cudaMemsetAsync(P->b_x.p, 0, sizeof(double) * (size_t)n_pad * cd.d_pad, st));

@@ -267,9 +267,9 @@ class Potential:
         return load_library().gap_potential_launch_count(self._h)
 
     def last_timings(self):
-        t = np.zeros(6)
+        t = np.zeros(8)
         load_library().gap_potential_last_timings(self._h, _dp(t))
-        return dict(zip(["connect", "soap_forward", "covariance", "soap_adjoint", "distance_2b", "total"], t))
+        return dict(zip(["connect", "soap_forward", "cov_gemm1", "cov_gemm2", "soap_adjoint", "distance_2b", "other", "total"], t))
 
     def finalise(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -281,3 +281,79 @@ class Potential:
             self.finalise()
         except Exception:
             pass
+
+
+class ShardedPotential:
+    """One process per GPU: the reference's MPI-parallel ``calc`` (atom mask + ``sum_in_place``,
+    src/GAP/descriptors.f95:1036-1051, src/Potentials/IPModel_GAP.f95:538-556) over ``torch.distributed``.
+
+    Every rank holds the whole configuration (positions replicated) and evaluates the centres of its contiguous
+    block; the ONLY collective is one all-reduce of the packed ``[E | virial(9) | F(3,N)]`` device buffer (NCCL on
+    GPUs; the reference issues five MPI_Allreduce calls).  torch is plumbing here (device memory, streams, the
+    process group); all arithmetic is in libgapb200.so.
+    """
+
+    def __init__(self, args_str="", param_filename=None, param_str=None, device=0, group=None, rank=None, world_size=None):
+        import torch
+
+        self.torch = torch
+        self.group = group
+        if rank is None or world_size is None:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                rank, world_size = dist.get_rank(group), dist.get_world_size(group)
+            else:
+                rank, world_size = 0, 1
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.pot = Potential(args_str, param_filename=param_filename, param_str=param_str, device=device)
+        self.pot.set_partition(self.rank, self.world_size)
+        self.device = torch.device("cuda", device)
+        self._N = -1
+
+    def _ensure(self, N):
+        torch = self.torch
+        if N == self._N:
+            return
+        self._N = N
+        self.h_pos = torch.empty((N, 3), dtype=torch.float64, pin_memory=True)
+        self.h_Z = torch.empty((N,), dtype=torch.int32, pin_memory=True)
+        self.h_packed = torch.empty((10 + 3 * N,), dtype=torch.float64, pin_memory=True)
+        self.d_pos = torch.empty((N, 3), dtype=torch.float64, device=self.device)
+        self.d_Z = torch.empty((N,), dtype=torch.int32, device=self.device)
+        self.d_packed = torch.empty((10 + 3 * N,), dtype=torch.float64, device=self.device)
+
+    def reduce_packed(self, d_packed):
+        """The path's one collective: sum of the per-rank partial [E | virial | F] buffers."""
+        if self.world_size > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(d_packed, op=dist.ReduceOp.SUM, group=self.group)
+
+    def calc_resident(self, N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad=True):
+        """Inputs and outputs are device tensors; work is enqueued on torch's current stream."""
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        self.pot.calc_device(N, d_pos.data_ptr(), d_Z.data_ptr(), lattice9, pbc3, d_packed.data_ptr(), want_grad=want_grad, stream_ptr=st)
+        self.reduce_packed(d_packed)
+
+    def calc(self, atoms, force=True, virial=True):
+        """Host in, host out: H2D of (pos, Z) from pinned memory, evaluation of this rank's block, all-reduce, D2H."""
+        torch = self.torch
+        pos, Z, lat, pbc = _geometry(atoms)
+        N = len(Z)
+        self._ensure(N)
+        with torch.cuda.device(self.device):
+            self.h_pos.numpy()[...] = pos
+            self.h_Z.numpy()[...] = Z
+            self.d_pos.copy_(self.h_pos, non_blocking=True)
+            self.d_Z.copy_(self.h_Z, non_blocking=True)
+            self.calc_resident(N, self.d_pos, self.d_Z, lat, pbc, self.d_packed, want_grad=force or virial)
+            self.h_packed.copy_(self.d_packed, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        out = self.h_packed.numpy()
+        r = {"energy": float(out[0])}
+        if virial:
+            r["virial"] = out[1:10].reshape(3, 3, order="F").copy()
+        if force:
+            r["force"] = out[10:].reshape(N, 3).copy()
+        return r
