@@ -115,18 +115,20 @@ def cpu_sample(om, atoms, n_centres):
     return time.perf_counter() - t
 
 
-def cpu_baseline_leg(xml, atoms, budget_s=15.0):
+def cpu_baseline_leg(xml, atoms, budget_s=12.0):
+    """About budget_s seconds of CPU work on the same workload: a probe sizes the sample; small configurations are repeated whole."""
     from oracle import oracle as orc
 
     om = orc.Model(xml)
     cores = int(orc.lib().orc_num_threads())
     n = min(len(atoms), 256)
-    dt = cpu_sample(om, atoms, n)
-    n2 = int(min(len(atoms), max(n, n / dt * budget_s)))
-    dt2 = cpu_sample(om, atoms, n2)
-    return {"value": n2 / dt2, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of %d centres of the same configuration (full neighbour list of all atoms built serially as in calc_connect), "
-                      "%.1f s, OpenMP over atoms with %d threads" % (n2, len(atoms), dt2, cores)}
+    rate = n / cpu_sample(om, atoms, n)
+    per_pass = int(min(len(atoms), max(n, rate * budget_s)))
+    passes = int(max(1, min(64, round(rate * budget_s / per_pass))))
+    t = sum(cpu_sample(om, atoms, per_pass) for _ in range(passes))
+    return {"value": per_pass * passes / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d pass(es) over %d of %d centres of the same configuration (neighbour list of all atoms rebuilt serially each pass, as "
+                      "calc_connect does), %.1f s in total, OpenMP over atoms with %d threads" % (passes, per_pass, len(atoms), t, cores)}
 
 
 def run_reference(args):
@@ -230,6 +232,8 @@ def run_b200(args):
         sp.calc_resident(N, d_pos, d_Z, lat, pbc, d_packed, want_grad=True)
 
     # ---- value: HBM-resident inputs, CUDA events per step, L2 flushed between steps ----
+    # everything below is enqueued on sp.stream (a real stream; events are recorded on the stream the kernels run on)
+    torch.cuda.set_stream(sp.stream)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()

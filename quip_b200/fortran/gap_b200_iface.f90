@@ -1,0 +1,146 @@
+! gap_b200_iface.f90 -- ISO_C_BINDING interface to libgapb200.so (include/gap_b200.h) and the replacement bodies
+! of IPModel_GAP_Initialise_str / IPModel_GAP_Calc / IPModel_GAP_Finalise a QUIP maintainer would drop into
+! src/Potentials/IPModel_GAP.f95 (:149, :233, :194).
+!
+! NOT COMPILED IN THIS REPOSITORY: the build image has no Fortran compiler.  The C ABI it binds is exercised by
+! quip_b200/potential.py (ctypes) and tests/; the array layouts below are the ones those tests use
+! (pos(3,N), f(3,N), virial(3,3) column-major, local_virial(9,N)), so no copies or transposes are needed.
+module gap_b200_iface
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+  public :: gap_potential_initialise, gap_potential_filename_initialise, gap_potential_finalise, gap_potential_cutoff
+  public :: gap_potential_calc, gap_potential_set_partition, gap_last_error, gap_b200_error_string
+
+  interface
+     ! int gap_potential_initialise(gap_potential** pot, const char* args_str, const char* param_str, const char* base_dir, int device)
+     function gap_potential_initialise(pot, args_str, param_str, base_dir, device) bind(C, name="gap_potential_initialise") result(ierr)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr), intent(out) :: pot
+       character(kind=c_char), dimension(*), intent(in) :: args_str, param_str, base_dir
+       integer(c_int), value :: device
+       integer(c_int) :: ierr
+     end function
+     function gap_potential_filename_initialise(pot, args_str, param_filename, device) &
+          bind(C, name="gap_potential_filename_initialise") result(ierr)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr), intent(out) :: pot
+       character(kind=c_char), dimension(*), intent(in) :: args_str, param_filename
+       integer(c_int), value :: device
+       integer(c_int) :: ierr
+     end function
+     subroutine gap_potential_finalise(pot) bind(C, name="gap_potential_finalise")
+       import :: c_ptr
+       type(c_ptr), value :: pot
+     end subroutine
+     function gap_potential_cutoff(pot) bind(C, name="gap_potential_cutoff") result(rc)
+       import :: c_ptr, c_double
+       type(c_ptr), value :: pot
+       real(c_double) :: rc
+     end function
+     function gap_potential_set_partition(pot, rank, n_ranks) bind(C, name="gap_potential_set_partition") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: pot
+       integer(c_int), value :: rank, n_ranks
+       integer(c_int) :: ierr
+     end function
+     ! absent optional outputs are passed as C_NULL_PTR, hence type(c_ptr), value for every output
+     function gap_potential_calc(pot, n, pos, z, lattice, pbc, args_str, energy, local_e, force, virial, local_virial) &
+          bind(C, name="gap_potential_calc") result(ierr)
+       import :: c_ptr, c_char, c_int, c_double
+       type(c_ptr), value :: pot
+       integer(c_int), value :: n
+       real(c_double), intent(in) :: pos(3, *), lattice(3, 3)
+       integer(c_int), intent(in) :: z(*), pbc(3)
+       character(kind=c_char), dimension(*), intent(in) :: args_str
+       type(c_ptr), value :: energy, local_e, force, virial, local_virial
+       integer(c_int) :: ierr
+     end function
+     function gap_last_error() bind(C, name="gap_last_error") result(msg)
+       import :: c_ptr
+       type(c_ptr) :: msg
+     end function
+  end interface
+
+contains
+
+  function gap_b200_error_string() result(s)
+    character(len=:), allocatable :: s
+    character(kind=c_char), pointer :: p(:)
+    type(c_ptr) :: cp
+    integer :: n
+    cp = gap_last_error()
+    s = ""
+    if (.not. c_associated(cp)) return
+    call c_f_pointer(cp, p, [4096])
+    n = 0
+    do while (n < 4096)
+       if (p(n + 1) == c_null_char) exit
+       n = n + 1
+    end do
+    allocate(character(len=n) :: s)
+    s = transfer(p(1:n), s)
+  end function
+
+end module gap_b200_iface
+
+! ----------------------------------------------------------------------------------------------------------------
+! Replacement bodies inside module IPModel_GAP_module (src/Potentials/IPModel_GAP.f95).  type(IPModel_GAP) gains one
+! component:   type(c_ptr) :: b200 = c_null_ptr
+! ----------------------------------------------------------------------------------------------------------------
+!
+! subroutine IPModel_GAP_Initialise_str(this, args_str, param_str)          ! IPModel_GAP.f95:149
+!   use gap_b200_iface
+!   type(IPModel_GAP), intent(inout) :: this
+!   character(len=*), intent(in) :: args_str, param_str
+!   call Finalise(this)
+!   ! Potential_Filename_Initialise has already chdir'ed to the XML's directory (Potential.f95:455-466): base_dir = "."
+!   if (gap_potential_initialise(this%b200, trim(args_str)//c_null_char, trim(param_str)//c_null_char, "."//c_null_char, &
+!                                gap_b200_device()) /= 0) &
+!      call system_abort("IPModel_GAP_Initialise_str: "//gap_b200_error_string())
+!   this%cutoff = gap_potential_cutoff(this%b200)                             ! read by IP_cutoff, IP.f95:704-705
+!   this%initialised = .true.
+! end subroutine
+!
+! subroutine IPModel_GAP_Finalise(this)                                       ! IPModel_GAP.f95:194
+!   if (c_associated(this%b200)) call gap_potential_finalise(this%b200)
+!   this%b200 = c_null_ptr ; this%cutoff = 0.0_dp ; this%initialised = .false.
+! end subroutine
+!
+! subroutine IPModel_GAP_Calc(this, at, e, local_e, f, virial, local_virial, args_str, mpi, error)   ! IPModel_GAP.f95:233
+!   use gap_b200_iface
+!   type(IPModel_GAP), intent(inout) :: this
+!   type(Atoms), intent(inout) :: at
+!   real(dp), intent(out), optional, target :: e, local_e(:), f(:,:), local_virial(:,:), virial(3,3)
+!   character(len=*), intent(in), optional :: args_str
+!   type(MPI_Context), intent(in), optional :: mpi
+!   integer, intent(out), optional :: error
+!   type(c_ptr) :: pe, ple, pf, pv, plv
+!   integer(c_int) :: pbc(3), ierr
+!   INIT_ERROR(error)
+!   pe = c_null_ptr; ple = c_null_ptr; pf = c_null_ptr; pv = c_null_ptr; plv = c_null_ptr
+!   if (present(e)) pe = c_loc(e)
+!   if (present(local_e)) then; call check_size('Local_E', local_e, (/at%N/), 'IPModel_GAP_Calc', error); ple = c_loc(local_e); end if
+!   if (present(f)) then; call check_size('Force', f, (/3, at%N/), 'IPModel_GAP_Calc', error); pf = c_loc(f); end if
+!   if (present(virial)) pv = c_loc(virial)
+!   if (present(local_virial)) then
+!      call check_size('Local_virial', local_virial, (/9, at%N/), 'IPModel_GAP_Calc', error); plv = c_loc(local_virial)
+!   end if
+!   pbc = merge(1, 0, at%is_periodic)
+!   if (present(mpi)) then                                    ! the reference's atom mask (descriptors.f95:1036-1051)
+!      if (mpi%active) ierr = gap_potential_set_partition(this%b200, mpi%my_proc, mpi%n_procs)
+!   end if
+!   ierr = gap_potential_calc(this%b200, at%N, at%pos, at%Z, at%lattice, pbc, trim(args_str)//c_null_char, pe, ple, pf, pv, plv)
+!   if (ierr /= 0) then
+!      RAISE_ERROR("IPModel_GAP_Calc: "//gap_b200_error_string(), error)
+!   end if
+!   if (present(mpi)) then                                    ! IPModel_GAP.f95:538-556, unchanged
+!      if (mpi%active) then
+!         if (present(f)) call sum_in_place(mpi, f)
+!         if (present(virial)) call sum_in_place(mpi, virial)
+!         if (present(local_virial)) call sum_in_place(mpi, local_virial)
+!         if (present(e)) e = sum(mpi, e)
+!         if (present(local_e)) call sum_in_place(mpi, local_e)
+!      end if
+!   end if
+! end subroutine

@@ -283,6 +283,31 @@ class Potential:
             pass
 
 
+def partition_bounds(rank, n_ranks, N):
+    """Centres [first, last) of ``rank``: the same contiguous blocks ``gap_potential_set_partition`` uses."""
+    return (rank * N) // n_ranks, ((rank + 1) * N) // n_ranks
+
+
+def pack_results(energy, virial, force):
+    """[E | virial(9) column-major | F(3,N)] -- the one buffer the path all-reduces."""
+    return np.concatenate([[float(energy)], np.asarray(virial, dtype=np.float64).reshape(9, order="F"),
+                           np.asarray(force, dtype=np.float64).reshape(-1)])
+
+
+def unpack_results(packed, N):
+    packed = np.asarray(packed)
+    return {"energy": float(packed[0]), "virial": packed[1:10].reshape(3, 3, order="F").copy(), "force": packed[10:10 + 3 * N].reshape(N, 3).copy()}
+
+
+def reduce_packed(t, group=None):
+    """Sum of the per-rank partial packed buffers (torch tensor, in place): NCCL for CUDA tensors, gloo for CPU ones."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
 class ShardedPotential:
     """One process per GPU: the reference's MPI-parallel ``calc`` (atom mask + ``sum_in_place``,
     src/GAP/descriptors.f95:1036-1051, src/Potentials/IPModel_GAP.f95:538-556) over ``torch.distributed``.
@@ -309,6 +334,7 @@ class ShardedPotential:
         self.pot = Potential(args_str, param_filename=param_filename, param_str=param_str, device=device)
         self.pot.set_partition(self.rank, self.world_size)
         self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.Stream(self.device)  # a real stream: the C ABI reads stream 0 / NULL as "the handle's own"
         self._N = -1
 
     def _ensure(self, N):
@@ -326,14 +352,21 @@ class ShardedPotential:
     def reduce_packed(self, d_packed):
         """The path's one collective: sum of the per-rank partial [E | virial | F] buffers."""
         if self.world_size > 1:
-            import torch.distributed as dist
-
-            dist.all_reduce(d_packed, op=dist.ReduceOp.SUM, group=self.group)
+            reduce_packed(d_packed, self.group)
 
     def calc_resident(self, N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad=True):
-        """Inputs and outputs are device tensors; work is enqueued on torch's current stream."""
-        st = self.torch.cuda.current_stream(self.device).cuda_stream
-        self.pot.calc_device(N, d_pos.data_ptr(), d_Z.data_ptr(), lattice9, pbc3, d_packed.data_ptr(), want_grad=want_grad, stream_ptr=st)
+        """Inputs and outputs are device tensors; work is enqueued on torch's current stream (on ``self.stream``, ordered
+        after and before the current stream, when the current stream is the legacy default stream)."""
+        torch = self.torch
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream == 0:
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                self.calc_resident(N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad)
+            cur.wait_stream(self.stream)
+            return
+        self.pot.calc_device(N, d_pos.data_ptr(), d_Z.data_ptr(), lattice9, pbc3, d_packed.data_ptr(), want_grad=want_grad,
+                             stream_ptr=cur.cuda_stream)
         self.reduce_packed(d_packed)
 
     def calc(self, atoms, force=True, virial=True):
@@ -342,18 +375,12 @@ class ShardedPotential:
         pos, Z, lat, pbc = _geometry(atoms)
         N = len(Z)
         self._ensure(N)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.h_pos.numpy()[...] = pos
             self.h_Z.numpy()[...] = Z
             self.d_pos.copy_(self.h_pos, non_blocking=True)
             self.d_Z.copy_(self.h_Z, non_blocking=True)
             self.calc_resident(N, self.d_pos, self.d_Z, lat, pbc, self.d_packed, want_grad=force or virial)
             self.h_packed.copy_(self.d_packed, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-        out = self.h_packed.numpy()
-        r = {"energy": float(out[0])}
-        if virial:
-            r["virial"] = out[1:10].reshape(3, 3, order="F").copy()
-        if force:
-            r["force"] = out[10:].reshape(N, 3).copy()
-        return r
+            self.stream.synchronize()
+        return unpack_results(self.h_packed.numpy(), N)
