@@ -28,7 +28,7 @@ namespace {
 constexpr int NT = 128;    // threads per CTA
 constexpr int NBCAP = 128; // CSR entries examined per pass (= compacted list capacity)
 constexpr int TNF = 32;    // neighbours per tile, forward
-constexpr int TNA = 16;    // neighbours per tile, adjoint
+constexpr int TNA = 32;    // neighbours per tile, adjoint
 constexpr int LC = SOAP_LMAX_CAP;
 constexpr double PI_D = 3.14159265358979323846264338327950288;
 
@@ -78,130 +78,71 @@ __device__ __forceinline__ void cutoff_fn(const SoapDev* sp, double r, double& f
   } else { f = fc; df = dfc; }
 }
 
-// Radial functions of one (neighbour, basis point) item for l = 0..l_max (descriptors.f95:8218-8258):
-// out[l*stride] = exp(-alpha (r^2 + r_a^2)) i_l(2 alpha r r_a), upward recursion exactly as the reference,
-// dout[l*stride] = d/dr of it.
-template <bool GRAD>
-__device__ __forceinline__ void radial_item(double alpha, double r, double rb, int l_max, double* out, double* dout, int stride) {
-  double arg = 2.0 * alpha * r * rb;
-  if (arg == 0.0) {
-    double bl = exp(-alpha * (rb * rb + r * r));
-    out[0] = bl;
-    if (GRAD) dout[0] = -2.0 * alpha * r * bl;
-    for (int l = 1; l <= l_max; l++) {
-      out[l * stride] = 0.0;
-      if (GRAD) dout[l * stride] = 0.0;
-    }
-    return;
-  }
-  double exp_p = exp(-alpha * (r + rb) * (r + rb));
-  double exp_m = exp(-alpha * (r - rb) * (r - rb));
-  double inv = 1.0 / arg, rinv = 1.0 / r;
-  double blm = 0.5 * (exp_m + exp_p) * inv;
-  double bl = 0.5 * (exp_m - exp_p) * inv;
-  double blp = blm - bl * inv;
-  out[0] = bl;
-  if (GRAD) dout[0] = -2.0 * alpha * r * bl + blp * 2.0 * alpha * rb;
-  for (int l = 1; l <= l_max; l++) {
-    blm = bl;
-    bl = blp;
-    blp = blm - (double)(2 * l + 1) * bl * inv;
-    out[l * stride] = bl;
-    if (GRAD) dout[l * stride] = -2.0 * alpha * r * bl + (double)l * bl * rinv + blp * 2.0 * alpha * rb;
-  }
-}
+// ------------------------------------------------------------------------------------------------------------
+// Work decomposition (one CTA of NT threads per centre, several CTAs resident per SM):
+//   gather   : the centre's CSR row -> shared memory (displacement, distance, species, cutoff function), compacted
+//              in list order (deterministic);
+//   tile loop over TN neighbours at a time:
+//     stage  : one item per (neighbour, radial basis point a): Phi_l(a) = f_cut * phi_l(a) for all l (and, for the
+//              adjoint, R_l(a) = f_cut * phi_l'(a) + f_cut' * phi_l(a));  forward only: one item per (neighbour, m):
+//              Y_{l,+-m} for all l >= m;
+//     forward accumulate: one item per (lm, group of 4 basis points): Xt_lm(s,a) += sum_q Phi_l(a;q) Y_lm(q) held in
+//              registers across the tile (the item owns its shared-memory row: no atomics, no extra barrier);
+//     adjoint contract : one item per (neighbour, m-pair): harmonics and their gradients are generated on the fly
+//              and contracted with Lambda~ and the radial tables straight away -- Y and grad Y never touch memory;
+//   The transform_basis product is hoisted out of the neighbour loop: X = Xt . T once per centre (forward) and
+//   Lambda~ = T . Lambda once per centre (adjoint), instead of the reference's per-neighbour matmul
+//   (descriptors.f95:8261-8263): (l_max+1) n_max^2 flops per NEIGHBOUR become (l_max+1)^2 n_max^2 per CENTRE.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int AG = 4;  // radial basis points per accumulate item
 
-// Real orthonormal spherical harmonics of the unit vector u for all l <= l_max, index lm = l*l + l + m
-// (m > 0: cos-type, m < 0: sin-type), and -- if GRAD -- their gradient with respect to the UNNORMALISED
-// displacement (u = dvec/r): grad = (g - u (u.g)) / r with g the gradient of the polynomial extension
-// N_lm Q_l^m(z) {C_m,S_m}(x,y), Q_l^m = d^m P_l/dz^m, C_m + i S_m = (x + i y)^m.
-template <bool GRAD>
-__device__ __forceinline__ void real_ylm(const double* __restrict__ ynorm, int L, double ux, double uy, double uz, double rinv, double* Y,
-                                         double* dY, int comp_stride) {
-  double Cm[LC + 1], Sm[LC + 1], Qn[LC + 2], Qc[LC + 2];
-  Cm[0] = 1.0;
-  Sm[0] = 0.0;
-  for (int m = 1; m <= L; m++) {
-    Cm[m] = ux * Cm[m - 1] - uy * Sm[m - 1];
-    Sm[m] = ux * Sm[m - 1] + uy * Cm[m - 1];
-  }
-  for (int l = 0; l <= L + 1; l++) Qn[l] = 0.0;
-  for (int m = L; m >= 0; m--) {
-    Qc[m] = c_dblfact[m];
-    if (m + 1 <= L) Qc[m + 1] = (double)(2 * m + 1) * uz * Qc[m];
-    for (int l = m + 2; l <= L; l++) Qc[l] = ((double)(2 * l - 1) * uz * Qc[l - 1] - (double)(l + m - 1) * Qc[l - 2]) * c_invint[l - m];
-    for (int l = m; l <= L; l++) {
-      double nrm = ynorm[l * (l + 1) / 2 + m];
-      double q = Qc[l] * nrm;
-      int base = l * l + l;
-      if (m == 0) {
-        Y[base] = q;
-        if (GRAD) {
-          double gz = Qn[l] * nrm;
-          double dot = uz * gz;
-          dY[base] = (-ux * dot) * rinv;
-          dY[comp_stride + base] = (-uy * dot) * rinv;
-          dY[2 * comp_stride + base] = (gz - uz * dot) * rinv;
-        }
-      } else {
-        Y[base + m] = q * Cm[m];
-        Y[base - m] = q * Sm[m];
-        if (GRAD) {
-          double qz = Qn[l] * nrm, qm = q * (double)m;
-          {
-            double gx = qm * Cm[m - 1], gy = -qm * Sm[m - 1], gz = qz * Cm[m];
-            double dot = ux * gx + uy * gy + uz * gz;
-            dY[base + m] = (gx - ux * dot) * rinv;
-            dY[comp_stride + base + m] = (gy - uy * dot) * rinv;
-            dY[2 * comp_stride + base + m] = (gz - uz * dot) * rinv;
-          }
-          {
-            double gx = qm * Sm[m - 1], gy = qm * Cm[m - 1], gz = qz * Sm[m];
-            double dot = ux * gx + uy * gy + uz * gz;
-            dY[base - m] = (gx - ux * dot) * rinv;
-            dY[comp_stride + base - m] = (gy - uy * dot) * rinv;
-            dY[2 * comp_stride + base - m] = (gz - uz * dot) * rinv;
-          }
-        }
-      }
-    }
-    for (int l = m; l <= L; l++) Qn[l] = Qc[l];
-    if (m >= 1) Qn[m - 1] = 0.0;
-  }
+__host__ __device__ inline int ceil4(int v) { return (v + 3) & ~3; }
+// row stride (doubles) of the per-neighbour radial tables: = 2 (mod 16), so that 8 consecutive neighbours read
+// 16-byte words from 8 distinct bank quads
+__host__ __device__ inline int rf_stride(int L1, int n4) {
+  int s = L1 * n4;
+  while ((s & 15) != 2) s += 2;
+  return s;
 }
+__host__ __device__ inline int y_stride(int nlm) { return nlm | 1; }
 
 struct Smem {
-  double* T;      // n_max*n_max
-  double* rb;     // n_max
-  double* ynorm;  // (L+1)(L+2)/2
-  double* X;      // nlm*K1   (forward: accumulates X ; adjoint: Lambda)
-  double* nbd;    // NBCAP*3 displacement
-  double* nbr;    // NBCAP distance
-  double* red;    // 64
-  double* rf;     // TN*(L+1)*n_max
-  double* drf;    // adjoint only
-  double* Y;      // TN*nlm
-  double* dY;     // adjoint only: 3 * TN*nlm
-  double* p;      // d_pad  (aliases rf.. region in forward; own region in adjoint)
-  int* nbs;       // NBCAP species
-  int* nbj;       // NBCAP neighbour atom
-  int* lof;       // nlm: l of lm
-  int* wcount;    // 8
+  double* T;       // n*n transform_basis, T[a + n*a']
+  double* rb;      // n
+  double* ynorm;   // (L+1)(L+2)/2
+  double* X;       // nlm * K1p : forward Xt -> X ; adjoint Lambda~   (row lm, column s*n4 + a)
+  double* nbd;     // NBCAP*3 displacement
+  double* nbr;     // NBCAP distance
+  double* nbf;     // NBCAP f_cut
+  double* nbdf;    // NBCAP f_cut'
+  double* red;     // 64
+  double* rf;      // TN * RFS
+  double* drf;     // adjoint: TN * RFS
+  double* Y;       // forward: TN * YS
+  double* part;    // adjoint: TN * MP * 3 partial forces
+  double* p;       // forward: d_pad power spectrum (aliases the staging area) ; adjoint: d_pad, own region
+  int* nbs;        // NBCAP species
+  int* nbj;        // NBCAP neighbour atom
+  int* lof;        // nlm: l of lm
+  int* wcount;     // 8
 };
 
+__host__ __device__ inline int m_pairs(int L) { return L / 2 + 1 + (L & 1); }  // items per neighbour in the adjoint contraction
+
 __host__ __device__ inline size_t carve(const SoapDev& h, bool adjoint, Smem* s, unsigned char* base) {
-  const int n = h.n_max, L1 = h.l_max + 1, nlm = h.nlm, TN = adjoint ? TNA : TNF;
+  const int n = h.n_max, L1 = h.l_max + 1, nlm = h.nlm, TN = adjoint ? TNA : TNF, n4 = ceil4(n), K1p = h.n_species * n4;
+  const int RFS = rf_stride(L1, n4), YS = y_stride(nlm), MP = m_pairs(h.l_max);
   size_t o = 0;
-  auto take = [&](size_t cnt) { size_t r = o; o += cnt * sizeof(double); return r; };
-  size_t oT = take(n * n), orb = take(n), oyn = take((size_t)L1 * (L1 + 1) / 2), oX = take((size_t)nlm * h.K1), onbd = take(NBCAP * 3),
-         onbr = take(NBCAP), ored = take(64);
-  size_t orf = take((size_t)TN * L1 * n), odrf = adjoint ? take((size_t)TN * L1 * n) : 0, oY = take((size_t)TN * nlm),
-         odY = adjoint ? take((size_t)3 * TN * nlm) : 0;
+  auto take = [&](size_t cnt) { size_t r = o; o += ((cnt + 1) & ~(size_t)1) * sizeof(double); return r; };
+  size_t oT = take(n * n), orb = take(n), oyn = take((size_t)L1 * (L1 + 1) / 2), oX = take((size_t)nlm * K1p), onbd = take(NBCAP * 3),
+         onbr = take(NBCAP), onbf = take(NBCAP), onbdf = take(NBCAP), ored = take(64);
+  size_t orf = take((size_t)TN * RFS), odrf = adjoint ? take((size_t)TN * RFS) : 0, oY = adjoint ? 0 : take((size_t)TN * YS),
+         opart = adjoint ? take((size_t)TN * MP * 3) : 0;
   size_t stage_bytes = o - orf;
   size_t op;
   if (adjoint) {
-    // the staging area doubles as scratch for X_lm while Lambda is formed
-    if ((size_t)nlm * h.K1 * sizeof(double) > stage_bytes) o = orf + (size_t)nlm * h.K1 * sizeof(double);
+    // the staging area doubles as scratch for X_lm / Lambda while Lambda~ is formed (2 * nlm * K1 doubles)
+    if ((size_t)2 * nlm * h.K1 * sizeof(double) > stage_bytes) o = orf + (size_t)2 * nlm * h.K1 * sizeof(double);
     op = take(h.d_pad);
   } else {
     op = orf;  // forward: the power spectrum reuses the staging area after the neighbour loop
@@ -209,10 +150,12 @@ __host__ __device__ inline size_t carve(const SoapDev& h, bool adjoint, Smem* s,
   }
   size_t oi = o;
   o += sizeof(int) * (NBCAP * 2 + nlm + 8);
+  o = (o + 15) & ~(size_t)15;
   if (s) {
     s->T = (double*)(base + oT); s->rb = (double*)(base + orb); s->ynorm = (double*)(base + oyn); s->X = (double*)(base + oX);
-    s->nbd = (double*)(base + onbd); s->nbr = (double*)(base + onbr); s->red = (double*)(base + ored); s->rf = (double*)(base + orf);
-    s->drf = (double*)(base + odrf); s->Y = (double*)(base + oY); s->dY = (double*)(base + odY); s->p = (double*)(base + op);
+    s->nbd = (double*)(base + onbd); s->nbr = (double*)(base + onbr); s->nbf = (double*)(base + onbf); s->nbdf = (double*)(base + onbdf);
+    s->red = (double*)(base + ored); s->rf = (double*)(base + orf); s->drf = (double*)(base + odrf); s->Y = (double*)(base + oY);
+    s->part = (double*)(base + opart); s->p = (double*)(base + op);
     s->nbs = (int*)(base + oi); s->nbj = s->nbs + NBCAP; s->lof = s->nbj + NBCAP; s->wcount = s->lof + nlm;
   }
   return o;
@@ -256,10 +199,14 @@ __device__ __forceinline__ int gather_neighbours(const SoapDev* sp, const Smem& 
   int total = s.wcount[0] + s.wcount[1] + s.wcount[2] + s.wcount[3];
   if (valid) {
     int q = off + __popc(bal & ((1u << lane) - 1u));
+    double f, df;
+    cutoff_fn(sp, r, f, df);
     s.nbd[3 * q] = dd[0];
     s.nbd[3 * q + 1] = dd[1];
     s.nbd[3 * q + 2] = dd[2];
     s.nbr[q] = r;
+    s.nbf[q] = f;
+    s.nbdf[q] = df;
     s.nbs[q] = spc;
     s.nbj[q] = j;
   }
@@ -267,100 +214,170 @@ __device__ __forceinline__ int gather_neighbours(const SoapDev* sp, const Smem& 
   return total;
 }
 
-// stage one tile: warp 0 -> harmonics, warps 1..3 -> radial functions; then the radial transform in place.
+// Radial item (neighbour q, basis point a): Phi_l(a) = f phi_l(a) (and R_l(a) = f phi_l'(a) + f' phi_l(a)) for l = 0..L,
+// written at out[l * n4] (descriptors.f95:8218-8258 -- the upward recursion exactly as the reference runs it).
 template <bool GRAD>
-__device__ __forceinline__ void stage_tile(const SoapDev* sp, const Smem& s, int t0, int tn) {
-  const int n = sp->n_max, L = sp->l_max, L1 = L + 1, nlm = sp->nlm, TN = GRAD ? TNA : TNF;
-  if (threadIdx.x < 32) {
-    int q = threadIdx.x;
-    if (q < tn) {
-      double r = s.nbr[t0 + q], rinv = 1.0 / r;
-      real_ylm<GRAD>(s.ynorm, L, s.nbd[3 * (t0 + q)] * rinv, s.nbd[3 * (t0 + q) + 1] * rinv, s.nbd[3 * (t0 + q) + 2] * rinv, rinv,
-                     s.Y + (size_t)q * nlm, GRAD ? s.dY + (size_t)q * nlm : nullptr, TN * nlm);
+__device__ __forceinline__ void radial_item(double alpha, double r, double rb, double f, double df, int L, double* out, double* dout, int n4) {
+  double arg = 2.0 * alpha * r * rb;
+  if (arg == 0.0) {
+    double bl = exp(-alpha * (rb * rb + r * r));
+    out[0] = f * bl;
+    if (GRAD) dout[0] = f * (-2.0 * alpha * r * bl) + df * bl;
+    for (int l = 1; l <= L; l++) {
+      out[l * n4] = 0.0;
+      if (GRAD) dout[l * n4] = 0.0;
     }
-  } else {
-    for (int it = threadIdx.x - 32; it < tn * n; it += NT - 32) {
-      int q = it / n, a = it - q * n;
-      radial_item<GRAD>(sp->alpha, s.nbr[t0 + q], s.rb[a], L, s.rf + (size_t)q * L1 * n + a, GRAD ? s.drf + (size_t)q * L1 * n + a : nullptr, n);
+    return;
+  }
+  double exp_p = exp(-alpha * (r + rb) * (r + rb));
+  double exp_m = exp(-alpha * (r - rb) * (r - rb));
+  double inv = 1.0 / arg, rinv = 1.0 / r;
+  double blm = 0.5 * (exp_m + exp_p) * inv;
+  double bl = 0.5 * (exp_m - exp_p) * inv;
+  double blp = blm - bl * inv;
+  out[0] = f * bl;
+  if (GRAD) dout[0] = f * (-2.0 * alpha * r * bl + blp * 2.0 * alpha * rb) + df * bl;
+  for (int l = 1; l <= L; l++) {
+    blm = bl;
+    bl = blp;
+    blp = blm - (double)(2 * l + 1) * bl * inv;
+    out[l * n4] = f * bl;
+    if (GRAD) dout[l * n4] = f * (-2.0 * alpha * r * bl + (double)l * bl * rinv + blp * 2.0 * alpha * rb) + df * bl;
+  }
+}
+
+// (x + i y)^m by repeated multiplication; also returns the (m-1)th power (needed by the gradient)
+__device__ __forceinline__ void cs_power(double ux, double uy, int m, double& Cm, double& Sm, double& Cm1, double& Sm1) {
+  Cm = 1.0; Sm = 0.0; Cm1 = 0.0; Sm1 = 0.0;
+  for (int k = 0; k < m; k++) {
+    Cm1 = Cm; Sm1 = Sm;
+    Cm = ux * Cm1 - uy * Sm1;
+    Sm = ux * Sm1 + uy * Cm1;
+  }
+}
+
+// Forward harmonic item (neighbour q, order m): real orthonormal Y_{l,+m} (cos type) and Y_{l,-m} (sin type), l = m..L,
+// index lm = l*l + l +- m.  Y_lm = N_lm Q_l^m(z) {C_m, S_m}(x, y) with Q_l^m = d^m P_l / dz^m (upward recursion in l) and
+// C_m + i S_m = (x + i y)^m; N_lm carries sqrt(2) for m > 0.  (The reference uses complex Y_lm,
+// angular_functions.f95:120-136; the power spectrum is invariant under this unitary change of basis.)
+__device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L, int m, double ux, double uy, double uz, double* Yq) {
+  double Cm, Sm, Cm1, Sm1;
+  cs_power(ux, uy, m, Cm, Sm, Cm1, Sm1);
+  double p2 = 0.0, p1 = c_dblfact[m];  // Q_{l-2}^m, Q_{l-1}^m while stepping; starts at Q_m^m = (2m-1)!!
+  for (int l = m; l <= L; l++) {
+    double pl;
+    if (l == m) pl = p1;
+    else {
+      pl = ((double)(2 * l - 1) * uz * p1 - (double)(l + m - 1) * p2) * c_invint[l - m];
+      p2 = p1;
+      p1 = pl;
+    }
+    double q = pl * ynorm[l * (l + 1) / 2 + m];
+    int base = l * l + l;
+    if (m == 0) Yq[base] = q;
+    else {
+      Yq[base + m] = q * Cm;
+      Yq[base - m] = q * Sm;
     }
   }
-  __syncthreads();
-  // radial_coefficient = matmul(radial_fun, transform_basis) * f_cut  (descriptors.f95:8261-8263), row (q,l) in place
-  for (int row = threadIdx.x; row < tn * L1; row += NT) {
-    int q = row / L1;
-    double f, df;
-    cutoff_fn(sp, s.nbr[t0 + q], f, df);
-    double v[SOAP_NMAX_CAP], dv[SOAP_NMAX_CAP];
-    double* rr = s.rf + (size_t)row * n;
-    double* dr = GRAD ? s.drf + (size_t)row * n : nullptr;
-    for (int a = 0; a < n; a++) {
-      v[a] = rr[a];
-      if (GRAD) dv[a] = dr[a];
-    }
-    for (int b = 0; b < n; b++) {
-      double t = 0.0, tg = 0.0;
-      for (int a = 0; a < n; a++) {
-        t += v[a] * s.T[a + n * b];
-        if (GRAD) tg += dv[a] * s.T[a + n * b];
-      }
-      rr[b] = t * f;
-      if (GRAD) dr[b] = tg * f + t * df;
-    }
-  }
-  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
 // forward: x (normalised power spectrum), X_lm (kept for the adjoint), |p|
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_soap_forward(const SoapDev* __restrict__ sp, const int* __restrict__ centres, int n_centres,
-                                                     const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
-                                                     const int* __restrict__ nbr_s, const double* __restrict__ pos,
-                                                     const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
-                                                     double* __restrict__ xlm, double* __restrict__ pnorm) {
+__global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restrict__ sp, const int* __restrict__ centres, int n_centres,
+                                                        const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
+                                                        const int* __restrict__ nbr_s, const double* __restrict__ pos,
+                                                        const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
+                                                        double* __restrict__ xlm, double* __restrict__ pnorm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem s;
   carve(*sp, false, &s, smem_raw);
   const int c = blockIdx.x;
   if (c >= n_centres) return;
   const int i = centres[c];
-  const int n = sp->n_max, L1 = sp->l_max + 1, nlm = sp->nlm, K1 = sp->K1, d = sp->d, d_pad = sp->d_pad;
+  const int n = sp->n_max, L = sp->l_max, L1 = L + 1, nlm = sp->nlm, K1 = sp->K1, d = sp->d, d_pad = sp->d_pad, ns = sp->n_species;
+  const int n4 = ceil4(n), K1p = ns * n4, RFS = rf_stride(L1, n4), YS = y_stride(nlm), NG = n4 / AG;
+  const double alpha = sp->alpha;
   load_tables(sp, s);
-  for (int k = threadIdx.x; k < nlm * K1; k += NT) s.X[k] = 0.0;
+  for (int k = threadIdx.x; k < nlm * K1p; k += NT) s.X[k] = 0.0;
   __syncthreads();
 
   const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
   for (int pb = pbeg; pb < pend; pb += NBCAP) {
     int nv = gather_neighbours(sp, s, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
     for (int t0 = 0; t0 < nv; t0 += TNF) {
-      int tn = min(TNF, nv - t0);
-      stage_tile<false>(sp, s, t0, tn);
-      // X_lm(species, a) += sum_q c_l(a; q) Y_lm(q)   (descriptors.f95:8289-8295)
-      for (int idx = threadIdx.x; idx < nlm * n; idx += NT) {
-        int lm = idx / n, a = idx - lm * n, l = s.lof[lm];
-        double acc = 0.0;
+      const int tn = min(TNF, nv - t0);
+      // ---- stage: radial items then harmonic items ----
+      const int n_rad = tn * n, n_items = n_rad + tn * L1;
+      for (int it = threadIdx.x; it < n_items; it += NT) {
+        if (it < n_rad) {
+          int q = it / n, a = it - q * n;
+          radial_item<false>(alpha, s.nbr[t0 + q], s.rb[a], s.nbf[t0 + q], 0.0, L, s.rf + (size_t)q * RFS + a, nullptr, n4);
+        } else {
+          int r2 = it - n_rad;
+          int m = r2 / tn, q = r2 - m * tn;
+          double rinv = 1.0 / s.nbr[t0 + q];
+          ylm_item(s.ynorm, L, m, s.nbd[3 * (t0 + q)] * rinv, s.nbd[3 * (t0 + q) + 1] * rinv, s.nbd[3 * (t0 + q) + 2] * rinv,
+                   s.Y + (size_t)q * YS);
+        }
+      }
+      if (n4 != n)  // zero the padding columns once per tile (read by the 4-wide accumulate)
+        for (int it = threadIdx.x; it < tn * L1 * (n4 - n); it += NT) {
+          int row = it / (n4 - n), a = n + it % (n4 - n);
+          int q = row / L1, l = row - q * L1;
+          s.rf[(size_t)q * RFS + l * n4 + a] = 0.0;
+        }
+      __syncthreads();
+      // ---- accumulate: Xt_lm(s, a) += sum_q Phi_l(a; q) Y_lm(q)   (descriptors.f95:8289-8295, before the basis transform) ----
+      for (int it = threadIdx.x; it < nlm * NG; it += NT) {
+        const int lm = it / NG, g = it - lm * NG, l = s.lof[lm];
+        const double* rfp = s.rf + l * n4 + g * AG;
+        const double* yp = s.Y + lm;
+        double* xrow = s.X + (size_t)lm * K1p + g * AG;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         int cur = s.nbs[t0];
         for (int q = 0; q < tn; q++) {
           int spq = s.nbs[t0 + q];
           if (spq != cur) {
-            s.X[lm * K1 + cur * n + a] += acc;
-            acc = 0.0;
+            double* xr = xrow + cur * n4;
+            xr[0] += a0; xr[1] += a1; xr[2] += a2; xr[3] += a3;
+            a0 = a1 = a2 = a3 = 0.0;
             cur = spq;
           }
-          acc += s.Y[(size_t)q * nlm + lm] * s.rf[((size_t)q * L1 + l) * n + a];
+          const double y = yp[(size_t)q * YS];
+          const double2 r01 = *reinterpret_cast<const double2*>(rfp + (size_t)q * RFS);
+          const double2 r23 = *reinterpret_cast<const double2*>(rfp + (size_t)q * RFS + 2);
+          a0 += y * r01.x; a1 += y * r01.y; a2 += y * r23.x; a3 += y * r23.y;
         }
-        s.X[lm * K1 + cur * n + a] += acc;
+        double* xr = xrow + cur * n4;
+        xr[0] += a0; xr[1] += a1; xr[2] += a2; xr[3] += a3;
       }
       __syncthreads();
     }
   }
-  // central atom term (descriptors.f95:8151-8182): only a = 1 is non-zero because the Cholesky factor is lower triangular
-  if (threadIdx.x < sp->n_species) {
-    int k = threadIdx.x;
-    if (sp->cras || sp->species_Z[k] == Z[i] || sp->species_Z[k] == 0) s.X[0 * K1 + k * n + 0] += sp->central_weight * sp->chol00 * 0.28209479177387814347;
+  // ---- basis transform, once per centre: X_lm(s, a') = sum_a Xt_lm(s, a) T(a, a')   (in place: the item owns its row) ----
+  for (int it = threadIdx.x; it < nlm * ns; it += NT) {
+    double* row = s.X + (size_t)(it / ns) * K1p + (it % ns) * n4;
+    double v[SOAP_NMAX_CAP];
+    for (int a = 0; a < n; a++) v[a] = row[a];
+    for (int b = 0; b < n; b++) {
+      double t = 0.0;
+      for (int a = 0; a < n; a++) t += v[a] * s.T[a + n * b];
+      row[b] = t;
+    }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < nlm * K1; k += NT) xlm[(size_t)c * nlm * K1 + k] = s.X[k];
+  // central atom term (descriptors.f95:8151-8182): only a = 1 is non-zero because the Cholesky factor is lower triangular
+  if (threadIdx.x < ns) {
+    int k = threadIdx.x;
+    if (sp->cras || sp->species_Z[k] == Z[i] || sp->species_Z[k] == 0) s.X[k * n4] += sp->central_weight * sp->chol00 * 0.28209479177387814347;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nlm * K1; k += NT) {
+    int lm = k / K1, ic = k - lm * K1, sk = ic / n;
+    xlm[(size_t)c * nlm * K1 + k] = s.X[(size_t)lm * K1p + sk * n4 + (ic - sk * n)];
+  }
 
   // power spectrum (descriptors.f95:8370-8418): element q = l + (l_max+1) * pair(ia, jb<=ia)
   double loc = 0.0;
@@ -370,8 +387,9 @@ __global__ void __launch_bounds__(NT) k_soap_forward(const SoapDev* __restrict__
     while ((ia + 1) * (ia + 2) / 2 <= pr) ia++;
     while (ia * (ia + 1) / 2 > pr) ia--;
     int jb = pr - ia * (ia + 1) / 2;
+    const int ca = (ia / n) * n4 + ia % n, cb = (jb / n) * n4 + jb % n;
     double t = 0.0;
-    for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) t += s.X[lm * K1 + ia] * s.X[lm * K1 + jb];
+    for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) t += s.X[lm * K1p + ca] * s.X[lm * K1p + cb];
     t *= sp->tlpo[l];
     if (ia != jb) t *= 1.41421356237309504880;
     s.p[q] = t;
@@ -387,32 +405,98 @@ __global__ void __launch_bounds__(NT) k_soap_forward(const SoapDev* __restrict__
 // ------------------------------------------------------------------------------------------------
 // adjoint: gvec = dE_i/dx  ->  forces / virial
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_soap_adjoint(const SoapDev* __restrict__ sp, const int* __restrict__ centres, int n_centres,
-                                                     const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
-                                                     const int* __restrict__ nbr_s, const double* __restrict__ pos,
-                                                     const int* __restrict__ Z, Lattice9 lat, const double* __restrict__ x,
-                                                     const double* __restrict__ xlm, const double* __restrict__ pnorm,
-                                                     const double* __restrict__ gvec, int ldg, double e_scale, double* __restrict__ force,
-                                                     double* __restrict__ vir_part, double* __restrict__ local_virial) {
+// Contribution of the harmonics of order m (both the cos and the sin type, all l >= m) of one neighbour to
+//   SA = sum_lm A_lm Y_lm           with A_lm = sum_a Lambda~_lm(a) R_l(a)
+//   G  = sum_lm B_lm grad_poly Y_lm with B_lm = sum_a Lambda~_lm(a) Phi_l(a)
+// where grad_poly is the gradient of the polynomial extension N_lm Q_l^m(z) {C_m,S_m}(x,y); the caller projects it:
+//   f_k = SA u_k + (G_k - u_k (u.G)) / r
+__device__ __forceinline__ void adjoint_order(const double* __restrict__ ynorm, int L, int m, double ux, double uy, double uz,
+                                              const double* __restrict__ lam /* Lambda~ + s*n4 */, int K1p, const double* __restrict__ rf,
+                                              const double* __restrict__ drf, int n4, double& SA, double& G0, double& G1, double& G2) {
+  double Cm, Sm, Cm1, Sm1;
+  cs_power(ux, uy, m, Cm, Sm, Cm1, Sm1);
+  const double dm = (double)m;
+  double p2 = 0.0, p1 = c_dblfact[m];        // Q^m recursion
+  double z2 = 0.0, z1 = 0.0;                 // Q^{m+1} recursion (dQ^m/dz): zero at l = m
+  for (int l = m; l <= L; l++) {
+    double pl, zl;
+    if (l == m) { pl = p1; zl = 0.0; }
+    else {
+      pl = ((double)(2 * l - 1) * uz * p1 - (double)(l + m - 1) * p2) * c_invint[l - m];
+      p2 = p1; p1 = pl;
+      if (l == m + 1) zl = c_dblfact[m + 1];
+      else zl = ((double)(2 * l - 1) * uz * z1 - (double)(l + m) * z2) * c_invint[l - m - 1];
+      z2 = z1; z1 = zl;
+    }
+    const double nrm = ynorm[l * (l + 1) / 2 + m];
+    const double q = pl * nrm, qz = zl * nrm;
+    const double* rl = rf + l * n4;
+    const double* dl = drf + l * n4;
+    const int base = l * l + l;
+    {  // cos type (or m = 0)
+      const double* lp = lam + (size_t)(base + m) * K1p;
+      double A = 0.0, B = 0.0;
+      for (int a = 0; a < n4; a += 2) {
+        const double2 lv = *reinterpret_cast<const double2*>(lp + a);
+        const double2 rv = *reinterpret_cast<const double2*>(rl + a);
+        const double2 dv = *reinterpret_cast<const double2*>(dl + a);
+        A += lv.x * dv.x + lv.y * dv.y;
+        B += lv.x * rv.x + lv.y * rv.y;
+      }
+      SA += A * (q * Cm);
+      G0 += B * (q * dm * Cm1);
+      G1 -= B * (q * dm * Sm1);
+      G2 += B * (qz * Cm);
+    }
+    if (m > 0) {  // sin type
+      const double* lp = lam + (size_t)(base - m) * K1p;
+      double A = 0.0, B = 0.0;
+      for (int a = 0; a < n4; a += 2) {
+        const double2 lv = *reinterpret_cast<const double2*>(lp + a);
+        const double2 rv = *reinterpret_cast<const double2*>(rl + a);
+        const double2 dv = *reinterpret_cast<const double2*>(dl + a);
+        A += lv.x * dv.x + lv.y * dv.y;
+        B += lv.x * rv.x + lv.y * rv.y;
+      }
+      SA += A * (q * Sm);
+      G0 += B * (q * dm * Sm1);
+      G1 += B * (q * dm * Cm1);
+      G2 += B * (qz * Sm);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restrict__ sp, const int* __restrict__ centres, int n_centres,
+                                                        const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
+                                                        const int* __restrict__ nbr_s, const double* __restrict__ pos,
+                                                        const int* __restrict__ Z, Lattice9 lat, const double* __restrict__ x,
+                                                        const double* __restrict__ xlm, const double* __restrict__ pnorm,
+                                                        const double* __restrict__ gvec, int ldg, double e_scale, double* __restrict__ force,
+                                                        double* __restrict__ vir_part, double* __restrict__ local_virial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem s;
   carve(*sp, true, &s, smem_raw);
   const int c = blockIdx.x;
   if (c >= n_centres) return;
   const int i = centres[c];
-  const int n = sp->n_max, L1 = sp->l_max + 1, nlm = sp->nlm, K1 = sp->K1, d = sp->d, d_pad = sp->d_pad;
+  const int n = sp->n_max, L = sp->l_max, L1 = L + 1, nlm = sp->nlm, K1 = sp->K1, d = sp->d, d_pad = sp->d_pad, ns = sp->n_species;
+  const int n4 = ceil4(n), K1p = ns * n4, RFS = rf_stride(L1, n4), MP = m_pairs(L);
+  const double alpha = sp->alpha;
+  (void)d_pad;
   load_tables(sp, s);
   // u = dE/dp: pull gradPredict back through x = p/|p| (reference forward form: descriptors.f95:8595-8600)
-  const double* xr = x + (size_t)c * d_pad;
+  const double* xr = x + (size_t)c * sp->d_pad;
   const double* gr = gvec + (size_t)c * ldg;
   double loc = 0.0;
   for (int q = threadIdx.x; q < d - 1; q += NT) loc += xr[q] * gr[q];
   double sdot = block_sum(loc, s.red);
   double nrm = pnorm[c];
   for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = sp->normalise ? (gr[q] - xr[q] * sdot) / nrm : gr[q];
-  // stage X in the (not yet used) rf area, then Lambda = dE/dX_lm into s.X
-  double* Xs = s.rf;  // nlm*K1 doubles fit: checked on the host
+  // X_lm and Lambda = dE/dX_lm are staged in the (not yet used) radial-table area
+  double* Xs = s.rf;                       // nlm*K1
+  double* Ls = s.rf + (size_t)nlm * K1;    // nlm*K1
   for (int k = threadIdx.x; k < nlm * K1; k += NT) Xs[k] = xlm[(size_t)c * nlm * K1 + k];
+  for (int k = threadIdx.x; k < nlm * K1p; k += NT) s.X[k] = 0.0;
   __syncthreads();
   for (int idx = threadIdx.x; idx < nlm * K1; idx += NT) {
     int lm = idx / K1, ia = idx - lm * K1, l = s.lof[lm];
@@ -422,68 +506,87 @@ __global__ void __launch_bounds__(NT) k_soap_adjoint(const SoapDev* __restrict__
       double u = s.p[l + L1 * (hi * (hi + 1) / 2 + lo)];
       t += (ia == jb ? 2.0 * u : 1.41421356237309504880 * u) * Xs[lm * K1 + jb];
     }
-    s.X[idx] = t * sp->tlpo[l];
+    Ls[idx] = t * sp->tlpo[l];
+  }
+  __syncthreads();
+  // Lambda~_lm(s, a) = sum_a' T(a, a') Lambda_lm(s, a')  : the basis transform pulled back once per centre
+  for (int idx = threadIdx.x; idx < nlm * K1; idx += NT) {
+    int lm = idx / K1, ic = idx - lm * K1, sk = ic / n, a = ic - sk * n;
+    const double* lrow = Ls + (size_t)lm * K1 + sk * n;
+    double t = 0.0;
+    for (int b = 0; b < n; b++) t += s.T[a + n * b] * lrow[b];
+    s.X[(size_t)lm * K1p + sk * n4 + a] = t;
   }
   __syncthreads();
 
   double fi[3] = {0, 0, 0}, vir[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
   for (int pb = pbeg; pb < pend; pb += NBCAP) {
     int nv = gather_neighbours(sp, s, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
     for (int t0 = 0; t0 < nv; t0 += TNA) {
-      int tn = min(TNA, nv - t0);
-      stage_tile<true>(sp, s, t0, tn);
-      // one warp per neighbour: f_gp,k = sum_{l,a} [ c'_l(a) u_k (sum_m Lambda_lm Y_lm) + c_l(a) (sum_m Lambda_lm dY_lm,k) ]
-      for (int q = w; q < tn; q += NT / 32) {
-        const double r = s.nbr[t0 + q], rinv = 1.0 / r;
-        const double ux = s.nbd[3 * (t0 + q)] * rinv, uy = s.nbd[3 * (t0 + q) + 1] * rinv, uz = s.nbd[3 * (t0 + q) + 2] * rinv;
-        const int spq = s.nbs[t0 + q];
-        const double* Yq = s.Y + (size_t)q * nlm;
-        const double* dYq = s.dY + (size_t)q * nlm;
-        const int cs = TNA * nlm;
-        double f0 = 0, f1 = 0, f2 = 0;
-        for (int it = lane; it < L1 * n; it += 32) {
-          int l = it / n, a = it - l * n;
-          double B = 0, D0 = 0, D1 = 0, D2 = 0;
-          for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) {
-            double lam = s.X[lm * K1 + spq * n + a];
-            B += lam * Yq[lm];
-            D0 += lam * dYq[lm];
-            D1 += lam * dYq[cs + lm];
-            D2 += lam * dYq[2 * cs + lm];
-          }
-          double cl = s.rf[((size_t)q * L1 + l) * n + a], dcl = s.drf[((size_t)q * L1 + l) * n + a];
-          f0 += dcl * ux * B + cl * D0;
-          f1 += dcl * uy * B + cl * D1;
-          f2 += dcl * uz * B + cl * D2;
-        }
-        f0 = warp_sum(f0) * e_scale;
-        f1 = warp_sum(f1) * e_scale;
-        f2 = warp_sum(f2) * e_scale;
-        if (lane == 0) {
-          // IPModel_GAP.f95:479-491: F_j -= f_gp ; centre row is minus the sum ; W_j -= (pos_j - pos_i) (x) f_gp
-          int j = s.nbj[t0 + q];
-          if (force) {
-            atomicAdd(&force[3 * (size_t)j + 0], -f0);
-            atomicAdd(&force[3 * (size_t)j + 1], -f1);
-            atomicAdd(&force[3 * (size_t)j + 2], -f2);
-            fi[0] += f0; fi[1] += f1; fi[2] += f2;
-          }
-          const double dx = s.nbd[3 * (t0 + q)], dy = s.nbd[3 * (t0 + q) + 1], dz = s.nbd[3 * (t0 + q) + 2];
-          double wv[9] = {dx * f0, dy * f0, dz * f0, dx * f1, dy * f1, dz * f1, dx * f2, dy * f2, dz * f2};  // column-major (a + 3b)
-#pragma unroll
-          for (int k = 0; k < 9; k++) vir[k] -= wv[k];
-          if (local_virial)
-#pragma unroll
-            for (int k = 0; k < 9; k++) atomicAdd(&local_virial[9 * (size_t)j + k], -wv[k]);
-        }
+      const int tn = min(TNA, nv - t0);
+      // ---- stage: radial tables with derivative ----
+      for (int it = threadIdx.x; it < tn * n4; it += NT) {
+        int q = it / n4, a = it - q * n4;
+        if (a < n)
+          radial_item<true>(alpha, s.nbr[t0 + q], s.rb[a], s.nbf[t0 + q], s.nbdf[t0 + q], L, s.rf + (size_t)q * RFS + a,
+                            s.drf + (size_t)q * RFS + a, n4);
+        else
+          for (int l = 0; l < L1; l++) s.rf[(size_t)q * RFS + l * n4 + a] = s.drf[(size_t)q * RFS + l * n4 + a] = 0.0;
       }
       __syncthreads();
+      // ---- contract: item (m-pair, neighbour); orders are paired (m, L+1-m) so that every item has about L+2 (l,m) terms ----
+      for (int it = threadIdx.x; it < tn * MP; it += NT) {
+        const int mp = it / tn, q = it - mp * tn;
+        const double r = s.nbr[t0 + q], rinv = 1.0 / r;
+        const double ux = s.nbd[3 * (t0 + q)] * rinv, uy = s.nbd[3 * (t0 + q) + 1] * rinv, uz = s.nbd[3 * (t0 + q) + 2] * rinv;
+        const double* lam = s.X + s.nbs[t0 + q] * n4;
+        const double* rfq = s.rf + (size_t)q * RFS;
+        const double* drq = s.drf + (size_t)q * RFS;
+        double SA = 0, G0 = 0, G1 = 0, G2 = 0;
+        adjoint_order(s.ynorm, L, mp, ux, uy, uz, lam, K1p, rfq, drq, n4, SA, G0, G1, G2);
+        const int m2 = L + 1 - mp;
+        if (mp > 0 && m2 > mp) adjoint_order(s.ynorm, L, m2, ux, uy, uz, lam, K1p, rfq, drq, n4, SA, G0, G1, G2);
+        const double ug = ux * G0 + uy * G1 + uz * G2;
+        double* pp = s.part + ((size_t)q * MP + mp) * 3;
+        pp[0] = SA * ux + (G0 - ux * ug) * rinv;
+        pp[1] = SA * uy + (G1 - uy * ug) * rinv;
+        pp[2] = SA * uz + (G2 - uz * ug) * rinv;
+      }
+      __syncthreads();
+      // ---- scatter: one thread per neighbour ----
+      if (threadIdx.x < tn) {
+        const int q = threadIdx.x;
+        double f0 = 0, f1 = 0, f2 = 0;
+        for (int mp = 0; mp < MP; mp++) {
+          const double* pp = s.part + ((size_t)q * MP + mp) * 3;
+          f0 += pp[0]; f1 += pp[1]; f2 += pp[2];
+        }
+        f0 *= e_scale; f1 *= e_scale; f2 *= e_scale;
+        // IPModel_GAP.f95:479-491: F_j -= f_gp ; centre row is minus the sum ; W_j -= (pos_j - pos_i) (x) f_gp
+        const int j = s.nbj[t0 + q];
+        if (force) {
+          atomicAdd(&force[3 * (size_t)j + 0], -f0);
+          atomicAdd(&force[3 * (size_t)j + 1], -f1);
+          atomicAdd(&force[3 * (size_t)j + 2], -f2);
+          fi[0] += f0; fi[1] += f1; fi[2] += f2;
+        }
+        const double dx = s.nbd[3 * (t0 + q)], dy = s.nbd[3 * (t0 + q) + 1], dz = s.nbd[3 * (t0 + q) + 2];
+        double wv[9] = {dx * f0, dy * f0, dz * f0, dx * f1, dy * f1, dz * f1, dx * f2, dy * f2, dz * f2};  // column-major (a + 3b)
+#pragma unroll
+        for (int k = 0; k < 9; k++) vir[k] -= wv[k];
+        if (local_virial)
+#pragma unroll
+          for (int k = 0; k < 9; k++) atomicAdd(&local_virial[9 * (size_t)j + k], -wv[k]);
+      }
+      // the next tile's stage phase overwrites rf/drf only after the barrier at its end; part is rewritten after that barrier too
     }
   }
-  // combine the 4 warp leaders in fixed order
+  // combine the per-thread centre force / virial partials in fixed order (threads 0..TNA-1 hold them)
+  for (int k = 0; k < 3; k++) fi[k] = warp_sum(fi[k]);
+  for (int k = 0; k < 9; k++) vir[k] = warp_sum(vir[k]);
   __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) {
     for (int k = 0; k < 3; k++) s.red[w * 12 + k] = fi[k];
     for (int k = 0; k < 9; k++) s.red[w * 12 + 3 + k] = vir[k];
