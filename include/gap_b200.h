@@ -64,7 +64,10 @@ int gap_potential_calc(gap_potential* pot, int N, const double* pos, const int* 
  *   d_local_e : device double[N] or NULL ; d_local_virial : device double[9*N] or NULL
  *   want_grad : 0 = energy only
  *   stream    : cudaStream_t (as void*) the work is enqueued on; NULL = the handle's own stream.
- * Returns after enqueueing except for two small device->host reads (neighbour count, centre count). */
+ * The neighbour list is sized speculatively from the previous call with the same N and partition and nothing is read
+ * back in mid-stream; the entry count is verified when the stream has drained, so from the second call on the
+ * function returns after the work has COMPLETED (and transparently repeats the evaluation if the list overflowed).
+ * The first call for a given N synchronises once after the neighbour count and returns after enqueueing the rest. */
 int gap_potential_calc_device(gap_potential* pot, int N, const double* d_pos, const int* d_Z, const double* lattice,
                               const int* pbc, const char* args_str, int want_grad, double* d_packed, double* d_local_e,
                               double* d_local_virial, void* stream);

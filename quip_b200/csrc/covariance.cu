@@ -12,9 +12,12 @@
 //
 // Both GEMMs are the same "NT" kernel (A[m][k], B[n][k], K contiguous in both), built on the FP64 tensor-core
 // instruction mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- tcgen05 has no FP64 kind), fed by a 3-stage
-// cp.async pipeline.  CTA tile 128x128x16, 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 DMMA tiles,
-// 64 FP64 accumulators per thread.  Shared-memory rows are padded to 20 doubles so that the (8 rows x 4 k)
-// fragment loads of a half-warp hit 16 distinct 8-byte banks.
+// cp.async pipeline.  CTA tile 64 x BN x 16 (BN = 128 or 112), 4 warps as 2(M) x 2(N), warp tile 32 x BN/2 =
+// 4 x (8 or 7) DMMA tiles, TWO CTAs resident per SM so that one CTA's epilogue (the kernel non-linearity and the
+// 64 x BN store) overlaps the other's main loop and the tail is balanced at half-tile granularity.  GEMM-2 can be
+// split along K (= the sparse-point index) into `ksplit` partial outputs when it has too few tiles to fill 148 SMs;
+// the consumer (the SOAP adjoint kernel) adds the partials in a fixed order.  Shared-memory rows are padded to
+// 20 doubles so that the (8 rows x 4 k) fragment loads of a half-warp hit 16 distinct 8-byte banks.
 #include <type_traits>
 
 #include "gap_device.cuh"
@@ -23,13 +26,14 @@ namespace gapb200 {
 
 namespace {
 
-constexpr int BM = COV_BM, BN = COV_BN, BK = COV_BK;
-constexpr int WARPS_M = 2, WARPS_N = 4, NTHREADS = WARPS_M * WARPS_N * 32;
-constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;  // 64 x 32
-constexpr int MT = WTM / 8, NTL = WTN / 8;             // 8 x 4 DMMA tiles per warp
-constexpr int LDS_ROW = BK + 4;                        // padded row (doubles)
+constexpr int BM = COV_BM, BK = COV_BK;
+constexpr int WARPS_M = 2, WARPS_N = 2, NTHREADS = WARPS_M * WARPS_N * 32;
+constexpr int WTM = BM / WARPS_M;   // 32
+constexpr int MT = WTM / 8;         // 4 DMMA tiles along M per warp
+constexpr int LDS_ROW = BK + 4;     // padded row (doubles)
 constexpr int STAGES = 3;
-constexpr size_t GEMM_SMEM = (size_t)STAGES * (BM + BN) * LDS_ROW * sizeof(double);
+template <int BN>
+constexpr size_t gemm_smem() { return (size_t)STAGES * (BM + BN) * LDS_ROW * sizeof(double); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -43,24 +47,42 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// load one K-slab (BK columns) of the A and B tiles into stage `st`
+// load one K-slab (BK columns) of the A and B tiles into a stage
+template <int BN>
 __device__ __forceinline__ void load_stage(double* As, double* Bs, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                                            int m0, int n0, int k0) {
-  // BM*BK/2 16-byte chunks for A, same for B: 1024 + 1024 chunks / 256 threads = 4 + 4 each
-#pragma unroll
-  for (int it = 0; it < (BM * BK / 2) / NTHREADS; it++) {
-    int chunk = threadIdx.x + it * NTHREADS;
-    int row = chunk / (BK / 2), cc = (chunk % (BK / 2)) * 2;
+  constexpr int CPR = BK / 2;  // 16-byte chunks per row
+  for (int chunk = threadIdx.x; chunk < BM * CPR; chunk += NTHREADS) {
+    int row = chunk / CPR, cc = (chunk % CPR) * 2;
     cp_async16(As + row * LDS_ROW + cc, A + (size_t)(m0 + row) * lda + k0 + cc);
   }
-#pragma unroll
-  for (int it = 0; it < (BN * BK / 2) / NTHREADS; it++) {
-    int chunk = threadIdx.x + it * NTHREADS;
-    int row = chunk / (BK / 2), cc = (chunk % (BK / 2)) * 2;
+  for (int chunk = threadIdx.x; chunk < BN * CPR; chunk += NTHREADS) {
+    int row = chunk / CPR, cc = (chunk % CPR) * 2;
     cp_async16(Bs + row * LDS_ROW + cc, B + (size_t)(n0 + row) * ldb + k0 + cc);
   }
 }
 
+// c^(zeta-1).  ZI = compile-time integer zeta (1..4, the usual GAP settings; fast_pow_1d multiplies repeatedly,
+// gp_predict.f95:3581-3605); ZI = 0 is the general case, kept OUT of line: inlined into the fully unrolled epilogue
+// (64 copies of the pow() slow path) it made the kernel instruction-cache bound.
+__device__ __noinline__ double pow_zm1_general(double c, double zeta, int zeta_int) {
+  if (zeta_int >= 1) {
+    double r = 1.0;
+    for (int i = 0; i < zeta_int - 1; i++) r *= c;
+    return r;
+  }
+  return zeta_int == 0 ? 0.0 : pow(c, zeta - 1.0);
+}
+template <int ZI>
+__device__ __forceinline__ double pow_zm1(double c, const CovParams& cp) {
+  if (ZI == 1) return 1.0;
+  if (ZI == 2) return c;
+  if (ZI == 3) return c * c;
+  if (ZI == 4) return (c * c) * c;
+  return pow_zm1_general(c, cp.zeta, cp.zeta_int);
+}
+
+template <int ZI>
 struct EpiCov {  // GEMM-1 epilogue
   const double* alpha;
   const double* cutoff;
@@ -70,25 +92,23 @@ struct EpiCov {  // GEMM-1 epilogue
   double* epart;
   int n_tiles_n;
   int M;  // real number of sparse points; columns >= M are padding
+  __device__ __forceinline__ double pw(double c) const { return pow_zm1<ZI>(c, cp); }
 };
 struct EpiStore {  // GEMM-2 epilogue
   double* out;
   int ldo;
+  size_t split_stride;  // doubles between the partial outputs of consecutive K splits
 };
 
-__device__ __forceinline__ double ipow(double v, int e) {  // fast_pow_1d: v**e_int by repeated multiplication
-  double r = 1.0;
-  for (int i = 0; i < e; i++) r *= v;
-  return r;
-}
-
-template <class Epi>
-__global__ void __launch_bounds__(NTHREADS, 1) k_dgemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int K,
-                                                          Epi epi) {
+template <int BN, class Epi>
+__global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int K,
+                                                          int row0, const int* __restrict__ n_rows_dev, Epi epi) {
+  constexpr int WTN = BN / WARPS_N, NTL = WTN / 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* As = (double*)smem_raw;                  // [STAGES][BM][LDS_ROW]
   double* Bs = As + (size_t)STAGES * BM * LDS_ROW;  // [STAGES][BN][LDS_ROW]
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (n_rows_dev && row0 + m0 >= *n_rows_dev) return;  // row tile beyond the (device-side) number of centres
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const int fr = lane >> 2, fk = lane & 3;  // fragment row (0..7) and k (0..3)
@@ -99,10 +119,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dgemm_nt(const double* __restri
 #pragma unroll
     for (int j = 0; j < NTL; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const int KT = K / BK;
+  // K range of this split (blockIdx.z of gridDim.z), in BK slabs
+  const int KT_all = K / BK;
+  const int kt_beg = (int)((long long)KT_all * blockIdx.z / gridDim.z), kt_end = (int)((long long)KT_all * (blockIdx.z + 1) / gridDim.z);
+  const int KT = kt_end - kt_beg;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
-    if (s < KT) load_stage(As + (size_t)s * BM * LDS_ROW, Bs + (size_t)s * BN * LDS_ROW, A, lda, B, ldb, m0, n0, s * BK);
+    if (s < KT) load_stage<BN>(As + (size_t)s * BM * LDS_ROW, Bs + (size_t)s * BN * LDS_ROW, A, lda, B, ldb, m0, n0, (kt_beg + s) * BK);
     cp_async_commit();
   }
   for (int kt = 0; kt < KT; kt++) {
@@ -112,7 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dgemm_nt(const double* __restri
       int kn = kt + STAGES - 1;
       if (kn < KT) {
         int s = kn % STAGES;
-        load_stage(As + (size_t)s * BM * LDS_ROW, Bs + (size_t)s * BN * LDS_ROW, A, lda, B, ldb, m0, n0, kn * BK);
+        load_stage<BN>(As + (size_t)s * BM * LDS_ROW, Bs + (size_t)s * BN * LDS_ROW, A, lda, B, ldb, m0, n0, (kt_beg + kn) * BK);
       }
       cp_async_commit();
     }
@@ -135,8 +158,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dgemm_nt(const double* __restri
   __syncthreads();
 
   // ---- epilogue: thread holds C[row = fr][col = 2*fk, 2*fk+1] of every 8x8 tile ----
-  if constexpr (std::is_same<Epi, EpiCov>::value) {
-    const EpiCov& e = *reinterpret_cast<const EpiCov*>(&epi);
+  if constexpr (!std::is_same<Epi, EpiStore>::value) {
+    const Epi& e = epi;
     double* red = (double*)smem_raw;  // [WARPS_N][BM]
     double al[NTL][2], cu[NTL][2];
 #pragma unroll
@@ -158,7 +181,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dgemm_nt(const double* __restri
         for (int t = 0; t < 2; t++) {
           double c = acc[i][j][t];
           if (n0 + wn * WTN + j * 8 + 2 * fk + t >= e.M) { outv[t] = 0.0; continue; }
-          double pw = e.cp.zeta_int >= 1 ? ipow(c, e.cp.zeta_int - 1) : (e.cp.zeta_int == 0 ? 0.0 : pow(c, e.cp.zeta - 1.0));
+          double pw = e.pw(c);
           double kval = e.cp.zeta_int == 0 ? e.cp.delta2 : e.cp.delta2 * (pw * c);
           esum += al[j][t] * (kval * cu[j][t]);
           outv[t] = al[j][t] * e.cp.delta2 * e.cp.zeta * pw * cu[j][t];
@@ -171,29 +194,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_dgemm_nt(const double* __restri
       if (fk == 0) red[wn * BM + wm * WTM + i * 8 + fr] = esum;
     }
     __syncthreads();
-    if (threadIdx.x < BM) {
-      double t = (red[threadIdx.x] + red[BM + threadIdx.x]) + (red[2 * BM + threadIdx.x] + red[3 * BM + threadIdx.x]);
-      e.epart[(size_t)(m0 + threadIdx.x) * e.n_tiles_n + blockIdx.x] = t;
-    }
+    if (threadIdx.x < BM) e.epart[(size_t)(m0 + threadIdx.x) * e.n_tiles_n + blockIdx.x] = red[threadIdx.x] + red[BM + threadIdx.x];
   } else {
     const EpiStore& e = *reinterpret_cast<const EpiStore*>(&epi);
+    double* out = e.out + (size_t)blockIdx.z * e.split_stride;
 #pragma unroll
     for (int i = 0; i < MT; i++) {
       int row = m0 + wm * WTM + i * 8 + fr;
 #pragma unroll
       for (int j = 0; j < NTL; j++) {
         int col = n0 + wn * WTN + j * 8 + 2 * fk;
-        *reinterpret_cast<double2*>(e.out + (size_t)row * e.ldo + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+        *reinterpret_cast<double2*>(out + (size_t)row * e.ldo + col) = make_double2(acc[i][j][0], acc[i][j][1]);
       }
     }
   }
 }
 
 // E_i = sum over column tiles (fixed order) ; local_e(centre) += E_i  (IPModel_GAP.f95:454-459 with cc = 1, |ci| = 1)
-__global__ void k_energy_rows(const double* __restrict__ epart, int n_tiles_n, const int* __restrict__ centres, int n_centres, double e_scale,
-                              double* __restrict__ local_e) {
+__global__ void k_energy_rows(const double* __restrict__ epart, int n_tiles_n, const int* __restrict__ centres, const int* __restrict__ n_centres_dev,
+                              int n_centres_ub, double e_scale, double* __restrict__ local_e) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_centres) return;
+  if (c >= (n_centres_dev ? *n_centres_dev : n_centres_ub)) return;
   double t = 0.0;
   for (int k = 0; k < n_tiles_n; k++) t += epart[(size_t)c * n_tiles_n + k];
   local_e[centres[c]] += e_scale * t;
@@ -201,29 +222,61 @@ __global__ void k_energy_rows(const double* __restrict__ epart, int n_tiles_n, c
 
 }  // namespace
 
-void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int M, int M_pad, int K_pad, const double* alpha,
-                      const double* cutoff, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n, cudaStream_t st,
-                      int* launches) {
-  EpiCov e{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M};
-  cudaFuncSetAttribute(k_dgemm_nt<EpiCov>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-  dim3 grid(M_pad / BN, n_rows_pad / BM);
-  k_dgemm_nt<EpiCov><<<grid, NTHREADS, GEMM_SMEM, st>>>(x, ldx, sp_rows, lds, K_pad, e);
+void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int row0, const int* n_rows_dev, int M, int M_pad,
+                      int K_pad, const double* alpha, const double* cutoff, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n,
+                      cudaStream_t st, int* launches) {
+  constexpr int BN = COV_BN1;
+  dim3 grid(M_pad / BN, n_rows_pad / BM, 1);
+  auto go = [&](auto e) {
+    using E = decltype(e);
+    cudaFuncSetAttribute(k_dgemm_nt<BN, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<BN>());
+    k_dgemm_nt<BN, E><<<grid, NTHREADS, gemm_smem<BN>(), st>>>(x, ldx, sp_rows, lds, K_pad, row0, n_rows_dev, e);
+  };
+  switch (cp.zeta_int) {
+    case 1: go(EpiCov<1>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
+    case 2: go(EpiCov<2>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
+    case 3: go(EpiCov<3>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
+    case 4: go(EpiCov<4>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
+    default: go(EpiCov<0>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
+  }
   *launches += 1;
 }
 
-void launch_cov_gemm2(const double* acoef, int lda, const double* st_rows, int ldst, int n_rows_pad, int dn_pad, int K_pad, double* gvec,
-                      int ldg, cudaStream_t st, int* launches) {
-  EpiStore e{gvec, ldg};
-  cudaFuncSetAttribute(k_dgemm_nt<EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-  dim3 grid(dn_pad / BN, n_rows_pad / BM);
-  k_dgemm_nt<EpiStore><<<grid, NTHREADS, GEMM_SMEM, st>>>(acoef, lda, st_rows, ldst, K_pad, e);
+int cov_gemm2_bn(int d) {  // column tile of GEMM-2: whichever of 128 / 112 pads the descriptor dimension less
+  int p128 = (d + 127) / 128 * 128, p112 = (d + 111) / 112 * 112;
+  return p112 < p128 ? 112 : 128;
+}
+
+int cov_gemm2_ksplit(int n_rows_pad, int dn_pad, int bn, int n_sm) {  // K splits that best fill 2 CTA slots per SM
+  long tiles = (long)(n_rows_pad / BM) * (dn_pad / bn), slots = 2L * n_sm;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ks = 1; ks <= COV_MAX_KSPLIT; ks++) {
+    long units = tiles * ks, waves = (units + slots - 1) / slots;
+    double eff = (double)units / (double)(waves * slots);
+    if (eff > best_eff + 0.03) { best_eff = eff; best = ks; }
+  }
+  return best;
+}
+
+void launch_cov_gemm2(const double* acoef, int lda, const double* st_rows, int ldst, int n_rows_pad, int row0, const int* n_rows_dev, int dn_pad,
+                      int bn, int ksplit, int K_pad, double* gvec, int ldg, size_t split_stride, cudaStream_t st, int* launches) {
+  EpiStore e{gvec, ldg, split_stride};
+  dim3 grid(dn_pad / bn, n_rows_pad / BM, ksplit);
+  if (bn == 112) {
+    cudaFuncSetAttribute(k_dgemm_nt<112, EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<112>());
+    k_dgemm_nt<112, EpiStore><<<grid, NTHREADS, gemm_smem<112>(), st>>>(acoef, lda, st_rows, ldst, K_pad, row0, n_rows_dev, e);
+  } else {
+    cudaFuncSetAttribute(k_dgemm_nt<128, EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128>());
+    k_dgemm_nt<128, EpiStore><<<grid, NTHREADS, gemm_smem<128>(), st>>>(acoef, lda, st_rows, ldst, K_pad, row0, n_rows_dev, e);
+  }
   *launches += 1;
 }
 
-void launch_energy_rows(const double* epart, int n_tiles_n, const int* centres, int n_centres, double e_scale, double* local_e,
-                        cudaStream_t st, int* launches) {
-  if (n_centres <= 0) return;
-  k_energy_rows<<<(n_centres + 255) / 256, 256, 0, st>>>(epart, n_tiles_n, centres, n_centres, e_scale, local_e);
+void launch_energy_rows(const double* epart, int n_tiles_n, const int* centres, const int* n_centres_dev, int n_centres_ub, double e_scale,
+                        double* local_e, cudaStream_t st, int* launches) {
+  if (n_centres_ub <= 0) return;
+  k_energy_rows<<<(n_centres_ub + 255) / 256, 256, 0, st>>>(epart, n_tiles_n, centres, n_centres_dev, n_centres_ub, e_scale, local_e);
   *launches += 1;
 }
 

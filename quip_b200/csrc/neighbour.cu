@@ -3,10 +3,10 @@
 //
 // Design (B200-first, not the reference's linked lists): atoms are binned into a cell grid with
 // cell width >= cutoff, sorted by cell with a stable radix sort (order inside a cell = ascending atom
-// index, so everything downstream is deterministic), and one thread per atom -- in sorted order, so
-// that the threads of a warp walk the same candidate cells and their loads coalesce/broadcast --
-// scans the (2R+1)^3 surrounding cells twice (count, exclusive scan, fill) into a CSR list holding
-// the FULL list (both directions; the reference stores a half list plus back references).
+// index, so everything downstream is deterministic), and one WARP per atom -- lanes sweep the
+// candidates of the (2R+1)^3 surrounding cells 32 at a time -- scans them twice (count, exclusive
+// scan, fill) into a CSR list holding the FULL list (both directions; the reference stores a half
+// list plus back references).
 //
 // Bit-exactness: the accept test d < cutoff uses the reference's operation order without FMA
 // (image_diff/norm_nofma in gap_device.cuh), on the ORIGINAL positions and the total integer shift
@@ -57,8 +57,10 @@ __global__ void k_minmax_final(const double* __restrict__ part, int nb, double* 
   out6[r] = v;
 }
 
+// err_flag: set when an atom lies more than MAX_MAP_SHIFT periodic images away from the cell (shifts are carried as int8)
+constexpr int MAX_MAP_SHIFT = 60;
 __global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int* __restrict__ cell_of, int* __restrict__ mshift,
-                      int* __restrict__ cell_count, int* __restrict__ iota) {
+                      int* __restrict__ cell_count, int* __restrict__ iota, int* __restrict__ err_flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double t[3];
@@ -68,7 +70,9 @@ __global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int*
   for (int r = 0; r < 3; r++) {
     double u;
     if (grid.pbc[r]) {
-      ms[r] = -(int)floor(t[r] + 0.5);  // map_shift, Connection.f95:1574
+      double fl = -floor(t[r] + 0.5);  // map_shift, Connection.f95:1574
+      if (!(fabs(fl) <= (double)MAX_MAP_SHIFT)) { atomicOr(err_flag, 1); fl = 0.0; }
+      ms[r] = (int)fl;
       u = t[r] + (double)ms[r] + 0.5;
     } else {
       ms[r] = 0;
@@ -97,59 +101,102 @@ __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __res
 
 __device__ __forceinline__ int floor_div(int a, int n) { return (a >= 0) ? a / n : -((-a + n - 1) / n); }
 
+// One WARP per atom (in cell-sorted order).  The (2R+1)^3 surrounding cells are taken 32 at a time: lane k looks up
+// cell k's range and image shift, a warp scan turns the counts into a flattened candidate index space, and the lanes
+// sweep that space 32 candidates per step (a shuffle-based binary search maps a candidate to its cell).  Accepted
+// pairs are written in candidate order through ballot/popc, so the list order is deterministic: cells in (o2,o1,o0)
+// order, ascending atom index inside a cell.
+constexpr int NEIGH_WARPS = 4;
+
 template <bool FILL>
-__global__ void k_neigh(int N, int first, int last, CellGrid grid, const int* __restrict__ sort_idx, const int* __restrict__ sort_keys,
-                        const double* __restrict__ spos, const int* __restrict__ smshift, const int* __restrict__ cell_start,
-                        int* __restrict__ nn, const int* __restrict__ nbr_off, int* __restrict__ nbr_j, int* __restrict__ nbr_s,
-                        double* __restrict__ nbr_d) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, int last, CellGrid grid, const int* __restrict__ sort_idx,
+                                                            const int* __restrict__ sort_keys, const double* __restrict__ spos,
+                                                            const int* __restrict__ smshift, const int* __restrict__ cell_start,
+                                                            int* __restrict__ nn, const int* __restrict__ nbr_off, int* __restrict__ nbr_j,
+                                                            int* __restrict__ nbr_s, double* __restrict__ nbr_d, int cap) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * NEIGH_WARPS + (threadIdx.x >> 5);
   if (p >= N) return;
   const int i = sort_idx[p];
   if (i < first || i >= last) {  // not a centre of this partition (descriptor_atomic_MPI_setup mask): empty row
-    if (!FILL) nn[i] = 0;
+    if (!FILL && lane == 0) nn[i] = 0;
     return;
   }
   const int cell = sort_keys[p];
-  int c0 = cell % grid.n[0], c1 = (cell / grid.n[0]) % grid.n[1], c2 = cell / (grid.n[0] * grid.n[1]);
-  double pi[3] = {spos[3 * (size_t)p], spos[3 * (size_t)p + 1], spos[3 * (size_t)p + 2]};
+  const int c0 = cell % grid.n[0], c1 = (cell / grid.n[0]) % grid.n[1], c2 = cell / (grid.n[0] * grid.n[1]);
+  const double pi[3] = {spos[3 * (size_t)p], spos[3 * (size_t)p + 1], spos[3 * (size_t)p + 2]};
   int mi0, mi1, mi2;
   unpack_shift(smshift[p], mi0, mi1, mi2);
-  int count = 0;
-  int w = FILL ? nbr_off[i] : 0;
+  const int w0 = 2 * grid.R[0] + 1, w1 = 2 * grid.R[1] + 1, w2 = 2 * grid.R[2] + 1;
+  const int n_nb_cells = w0 * w1 * w2;
   const double cutoff = grid.cutoff;
-  for (int o2 = -grid.R[2]; o2 <= grid.R[2]; o2++) {
-    int z = c2 + o2, s2 = 0;
-    if (grid.pbc[2]) { s2 = floor_div(z, grid.n[2]); z -= s2 * grid.n[2]; } else if (z < 0 || z >= grid.n[2]) continue;
-    for (int o1 = -grid.R[1]; o1 <= grid.R[1]; o1++) {
-      int y = c1 + o1, s1 = 0;
-      if (grid.pbc[1]) { s1 = floor_div(y, grid.n[1]); y -= s1 * grid.n[1]; } else if (y < 0 || y >= grid.n[1]) continue;
-      for (int o0 = -grid.R[0]; o0 <= grid.R[0]; o0++) {
-        int x = c0 + o0, s0 = 0;
-        if (grid.pbc[0]) { s0 = floor_div(x, grid.n[0]); x -= s0 * grid.n[0]; } else if (x < 0 || x >= grid.n[0]) continue;
+  int count = 0;
+  int wpos = FILL ? nbr_off[i] : 0;
+  for (int cbase = 0; cbase < n_nb_cells; cbase += 32) {
+    // lane -> one neighbouring cell
+    int ck = cbase + lane, qb = 0, cnt = 0, sh = 0;
+    if (ck < n_nb_cells) {
+      int o0 = ck % w0 - grid.R[0], o1 = (ck / w0) % w1 - grid.R[1], o2 = ck / (w0 * w1) - grid.R[2];
+      int x = c0 + o0, y = c1 + o1, z = c2 + o2, s0 = 0, s1 = 0, s2 = 0;
+      bool ok = true;
+      if (grid.pbc[0]) { s0 = floor_div(x, grid.n[0]); x -= s0 * grid.n[0]; } else if (x < 0 || x >= grid.n[0]) ok = false;
+      if (grid.pbc[1]) { s1 = floor_div(y, grid.n[1]); y -= s1 * grid.n[1]; } else if (y < 0 || y >= grid.n[1]) ok = false;
+      if (grid.pbc[2]) { s2 = floor_div(z, grid.n[2]); z -= s2 * grid.n[2]; } else if (z < 0 || z >= grid.n[2]) ok = false;
+      if (ok) {
         int nc = (z * grid.n[1] + y) * grid.n[0] + x;
-        int qb = cell_start[nc], qe = cell_start[nc + 1];
-        for (int q = qb; q < qe; q++) {
-          int mj0, mj1, mj2;
-          unpack_shift(smshift[q], mj0, mj1, mj2);
-          int t0 = s0 - mi0 + mj0, t1 = s1 - mi1 + mj1, t2 = s2 - mi2 + mj2;
-          if (q == p && t0 == 0 && t1 == 0 && t2 == 0) continue;  // self, zero shift (:1266-1272)
-          double dd[3];
-          image_diff(pi, spos + 3 * (size_t)q, grid.lat, t0, t1, t2, dd);
-          double d = norm_nofma(dd);
-          if (d < cutoff) {  // strict, Connection.f95:517
-            if (FILL) {
-              nbr_j[w] = sort_idx[q];
-              nbr_s[w] = pack_shift(t0, t1, t2);
-              if (nbr_d) nbr_d[w] = d;
-              w++;
-            }
-            count++;
-          }
-        }
+        qb = cell_start[nc];
+        cnt = cell_start[nc + 1] - qb;
+        sh = pack_shift(s0 - mi0, s1 - mi1, s2 - mi2);
       }
     }
+    int pre = cnt;  // inclusive scan of the counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    for (int base = 0; base < total; base += 32) {
+      const int t = base + lane;
+      // smallest k with pre_k > t
+      int k = 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        int v = __shfl_sync(0xffffffffu, pre, k + o - 1);
+        if (v <= t) k += o;
+      }
+      const int pk = __shfl_sync(0xffffffffu, pre, k), ck_cnt = __shfl_sync(0xffffffffu, cnt, k), kqb = __shfl_sync(0xffffffffu, qb, k),
+                ksh = __shfl_sync(0xffffffffu, sh, k);
+      bool acc = false;
+      int q = 0, t0 = 0, t1 = 0, t2 = 0;
+      double d = 0.0;
+      if (t < total) {
+        q = kqb + (t - (pk - ck_cnt));
+        int mj0, mj1, mj2, b0, b1, b2;
+        unpack_shift(smshift[q], mj0, mj1, mj2);
+        unpack_shift(ksh, b0, b1, b2);
+        t0 = b0 + mj0; t1 = b1 + mj1; t2 = b2 + mj2;
+        if (!(q == p && t0 == 0 && t1 == 0 && t2 == 0)) {  // self, zero shift (:1266-1272)
+          double dd[3];
+          image_diff(pi, spos + 3 * (size_t)q, grid.lat, t0, t1, t2, dd);
+          d = norm_nofma(dd);
+          acc = d < cutoff;  // strict, Connection.f95:517
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, acc);
+      if (FILL && acc) {
+        int w = wpos + __popc(bal & ((1u << lane) - 1u));
+        if (w < cap) {  // cap < total only when a speculatively sized list overflowed; the host then repeats the call
+          nbr_j[w] = sort_idx[q];
+          nbr_s[w] = pack_shift(t0, t1, t2);
+          if (nbr_d) nbr_d[w] = d;
+        }
+      }
+      wpos += __popc(bal);
+      count += __popc(bal);
+    }
   }
-  if (!FILL) nn[i] = count;
+  if (!FILL && lane == 0) nn[i] = count;
 }
 
 }  // namespace
@@ -176,7 +223,7 @@ void launch_frac_minmax(const double* pos, int N, const double*, const CellGrid&
 void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell, NeighbourWork& w, cudaStream_t st, int* launches) {
   cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (ncell + 1), st);
   int nb = (N + 255) / 256;
-  k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.cell_count, w.iota);
+  k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.cell_count, w.iota, w.err_flag);
   size_t bytes = w.cub_bytes;
   cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.cell_count, w.cell_start, ncell + 1, st);
   int bits = 1;
@@ -190,9 +237,9 @@ void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell,
 void launch_neigh_count(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, cudaStream_t st,
                         int* launches) {
   (void)pos;
-  int nb = (N + 127) / 128;
-  k_neigh<false><<<nb, 128, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nullptr, nullptr, nullptr,
-                                     nullptr);
+  int nb = (N + NEIGH_WARPS - 1) / NEIGH_WARPS;
+  k_neigh<false><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nullptr, nullptr, nullptr,
+                                     nullptr, 0);
   cudaMemsetAsync(w.nn + N, 0, sizeof(int), st);
   size_t bytes = w.cub_bytes;
   cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.nn, nbr_off, N + 1, st);
@@ -200,10 +247,10 @@ void launch_neigh_count(const double* pos, int N, int first, int last, const Cel
 }
 
 void launch_neigh_fill(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, const int* nbr_off, int* nbr_j,
-                       int* nbr_s, double* nbr_d, cudaStream_t st, int* launches) {
+                       int* nbr_s, double* nbr_d, int cap, cudaStream_t st, int* launches) {
   (void)pos;
-  int nb = (N + 127) / 128;
-  k_neigh<true><<<nb, 128, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nbr_off, nbr_j, nbr_s, nbr_d);
+  int nb = (N + NEIGH_WARPS - 1) / NEIGH_WARPS;
+  k_neigh<true><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nbr_off, nbr_j, nbr_s, nbr_d, cap);
   *launches += 1;
 }
 

@@ -66,7 +66,7 @@ struct CoordDev {
   SoapDev h;
   SoapDev* d_sp = nullptr;
   double *sp_rows = nullptr, *st_rows = nullptr, *alpha = nullptr, *scut = nullptr;
-  int M = 0, M_pad = 0, d_pad = 0, dn_pad = 0;
+  int M = 0, M_pad = 0, d_pad = 0, dn_pad = 0, bn2 = 128;
   CovParams cp;
   // distance_2b
   Pair2bDev p2;
@@ -82,6 +82,17 @@ struct gap_potential {
   std::vector<CoordDev> cd;
   double* d_e0 = nullptr;
   int rank = 0, n_ranks = 1;
+  int n_sm = 148;
+  int g_splits = 1;            // K splits of the last GEMM-2 (partial gvec buffers)
+  size_t g_split_stride = 0;
+  // speculative neighbour-list sizing: the entry count of the previous call sizes the buffers of the next one, the
+  // real count comes back asynchronously (pinned) and is verified after the final synchronisation of the call
+  int* h_pin = nullptr;        // pinned [2]: entry count, error flag
+  long nnz_hint = -1;
+  int hint_N = -1, hint_first = -1, hint_last = -1;
+  bool pending_check = false;
+  long pending_cap = 0;
+  unsigned int* d_fin_counter = nullptr;
   long launches = 0;
   double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -106,12 +117,15 @@ namespace {
 // ---------------------------------------------------------------------------------------------------
 constexpr int FIN_BLOCKS = 128, FIN_THREADS = 256;
 
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize_partial(const int* __restrict__ Z, int N, int first, int last,
-                                                                  const double* __restrict__ e0, double e_scale, double* __restrict__ local_e,
-                                                                  const double* __restrict__ vir_part, int n_slots,
-                                                                  double* __restrict__ part /* [FIN_BLOCKS][10] */) {
+// One kernel: per-block partial sums, and the LAST block to finish (atomic ticket) adds the partials in block order,
+// so the totals are deterministic.
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict__ Z, int N, int first, int last, const double* __restrict__ e0,
+                                                          double e_scale, double* __restrict__ local_e, const double* __restrict__ vir_part,
+                                                          int n_slots, double* __restrict__ part /* [FIN_BLOCKS][10] */,
+                                                          unsigned int* __restrict__ counter, double* __restrict__ packed) {
   typedef cub::BlockReduce<double, FIN_THREADS> BR;
   __shared__ typename BR::TempStorage tmp;
+  __shared__ bool is_last;
   double v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = blockIdx.x * FIN_THREADS + threadIdx.x; i < N; i += FIN_BLOCKS * FIN_THREADS) {
     double le = local_e[i];
@@ -130,13 +144,20 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_partial(const int* __r
     __syncthreads();
     if (threadIdx.x == 0) part[10 * blockIdx.x + k] = t;
   }
-}
-__global__ void k_finalize_final(const double* __restrict__ part, double* __restrict__ packed) {
-  int k = threadIdx.x;
-  if (k >= 10) return;
-  double t = 0.0;
-  for (int b = 0; b < FIN_BLOCKS; b++) t += part[10 * b + k];
-  packed[k] = t;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < 10) {
+      double t = 0.0;
+      for (int b = 0; b < (int)gridDim.x; b++) t += __ldcg(&part[10 * b + threadIdx.x]);
+      packed[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
 }
 __global__ void k_iota(int* p, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,8 +212,11 @@ void inv3(const double* a, double* g) {  // column-major both
   g[2 + 3 * 2] = (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0)) / det;
 }
 
+// speculative = true: size the list from the previous call's entry count and do NOT wait for the real count (it arrives in
+// P->h_pin; verify_connect() checks it after the caller's final synchronisation).
 void build_connect(gap_potential* P, int N, int first, int last, const double* d_pos, const double* lattice, const int* pbc, double cutoff,
-                   bool want_dist, cudaStream_t st) {
+                   bool want_dist, bool speculative, cudaStream_t st) {
+  P->pending_check = false;
   if (N < 0) throw GapError("calc_connect: negative number of atoms");
   if (cutoff < 0.0) throw GapError("calc_connect: Negative cutoff radius " + std::to_string(cutoff));  // Connection.f95:1069
   P->conn_N = N;
@@ -308,20 +332,46 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   size_t cb = neighbour_cub_bytes(N, ncell);
   P->b_cub.ensure(cb); w.cub_tmp = P->b_cub.p; w.cub_bytes = P->b_cub.cap;
 
+  w.err_flag = P->b_off.as<int>() + N + 1;  // read back together with the entry count
+  CUDA_OK(cudaMemsetAsync(w.err_flag, 0, sizeof(int), st));
   launch_bin_atoms(d_pos, N, grid, ncell, w, st, &launches);
   launch_neigh_count(d_pos, N, first, last, grid, w, P->b_off.as<int>(), st, &launches);
-  int nnz = 0;
-  CUDA_OK(cudaMemcpyAsync(&nnz, P->b_off.as<int>() + N, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
-  if (nnz < 0) throw GapError("calc_connect: neighbour list exceeds 2^31 entries");
-  P->conn_nnz = nnz;
-  P->b_j.ensure(sizeof(int) * (size_t)(nnz + 1));
-  P->b_s.ensure(sizeof(int) * (size_t)(nnz + 1));
-  if (want_dist) P->b_d.ensure(sizeof(double) * (size_t)(nnz + 1));
-  launch_neigh_fill(d_pos, N, first, last, grid, w, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), want_dist ? P->b_d.as<double>() : nullptr, st,
-                    &launches);
+  CUDA_OK(cudaMemcpyAsync(P->h_pin, P->b_off.as<int>() + N, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  long cap;
+  if (speculative && !want_dist && P->nnz_hint >= 0 && P->hint_N == N && P->hint_first == first && P->hint_last == last) {
+    cap = P->nnz_hint + P->nnz_hint / 4 + 4096;
+    if (cap > 2147483000L) cap = 2147483000L;
+    P->pending_check = true;
+    P->pending_cap = cap;
+  } else {
+    CUDA_OK(cudaStreamSynchronize(st));
+    const int nnz = P->h_pin[0];
+    if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 60 periodic images away from the cell; wrap the positions first");
+    if (nnz < 0) throw GapError("calc_connect: neighbour list exceeds 2^31 entries");
+    P->conn_nnz = nnz;
+    P->nnz_hint = nnz; P->hint_N = N; P->hint_first = first; P->hint_last = last;
+    cap = nnz;
+  }
+  P->b_j.ensure(sizeof(int) * (size_t)(cap + 1));
+  P->b_s.ensure(sizeof(int) * (size_t)(cap + 1));
+  if (want_dist) P->b_d.ensure(sizeof(double) * (size_t)(cap + 1));
+  launch_neigh_fill(d_pos, N, first, last, grid, w, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), want_dist ? P->b_d.as<double>() : nullptr,
+                    (int)cap, st, &launches);
   P->launches += launches;
   CUDA_OK(cudaGetLastError());
+}
+
+// After the stream has been synchronised: did the speculatively sized list hold every entry?  false = repeat the call.
+bool verify_connect(gap_potential* P) {
+  if (!P->pending_check) return true;
+  P->pending_check = false;
+  const int nnz = P->h_pin[0];
+  if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 60 periodic images away from the cell; wrap the positions first");
+  if (nnz < 0) throw GapError("calc_connect: neighbour list exceeds 2^31 entries");
+  P->conn_nnz = nnz;
+  const bool ok = nnz <= P->pending_cap;
+  P->nnz_hint = ok ? nnz : -1;  // overflow: the repeat takes the exact (synchronising) path
+  return ok;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -335,6 +385,9 @@ double factorial_d(int n) {
 
 void upload_model(gap_potential* P) {
   const double pi = 3.14159265358979323846264338327950288;
+  CUDA_OK(cudaMalloc(&P->d_fin_counter, sizeof(unsigned int)));
+  CUDA_OK(cudaMemset(P->d_fin_counter, 0, sizeof(unsigned int)));
+  CUDA_OK(cudaHostAlloc((void**)&P->h_pin, 2 * sizeof(int), cudaHostAllocDefault));
   CUDA_OK(cudaMalloc(&P->d_e0, sizeof(double) * 128));
   CUDA_OK(cudaMemcpy(P->d_e0, P->model.e0, sizeof(double) * 128, cudaMemcpyHostToDevice));
   for (const Coordinate& c : P->model.coord) {
@@ -366,14 +419,16 @@ void upload_model(gap_potential* P) {
       }
       cudaDeviceProp prop;
       CUDA_OK(cudaGetDeviceProperties(&prop, P->device));
+      P->n_sm = prop.multiProcessorCount;
       if (soap_adjoint_smem(h) > prop.sharedMemPerBlockOptin || soap_forward_smem(h) > prop.sharedMemPerBlockOptin)
         throw GapError("soap descriptor too large for the shared memory of this device");
       CUDA_OK(cudaMalloc(&cd.d_sp, sizeof(SoapDev)));
       CUDA_OK(cudaMemcpy(cd.d_sp, &h, sizeof(SoapDev), cudaMemcpyHostToDevice));
       cd.M = c.M;
-      cd.M_pad = round_up(c.M > 0 ? c.M : 1, COV_BN);
+      cd.M_pad = round_up(c.M > 0 ? c.M : 1, COV_BN1);
       cd.d_pad = h.d_pad;
-      cd.dn_pad = round_up(s.d, COV_BN);
+      cd.bn2 = cov_gemm2_bn(s.d);
+      cd.dn_pad = round_up(s.d, cd.bn2);
       // sparse points: rows [M_pad][d_pad] (GEMM-1 B operand) and transposed [dn_pad][M_pad] (GEMM-2 B operand)
       std::vector<double> rows((size_t)cd.M_pad * cd.d_pad, 0.0), trn((size_t)cd.dn_pad * cd.M_pad, 0.0), al(cd.M_pad, 0.0), cu(cd.M_pad, 0.0);
       for (int m = 0; m < c.M; m++) {
@@ -460,7 +515,8 @@ struct SoapRun {
   int nc = 0, nc_pad = 0;
 };
 
-// select + compact the centres of SOAP coordinate cd among atoms [first,last)
+// select + compact the centres of SOAP coordinate cd among atoms [first,last).  The number of centres stays on the
+// device (P->b_scan[n], see nc_dev()); the host sizes grids and buffers with the upper bound n = last - first.
 int select_centres(gap_potential* P, const CoordDev& cd, const int* d_Z, int first, int last, cudaStream_t st) {
   int n = last - first;
   if (n <= 0) return 0;
@@ -475,46 +531,48 @@ int select_centres(gap_potential* P, const CoordDev& cd, const int* d_Z, int fir
   size_t bytes = P->b_cub.cap;
   cub::DeviceScan::ExclusiveSum(P->b_cub.p, bytes, P->b_flags.as<int>(), P->b_scan.as<int>(), n + 1, st);
   launches++;
-  int nc = 0;
-  CUDA_OK(cudaMemcpyAsync(&nc, P->b_scan.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
   launch_compact(P->b_scan.as<int>(), P->b_flags.as<int>(), first, n, P->b_centres.as<int>(), st, &launches);
   P->launches += launches;
-  return nc;
+  return n;
 }
+const int* nc_dev(const gap_potential* P, int n_ub) { return P->b_scan.as<int>() + n_ub; }
 
-void soap_forward_stage(gap_potential* P, const CoordDev& cd, int nc, const double* d_pos, const int* d_Z, const Lattice9& lat, cudaStream_t st) {
+void soap_forward_stage(gap_potential* P, const CoordDev& cd, int n_ub, const double* d_pos, const int* d_Z, const Lattice9& lat, cudaStream_t st) {
   int launches = 0;
-  int nc_pad = round_up(nc > 0 ? nc : 1, COV_BM);
+  int nc_pad = round_up(n_ub > 0 ? n_ub : 1, COV_BM);
   P->b_x.ensure(sizeof(double) * (size_t)nc_pad * cd.d_pad);
-  P->b_xlm.ensure(sizeof(double) * (size_t)(nc > 0 ? nc : 1) * cd.h.nlm * cd.h.K1);
+  P->b_xlm.ensure(sizeof(double) * (size_t)(n_ub > 0 ? n_ub : 1) * cd.h.nlm * cd.h.K1);
   P->b_pnorm.ensure(sizeof(double) * (size_t)nc_pad);
-  if (nc_pad > nc) CUDA_OK(cudaMemsetAsync(P->b_x.as<double>() + (size_t)nc * cd.d_pad, 0, sizeof(double) * (size_t)(nc_pad - nc) * cd.d_pad, st));
-  launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos, d_Z, lat,
-                      P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
+  launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos,
+                      d_Z, lat, P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
   P->launches += launches;
 }
 
 // covariance for rows [0, nc_pad) of b_x: epart (all rows) and, if want_grad, gvec (all rows)
-void covariance_stage(gap_potential* P, const CoordDev& cd, int nc, bool want_grad, cudaStream_t st) {
+// rows_dev: device-side row count (NULL = all nc rows are real)
+void covariance_stage(gap_potential* P, const CoordDev& cd, int nc, const int* rows_dev, bool want_grad, bool allow_split, cudaStream_t st) {
   int launches = 0;
   int nc_pad = round_up(nc > 0 ? nc : 1, COV_BM);
-  int n_tiles_n = cd.M_pad / COV_BN;
+  int n_tiles_n = cd.M_pad / COV_BN1;
   size_t budget = (size_t)1 << 30;  // bytes of acoef kept live at once
   int chunk = (int)(budget / ((size_t)cd.M_pad * sizeof(double)) / COV_BM) * COV_BM;
   if (chunk < COV_BM) chunk = COV_BM;
   if (chunk > nc_pad) chunk = nc_pad;
   P->b_acoef.ensure(sizeof(double) * (size_t)chunk * cd.M_pad);
   P->b_epart.ensure(sizeof(double) * (size_t)nc_pad * n_tiles_n);
-  if (want_grad) P->b_gvec.ensure(sizeof(double) * (size_t)nc_pad * cd.dn_pad);
+  int ksplit = allow_split ? cov_gemm2_ksplit(chunk, cd.dn_pad, cd.bn2, P->n_sm) : 1;
+  P->g_splits = ksplit;
+  P->g_split_stride = (size_t)nc_pad * cd.dn_pad;
+  if (want_grad) P->b_gvec.ensure(sizeof(double) * (size_t)nc_pad * cd.dn_pad * ksplit);
   for (int r0 = 0; r0 < nc_pad; r0 += chunk) {
     int rows = std::min(chunk, nc_pad - r0);
-    launch_cov_gemm1(P->b_x.as<double>() + (size_t)r0 * cd.d_pad, cd.d_pad, cd.sp_rows, cd.d_pad, rows, cd.M, cd.M_pad, cd.d_pad, cd.alpha, cd.scut,
-                     cd.cp, P->b_acoef.as<double>(), cd.M_pad, P->b_epart.as<double>() + (size_t)r0 * n_tiles_n, n_tiles_n, st, &launches);
+    launch_cov_gemm1(P->b_x.as<double>() + (size_t)r0 * cd.d_pad, cd.d_pad, cd.sp_rows, cd.d_pad, rows, r0, rows_dev, cd.M, cd.M_pad, cd.d_pad,
+                     cd.alpha, cd.scut, cd.cp, P->b_acoef.as<double>(), cd.M_pad, P->b_epart.as<double>() + (size_t)r0 * n_tiles_n, n_tiles_n, st,
+                     &launches);
     mark(P, st, ST_COV_GEMM1);
     if (want_grad) {
-      launch_cov_gemm2(P->b_acoef.as<double>(), cd.M_pad, cd.st_rows, cd.M_pad, rows, cd.dn_pad, cd.M_pad, P->b_gvec.as<double>() + (size_t)r0 * cd.dn_pad,
-                       cd.dn_pad, st, &launches);
+      launch_cov_gemm2(P->b_acoef.as<double>(), cd.M_pad, cd.st_rows, cd.M_pad, rows, r0, rows_dev, cd.dn_pad, cd.bn2, ksplit, cd.M_pad,
+                       P->b_gvec.as<double>() + (size_t)r0 * cd.dn_pad, cd.dn_pad, P->g_split_stride, st, &launches);
       mark(P, st, ST_COV_GEMM2);
     }
   }
@@ -529,7 +587,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   const int first = (int)((long long)P->rank * N / P->n_ranks), last = (int)((long long)(P->rank + 1) * N / P->n_ranks);
   P->ev_used = 0;
   mark(P, st, -1);
-  build_connect(P, N, first, last, d_pos, lattice, pbc, P->model.cutoff, false, st);
+  build_connect(P, N, first, last, d_pos, lattice, pbc, P->model.cutoff, false, true, st);
   mark(P, st, ST_CONNECT);
   Lattice9 lat;
   for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
@@ -556,20 +614,23 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
     const CoordDev& cd = P->cd[ic];
     int launches = 0;
     if (cd.kind == DESC_SOAP) {
-      int nc = select_centres(P, cd, d_Z, first, last, st);
+      int nc = select_centres(P, cd, d_Z, first, last, st);  // upper bound; the count itself stays on the device
       mark(P, st, ST_OTHER);
       if (nc > 0) {
+        const int* ncd = nc_dev(P, nc);
         soap_forward_stage(P, cd, nc, d_pos, d_Z, lat, st);
         mark(P, st, ST_SOAP_FWD);
-        covariance_stage(P, cd, nc, want_grad, st);
-        launch_energy_rows(P->b_epart.as<double>(), cd.M_pad / COV_BN, P->b_centres.as<int>(), nc, es, d_le, st, &launches);
-        mark(P, st, ST_OTHER);
+        covariance_stage(P, cd, nc, ncd, want_grad, true, st);
         if (want_grad) {
-          launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), nc, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos, d_Z, lat,
-                              P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, es, d_force,
+          launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), ncd, nc, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos, d_Z, lat,
+                              P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, P->g_splits,
+                              P->g_split_stride, P->b_epart.as<double>(), cd.M_pad / COV_BN1, d_le, es, d_force,
                               P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches);
           slot += nc;
           mark(P, st, ST_SOAP_ADJ);
+        } else {
+          launch_energy_rows(P->b_epart.as<double>(), cd.M_pad / COV_BN1, P->b_centres.as<int>(), ncd, nc, es, d_le, st, &launches);
+          mark(P, st, ST_OTHER);
         }
       }
     } else {
@@ -584,10 +645,9 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   }
   // totals
   P->b_fin.ensure(sizeof(double) * 10 * FIN_BLOCKS);
-  k_finalize_partial<<<FIN_BLOCKS, FIN_THREADS, 0, st>>>(d_Z, N, first, last, P->d_e0, es, d_le, want_grad ? P->b_vir.as<double>() : nullptr,
-                                                        want_grad ? (int)slot : 0, P->b_fin.as<double>());
-  k_finalize_final<<<1, 32, 0, st>>>(P->b_fin.as<double>(), d_packed);
-  P->launches += 2;
+  k_finalize<<<FIN_BLOCKS, FIN_THREADS, 0, st>>>(d_Z, N, first, last, P->d_e0, es, d_le, want_grad ? P->b_vir.as<double>() : nullptr,
+                                                want_grad ? (int)slot : 0, P->b_fin.as<double>(), P->d_fin_counter, d_packed);
+  P->launches += 1;
   mark(P, st, ST_OTHER);
   CUDA_OK(cudaGetLastError());
 }
@@ -648,6 +708,8 @@ void gap_potential_finalise(gap_potential* P) {
     cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2);
   }
   cudaFree(P->d_e0);
+  cudaFree(P->d_fin_counter);
+  if (P->h_pin) cudaFreeHost(P->h_pin);
   DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_ccount, &P->b_cstart, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
@@ -699,7 +761,12 @@ int gap_potential_calc_device(gap_potential* P, int N, const double* d_pos, cons
     if (N < 0) throw GapError("gap_potential_calc_device: N < 0");
     if (!d_packed) throw GapError("gap_potential_calc_device: d_packed is NULL");
     cudaStream_t st = stream ? (cudaStream_t)stream : P->stream;
-    calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad != 0 || d_local_virial != nullptr, d_packed, d_local_e, d_local_virial, st);
+    for (int attempt = 0; attempt < 2; attempt++) {
+      calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad != 0 || d_local_virial != nullptr, d_packed, d_local_e, d_local_virial, st);
+      if (!P->pending_check) break;  // exact list: nothing to verify, the work is simply enqueued
+      CUDA_OK(cudaStreamSynchronize(st));
+      if (verify_connect(P)) break;  // otherwise the speculatively sized neighbour list overflowed: repeat with the exact size
+    }
   });
 }
 
@@ -721,14 +788,17 @@ int gap_potential_calc(gap_potential* P, int N, const double* pos, const int* Z,
       CUDA_OK(cudaMemcpyAsync(P->b_Z.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
     }
     bool want_grad = force || virial || local_virial;  // IPModel_GAP.f95:416-424
-    calc_device_impl(P, N, P->b_pos.as<double>(), P->b_Z.as<int>(), lattice, pbc, args_str, want_grad, P->b_packed.as<double>(),
-                     P->b_le.as<double>(), local_virial ? P->b_lv.as<double>() : nullptr, st);
     double head[10];
-    CUDA_OK(cudaMemcpyAsync(head, P->b_packed.p, sizeof(head), cudaMemcpyDeviceToHost, st));
-    if (force && N > 0) CUDA_OK(cudaMemcpyAsync(force, P->b_packed.as<double>() + 10, sizeof(double) * 3 * (size_t)N, cudaMemcpyDeviceToHost, st));
-    if (local_e && N > 0) CUDA_OK(cudaMemcpyAsync(local_e, P->b_le.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
-    if (local_virial && N > 0) CUDA_OK(cudaMemcpyAsync(local_virial, P->b_lv.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    for (int attempt = 0; attempt < 2; attempt++) {
+      calc_device_impl(P, N, P->b_pos.as<double>(), P->b_Z.as<int>(), lattice, pbc, args_str, want_grad, P->b_packed.as<double>(),
+                       P->b_le.as<double>(), local_virial ? P->b_lv.as<double>() : nullptr, st);
+      CUDA_OK(cudaMemcpyAsync(head, P->b_packed.p, sizeof(head), cudaMemcpyDeviceToHost, st));
+      if (force && N > 0) CUDA_OK(cudaMemcpyAsync(force, P->b_packed.as<double>() + 10, sizeof(double) * 3 * (size_t)N, cudaMemcpyDeviceToHost, st));
+      if (local_e && N > 0) CUDA_OK(cudaMemcpyAsync(local_e, P->b_le.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
+      if (local_virial && N > 0) CUDA_OK(cudaMemcpyAsync(local_virial, P->b_lv.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      if (verify_connect(P)) break;  // false: the speculatively sized neighbour list overflowed; repeat with the exact size
+    }
     if (energy) *energy = head[0];
     if (virial)
       for (int k = 0; k < 9; k++) virial[k] = head[1 + k];
@@ -764,7 +834,7 @@ int gap_calc_connect(gap_potential* P, int N, const double* pos, const double* l
     CUDA_OK(cudaSetDevice(P->device));
     P->b_pos.ensure(sizeof(double) * 3 * (size_t)(N + 1));
     if (N > 0) CUDA_OK(cudaMemcpyAsync(P->b_pos.p, pos, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, P->stream));
-    build_connect(P, N, 0, N, P->b_pos.as<double>(), lattice, pbc, cutoff, true, P->stream);
+    build_connect(P, N, 0, N, P->b_pos.as<double>(), lattice, pbc, cutoff, true, false, P->stream);
     CUDA_OK(cudaStreamSynchronize(P->stream));
     if (n_entries) *n_entries = P->conn_nnz;
   });
@@ -806,14 +876,19 @@ int gap_descriptor_calc(gap_potential* P, int i_coord, int N, const double* pos,
       CUDA_OK(cudaMemcpyAsync(P->b_pos.p, pos, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, st));
       CUDA_OK(cudaMemcpyAsync(P->b_Z.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
     }
-    int nc = select_centres(P, cd, P->b_Z.as<int>(), 0, N, st);
+    int n_ub = select_centres(P, cd, P->b_Z.as<int>(), 0, N, st);
+    int nc = 0;
+    if (n_ub > 0) {
+      CUDA_OK(cudaMemcpyAsync(&nc, nc_dev(P, n_ub), sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+    }
     if (n_desc) *n_desc = nc;
     if (d_out) *d_out = cd.h.d;
     if (!x) return;
-    build_connect(P, N, 0, N, P->b_pos.as<double>(), lattice, pbc, cd.h.cutoff, false, st);
+    build_connect(P, N, 0, N, P->b_pos.as<double>(), lattice, pbc, cd.h.cutoff, false, false, st);
     Lattice9 lat;
     for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
-    soap_forward_stage(P, cd, nc, P->b_pos.as<double>(), P->b_Z.as<int>(), lat, st);
+    soap_forward_stage(P, cd, n_ub, P->b_pos.as<double>(), P->b_Z.as<int>(), lat, st);
     if (nc > 0) {
       CUDA_OK(cudaMemcpy2DAsync(x, sizeof(double) * cd.h.d, P->b_x.p, sizeof(double) * cd.d_pad, sizeof(double) * cd.h.d, nc, cudaMemcpyDeviceToHost, st));
       if (ci) CUDA_OK(cudaMemcpyAsync(ci, P->b_centres.p, sizeof(int) * nc, cudaMemcpyDeviceToHost, st));
@@ -841,9 +916,9 @@ int gap_gp_predict(gap_potential* P, int i_coord, int n, const double* x, double
     k_iota<<<(n + 255) / 256, 256, 0, st>>>(P->b_centres.as<int>(), n);
     P->b_le.ensure(sizeof(double) * (size_t)(n + 1));
     CUDA_OK(cudaMemsetAsync(P->b_le.p, 0, sizeof(double) * (size_t)(n + 1), st));
-    covariance_stage(P, cd, n, grad != nullptr, st);
+    covariance_stage(P, cd, n, nullptr, grad != nullptr, false, st);
     int launches = 1;
-    launch_energy_rows(P->b_epart.as<double>(), cd.M_pad / COV_BN, P->b_centres.as<int>(), n, 1.0, P->b_le.as<double>(), st, &launches);
+    launch_energy_rows(P->b_epart.as<double>(), cd.M_pad / COV_BN1, P->b_centres.as<int>(), nullptr, n, 1.0, P->b_le.as<double>(), st, &launches);
     P->launches += launches;
     if (e) CUDA_OK(cudaMemcpyAsync(e, P->b_le.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     if (grad)

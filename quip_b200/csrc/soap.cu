@@ -285,7 +285,8 @@ __device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L
 // ------------------------------------------------------------------------------------------------
 // forward: x (normalised power spectrum), X_lm (kept for the adjoint), |p|
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restrict__ sp, const int* __restrict__ centres, int n_centres,
+__global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
+                                                        const int* __restrict__ n_centres_dev,
                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
                                                         const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
   Smem s;
   carve(*sp, false, &s, smem_raw);
   const int c = blockIdx.x;
-  if (c >= n_centres) return;
+  if (c >= *n_centres_dev) return;  // the grid is sized by an upper bound; the centre count never leaves the device
   const int i = centres[c];
   const int n = sp->n_max, L = sp->l_max, L1 = L + 1, nlm = sp->nlm, K1 = sp->K1, d = sp->d, d_pad = sp->d_pad, ns = sp->n_species;
   const int n4 = ceil4(n), K1p = ns * n4, RFS = rf_stride(L1, n4), YS = y_stride(nlm), NG = n4 / AG;
@@ -466,19 +467,31 @@ __device__ __forceinline__ void adjoint_order(const double* __restrict__ ynorm, 
   }
 }
 
-__global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restrict__ sp, const int* __restrict__ centres, int n_centres,
+__global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
+                                                        const int* __restrict__ n_centres_dev,
                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
                                                         const int* __restrict__ Z, Lattice9 lat, const double* __restrict__ x,
                                                         const double* __restrict__ xlm, const double* __restrict__ pnorm,
-                                                        const double* __restrict__ gvec, int ldg, double e_scale, double* __restrict__ force,
-                                                        double* __restrict__ vir_part, double* __restrict__ local_virial) {
+                                                        const double* __restrict__ gvec, int ldg, int g_splits, size_t g_split_stride,
+                                                        const double* __restrict__ epart, int n_tiles_n, double* __restrict__ local_e,
+                                                        double e_scale, double* __restrict__ force, double* __restrict__ vir_part,
+                                                        double* __restrict__ local_virial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem s;
   carve(*sp, true, &s, smem_raw);
   const int c = blockIdx.x;
-  if (c >= n_centres) return;
+  if (c >= *n_centres_dev) {
+    if (vir_part && threadIdx.x < 9) vir_part[9 * (size_t)c + threadIdx.x] = 0.0;  // unused slot of the upper-bound grid
+    return;
+  }
   const int i = centres[c];
+  // E_i = sum over the column tiles of GEMM-1 (fixed order) ; local_e(centre) += E_i  (IPModel_GAP.f95:454-459, cc = 1, |ci| = 1)
+  if (epart && threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < n_tiles_n; k++) t += epart[(size_t)c * n_tiles_n + k];
+    local_e[i] += e_scale * t;
+  }
   const int n = sp->n_max, L = sp->l_max, L1 = L + 1, nlm = sp->nlm, K1 = sp->K1, d = sp->d, d_pad = sp->d_pad, ns = sp->n_species;
   const int n4 = ceil4(n), K1p = ns * n4, RFS = rf_stride(L1, n4), MP = m_pairs(L);
   const double alpha = sp->alpha;
@@ -487,11 +500,18 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
   // u = dE/dp: pull gradPredict back through x = p/|p| (reference forward form: descriptors.f95:8595-8600)
   const double* xr = x + (size_t)c * sp->d_pad;
   const double* gr = gvec + (size_t)c * ldg;
+  // gradPredict arrives as g_splits partial sums (the K splits of GEMM-2), added here in a fixed order
   double loc = 0.0;
-  for (int q = threadIdx.x; q < d - 1; q += NT) loc += xr[q] * gr[q];
+  for (int q = threadIdx.x; q < d - 1; q += NT) {
+    double g = gr[q];
+    for (int k = 1; k < g_splits; k++) g += gr[(size_t)k * g_split_stride + q];
+    s.p[q] = g;
+    loc += xr[q] * g;
+  }
   double sdot = block_sum(loc, s.red);
   double nrm = pnorm[c];
-  for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = sp->normalise ? (gr[q] - xr[q] * sdot) / nrm : gr[q];
+  if (sp->normalise)
+    for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = (s.p[q] - xr[q] * sdot) / nrm;
   // X_lm and Lambda = dE/dX_lm are staged in the (not yet used) radial-table area
   double* Xs = s.rf;                       // nlm*K1
   double* Ls = s.rf + (size_t)nlm * K1;    // nlm*K1
@@ -633,25 +653,28 @@ void launch_compact(const int* flags_scan, const int* flags, int first, int n, i
   *launches += 1;
 }
 
-void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres, int n_centres, const int* nbr_off, const int* nbr_j,
-                         const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, double* x, double* xlm, double* pnorm,
+void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off,
+                         const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, double* x, double* xlm, double* pnorm,
                          cudaStream_t st, int* launches) {
+  const int n_centres = n_centres_ub;
   if (n_centres <= 0) return;
   size_t sm = soap_forward_smem(h);
   cudaFuncSetAttribute(k_soap_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_soap_forward<<<n_centres, NT, sm, st>>>(sp, centres, n_centres, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
+  k_soap_forward<<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
   *launches += 1;
 }
 
-void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, int n_centres, const int* nbr_off, const int* nbr_j,
-                         const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
-                         const double* pnorm, const double* gvec, int ldg, double e_scale, double* force, double* vir_part,
-                         double* local_virial, cudaStream_t st, int* launches) {
+void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off,
+                         const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
+                         const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
+                         double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st,
+                         int* launches) {
+  const int n_centres = n_centres_ub;
   if (n_centres <= 0) return;
   size_t sm = soap_adjoint_smem(h);
   cudaFuncSetAttribute(k_soap_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_soap_adjoint<<<n_centres, NT, sm, st>>>(sp, centres, n_centres, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, e_scale,
-                                            force, vir_part, local_virial);
+  k_soap_adjoint<<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, g_splits,
+                                            g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);
   *launches += 1;
 }
 

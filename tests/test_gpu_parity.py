@@ -323,3 +323,24 @@ def test_error_reporting(golden):
         pot.calc(at, args_str="E_scale=2.0")
     with pytest.raises(RuntimeError, match="singular lattice|zero-length"):
         pot.calc(Atoms(at.numbers, at.positions, np.zeros((3, 3)), True))
+
+
+def test_speculative_neighbour_list_overflow_repeats(si_model, si_frames):
+    # the list of call k+1 is sized from call k (same N): a denser configuration of the same N must trigger the
+    # transparent repeat and still give the exact result
+    pot, om, xml = si_model
+    a = si_frames[8]
+    r0 = pot.calc(a, force=True, virial=True)
+    r1 = pot.calc(a, force=True, virial=True)  # speculative path, same list
+    assert r0["energy"] == r1["energy"] and np.abs(r0["force"] - r1["force"]).max() < 1e-12
+    dense = Atoms(a.numbers, a.positions * 0.93, a.cell * 0.93, True)  # ~25% more neighbours... then much more:
+    for scale in (0.93, 0.8):
+        dense = Atoms(a.numbers, a.positions * scale, a.cell * scale, True)
+        r = pot.calc(dense, force=True, virial=True)
+        fresh = Potential("IP GAP", param_filename=xml).calc(dense, force=True, virial=True)
+        assert abs(r["energy"] - fresh["energy"]) < 1e-9 * abs(fresh["energy"])
+        assert np.abs(r["force"] - fresh["force"]).max() < 1e-9
+        assert np.abs(r["virial"] - fresh["virial"]).max() < 1e-8
+    o = om.calc(dense)
+    assert abs(r["energy"] - o["energy"]) / len(a) < TOL_E_PER_ATOM
+    assert np.abs(r["force"] - o["force"]).max() < TOL_F

@@ -22,7 +22,7 @@ for r in rows:
         i_x = hdr.index("Instructions Executed")
         st_cols = [(k, h) for k, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
         continue
-    if hdr is None or len(r) < len(hdr) - 2:
+    if hdr is None or len(r) <= i_x or r[0] == "":  # SASS rows repeat the samples of their source line
         continue
     try:
         s = int(r[i_s]); x = int(r[i_x])
