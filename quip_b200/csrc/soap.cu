@@ -15,10 +15,20 @@
 //    centre (Lambda = dE_i/dX_lm, a nlm x K1 block in shared memory) and each neighbour costs
 //    O(n_max (l_max+1)^2) to turn Lambda into the 3-vector f_gp: grad_data never exists.
 //
-// One CTA (128 threads) per centre.  Neighbour shells are staged in shared memory in tiles; warp 0 evaluates the
-// harmonics (one neighbour per lane) while warps 1-3 evaluate the radial functions; the contraction over the
-// tile is done by all threads with register accumulation; all reductions are fixed-order (deterministic) except
-// the final force scatter, which uses FP64 atomics on HBM.
+//  * The three dense contractions of the descriptor run on the FP64 TENSOR CORES (mma.sync.m8n8k4.f64, SASS DMMA):
+//      density expansion   Xt_lm(c)   = sum_q  Y_lm(q) Phi_l(c; q)          (M = lm, N = channel, K = neighbour)
+//      power spectrum      p_l(c,c')  = sum_m  X_lm(c) X_lm(c')             (M = N = channel, K = m)
+//      adjoint             A_lm(q)    = sum_c  Lambda~_lm(c) R_l(c; q)      (M = lm, N = neighbour, K = channel)
+//    plus the small basis-transform and Lambda products; fragments are read straight from shared memory whose row
+//    strides are = 4 (mod 16) doubles, which makes every fragment load bank-conflict free.
+//  * The transform_basis product is hoisted out of the neighbour loop (it is linear): X = Xt.T once per centre and
+//    Lambda~ = Lambda.T^T once per centre, instead of the reference's per-neighbour matmul (descriptors.f95:8261-8263).
+//
+// One CTA (128 threads = 4 warps) per centre, several CTAs resident per SM.  Per tile of neighbours the threads first
+// evaluate per-neighbour items -- (neighbour, radial basis point) -> Phi_l / R_l by the reference's upward recursion,
+// (neighbour, m) -> Y_{l,+-m} (and gradient) by recursion in l -- into shared memory, then the warps run the tensor-core
+// contractions over output tiles.  All reductions are fixed-order (deterministic) except the final force scatter,
+// which uses FP64 atomics on HBM.
 #include "gap_device.cuh"
 
 namespace gapb200 {
@@ -27,8 +37,9 @@ namespace {
 
 constexpr int NT = 128;    // threads per CTA
 constexpr int NBCAP = 128; // CSR entries examined per pass (= compacted list capacity)
-constexpr int TNF = 32;    // neighbours per tile, forward
-constexpr int TNA = 32;    // neighbours per tile, adjoint
+constexpr int NW = NT / 32;
+constexpr int TNF = 32;    // neighbours per tile, forward (multiple of 4: K steps of the DMMA)
+constexpr int TNA = 8;     // neighbours per tile, adjoint (= one DMMA N tile)
 constexpr int LC = SOAP_LMAX_CAP;
 constexpr double PI_D = 3.14159265358979323846264338327950288;
 
@@ -79,98 +90,120 @@ __device__ __forceinline__ void cutoff_fn(const SoapDev* sp, double r, double& f
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Work decomposition (one CTA of NT threads per centre, several CTAs resident per SM):
-//   gather   : the centre's CSR row -> shared memory (displacement, distance, species, cutoff function), compacted
-//              in list order (deterministic);
-//   tile loop over TN neighbours at a time:
-//     stage  : one item per (neighbour, radial basis point a): Phi_l(a) = f_cut * phi_l(a) for all l (and, for the
-//              adjoint, R_l(a) = f_cut * phi_l'(a) + f_cut' * phi_l(a));  forward only: one item per (neighbour, m):
-//              Y_{l,+-m} for all l >= m;
-//     forward accumulate: one item per (lm, group of 4 basis points): Xt_lm(s,a) += sum_q Phi_l(a;q) Y_lm(q) held in
-//              registers across the tile (the item owns its shared-memory row: no atomics, no extra barrier);
-//     adjoint contract : one item per (neighbour, m-pair): harmonics and their gradients are generated on the fly
-//              and contracted with Lambda~ and the radial tables straight away -- Y and grad Y never touch memory;
-//   The transform_basis product is hoisted out of the neighbour loop: X = Xt . T once per centre (forward) and
-//   Lambda~ = T . Lambda once per centre (adjoint), instead of the reference's per-neighbour matmul
-//   (descriptors.f95:8261-8263): (l_max+1) n_max^2 flops per NEIGHBOUR become (l_max+1)^2 n_max^2 per CENTRE.
+// geometry of the shared-memory tables (identical on host and device)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int AG = 4;  // radial basis points per accumulate item
-
 __host__ __device__ inline int ceil4(int v) { return (v + 3) & ~3; }
-// row stride (doubles) of the per-neighbour radial tables: = 2 (mod 16), so that 8 consecutive neighbours read
-// 16-byte words from 8 distinct bank quads
-__host__ __device__ inline int rf_stride(int L1, int n4) {
-  int s = L1 * n4;
-  while ((s & 15) != 2) s += 2;
-  return s;
+__host__ __device__ inline int ceil8(int v) { return (v + 7) & ~7; }
+__host__ __device__ inline int stride4mod16(int v) {  // smallest s >= v with s = 4 (mod 16)
+  int s = (v & ~15) + 4;
+  return s >= v ? s : s + 16;
 }
-__host__ __device__ inline int y_stride(int nlm) { return nlm | 1; }
+struct Geo {
+  int n, L, L1, nlm, ns, K1, K18, n2, n8, RFS, YS, XS, XR, TS, NTM, NTN;
+};
+__host__ __device__ __forceinline__ Geo make_geo(int n_max, int l_max, int n_species) {
+  Geo g;
+  g.n = n_max; g.L = l_max; g.L1 = l_max + 1; g.nlm = (l_max + 1) * (l_max + 1); g.ns = n_species; g.K1 = n_species * n_max;
+  g.K18 = ceil8(g.K1);            // channels padded to DMMA tiles
+  g.n2 = (g.n + 1) & ~1;
+  g.n8 = ceil8(g.n);
+  g.RFS = stride4mod16(g.L1 * g.n2);   // per-neighbour radial table [l][a]
+  g.YS = stride4mod16(g.nlm + 7);      // per-neighbour harmonics row (tile reads run up to 7 rows past nlm)
+  g.XS = g.K18 + 4;                    // X / Lambda row stride: = 4 or 12 (mod 16)
+  g.XR = g.nlm + 8;                    // rows allocated
+  g.TS = stride4mod16(g.n8);           // padded transform_basis row stride
+  // lm tiles of 8 rows, never straddling two l: sum_l ceil((2l+1)/8) in closed form: l <= 3 -> 1 tile, 4..7 -> 2, 8..11 -> 3, 12 -> 4
+  int ntm = 0;
+#pragma unroll
+  for (int l = 0; l <= SOAP_LMAX_CAP; l++)
+    if (l <= l_max) ntm += (2 * l + 1 + 7) / 8;
+  g.NTM = ntm;
+  g.NTN = g.K18 / 8;
+  return g;
+}
 
 struct Smem {
-  double* T;       // n*n transform_basis, T[a + n*a']
+  double* Tp;      // n8 x TS  transform_basis zero-padded: Tp[a*TS + a'] = T(a, a')
   double* rb;      // n
   double* ynorm;   // (L+1)(L+2)/2
-  double* X;       // nlm * K1p : forward Xt -> X ; adjoint Lambda~   (row lm, column s*n4 + a)
+  double* X;       // XR x XS : forward Xt -> X ; adjoint X -> Lambda~   (row lm, column = channel s*n + a)
+  double* X2;      // adjoint: XR x XS Lambda (aliases the staging area)
   double* nbd;     // NBCAP*3 displacement
   double* nbr;     // NBCAP distance
   double* nbf;     // NBCAP f_cut
   double* nbdf;    // NBCAP f_cut'
   double* red;     // 64
-  double* rf;      // TN * RFS
-  double* drf;     // adjoint: TN * RFS
-  double* Y;       // forward: TN * YS
-  double* part;    // adjoint: TN * MP * 3 partial forces
-  double* p;       // forward: d_pad power spectrum (aliases the staging area) ; adjoint: d_pad, own region
+  double* rf;      // TN x RFS
+  double* drf;     // adjoint: TN x RFS
+  double* Y;       // TN x YS
+  double* G;       // adjoint: 3 x TN x YS  polynomial gradients of the harmonics
+  double* part;    // adjoint: NW x TNA x 4
+  double* p;       // d_pad : forward power spectrum (aliases the staging area) ; adjoint u = dE/dp (own region)
   int* nbs;        // NBCAP species
   int* nbj;        // NBCAP neighbour atom
-  int* lof;        // nlm: l of lm
+  int* mt_lm0;     // NTM first row of the lm tile
+  int* mt_l;       // NTM its l
+  int* col_s;      // K18 species of channel (-1: padding)
+  int* col_a;      // K18 radial index of channel
   int* wcount;     // 8
 };
 
-__host__ __device__ inline int m_pairs(int L) { return L / 2 + 1 + (L & 1); }  // items per neighbour in the adjoint contraction
-
-__host__ __device__ inline size_t carve(const SoapDev& h, bool adjoint, Smem* s, unsigned char* base) {
-  const int n = h.n_max, L1 = h.l_max + 1, nlm = h.nlm, TN = adjoint ? TNA : TNF, n4 = ceil4(n), K1p = h.n_species * n4;
-  const int RFS = rf_stride(L1, n4), YS = y_stride(nlm), MP = m_pairs(h.l_max);
+__host__ __device__ __forceinline__ size_t carve(const Geo& g, int d_pad, bool adjoint, Smem* s, unsigned char* base) {
+  const int TN = adjoint ? TNA : TNF;
   size_t o = 0;
   auto take = [&](size_t cnt) { size_t r = o; o += ((cnt + 1) & ~(size_t)1) * sizeof(double); return r; };
-  size_t oT = take(n * n), orb = take(n), oyn = take((size_t)L1 * (L1 + 1) / 2), oX = take((size_t)nlm * K1p), onbd = take(NBCAP * 3),
-         onbr = take(NBCAP), onbf = take(NBCAP), onbdf = take(NBCAP), ored = take(64);
-  size_t orf = take((size_t)TN * RFS), odrf = adjoint ? take((size_t)TN * RFS) : 0, oY = adjoint ? 0 : take((size_t)TN * YS),
-         opart = adjoint ? take((size_t)TN * MP * 3) : 0;
-  size_t stage_bytes = o - orf;
+  size_t oT = take((size_t)g.n8 * g.TS), orb = take(g.n), oyn = take((size_t)g.L1 * (g.L1 + 1) / 2), oX = take((size_t)g.XR * g.XS),
+         onbd = take(NBCAP * 3), onbr = take(NBCAP), onbf = take(NBCAP), onbdf = take(NBCAP), ored = take(64);
+  size_t ostage = o;
+  size_t orf = take((size_t)TN * g.RFS), odrf = adjoint ? take((size_t)TN * g.RFS) : 0, oY = take((size_t)TN * g.YS),
+         oG = adjoint ? take((size_t)3 * TN * g.YS) : 0, opart = adjoint ? take((size_t)NW * TNA * 4) : 0;
+  size_t stage_bytes = o - ostage;
   size_t op;
   if (adjoint) {
-    // the staging area doubles as scratch for X_lm / Lambda while Lambda~ is formed (2 * nlm * K1 doubles)
-    if ((size_t)2 * nlm * h.K1 * sizeof(double) > stage_bytes) o = orf + (size_t)2 * nlm * h.K1 * sizeof(double);
-    op = take(h.d_pad);
+    // the staging area doubles as the Lambda buffer (XR x XS) while Lambda~ is formed
+    size_t need = (size_t)g.XR * g.XS * sizeof(double);
+    if (need > stage_bytes) o = ostage + need;
+    op = take(d_pad);
   } else {
-    op = orf;  // forward: the power spectrum reuses the staging area after the neighbour loop
-    if ((size_t)h.d_pad * sizeof(double) > stage_bytes) o = orf + (size_t)h.d_pad * sizeof(double);
+    op = ostage;  // forward: the power spectrum reuses the staging area after the neighbour loop
+    if ((size_t)d_pad * sizeof(double) > stage_bytes) o = ostage + (size_t)d_pad * sizeof(double);
   }
   size_t oi = o;
-  o += sizeof(int) * (NBCAP * 2 + nlm + 8);
+  o += sizeof(int) * (NBCAP * 2 + 2 * g.NTM + 2 * g.K18 + 8);
   o = (o + 15) & ~(size_t)15;
   if (s) {
-    s->T = (double*)(base + oT); s->rb = (double*)(base + orb); s->ynorm = (double*)(base + oyn); s->X = (double*)(base + oX);
+    s->Tp = (double*)(base + oT); s->rb = (double*)(base + orb); s->ynorm = (double*)(base + oyn); s->X = (double*)(base + oX);
+    s->X2 = (double*)(base + ostage);
     s->nbd = (double*)(base + onbd); s->nbr = (double*)(base + onbr); s->nbf = (double*)(base + onbf); s->nbdf = (double*)(base + onbdf);
     s->red = (double*)(base + ored); s->rf = (double*)(base + orf); s->drf = (double*)(base + odrf); s->Y = (double*)(base + oY);
-    s->part = (double*)(base + opart); s->p = (double*)(base + op);
-    s->nbs = (int*)(base + oi); s->nbj = s->nbs + NBCAP; s->lof = s->nbj + NBCAP; s->wcount = s->lof + nlm;
+    s->G = (double*)(base + oG); s->part = (double*)(base + opart); s->p = (double*)(base + op);
+    s->nbs = (int*)(base + oi); s->nbj = s->nbs + NBCAP; s->mt_lm0 = s->nbj + NBCAP; s->mt_l = s->mt_lm0 + g.NTM; s->col_s = s->mt_l + g.NTM;
+    s->col_a = s->col_s + g.K18; s->wcount = s->col_a + g.K18;
   }
   return o;
 }
 
-__device__ __forceinline__ void load_tables(const SoapDev* sp, const Smem& s) {
-  const int n = sp->n_max, L1 = sp->l_max + 1;
-  for (int k = threadIdx.x; k < n * n; k += NT) s.T[k] = sp->T[k];
-  for (int k = threadIdx.x; k < n; k += NT) s.rb[k] = sp->r_basis[k];
-  for (int k = threadIdx.x; k < L1 * (L1 + 1) / 2; k += NT) s.ynorm[k] = sp->ynorm[k];
-  for (int k = threadIdx.x; k < sp->nlm; k += NT) {
-    int l = 0;
-    while ((l + 1) * (l + 1) <= k) l++;
-    s.lof[k] = l;
+__device__ __forceinline__ void load_tables(const SoapDev* sp, const Geo& g, const Smem& s) {
+  for (int k = threadIdx.x; k < g.n8 * g.TS; k += NT) {
+    int a = k / g.TS, b = k - a * g.TS;
+    s.Tp[k] = (a < g.n && b < g.n) ? sp->T[a + g.n * b] : 0.0;
   }
+  for (int k = threadIdx.x; k < g.n; k += NT) s.rb[k] = sp->r_basis[k];
+  for (int k = threadIdx.x; k < g.L1 * (g.L1 + 1) / 2; k += NT) s.ynorm[k] = sp->ynorm[k];
+  if (threadIdx.x <= g.L) {  // thread l writes the lm tiles of its l
+    const int l = threadIdx.x;
+    int t = 0;
+    for (int k = 0; k < l; k++) t += (2 * k + 1 + 7) / 8;
+    for (int r0 = l * l; r0 < (l + 1) * (l + 1); r0 += 8) { s.mt_lm0[t] = r0; s.mt_l[t] = l; t++; }
+  }
+  for (int k = threadIdx.x; k < g.K18; k += NT) {
+    s.col_s[k] = k < g.K1 ? k / g.n : -1;
+    s.col_a[k] = k < g.K1 ? k % g.n : 0;
+  }
+}
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // Ordered (deterministic) block compaction of up to NBCAP CSR entries of centre i into shared memory.
@@ -215,17 +248,17 @@ __device__ __forceinline__ int gather_neighbours(const SoapDev* sp, const Smem& 
 }
 
 // Radial item (neighbour q, basis point a): Phi_l(a) = f phi_l(a) (and R_l(a) = f phi_l'(a) + f' phi_l(a)) for l = 0..L,
-// written at out[l * n4] (descriptors.f95:8218-8258 -- the upward recursion exactly as the reference runs it).
+// written at out[l * ld] (descriptors.f95:8218-8258 -- the upward recursion exactly as the reference runs it).
 template <bool GRAD>
-__device__ __forceinline__ void radial_item(double alpha, double r, double rb, double f, double df, int L, double* out, double* dout, int n4) {
+__device__ __forceinline__ void radial_item(double alpha, double r, double rb, double f, double df, int L, double* out, double* dout, int ld) {
   double arg = 2.0 * alpha * r * rb;
   if (arg == 0.0) {
     double bl = exp(-alpha * (rb * rb + r * r));
     out[0] = f * bl;
     if (GRAD) dout[0] = f * (-2.0 * alpha * r * bl) + df * bl;
     for (int l = 1; l <= L; l++) {
-      out[l * n4] = 0.0;
-      if (GRAD) dout[l * n4] = 0.0;
+      out[l * ld] = 0.0;
+      if (GRAD) dout[l * ld] = 0.0;
     }
     return;
   }
@@ -241,8 +274,8 @@ __device__ __forceinline__ void radial_item(double alpha, double r, double rb, d
     blm = bl;
     bl = blp;
     blp = blm - (double)(2 * l + 1) * bl * inv;
-    out[l * n4] = f * bl;
-    if (GRAD) dout[l * n4] = f * (-2.0 * alpha * r * bl + (double)l * bl * rinv + blp * 2.0 * alpha * rb) + df * bl;
+    out[l * ld] = f * bl;
+    if (GRAD) dout[l * ld] = f * (-2.0 * alpha * r * bl + (double)l * bl * rinv + blp * 2.0 * alpha * rb) + df * bl;
   }
 }
 
@@ -256,28 +289,46 @@ __device__ __forceinline__ void cs_power(double ux, double uy, int m, double& Cm
   }
 }
 
-// Forward harmonic item (neighbour q, order m): real orthonormal Y_{l,+m} (cos type) and Y_{l,-m} (sin type), l = m..L,
-// index lm = l*l + l +- m.  Y_lm = N_lm Q_l^m(z) {C_m, S_m}(x, y) with Q_l^m = d^m P_l / dz^m (upward recursion in l) and
+// Harmonic item (neighbour q, order m): real orthonormal Y_{l,+m} (cos type) and Y_{l,-m} (sin type), l = m..L, index
+// lm = l*l + l +- m.  Y_lm = N_lm Q_l^m(z) {C_m, S_m}(x, y) with Q_l^m = d^m P_l / dz^m (upward recursion in l) and
 // C_m + i S_m = (x + i y)^m; N_lm carries sqrt(2) for m > 0.  (The reference uses complex Y_lm,
 // angular_functions.f95:120-136; the power spectrum is invariant under this unitary change of basis.)
-__device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L, int m, double ux, double uy, double uz, double* Yq) {
+// GRAD: also the gradient of the polynomial extension N_lm Q_l^m(z) {C_m,S_m}(x,y) (three tables, stride gstride); the
+// consumer projects it: grad Y = (g - u (u.g)) / r  (GradSphericalYCartesian_all, angular_functions.f95:205-278).
+template <bool GRAD>
+__device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L, int m, double ux, double uy, double uz, double* Yq, double* Gq,
+                                         int gstride) {
   double Cm, Sm, Cm1, Sm1;
   cs_power(ux, uy, m, Cm, Sm, Cm1, Sm1);
-  double p2 = 0.0, p1 = c_dblfact[m];  // Q_{l-2}^m, Q_{l-1}^m while stepping; starts at Q_m^m = (2m-1)!!
+  const double dm = (double)m;
+  double p2 = 0.0, p1 = c_dblfact[m];  // Q^m recursion, starts at Q_m^m = (2m-1)!!
+  double z2 = 0.0, z1 = 0.0;           // Q^{m+1} recursion (= dQ^m/dz), zero at l = m
   for (int l = m; l <= L; l++) {
-    double pl;
+    double pl, zl = 0.0;
     if (l == m) pl = p1;
     else {
       pl = ((double)(2 * l - 1) * uz * p1 - (double)(l + m - 1) * p2) * c_invint[l - m];
-      p2 = p1;
-      p1 = pl;
+      p2 = p1; p1 = pl;
+      if (GRAD) {
+        if (l == m + 1) zl = c_dblfact[m + 1];
+        else zl = ((double)(2 * l - 1) * uz * z1 - (double)(l + m) * z2) * c_invint[l - m - 1];
+        z2 = z1; z1 = zl;
+      }
     }
-    double q = pl * ynorm[l * (l + 1) / 2 + m];
-    int base = l * l + l;
-    if (m == 0) Yq[base] = q;
-    else {
+    const double nrm = ynorm[l * (l + 1) / 2 + m];
+    const double q = pl * nrm, qz = zl * nrm;
+    const int base = l * l + l;
+    if (m == 0) {
+      Yq[base] = q;
+      if (GRAD) { Gq[base] = 0.0; Gq[gstride + base] = 0.0; Gq[2 * gstride + base] = qz; }
+    } else {
       Yq[base + m] = q * Cm;
       Yq[base - m] = q * Sm;
+      if (GRAD) {
+        const double qm = q * dm;
+        Gq[base + m] = qm * Cm1; Gq[gstride + base + m] = -qm * Sm1; Gq[2 * gstride + base + m] = qz * Cm;
+        Gq[base - m] = qm * Sm1; Gq[gstride + base - m] = qm * Cm1;  Gq[2 * gstride + base - m] = qz * Sm;
+      }
     }
   }
 }
@@ -285,118 +336,149 @@ __device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L
 // ------------------------------------------------------------------------------------------------
 // forward: x (normalised power spectrum), X_lm (kept for the adjoint), |p|
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
+// CN / CL / CNS: compile-time n_max / l_max / n_species (0 = read them from the model: generic instantiation).  With
+// constants every table stride, loop bound and index division folds at compile time.
+template <int CN, int CL, int CNS>
+__global__ void __launch_bounds__(NT, 3) k_soap_forward(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
                                                         const int* __restrict__ n_centres_dev,
                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
                                                         const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
                                                         double* __restrict__ xlm, double* __restrict__ pnorm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem s;
-  carve(*sp, false, &s, smem_raw);
   const int c = blockIdx.x;
   if (c >= *n_centres_dev) return;  // the grid is sized by an upper bound; the centre count never leaves the device
+  const Geo g = make_geo(CN ? CN : sp->n_max, CN ? CL : sp->l_max, CN ? CNS : sp->n_species);
+  const int n = g.n, L = g.L, L1 = g.L1, nlm = g.nlm, K1 = g.K1, d = sp->d, d_pad = sp->d_pad, ns = g.ns;
+  Smem s;
+  carve(g, d_pad, false, &s, smem_raw);
   const int i = centres[c];
-  const int n = sp->n_max, L = sp->l_max, L1 = L + 1, nlm = sp->nlm, K1 = sp->K1, d = sp->d, d_pad = sp->d_pad, ns = sp->n_species;
-  const int n4 = ceil4(n), K1p = ns * n4, RFS = rf_stride(L1, n4), YS = y_stride(nlm), NG = n4 / AG;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;  // DMMA fragment coordinates
   const double alpha = sp->alpha;
-  load_tables(sp, s);
-  for (int k = threadIdx.x; k < nlm * K1p; k += NT) s.X[k] = 0.0;
+  load_tables(sp, g, s);
+  for (int k = threadIdx.x; k < g.XR * g.XS; k += NT) s.X[k] = 0.0;
   __syncthreads();
 
   const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
   for (int pb = pbeg; pb < pend; pb += NBCAP) {
     int nv = gather_neighbours(sp, s, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
     for (int t0 = 0; t0 < nv; t0 += TNF) {
-      const int tn = min(TNF, nv - t0);
-      // ---- stage: radial items then harmonic items ----
+      const int tn = min(TNF, nv - t0), tn4 = ceil4(tn);
+      // ---- stage: radial items (q, a) and harmonic items (q, m); rows q in [tn, tn4) are zero (K padding) ----
       const int n_rad = tn * n, n_items = n_rad + tn * L1;
       for (int it = threadIdx.x; it < n_items; it += NT) {
         if (it < n_rad) {
           int q = it / n, a = it - q * n;
-          radial_item<false>(alpha, s.nbr[t0 + q], s.rb[a], s.nbf[t0 + q], 0.0, L, s.rf + (size_t)q * RFS + a, nullptr, n4);
+          radial_item<false>(alpha, s.nbr[t0 + q], s.rb[a], s.nbf[t0 + q], 0.0, L, s.rf + q * g.RFS + a, nullptr, g.n2);
         } else {
           int r2 = it - n_rad;
           int m = r2 / tn, q = r2 - m * tn;
           double rinv = 1.0 / s.nbr[t0 + q];
-          ylm_item(s.ynorm, L, m, s.nbd[3 * (t0 + q)] * rinv, s.nbd[3 * (t0 + q) + 1] * rinv, s.nbd[3 * (t0 + q) + 2] * rinv,
-                   s.Y + (size_t)q * YS);
+          ylm_item<false>(s.ynorm, L, m, s.nbd[3 * (t0 + q)] * rinv, s.nbd[3 * (t0 + q) + 1] * rinv, s.nbd[3 * (t0 + q) + 2] * rinv,
+                          s.Y + q * g.YS, nullptr, 0);
         }
       }
-      if (n4 != n)  // zero the padding columns once per tile (read by the 4-wide accumulate)
-        for (int it = threadIdx.x; it < tn * L1 * (n4 - n); it += NT) {
-          int row = it / (n4 - n), a = n + it % (n4 - n);
-          int q = row / L1, l = row - q * L1;
-          s.rf[(size_t)q * RFS + l * n4 + a] = 0.0;
-        }
+      for (int it = threadIdx.x; it < (tn4 - tn) * (g.RFS + g.YS); it += NT) {
+        int q = tn + it / (g.RFS + g.YS), k = it % (g.RFS + g.YS);
+        if (k < g.RFS) s.rf[q * g.RFS + k] = 0.0;
+        else s.Y[q * g.YS + (k - g.RFS)] = 0.0;
+      }
       __syncthreads();
-      // ---- accumulate: Xt_lm(s, a) += sum_q Phi_l(a; q) Y_lm(q)   (descriptors.f95:8289-8295, before the basis transform) ----
-      for (int it = threadIdx.x; it < nlm * NG; it += NT) {
-        const int lm = it / NG, g = it - lm * NG, l = s.lof[lm];
-        const double* rfp = s.rf + l * n4 + g * AG;
-        const double* yp = s.Y + lm;
-        double* xrow = s.X + (size_t)lm * K1p + g * AG;
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        int cur = s.nbs[t0];
-        for (int q = 0; q < tn; q++) {
-          int spq = s.nbs[t0 + q];
-          if (spq != cur) {
-            double* xr = xrow + cur * n4;
-            xr[0] += a0; xr[1] += a1; xr[2] += a2; xr[3] += a3;
-            a0 = a1 = a2 = a3 = 0.0;
-            cur = spq;
-          }
-          const double y = yp[(size_t)q * YS];
-          const double2 r01 = *reinterpret_cast<const double2*>(rfp + (size_t)q * RFS);
-          const double2 r23 = *reinterpret_cast<const double2*>(rfp + (size_t)q * RFS + 2);
-          a0 += y * r01.x; a1 += y * r01.y; a2 += y * r23.x; a3 += y * r23.y;
+      // ---- density expansion on the tensor cores: Xt[lm][c] += sum_q Y[q][lm] * Phi[q][l][a(c)] [species(q) == s(c)]
+      //      (descriptors.f95:8289-8295, before the basis transform); one warp per (lm tile, channel tile) ----
+      for (int t = warp; t < g.NTM * g.NTN; t += NW) {
+        const int mt = t / g.NTN, nt = t - mt * g.NTN;
+        const int lm0 = s.mt_lm0[mt], l = s.mt_l[mt];
+        const int ch = nt * 8 + fr, cs = s.col_s[ch], ca = s.col_a[ch];  // this thread's B column
+        const double* ap = s.Y + fk * g.YS + lm0 + fr;
+        const double* bp = s.rf + fk * g.RFS + l * g.n2 + ca;
+        double c0 = 0.0, c1 = 0.0;
+        for (int k0 = 0; k0 < tn4; k0 += 4) {
+          double a = ap[k0 * g.YS];
+          // padding rows q >= tn are zero; padding channels (cs < 0) only feed padding columns of X, which nothing reads
+          double b = (ns == 1 || s.nbs[t0 + k0 + fk] == cs) ? bp[k0 * g.RFS] : 0.0;
+          dmma(c0, c1, a, b);
         }
-        double* xr = xrow + cur * n4;
-        xr[0] += a0; xr[1] += a1; xr[2] += a2; xr[3] += a3;
+        const int lm = lm0 + fr;
+        if (lm < (l + 1) * (l + 1)) {
+          double* xr = s.X + lm * g.XS + nt * 8 + 2 * fk;
+          xr[0] += c0;
+          xr[1] += c1;
+        }
       }
       __syncthreads();
     }
   }
-  // ---- basis transform, once per centre: X_lm(s, a') = sum_a Xt_lm(s, a) T(a, a')   (in place: the item owns its row) ----
-  for (int it = threadIdx.x; it < nlm * ns; it += NT) {
-    double* row = s.X + (size_t)(it / ns) * K1p + (it % ns) * n4;
-    double v[SOAP_NMAX_CAP];
-    for (int a = 0; a < n; a++) v[a] = row[a];
-    for (int b = 0; b < n; b++) {
-      double t = 0.0;
-      for (int a = 0; a < n; a++) t += v[a] * s.T[a + n * b];
-      row[b] = t;
+  // ---- basis transform on the tensor cores, per species: X[lm][s,a'] = sum_a Xt[lm][s,a] T(a,a').  A warp owns 8 rows
+  //      (all species of them): it reads a species block completely before overwriting it ----
+  {
+    const int n_mt = (nlm + 7) / 8, n_nt = g.n8 / 8, n_ks = ceil4(n) / 4;
+    for (int mt = warp; mt < n_mt; mt += NW) {
+      for (int sk = 0; sk < ns; sk++) {
+        double acc[2][2] = {{0, 0}, {0, 0}};  // n8 <= 16: at most two output tiles
+        for (int ks = 0; ks < n_ks; ks++) {
+          const double a = s.X[(mt * 8 + fr) * g.XS + sk * n + ks * 4 + fk];  // columns >= n of the block meet zero rows of Tp
+#pragma unroll
+          for (int nt = 0; nt < 2; nt++)
+            if (nt < n_nt) dmma(acc[nt][0], acc[nt][1], a, s.Tp[(ks * 4 + fk) * g.TS + nt * 8 + fr]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            int ap = nt * 8 + 2 * fk + j;
+            if (nt < n_nt && ap < n) s.X[(mt * 8 + fr) * g.XS + sk * n + ap] = acc[nt][j];
+          }
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
   // central atom term (descriptors.f95:8151-8182): only a = 1 is non-zero because the Cholesky factor is lower triangular
   if (threadIdx.x < ns) {
     int k = threadIdx.x;
-    if (sp->cras || sp->species_Z[k] == Z[i] || sp->species_Z[k] == 0) s.X[k * n4] += sp->central_weight * sp->chol00 * 0.28209479177387814347;
+    if (sp->cras || sp->species_Z[k] == Z[i] || sp->species_Z[k] == 0) s.X[k * n] += sp->central_weight * sp->chol00 * 0.28209479177387814347;
   }
   __syncthreads();
   for (int k = threadIdx.x; k < nlm * K1; k += NT) {
-    int lm = k / K1, ic = k - lm * K1, sk = ic / n;
-    xlm[(size_t)c * nlm * K1 + k] = s.X[(size_t)lm * K1p + sk * n4 + (ic - sk * n)];
+    int lm = k / K1, ic = k - lm * K1;
+    xlm[(size_t)c * nlm * K1 + k] = s.X[lm * g.XS + ic];
   }
-
-  // power spectrum (descriptors.f95:8370-8418): element q = l + (l_max+1) * pair(ia, jb<=ia)
+  // ---- power spectrum on the tensor cores (descriptors.f95:8370-8418): p_l(ia,jb) = sum_m X_lm(ia) X_lm(jb) / sqrt(2l+1),
+  //      element q = l + (l_max+1) * pair(ia, jb<=ia), off-diagonal pairs times sqrt(2); one warp per (l, tile pair) ----
   double loc = 0.0;
-  for (int q = threadIdx.x; q < d - 1; q += NT) {
-    int l = q % L1, pr = q / L1;
-    int ia = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
-    while ((ia + 1) * (ia + 2) / 2 <= pr) ia++;
-    while (ia * (ia + 1) / 2 > pr) ia--;
-    int jb = pr - ia * (ia + 1) / 2;
-    const int ca = (ia / n) * n4 + ia % n, cb = (jb / n) * n4 + jb % n;
-    double t = 0.0;
-    for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) t += s.X[lm * K1p + ca] * s.X[lm * K1p + cb];
-    t *= sp->tlpo[l];
-    if (ia != jb) t *= 1.41421356237309504880;
-    s.p[q] = t;
-    loc += t * t;
+  {
+    const int n_pairs = g.NTN * (g.NTN + 1) / 2;
+    for (int t = warp; t < L1 * n_pairs; t += NW) {
+      const int l = t / n_pairs;
+      int pr = t - l * n_pairs, ti = 0;
+      while ((ti + 1) * (ti + 2) / 2 <= pr) ti++;
+      const int tj = pr - ti * (ti + 1) / 2;
+      const int lm_beg = l * l, lm_end = (l + 1) * (l + 1);
+      double c0 = 0.0, c1 = 0.0;
+      for (int k0 = lm_beg; k0 < lm_end; k0 += 4) {
+        const int lm = k0 + fk;
+        const double a = lm < lm_end ? s.X[lm * g.XS + ti * 8 + fr] : 0.0;
+        const double b = lm < lm_end ? s.X[lm * g.XS + tj * 8 + fr] : 0.0;
+        dmma(c0, c1, a, b);
+      }
+      const int ia = ti * 8 + fr;
+      const double scale = sp->tlpo[l];
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int jb = tj * 8 + 2 * fk + j;
+        if (ia < K1 && jb <= ia) {
+          double v = (j ? c1 : c0) * scale;
+          if (ia != jb) v *= 1.41421356237309504880;
+          s.p[l + L1 * (ia * (ia + 1) / 2 + jb)] = v;
+          loc += v * v;
+        }
+      }
+    }
   }
-  double nrm = sqrt(block_sum(loc, s.red));  // :8450-8451
+  double nrm = sqrt(block_sum(loc, s.red));  // :8450-8451 (block_sum synchronises: p is complete afterwards)
   double inv = sp->normalise ? 1.0 / nrm : 1.0;
   double* xr = x + (size_t)c * d_pad;
   for (int q = threadIdx.x; q < d_pad; q += NT) xr[q] = q < d - 1 ? s.p[q] * inv : (q == d - 1 ? sp->sigma0 : 0.0);
@@ -406,68 +488,8 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
 // ------------------------------------------------------------------------------------------------
 // adjoint: gvec = dE_i/dx  ->  forces / virial
 // ------------------------------------------------------------------------------------------------
-// Contribution of the harmonics of order m (both the cos and the sin type, all l >= m) of one neighbour to
-//   SA = sum_lm A_lm Y_lm           with A_lm = sum_a Lambda~_lm(a) R_l(a)
-//   G  = sum_lm B_lm grad_poly Y_lm with B_lm = sum_a Lambda~_lm(a) Phi_l(a)
-// where grad_poly is the gradient of the polynomial extension N_lm Q_l^m(z) {C_m,S_m}(x,y); the caller projects it:
-//   f_k = SA u_k + (G_k - u_k (u.G)) / r
-__device__ __forceinline__ void adjoint_order(const double* __restrict__ ynorm, int L, int m, double ux, double uy, double uz,
-                                              const double* __restrict__ lam /* Lambda~ + s*n4 */, int K1p, const double* __restrict__ rf,
-                                              const double* __restrict__ drf, int n4, double& SA, double& G0, double& G1, double& G2) {
-  double Cm, Sm, Cm1, Sm1;
-  cs_power(ux, uy, m, Cm, Sm, Cm1, Sm1);
-  const double dm = (double)m;
-  double p2 = 0.0, p1 = c_dblfact[m];        // Q^m recursion
-  double z2 = 0.0, z1 = 0.0;                 // Q^{m+1} recursion (dQ^m/dz): zero at l = m
-  for (int l = m; l <= L; l++) {
-    double pl, zl;
-    if (l == m) { pl = p1; zl = 0.0; }
-    else {
-      pl = ((double)(2 * l - 1) * uz * p1 - (double)(l + m - 1) * p2) * c_invint[l - m];
-      p2 = p1; p1 = pl;
-      if (l == m + 1) zl = c_dblfact[m + 1];
-      else zl = ((double)(2 * l - 1) * uz * z1 - (double)(l + m) * z2) * c_invint[l - m - 1];
-      z2 = z1; z1 = zl;
-    }
-    const double nrm = ynorm[l * (l + 1) / 2 + m];
-    const double q = pl * nrm, qz = zl * nrm;
-    const double* rl = rf + l * n4;
-    const double* dl = drf + l * n4;
-    const int base = l * l + l;
-    {  // cos type (or m = 0)
-      const double* lp = lam + (size_t)(base + m) * K1p;
-      double A = 0.0, B = 0.0;
-      for (int a = 0; a < n4; a += 2) {
-        const double2 lv = *reinterpret_cast<const double2*>(lp + a);
-        const double2 rv = *reinterpret_cast<const double2*>(rl + a);
-        const double2 dv = *reinterpret_cast<const double2*>(dl + a);
-        A += lv.x * dv.x + lv.y * dv.y;
-        B += lv.x * rv.x + lv.y * rv.y;
-      }
-      SA += A * (q * Cm);
-      G0 += B * (q * dm * Cm1);
-      G1 -= B * (q * dm * Sm1);
-      G2 += B * (qz * Cm);
-    }
-    if (m > 0) {  // sin type
-      const double* lp = lam + (size_t)(base - m) * K1p;
-      double A = 0.0, B = 0.0;
-      for (int a = 0; a < n4; a += 2) {
-        const double2 lv = *reinterpret_cast<const double2*>(lp + a);
-        const double2 rv = *reinterpret_cast<const double2*>(rl + a);
-        const double2 dv = *reinterpret_cast<const double2*>(dl + a);
-        A += lv.x * dv.x + lv.y * dv.y;
-        B += lv.x * rv.x + lv.y * rv.y;
-      }
-      SA += A * (q * Sm);
-      G0 += B * (q * dm * Sm1);
-      G1 += B * (q * dm * Cm1);
-      G2 += B * (qz * Sm);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
+template <int CN, int CL, int CNS>
+__global__ void __launch_bounds__(NT, 3) k_soap_adjoint(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
                                                         const int* __restrict__ n_centres_dev,
                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
@@ -478,8 +500,6 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
                                                         double e_scale, double* __restrict__ force, double* __restrict__ vir_part,
                                                         double* __restrict__ local_virial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem s;
-  carve(*sp, true, &s, smem_raw);
   const int c = blockIdx.x;
   if (c >= *n_centres_dev) {
     if (vir_part && threadIdx.x < 9) vir_part[9 * (size_t)c + threadIdx.x] = 0.0;  // unused slot of the upper-bound grid
@@ -492,97 +512,183 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
     for (int k = 0; k < n_tiles_n; k++) t += epart[(size_t)c * n_tiles_n + k];
     local_e[i] += e_scale * t;
   }
-  const int n = sp->n_max, L = sp->l_max, L1 = L + 1, nlm = sp->nlm, K1 = sp->K1, d = sp->d, d_pad = sp->d_pad, ns = sp->n_species;
-  const int n4 = ceil4(n), K1p = ns * n4, RFS = rf_stride(L1, n4), MP = m_pairs(L);
+  const Geo g = make_geo(CN ? CN : sp->n_max, CN ? CL : sp->l_max, CN ? CNS : sp->n_species);
+  const int n = g.n, L = g.L, L1 = g.L1, nlm = g.nlm, K1 = g.K1, d = sp->d, ns = g.ns;
+  Smem s;
+  carve(g, sp->d_pad, true, &s, smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
   const double alpha = sp->alpha;
-  (void)d_pad;
-  load_tables(sp, s);
+  load_tables(sp, g, s);
   // u = dE/dp: pull gradPredict back through x = p/|p| (reference forward form: descriptors.f95:8595-8600)
   const double* xr = x + (size_t)c * sp->d_pad;
   const double* gr = gvec + (size_t)c * ldg;
   // gradPredict arrives as g_splits partial sums (the K splits of GEMM-2), added here in a fixed order
   double loc = 0.0;
   for (int q = threadIdx.x; q < d - 1; q += NT) {
-    double g = gr[q];
-    for (int k = 1; k < g_splits; k++) g += gr[(size_t)k * g_split_stride + q];
-    s.p[q] = g;
-    loc += xr[q] * g;
+    double gq = gr[q];
+    for (int k = 1; k < g_splits; k++) gq += gr[(size_t)k * g_split_stride + q];
+    s.p[q] = gq;
+    loc += xr[q] * gq;
   }
   double sdot = block_sum(loc, s.red);
   double nrm = pnorm[c];
   if (sp->normalise)
     for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = (s.p[q] - xr[q] * sdot) / nrm;
-  // X_lm and Lambda = dE/dX_lm are staged in the (not yet used) radial-table area
-  double* Xs = s.rf;                       // nlm*K1
-  double* Ls = s.rf + (size_t)nlm * K1;    // nlm*K1
-  for (int k = threadIdx.x; k < nlm * K1; k += NT) Xs[k] = xlm[(size_t)c * nlm * K1 + k];
-  for (int k = threadIdx.x; k < nlm * K1p; k += NT) s.X[k] = 0.0;
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < nlm * K1; idx += NT) {
-    int lm = idx / K1, ia = idx - lm * K1, l = s.lof[lm];
-    double t = 0.0;
-    for (int jb = 0; jb < K1; jb++) {
-      int hi = ia > jb ? ia : jb, lo = ia > jb ? jb : ia;
-      double u = s.p[l + L1 * (hi * (hi + 1) / 2 + lo)];
-      t += (ia == jb ? 2.0 * u : 1.41421356237309504880 * u) * Xs[lm * K1 + jb];
-    }
-    Ls[idx] = t * sp->tlpo[l];
+  // X_lm -> shared (zero padding in rows and columns)
+  for (int k = threadIdx.x; k < g.XR * g.XS; k += NT) {
+    int lm = k / g.XS, ic = k - lm * g.XS;
+    s.X[k] = (lm < nlm && ic < K1) ? xlm[(size_t)c * nlm * K1 + (size_t)lm * K1 + ic] : 0.0;
+    s.X2[k] = 0.0;
   }
   __syncthreads();
-  // Lambda~_lm(s, a) = sum_a' T(a, a') Lambda_lm(s, a')  : the basis transform pulled back once per centre
-  for (int idx = threadIdx.x; idx < nlm * K1; idx += NT) {
-    int lm = idx / K1, ic = idx - lm * K1, sk = ic / n, a = ic - sk * n;
-    const double* lrow = Ls + (size_t)lm * K1 + sk * n;
-    double t = 0.0;
-    for (int b = 0; b < n; b++) t += s.T[a + n * b] * lrow[b];
-    s.X[(size_t)lm * K1p + sk * n4 + a] = t;
+  // ---- Lambda = dE/dX_lm on the tensor cores: Lambda[lm][ia] = sum_jb X[lm][jb] U~_l(jb, ia) / sqrt(2l+1), with the symmetric
+  //      U~_l(ia,jb) = 2 u (ia == jb) or sqrt(2) u (ia != jb), u = dE/dp at (l, pair(ia, jb)) ----
+  for (int t = warp; t < g.NTM * g.NTN; t += NW) {
+    const int mt = t / g.NTN, nt = t - mt * g.NTN;
+    const int lm0 = s.mt_lm0[mt], l = s.mt_l[mt];
+    const int ia = nt * 8 + fr;
+    double c0 = 0.0, c1 = 0.0;
+    for (int k0 = 0; k0 < g.K18; k0 += 4) {
+      const int jb = k0 + fk;
+      const double a = s.X[(lm0 + fr) * g.XS + jb];
+      double b = 0.0;
+      if (ia < K1 && jb < K1) {
+        const int hi = ia > jb ? ia : jb, lo = ia > jb ? jb : ia;
+        const double u = s.p[l + L1 * (hi * (hi + 1) / 2 + lo)];
+        b = ia == jb ? 2.0 * u : 1.41421356237309504880 * u;
+      }
+      dmma(c0, c1, a, b);
+    }
+    const int lm = lm0 + fr;
+    if (lm < (l + 1) * (l + 1)) {
+      const double sc = sp->tlpo[l];
+      double* lr = s.X2 + lm * g.XS + nt * 8 + 2 * fk;
+      lr[0] = c0 * sc;
+      lr[1] = c1 * sc;
+    }
+  }
+  __syncthreads();
+  // ---- Lambda~[lm][s,a] = sum_a' Lambda[lm][s,a'] T(a,a') : the basis transform pulled back once per centre (into s.X) ----
+  {
+    const int n_mt = (nlm + 7) / 8, n_nt = g.n8 / 8, n_ks = ceil4(n) / 4;
+    for (int t = warp; t < n_mt * ns; t += NW) {
+      const int mt = t / ns, sk = t - mt * ns;
+      double acc[2][2] = {{0, 0}, {0, 0}};
+      for (int ks = 0; ks < n_ks; ks++) {
+        const int ap = ks * 4 + fk;  // k index = a'
+        const double a = ap < n ? s.X2[(mt * 8 + fr) * g.XS + sk * n + ap] : 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+          if (nt < n_nt) dmma(acc[nt][0], acc[nt][1], a, s.Tp[(nt * 8 + fr) * g.TS + ap]);  // B[k=a'][col=a] = T(a,a')
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          int a = nt * 8 + 2 * fk + j;
+          if (nt < n_nt && a < n) s.X[(mt * 8 + fr) * g.XS + sk * n + a] = acc[nt][j];
+        }
+    }
   }
   __syncthreads();
 
   double fi[3] = {0, 0, 0}, vir[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const int gstride = TNA * g.YS;
   const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
   for (int pb = pbeg; pb < pend; pb += NBCAP) {
     int nv = gather_neighbours(sp, s, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
     for (int t0 = 0; t0 < nv; t0 += TNA) {
       const int tn = min(TNA, nv - t0);
-      // ---- stage: radial tables with derivative ----
-      for (int it = threadIdx.x; it < tn * n4; it += NT) {
-        int q = it / n4, a = it - q * n4;
-        if (a < n)
-          radial_item<true>(alpha, s.nbr[t0 + q], s.rb[a], s.nbf[t0 + q], s.nbdf[t0 + q], L, s.rf + (size_t)q * RFS + a,
-                            s.drf + (size_t)q * RFS + a, n4);
-        else
-          for (int l = 0; l < L1; l++) s.rf[(size_t)q * RFS + l * n4 + a] = s.drf[(size_t)q * RFS + l * n4 + a] = 0.0;
+      // ---- stage: radial tables with derivative, harmonics with polynomial gradients; columns q in [tn, 8) zero ----
+      const int n_rad = tn * n, n_items = n_rad + tn * L1;
+      for (int it = threadIdx.x; it < n_items; it += NT) {
+        if (it < n_rad) {
+          int q = it / n, a = it - q * n;
+          radial_item<true>(alpha, s.nbr[t0 + q], s.rb[a], s.nbf[t0 + q], s.nbdf[t0 + q], L, s.rf + q * g.RFS + a,
+                            s.drf + q * g.RFS + a, g.n2);
+        } else {
+          int r2 = it - n_rad;
+          int m = r2 / tn, q = r2 - m * tn;
+          double rinv = 1.0 / s.nbr[t0 + q];
+          ylm_item<true>(s.ynorm, L, m, s.nbd[3 * (t0 + q)] * rinv, s.nbd[3 * (t0 + q) + 1] * rinv, s.nbd[3 * (t0 + q) + 2] * rinv,
+                         s.Y + q * g.YS, s.G + q * g.YS, gstride);
+        }
+      }
+      for (int it = threadIdx.x; it < (TNA - tn) * g.YS; it += NT) {  // harmonics of the padding neighbours: zero (their A, B are zero too)
+        int q = tn + it / g.YS, k = it % g.YS;
+        s.Y[q * g.YS + k] = 0.0;
+        s.G[q * g.YS + k] = 0.0;
+        s.G[gstride + q * g.YS + k] = 0.0;
+        s.G[2 * gstride + q * g.YS + k] = 0.0;
       }
       __syncthreads();
-      // ---- contract: item (m-pair, neighbour); orders are paired (m, L+1-m) so that every item has about L+2 (l,m) terms ----
-      for (int it = threadIdx.x; it < tn * MP; it += NT) {
-        const int mp = it / tn, q = it - mp * tn;
-        const double r = s.nbr[t0 + q], rinv = 1.0 / r;
-        const double ux = s.nbd[3 * (t0 + q)] * rinv, uy = s.nbd[3 * (t0 + q) + 1] * rinv, uz = s.nbd[3 * (t0 + q) + 2] * rinv;
-        const double* lam = s.X + s.nbs[t0 + q] * n4;
-        const double* rfq = s.rf + (size_t)q * RFS;
-        const double* drq = s.drf + (size_t)q * RFS;
-        double SA = 0, G0 = 0, G1 = 0, G2 = 0;
-        adjoint_order(s.ynorm, L, mp, ux, uy, uz, lam, K1p, rfq, drq, n4, SA, G0, G1, G2);
-        const int m2 = L + 1 - mp;
-        if (mp > 0 && m2 > mp) adjoint_order(s.ynorm, L, m2, ux, uy, uz, lam, K1p, rfq, drq, n4, SA, G0, G1, G2);
-        const double ug = ux * G0 + uy * G1 + uz * G2;
-        double* pp = s.part + ((size_t)q * MP + mp) * 3;
-        pp[0] = SA * ux + (G0 - ux * ug) * rinv;
-        pp[1] = SA * uy + (G1 - uy * ug) * rinv;
-        pp[2] = SA * uz + (G2 - uz * ug) * rinv;
+      // ---- contraction on the tensor cores: A_lm(q) = sum_c Lambda~[lm][c] R[q][l][a(c)], B_lm(q) likewise with Phi;
+      //      each thread then folds its two (lm, q) elements with Y and grad Y:
+      //      SA(q) += A_lm(q) Y_lm(q),  G_k(q) += B_lm(q) g_k,lm(q) ----
+      double SA[2] = {0, 0}, G0[2] = {0, 0}, G1[2] = {0, 0}, G2[2] = {0, 0};
+      const int qb = fr;  // this thread's B column = neighbour
+      const int sq = qb < tn ? s.nbs[t0 + qb] : -2;
+      for (int mt = warp; mt < g.NTM; mt += NW) {
+        const int lm0 = s.mt_lm0[mt], l = s.mt_l[mt];
+        double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+        for (int k0 = 0; k0 < g.K18; k0 += 4) {
+          const int ch = k0 + fk;
+          const double lam = s.X[(lm0 + fr) * g.XS + ch];
+          const bool on = s.col_s[ch] == sq;
+          const int off = qb * g.RFS + l * g.n2 + s.col_a[ch];
+          const double rv = on ? s.drf[off] : 0.0, pv = on ? s.rf[off] : 0.0;
+          dmma(a0, a1, lam, rv);
+          dmma(b0, b1, lam, pv);
+        }
+        const int lm = lm0 + fr;
+        if (lm < (l + 1) * (l + 1)) {
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const int yo = (2 * fk + j) * g.YS + lm;
+            const double av = j ? a1 : a0, bv = j ? b1 : b0;
+            SA[j] += av * s.Y[yo];
+            G0[j] += bv * s.G[yo];
+            G1[j] += bv * s.G[gstride + yo];
+            G2[j] += bv * s.G[2 * gstride + yo];
+          }
+        }
+      }
+      // sum over the 8 fragment rows (lanes with equal fk), then over the warps through shared memory
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          SA[j] += __shfl_xor_sync(0xffffffffu, SA[j], o);
+          G0[j] += __shfl_xor_sync(0xffffffffu, G0[j], o);
+          G1[j] += __shfl_xor_sync(0xffffffffu, G1[j], o);
+          G2[j] += __shfl_xor_sync(0xffffffffu, G2[j], o);
+        }
+      }
+      if (fr == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          double* pp = s.part + (warp * TNA + 2 * fk + j) * 4;
+          pp[0] = SA[j]; pp[1] = G0[j]; pp[2] = G1[j]; pp[3] = G2[j];
+        }
       }
       __syncthreads();
       // ---- scatter: one thread per neighbour ----
       if (threadIdx.x < tn) {
         const int q = threadIdx.x;
-        double f0 = 0, f1 = 0, f2 = 0;
-        for (int mp = 0; mp < MP; mp++) {
-          const double* pp = s.part + ((size_t)q * MP + mp) * 3;
-          f0 += pp[0]; f1 += pp[1]; f2 += pp[2];
+        double sa = 0, g0 = 0, g1 = 0, g2 = 0;
+        for (int w = 0; w < NW; w++) {
+          const double* pp = s.part + (w * TNA + q) * 4;
+          sa += pp[0]; g0 += pp[1]; g1 += pp[2]; g2 += pp[3];
         }
-        f0 *= e_scale; f1 *= e_scale; f2 *= e_scale;
+        const double r = s.nbr[t0 + q], rinv = 1.0 / r;
+        const double dx = s.nbd[3 * (t0 + q)], dy = s.nbd[3 * (t0 + q) + 1], dz = s.nbd[3 * (t0 + q) + 2];
+        const double ux = dx * rinv, uy = dy * rinv, uz = dz * rinv;
+        const double ug = ux * g0 + uy * g1 + uz * g2;
+        // f_gp,k = sum_lm [ A_lm Y_lm u_k + B_lm grad_k Y_lm ],  grad Y = (g - u (u.g)) / r
+        const double f0 = (sa * ux + (g0 - ux * ug) * rinv) * e_scale;
+        const double f1 = (sa * uy + (g1 - uy * ug) * rinv) * e_scale;
+        const double f2 = (sa * uz + (g2 - uz * ug) * rinv) * e_scale;
         // IPModel_GAP.f95:479-491: F_j -= f_gp ; centre row is minus the sum ; W_j -= (pos_j - pos_i) (x) f_gp
         const int j = s.nbj[t0 + q];
         if (force) {
@@ -591,7 +697,6 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
           atomicAdd(&force[3 * (size_t)j + 2], -f2);
           fi[0] += f0; fi[1] += f1; fi[2] += f2;
         }
-        const double dx = s.nbd[3 * (t0 + q)], dy = s.nbd[3 * (t0 + q) + 1], dz = s.nbd[3 * (t0 + q) + 2];
         double wv[9] = {dx * f0, dy * f0, dz * f0, dx * f1, dy * f1, dz * f1, dx * f2, dy * f2, dz * f2};  // column-major (a + 3b)
 #pragma unroll
         for (int k = 0; k < 9; k++) vir[k] -= wv[k];
@@ -599,17 +704,17 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
 #pragma unroll
           for (int k = 0; k < 9; k++) atomicAdd(&local_virial[9 * (size_t)j + k], -wv[k]);
       }
-      // the next tile's stage phase overwrites rf/drf only after the barrier at its end; part is rewritten after that barrier too
+      // (the next tile's stage phase only writes rf/drf/Y/G, which the scatter does not read; part is rewritten after the
+      //  next stage barrier)
     }
   }
   // combine the per-thread centre force / virial partials in fixed order (threads 0..TNA-1 hold them)
   for (int k = 0; k < 3; k++) fi[k] = warp_sum(fi[k]);
   for (int k = 0; k < 9; k++) vir[k] = warp_sum(vir[k]);
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) {
-    for (int k = 0; k < 3; k++) s.red[w * 12 + k] = fi[k];
-    for (int k = 0; k < 9; k++) s.red[w * 12 + 3 + k] = vir[k];
+    for (int k = 0; k < 3; k++) s.red[warp * 12 + k] = fi[k];
+    for (int k = 0; k < 9; k++) s.red[warp * 12 + 3 + k] = vir[k];
   }
   __syncthreads();
   if (threadIdx.x < 12) {
@@ -639,8 +744,11 @@ __global__ void k_compact(const int* __restrict__ scan, const int* __restrict__ 
 
 }  // namespace
 
-size_t soap_forward_smem(const SoapDev& h) { return carve(h, false, nullptr, nullptr); }
-size_t soap_adjoint_smem(const SoapDev& h) { return carve(h, true, nullptr, nullptr); }
+size_t soap_forward_smem(const SoapDev& h) { return carve(make_geo(h.n_max, h.l_max, h.n_species), h.d_pad, false, nullptr, nullptr); }
+size_t soap_adjoint_smem(const SoapDev& h) { return carve(make_geo(h.n_max, h.l_max, h.n_species), h.d_pad, true, nullptr, nullptr); }
+
+// (n_max, l_max, n_species) combinations with a fully specialised instantiation; everything else runs the generic one
+#define SOAP_SPECIALISATIONS(X) X(8, 8, 1) X(12, 8, 1) X(10, 6, 2)
 
 void launch_select_centres(const int* Z, int first, int last, const SoapDev* sp, int* flags, cudaStream_t st, int* launches) {
   int n = last - first + 1;
@@ -659,9 +767,17 @@ void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres
   const int n_centres = n_centres_ub;
   if (n_centres <= 0) return;
   size_t sm = soap_forward_smem(h);
-  cudaFuncSetAttribute(k_soap_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_soap_forward<<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
   *launches += 1;
+#define GO(N, L, S)                                                                                                       \
+  if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                  \
+    cudaFuncSetAttribute(k_soap_forward<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                   \
+    k_soap_forward<N, L, S><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm); \
+    return;                                                                                                                \
+  }
+  SOAP_SPECIALISATIONS(GO)
+#undef GO
+  cudaFuncSetAttribute(k_soap_forward<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_soap_forward<0, 0, 0><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
 }
 
 void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off,
@@ -672,10 +788,20 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
   const int n_centres = n_centres_ub;
   if (n_centres <= 0) return;
   size_t sm = soap_adjoint_smem(h);
-  cudaFuncSetAttribute(k_soap_adjoint, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_soap_adjoint<<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, g_splits,
-                                            g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);
   *launches += 1;
+#define GO(N, L, S)                                                                                                                          \
+  if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                                     \
+    cudaFuncSetAttribute(k_soap_adjoint<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                      \
+    k_soap_adjoint<N, L, S><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, \
+                                                       g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part,         \
+                                                       local_virial);                                                                         \
+    return;                                                                                                                                   \
+  }
+  SOAP_SPECIALISATIONS(GO)
+#undef GO
+  cudaFuncSetAttribute(k_soap_adjoint<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_soap_adjoint<0, 0, 0><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
+                                                     g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);
 }
 
 }  // namespace gapb200
