@@ -38,7 +38,7 @@ namespace {
 constexpr int NT = 128;    // threads per CTA
 constexpr int NBCAP = 128; // CSR entries examined per pass (= compacted list capacity)
 constexpr int NW = NT / 32;
-constexpr int TNF = 32;    // neighbours per tile, forward (multiple of 4: K steps of the DMMA)
+constexpr int TNF = 16;    // neighbours per tile, forward (multiple of 4: K steps of the DMMA)
 constexpr int TNA = 8;     // neighbours per tile, adjoint (= one DMMA N tile)
 constexpr int LC = SOAP_LMAX_CAP;
 constexpr double PI_D = 3.14159265358979323846264338327950288;
@@ -202,6 +202,13 @@ __device__ __forceinline__ void load_tables(const SoapDev* sp, const Geo& g, con
   }
 }
 
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -339,7 +346,7 @@ __device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L
 // CN / CL / CNS: compile-time n_max / l_max / n_species (0 = read them from the model: generic instantiation).  With
 // constants every table stride, loop bound and index division folds at compile time.
 template <int CN, int CL, int CNS>
-__global__ void __launch_bounds__(NT, 3) k_soap_forward(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
+__global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
                                                         const int* __restrict__ n_centres_dev,
                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
@@ -489,7 +496,7 @@ __global__ void __launch_bounds__(NT, 3) k_soap_forward(const SoapDev* __restric
 // adjoint: gvec = dE_i/dx  ->  forces / virial
 // ------------------------------------------------------------------------------------------------
 template <int CN, int CL, int CNS>
-__global__ void __launch_bounds__(NT, 3) k_soap_adjoint(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
+__global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
                                                         const int* __restrict__ n_centres_dev,
                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
@@ -523,24 +530,47 @@ __global__ void __launch_bounds__(NT, 3) k_soap_adjoint(const SoapDev* __restric
   // u = dE/dp: pull gradPredict back through x = p/|p| (reference forward form: descriptors.f95:8595-8600)
   const double* xr = x + (size_t)c * sp->d_pad;
   const double* gr = gvec + (size_t)c * ldg;
-  // gradPredict arrives as g_splits partial sums (the K splits of GEMM-2), added here in a fixed order
-  double loc = 0.0;
-  for (int q = threadIdx.x; q < d - 1; q += NT) {
-    double gq = gr[q];
-    for (int k = 1; k < g_splits; k++) gq += gr[(size_t)k * g_split_stride + q];
-    s.p[q] = gq;
-    loc += xr[q] * gq;
+  // X_lm -> shared: asynchronous copies issued first so that their latency overlaps the gradPredict loads below
+  for (int k = threadIdx.x; k < nlm * K1; k += NT) {
+    int lm = k / K1, ic = k - lm * K1;
+    cp_async8(s.X + lm * g.XS + ic, xlm + (size_t)c * nlm * K1 + k);
   }
-  double sdot = block_sum(loc, s.red);
-  double nrm = pnorm[c];
-  if (sp->normalise)
-    for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = (s.p[q] - xr[q] * sdot) / nrm;
-  // X_lm -> shared (zero padding in rows and columns)
+  cp_async_commit();
+  // gradPredict arrives as g_splits partial sums (the K splits of GEMM-2), added here in a fixed order; four elements per
+  // thread are in flight at a time
+  double loc = 0.0;
+  const double nrm = pnorm[c];
+  for (int q0 = 0; q0 < d - 1; q0 += 4 * NT) {
+    double xv[4], gv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int q = q0 + u * NT + threadIdx.x;
+      xv[u] = q < d - 1 ? xr[q] : 0.0;
+      gv[u] = q < d - 1 ? gr[q] : 0.0;
+    }
+    for (int k = 1; k < g_splits; k++)
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int q = q0 + u * NT + threadIdx.x;
+        if (q < d - 1) gv[u] += gr[(size_t)k * g_split_stride + q];
+      }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int q = q0 + u * NT + threadIdx.x;
+      if (q < d - 1) s.p[q] = gv[u];
+      loc += xv[u] * gv[u];
+    }
+  }
+  // zero padding of X (rows >= nlm, columns >= K1) and the Lambda buffer
   for (int k = threadIdx.x; k < g.XR * g.XS; k += NT) {
     int lm = k / g.XS, ic = k - lm * g.XS;
-    s.X[k] = (lm < nlm && ic < K1) ? xlm[(size_t)c * nlm * K1 + (size_t)lm * K1 + ic] : 0.0;
+    if (lm >= nlm || ic >= K1) s.X[k] = 0.0;
     s.X2[k] = 0.0;
   }
+  double sdot = block_sum(loc, s.red);
+  if (sp->normalise)
+    for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = (s.p[q] - xr[q] * sdot) / nrm;
+  cp_async_wait_all();
   __syncthreads();
   // ---- Lambda = dE/dX_lm on the tensor cores: Lambda[lm][ia] = sum_jb X[lm][jb] U~_l(jb, ia) / sqrt(2l+1), with the symmetric
   //      U~_l(ia,jb) = 2 u (ia == jb) or sqrt(2) u (ia != jb), u = dE/dp at (l, pair(ia, jb)) ----
