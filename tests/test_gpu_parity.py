@@ -344,3 +344,109 @@ def test_speculative_neighbour_list_overflow_repeats(si_model, si_frames):
     o = om.calc(dense)
     assert abs(r["energy"] - o["energy"]) / len(a) < TOL_E_PER_ATOM
     assert np.abs(r["force"] - o["force"]).max() < TOL_F
+
+
+# ----------------------------------------------------------------------------------------------------
+# the other BASELINE configurations: reduced sizes against the oracle, full sizes through invariances
+# ----------------------------------------------------------------------------------------------------
+def _oracle_desc(desc, at):
+    return orc.soap_descriptor(desc, at)["data"]
+
+
+def test_config_B_reduced_vs_oracle(tmp_path):
+    # SiC, 2 species: three distance_2b + one SOAP (n_max=10 l_max=6) per centre species
+    atoms, xml = syn.build_config_B(str(tmp_path), _oracle_desc, n_cells=3, M=60)
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    assert pot.n_coordinate == 5
+    check_efv(pot, om, atoms)
+
+
+def test_config_C_reduced_vs_oracle(tmp_path):
+    # amorphous carbon, cutoff 5.5 (about 105 neighbours: several shared-memory tiles per centre), small periodic box
+    atoms, xml = syn.build_config_C(str(tmp_path), _oracle_desc, N=400, M=80, n_src=300)
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    r, o = check_efv(pot, om, atoms)
+    off = pot.calc_connect(atoms)[0]
+    assert np.diff(off).mean() > 90
+
+
+def test_config_D_reduced_vs_oracle(tmp_path):
+    # Si slab with vacuum, n_max=12 (two DMMA channel tiles), evaluated whole and as 8 centre blocks
+    atoms, xml = syn.build_config_D(str(tmp_path), _oracle_desc, nx=3, ny=3, nz=2, M=60)
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    r, o = check_efv(pot, om, atoms)
+    tot = {k: 0.0 for k in ("energy", "force", "virial")}
+    for rank in range(8):
+        p = Potential("", param_filename=xml)
+        p.set_partition(rank, 8)
+        pr = p.calc(atoms, force=True, virial=True)
+        for k in tot:
+            tot[k] = tot[k] + np.asarray(pr[k])
+    assert abs(tot["energy"] - o["energy"]) / len(atoms) < TOL_E_PER_ATOM
+    assert np.abs(tot["force"] - o["force"]).max() < TOL_F
+    assert np.abs(tot["virial"] - o["virial"]).max() < TOL_V
+
+
+def _invariance_checks(pot, atoms, r, fd_tol=2e-6):
+    assert np.abs(r["force"].sum(axis=0)).max() < 1e-7          # translation invariance
+    assert np.abs(r["virial"] - r["virial"].T).max() < 1e-6 * max(1.0, np.abs(r["virial"]).max())  # rotation invariance
+    rng = np.random.default_rng(0)
+    dirn = rng.normal(size=atoms.positions.shape)
+    dirn /= np.linalg.norm(dirn)
+    h = 1e-4
+    ep = pot.calc(Atoms(atoms.numbers, atoms.positions + h * dirn, atoms.cell, atoms.pbc))["energy"]
+    em = pot.calc(Atoms(atoms.numbers, atoms.positions - h * dirn, atoms.cell, atoms.pbc))["energy"]
+    assert abs((ep - em) / (2 * h) + np.sum(r["force"] * dirn)) < fd_tol * max(1.0, np.linalg.norm(r["force"]))
+
+
+def test_config_B_full_size_properties(tmp_path):
+    boot = syn.bootstrap_xml(str(tmp_path / "boot.xml"), [(syn.SOAP_B % 6, syn.soap_dimension(10, 6, 2)), (syn.SOAP_B % 14, syn.soap_dimension(10, 6, 2))])
+    bp = Potential("", param_filename=boot)
+    ic = {syn.SOAP_B % 6: 0, syn.SOAP_B % 14: 1}
+    atoms, xml = syn.build_config_B(str(tmp_path), lambda desc, at: bp.descriptor_calc(at, ic[desc])[0], n_cells=16, M=4000)
+    assert len(atoms) == 32768
+    pot = Potential("", param_filename=xml)
+    r = pot.calc(atoms, force=True, virial=True, local_energy=True)
+    assert abs(r["local_energy"].sum() - r["energy"]) < 1e-6
+    _invariance_checks(pot, atoms, r)
+    # oracle on a bounded sample of centres, SOAP coordinates only (distance_2b splits each pair energy between both ends, so
+    # its partial local energies are not comparable centre by centre): a SOAP-only copy of the same model
+    spec = orc.load_gap_xml(xml)
+    spec["coordinates"] = spec["coordinates"][3:]
+    om = orc.Model(model=spec)
+    first, last = 5000, 5016
+    o = om.calc(atoms, first=first, last=last, local_energy=True, force=False, virial=False)
+    e_soap = sum(pot.calc(atoms, local_energy=True, args_str="only_descriptor=%d" % k)["local_energy"] for k in (4, 5))
+    e0 = np.where(atoms.numbers == 14, -158.54496821, -148.314002)
+    assert np.abs((e_soap - 2 * e0)[first:last] - (o["local_energy"] - e0)[first:last]).max() < 1e-8
+
+
+def test_config_C_full_size_properties(tmp_path):
+    boot = syn.bootstrap_xml(str(tmp_path / "boot.xml"), [(syn.SOAP_C, syn.soap_dimension(8, 8))])
+    bp = Potential("", param_filename=boot)
+    atoms, xml = syn.build_config_C(str(tmp_path), lambda desc, at: bp.descriptor_calc(at, 0)[0], N=262144, M=9000, n_src=12288)
+    pot = Potential("", param_filename=xml)
+    r = pot.calc(atoms, force=True, virial=True, local_energy=True)
+    assert abs(r["local_energy"].sum() - r["energy"]) < 1e-5
+    _invariance_checks(pot, atoms, r)
+    om = orc.Model(xml)
+    first, last = 1000, 1016
+    o = om.calc(atoms, first=first, last=last, local_energy=True, force=False, virial=False)
+    assert np.abs(r["local_energy"][first:last] - o["local_energy"][first:last]).max() < 1e-8
+
+
+def test_config_D_full_size_one_of_eight_blocks(tmp_path):
+    # the 1,048,576-atom slab as rank 0 of 8 sees it: all positions resident, 131,072 centres evaluated
+    boot = syn.bootstrap_xml(str(tmp_path / "boot.xml"), [(syn.SOAP_D, syn.soap_dimension(12, 8))])
+    bp = Potential("", param_filename=boot)
+    atoms, xml = syn.build_config_D(str(tmp_path), lambda desc, at: bp.descriptor_calc(at, 0)[0], M=8000)
+    assert len(atoms) == 1048576
+    pot = Potential("", param_filename=xml)
+    pot.set_partition(0, 8)
+    r = pot.calc(atoms, force=True, virial=True, local_energy=True)
+    assert np.abs(r["force"].sum(axis=0)).max() < 1e-7  # every centre's contributions sum to zero
+    assert np.count_nonzero(r["local_energy"]) == 131072
+    om = orc.Model(xml)
+    first, last = 70000, 70008
+    o = om.calc(atoms, first=first, last=last, local_energy=True, force=False, virial=False)
+    assert np.abs(r["local_energy"][first:last] - o["local_energy"][first:last]).max() < 1e-8
