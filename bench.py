@@ -33,6 +33,8 @@ import numpy as np  # noqa: E402
 METRIC = "GAP-SOAP energy+force+virial atoms/sec (incl. neighbour-list build)"
 UNIT = "atoms/s"
 N_MAX, L_MAX, M_SPARSE, CELLS = 8, 8, 2000, 8
+# (n_max, l_max, n_species, sparse points per SOAP coordinate, neighbours per centre) of the named shapes
+SHAPES = {"A": (8, 8, 1, 2000, 28.0), "B": (10, 6, 2, 4000, 50.0), "C": (8, 8, 1, 9000, 104.0), "D": (12, 8, 1, 8000, 27.0)}
 
 
 def peaks():
@@ -88,11 +90,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+CONFIG = "A"  # --config: A is the bench line (BASELINE configs[1]); B, C, D are exploration runs of the other named shapes
+
+
 def build_workload(tmp, n_gpus, descriptor_fn):
     """Config A (x n_gpus along z for weak scaling) + its random-init model, written as a reference-format GAP XML."""
     from quip_b200 import synthetic as syn
     from quip_b200.gap_xml import write_gap_xml
 
+    if CONFIG == "B":
+        return syn.build_config_B(tmp, descriptor_fn)
+    if CONFIG == "C":
+        return syn.build_config_C(tmp, descriptor_fn, n_src=12288)
+    if CONFIG == "D":
+        return syn.build_config_D(tmp, descriptor_fn)
     atoms = syn.si_diamond(CELLS, CELLS, CELLS * n_gpus, seed=1)
     src = syn.si_diamond(CELLS, CELLS, CELLS, rattle=0.08, seed=101, strain=0.01)
     X = descriptor_fn(syn.SOAP_A, src)
@@ -102,6 +113,10 @@ def build_workload(tmp, n_gpus, descriptor_fn):
 
 
 def workload_name(n_gpus):
+    if CONFIG != "A":
+        return {"B": "SiC 32768 atoms, 3x distance_2b + 2x SOAP n_max=10 l_max=6, 4000 sparse points per species (strong scaling over %d GPUs)",
+                "C": "amorphous carbon 262144 atoms, SOAP cutoff 5.5 n_max=8 l_max=8, 9000 sparse points (strong scaling over %d GPUs)",
+                "D": "Si slab 1048576 atoms, SOAP n_max=12 l_max=8, 8000 sparse points (strong scaling over %d GPUs)"}[CONFIG] % n_gpus
     return ("Si diamond %d atoms (8x8x%d cells, rattled 0.05 A), SOAP n_max=8 l_max=8 cutoff=5.0 zeta=4, 2000 sparse points, "
             "single-step E/F/V incl. neighbour list" % (4096 * n_gpus, 8 * n_gpus))
 
@@ -207,9 +222,12 @@ def run_b200(args):
     from quip_b200 import synthetic as syn
 
     tmp = tempfile.mkdtemp(prefix="gapb200_bench_r%d_" % rank)
-    boot = syn.bootstrap_xml(os.path.join(tmp, "boot.xml"), [(syn.SOAP_A, syn.soap_dimension(N_MAX, L_MAX))])
+    descs = {"A": [(syn.SOAP_A, syn.soap_dimension(8, 8))], "B": [(syn.SOAP_B % 6, syn.soap_dimension(10, 6, 2)), (syn.SOAP_B % 14, syn.soap_dimension(10, 6, 2))],
+             "C": [(syn.SOAP_C, syn.soap_dimension(8, 8))], "D": [(syn.SOAP_D, syn.soap_dimension(12, 8))]}[CONFIG]
+    boot = syn.bootstrap_xml(os.path.join(tmp, "boot.xml"), descs)
     bp = Potential("", param_filename=boot, device=local)
-    atoms, xml = build_workload(tmp, n_gpus, lambda desc, at: bp.descriptor_calc(at, 0)[0])
+    which = {dsc: k for k, (dsc, _) in enumerate(descs)}
+    atoms, xml = build_workload(tmp, n_gpus, lambda desc, at: bp.descriptor_calc(at, which[desc])[0])
     bp.finalise()
     N = len(atoms)
     sp = ShardedPotential("", param_filename=xml, device=local, rank=rank, world_size=world)
@@ -290,9 +308,9 @@ def run_b200(args):
     pk = peaks()
     st = {k: v / args.steps for k, v in stage_sum.items()}
     nc = N // world  # centres of this rank
-    d = syn.soap_dimension(N_MAX, L_MAX)
-    nn = 28.0
-    nlmK1 = (L_MAX + 1) ** 2 * N_MAX
+    n_max, l_max, n_spec, M_SPARSE, nn = SHAPES[CONFIG]
+    d = syn.soap_dimension(n_max, l_max, n_spec)
+    nlmK1 = (l_max + 1) ** 2 * n_max * n_spec
     kernels = {
         # FP64 tensor-core GEMMs: 2 d M flops per centre each (F_cov = 4 d M per atom for the pair)
         "cov_gemm1": {"bound": "tensor", "work": 2.0 * d * M_SPARSE * nc, "unit": "TFLOP/s"},
@@ -303,6 +321,7 @@ def run_b200(args):
         "soap_adjoint": {"bound": "hbm", "work": nc * (8.0 * nn + 28.0 * nn + 8.0 * (2 * d + nlmK1 + 1) + 24.0 * (nn + 1)), "unit": "GB/s"},
         "connect": {"bound": "hbm", "work": N * (24.0 + 4.0) * 2 + nc * nn * 8.0, "unit": "GB/s"},
     }
+    M_SPARSE = SHAPES[CONFIG][3]
     dom = max(kernels, key=lambda k: st.get(k, 0.0))
     kd = kernels[dom]
     secs = st[dom] * 1e-3
@@ -319,7 +338,7 @@ def run_b200(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n_gpus), "atoms": N, "atoms_per_gpu": N // world, "sparse_points": M_SPARSE, "descriptor_dim": d,
+            "config": {"workload": workload_name(n_gpus), "atoms": N, "atoms_per_gpu": N // world, "sparse_points": SHAPES[CONFIG][3], "descriptor_dim": d,
                        "parallelism": "centre-block x%d, positions replicated, one all-reduce of [E|virial|F]" % world,
                        "l2": "flushed between timed steps (512 MiB memset)", "timing": "CUDA events per step on the launching stream, max over ranks"},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 28 * N, "d2h_bytes_per_step": 8 * (10 + 3 * N)},
@@ -340,7 +359,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="A", choices=["A", "B", "C", "D"], help="A = the bench line; B/C/D = the other BASELINE shapes (exploration)")
     args = ap.parse_args()
+    global CONFIG
+    CONFIG = args.config
     if args.impl == "reference":
         run_reference(args)
     else:

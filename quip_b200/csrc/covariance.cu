@@ -33,7 +33,7 @@ constexpr int MT = WTM / 8;         // 4 DMMA tiles along M per warp
 constexpr int LDS_ROW = BK + 4;     // padded row (doubles)
 constexpr int STAGES = 3;
 template <int BN>
-constexpr size_t gemm_smem() { return (size_t)STAGES * (BM + BN) * LDS_ROW * sizeof(double); }
+constexpr size_t gemm_smem() { return ((size_t)STAGES * (BM + BN) * LDS_ROW + BN) * sizeof(double); }  // + the tile's GP weights
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -47,19 +47,22 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// load one K-slab (BK columns) of the A and B tiles into a stage
+// One K-slab (BK columns) of the A and B tiles -> a pipeline stage.  With BK/2 = 8 sixteen-byte chunks per row and 128
+// threads, thread t always copies column chunk (t % 8) of rows t/8, t/8 + 16, t/8 + 32, ...: the global pointers and the
+// shared addresses are computed ONCE per tile (gA/gB/sA/sB below) and only advance by constants afterwards -- the
+// index arithmetic of the first version cost more issue slots than the DMMAs of a slab.
+constexpr int CPR = BK / 2;                       // 16-byte chunks per row
+constexpr int ROWS_PER_PASS = NTHREADS / CPR;     // 16
+static_assert(BM % ROWS_PER_PASS == 0, "tile rows must be a multiple of the rows copied per pass");
 template <int BN>
-__device__ __forceinline__ void load_stage(double* As, double* Bs, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-                                           int m0, int n0, int k0) {
-  constexpr int CPR = BK / 2;  // 16-byte chunks per row
-  for (int chunk = threadIdx.x; chunk < BM * CPR; chunk += NTHREADS) {
-    int row = chunk / CPR, cc = (chunk % CPR) * 2;
-    cp_async16(As + row * LDS_ROW + cc, A + (size_t)(m0 + row) * lda + k0 + cc);
-  }
-  for (int chunk = threadIdx.x; chunk < BN * CPR; chunk += NTHREADS) {
-    int row = chunk / CPR, cc = (chunk % CPR) * 2;
-    cp_async16(Bs + row * LDS_ROW + cc, B + (size_t)(n0 + row) * ldb + k0 + cc);
-  }
+__device__ __forceinline__ void load_stage(unsigned sA, unsigned sB, const double* gA, const double* gB, size_t lda16, size_t ldb16) {
+  static_assert(BN % ROWS_PER_PASS == 0, "tile rows must be a multiple of the rows copied per pass");
+#pragma unroll
+  for (int it = 0; it < BM / ROWS_PER_PASS; it++)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sA + it * ROWS_PER_PASS * LDS_ROW * 8), "l"(gA + it * lda16));
+#pragma unroll
+  for (int it = 0; it < BN / ROWS_PER_PASS; it++)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sB + it * ROWS_PER_PASS * LDS_ROW * 8), "l"(gB + it * ldb16));
 }
 
 // c^(zeta-1).  ZI = compile-time integer zeta (1..4, the usual GAP settings; fast_pow_1d multiplies repeatedly,
@@ -84,14 +87,13 @@ __device__ __forceinline__ double pow_zm1(double c, const CovParams& cp) {
 
 template <int ZI>
 struct EpiCov {  // GEMM-1 epilogue
-  const double* alpha;
-  const double* cutoff;
+  const double* w;  // w_s = alpha_s * sparseCutoff_s * delta^2 (0 for padding columns), precombined at model upload
   CovParams cp;
   double* acoef;
   int lda_out;
   double* epart;
   int n_tiles_n;
-  int M;  // real number of sparse points; columns >= M are padding
+  static constexpr int zi = ZI;
   __device__ __forceinline__ double pw(double c) const { return pow_zm1<ZI>(c, cp); }
 };
 struct EpiStore {  // GEMM-2 epilogue
@@ -123,9 +125,26 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
   const int KT_all = K / BK;
   const int kt_beg = (int)((long long)KT_all * blockIdx.z / gridDim.z), kt_end = (int)((long long)KT_all * (blockIdx.z + 1) / gridDim.z);
   const int KT = kt_end - kt_beg;
+  // per-thread copy addresses (see load_stage)
+  const int lrow = threadIdx.x / CPR, lcc = (threadIdx.x % CPR) * 2;
+  const double* gA = A + (size_t)(m0 + lrow) * lda + (size_t)kt_beg * BK + lcc;
+  const double* gB = B + (size_t)(n0 + lrow) * ldb + (size_t)kt_beg * BK + lcc;
+  const size_t lda16 = (size_t)ROWS_PER_PASS * lda, ldb16 = (size_t)ROWS_PER_PASS * ldb;
+  const unsigned sA0 = (unsigned)__cvta_generic_to_shared(As + lrow * LDS_ROW + lcc);
+  const unsigned sB0 = (unsigned)__cvta_generic_to_shared(Bs + lrow * LDS_ROW + lcc);
+  constexpr unsigned A_STAGE = BM * LDS_ROW * 8, B_STAGE = BN * LDS_ROW * 8;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
-    if (s < KT) load_stage<BN>(As + (size_t)s * BM * LDS_ROW, Bs + (size_t)s * BN * LDS_ROW, A, lda, B, ldb, m0, n0, (kt_beg + s) * BK);
+    if (s < KT) load_stage<BN>(sA0 + s * A_STAGE, sB0 + s * B_STAGE, gA + s * BK, gB + s * BK, lda16, ldb16);
+    cp_async_commit();
+  }
+  if constexpr (!std::is_same<Epi, EpiStore>::value) {
+    // the tile's GP weights ride along with the first slabs (read in the epilogue)
+    double* wsm = Bs + (size_t)STAGES * BN * LDS_ROW;
+    if (threadIdx.x < BN / 2) {
+      unsigned sw = (unsigned)__cvta_generic_to_shared(wsm + 2 * threadIdx.x);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sw), "l"(epi.w + n0 + 2 * threadIdx.x));
+    }
     cp_async_commit();
   }
   for (int kt = 0; kt < KT; kt++) {
@@ -135,7 +154,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
       int kn = kt + STAGES - 1;
       if (kn < KT) {
         int s = kn % STAGES;
-        load_stage<BN>(As + (size_t)s * BM * LDS_ROW, Bs + (size_t)s * BN * LDS_ROW, A, lda, B, ldb, m0, n0, (kt_beg + kn) * BK);
+        load_stage<BN>(sA0 + s * A_STAGE, sB0 + s * B_STAGE, gA + (size_t)kn * BK, gB + (size_t)kn * BK, lda16, ldb16);
       }
       cp_async_commit();
     }
@@ -160,16 +179,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
   // ---- epilogue: thread holds C[row = fr][col = 2*fk, 2*fk+1] of every 8x8 tile ----
   if constexpr (!std::is_same<Epi, EpiStore>::value) {
     const Epi& e = epi;
-    double* red = (double*)smem_raw;  // [WARPS_N][BM]
-    double al[NTL][2], cu[NTL][2];
+    double* red = (double*)smem_raw;  // [WARPS_N][BM] (the pipeline stages are drained)
+    const double* wsm = Bs + (size_t)STAGES * BN * LDS_ROW;
+    const double zeta = e.cp.zeta;
+    const bool zeta0 = e.cp.zeta_int == 0;
+    double wv[NTL][2];
 #pragma unroll
-    for (int j = 0; j < NTL; j++)
-#pragma unroll
-      for (int t = 0; t < 2; t++) {
-        int col = n0 + wn * WTN + j * 8 + 2 * fk + t;
-        al[j][t] = e.alpha[col];
-        cu[j][t] = e.cutoff[col];
-      }
+    for (int j = 0; j < NTL; j++) {
+      const double2 t = *reinterpret_cast<const double2*>(wsm + wn * WTN + j * 8 + 2 * fk);
+      wv[j][0] = t.x;
+      wv[j][1] = t.y;
+    }
+    __syncthreads();  // everyone has its weights: the stage area may now be reused for the row sums
 #pragma unroll
     for (int i = 0; i < MT; i++) {
       int row = m0 + wm * WTM + i * 8 + fr;
@@ -179,12 +200,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
         double outv[2];
 #pragma unroll
         for (int t = 0; t < 2; t++) {
-          double c = acc[i][j][t];
-          if (n0 + wn * WTN + j * 8 + 2 * fk + t >= e.M) { outv[t] = 0.0; continue; }
-          double pw = e.pw(c);
-          double kval = e.cp.zeta_int == 0 ? e.cp.delta2 : e.cp.delta2 * (pw * c);
-          esum += al[j][t] * (kval * cu[j][t]);
-          outv[t] = al[j][t] * e.cp.delta2 * e.cp.zeta * pw * cu[j][t];
+          const double c = acc[i][j][t];
+          // c^(zeta-1); a zero weight (padding column, c = 0 exactly) must not meet 0^(negative) in the general-zeta path
+          const double pw = (Epi::zi == 0 && wv[j][t] == 0.0) ? 0.0 : e.pw(c);
+          esum += wv[j][t] * (zeta0 ? 1.0 : pw * c);     // alpha_s * delta^2 c^zeta cutoff_s   (gp_predict.f95:3766-3768, 3854)
+          outv[t] = wv[j][t] * zeta * pw;                // alpha_s * d k_s / d c                (:3771-3772)
         }
         int col = n0 + wn * WTN + j * 8 + 2 * fk;
         *reinterpret_cast<double2*>(e.acoef + (size_t)row * e.lda_out + col) = make_double2(outv[0], outv[1]);
@@ -222,9 +242,9 @@ __global__ void k_energy_rows(const double* __restrict__ epart, int n_tiles_n, c
 
 }  // namespace
 
-void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int row0, const int* n_rows_dev, int M, int M_pad,
-                      int K_pad, const double* alpha, const double* cutoff, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n,
-                      cudaStream_t st, int* launches) {
+void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int row0, const int* n_rows_dev, int M_pad,
+                      int K_pad, const double* w, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n, cudaStream_t st,
+                      int* launches) {
   constexpr int BN = COV_BN1;
   dim3 grid(M_pad / BN, n_rows_pad / BM, 1);
   auto go = [&](auto e) {
@@ -233,11 +253,11 @@ void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, 
     k_dgemm_nt<BN, E><<<grid, NTHREADS, gemm_smem<BN>(), st>>>(x, ldx, sp_rows, lds, K_pad, row0, n_rows_dev, e);
   };
   switch (cp.zeta_int) {
-    case 1: go(EpiCov<1>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
-    case 2: go(EpiCov<2>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
-    case 3: go(EpiCov<3>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
-    case 4: go(EpiCov<4>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
-    default: go(EpiCov<0>{alpha, cutoff, cp, acoef, lda, epart, n_tiles_n, M}); break;
+    case 1: go(EpiCov<1>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+    case 2: go(EpiCov<2>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+    case 3: go(EpiCov<3>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+    case 4: go(EpiCov<4>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+    default: go(EpiCov<0>{w, cp, acoef, lda, epart, n_tiles_n}); break;
   }
   *launches += 1;
 }

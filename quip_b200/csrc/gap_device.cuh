@@ -123,9 +123,10 @@ constexpr int COV_BM = 64, COV_BN1 = 128, COV_BK = 16, COV_MAX_KSPLIT = 4;
 // GEMM-1 + epilogue: c = X S^T ; k = delta^2 c^zeta cutoff_s ; acoef = alpha_s delta^2 zeta c^(zeta-1) cutoff_s ;
 // epart[row][n_tile] = sum over the tile's columns of alpha_s k
 // n_rows_dev (may be NULL): device int, tiles whose first row is >= *n_rows_dev are skipped
-void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int row0, const int* n_rows_dev, int M, int M_pad,
-                      int K_pad, const double* alpha, const double* cutoff, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n,
-                      cudaStream_t st, int* launches);
+// w[M_pad] = alpha_s * sparseCutoff_s * delta^2 (0 in the padding)
+void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int row0, const int* n_rows_dev, int M_pad,
+                      int K_pad, const double* w, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n, cudaStream_t st,
+                      int* launches);
 // GEMM-2: gvec[split] = acoef[:, K range of split] S   (S given transposed: st_rows[q][s]); column tile bn (112 or 128),
 // ksplit partial outputs split_stride doubles apart
 int cov_gemm2_bn(int d);

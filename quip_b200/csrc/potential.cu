@@ -437,7 +437,7 @@ void upload_model(gap_potential* P) {
           rows[(size_t)m * cd.d_pad + q] = v;
           trn[(size_t)q * cd.M_pad + m] = v;
         }
-        al[m] = c.alpha[m];
+        al[m] = c.alpha[m] * c.sparseCutoff[m] * (c.delta * c.delta);  // GP weight of the fused epilogue (0 in the padding)
         cu[m] = c.sparseCutoff[m];
       }
       CUDA_OK(cudaMalloc(&cd.sp_rows, rows.size() * sizeof(double)));
@@ -566,9 +566,8 @@ void covariance_stage(gap_potential* P, const CoordDev& cd, int nc, const int* r
   if (want_grad) P->b_gvec.ensure(sizeof(double) * (size_t)nc_pad * cd.dn_pad * ksplit);
   for (int r0 = 0; r0 < nc_pad; r0 += chunk) {
     int rows = std::min(chunk, nc_pad - r0);
-    launch_cov_gemm1(P->b_x.as<double>() + (size_t)r0 * cd.d_pad, cd.d_pad, cd.sp_rows, cd.d_pad, rows, r0, rows_dev, cd.M, cd.M_pad, cd.d_pad,
-                     cd.alpha, cd.scut, cd.cp, P->b_acoef.as<double>(), cd.M_pad, P->b_epart.as<double>() + (size_t)r0 * n_tiles_n, n_tiles_n, st,
-                     &launches);
+    launch_cov_gemm1(P->b_x.as<double>() + (size_t)r0 * cd.d_pad, cd.d_pad, cd.sp_rows, cd.d_pad, rows, r0, rows_dev, cd.M_pad, cd.d_pad,
+                     cd.alpha, cd.cp, P->b_acoef.as<double>(), cd.M_pad, P->b_epart.as<double>() + (size_t)r0 * n_tiles_n, n_tiles_n, st, &launches);
     mark(P, st, ST_COV_GEMM1);
     if (want_grad) {
       launch_cov_gemm2(P->b_acoef.as<double>(), cd.M_pad, cd.st_rows, cd.M_pad, rows, r0, rows_dev, cd.dn_pad, cd.bn2, ksplit, cd.M_pad,
