@@ -93,13 +93,16 @@ __device__ __forceinline__ void cutoff_fn(const SoapDev* sp, double r, double& f
 // geometry of the shared-memory tables (identical on host and device)
 // ------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline int ceil4(int v) { return (v + 3) & ~3; }
+// Harmonic items per neighbour: the orders m are paired as (m, L+1-m) so that every item runs about L+2 recursion steps
+// (order m alone costs L-m+1): item 0 -> m = 0, item k >= 1 -> m = k and, if different and larger, m = L+1-k.
+__host__ __device__ inline int m_pairs(int L) { return L / 2 + 1 + (L & 1); }
 __host__ __device__ inline int ceil8(int v) { return (v + 7) & ~7; }
 __host__ __device__ inline int stride4mod16(int v) {  // smallest s >= v with s = 4 (mod 16)
   int s = (v & ~15) + 4;
   return s >= v ? s : s + 16;
 }
 struct Geo {
-  int n, L, L1, nlm, ns, K1, K18, n2, n8, RFS, YS, XS, XR, TS, NTM, NTN;
+  int n, L, L1, nlm, ns, K1, K18, n2, n8, RFS, YS, YSA, XS, XR, TS, NTM, NTN, MP;
 };
 __host__ __device__ __forceinline__ Geo make_geo(int n_max, int l_max, int n_species) {
   Geo g;
@@ -108,7 +111,10 @@ __host__ __device__ __forceinline__ Geo make_geo(int n_max, int l_max, int n_spe
   g.n2 = (g.n + 1) & ~1;
   g.n8 = ceil8(g.n);
   g.RFS = stride4mod16(g.L1 * g.n2);   // per-neighbour radial table [l][a]
-  g.YS = stride4mod16(g.nlm + 7);      // per-neighbour harmonics row (tile reads run up to 7 rows past nlm)
+  g.YS = stride4mod16(g.nlm + 7);      // forward: per-neighbour harmonics row = DMMA A operand (tile reads run up to 7 rows past nlm)
+  g.YSA = g.nlm;                       // adjoint: harmonics are read element-wise as [q = 2 fk + j][lm = lm0 + fr]: = 2 (mod 8) is
+  while ((g.YSA & 7) != 2) g.YSA++;    //          conflict free for that pattern
+  g.MP = m_pairs(g.L);
   g.XS = g.K18 + 4;                    // X / Lambda row stride: = 4 or 12 (mod 16)
   g.XR = g.nlm + 8;                    // rows allocated
   g.TS = stride4mod16(g.n8);           // padded transform_basis row stride
@@ -155,8 +161,9 @@ __host__ __device__ __forceinline__ size_t carve(const Geo& g, int d_pad, bool a
   size_t oT = take((size_t)g.n8 * g.TS), orb = take(g.n), oyn = take((size_t)g.L1 * (g.L1 + 1) / 2), oX = take((size_t)g.XR * g.XS),
          onbd = take(NBCAP * 3), onbr = take(NBCAP), onbf = take(NBCAP), onbdf = take(NBCAP), ored = take(64);
   size_t ostage = o;
-  size_t orf = take((size_t)TN * g.RFS), odrf = adjoint ? take((size_t)TN * g.RFS) : 0, oY = take((size_t)TN * g.YS),
-         oG = adjoint ? take((size_t)3 * TN * g.YS) : 0, opart = adjoint ? take((size_t)NW * TNA * 4) : 0;
+  const int ys = adjoint ? g.YSA : g.YS;
+  size_t orf = take((size_t)TN * g.RFS), odrf = adjoint ? take((size_t)TN * g.RFS) : 0, oY = take((size_t)TN * ys),
+         oG = adjoint ? take((size_t)3 * TN * ys) : 0, opart = adjoint ? take((size_t)NW * TNA * 4) : 0;
   size_t stage_bytes = o - ostage;
   size_t op;
   if (adjoint) {
@@ -303,8 +310,8 @@ __device__ __forceinline__ void cs_power(double ux, double uy, int m, double& Cm
 // GRAD: also the gradient of the polynomial extension N_lm Q_l^m(z) {C_m,S_m}(x,y) (three tables, stride gstride); the
 // consumer projects it: grad Y = (g - u (u.g)) / r  (GradSphericalYCartesian_all, angular_functions.f95:205-278).
 template <bool GRAD>
-__device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L, int m, double ux, double uy, double uz, double* Yq, double* Gq,
-                                         int gstride) {
+__device__ __forceinline__ void ylm_order(const double* __restrict__ ynorm, int L, int m, double ux, double uy, double uz, double* Yq, double* Gq,
+                                          int gstride) {
   double Cm, Sm, Cm1, Sm1;
   cs_power(ux, uy, m, Cm, Sm, Cm1, Sm1);
   const double dm = (double)m;
@@ -340,6 +347,14 @@ __device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L
   }
 }
 
+template <bool GRAD>
+__device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L, int item, double ux, double uy, double uz, double* Yq, double* Gq,
+                                         int gstride) {
+  ylm_order<GRAD>(ynorm, L, item, ux, uy, uz, Yq, Gq, gstride);
+  const int m2 = L + 1 - item;
+  if (item > 0 && m2 > item) ylm_order<GRAD>(ynorm, L, m2, ux, uy, uz, Yq, Gq, gstride);
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward: x (normalised power spectrum), X_lm (kept for the adjoint), |p|
 // ------------------------------------------------------------------------------------------------
@@ -373,7 +388,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
     for (int t0 = 0; t0 < nv; t0 += TNF) {
       const int tn = min(TNF, nv - t0), tn4 = ceil4(tn);
       // ---- stage: radial items (q, a) and harmonic items (q, m); rows q in [tn, tn4) are zero (K padding) ----
-      const int n_rad = tn * n, n_items = n_rad + tn * L1;
+      const int n_rad = tn * n, n_items = n_rad + tn * g.MP;
       for (int it = threadIdx.x; it < n_items; it += NT) {
         if (it < n_rad) {
           int q = it / n, a = it - q * n;
@@ -624,14 +639,14 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
   __syncthreads();
 
   double fi[3] = {0, 0, 0}, vir[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const int gstride = TNA * g.YS;
+  const int gstride = TNA * g.YSA;
   const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
   for (int pb = pbeg; pb < pend; pb += NBCAP) {
     int nv = gather_neighbours(sp, s, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
     for (int t0 = 0; t0 < nv; t0 += TNA) {
       const int tn = min(TNA, nv - t0);
       // ---- stage: radial tables with derivative, harmonics with polynomial gradients; columns q in [tn, 8) zero ----
-      const int n_rad = tn * n, n_items = n_rad + tn * L1;
+      const int n_rad = tn * n, n_items = n_rad + tn * g.MP;
       for (int it = threadIdx.x; it < n_items; it += NT) {
         if (it < n_rad) {
           int q = it / n, a = it - q * n;
@@ -642,15 +657,15 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
           int m = r2 / tn, q = r2 - m * tn;
           double rinv = 1.0 / s.nbr[t0 + q];
           ylm_item<true>(s.ynorm, L, m, s.nbd[3 * (t0 + q)] * rinv, s.nbd[3 * (t0 + q) + 1] * rinv, s.nbd[3 * (t0 + q) + 2] * rinv,
-                         s.Y + q * g.YS, s.G + q * g.YS, gstride);
+                         s.Y + q * g.YSA, s.G + q * g.YSA, gstride);
         }
       }
-      for (int it = threadIdx.x; it < (TNA - tn) * g.YS; it += NT) {  // harmonics of the padding neighbours: zero (their A, B are zero too)
-        int q = tn + it / g.YS, k = it % g.YS;
-        s.Y[q * g.YS + k] = 0.0;
-        s.G[q * g.YS + k] = 0.0;
-        s.G[gstride + q * g.YS + k] = 0.0;
-        s.G[2 * gstride + q * g.YS + k] = 0.0;
+      for (int it = threadIdx.x; it < (TNA - tn) * g.YSA; it += NT) {  // harmonics of the padding neighbours: zero (their A, B are zero too)
+        int q = tn + it / g.YSA, k = it % g.YSA;
+        s.Y[q * g.YSA + k] = 0.0;
+        s.G[q * g.YSA + k] = 0.0;
+        s.G[gstride + q * g.YSA + k] = 0.0;
+        s.G[2 * gstride + q * g.YSA + k] = 0.0;
       }
       __syncthreads();
       // ---- contraction on the tensor cores: A_lm(q) = sum_c Lambda~[lm][c] R[q][l][a(c)], B_lm(q) likewise with Phi;
@@ -675,7 +690,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
         if (lm < (l + 1) * (l + 1)) {
 #pragma unroll
           for (int j = 0; j < 2; j++) {
-            const int yo = (2 * fk + j) * g.YS + lm;
+            const int yo = (2 * fk + j) * g.YSA + lm;
             const double av = j ? a1 : a0, bv = j ? b1 : b0;
             SA[j] += av * s.Y[yo];
             G0[j] += bv * s.G[yo];

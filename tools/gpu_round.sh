@@ -16,6 +16,6 @@ cat $OUT/bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1
 # full capture of the path's kernels in one timed step (after bootstrap + 3 warm-up steps)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_soap|k_dgemm|k_neigh' -s 21 -c 6 -f -o $OUT/prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_soap|k_dgemm|k_neigh" -s 21 -c 6 -f -o $OUT/prof \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 ls -la $OUT
