@@ -72,6 +72,16 @@ int gap_potential_calc_device(gap_potential* pot, int N, const double* d_pos, co
                               const int* pbc, const char* args_str, int want_grad, double* d_packed, double* d_local_e,
                               double* d_local_virial, void* stream);
 
+/* DynamicalSystem_run (src/Potentials/Potential.f95:2304-2369) for plain NVE dynamics: n_steps of velocity Verlet
+ * (advance_verlet1 / advance_verlet2, src/libAtoms/DynamicalSystem.f95:1814, 2159; no thermostat, barostat or constraints),
+ * forces from this potential, the neighbour list rebuilt on the device every step.  Positions, velocities and
+ * accelerations stay resident on the GPU for the whole run; only the step energies come back.
+ *   pos, velo : host double[3*N], in = initial state, out = final state (Angstrom, Angstrom/fs)
+ *   mass      : host double[N] in QUIP units (amu * MASSCONVERT, src/libAtoms/Units.f95:68)
+ *   epot,ekin : host double[n_steps+1] or NULL: potential / kinetic energy after the initial evaluation and each step */
+int gap_md_run(gap_potential* pot, int N, double* pos, double* velo, const int* Z, const double* mass, const double* lattice, const int* pbc,
+               double dt, int n_steps, const char* args_str, double* epot, double* ekin);
+
 /* F77-style one-shot entry point, same argument list as quip_wrapper_simple_
  * (src/Potentials/quip_unified_wrapper.f95:311-332) plus the XML file name; pbc = T T T. */
 int gap_b200_wrapper_simple(const char* param_filename, const int* N, const double* lattice, const int* Z, const double* pos,

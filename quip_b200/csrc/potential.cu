@@ -104,6 +104,7 @@ struct gap_potential {
   // inputs / outputs owned for the host-pointer API
   DevBuf b_pos, b_Z, b_packed, b_le, b_lv;
   // per-coordinate workspaces
+  DevBuf b_velo, b_velo2, b_acc, b_mass, b_ke;  // MD driver state
   DevBuf b_flags, b_scan, b_centres, b_x, b_xlm, b_pnorm, b_acoef, b_gvec, b_epart, b_vir, b_fin;
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_stage;
@@ -159,6 +160,36 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict_
     if (threadIdx.x == 0) *counter = 0u;
   }
 }
+// ---------------------------------------------------------------------------------------------------
+// velocity Verlet (advance_verlet1 / advance_verlet2, src/libAtoms/DynamicalSystem.f95:1814-2132, 2159-2383; plain atoms,
+// no thermostat / barostat / constraints):  v += a dt/2 ; x += v dt   |   a = f/m ; v += a dt/2
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_verlet1(int N, double dt, double* __restrict__ pos, double* __restrict__ velo, const double* __restrict__ acc) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= 3 * N) return;
+  double v = velo[k] + 0.5 * acc[k] * dt;
+  velo[k] = v;
+  pos[k] = pos[k] + v * dt;
+}
+__global__ void k_verlet2(int N, double dt, const double* __restrict__ force, const double* __restrict__ mass, const double* __restrict__ velo_in,
+                          double* __restrict__ velo_out, double* __restrict__ acc, int half_kick) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= 3 * N) return;
+  double a = force[k] / mass[k / 3];
+  acc[k] = a;
+  velo_out[k] = half_kick ? velo_in[k] + 0.5 * a * dt : velo_in[k];
+}
+// kinetic energy partials: sum_i m_i |v_i|^2 / 2 (kinetic_energy, DynamicalSystem.f95:1351)
+__global__ void __launch_bounds__(256) k_kinetic(int N, const double* __restrict__ mass, const double* __restrict__ velo, double* __restrict__ part) {
+  typedef cub::BlockReduce<double, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  double t = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < N; i += gridDim.x * 256)
+    t += 0.5 * mass[i] * (velo[3 * i] * velo[3 * i] + velo[3 * i + 1] * velo[3 * i + 1] + velo[3 * i + 2] * velo[3 * i + 2]);
+  t = BR(tmp).Sum(t);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
 __global__ void k_iota(int* p, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = i;
@@ -712,7 +743,7 @@ void gap_potential_finalise(gap_potential* P) {
   DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_ccount, &P->b_cstart, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
-                    &P->b_vir, &P->b_fin};
+                    &P->b_vir, &P->b_fin, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : P->ev) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);
@@ -802,6 +833,71 @@ int gap_potential_calc(gap_potential* P, int N, const double* pos, const int* Z,
     if (virial)
       for (int k = 0; k < 9; k++) virial[k] = head[1 + k];
     collect_timings(P);
+  });
+}
+
+int gap_md_run(gap_potential* P, int N, double* pos, double* velo, const int* Z, const double* mass, const double* lattice, const int* pbc,
+               double dt, int n_steps, const char* args_str, double* epot, double* ekin) {
+  return guard([&] {
+    if (!P) throw GapError("gap_md_run: pot is NULL");
+    if (N <= 0 || !pos || !velo || !Z || !mass) throw GapError("gap_md_run: N, pos, velo, Z and mass are required");
+    if (n_steps < 0) throw GapError("gap_md_run: n_steps < 0");
+    if (P->n_ranks != 1) throw GapError("gap_md_run: the MD driver runs on one GPU (use calc_device + your own integrator for sharded runs)");
+    CUDA_OK(cudaSetDevice(P->device));
+    cudaStream_t st = P->stream;
+    const size_t n3 = 3 * (size_t)N;
+    P->b_pos.ensure(sizeof(double) * (n3 + 3));
+    P->b_Z.ensure(sizeof(int) * (size_t)(N + 1));
+    P->b_velo.ensure(sizeof(double) * n3);
+    P->b_velo2.ensure(sizeof(double) * n3);
+    P->b_acc.ensure(sizeof(double) * n3);
+    P->b_mass.ensure(sizeof(double) * (size_t)N);
+    P->b_ke.ensure(sizeof(double) * 128);
+    P->b_packed.ensure(sizeof(double) * (10 + n3));
+    P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
+    CUDA_OK(cudaMemcpyAsync(P->b_pos.p, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->b_velo.p, velo, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->b_Z.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->b_mass.p, mass, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+    const int nb = (int)((n3 + 255) / 256);
+    double ke_part[128];
+    auto evaluate = [&](int step) {  // calc(pot, atoms, "energy force") with the per-step neighbour-list rebuild (Potential.f95:2340-2365)
+      for (int attempt = 0; attempt < 2; attempt++) {
+        calc_device_impl(P, N, P->b_pos.as<double>(), P->b_Z.as<int>(), lattice, pbc, args_str, true, P->b_packed.as<double>(), P->b_le.as<double>(),
+                         nullptr, st);
+        // the new velocities go to a second buffer: if the speculatively sized neighbour list overflowed, the evaluation is simply repeated
+        k_verlet2<<<nb, 256, 0, st>>>(N, dt, P->b_packed.as<double>() + 10, P->b_mass.as<double>(), P->b_velo.as<double>(), P->b_velo2.as<double>(),
+                                      P->b_acc.as<double>(), step > 0 ? 1 : 0);
+        P->launches += 1;
+        if (ekin) {
+          k_kinetic<<<128, 256, 0, st>>>(N, P->b_mass.as<double>(), P->b_velo2.as<double>(), P->b_ke.as<double>());
+          P->launches += 1;
+          CUDA_OK(cudaMemcpyAsync(ke_part, P->b_ke.p, sizeof(ke_part), cudaMemcpyDeviceToHost, st));
+        }
+        double e = 0.0;
+        CUDA_OK(cudaMemcpyAsync(&e, P->b_packed.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        if (!verify_connect(P)) continue;  // repeat with the exact list size
+        std::swap(P->b_velo, P->b_velo2);
+        if (epot) epot[step] = e;
+        if (ekin) {
+          double t = 0.0;
+          for (int k = 0; k < 128; k++) t += ke_part[k];
+          ekin[step] = t;
+        }
+        break;
+      }
+    };
+    evaluate(0);  // initial forces -> accelerations (Potential.f95:2348-2351)
+    for (int n = 1; n <= n_steps; n++) {
+      k_verlet1<<<nb, 256, 0, st>>>(N, dt, P->b_pos.as<double>(), P->b_velo.as<double>(), P->b_acc.as<double>());
+      P->launches += 1;
+      evaluate(n);
+    }
+    CUDA_OK(cudaMemcpyAsync(pos, P->b_pos.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(velo, P->b_velo.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaGetLastError());
   });
 }
 

@@ -35,6 +35,7 @@ ABI = {
     "gap_potential_calc": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "gap_potential_calc_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_dp, c_ip, C.c_char_p, C.c_int,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gap_md_run": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_ip, C.c_double, C.c_int, C.c_char_p, c_dp, c_dp]),
     "gap_b200_wrapper_simple": (C.c_int, [C.c_char_p, c_ip, c_dp, c_ip, c_dp, c_dp, c_dp, c_dp]),
     "gap_calc_connect": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip, C.c_double, c_ip]),
     "gap_get_connect": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_dp]),
@@ -86,6 +87,23 @@ def model_describe(param_str=None, param_filename=None, args_str="", base_dir=".
     buf = C.create_string_buffer(1 << 20)
     _check(load_library().gap_model_describe(args_str.encode(), param_str.encode(), base_dir.encode(), buf, len(buf)))
     return buf.value.decode()
+
+
+# src/libAtoms/Units.f95:56-68 (the constants of the default unit system) and PeriodicTable.f95:90 (IUPAC 2013 masses)
+_ELECTRONMASS_GPERMOL, _HARTREE, _BOHR, _HBAR_EVSEC = 5.48579903e-4, 27.2113961, 0.529177249, 6.5821220e-16
+_AU_FS = 1.0 / (1.0 / (_HBAR_EVSEC / _HARTREE)) * 1e15
+MASSCONVERT = 1.0 / _ELECTRONMASS_GPERMOL * _HARTREE * _AU_FS * _AU_FS / (_BOHR * _BOHR)
+_AMU = {1: 1.008, 2: 4.002602, 3: 6.94, 4: 9.0121831, 5: 10.81, 6: 12.011, 7: 14.007, 8: 15.999, 9: 18.998403163, 10: 20.1797, 11: 22.98976928,
+        12: 24.305, 13: 26.9815385, 14: 28.085, 15: 30.973761998, 16: 32.06, 17: 35.45, 18: 39.948, 22: 47.867, 23: 50.9415, 26: 55.845,
+        28: 58.6934, 29: 63.546, 32: 72.63, 41: 92.90637, 42: 95.95, 73: 180.94788, 74: 183.84}
+
+
+def element_masses(Z):
+    """``ElementMass(Z)`` in QUIP's internal units (amu * MASSCONVERT)."""
+    try:
+        return np.array([_AMU[int(z)] for z in Z]) * MASSCONVERT
+    except KeyError as e:
+        raise RuntimeError("element_masses: no mass tabulated for Z=%s; pass masses= explicitly" % e)
 
 
 def key_val_dict_to_str(d):
@@ -246,6 +264,20 @@ class Potential:
         g = np.zeros((n, d)) if grad else None
         _check(load_library().gap_gp_predict(self._h, i_coord, n, _dp(x), _dp(e), _dp(g)))
         return e, g
+
+    def run(self, atoms, velocities, dt=1.0, n_steps=10, masses=None, args_str=""):
+        """``DynamicalSystem_run(ds, pot, dt, n_steps)`` (Potential.f95:2304): NVE velocity Verlet, everything resident on the GPU,
+        neighbour list rebuilt every step.  Updates ``atoms.positions`` in place; returns (velocities, epot[n_steps+1], ekin[n_steps+1])."""
+        pos, Z, lat, pbc = _geometry(atoms)
+        N = len(Z)
+        pos = pos.copy()
+        vel = np.ascontiguousarray(velocities, dtype=np.float64).copy()
+        m = np.ascontiguousarray(element_masses(Z) if masses is None else masses, dtype=np.float64)
+        ep, ek = np.zeros(n_steps + 1), np.zeros(n_steps + 1)
+        _check(load_library().gap_md_run(self._h, N, _dp(pos), _dp(vel), _ip(Z), _dp(m), _dp(lat), _ip(pbc), float(dt), int(n_steps),
+                                         (self.calc_args + " " + args_str).strip().encode(), _dp(ep), _dp(ek)))
+        atoms.positions[...] = pos
+        return vel, ep, ek
 
     def calc_device(self, N, d_pos_ptr, d_Z_ptr, lattice9, pbc3, d_packed_ptr, want_grad=True, d_local_e_ptr=None,
                     d_local_virial_ptr=None, stream_ptr=None, args_str=""):
