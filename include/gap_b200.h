@@ -82,6 +82,17 @@ int gap_potential_calc_device(gap_potential* pot, int N, const double* d_pos, co
 int gap_md_run(gap_potential* pot, int N, double* pos, double* velo, const int* Z, const double* mass, const double* lattice, const int* pbc,
                double dt, int n_steps, const char* args_str, double* epot, double* ekin);
 
+/* ---- LAMMPS `pair_style quip` ABI: the three bind(c) symbols of src/Potentials/quip_lammps_wrapper.f95 (:24, :30-56,
+ * :158-168) with identical names and argument lists (all by reference), so that LAMMPS' pair_quip.cpp links against
+ * libgapb200.so instead of libquip.  The neighbour list is the caller's (full list of the local atoms, 1-based neighbour
+ * indices, periodic images as explicit ghost atoms); only the local atoms are centres; forces on ghosts are returned. */
+int quip_lammps_api_version(void);
+void quip_lammps_potential_initialise(int* quip_potential, int* n_quip_potential, double* quip_cutoff, char* quip_file, int* n_quip_file,
+                                      char* quip_string, int* n_quip_string);
+void quip_lammps_wrapper(int* nlocal, int* nghost, int* atomic_numbers, int* lmptag, int* inum, int* sum_num_neigh, int* ilist, int* quip_num_neigh,
+                         int* quip_neigh, double* lattice, int* quip_potential, int* n_quip_potential, double* quip_x, double* quip_e,
+                         double* quip_local_e, double* quip_virial, double* quip_local_virial, double* quip_force);
+
 /* F77-style one-shot entry point, same argument list as quip_wrapper_simple_
  * (src/Potentials/quip_unified_wrapper.f95:311-332) plus the XML file name; pbc = T T T. */
 int gap_b200_wrapper_simple(const char* param_filename, const int* N, const double* lattice, const int* Z, const double* pos,

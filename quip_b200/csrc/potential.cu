@@ -93,6 +93,9 @@ struct gap_potential {
   bool pending_check = false;
   long pending_cap = 0;
   unsigned int* d_fin_counter = nullptr;
+  // neighbour list the descriptor kernels read: the handle's own (build_connect) or one supplied by the caller (LAMMPS entry)
+  const int *cv_off = nullptr, *cv_j = nullptr, *cv_s = nullptr;
+  DevBuf b_xoff, b_xj, b_xs, b_zc;  // device copies of an external list and of the centre mask
   long launches = 0;
   double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -574,8 +577,8 @@ void soap_forward_stage(gap_potential* P, const CoordDev& cd, int n_ub, const do
   P->b_x.ensure(sizeof(double) * (size_t)nc_pad * cd.d_pad);
   P->b_xlm.ensure(sizeof(double) * (size_t)(n_ub > 0 ? n_ub : 1) * cd.h.nlm * cd.h.K1);
   P->b_pnorm.ensure(sizeof(double) * (size_t)nc_pad);
-  launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos,
-                      d_Z, lat, P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
+  launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_j, P->cv_s, d_pos, d_Z, lat,
+                      P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
   P->launches += launches;
 }
 
@@ -609,15 +612,34 @@ void covariance_stage(gap_potential* P, const CoordDev& cd, int nc, const int* r
   P->launches += launches;
 }
 
+// An externally supplied neighbour list (quip_lammps_wrapper): CSR over all N = nlocal + nghost atoms with zero shifts
+// (periodic images are explicit ghost atoms), and d_Zc = Z for the atoms that are centres, -1 for the others
+// (the reference's atom_mask_name=local, quip_lammps_wrapper.f95:97-147).
+struct ExtList {
+  const int *off, *j, *s, *Zc;
+  int nlocal;
+};
+
 void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d_Z, const double* lattice, const int* pbc,
-                      const char* args_str, bool want_grad, double* d_packed, double* d_le_user, double* d_lv, cudaStream_t st) {
+                      const char* args_str, bool want_grad, double* d_packed, double* d_le_user, double* d_lv, cudaStream_t st,
+                      const ExtList* ext = nullptr) {
   CUDA_OK(cudaSetDevice(P->device));
   CalcArgs ca = parse_calc_args(P, args_str);
   if (!lattice || !pbc) throw GapError("gap_potential_calc: lattice and pbc are required");
-  const int first = (int)((long long)P->rank * N / P->n_ranks), last = (int)((long long)(P->rank + 1) * N / P->n_ranks);
+  int first = (int)((long long)P->rank * N / P->n_ranks), last = (int)((long long)(P->rank + 1) * N / P->n_ranks);
+  const int* d_Zc = d_Z;  // atomic numbers as seen by the centre selection and the e0 sum
   P->ev_used = 0;
   mark(P, st, -1);
-  build_connect(P, N, first, last, d_pos, lattice, pbc, P->model.cutoff, false, true, st);
+  if (ext) {
+    first = 0;
+    last = ext->nlocal;
+    d_Zc = ext->Zc;
+    P->cv_off = ext->off; P->cv_j = ext->j; P->cv_s = ext->s;
+    P->pending_check = false;
+  } else {
+    build_connect(P, N, first, last, d_pos, lattice, pbc, P->model.cutoff, false, true, st);
+    P->cv_off = P->b_off.as<int>(); P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
+  }
   mark(P, st, ST_CONNECT);
   Lattice9 lat;
   for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
@@ -644,7 +666,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
     const CoordDev& cd = P->cd[ic];
     int launches = 0;
     if (cd.kind == DESC_SOAP) {
-      int nc = select_centres(P, cd, d_Z, first, last, st);  // upper bound; the count itself stays on the device
+      int nc = select_centres(P, cd, d_Zc, first, last, st);  // upper bound; the count itself stays on the device
       mark(P, st, ST_OTHER);
       if (nc > 0) {
         const int* ncd = nc_dev(P, nc);
@@ -652,7 +674,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
         mark(P, st, ST_SOAP_FWD);
         covariance_stage(P, cd, nc, ncd, want_grad, true, st);
         if (want_grad) {
-          launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), ncd, nc, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos, d_Z, lat,
+          launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_j, P->cv_s, d_pos, d_Z, lat,
                               P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, P->g_splits,
                               P->g_split_stride, P->b_epart.as<double>(), cd.M_pad / COV_BN1, d_le, es, d_force,
                               P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches);
@@ -665,7 +687,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
       }
     } else {
       int nb = 0;
-      launch_pair2b(cd.p2, first, last, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), d_pos, d_Z, lat, es, want_grad ? 1 : 0, d_le,
+      launch_pair2b(cd.p2, first, last, P->cv_off, P->cv_j, P->cv_s, d_pos, d_Z, lat, es, want_grad ? 1 : 0, d_le,
                     want_grad ? d_force : nullptr, want_grad ? P->b_vir.as<double>() + 9 * slot : nullptr, want_grad ? d_lv : nullptr, st, &launches,
                     &nb);
       if (want_grad) slot += nb;
@@ -675,7 +697,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   }
   // totals
   P->b_fin.ensure(sizeof(double) * 10 * FIN_BLOCKS);
-  k_finalize<<<FIN_BLOCKS, FIN_THREADS, 0, st>>>(d_Z, N, first, last, P->d_e0, es, d_le, want_grad ? P->b_vir.as<double>() : nullptr,
+  k_finalize<<<FIN_BLOCKS, FIN_THREADS, 0, st>>>(d_Zc, N, first, last, P->d_e0, es, d_le, want_grad ? P->b_vir.as<double>() : nullptr,
                                                 want_grad ? (int)slot : 0, P->b_fin.as<double>(), P->d_fin_counter, d_packed);
   P->launches += 1;
   mark(P, st, ST_OTHER);
@@ -743,7 +765,7 @@ void gap_potential_finalise(gap_potential* P) {
   DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_ccount, &P->b_cstart, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
-                    &P->b_vir, &P->b_fin, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke};
+                    &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : P->ev) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);
@@ -901,6 +923,118 @@ int gap_md_run(gap_potential* P, int N, double* pos, double* velo, const int* Z,
   });
 }
 
+// -----------------------------------------------------------------------------------------------------
+// LAMMPS `pair_style quip` ABI (src/Potentials/quip_lammps_wrapper.f95:24-197): same symbols, same argument lists
+// (everything by reference, as Fortran bind(c) passes it), so pair_quip.cpp links against libgapb200.so unchanged.
+// -----------------------------------------------------------------------------------------------------
+int quip_lammps_api_version(void) { return 1; }  // quip_lammps_wrapper.f95:24-28
+
+static gap_potential* g_lammps_pot = nullptr;  // the reference keeps ONE saved Potential as well (:171)
+
+void quip_lammps_potential_initialise(int* quip_potential, int* n_quip_potential, double* quip_cutoff, char* quip_file, int* n_quip_file,
+                                      char* quip_string, int* n_quip_string) {
+  // two-call protocol (:176-192): first call (n == 0) builds the potential and returns the handle size in ints, the second
+  // call stores the handle in the caller's integer array
+  static_assert(sizeof(gap_potential*) <= 2 * sizeof(int), "handle does not fit two ints");
+  if (*n_quip_potential == 0) {
+    std::string file(quip_file, (size_t)*n_quip_file), args(quip_string, (size_t)*n_quip_string);
+    if (g_lammps_pot) gap_potential_finalise(g_lammps_pot);
+    g_lammps_pot = nullptr;
+    if (gap_potential_filename_initialise(&g_lammps_pot, args.c_str(), file.c_str(), 0) != 0) {
+      fprintf(stderr, "SYSTEM ABORT: quip_lammps_potential_initialise: %s\n", gap_last_error());  // the reference system_aborts here
+      abort();
+    }
+    *n_quip_potential = 2;
+  } else {
+    memcpy(quip_potential, &g_lammps_pot, sizeof(gap_potential*));
+  }
+  *quip_cutoff = g_lammps_pot ? gap_potential_cutoff(g_lammps_pot) : 0.0;
+}
+
+void quip_lammps_wrapper(int* nlocal, int* nghost, int* atomic_numbers, int* lmptag, int* inum, int* sum_num_neigh, int* ilist, int* quip_num_neigh,
+                         int* quip_neigh, double* lattice, int* quip_potential, int* n_quip_potential, double* quip_x, double* quip_e,
+                         double* quip_local_e, double* quip_virial, double* quip_local_virial, double* quip_force) {
+  (void)lmptag;
+  const int N = *nlocal + *nghost;
+  int rc = guard([&] {
+    if (*n_quip_potential == 0) throw GapError("quip_lammps_wrapper: quip_potential not initialised");  // :70-72
+    gap_potential* P = nullptr;
+    memcpy(&P, quip_potential, sizeof(gap_potential*));
+    if (!P) throw GapError("quip_lammps_wrapper: quip_potential not initialised");
+    *quip_e = 0.0;
+    for (int k = 0; k < 9; k++) quip_virial[k] = 0.0;
+    std::fill(quip_local_e, quip_local_e + N, 0.0);
+    std::fill(quip_local_virial, quip_local_virial + 9 * (size_t)N, 0.0);
+    std::fill(quip_force, quip_force + 3 * (size_t)N, 0.0);
+    if (*nlocal <= 0) return;  // vacuum region: nothing to do (:78, :148-154)
+    CUDA_OK(cudaSetDevice(P->device));
+    cudaStream_t st = P->stream;
+    // LAMMPS' full list -> CSR over all atoms (rows of ghosts and of unlisted atoms stay empty); neighbour indices arrive
+    // 1-based (:107-109), shifts are zero because periodic images are explicit ghosts (:112-116)
+    std::vector<int> off((size_t)N + 1, 0), zc((size_t)N, -1);
+    for (int ni = 0; ni < *inum; ni++) {
+      int i = ilist[ni];
+      if (i < 0 || i >= *nlocal) throw GapError("quip_lammps_wrapper: ilist entry outside the local atoms");
+      off[(size_t)i + 1] = quip_num_neigh[ni];
+      zc[i] = atomic_numbers[i];
+    }
+    for (int i = 0; i < N; i++) off[(size_t)i + 1] += off[i];
+    if (off[N] != *sum_num_neigh) throw GapError("quip_lammps_wrapper: sum_num_neigh does not match the neighbour counts");
+    std::vector<int> nj((size_t)std::max(*sum_num_neigh, 1));
+    {
+      size_t nn = 0;
+      for (int ni = 0; ni < *inum; ni++) {
+        int i = ilist[ni], w = off[i];
+        for (int n = 0; n < quip_num_neigh[ni]; n++, nn++) {
+          int j = quip_neigh[nn] - 1;
+          if (j < 0 || j >= N) throw GapError("quip_lammps_wrapper: neighbour index out of range");
+          nj[(size_t)w + n] = j;
+        }
+      }
+    }
+    const size_t nnz = (size_t)*sum_num_neigh;
+    P->b_pos.ensure(sizeof(double) * 3 * (size_t)(N + 1));
+    P->b_Z.ensure(sizeof(int) * (size_t)(N + 1));
+    P->b_zc.ensure(sizeof(int) * (size_t)(N + 1));
+    P->b_xoff.ensure(sizeof(int) * (size_t)(N + 2));
+    P->b_xj.ensure(sizeof(int) * (nnz + 1));
+    P->b_xs.ensure(sizeof(int) * (nnz + 1));
+    P->b_packed.ensure(sizeof(double) * (10 + 3 * (size_t)N));
+    P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
+    P->b_lv.ensure(sizeof(double) * 9 * (size_t)(N + 1));
+    CUDA_OK(cudaMemcpyAsync(P->b_pos.p, quip_x, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->b_Z.p, atomic_numbers, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->b_zc.p, zc.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->b_xoff.p, off.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, st));
+    if (nnz) CUDA_OK(cudaMemcpyAsync(P->b_xj.p, nj.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemsetAsync(P->b_xs.p, 0, sizeof(int) * (nnz + 1), st));
+    ExtList ext{P->b_xoff.as<int>(), P->b_xj.as<int>(), P->b_xs.as<int>(), P->b_zc.as<int>(), *nlocal};
+    const int pbc[3] = {0, 0, 0};
+    const int save_rank = P->rank, save_n = P->n_ranks;
+    P->rank = 0; P->n_ranks = 1;
+    try {
+      calc_device_impl(P, N, P->b_pos.as<double>(), P->b_Z.as<int>(), lattice, pbc, "", true, P->b_packed.as<double>(), P->b_le.as<double>(),
+                       P->b_lv.as<double>(), st, &ext);
+    } catch (...) {
+      P->rank = save_rank; P->n_ranks = save_n;
+      throw;
+    }
+    P->rank = save_rank; P->n_ranks = save_n;
+    double head[10];
+    CUDA_OK(cudaMemcpyAsync(head, P->b_packed.p, sizeof(head), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(quip_force, P->b_packed.as<double>() + 10, sizeof(double) * 3 * (size_t)N, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(quip_local_e, P->b_le.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(quip_local_virial, P->b_lv.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    *quip_e = head[0];
+    for (int k = 0; k < 9; k++) quip_virial[k] = head[1 + k];
+  });
+  if (rc != 0) {  // the Fortran wrapper has no error argument: it system_aborts
+    fprintf(stderr, "SYSTEM ABORT: %s\n", gap_last_error());
+    abort();
+  }
+}
+
 int gap_potential_last_timings(gap_potential* P, double* ms8) {
   if (!P || !ms8) return 1;
   if (P->ev_used >= 2) {  // events of the last calc (host- or device-pointer entry): wait for the last one, then read
@@ -981,6 +1115,7 @@ int gap_descriptor_calc(gap_potential* P, int i_coord, int N, const double* pos,
     if (d_out) *d_out = cd.h.d;
     if (!x) return;
     build_connect(P, N, 0, N, P->b_pos.as<double>(), lattice, pbc, cd.h.cutoff, false, false, st);
+    P->cv_off = P->b_off.as<int>(); P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
     Lattice9 lat;
     for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
     soap_forward_stage(P, cd, n_ub, P->b_pos.as<double>(), P->b_Z.as<int>(), lat, st);

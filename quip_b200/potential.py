@@ -36,6 +36,9 @@ ABI = {
     "gap_potential_calc_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_dp, c_ip, C.c_char_p, C.c_int,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gap_md_run": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_ip, C.c_double, C.c_int, C.c_char_p, c_dp, c_dp]),
+    "quip_lammps_api_version": (C.c_int, []),
+    "quip_lammps_potential_initialise": (None, [c_ip, c_ip, c_dp, C.c_char_p, c_ip, C.c_char_p, c_ip]),
+    "quip_lammps_wrapper": (None, [c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_dp, c_ip, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "gap_b200_wrapper_simple": (C.c_int, [C.c_char_p, c_ip, c_dp, c_ip, c_dp, c_dp, c_dp, c_dp]),
     "gap_calc_connect": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip, C.c_double, c_ip]),
     "gap_get_connect": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_dp]),

@@ -498,3 +498,90 @@ def test_md_energy_conservation_config_A_shape(tmp_path):
     etot = epot + ekin
     assert np.abs(etot - etot[0]).max() < 2e-4 * max(1.0, ekin[0])  # NVE: total energy conserved to O(dt^2)
     assert abs(epot[-1] - epot[0]) > 1e-6  # and something actually moved
+
+
+def test_quip_cli_known_answer(golden):
+    # `quip atoms_filename=gap_sample.xyz param_filename=GAP.xml E F V` (quip.f95:135-235, 698-821)
+    import io
+
+    from quip_b200 import cli
+
+    buf = io.StringIO()
+    cli.main(["atoms_filename=" + os.path.join(golden, "gap_sample.xyz"), "param_filename=" + os.path.join(golden, "GAP.xml"), "E", "F", "V"], out=buf)
+    lines = buf.getvalue().splitlines()
+    e = float([ln for ln in lines if ln.startswith("Energy=")][0].split("=")[1])
+    assert abs(e - 30.855129585407724) < 1e-7  # tests/test_gappot.py:36
+    assert sum(ln.startswith("Virial ") for ln in lines) == 3 and sum(ln.startswith("Pressure eV/A^3") for ln in lines) == 3
+    at = [ln for ln in lines if ln.startswith("AT ")]
+    assert at[0].split()[1] == "81" and "force:R:3" in at[1]
+    f = np.array([[float(t) for t in ln.split()[5:8]] for ln in at[2:]])
+    ref = read_xyz(os.path.join(golden, "gap_sample.xyz"), 0).arrays["force"]
+    assert np.abs(f - ref).max() < 1e-6
+    with pytest.raises(RuntimeError, match="Nothing to be calculated"):
+        cli.main(["atoms_filename=x.xyz", "param_filename=y.xml"])
+
+
+def test_lammps_pair_style_quip_abi(si_model, si_frames):
+    # quip_lammps_wrapper (quip_lammps_wrapper.f95:30-156) driven the way LAMMPS' pair_quip.cpp drives it: local atoms + explicit
+    # ghost images, a full neighbour list with skin, 1-based neighbour indices; ghost forces folded back (reverse communication)
+    import ctypes as C
+    import itertools
+
+    from quip_b200 import load_library
+
+    pot, om, xml = si_model
+    a = si_frames[8]
+    ref = pot.calc(a, force=True, virial=True, local_energy=True)
+    lib = load_library()
+    assert lib.quip_lammps_api_version() == 1
+    n_h = C.c_int(0)
+    cutoff = C.c_double(0.0)
+    f, s = xml.encode(), b"IP GAP"
+    handle = (C.c_int * 2)()
+    lib.quip_lammps_potential_initialise(handle, C.byref(n_h), C.byref(cutoff), f, C.byref(C.c_int(len(f))), s, C.byref(C.c_int(len(s))))
+    assert n_h.value == 2 and cutoff.value == 6.0
+    lib.quip_lammps_potential_initialise(handle, C.byref(n_h), C.byref(cutoff), f, C.byref(C.c_int(len(f))), s, C.byref(C.c_int(len(s))))
+    # ghosts: every periodic image within cutoff + skin of the cell
+    rc = cutoff.value + 0.3
+    N = len(a)
+    frac = np.linalg.solve(a.cell.T, a.positions.T).T
+    frac -= np.floor(frac)
+    pos0 = frac @ a.cell
+    gpos, gorig = [], []
+    heights = 1.0 / np.linalg.norm(np.linalg.inv(a.cell), axis=0)
+    R = [int(np.ceil(rc / h)) for h in heights]
+    for sh in itertools.product(*[range(-r, r + 1) for r in R]):
+        if sh == (0, 0, 0):
+            continue
+        p = pos0 + np.array(sh) @ a.cell
+        f2 = np.linalg.solve(a.cell.T, p.T).T
+        keep = np.all((f2 > -rc / heights) & (f2 < 1 + rc / heights), axis=1)
+        gpos.append(p[keep])
+        gorig.append(np.nonzero(keep)[0])
+    gpos, gorig = np.concatenate(gpos), np.concatenate(gorig)
+    x = np.ascontiguousarray(np.concatenate([pos0, gpos]))
+    Zall = np.ascontiguousarray(np.concatenate([a.numbers, a.numbers[gorig]]).astype(np.int32))
+    ntot = len(x)
+    from scipy.spatial import cKDTree
+
+    tree = cKDTree(x)
+    lists = tree.query_ball_point(pos0, rc)
+    ilist = np.arange(N, dtype=np.int32)
+    numneigh = np.array([len([j for j in l if j != i]) for i, l in enumerate(lists)], dtype=np.int32)
+    neigh = np.array([j + 1 for i, l in enumerate(lists) for j in sorted(l) if j != i], dtype=np.int32)
+    e = C.c_double(0.0)
+    le, vir, lv, frc = np.zeros(ntot), np.zeros(9), np.zeros(9 * ntot), np.zeros((ntot, 3))
+    tag = np.arange(1, ntot + 1, dtype=np.int32)
+    ip = lambda v: v.ctypes.data_as(C.POINTER(C.c_int))
+    dp = lambda v: v.ctypes.data_as(C.POINTER(C.c_double))
+    lat = np.ascontiguousarray(a.cell.reshape(9))
+    lib.quip_lammps_wrapper(C.byref(C.c_int(N)), C.byref(C.c_int(ntot - N)), ip(Zall), ip(tag), C.byref(C.c_int(N)), C.byref(C.c_int(len(neigh))),
+                            ip(ilist), ip(numneigh), ip(neigh), dp(lat), handle, C.byref(n_h), dp(x), C.byref(e), dp(le), dp(vir), dp(lv), dp(frc))
+    assert abs(e.value - ref["energy"]) / N < TOL_E_PER_ATOM
+    ftot = frc[:N].copy()
+    np.add.at(ftot, gorig, frc[N:])
+    assert np.abs(ftot - ref["force"]).max() < TOL_F
+    assert np.abs(vir.reshape(3, 3, order="F") - ref["virial"]).max() < TOL_V
+    letot = le[:N].copy()
+    np.add.at(letot, gorig, le[N:])
+    assert np.abs(letot - ref["local_energy"]).max() < 1e-8

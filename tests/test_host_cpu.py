@@ -133,3 +133,15 @@ def test_key_value_grammar_agrees():
                                    "species_Z=8 1", "normalise=F"]
     sp = orc.soap_params(s)
     assert sp["Z"] == [1, 8] and sp["species_Z"] == [8, 1] and not sp["normalise"] and not sp["central_reference_all_species"]
+
+
+def test_cli_argument_grammar():
+    from quip_b200 import cli
+
+    c = cli.parse_cli(["atoms_filename=a.xyz", "param_filename=p.xml", "E", "forces", "V=T", 'calc_args={only_descriptor=2}', "init_args=IP GAP"])
+    assert c["E"] and c["F"] and c["V"] and not c["local"]
+    assert c["atoms_filename"] == "a.xyz" and c["calc_args"] == "only_descriptor=2"
+    import pytest
+
+    with pytest.raises(RuntimeError, match="outside the GAP evaluation path"):
+        cli.parse_cli(["relax=T"])
