@@ -35,7 +35,7 @@ def parse_describe(text):
 def test_abi_exports_match_header():
     hdr = open(os.path.join(ROOT, "include", "gap_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(gap_\w+)\s*\(", hdr))
+    declared = set(re.findall(r"\b((?:gap|quip_lammps)_\w+)\s*\(", hdr))
     assert declared == set(P.ABI), declared ^ set(P.ABI)
     lib = P.load_library()
     for name in declared:
