@@ -93,6 +93,15 @@ void quip_lammps_wrapper(int* nlocal, int* nghost, int* atomic_numbers, int* lmp
                          int* quip_neigh, double* lattice, int* quip_potential, int* n_quip_potential, double* quip_x, double* quip_e,
                          double* quip_local_e, double* quip_virial, double* quip_local_virial, double* quip_force);
 
+/* Two-phase form of gap_potential_calc_device for callers that enqueue more work behind the evaluation (e.g. the NCCL
+ * all-reduce of d_packed) before they synchronise: _enqueue only enqueues; after the caller has synchronised the stream,
+ * _verify reports in *repeat whether the speculatively sized neighbour list overflowed (1 = call _enqueue again; the
+ * second attempt sizes the list exactly). */
+int gap_potential_calc_device_enqueue(gap_potential* pot, int N, const double* d_pos, const int* d_Z, const double* lattice, const int* pbc,
+                                      const char* args_str, int want_grad, double* d_packed, double* d_local_e, double* d_local_virial,
+                                      void* stream);
+int gap_potential_calc_device_verify(gap_potential* pot, int* repeat);
+
 /* F77-style one-shot entry point, same argument list as quip_wrapper_simple_
  * (src/Potentials/quip_unified_wrapper.f95:311-332) plus the XML file name; pbc = T T T. */
 int gap_b200_wrapper_simple(const char* param_filename, const int* N, const double* lattice, const int* Z, const double* pos,

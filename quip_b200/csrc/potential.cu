@@ -126,7 +126,8 @@ constexpr int FIN_BLOCKS = 128, FIN_THREADS = 256;
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict__ Z, int N, int first, int last, const double* __restrict__ e0,
                                                           double e_scale, double* __restrict__ local_e, const double* __restrict__ vir_part,
                                                           int n_slots, double* __restrict__ part /* [FIN_BLOCKS][10] */,
-                                                          unsigned int* __restrict__ counter, double* __restrict__ packed) {
+                                                          unsigned int* __restrict__ counter, double* __restrict__ packed,
+                                                          const int* __restrict__ nnz_dev, long cap) {
   typedef cub::BlockReduce<double, FIN_THREADS> BR;
   __shared__ typename BR::TempStorage tmp;
   __shared__ bool is_last;
@@ -158,6 +159,9 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict_
     if (threadIdx.x < 10) {
       double t = 0.0;
       for (int b = 0; b < (int)gridDim.x; b++) t += __ldcg(&part[10 * b + threadIdx.x]);
+      // a speculatively sized neighbour list that overflowed poisons the energy: after the all-reduce EVERY rank sees the NaN
+      // and repeats the evaluation, with no extra collective
+      if (threadIdx.x == 0 && nnz_dev && (long)*nnz_dev > cap) t = __longlong_as_double(0x7ff8000000000000LL);
       packed[threadIdx.x] = t;
     }
     if (threadIdx.x == 0) *counter = 0u;
@@ -698,7 +702,8 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   // totals
   P->b_fin.ensure(sizeof(double) * 10 * FIN_BLOCKS);
   k_finalize<<<FIN_BLOCKS, FIN_THREADS, 0, st>>>(d_Zc, N, first, last, P->d_e0, es, d_le, want_grad ? P->b_vir.as<double>() : nullptr,
-                                                want_grad ? (int)slot : 0, P->b_fin.as<double>(), P->d_fin_counter, d_packed);
+                                                want_grad ? (int)slot : 0, P->b_fin.as<double>(), P->d_fin_counter, d_packed,
+                                                P->pending_check ? P->b_off.as<int>() + N : nullptr, P->pending_cap);
   P->launches += 1;
   mark(P, st, ST_OTHER);
   CUDA_OK(cudaGetLastError());
@@ -819,6 +824,24 @@ int gap_potential_calc_device(gap_potential* P, int N, const double* d_pos, cons
       CUDA_OK(cudaStreamSynchronize(st));
       if (verify_connect(P)) break;  // otherwise the speculatively sized neighbour list overflowed: repeat with the exact size
     }
+  });
+}
+
+int gap_potential_calc_device_enqueue(gap_potential* P, int N, const double* d_pos, const int* d_Z, const double* lattice, const int* pbc,
+                                      const char* args_str, int want_grad, double* d_packed, double* d_local_e, double* d_local_virial, void* stream) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_calc_device_enqueue: pot is NULL");
+    if (N < 0) throw GapError("gap_potential_calc_device_enqueue: N < 0");
+    if (!d_packed) throw GapError("gap_potential_calc_device_enqueue: d_packed is NULL");
+    cudaStream_t st = stream ? (cudaStream_t)stream : P->stream;
+    calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad != 0 || d_local_virial != nullptr, d_packed, d_local_e, d_local_virial, st);
+  });
+}
+
+int gap_potential_calc_device_verify(gap_potential* P, int* repeat) {
+  return guard([&] {
+    if (!P || !repeat) throw GapError("gap_potential_calc_device_verify: bad arguments");
+    *repeat = verify_connect(P) ? 0 : 1;
   });
 }
 

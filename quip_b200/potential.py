@@ -39,6 +39,9 @@ ABI = {
     "quip_lammps_api_version": (C.c_int, []),
     "quip_lammps_potential_initialise": (None, [c_ip, c_ip, c_dp, C.c_char_p, c_ip, C.c_char_p, c_ip]),
     "quip_lammps_wrapper": (None, [c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_dp, c_ip, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "gap_potential_calc_device_enqueue": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_dp, c_ip, C.c_char_p, C.c_int,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gap_potential_calc_device_verify": (C.c_int, [C.c_void_p, c_ip]),
     "gap_b200_wrapper_simple": (C.c_int, [C.c_char_p, c_ip, c_dp, c_ip, c_dp, c_dp, c_dp, c_dp]),
     "gap_calc_connect": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip, C.c_double, c_ip]),
     "gap_get_connect": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_dp]),
@@ -293,6 +296,20 @@ class Potential:
                                                         C.c_void_p(d_local_virial_ptr) if d_local_virial_ptr else None,
                                                         C.c_void_p(stream_ptr) if stream_ptr else None))
 
+    def calc_device_enqueue(self, N, d_pos_ptr, d_Z_ptr, lattice9, pbc3, d_packed_ptr, want_grad=True, stream_ptr=None, args_str=""):
+        """Enqueue-only evaluation (see ``gap_potential_calc_device_enqueue``); pair with :meth:`calc_device_verify` after a stream sync."""
+        lat = np.ascontiguousarray(lattice9, dtype=np.float64).reshape(9)
+        pbc = np.ascontiguousarray(np.asarray(pbc3, dtype=bool).astype(np.int32))
+        _check(load_library().gap_potential_calc_device_enqueue(self._h, int(N), C.c_void_p(d_pos_ptr), C.c_void_p(d_Z_ptr), _dp(lat), _ip(pbc),
+                                                                args_str.encode(), int(bool(want_grad)), C.c_void_p(d_packed_ptr), None, None,
+                                                                C.c_void_p(stream_ptr) if stream_ptr else None))
+
+    def calc_device_verify(self):
+        """True when the last enqueued evaluation is valid; False = enqueue it again (the neighbour list overflowed its speculative size)."""
+        rep = C.c_int(0)
+        _check(load_library().gap_potential_calc_device_verify(self._h, C.byref(rep)))
+        return rep.value == 0
+
     @property
     def n_coordinate(self):
         return load_library().gap_potential_n_coordinate(self._h)
@@ -370,6 +387,7 @@ class ShardedPotential:
         self.pot.set_partition(self.rank, self.world_size)
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.Stream(self.device)  # a real stream: the C ABI reads stream 0 / NULL as "the handle's own"
+        self._h_e = torch.zeros(1, dtype=torch.float64, pin_memory=True)
         self._N = -1
 
     def _ensure(self, N):
@@ -400,9 +418,18 @@ class ShardedPotential:
                 self.calc_resident(N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad)
             cur.wait_stream(self.stream)
             return
-        self.pot.calc_device(N, d_pos.data_ptr(), d_Z.data_ptr(), lattice9, pbc3, d_packed.data_ptr(), want_grad=want_grad,
-                             stream_ptr=cur.cuda_stream)
-        self.reduce_packed(d_packed)
+        # enqueue the evaluation AND the collective, synchronise once, then check the speculatively sized neighbour list
+        for _ in range(2):
+            self.pot.calc_device_enqueue(N, d_pos.data_ptr(), d_Z.data_ptr(), lattice9, pbc3, d_packed.data_ptr(), want_grad=want_grad,
+                                         stream_ptr=cur.cuda_stream)
+            self.reduce_packed(d_packed)
+            # a rank whose list overflowed has poisoned its energy with NaN (k_finalize): after the reduction every rank sees it, so
+            # all ranks repeat together without an extra collective
+            self._h_e.copy_(d_packed[:1], non_blocking=True)
+            cur.synchronize()
+            ok = self.pot.calc_device_verify()
+            if ok and not bool(torch.isnan(self._h_e[0])):
+                break
 
     def calc(self, atoms, force=True, virial=True):
         """Host in, host out: H2D of (pos, Z) from pinned memory, evaluation of this rank's block, all-reduce, D2H."""
