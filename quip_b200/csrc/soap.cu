@@ -102,7 +102,7 @@ __host__ __device__ inline int stride4mod16(int v) {  // smallest s >= v with s 
   return s >= v ? s : s + 16;
 }
 struct Geo {
-  int n, L, L1, nlm, ns, K1, K18, n2, n8, RFS, YS, YSA, XS, XR, TS, NTM, NTN, MP;
+  int n, L, L1, nlm, ns, K1, K18, n2, n8, RFS, YS, XS, XR, TS, NTM, NTN, MP;
 };
 __host__ __device__ __forceinline__ Geo make_geo(int n_max, int l_max, int n_species) {
   Geo g;
@@ -112,8 +112,6 @@ __host__ __device__ __forceinline__ Geo make_geo(int n_max, int l_max, int n_spe
   g.n8 = ceil8(g.n);
   g.RFS = stride4mod16(g.L1 * g.n2);   // per-neighbour radial table [l][a]
   g.YS = stride4mod16(g.nlm + 7);      // forward: per-neighbour harmonics row = DMMA A operand (tile reads run up to 7 rows past nlm)
-  g.YSA = g.nlm;                       // adjoint: harmonics are read element-wise as [q = 2 fk + j][lm = lm0 + fr]: = 2 (mod 8) is
-  while ((g.YSA & 7) != 2) g.YSA++;    //          conflict free for that pattern
   g.MP = m_pairs(g.L);
   g.XS = g.K18 + 4;                    // X / Lambda row stride: = 4 or 12 (mod 16)
   g.XR = g.nlm + 8;                    // rows allocated
@@ -132,18 +130,18 @@ struct Smem {
   double* Tp;      // n8 x TS  transform_basis zero-padded: Tp[a*TS + a'] = T(a, a')
   double* rb;      // n
   double* ynorm;   // (L+1)(L+2)/2
+  double* invint;  // 16: 1/k (0 for k = 0)
+  double* dblf;    // 20: (2k-1)!! (0 beyond the table)
   double* X;       // XR x XS : forward Xt -> X ; adjoint X -> Lambda~   (row lm, column = channel s*n + a)
-  double* X2;      // adjoint: XR x XS Lambda (aliases the staging area)
+  double* X2;      // adjoint: XR x XS Lambda
   double* nbd;     // NBCAP*3 displacement
   double* nbr;     // NBCAP distance
   double* nbf;     // NBCAP f_cut
   double* nbdf;    // NBCAP f_cut'
   double* red;     // 64
-  double* rf;      // TN x RFS
-  double* drf;     // adjoint: TN x RFS
-  double* Y;       // TN x YS
-  double* G;       // adjoint: 3 x TN x YS  polynomial gradients of the harmonics
-  double* part;    // adjoint: NW x TNA x 4
+  double* rf;      // forward: TN x RFS
+  double* Y;       // forward: TN x YS
+  double* acc;     // adjoint: NW x 8 x 12 centre force / virial partials, one slot per (warp, fragment row)
   double* p;       // d_pad : forward power spectrum (aliases the staging area) ; adjoint u = dE/dp (own region)
   int* nbs;        // NBCAP species
   int* nbj;        // NBCAP neighbour atom
@@ -151,41 +149,38 @@ struct Smem {
   int* mt_l;       // NTM its l
   int* col_s;      // K18 species of channel (-1: padding)
   int* col_a;      // K18 radial index of channel
-  int* wcount;     // 8
+  int* wcount;     // NW x SOAP_SPECIES_CAP
+  int* seg;        // SOAP_SPECIES_CAP + 1: the compacted neighbours are sorted by species; species k occupies [seg[k], seg[k+1])
 };
 
 __host__ __device__ __forceinline__ size_t carve(const Geo& g, int d_pad, bool adjoint, Smem* s, unsigned char* base) {
-  const int TN = adjoint ? TNA : TNF;
   size_t o = 0;
   auto take = [&](size_t cnt) { size_t r = o; o += ((cnt + 1) & ~(size_t)1) * sizeof(double); return r; };
-  size_t oT = take((size_t)g.n8 * g.TS), orb = take(g.n), oyn = take((size_t)g.L1 * (g.L1 + 1) / 2), oX = take((size_t)g.XR * g.XS),
-         onbd = take(NBCAP * 3), onbr = take(NBCAP), onbf = take(NBCAP), onbdf = take(NBCAP), ored = take(64);
-  size_t ostage = o;
-  const int ys = adjoint ? g.YSA : g.YS;
-  size_t orf = take((size_t)TN * g.RFS), odrf = adjoint ? take((size_t)TN * g.RFS) : 0, oY = take((size_t)TN * ys),
-         oG = adjoint ? take((size_t)3 * TN * ys) : 0, opart = adjoint ? take((size_t)NW * TNA * 4) : 0;
-  size_t stage_bytes = o - ostage;
-  size_t op;
+  size_t oT = take((size_t)g.n8 * g.TS), orb = take(g.n), oyn = take((size_t)g.L1 * (g.L1 + 1) / 2), oinv = take(16), odbl = take(20),
+         oX = take((size_t)g.XR * g.XS), onbd = take(NBCAP * 3), onbr = take(NBCAP), onbf = take(NBCAP), onbdf = take(NBCAP), ored = take(64);
+  size_t ostage = o, orf = 0, oY = 0, oX2 = 0, oacc = 0, op;
   if (adjoint) {
-    // the staging area doubles as the Lambda buffer (XR x XS) while Lambda~ is formed
-    size_t need = (size_t)g.XR * g.XS * sizeof(double);
-    if (need > stage_bytes) o = ostage + need;
+    oX2 = take((size_t)g.XR * g.XS);
     op = take(d_pad);
+    oacc = take((size_t)NW * 8 * 12);
   } else {
+    orf = take((size_t)TNF * g.RFS);
+    oY = take((size_t)TNF * g.YS);
+    size_t stage_bytes = o - ostage;
     op = ostage;  // forward: the power spectrum reuses the staging area after the neighbour loop
     if ((size_t)d_pad * sizeof(double) > stage_bytes) o = ostage + (size_t)d_pad * sizeof(double);
   }
   size_t oi = o;
-  o += sizeof(int) * (NBCAP * 2 + 2 * g.NTM + 2 * g.K18 + 8);
+  o += sizeof(int) * (NBCAP * 2 + 2 * g.NTM + 2 * g.K18 + NW * SOAP_SPECIES_CAP + SOAP_SPECIES_CAP + 2);
   o = (o + 15) & ~(size_t)15;
   if (s) {
-    s->Tp = (double*)(base + oT); s->rb = (double*)(base + orb); s->ynorm = (double*)(base + oyn); s->X = (double*)(base + oX);
-    s->X2 = (double*)(base + ostage);
+    s->Tp = (double*)(base + oT); s->rb = (double*)(base + orb); s->ynorm = (double*)(base + oyn); s->invint = (double*)(base + oinv);
+    s->dblf = (double*)(base + odbl); s->X = (double*)(base + oX); s->X2 = (double*)(base + oX2);
     s->nbd = (double*)(base + onbd); s->nbr = (double*)(base + onbr); s->nbf = (double*)(base + onbf); s->nbdf = (double*)(base + onbdf);
-    s->red = (double*)(base + ored); s->rf = (double*)(base + orf); s->drf = (double*)(base + odrf); s->Y = (double*)(base + oY);
-    s->G = (double*)(base + oG); s->part = (double*)(base + opart); s->p = (double*)(base + op);
+    s->red = (double*)(base + ored); s->rf = (double*)(base + orf); s->Y = (double*)(base + oY); s->acc = (double*)(base + oacc);
+    s->p = (double*)(base + op);
     s->nbs = (int*)(base + oi); s->nbj = s->nbs + NBCAP; s->mt_lm0 = s->nbj + NBCAP; s->mt_l = s->mt_lm0 + g.NTM; s->col_s = s->mt_l + g.NTM;
-    s->col_a = s->col_s + g.K18; s->wcount = s->col_a + g.K18;
+    s->col_a = s->col_s + g.K18; s->wcount = s->col_a + g.K18; s->seg = s->wcount + NW * SOAP_SPECIES_CAP;
   }
   return o;
 }
@@ -197,6 +192,8 @@ __device__ __forceinline__ void load_tables(const SoapDev* sp, const Geo& g, con
   }
   for (int k = threadIdx.x; k < g.n; k += NT) s.rb[k] = sp->r_basis[k];
   for (int k = threadIdx.x; k < g.L1 * (g.L1 + 1) / 2; k += NT) s.ynorm[k] = sp->ynorm[k];
+  if (threadIdx.x < 16) s.invint[threadIdx.x] = threadIdx.x <= LC + 1 ? c_invint[threadIdx.x] : 0.0;
+  if (threadIdx.x < 20) s.dblf[threadIdx.x] = threadIdx.x <= LC ? c_dblfact[threadIdx.x] : 0.0;
   if (threadIdx.x <= g.L) {  // thread l writes the lm tiles of its l
     const int l = threadIdx.x;
     int t = 0;
@@ -220,10 +217,12 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Ordered (deterministic) block compaction of up to NBCAP CSR entries of centre i into shared memory.
-__device__ __forceinline__ int gather_neighbours(const SoapDev* sp, const Smem& s, int i, int pbeg, int pend, const int* __restrict__ nbr_j,
-                                                 const int* __restrict__ nbr_s, const double* __restrict__ pos, const int* __restrict__ Z,
-                                                 const Lattice9& lat) {
+// Ordered (deterministic) block compaction of up to NBCAP CSR entries of centre i into shared memory, SORTED BY SPECIES
+// (stable within a species): species k occupies [seg[k], seg[k+1]), so that a tile of neighbours of one species only
+// touches that species' n_max channels.
+__device__ __forceinline__ int gather_neighbours(const SoapDev* sp, const Smem& s, int ns, int i, int pbeg, int pend,
+                                                 const int* __restrict__ nbr_j, const int* __restrict__ nbr_s, const double* __restrict__ pos,
+                                                 const int* __restrict__ Z, const Lattice9& lat) {
   int p = pbeg + threadIdx.x;
   bool valid = false;
   double dd[3], r = 0.0;
@@ -237,15 +236,30 @@ __device__ __forceinline__ int gather_neighbours(const SoapDev* sp, const Smem& 
     spc = species_of(sp, Z[j]);
     valid = (r < sp->cutoff) && (spc >= 0);  // descriptors.f95:8190, 8194-8195
   }
-  unsigned bal = __ballot_sync(0xffffffffu, valid);
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) s.wcount[w] = __popc(bal);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int myrank = 0;
+  for (int k = 0; k < ns; k++) {
+    const bool mine = valid && spc == k;
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0) s.wcount[w * SOAP_SPECIES_CAP + k] = __popc(bal);
+    if (mine) myrank = __popc(bal & ((1u << lane) - 1u));
+  }
   __syncthreads();
-  int off = 0;
-  for (int k = 0; k < w; k++) off += s.wcount[k];
-  int total = s.wcount[0] + s.wcount[1] + s.wcount[2] + s.wcount[3];
+  int total = 0, q = 0;
+  for (int k = 0; k < ns; k++) {
+    int before = 0, tk = 0;
+#pragma unroll
+    for (int ww = 0; ww < NW; ww++) {
+      const int c = s.wcount[ww * SOAP_SPECIES_CAP + k];
+      tk += c;
+      if (ww < w) before += c;
+    }
+    if (spc == k) q = total + before + myrank;
+    if (threadIdx.x == 0) s.seg[k] = total;
+    total += tk;
+  }
+  if (threadIdx.x == 0) s.seg[ns] = total;
   if (valid) {
-    int q = off + __popc(bal & ((1u << lane) - 1u));
     double f, df;
     cutoff_fn(sp, r, f, df);
     s.nbd[3 * q] = dd[0];
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
 
   const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
   for (int pb = pbeg; pb < pend; pb += NBCAP) {
-    int nv = gather_neighbours(sp, s, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
+    int nv = gather_neighbours(sp, s, ns, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
     for (int t0 = 0; t0 < nv; t0 += TNF) {
       const int tn = min(TNF, nv - t0), tn4 = ceil4(tn);
       // ---- stage: radial items (q, a) and harmonic items (q, m); rows q in [tn, tn4) are zero (K padding) ----
@@ -505,6 +519,185 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
   double* xr = x + (size_t)c * d_pad;
   for (int q = threadIdx.x; q < d_pad; q += NT) xr[q] = q < d - 1 ? s.p[q] * inv : (q == d - 1 ? sp->sigma0 : 0.0);
   if (threadIdx.x == 0) pnorm[c] = nrm;
+}
+
+// One tile of up to 8 neighbours (all of species sk) of the adjoint, run by ONE warp entirely in registers:
+//     A_lm(q) = sum_a Lambda~_lm(sk,a) R_l(a; q),   B_lm(q) = sum_a Lambda~_lm(sk,a) Phi_l(a; q)        (FP64 tensor cores)
+//     f_gp(q) = sum_lm [ A_lm Y_lm(q) u_q + B_lm grad Y_lm(q) ]                                          (IPModel_GAP.f95:479)
+// as DMMA tiles C[q][m] = sum_a R[q][a] Lambda~[l,m][a], level by level in l.  The fragment layout of mma.m8n8k4 is
+// exploited so that nothing is staged through shared memory:
+//   * lane (fr, fk) holds A-operand element (row q = fr, k = a = 4 ks + fk): it runs the reference's upward recursion in l
+//     (descriptors.f95:8218-8258) for ITS (neighbour, basis point) items and hands R_l / Phi_l to the tensor core as they appear;
+//   * it receives C elements (row q = fr, columns m = 2 fk, 2 fk + 1 of the column tile): for its neighbour and those two
+//     orders it runs the harmonic recursion in l (Y_{l,+-m}, grad Y_{l,+-m}; GradSphericalYCartesian_all,
+//     angular_functions.f95:205-278) in step with the level loop and folds the products into four scalars.
+// Column tiles at level l: P_g (m = 8g + column, cos type) and N_g (m = -(8g + column), sin type), g = 0 [, 1 if l >= 8];
+// +m and -m of a thread share the Legendre recursion.  Four shuffles finish the sum over m; lane fk == 0 scatters.
+template <int CN, int CL>
+__device__ __forceinline__ void adjoint_tile(const Smem& s, const Geo& g, const double alpha, const int sk, const int q0, const int tn, const int fr,
+                                             const int fk, const double e_scale, double* __restrict__ force,
+                                             double* __restrict__ local_virial, double* accs) {
+  constexpr bool SPEC = CN != 0;
+  constexpr int KS = SPEC ? (CN + 3) / 4 : (SOAP_NMAX_CAP + 3) / 4;   // DMMA k steps over the radial channels of one species
+  constexpr int NG = SPEC ? (CL >= 8 ? 2 : 1) : 2;                    // groups of 8 orders |m|
+  constexpr int NJ1 = SPEC ? (CL >= 9 ? 2 : (CL == 8 ? 1 : 0)) : 2;   // orders of the second group a thread can own
+  constexpr int NMJ = 2 + NJ1;
+  const int n = g.n, L = SPEC ? CL : g.L, XS = g.XS;
+  const bool vq = fr < tn;
+  const int q = q0 + (vq ? fr : 0);  // padding rows reuse the tile's first neighbour with f = f' = 0: their A fragments vanish
+  const double r = s.nbr[q], rinv = 1.0 / r;
+  const double dx = s.nbd[3 * q], dy = s.nbd[3 * q + 1], dz = s.nbd[3 * q + 2];
+  const double f = vq ? s.nbf[q] : 0.0, df = vq ? s.nbdf[q] : 0.0;
+  const double ux = dx * rinv, uy = dy * rinv, uz = dz * rinv;
+  const double tar = 2.0 * alpha * r;
+
+  // ---- radial items (q, a = 4 ks + fk): state of the recursion i_{l+1} = i_{l-1} - (2l+1) i_l / x ----
+  double bl[KS], blp[KS], inv[KS], tarb[KS];
+  bool za[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) {
+    const int a = 4 * ks + fk;
+    bl[ks] = blp[ks] = inv[ks] = tarb[ks] = 0.0;
+    za[ks] = true;
+    if (a < n) {
+      const double rb = s.rb[a], arg = tar * rb;
+      tarb[ks] = 2.0 * alpha * rb;
+      if (arg == 0.0) bl[ks] = exp(-alpha * (rb * rb + r * r));  // :8225-8240: i_0 = exp(-alpha r^2), i_{l>0} = 0
+      else {
+        const double exp_p = exp(-alpha * (r + rb) * (r + rb)), exp_m = exp(-alpha * (r - rb) * (r - rb));
+        const double iv = 1.0 / arg, blm = 0.5 * (exp_m + exp_p) * iv, b0 = 0.5 * (exp_m - exp_p) * iv;
+        inv[ks] = iv;
+        bl[ks] = b0;
+        blp[ks] = blm - b0 * iv;
+        za[ks] = false;
+      }
+    }
+  }
+  // ---- harmonic state: powers (ux + i uy)^m and Legendre-derivative recursions of this thread's orders ----
+  double Cm[NMJ], Sm[NMJ], cM[NMJ], sM[NMJ], p1[NMJ], p2[NMJ], z1[NMJ], z2[NMJ];
+  {
+    double ca = 1.0, sa = 0.0, cb = 0.0, sb = 0.0;  // P_k and P_{k-1}, P_k = (ux + i uy)^k
+    for (int k = 0; k < 2 * fk; k++) {
+      const double t = ca, u = sa;
+      ca = ux * t - uy * u;
+      sa = ux * u + uy * t;
+      cb = t;
+      sb = u;
+    }
+    const double m0 = (double)(2 * fk);
+    Cm[0] = ca; Sm[0] = sa; cM[0] = m0 * cb; sM[0] = m0 * sb;
+    const double c1 = ux * ca - uy * sa, s1 = ux * sa + uy * ca;
+    Cm[1] = c1; Sm[1] = s1; cM[1] = (m0 + 1.0) * ca; sM[1] = (m0 + 1.0) * sa;
+    if constexpr (NJ1 >= 1) {
+      const double c2 = ux * ux - uy * uy, s2 = 2.0 * ux * uy, c4 = c2 * c2 - s2 * s2, s4 = 2.0 * c2 * s2, c8 = c4 * c4 - s4 * s4, s8 = 2.0 * c4 * s4;
+      const double c6 = c4 * c2 - s4 * s2, s6 = c4 * s2 + s4 * c2, c7 = c6 * ux - s6 * uy, s7 = c6 * uy + s6 * ux;
+      Cm[2] = c8 * ca - s8 * sa; Sm[2] = c8 * sa + s8 * ca;                                    // P_{8+2fk}
+      cM[2] = (m0 + 8.0) * (c7 * ca - s7 * sa); sM[2] = (m0 + 8.0) * (c7 * sa + s7 * ca);      // (8+2fk) P_{7+2fk}
+      if constexpr (NJ1 >= 2) {
+        Cm[NMJ - 1] = c8 * c1 - s8 * s1; Sm[NMJ - 1] = c8 * s1 + s8 * c1;                      // P_{9+2fk}
+        cM[NMJ - 1] = (m0 + 9.0) * Cm[2]; sM[NMJ - 1] = (m0 + 9.0) * Sm[2];
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < NMJ; jj++) {
+      const int mv = (jj < 2 ? 0 : 8) + 2 * fk + (jj & 1);
+      p1[jj] = s.dblf[mv];  // Q_m^m = (2m-1)!!
+      p2[jj] = z1[jj] = z2[jj] = 0.0;
+    }
+  }
+
+  double SA = 0.0, G0 = 0.0, G1 = 0.0, G2 = 0.0;
+  const double* Xc = s.X + sk * n + fk;  // Lambda~ columns of this species, this thread's k offset
+#pragma unroll(SPEC ? 16 : 1)
+  for (int l = 0; l <= L; l++) {
+    double phi[KS], rr[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+      if (l > 0) {
+        const double blm = bl[ks], b = blp[ks];
+        bl[ks] = za[ks] ? 0.0 : b;
+        blp[ks] = za[ks] ? 0.0 : blm - (double)(2 * l + 1) * b * inv[ks];
+      }
+      phi[ks] = f * bl[ks];
+      rr[ks] = f * (-tar * bl[ks] + (double)l * bl[ks] * rinv + blp[ks] * tarb[ks]) + df * bl[ks];  // :8254-8255 and f' Phi (:8261-8263)
+    }
+    const int lmc = l * l + l;
+    const double tz = (double)(2 * l - 1) * uz;
+#pragma unroll
+    for (int gi = 0; gi < NG; gi++) {
+      if (8 * gi <= l) {
+        const int mcol = 8 * gi + fr;  // |m| of this thread's B-operand column
+        const bool vP = mcol <= l, vN = vP && mcol >= 1;
+        double aP[2] = {0.0, 0.0}, bP[2] = {0.0, 0.0}, aN[2] = {0.0, 0.0}, bN[2] = {0.0, 0.0};
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+          const double xp = vP ? Xc[(lmc + mcol) * XS + 4 * ks] : 0.0;
+          dmma(aP[0], aP[1], rr[ks], xp);
+          dmma(bP[0], bP[1], phi[ks], xp);
+        }
+        if (l >= 1) {
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) {
+            const double xn = vN ? Xc[(lmc - mcol) * XS + 4 * ks] : 0.0;
+            dmma(aN[0], aN[1], rr[ks], xn);
+            dmma(bN[0], bN[1], phi[ks], xn);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const int jj = 2 * gi + j;
+          if (jj < NMJ) {
+            const int mv = 8 * gi + 2 * fk + j;
+            if (mv <= l) {
+              double pl, zl;
+              if (l == mv) { pl = p1[jj]; zl = 0.0; }
+              else {
+                pl = (tz * p1[jj] - (double)(l + mv - 1) * p2[jj]) * s.invint[l - mv];
+                zl = (l == mv + 1) ? s.dblf[mv + 1] : (tz * z1[jj] - (double)(l + mv) * z2[jj]) * s.invint[l - mv - 1];
+                p2[jj] = p1[jj]; p1[jj] = pl;
+                z2[jj] = z1[jj]; z1[jj] = zl;
+              }
+              const double nrm = s.ynorm[l * (l + 1) / 2 + mv];
+              const double qv = pl * nrm, qz = zl * nrm;
+              SA += qv * (aP[j] * Cm[jj] + aN[j] * Sm[jj]);
+              G0 += qv * (bP[j] * cM[jj] + bN[j] * sM[jj]);
+              G1 += qv * (bN[j] * cM[jj] - bP[j] * sM[jj]);
+              G2 += qz * (bP[j] * Cm[jj] + bN[j] * Sm[jj]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // sum over the orders held by the four lanes of a fragment row
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    SA += __shfl_xor_sync(0xffffffffu, SA, o);
+    G0 += __shfl_xor_sync(0xffffffffu, G0, o);
+    G1 += __shfl_xor_sync(0xffffffffu, G1, o);
+    G2 += __shfl_xor_sync(0xffffffffu, G2, o);
+  }
+  if (fk == 0 && vq) {
+    const double ug = ux * G0 + uy * G1 + uz * G2;
+    // f_gp,k = sum_lm [ A_lm Y_lm u_k + B_lm grad_k Y_lm ],  grad Y = (g - u (u.g)) / r
+    const double f0 = (SA * ux + (G0 - ux * ug) * rinv) * e_scale;
+    const double f1 = (SA * uy + (G1 - uy * ug) * rinv) * e_scale;
+    const double f2 = (SA * uz + (G2 - uz * ug) * rinv) * e_scale;
+    // IPModel_GAP.f95:479-491: F_j -= f_gp ; centre row is minus the sum ; W_j -= (pos_j - pos_i) (x) f_gp
+    const int j = s.nbj[q];
+    if (force) {
+      atomicAdd(&force[3 * (size_t)j + 0], -f0);
+      atomicAdd(&force[3 * (size_t)j + 1], -f1);
+      atomicAdd(&force[3 * (size_t)j + 2], -f2);
+      accs[0] += f0; accs[1] += f1; accs[2] += f2;
+    }
+    const double wv[9] = {dx * f0, dy * f0, dz * f0, dx * f1, dy * f1, dz * f1, dx * f2, dy * f2, dz * f2};  // column-major (a + 3b)
+#pragma unroll
+    for (int k = 0; k < 9; k++) accs[3 + k] -= wv[k];
+    if (local_virial)
+#pragma unroll
+      for (int k = 0; k < 9; k++) atomicAdd(&local_virial[9 * (size_t)j + k], -wv[k]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -638,133 +831,31 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
   }
   __syncthreads();
 
-  double fi[3] = {0, 0, 0}, vir[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const int gstride = TNA * g.YSA;
+  // ---- neighbour phase: every warp works through tiles of 8 neighbours on its own (no block barrier, no staging) ----
+  double* accs = s.acc + (warp * 8 + fr) * 12;  // centre force (3) and virial (9) partials of this (warp, fragment row), lane fk == 0
+  if (fk == 0)
+#pragma unroll
+    for (int k = 0; k < 12; k++) accs[k] = 0.0;
   const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
   for (int pb = pbeg; pb < pend; pb += NBCAP) {
-    int nv = gather_neighbours(sp, s, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
-    for (int t0 = 0; t0 < nv; t0 += TNA) {
-      const int tn = min(TNA, nv - t0);
-      // ---- stage: radial tables with derivative, harmonics with polynomial gradients; columns q in [tn, 8) zero ----
-      const int n_rad = tn * n, n_items = n_rad + tn * g.MP;
-      for (int it = threadIdx.x; it < n_items; it += NT) {
-        if (it < n_rad) {
-          int q = it / n, a = it - q * n;
-          radial_item<true>(alpha, s.nbr[t0 + q], s.rb[a], s.nbf[t0 + q], s.nbdf[t0 + q], L, s.rf + q * g.RFS + a,
-                            s.drf + q * g.RFS + a, g.n2);
-        } else {
-          int r2 = it - n_rad;
-          int m = r2 / tn, q = r2 - m * tn;
-          double rinv = 1.0 / s.nbr[t0 + q];
-          ylm_item<true>(s.ynorm, L, m, s.nbd[3 * (t0 + q)] * rinv, s.nbd[3 * (t0 + q) + 1] * rinv, s.nbd[3 * (t0 + q) + 2] * rinv,
-                         s.Y + q * g.YSA, s.G + q * g.YSA, gstride);
-        }
-      }
-      for (int it = threadIdx.x; it < (TNA - tn) * g.YSA; it += NT) {  // harmonics of the padding neighbours: zero (their A, B are zero too)
-        int q = tn + it / g.YSA, k = it % g.YSA;
-        s.Y[q * g.YSA + k] = 0.0;
-        s.G[q * g.YSA + k] = 0.0;
-        s.G[gstride + q * g.YSA + k] = 0.0;
-        s.G[2 * gstride + q * g.YSA + k] = 0.0;
-      }
-      __syncthreads();
-      // ---- contraction on the tensor cores: A_lm(q) = sum_c Lambda~[lm][c] R[q][l][a(c)], B_lm(q) likewise with Phi;
-      //      each thread then folds its two (lm, q) elements with Y and grad Y:
-      //      SA(q) += A_lm(q) Y_lm(q),  G_k(q) += B_lm(q) g_k,lm(q) ----
-      double SA[2] = {0, 0}, G0[2] = {0, 0}, G1[2] = {0, 0}, G2[2] = {0, 0};
-      const int qb = fr;  // this thread's B column = neighbour
-      const int sq = qb < tn ? s.nbs[t0 + qb] : -2;
-      for (int mt = warp; mt < g.NTM; mt += NW) {
-        const int lm0 = s.mt_lm0[mt], l = s.mt_l[mt];
-        double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-        for (int k0 = 0; k0 < g.K18; k0 += 4) {
-          const int ch = k0 + fk;
-          const double lam = s.X[(lm0 + fr) * g.XS + ch];
-          const bool on = s.col_s[ch] == sq;
-          const int off = qb * g.RFS + l * g.n2 + s.col_a[ch];
-          const double rv = on ? s.drf[off] : 0.0, pv = on ? s.rf[off] : 0.0;
-          dmma(a0, a1, lam, rv);
-          dmma(b0, b1, lam, pv);
-        }
-        const int lm = lm0 + fr;
-        if (lm < (l + 1) * (l + 1)) {
-#pragma unroll
-          for (int j = 0; j < 2; j++) {
-            const int yo = (2 * fk + j) * g.YSA + lm;
-            const double av = j ? a1 : a0, bv = j ? b1 : b0;
-            SA[j] += av * s.Y[yo];
-            G0[j] += bv * s.G[yo];
-            G1[j] += bv * s.G[gstride + yo];
-            G2[j] += bv * s.G[2 * gstride + yo];
-          }
-        }
-      }
-      // sum over the 8 fragment rows (lanes with equal fk), then over the warps through shared memory
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          SA[j] += __shfl_xor_sync(0xffffffffu, SA[j], o);
-          G0[j] += __shfl_xor_sync(0xffffffffu, G0[j], o);
-          G1[j] += __shfl_xor_sync(0xffffffffu, G1[j], o);
-          G2[j] += __shfl_xor_sync(0xffffffffu, G2[j], o);
-        }
-      }
-      if (fr == 0) {
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          double* pp = s.part + (warp * TNA + 2 * fk + j) * 4;
-          pp[0] = SA[j]; pp[1] = G0[j]; pp[2] = G1[j]; pp[3] = G2[j];
-        }
-      }
-      __syncthreads();
-      // ---- scatter: one thread per neighbour ----
-      if (threadIdx.x < tn) {
-        const int q = threadIdx.x;
-        double sa = 0, g0 = 0, g1 = 0, g2 = 0;
-        for (int w = 0; w < NW; w++) {
-          const double* pp = s.part + (w * TNA + q) * 4;
-          sa += pp[0]; g0 += pp[1]; g1 += pp[2]; g2 += pp[3];
-        }
-        const double r = s.nbr[t0 + q], rinv = 1.0 / r;
-        const double dx = s.nbd[3 * (t0 + q)], dy = s.nbd[3 * (t0 + q) + 1], dz = s.nbd[3 * (t0 + q) + 2];
-        const double ux = dx * rinv, uy = dy * rinv, uz = dz * rinv;
-        const double ug = ux * g0 + uy * g1 + uz * g2;
-        // f_gp,k = sum_lm [ A_lm Y_lm u_k + B_lm grad_k Y_lm ],  grad Y = (g - u (u.g)) / r
-        const double f0 = (sa * ux + (g0 - ux * ug) * rinv) * e_scale;
-        const double f1 = (sa * uy + (g1 - uy * ug) * rinv) * e_scale;
-        const double f2 = (sa * uz + (g2 - uz * ug) * rinv) * e_scale;
-        // IPModel_GAP.f95:479-491: F_j -= f_gp ; centre row is minus the sum ; W_j -= (pos_j - pos_i) (x) f_gp
-        const int j = s.nbj[t0 + q];
-        if (force) {
-          atomicAdd(&force[3 * (size_t)j + 0], -f0);
-          atomicAdd(&force[3 * (size_t)j + 1], -f1);
-          atomicAdd(&force[3 * (size_t)j + 2], -f2);
-          fi[0] += f0; fi[1] += f1; fi[2] += f2;
-        }
-        double wv[9] = {dx * f0, dy * f0, dz * f0, dx * f1, dy * f1, dz * f1, dx * f2, dy * f2, dz * f2};  // column-major (a + 3b)
-#pragma unroll
-        for (int k = 0; k < 9; k++) vir[k] -= wv[k];
-        if (local_virial)
-#pragma unroll
-          for (int k = 0; k < 9; k++) atomicAdd(&local_virial[9 * (size_t)j + k], -wv[k]);
-      }
-      // (the next tile's stage phase only writes rf/drf/Y/G, which the scatter does not read; part is rewritten after the
-      //  next stage barrier)
+    gather_neighbours(sp, s, ns, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
+    int tbase = 0;
+    for (int sk = 0; sk < ns; sk++) {
+      const int sbeg = s.seg[sk], send = s.seg[sk + 1];
+      const int ntile = (send - sbeg + 7) >> 3;
+      for (int t = (warp + NW - (tbase & (NW - 1))) & (NW - 1); t < ntile; t += NW)
+        adjoint_tile<CN, CL>(s, g, alpha, sk, sbeg + 8 * t, min(8, send - sbeg - 8 * t), fr, fk, e_scale, force, local_virial, accs);
+      tbase += ntile;
     }
+    if (pb + NBCAP < pend) __syncthreads();  // the next pass overwrites the compacted list
   }
-  // combine the per-thread centre force / virial partials in fixed order (threads 0..TNA-1 hold them)
-  for (int k = 0; k < 3; k++) fi[k] = warp_sum(fi[k]);
-  for (int k = 0; k < 9; k++) vir[k] = warp_sum(vir[k]);
-  __syncthreads();
-  if (lane == 0) {
-    for (int k = 0; k < 3; k++) s.red[warp * 12 + k] = fi[k];
-    for (int k = 0; k < 9; k++) s.red[warp * 12 + 3 + k] = vir[k];
-  }
+  // centre force / virial: the 32 slots are added in a fixed order
   __syncthreads();
   if (threadIdx.x < 12) {
-    int k = threadIdx.x;
-    double t = (s.red[k] + s.red[12 + k]) + (s.red[24 + k] + s.red[36 + k]);
+    const int k = threadIdx.x;
+    double t = 0.0;
+#pragma unroll 8
+    for (int sl = 0; sl < NW * 8; sl++) t += s.acc[sl * 12 + k];
     if (k < 3) {
       if (force) atomicAdd(&force[3 * (size_t)i + k], t);
     } else if (vir_part) vir_part[9 * (size_t)c + (k - 3)] = t;
