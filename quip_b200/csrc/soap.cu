@@ -370,6 +370,130 @@ __device__ __forceinline__ void ylm_item(const double* __restrict__ ynorm, int L
 }
 
 // ------------------------------------------------------------------------------------------------
+// Register-resident density expansion (specialised n_max, l_max): one warp, 4 neighbours q of one species per call.
+//     Xt_lm(a) += sum_q Y_lm(q) Phi_l(a; q)                                              (descriptors.f95:8289-8295)
+// as DMMA tiles C[m][a] += A[m][q] B[q][a] per level l, with the operands produced where the tensor core wants them:
+// lane (fr, fk) runs the harmonic recursion in l for (order |m| = 8g + fr, neighbour fk) -> A elements of the cos tile P_g
+// and the sin tile N_g, and the radial recursion for (neighbour fk, basis point a = 8 nt + fr) -> B elements.  The
+// accumulators of ALL (l, tile, nt) stay in registers across the warp's neighbours and are flushed once per centre.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int fwd_tiles(int L) { return 2 * L + 1 + (L >= 8 ? 2 * (L - 7) : 0); }
+__host__ __device__ constexpr int fwd_tile_index(int L, int l, int gi, int sgn) {
+  return gi == 0 ? (sgn == 0 ? l : L + l) : 2 * L + 1 + 2 * (l - 8) + sgn;
+}
+
+template <int CN, int CL>
+__device__ __forceinline__ void forward_group(const Smem& s, const double alpha, const int q, const bool vq, const int fr, const int fk,
+                                              double (&acc)[fwd_tiles(CL)][(CN + 7) / 8][2]) {
+  // q = this lane's neighbour (buffer index); vq false = K padding: the lane is given a valid neighbour of the group and f = 0
+  constexpr int NTN = (CN + 7) / 8, NG = CL >= 8 ? 2 : 1;
+  const double r = s.nbr[q], rinv = 1.0 / r;
+  const double f = vq ? s.nbf[q] : 0.0;
+  const double ux = s.nbd[3 * q] * rinv, uy = s.nbd[3 * q + 1] * rinv, uz = s.nbd[3 * q + 2] * rinv;
+  const double tar = 2.0 * alpha * r;
+  double bl[NTN], blp[NTN], inv[NTN];
+  bool za[NTN];
+#pragma unroll
+  for (int nt = 0; nt < NTN; nt++) {
+    const int a = 8 * nt + fr;
+    bl[nt] = blp[nt] = inv[nt] = 0.0;
+    za[nt] = true;
+    if (a < CN) {
+      const double rb = s.rb[a], arg = tar * rb;
+      if (arg == 0.0) bl[nt] = exp(-alpha * (rb * rb + r * r));
+      else {
+        const double exp_p = exp(-alpha * (r + rb) * (r + rb)), exp_m = exp(-alpha * (r - rb) * (r - rb));
+        const double iv = 1.0 / arg, blm = 0.5 * (exp_m + exp_p) * iv, b0 = 0.5 * (exp_m - exp_p) * iv;
+        inv[nt] = iv;
+        bl[nt] = b0;
+        blp[nt] = blm - b0 * iv;
+        za[nt] = false;
+      }
+    }
+  }
+  double Cm[NG], Sm[NG], p1[NG], p2[NG];
+  {
+    double ca = 1.0, sa = 0.0;
+    for (int k = 0; k < fr; k++) {
+      const double t = ca;
+      ca = ux * t - uy * sa;
+      sa = ux * sa + uy * t;
+    }
+    Cm[0] = ca; Sm[0] = sa;
+    if constexpr (NG == 2) {
+      const double c2 = ux * ux - uy * uy, s2 = 2.0 * ux * uy, c4 = c2 * c2 - s2 * s2, s4 = 2.0 * c2 * s2, c8 = c4 * c4 - s4 * s4, s8 = 2.0 * c4 * s4;
+      Cm[NG - 1] = c8 * ca - s8 * sa; Sm[NG - 1] = c8 * sa + s8 * ca;
+    }
+#pragma unroll
+    for (int gi = 0; gi < NG; gi++) { p1[gi] = s.dblf[8 * gi + fr]; p2[gi] = 0.0; }
+  }
+#pragma unroll
+  for (int l = 0; l <= CL; l++) {
+    double phi[NTN];
+#pragma unroll
+    for (int nt = 0; nt < NTN; nt++) {
+      if (l > 0) {
+        const double blm = bl[nt], b = blp[nt];
+        bl[nt] = za[nt] ? 0.0 : b;
+        blp[nt] = za[nt] ? 0.0 : blm - (double)(2 * l + 1) * b * inv[nt];
+      }
+      phi[nt] = f * bl[nt];
+    }
+    const double tz = (double)(2 * l - 1) * uz;
+#pragma unroll
+    for (int gi = 0; gi < NG; gi++) {
+      if (8 * gi <= l) {
+        const int mv = 8 * gi + fr;
+        double yc = 0.0, ys = 0.0;
+        if (mv <= l) {
+          double pl;
+          if (l == mv) pl = p1[gi];
+          else {
+            pl = (tz * p1[gi] - (double)(l + mv - 1) * p2[gi]) * s.invint[l - mv];
+            p2[gi] = p1[gi]; p1[gi] = pl;
+          }
+          const double qv = pl * s.ynorm[l * (l + 1) / 2 + mv];
+          yc = qv * Cm[gi];
+          ys = qv * Sm[gi];
+        }
+#pragma unroll
+        for (int nt = 0; nt < NTN; nt++) dmma(acc[fwd_tile_index(CL, l, gi, 0)][nt][0], acc[fwd_tile_index(CL, l, gi, 0)][nt][1], yc, phi[nt]);
+        if (l >= 1) {
+#pragma unroll
+          for (int nt = 0; nt < NTN; nt++) dmma(acc[fwd_tile_index(CL, l, gi, 1)][nt][0], acc[fwd_tile_index(CL, l, gi, 1)][nt][1], ys, phi[nt]);
+        }
+      }
+    }
+  }
+}
+
+// adds a warp's accumulators into Xt (rows lm, columns c0 + a); invalid rows (|m| > l) and padding channels are skipped
+template <int CN, int CL>
+__device__ __forceinline__ void forward_flush(double* X, const int XS, const int c0, const int fr, const int fk,
+                                              const double (&acc)[fwd_tiles(CL)][(CN + 7) / 8][2]) {
+  constexpr int NTN = (CN + 7) / 8, NG = CL >= 8 ? 2 : 1;
+#pragma unroll
+  for (int l = 0; l <= CL; l++)
+#pragma unroll
+    for (int gi = 0; gi < NG; gi++)
+      if (8 * gi <= l) {
+        const int mrow = 8 * gi + fr;
+        if (mrow <= l) {
+#pragma unroll
+          for (int sgn = 0; sgn < 2; sgn++) {
+            if (sgn == 1 && (l == 0 || mrow == 0)) continue;
+            double* xr = X + (l * l + l + (sgn ? -mrow : mrow)) * XS + c0 + 2 * fk;
+#pragma unroll
+            for (int nt = 0; nt < NTN; nt++)
+#pragma unroll
+              for (int j = 0; j < 2; j++)
+                if (8 * nt + 2 * fk + j < CN) xr[8 * nt + j] += acc[fwd_tile_index(CL, l, gi, sgn)][nt][j];
+          }
+        }
+      }
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward: x (normalised power spectrum), X_lm (kept for the adjoint), |p|
 // ------------------------------------------------------------------------------------------------
 // CN / CL / CNS: compile-time n_max / l_max / n_species (0 = read them from the model: generic instantiation).  With
@@ -519,6 +643,256 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
   double* xr = x + (size_t)c * d_pad;
   for (int q = threadIdx.x; q < d_pad; q += NT) xr[q] = q < d - 1 ? s.p[q] * inv : (q == d - 1 ? sp->sigma0 : 0.0);
   if (threadIdx.x == 0) pnorm[c] = nrm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WARP-PER-CENTRE kernels (specialised n_max, l_max, n_species): a warp owns a centre from the neighbour gather to the
+// final store, so nothing in the centre's life needs a block barrier; the four warps of a CTA only share the read-only
+// tables.  Per-warp shared memory: X (nlm x K1, padded), a compacted neighbour buffer of NBW entries (reused for the
+// power spectrum / dE/dp vector once the neighbours are consumed).
+// ------------------------------------------------------------------------------------------------
+constexpr int NBW = 64;  // compacted neighbours buffered per warp; longer rows are worked off in several passes
+
+struct WSmem {
+  double *Tp, *rb, *ynorm, *invint, *dblf;  // block-shared tables
+  double *X, *acc, *nbd, *nbr, *nbf, *nbdf, *p;  // per warp
+  int *nbj, *nbs, *ord;
+};
+__host__ __device__ __forceinline__ size_t carve_w(const Geo& g, int d_pad, bool adjoint, int warp, WSmem* w, unsigned char* base) {
+  size_t o = 0;
+  auto take = [&](size_t cnt) { size_t r = o; o += ((cnt + 1) & ~(size_t)1) * sizeof(double); return r; };
+  const size_t oT = take((size_t)g.n8 * g.TS), orb = take(g.n), oyn = take((size_t)g.L1 * (g.L1 + 1) / 2), oinv = take(16), odbl = take(20);
+  const size_t tables = o;
+  o = 0;
+  const size_t oX = take((size_t)g.XR * g.XS), oacc = take(adjoint ? 96 : 0);
+  const size_t oreg = o;
+  const size_t onbd = take(3 * NBW), onbr = take(NBW), onbf = take(NBW), onbdf = take(adjoint ? NBW : 0);
+  const size_t oint = o;
+  o += sizeof(int) * 3 * NBW;
+  if (o - oreg < (size_t)d_pad * sizeof(double)) o = oreg + (size_t)d_pad * sizeof(double);
+  o = (o + 15) & ~(size_t)15;
+  const size_t per_warp = o;
+  if (w) {
+    w->Tp = (double*)(base + oT); w->rb = (double*)(base + orb); w->ynorm = (double*)(base + oyn); w->invint = (double*)(base + oinv);
+    w->dblf = (double*)(base + odbl);
+    unsigned char* wb = base + tables + (size_t)warp * per_warp;
+    w->X = (double*)(wb + oX); w->acc = (double*)(wb + oacc); w->nbd = (double*)(wb + onbd); w->nbr = (double*)(wb + onbr);
+    w->nbf = (double*)(wb + onbf); w->nbdf = (double*)(wb + onbdf); w->p = (double*)(wb + oreg);
+    w->nbj = (int*)(wb + oint); w->nbs = w->nbj + NBW; w->ord = w->nbs + NBW;
+  }
+  return tables + (size_t)NW * per_warp;
+}
+__device__ __forceinline__ void load_tables_w(const SoapDev* sp, const Geo& g, const WSmem& w) {
+  for (int k = threadIdx.x; k < g.n8 * g.TS; k += NT) {
+    int a = k / g.TS, b = k - a * g.TS;
+    w.Tp[k] = (a < g.n && b < g.n) ? sp->T[a + g.n * b] : 0.0;
+  }
+  for (int k = threadIdx.x; k < g.n; k += NT) w.rb[k] = sp->r_basis[k];
+  for (int k = threadIdx.x; k < g.L1 * (g.L1 + 1) / 2; k += NT) w.ynorm[k] = sp->ynorm[k];
+  if (threadIdx.x < 16) w.invint[threadIdx.x] = threadIdx.x <= LC + 1 ? c_invint[threadIdx.x] : 0.0;
+  if (threadIdx.x < 20) w.dblf[threadIdx.x] = threadIdx.x <= LC ? c_dblfact[threadIdx.x] : 0.0;
+}
+
+// 32 CSR entries of centre i -> appended (ordered) to the warp's compacted buffer; returns the new fill
+template <bool ADJ>
+__device__ __forceinline__ int gather_chunk_w(const SoapDev* sp, const WSmem& w, int fill, int i, int p0, int pend, const int* __restrict__ nbr_j,
+                                              const int* __restrict__ nbr_s, const double* __restrict__ pos, const int* __restrict__ Z,
+                                              const Lattice9& lat, int lane) {
+  const int p = p0 + lane;
+  bool valid = false;
+  double dd[3], r = 0.0;
+  int spc = -1, j = -1;
+  if (p < pend) {
+    j = nbr_j[p];
+    int s0, s1, s2;
+    unpack_shift(nbr_s[p], s0, s1, s2);
+    image_diff(pos + 3 * (size_t)i, pos + 3 * (size_t)j, lat.v, s0, s1, s2, dd);
+    r = norm_nofma(dd);
+    spc = species_of(sp, Z[j]);
+    valid = (r < sp->cutoff) && (spc >= 0);  // descriptors.f95:8190, 8194-8195
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const int q = fill + __popc(bal & ((1u << lane) - 1u));
+    double f, df;
+    cutoff_fn(sp, r, f, df);
+    w.nbd[3 * q] = dd[0];
+    w.nbd[3 * q + 1] = dd[1];
+    w.nbd[3 * q + 2] = dd[2];
+    w.nbr[q] = r;
+    w.nbf[q] = f;
+    if (ADJ) { w.nbdf[q] = df; w.nbj[q] = j; }
+    w.nbs[q] = spc;
+  }
+  return fill + __popc(bal);
+}
+// stable partition of the buffer by species: ord[seg[k] .. seg[k+1]) lists the entries of species k
+template <int CNS>
+__device__ __forceinline__ void sort_species_w(const WSmem& w, int fill, int lane, int (&seg)[CNS + 1]) {
+  int base = 0;
+#pragma unroll
+  for (int sk = 0; sk < CNS; sk++) {
+    seg[sk] = base;
+    for (int b0 = 0; b0 < fill; b0 += 32) {
+      const int idx = b0 + lane;
+      const bool mine = idx < fill && (CNS == 1 || w.nbs[idx] == sk);
+      const unsigned bal = __ballot_sync(0xffffffffu, mine);
+      if (mine) w.ord[base + __popc(bal & ((1u << lane) - 1u))] = idx;
+      base += __popc(bal);
+    }
+  }
+  seg[CNS] = base;
+  __syncwarp();
+}
+
+// the Smem view forward_group / adjoint_tile read (neighbour arrays + tables) for a warp-owned buffer
+__device__ __forceinline__ Smem view_of(const WSmem& w) {
+  Smem s;
+  s.Tp = w.Tp; s.rb = w.rb; s.ynorm = w.ynorm; s.invint = w.invint; s.dblf = w.dblf; s.X = w.X; s.nbd = w.nbd; s.nbr = w.nbr; s.nbf = w.nbf;
+  s.nbdf = w.nbdf; s.nbj = w.nbj; s.nbs = w.nbs; s.p = w.p; s.acc = w.acc;
+  s.X2 = nullptr; s.red = nullptr; s.rf = nullptr; s.Y = nullptr; s.mt_lm0 = nullptr; s.mt_l = nullptr; s.col_s = nullptr; s.col_a = nullptr;
+  s.wcount = nullptr; s.seg = nullptr;
+  return s;
+}
+
+template <int CN, int CL, int CNS>
+__global__ void __launch_bounds__(NT, (CN > 8 ? 2 : 4)) k_soap_forward_w(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
+                                                                         const int* __restrict__ n_centres_dev,
+                                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
+                                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
+                                                                         const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
+                                                                         double* __restrict__ xlm, double* __restrict__ pnorm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Geo g = make_geo(CN, CL, CNS);
+  constexpr int n = CN, L1 = CL + 1, nlm = (CL + 1) * (CL + 1), K1 = CN * CNS, ns = CNS;
+  constexpr int NTN = (CN + 7) / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int d = sp->d, d_pad = sp->d_pad;
+  WSmem w;
+  carve_w(g, d_pad, false, warp, &w, smem_raw);
+  load_tables_w(sp, g, w);
+  __syncthreads();  // the only block barrier: the tables
+  const int c = blockIdx.x * NW + warp;
+  if (c >= *n_centres_dev) return;
+  const Smem s = view_of(w);
+  const int i = centres[c];
+  const double alpha = sp->alpha;
+  for (int k = lane; k < g.XR * g.XS; k += 32) w.X[k] = 0.0;
+  __syncwarp();
+
+  // ---- density expansion: gather -> groups of 4 neighbours of one species -> register accumulators -> X ----
+  double acc[fwd_tiles(CL)][NTN][2];
+  auto zero_acc = [&]() {
+#pragma unroll
+    for (int t = 0; t < fwd_tiles(CL); t++)
+#pragma unroll
+      for (int nt = 0; nt < NTN; nt++) acc[t][nt][0] = acc[t][nt][1] = 0.0;
+  };
+  zero_acc();
+  const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
+  int fill = 0;
+  for (int p0 = pbeg; p0 < pend; p0 += 32) {
+    fill = gather_chunk_w<false>(sp, w, fill, i, p0, pend, nbr_j, nbr_s, pos, Z, lat, lane);
+    if (fill > NBW - 32 || p0 + 32 >= pend) {  // the buffer cannot take another chunk, or the row is finished: work it off
+      __syncwarp();
+      int seg[CNS + 1];
+      if (CNS == 1) { seg[0] = 0; seg[CNS] = fill; }
+      else sort_species_w<CNS>(w, fill, lane, seg);
+#pragma unroll
+      for (int sk = 0; sk < CNS; sk++) {
+        const int cnt = seg[sk + 1] - seg[sk];
+        for (int t0 = 0; t0 < cnt; t0 += 4) {
+          const bool vq = fk < cnt - t0;
+          const int k = seg[sk] + t0 + (vq ? fk : 0);
+          forward_group<CN, CL>(s, alpha, CNS == 1 ? k : w.ord[k], vq, fr, fk, acc);
+        }
+        if (CNS > 1 && cnt > 0) {
+          forward_flush<CN, CL>(w.X, g.XS, sk * CN, fr, fk, acc);
+          zero_acc();
+        }
+      }
+      fill = 0;
+      __syncwarp();
+    }
+  }
+  if (CNS == 1) forward_flush<CN, CL>(w.X, g.XS, 0, fr, fk, acc);
+  __syncwarp();
+  // ---- basis transform on the tensor cores, per species: X[lm][s,a'] = sum_a Xt[lm][s,a] T(a,a') ----
+  {
+    constexpr int n_mt = (nlm + 7) / 8, n_nt = (CN + 7) / 8, n_ks = (CN + 3) / 4;
+    for (int mt = 0; mt < n_mt; mt++) {
+#pragma unroll
+      for (int sk = 0; sk < ns; sk++) {
+        double ta[n_nt][2];
+#pragma unroll
+        for (int nt = 0; nt < n_nt; nt++) ta[nt][0] = ta[nt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < n_ks; ks++) {
+          const double a = w.X[(mt * 8 + fr) * g.XS + sk * n + ks * 4 + fk];  // columns >= n of the block meet zero rows of Tp
+#pragma unroll
+          for (int nt = 0; nt < n_nt; nt++) dmma(ta[nt][0], ta[nt][1], a, w.Tp[(ks * 4 + fk) * g.TS + nt * 8 + fr]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < n_nt; nt++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const int ap = nt * 8 + 2 * fk + j;
+            if (ap < n) w.X[(mt * 8 + fr) * g.XS + sk * n + ap] = ta[nt][j];
+          }
+        __syncwarp();
+      }
+    }
+  }
+  // central atom term (descriptors.f95:8151-8182): only a = 1 is non-zero because the Cholesky factor is lower triangular
+  if (lane < ns) {
+    if (sp->cras || sp->species_Z[lane] == Z[i] || sp->species_Z[lane] == 0) w.X[lane * n] += sp->central_weight * sp->chol00 * 0.28209479177387814347;
+  }
+  __syncwarp();
+  for (int k = lane; k < nlm * K1; k += 32) {
+    const int lm = k / K1, ic = k - lm * K1;
+    xlm[(size_t)c * nlm * K1 + k] = w.X[lm * g.XS + ic];
+  }
+  // ---- power spectrum on the tensor cores (descriptors.f95:8370-8418) ----
+  double loc = 0.0;
+  {
+    constexpr int NTC = (K1 + 7) / 8;
+#pragma unroll 1
+    for (int l = 0; l < L1; l++) {
+      const int lm_beg = l * l, lm_end = (l + 1) * (l + 1);
+      const double scale = sp->tlpo[l];
+#pragma unroll
+      for (int ti = 0; ti < NTC; ti++)
+#pragma unroll
+        for (int tj = 0; tj <= ti; tj++) {
+          double c0 = 0.0, c1 = 0.0;
+          for (int k0 = lm_beg; k0 < lm_end; k0 += 4) {
+            const int lm = k0 + fk;
+            const double a = lm < lm_end ? w.X[lm * g.XS + ti * 8 + fr] : 0.0;
+            const double b = lm < lm_end ? w.X[lm * g.XS + tj * 8 + fr] : 0.0;
+            dmma(c0, c1, a, b);
+          }
+          const int ia = ti * 8 + fr;
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const int jb = tj * 8 + 2 * fk + j;
+            if (ia < K1 && jb <= ia) {
+              double v = (j ? c1 : c0) * scale;
+              if (ia != jb) v *= 1.41421356237309504880;
+              w.p[l + L1 * (ia * (ia + 1) / 2 + jb)] = v;
+              loc += v * v;
+            }
+          }
+        }
+    }
+  }
+  const double nrm = sqrt(warp_sum(loc));  // :8450-8451
+  __syncwarp();
+  const double inv = sp->normalise ? 1.0 / nrm : 1.0;
+  double* xr = x + (size_t)c * d_pad;
+  for (int q = lane; q < d_pad; q += 32) xr[q] = q < d - 1 ? w.p[q] * inv : (q == d - 1 ? sp->sigma0 : 0.0);
+  if (lane == 0) pnorm[c] = nrm;
 }
 
 // One tile of up to 8 neighbours (all of species sk) of the adjoint, run by ONE warp entirely in registers:
@@ -906,8 +1280,10 @@ void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres
   *launches += 1;
 #define GO(N, L, S)                                                                                                       \
   if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                  \
-    cudaFuncSetAttribute(k_soap_forward<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                   \
-    k_soap_forward<N, L, S><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm); \
+    const size_t smw = carve_w(make_geo(N, L, S), h.d_pad, false, 0, nullptr, nullptr);                                    \
+    cudaFuncSetAttribute(k_soap_forward_w<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);                \
+    k_soap_forward_w<N, L, S><<<(n_centres + NW - 1) / NW, NT, smw, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, \
+                                                                         xlm, pnorm);                                      \
     return;                                                                                                                \
   }
   SOAP_SPECIALISATIONS(GO)
