@@ -121,8 +121,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
 #pragma unroll
     for (int j = 0; j < NTL; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  // K range of this split (blockIdx.z of gridDim.z), in BK slabs
-  const int KT_all = K / BK;
+  // K range of this split (blockIdx.z of gridDim.z), in BK slabs.  K is a multiple of 4 (one DMMA k-step), not of BK:
+  // the last slab is loaded whole (both operands are zero-padded to a multiple of BK) but only its first
+  // nk_last k-steps are multiplied.
+  const int KT_all = (K + BK - 1) / BK;
+  const int nk_last = ((K - 1) % BK) / 4 + 1;
   const int kt_beg = (int)((long long)KT_all * blockIdx.z / gridDim.z), kt_end = (int)((long long)KT_all * (blockIdx.z + 1) / gridDim.z);
   const int KT = kt_end - kt_beg;
   // per-thread copy addresses (see load_stage)
@@ -160,8 +163,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
     }
     const double* as = As + (size_t)(kt % STAGES) * BM * LDS_ROW + (wm * WTM + fr) * LDS_ROW + fk;
     const double* bs = Bs + (size_t)(kt % STAGES) * BN * LDS_ROW + (wn * WTN + fr) * LDS_ROW + fk;
+    const int nk = (kt_beg + kt == KT_all - 1) ? nk_last : BK / 4;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; kk++) {
+      if (kk >= nk) break;
       double af[MT], bf[NTL];
 #pragma unroll
       for (int i = 0; i < MT; i++) af[i] = as[i * 8 * LDS_ROW + kk * 4];
@@ -242,22 +247,48 @@ __global__ void k_energy_rows(const double* __restrict__ epart, int n_tiles_n, c
 
 }  // namespace
 
-void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int row0, const int* n_rows_dev, int M_pad,
-                      int K_pad, const double* w, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n, cudaStream_t st,
+// Column tile of GEMM-1 for n_rows_pad rows and M sparse points.  All tiles of one launch cost the same, so the launch
+// takes ceil(tiles / slots) rounds of (bn + fixed) each: 4,096 centres x 2,000 sparse points are 1,024 tiles of 128
+// columns = 3.46 rounds on the 296 CTA slots (4 paid), but 1,152 tiles of 112 columns = 3.89 rounds of 7/8 the length.
+int cov_gemm1_bn(int n_rows_pad, int M, int n_sm) {
+  const int cand[4] = {128, 112, 96, 80};
+  const long slots = 2L * n_sm, row_tiles = n_rows_pad / BM;
+  int best = 128;
+  double best_cost = 1e300;
+  for (int c = 0; c < 4; c++) {
+    const int bn = cand[c];
+    const long tiles = row_tiles * ((M + bn - 1) / bn), rounds = (tiles + slots - 1) / slots;
+    // per-tile cost model: main loop ~ bn columns, + prologue/epilogue and the A-operand share that does not shrink with bn
+    const double cost = (double)rounds * (bn + 24.0);
+    if (cost < best_cost * 0.98) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int row0, const int* n_rows_dev, int bn, int M,
+                      int K, const double* w, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n, cudaStream_t st,
                       int* launches) {
-  constexpr int BN = COV_BN1;
-  dim3 grid(M_pad / BN, n_rows_pad / BM, 1);
-  auto go = [&](auto e) {
+  auto go = [&](auto bn_tag, auto e) {
+    constexpr int BN = decltype(bn_tag)::value;
     using E = decltype(e);
+    dim3 grid((M + BN - 1) / BN, n_rows_pad / BM, 1);
     cudaFuncSetAttribute(k_dgemm_nt<BN, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<BN>());
-    k_dgemm_nt<BN, E><<<grid, NTHREADS, gemm_smem<BN>(), st>>>(x, ldx, sp_rows, lds, K_pad, row0, n_rows_dev, e);
+    k_dgemm_nt<BN, E><<<grid, NTHREADS, gemm_smem<BN>(), st>>>(x, ldx, sp_rows, lds, K, row0, n_rows_dev, e);
   };
-  switch (cp.zeta_int) {
-    case 1: go(EpiCov<1>{w, cp, acoef, lda, epart, n_tiles_n}); break;
-    case 2: go(EpiCov<2>{w, cp, acoef, lda, epart, n_tiles_n}); break;
-    case 3: go(EpiCov<3>{w, cp, acoef, lda, epart, n_tiles_n}); break;
-    case 4: go(EpiCov<4>{w, cp, acoef, lda, epart, n_tiles_n}); break;
-    default: go(EpiCov<0>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+  auto by_zeta = [&](auto bn_tag) {
+    switch (cp.zeta_int) {
+      case 1: go(bn_tag, EpiCov<1>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+      case 2: go(bn_tag, EpiCov<2>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+      case 3: go(bn_tag, EpiCov<3>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+      case 4: go(bn_tag, EpiCov<4>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+      default: go(bn_tag, EpiCov<0>{w, cp, acoef, lda, epart, n_tiles_n}); break;
+    }
+  };
+  switch (bn) {
+    case 112: by_zeta(std::integral_constant<int, 112>{}); break;
+    case 96: by_zeta(std::integral_constant<int, 96>{}); break;
+    case 80: by_zeta(std::integral_constant<int, 80>{}); break;
+    default: by_zeta(std::integral_constant<int, 128>{}); break;
   }
   *launches += 1;
 }
@@ -280,15 +311,15 @@ int cov_gemm2_ksplit(int n_rows_pad, int dn_pad, int bn, int n_sm) {  // K split
 }
 
 void launch_cov_gemm2(const double* acoef, int lda, const double* st_rows, int ldst, int n_rows_pad, int row0, const int* n_rows_dev, int dn_pad,
-                      int bn, int ksplit, int K_pad, double* gvec, int ldg, size_t split_stride, cudaStream_t st, int* launches) {
+                      int bn, int ksplit, int K, double* gvec, int ldg, size_t split_stride, cudaStream_t st, int* launches) {
   EpiStore e{gvec, ldg, split_stride};
   dim3 grid(dn_pad / bn, n_rows_pad / BM, ksplit);
   if (bn == 112) {
     cudaFuncSetAttribute(k_dgemm_nt<112, EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<112>());
-    k_dgemm_nt<112, EpiStore><<<grid, NTHREADS, gemm_smem<112>(), st>>>(acoef, lda, st_rows, ldst, K_pad, row0, n_rows_dev, e);
+    k_dgemm_nt<112, EpiStore><<<grid, NTHREADS, gemm_smem<112>(), st>>>(acoef, lda, st_rows, ldst, K, row0, n_rows_dev, e);
   } else {
     cudaFuncSetAttribute(k_dgemm_nt<128, EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128>());
-    k_dgemm_nt<128, EpiStore><<<grid, NTHREADS, gemm_smem<128>(), st>>>(acoef, lda, st_rows, ldst, K_pad, row0, n_rows_dev, e);
+    k_dgemm_nt<128, EpiStore><<<grid, NTHREADS, gemm_smem<128>(), st>>>(acoef, lda, st_rows, ldst, K, row0, n_rows_dev, e);
   }
   *launches += 1;
 }
