@@ -77,7 +77,6 @@ struct NeighbourWork {  // device scratch owned by the potential handle; sized f
   int* sort_idx = nullptr;     // [N] atom ids sorted by cell (stable)
   int* iota = nullptr;         // [N]
   int* keys_tmp = nullptr;     // [N]
-  int* cell_count = nullptr;   // [ncell+1]
   int* cell_start = nullptr;   // [ncell+1]
   double* spos = nullptr;      // [N][3] positions in sorted order
   int* smshift = nullptr;      // [N]
@@ -91,11 +90,15 @@ size_t neighbour_cub_bytes(int N, int ncell);
 void launch_frac_minmax(const double* pos, int N, const double* g9_dev_unused, const CellGrid& grid, double* minmax6, cudaStream_t st, int* launches);
 void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell, NeighbourWork& w, cudaStream_t st, int* launches);
 // rows are built only for the centres [first, last) (the partition of this handle); other rows are empty
-void launch_neigh_count(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, cudaStream_t st,
-                        int* launches);
-// cap = capacity (entries) of nbr_j / nbr_s: entries beyond it are dropped (speculative sizing, verified by the host afterwards)
-void launch_neigh_fill(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, const int* nbr_off, int* nbr_j,
+// exact layout: count (+ the largest row -> *max_row), exclusive scan into nbr_off[N+1], fill packed CSR rows (nbr_end = nbr_off + 1)
+void launch_neigh_count(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, int* max_row,
+                        cudaStream_t st, int* launches);
+void launch_neigh_fill(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, int* nbr_j,
                        int* nbr_s, double* nbr_d, int cap, cudaStream_t st, int* launches);
+// speculative layout: ONE pass into rows of row_cap entries at (i - first) * row_cap; entries beyond the capacity are dropped
+// and *max_row (> row_cap) tells the host to repeat the call with the exact layout
+void launch_neigh_onepass(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, int* nbr_end,
+                          int* nbr_j, int* nbr_s, int row_cap, int* max_row, cudaStream_t st, int* launches);
 
 // ---- soap.cu -------------------------------------------------------------------------------
 void launch_select_centres(const int* Z, int first, int last, const SoapDev* sp, int* flags, cudaStream_t st, int* launches);
@@ -103,11 +106,11 @@ void launch_compact(const int* flags_scan, const int* flags, int first, int n, i
 size_t soap_forward_smem(const SoapDev& h);
 size_t soap_adjoint_smem(const SoapDev& h);
 // n_centres_dev: device int holding the number of centres (the grid is sized by the host-side upper bound n_centres_ub)
-void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off,
+void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, double* x, double* xlm, double* pnorm,
                          cudaStream_t st, int* launches);
 // epart/n_tiles_n/local_e: if epart != NULL the kernel also folds the GEMM-1 row sums into local_e (E_i)
-void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off,
+void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
                          const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
                          double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st,
@@ -119,20 +122,25 @@ struct CovParams {
   double zeta;
   int zeta_int;    // >=0: integer fast path (fast_pow_1d), -1: general pow
 };
-constexpr int COV_BM = 64, COV_BN1 = 128, COV_BK = 16, COV_MAX_KSPLIT = 4;
+constexpr int COV_BM = 64, COV_BN1_MAX = 128, COV_BK = 16, COV_MAX_KSPLIT = 4;
 // GEMM-1 + epilogue: c = X S^T ; k = delta^2 c^zeta cutoff_s ; acoef = alpha_s delta^2 zeta c^(zeta-1) cutoff_s ;
 // epart[row][n_tile] = sum over the tile's columns of alpha_s k
 // n_rows_dev (may be NULL): device int, tiles whose first row is >= *n_rows_dev are skipped
 // w[M_pad] = alpha_s * sparseCutoff_s * delta^2 (0 in the padding)
-void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int row0, const int* n_rows_dev, int M_pad,
-                      int K_pad, const double* w, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n, cudaStream_t st,
+// bn = column tile (cov_gemm1_bn: 128, 112, 96 or 80, whichever wastes the fewest CTA slots of the last round);
+// n_tiles_n = ceil(M / bn); sp_rows, w and acoef are allocated M_pad >= M + 127 wide so that any tiling stays in bounds.
+// K = descriptor dimension rounded up to 4 (operand rows are zero-padded to a multiple of COV_BK).
+int cov_gemm1_bn(int n_rows_pad, int M, int n_sm);
+void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, int n_rows_pad, int row0, const int* n_rows_dev, int bn, int M,
+                      int K, const double* w, CovParams cp, double* acoef, int lda, double* epart, int n_tiles_n, cudaStream_t st,
                       int* launches);
 // GEMM-2: gvec[split] = acoef[:, K range of split] S   (S given transposed: st_rows[q][s]); column tile bn (112 or 128),
 // ksplit partial outputs split_stride doubles apart
 int cov_gemm2_bn(int d);
 int cov_gemm2_ksplit(int n_rows_pad, int dn_pad, int bn, int n_sm);
 void launch_cov_gemm2(const double* acoef, int lda, const double* st_rows, int ldst, int n_rows_pad, int row0, const int* n_rows_dev, int dn_pad,
-                      int bn, int ksplit, int K_pad, double* gvec, int ldg, size_t split_stride, cudaStream_t st, int* launches);
+                      int bn, int ksplit, int K /* sparse points rounded up to 4 */, double* gvec, int ldg, size_t split_stride, cudaStream_t st,
+                      int* launches);
 void launch_energy_rows(const double* epart, int n_tiles_n, const int* centres, const int* n_centres_dev, int n_centres_ub, double e_scale,
                         double* local_e, cudaStream_t st, int* launches);
 
@@ -144,7 +152,7 @@ struct Pair2bDev {
   const double* alpha;    // [M]
   const double* scut;     // [M]
 };
-void launch_pair2b(Pair2bDev p, int first, int last, const int* nbr_off, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z,
+void launch_pair2b(Pair2bDev p, int first, int last, const int* nbr_off, const int* nbr_end, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z,
                    Lattice9 lat, double e_scale, int do_grad, double* local_e, double* force, double* vir_part, double* local_virial,
                    cudaStream_t st, int* launches, int* n_blocks_out);
 

@@ -3,10 +3,14 @@
 //
 // Design (B200-first, not the reference's linked lists): atoms are binned into a cell grid with
 // cell width >= cutoff, sorted by cell with a stable radix sort (order inside a cell = ascending atom
-// index, so everything downstream is deterministic), and one WARP per atom -- lanes sweep the
-// candidates of the (2R+1)^3 surrounding cells 32 at a time -- scans them twice (count, exclusive
-// scan, fill) into a CSR list holding the FULL list (both directions; the reference stores a half
-// list plus back references).
+// index, so everything downstream is deterministic; the cell ranges are read off the sorted keys, no
+// counting pass), and one WARP per atom -- lanes sweep the candidates of the (2R+1)^3 surrounding
+// cells 32 at a time -- writes the FULL list (both directions; the reference stores a half list plus
+// back references) in one of two row layouts:
+//   exact       count, exclusive scan, fill -> packed CSR rows (first call for a geometry, stage-level entry points)
+//   speculative ONE pass into fixed-capacity rows (row capacity = largest row of the previous call + 25 %), no
+//               count / scan; the largest row comes back asynchronously and the host verifies it afterwards.
+// Consumers read a row as [nbr_off[i], nbr_end[i]) in both layouts.
 //
 // Bit-exactness: the accept test d < cutoff uses the reference's operation order without FMA
 // (image_diff/norm_nofma in gap_device.cuh), on the ORIGINAL positions and the total integer shift
@@ -60,7 +64,7 @@ __global__ void k_minmax_final(const double* __restrict__ part, int nb, double* 
 // err_flag: set when an atom lies more than MAX_MAP_SHIFT periodic images away from the cell (shifts are carried as int8)
 constexpr int MAX_MAP_SHIFT = 60;
 __global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int* __restrict__ cell_of, int* __restrict__ mshift,
-                      int* __restrict__ cell_count, int* __restrict__ iota, int* __restrict__ err_flag) {
+                      int* __restrict__ iota, int* __restrict__ err_flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double t[3];
@@ -85,13 +89,19 @@ __global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int*
   cell_of[i] = cell;
   mshift[i] = pack_shift(ms[0], ms[1], ms[2]);
   iota[i] = i;
-  atomicAdd(&cell_count[cell], 1);
 }
 
-__global__ void k_gather_sorted(const double* __restrict__ pos, const int* __restrict__ mshift, const int* __restrict__ sort_idx, int N,
-                                double* __restrict__ spos, int* __restrict__ smshift) {
+// positions in cell-sorted order, and the cell ranges from the sorted keys: cell_start[c] = first sorted slot whose
+// key is >= c (every thread fills the cells between its predecessor's key and its own; cell_start[ncell] = N)
+__global__ void k_gather_sorted(const double* __restrict__ pos, const int* __restrict__ mshift, const int* __restrict__ sort_idx,
+                                const int* __restrict__ sort_keys, int N, int ncell, double* __restrict__ spos, int* __restrict__ smshift,
+                                int* __restrict__ cell_start) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
+  const int key = sort_keys[p], prev = p > 0 ? sort_keys[p - 1] : -1;
+  for (int c = prev + 1; c <= key; c++) cell_start[c] = p;
+  if (p == N - 1)
+    for (int c = key + 1; c <= ncell; c++) cell_start[c] = N;
   int i = sort_idx[p];
   spos[3 * (size_t)p + 0] = pos[3 * (size_t)i + 0];
   spos[3 * (size_t)p + 1] = pos[3 * (size_t)i + 1];
@@ -107,19 +117,25 @@ __device__ __forceinline__ int floor_div(int a, int n) { return (a >= 0) ? a / n
 // pairs are written in candidate order through ballot/popc, so the list order is deterministic: cells in (o2,o1,o0)
 // order, ascending atom index inside a cell.
 constexpr int NEIGH_WARPS = 4;
+// MODE 0: count (nn[i], largest row -> *max_row) ; 1: fill packed CSR rows at nbr_off[i] ; 2: one pass into rows of
+// fixed capacity row_cap at (i - first) * row_cap, writing nbr_off[i] / nbr_end[i] and the largest row
+enum { NEIGH_COUNT = 0, NEIGH_FILL = 1, NEIGH_ONEPASS = 2 };
 
-template <bool FILL>
+template <int MODE>
 __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, int last, CellGrid grid, const int* __restrict__ sort_idx,
                                                             const int* __restrict__ sort_keys, const double* __restrict__ spos,
                                                             const int* __restrict__ smshift, const int* __restrict__ cell_start,
-                                                            int* __restrict__ nn, const int* __restrict__ nbr_off, int* __restrict__ nbr_j,
-                                                            int* __restrict__ nbr_s, double* __restrict__ nbr_d, int cap) {
+                                                            int* __restrict__ nn, int* __restrict__ nbr_off, int* __restrict__ nbr_end,
+                                                            int* __restrict__ nbr_j, int* __restrict__ nbr_s, double* __restrict__ nbr_d, int cap,
+                                                            int row_cap, int* __restrict__ max_row) {
+  constexpr bool FILL = MODE != NEIGH_COUNT;
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * NEIGH_WARPS + (threadIdx.x >> 5);
   if (p >= N) return;
   const int i = sort_idx[p];
   if (i < first || i >= last) {  // not a centre of this partition (descriptor_atomic_MPI_setup mask): empty row
-    if (!FILL && lane == 0) nn[i] = 0;
+    if (MODE == NEIGH_COUNT && lane == 0) nn[i] = 0;
+    if (MODE == NEIGH_ONEPASS && lane == 0) nbr_off[i] = nbr_end[i] = 0;
     return;
   }
   const int cell = sort_keys[p];
@@ -131,7 +147,9 @@ __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, in
   const int n_nb_cells = w0 * w1 * w2;
   const double cutoff = grid.cutoff;
   int count = 0;
-  int wpos = FILL ? nbr_off[i] : 0;
+  const int row_beg = MODE == NEIGH_FILL ? nbr_off[i] : (MODE == NEIGH_ONEPASS ? (i - first) * row_cap : 0);
+  if (MODE == NEIGH_ONEPASS) cap = row_beg + row_cap;  // a fixed-capacity row ends where the next one begins
+  int wpos = row_beg;
   for (int cbase = 0; cbase < n_nb_cells; cbase += 32) {
     // lane -> one neighbouring cell
     int ck = cbase + lane, qb = 0, cnt = 0, sh = 0;
@@ -186,7 +204,7 @@ __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, in
       const unsigned bal = __ballot_sync(0xffffffffu, acc);
       if (FILL && acc) {
         int w = wpos + __popc(bal & ((1u << lane) - 1u));
-        if (w < cap) {  // cap < total only when a speculatively sized list overflowed; the host then repeats the call
+        if (w < cap) {  // only a speculatively sized row can overflow; the host then repeats the call with the exact layout
           nbr_j[w] = sort_idx[q];
           nbr_s[w] = pack_shift(t0, t1, t2);
           if (nbr_d) nbr_d[w] = d;
@@ -196,18 +214,25 @@ __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, in
       count += __popc(bal);
     }
   }
-  if (!FILL && lane == 0) nn[i] = count;
+  if (lane == 0) {
+    if (MODE == NEIGH_COUNT) nn[i] = count;
+    if (MODE == NEIGH_ONEPASS) {
+      nbr_off[i] = row_beg;
+      nbr_end[i] = row_beg + (count < row_cap ? count : row_cap);
+    }
+    // largest row: the plain read keeps all but a handful of warps away from the atomic
+    if (MODE != NEIGH_FILL && count > *(volatile int*)max_row) atomicMax(max_row, count);
+  }
 }
 
 }  // namespace
 
 size_t neighbour_cub_bytes(int N, int ncell) {
-  size_t a = 0, b = 0, c = 0;
+  (void)ncell;
+  size_t a = 0, c = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, a, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, N);
-  cub::DeviceScan::ExclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, ncell + 1);
   cub::DeviceScan::ExclusiveSum(nullptr, c, (int*)nullptr, (int*)nullptr, N + 1);
-  size_t m = a > b ? a : b;
-  return (m > c ? m : c) + 256;
+  return (a > c ? a : c) + 256;
 }
 
 void launch_frac_minmax(const double* pos, int N, const double*, const CellGrid& grid, double* minmax6, cudaStream_t st, int* launches) {
@@ -221,36 +246,43 @@ void launch_frac_minmax(const double* pos, int N, const double*, const CellGrid&
 }
 
 void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell, NeighbourWork& w, cudaStream_t st, int* launches) {
-  cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (ncell + 1), st);
   int nb = (N + 255) / 256;
-  k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.cell_count, w.iota, w.err_flag);
-  size_t bytes = w.cub_bytes;
-  cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.cell_count, w.cell_start, ncell + 1, st);
+  k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.iota, w.err_flag);
   int bits = 1;
   while ((1 << bits) < ncell && bits < 31) bits++;
-  bytes = w.cub_bytes;
+  size_t bytes = w.cub_bytes;
   cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.cell_of, w.sort_keys, w.iota, w.sort_idx, N, 0, bits, st);
-  k_gather_sorted<<<nb, 256, 0, st>>>(pos, w.mshift, w.sort_idx, N, w.spos, w.smshift);
-  *launches += 4;
+  k_gather_sorted<<<nb, 256, 0, st>>>(pos, w.mshift, w.sort_idx, w.sort_keys, N, ncell, w.spos, w.smshift, w.cell_start);
+  *launches += 3;
 }
 
-void launch_neigh_count(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, cudaStream_t st,
-                        int* launches) {
+void launch_neigh_count(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, int* max_row,
+                        cudaStream_t st, int* launches) {
   (void)pos;
   int nb = (N + NEIGH_WARPS - 1) / NEIGH_WARPS;
-  k_neigh<false><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nullptr, nullptr, nullptr,
-                                     nullptr, 0);
+  k_neigh<NEIGH_COUNT><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nullptr,
+                                                        nullptr, nullptr, nullptr, nullptr, 0, 0, max_row);
   cudaMemsetAsync(w.nn + N, 0, sizeof(int), st);
   size_t bytes = w.cub_bytes;
   cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.nn, nbr_off, N + 1, st);
   *launches += 2;
 }
 
-void launch_neigh_fill(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, const int* nbr_off, int* nbr_j,
+void launch_neigh_fill(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, int* nbr_j,
                        int* nbr_s, double* nbr_d, int cap, cudaStream_t st, int* launches) {
   (void)pos;
   int nb = (N + NEIGH_WARPS - 1) / NEIGH_WARPS;
-  k_neigh<true><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nbr_off, nbr_j, nbr_s, nbr_d, cap);
+  k_neigh<NEIGH_FILL><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nbr_off,
+                                                       nullptr, nbr_j, nbr_s, nbr_d, cap, 0, nullptr);
+  *launches += 1;
+}
+
+void launch_neigh_onepass(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, int* nbr_end,
+                          int* nbr_j, int* nbr_s, int row_cap, int* max_row, cudaStream_t st, int* launches) {
+  (void)pos;
+  int nb = (N + NEIGH_WARPS - 1) / NEIGH_WARPS;
+  k_neigh<NEIGH_ONEPASS><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn,
+                                                          nbr_off, nbr_end, nbr_j, nbr_s, nullptr, 0, row_cap, max_row);
   *launches += 1;
 }
 

@@ -24,7 +24,7 @@ __device__ __forceinline__ double wsum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int last, const int* __restrict__ nbr_off,
+__global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int last, const int* __restrict__ nbr_off, const int* __restrict__ nbr_end,
                                                      const int* __restrict__ nbr_j, const int* __restrict__ nbr_s,
                                                      const double* __restrict__ pos, const int* __restrict__ Z, Lattice9 lat, double e_scale,
                                                      int do_grad, double* __restrict__ local_e, double* __restrict__ force,
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int
     const int Zi = Z[i];
     const bool Zi1 = (p.Z1 == 0) || (Zi == p.Z1), Zi2 = (p.Z2 == 0) || (Zi == p.Z2);
     if (Zi1 || Zi2) {
-      for (int q = nbr_off[i] + lane; q < nbr_off[i + 1]; q += 32) {
+      for (int q = nbr_off[i] + lane; q < nbr_end[i]; q += 32) {
         int j = nbr_j[q], s0, s1, s2;
         unpack_shift(nbr_s[q], s0, s1, s2);
         double dd[3];
@@ -111,14 +111,14 @@ __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int
 }
 }  // namespace
 
-void launch_pair2b(Pair2bDev p, int first, int last, const int* nbr_off, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z,
+void launch_pair2b(Pair2bDev p, int first, int last, const int* nbr_off, const int* nbr_end, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z,
                    Lattice9 lat, double e_scale, int do_grad, double* local_e, double* force, double* vir_part, double* local_virial,
                    cudaStream_t st, int* launches, int* n_blocks_out) {
   int n = last - first;
   int nb = (n + WPB - 1) / WPB;
   *n_blocks_out = nb;
   if (nb <= 0) return;
-  k_pair2b<<<nb, WPB * 32, 0, st>>>(p, first, last, nbr_off, nbr_j, nbr_s, pos, Z, lat, e_scale, do_grad, local_e, force, vir_part,
+  k_pair2b<<<nb, WPB * 32, 0, st>>>(p, first, last, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, e_scale, do_grad, local_e, force, vir_part,
                                     local_virial);
   *launches += 1;
 }

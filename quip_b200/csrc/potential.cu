@@ -84,25 +84,27 @@ struct gap_potential {
   int rank = 0, n_ranks = 1;
   int n_sm = 148;
   int g_splits = 1;            // K splits of the last GEMM-2 (partial gvec buffers)
+  int g_tiles_n = 1;           // column tiles of the last GEMM-1 (partial energies per row in epart)
   size_t g_split_stride = 0;
   // speculative neighbour-list sizing: the entry count of the previous call sizes the buffers of the next one, the
   // real count comes back asynchronously (pinned) and is verified after the final synchronisation of the call
-  int* h_pin = nullptr;        // pinned [2]: entry count, error flag
-  long nnz_hint = -1;
+  int* h_pin = nullptr;        // pinned [3]: entry count (exact layout only), error flag, largest row
+  int row_hint = -1;           // largest neighbour row of the previous call with the same (N, first, last)
   int hint_N = -1, hint_first = -1, hint_last = -1;
   bool pending_check = false;
-  long pending_cap = 0;
+  long pending_cap = 0;        // row capacity of the speculative layout in flight
   unsigned int* d_fin_counter = nullptr;
   // neighbour list the descriptor kernels read: the handle's own (build_connect) or one supplied by the caller (LAMMPS entry)
-  const int *cv_off = nullptr, *cv_j = nullptr, *cv_s = nullptr;
+  // (row i = entries [cv_off[i], cv_end[i]); cv_end = cv_off + 1 for packed CSR rows)
+  const int *cv_off = nullptr, *cv_end = nullptr, *cv_j = nullptr, *cv_s = nullptr;
   DevBuf b_xoff, b_xj, b_xs, b_zc;  // device copies of an external list and of the centre mask
   long launches = 0;
   double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   // neighbour list state
   NeighbourWork nw;
-  DevBuf b_cell_of, b_mshift, b_keys, b_idx, b_iota, b_ccount, b_cstart, b_spos, b_smshift, b_nn, b_cub, b_minmax;
-  DevBuf b_off, b_j, b_s, b_d;
+  DevBuf b_cell_of, b_mshift, b_keys, b_idx, b_iota, b_cstart, b_spos, b_smshift, b_nn, b_cub, b_minmax;
+  DevBuf b_off, b_end, b_j, b_s, b_d;
   int conn_N = 0, conn_nnz = 0;
   // inputs / outputs owned for the host-pointer API
   DevBuf b_pos, b_Z, b_packed, b_le, b_lv;
@@ -121,18 +123,18 @@ namespace {
 // ---------------------------------------------------------------------------------------------------
 constexpr int FIN_BLOCKS = 128, FIN_THREADS = 256;
 
-// One kernel: per-block partial sums, and the LAST block to finish (atomic ticket) adds the partials in block order,
-// so the totals are deterministic.
+// One kernel: per-block partial sums (warp shuffles, then one pass over the 8 warp rows), and the LAST block to finish
+// (atomic ticket) adds the partials in block order, so the totals are deterministic.
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict__ Z, int N, int first, int last, const double* __restrict__ e0,
                                                           double e_scale, double* __restrict__ local_e, const double* __restrict__ vir_part,
-                                                          int n_slots, double* __restrict__ part /* [FIN_BLOCKS][10] */,
+                                                          int n_slots, double* __restrict__ part /* [gridDim][10] */,
                                                           unsigned int* __restrict__ counter, double* __restrict__ packed,
-                                                          const int* __restrict__ nnz_dev, long cap) {
-  typedef cub::BlockReduce<double, FIN_THREADS> BR;
-  __shared__ typename BR::TempStorage tmp;
+                                                          const int* __restrict__ max_row_dev, long cap) {
+  __shared__ double wsum[FIN_THREADS / 32][10];
   __shared__ bool is_last;
+  const int stride = gridDim.x * FIN_THREADS;
   double v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int i = blockIdx.x * FIN_THREADS + threadIdx.x; i < N; i += FIN_BLOCKS * FIN_THREADS) {
+  for (int i = blockIdx.x * FIN_THREADS + threadIdx.x; i < N; i += stride) {
     double le = local_e[i];
     if (i >= first && i < last) {
       int z = Z[i];
@@ -141,18 +143,25 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict_
     }
     v[0] += le;
   }
-  for (int s = blockIdx.x * FIN_THREADS + threadIdx.x; s < n_slots; s += FIN_BLOCKS * FIN_THREADS)
+  for (int s = blockIdx.x * FIN_THREADS + threadIdx.x; s < n_slots; s += stride)
 #pragma unroll
     for (int k = 0; k < 9; k++) v[1 + k] += vir_part[9 * (size_t)s + k];
+#pragma unroll
   for (int k = 0; k < 10; k++) {
-    double t = BR(tmp).Sum(v[k]);
-    __syncthreads();
-    if (threadIdx.x == 0) part[10 * blockIdx.x + k] = t;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][k] = v[k];
   }
-  if (threadIdx.x == 0) {
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < FIN_THREADS / 32; w++) t += wsum[w][threadIdx.x];
+    part[10 * blockIdx.x + threadIdx.x] = t;
     __threadfence();
-    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
   __syncthreads();
   if (is_last) {
     __threadfence();
@@ -161,12 +170,52 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict_
       for (int b = 0; b < (int)gridDim.x; b++) t += __ldcg(&part[10 * b + threadIdx.x]);
       // a speculatively sized neighbour list that overflowed poisons the energy: after the all-reduce EVERY rank sees the NaN
       // and repeats the evaluation, with no extra collective
-      if (threadIdx.x == 0 && nnz_dev && (long)*nnz_dev > cap) t = __longlong_as_double(0x7ff8000000000000LL);
+      if (threadIdx.x == 0 && max_row_dev && (long)*max_row_dev > cap) t = __longlong_as_double(0x7ff8000000000000LL);
       packed[threadIdx.x] = t;
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
 }
+
+// zero the outputs of a calc in one launch: packed [E | virial | F], local_e, local_virial (may be NULL)
+__global__ void k_zero_outputs(double* __restrict__ a, size_t na, double* __restrict__ b, size_t nb, double* __restrict__ c, size_t nc) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t t = t0; t < na; t += stride) a[t] = 0.0;
+  for (size_t t = t0; t < nb; t += stride) b[t] = 0.0;
+  for (size_t t = t0; t < nc; t += stride) c[t] = 0.0;
+}
+
+// Centre selection of a SOAP coordinate for small partitions, ONE block: flag (descriptors.f95:7962), block scan and ordered
+// compaction, 4 atoms per thread and 4,096 per round; the count goes where the multi-kernel path leaves it (scan[n]).
+constexpr int SEL_THREADS = 1024, SEL_ITEMS = 4, SEL_MAX_N = 16384;
+__global__ void __launch_bounds__(SEL_THREADS) k_select_compact_block(const int* __restrict__ Z, int first, int last, const SoapDev* __restrict__ sp,
+                                                                       int* __restrict__ centres, int* __restrict__ count_out) {
+  typedef cub::BlockScan<int, SEL_THREADS> BS;
+  __shared__ typename BS::TempStorage tmp;
+  const int n = last - first, nZ = sp->n_Z;
+  int base = 0;
+  for (int t0 = 0; t0 < n; t0 += SEL_THREADS * SEL_ITEMS) {
+    int f[SEL_ITEMS], pos[SEL_ITEMS], total;
+#pragma unroll
+    for (int k = 0; k < SEL_ITEMS; k++) {
+      const int t = t0 + SEL_ITEMS * threadIdx.x + k;
+      f[k] = 0;
+      if (t < n) {
+        const int Zi = Z[first + t];
+        for (int q = 0; q < nZ; q++)
+          if (sp->centre_Z[q] == Zi || sp->centre_Z[q] == 0) f[k] = 1;
+      }
+    }
+    BS(tmp).ExclusiveSum(f, pos, total);
+#pragma unroll
+    for (int k = 0; k < SEL_ITEMS; k++)
+      if (f[k]) centres[base + pos[k]] = first + t0 + SEL_ITEMS * threadIdx.x + k;
+    base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count_out = base;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // velocity Verlet (advance_verlet1 / advance_verlet2, src/libAtoms/DynamicalSystem.f95:1814-2132, 2159-2383; plain atoms,
 // no thermostat / barostat / constraints):  v += a dt/2 ; x += v dt   |   a = f/m ; v += a dt/2
@@ -250,8 +299,10 @@ void inv3(const double* a, double* g) {  // column-major both
   g[2 + 3 * 2] = (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0)) / det;
 }
 
-// speculative = true: size the list from the previous call's entry count and do NOT wait for the real count (it arrives in
-// P->h_pin; verify_connect() checks it after the caller's final synchronisation).
+// speculative = true: if the previous call had the same (N, first, last), build the list in ONE pass into rows of fixed
+// capacity (largest row of that call + 25 %) and do NOT wait for anything: the largest row of this call arrives in
+// P->h_pin and verify_connect() checks it after the caller's final synchronisation.  Otherwise: exact packed CSR rows
+// (count, scan, one synchronisation for the entry count, fill).  Sets P->cv_off / cv_end / cv_j / cv_s.
 void build_connect(gap_potential* P, int N, int first, int last, const double* d_pos, const double* lattice, const int* pbc, double cutoff,
                    bool want_dist, bool speculative, cudaStream_t st) {
   P->pending_check = false;
@@ -259,9 +310,10 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   if (cutoff < 0.0) throw GapError("calc_connect: Negative cutoff radius " + std::to_string(cutoff));  // Connection.f95:1069
   P->conn_N = N;
   P->conn_nnz = 0;
-  P->b_off.ensure(sizeof(int) * (N + 2));
+  P->b_off.ensure(sizeof(int) * (N + 4));  // [0..N] row offsets, then: [N+1] error flag, [N+2] largest row
+  P->cv_off = P->b_off.as<int>(); P->cv_end = P->b_off.as<int>() + 1; P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
   if (N == 0 || cutoff == 0.0) {  // cutoff == 0: "don't compute neighbours" (:1079)
-    CUDA_OK(cudaMemsetAsync(P->b_off.p, 0, sizeof(int) * (N + 2), st));
+    CUDA_OK(cudaMemsetAsync(P->b_off.p, 0, sizeof(int) * (N + 4), st));
     return;
   }
   CellGrid grid;
@@ -362,7 +414,6 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   P->b_keys.ensure(sizeof(int) * N); w.sort_keys = P->b_keys.as<int>();
   P->b_idx.ensure(sizeof(int) * N); w.sort_idx = P->b_idx.as<int>();
   P->b_iota.ensure(sizeof(int) * N); w.iota = P->b_iota.as<int>();
-  P->b_ccount.ensure(sizeof(int) * (ncell + 2)); w.cell_count = P->b_ccount.as<int>();
   P->b_cstart.ensure(sizeof(int) * (ncell + 2)); w.cell_start = P->b_cstart.as<int>();
   P->b_spos.ensure(sizeof(double) * 3 * N); w.spos = P->b_spos.as<double>();
   P->b_smshift.ensure(sizeof(int) * N); w.smshift = P->b_smshift.as<int>();
@@ -370,31 +421,42 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   size_t cb = neighbour_cub_bytes(N, ncell);
   P->b_cub.ensure(cb); w.cub_tmp = P->b_cub.p; w.cub_bytes = P->b_cub.cap;
 
-  w.err_flag = P->b_off.as<int>() + N + 1;  // read back together with the entry count
-  CUDA_OK(cudaMemsetAsync(w.err_flag, 0, sizeof(int), st));
+  int* const stat = P->b_off.as<int>() + N;  // [0] entry count (written by the scan of the exact layout) [1] error flag [2] largest row
+  w.err_flag = stat + 1;
+  CUDA_OK(cudaMemsetAsync(stat, 0, 3 * sizeof(int), st));
   launch_bin_atoms(d_pos, N, grid, ncell, w, st, &launches);
-  launch_neigh_count(d_pos, N, first, last, grid, w, P->b_off.as<int>(), st, &launches);
-  CUDA_OK(cudaMemcpyAsync(P->h_pin, P->b_off.as<int>() + N, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  long cap;
-  if (speculative && !want_dist && P->nnz_hint >= 0 && P->hint_N == N && P->hint_first == first && P->hint_last == last) {
-    cap = P->nnz_hint + P->nnz_hint / 4 + 4096;
-    if (cap > 2147483000L) cap = 2147483000L;
-    P->pending_check = true;
-    P->pending_cap = cap;
-  } else {
-    CUDA_OK(cudaStreamSynchronize(st));
-    const int nnz = P->h_pin[0];
-    if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 60 periodic images away from the cell; wrap the positions first");
-    if (nnz < 0) throw GapError("calc_connect: neighbour list exceeds 2^31 entries");
-    P->conn_nnz = nnz;
-    P->nnz_hint = nnz; P->hint_N = N; P->hint_first = first; P->hint_last = last;
-    cap = nnz;
+  if (speculative && !want_dist && P->row_hint >= 0 && P->hint_N == N && P->hint_first == first && P->hint_last == last) {
+    const int row_cap = round_up(P->row_hint + P->row_hint / 4 + 8, 4);
+    const long cap = (long)row_cap * (last - first);
+    if (cap <= 2147483000L) {
+      P->b_end.ensure(sizeof(int) * (N + 1));
+      P->b_j.ensure(sizeof(int) * (size_t)(cap + 1));
+      P->b_s.ensure(sizeof(int) * (size_t)(cap + 1));
+      launch_neigh_onepass(d_pos, N, first, last, grid, w, P->b_off.as<int>(), P->b_end.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), row_cap,
+                           stat + 2, st, &launches);
+      CUDA_OK(cudaMemcpyAsync(P->h_pin, stat, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      P->pending_check = true;
+      P->pending_cap = row_cap;
+      P->cv_end = P->b_end.as<int>(); P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
+      P->launches += launches;
+      CUDA_OK(cudaGetLastError());
+      return;
+    }
   }
-  P->b_j.ensure(sizeof(int) * (size_t)(cap + 1));
-  P->b_s.ensure(sizeof(int) * (size_t)(cap + 1));
-  if (want_dist) P->b_d.ensure(sizeof(double) * (size_t)(cap + 1));
+  launch_neigh_count(d_pos, N, first, last, grid, w, P->b_off.as<int>(), stat + 2, st, &launches);
+  CUDA_OK(cudaMemcpyAsync(P->h_pin, stat, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  const int nnz = P->h_pin[0];
+  if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 60 periodic images away from the cell; wrap the positions first");
+  if (nnz < 0) throw GapError("calc_connect: neighbour list exceeds 2^31 entries");
+  P->conn_nnz = nnz;
+  P->row_hint = P->h_pin[2]; P->hint_N = N; P->hint_first = first; P->hint_last = last;
+  P->b_j.ensure(sizeof(int) * (size_t)(nnz + 1));
+  P->b_s.ensure(sizeof(int) * (size_t)(nnz + 1));
+  if (want_dist) P->b_d.ensure(sizeof(double) * (size_t)(nnz + 1));
   launch_neigh_fill(d_pos, N, first, last, grid, w, P->b_off.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), want_dist ? P->b_d.as<double>() : nullptr,
-                    (int)cap, st, &launches);
+                    nnz, st, &launches);
+  P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
   P->launches += launches;
   CUDA_OK(cudaGetLastError());
 }
@@ -403,12 +465,10 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
 bool verify_connect(gap_potential* P) {
   if (!P->pending_check) return true;
   P->pending_check = false;
-  const int nnz = P->h_pin[0];
   if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 60 periodic images away from the cell; wrap the positions first");
-  if (nnz < 0) throw GapError("calc_connect: neighbour list exceeds 2^31 entries");
-  P->conn_nnz = nnz;
-  const bool ok = nnz <= P->pending_cap;
-  P->nnz_hint = ok ? nnz : -1;  // overflow: the repeat takes the exact (synchronising) path
+  const int max_row = P->h_pin[2];
+  const bool ok = max_row <= P->pending_cap;
+  P->row_hint = ok ? max_row : -1;  // overflow: the repeat takes the exact (synchronising) path
   return ok;
 }
 
@@ -425,7 +485,7 @@ void upload_model(gap_potential* P) {
   const double pi = 3.14159265358979323846264338327950288;
   CUDA_OK(cudaMalloc(&P->d_fin_counter, sizeof(unsigned int)));
   CUDA_OK(cudaMemset(P->d_fin_counter, 0, sizeof(unsigned int)));
-  CUDA_OK(cudaHostAlloc((void**)&P->h_pin, 2 * sizeof(int), cudaHostAllocDefault));
+  CUDA_OK(cudaHostAlloc((void**)&P->h_pin, 4 * sizeof(int), cudaHostAllocDefault));
   CUDA_OK(cudaMalloc(&P->d_e0, sizeof(double) * 128));
   CUDA_OK(cudaMemcpy(P->d_e0, P->model.e0, sizeof(double) * 128, cudaMemcpyHostToDevice));
   for (const Coordinate& c : P->model.coord) {
@@ -463,7 +523,7 @@ void upload_model(gap_potential* P) {
       CUDA_OK(cudaMalloc(&cd.d_sp, sizeof(SoapDev)));
       CUDA_OK(cudaMemcpy(cd.d_sp, &h, sizeof(SoapDev), cudaMemcpyHostToDevice));
       cd.M = c.M;
-      cd.M_pad = round_up(c.M > 0 ? c.M : 1, COV_BN1);
+      cd.M_pad = round_up(c.M > 0 ? c.M : 1, COV_BK) + COV_BN1_MAX;  // any GEMM-1 column tiling (cov_gemm1_bn) stays in bounds
       cd.d_pad = h.d_pad;
       cd.bn2 = cov_gemm2_bn(s.d);
       cd.dn_pad = round_up(s.d, cd.bn2);
@@ -562,6 +622,11 @@ int select_centres(gap_potential* P, const CoordDev& cd, const int* d_Z, int fir
   P->b_flags.ensure(sizeof(int) * (n + 1));
   P->b_scan.ensure(sizeof(int) * (n + 1));
   P->b_centres.ensure(sizeof(int) * (n + 1));
+  if (n <= SEL_MAX_N) {
+    k_select_compact_block<<<1, SEL_THREADS, 0, st>>>(d_Z, first, last, cd.d_sp, P->b_centres.as<int>(), P->b_scan.as<int>() + n);
+    P->launches += 1;
+    return n;
+  }
   launch_select_centres(d_Z, first, last, cd.d_sp, P->b_flags.as<int>(), st, &launches);
   size_t cb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, cb, (int*)nullptr, (int*)nullptr, n + 1);
@@ -581,7 +646,7 @@ void soap_forward_stage(gap_potential* P, const CoordDev& cd, int n_ub, const do
   P->b_x.ensure(sizeof(double) * (size_t)nc_pad * cd.d_pad);
   P->b_xlm.ensure(sizeof(double) * (size_t)(n_ub > 0 ? n_ub : 1) * cd.h.nlm * cd.h.K1);
   P->b_pnorm.ensure(sizeof(double) * (size_t)nc_pad);
-  launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_j, P->cv_s, d_pos, d_Z, lat,
+  launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
                       P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
   P->launches += launches;
 }
@@ -591,11 +656,13 @@ void soap_forward_stage(gap_potential* P, const CoordDev& cd, int n_ub, const do
 void covariance_stage(gap_potential* P, const CoordDev& cd, int nc, const int* rows_dev, bool want_grad, bool allow_split, cudaStream_t st) {
   int launches = 0;
   int nc_pad = round_up(nc > 0 ? nc : 1, COV_BM);
-  int n_tiles_n = cd.M_pad / COV_BN1;
   size_t budget = (size_t)1 << 30;  // bytes of acoef kept live at once
   int chunk = (int)(budget / ((size_t)cd.M_pad * sizeof(double)) / COV_BM) * COV_BM;
   if (chunk < COV_BM) chunk = COV_BM;
   if (chunk > nc_pad) chunk = nc_pad;
+  const int Mr = cd.M > 0 ? cd.M : 1;
+  const int bn1 = cov_gemm1_bn(chunk, Mr, P->n_sm), n_tiles_n = (Mr + bn1 - 1) / bn1;
+  P->g_tiles_n = n_tiles_n;
   P->b_acoef.ensure(sizeof(double) * (size_t)chunk * cd.M_pad);
   P->b_epart.ensure(sizeof(double) * (size_t)nc_pad * n_tiles_n);
   int ksplit = allow_split ? cov_gemm2_ksplit(chunk, cd.dn_pad, cd.bn2, P->n_sm) : 1;
@@ -604,11 +671,11 @@ void covariance_stage(gap_potential* P, const CoordDev& cd, int nc, const int* r
   if (want_grad) P->b_gvec.ensure(sizeof(double) * (size_t)nc_pad * cd.dn_pad * ksplit);
   for (int r0 = 0; r0 < nc_pad; r0 += chunk) {
     int rows = std::min(chunk, nc_pad - r0);
-    launch_cov_gemm1(P->b_x.as<double>() + (size_t)r0 * cd.d_pad, cd.d_pad, cd.sp_rows, cd.d_pad, rows, r0, rows_dev, cd.M_pad, cd.d_pad,
+    launch_cov_gemm1(P->b_x.as<double>() + (size_t)r0 * cd.d_pad, cd.d_pad, cd.sp_rows, cd.d_pad, rows, r0, rows_dev, bn1, Mr, round_up(cd.h.d, 4),
                      cd.alpha, cd.cp, P->b_acoef.as<double>(), cd.M_pad, P->b_epart.as<double>() + (size_t)r0 * n_tiles_n, n_tiles_n, st, &launches);
     mark(P, st, ST_COV_GEMM1);
     if (want_grad) {
-      launch_cov_gemm2(P->b_acoef.as<double>(), cd.M_pad, cd.st_rows, cd.M_pad, rows, r0, rows_dev, cd.dn_pad, cd.bn2, ksplit, cd.M_pad,
+      launch_cov_gemm2(P->b_acoef.as<double>(), cd.M_pad, cd.st_rows, cd.M_pad, rows, r0, rows_dev, cd.dn_pad, cd.bn2, ksplit, round_up(Mr, 4),
                        P->b_gvec.as<double>() + (size_t)r0 * cd.dn_pad, cd.dn_pad, P->g_split_stride, st, &launches);
       mark(P, st, ST_COV_GEMM2);
     }
@@ -638,11 +705,10 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
     first = 0;
     last = ext->nlocal;
     d_Zc = ext->Zc;
-    P->cv_off = ext->off; P->cv_j = ext->j; P->cv_s = ext->s;
+    P->cv_off = ext->off; P->cv_end = ext->off + 1; P->cv_j = ext->j; P->cv_s = ext->s;
     P->pending_check = false;
   } else {
     build_connect(P, N, first, last, d_pos, lattice, pbc, P->model.cutoff, false, true, st);
-    P->cv_off = P->b_off.as<int>(); P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
   }
   mark(P, st, ST_CONNECT);
   Lattice9 lat;
@@ -653,9 +719,12 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
     P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
     d_le = P->b_le.as<double>();
   }
-  CUDA_OK(cudaMemsetAsync(d_packed, 0, sizeof(double) * (10 + 3 * (size_t)N), st));
-  CUDA_OK(cudaMemsetAsync(d_le, 0, sizeof(double) * (size_t)(N + 1), st));
-  if (d_lv) CUDA_OK(cudaMemsetAsync(d_lv, 0, sizeof(double) * 9 * (size_t)N, st));
+  {
+    const size_t nz = (d_lv ? 9 : 3) * (size_t)N + 10;
+    int zb = (int)std::min<size_t>((nz + 255) / 256, 2048);
+    k_zero_outputs<<<zb, 256, 0, st>>>(d_packed, 10 + 3 * (size_t)N, d_le, (size_t)N + (d_le_user ? 0 : 1), d_lv, d_lv ? 9 * (size_t)N : 0);
+    P->launches += 1;
+  }
   double* d_force = d_packed + 10;
   const double es = P->model.E_scale;
 
@@ -678,20 +747,20 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
         mark(P, st, ST_SOAP_FWD);
         covariance_stage(P, cd, nc, ncd, want_grad, true, st);
         if (want_grad) {
-          launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_j, P->cv_s, d_pos, d_Z, lat,
+          launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
                               P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, P->g_splits,
-                              P->g_split_stride, P->b_epart.as<double>(), cd.M_pad / COV_BN1, d_le, es, d_force,
+                              P->g_split_stride, P->b_epart.as<double>(), P->g_tiles_n, d_le, es, d_force,
                               P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches);
           slot += nc;
           mark(P, st, ST_SOAP_ADJ);
         } else {
-          launch_energy_rows(P->b_epart.as<double>(), cd.M_pad / COV_BN1, P->b_centres.as<int>(), ncd, nc, es, d_le, st, &launches);
+          launch_energy_rows(P->b_epart.as<double>(), P->g_tiles_n, P->b_centres.as<int>(), ncd, nc, es, d_le, st, &launches);
           mark(P, st, ST_OTHER);
         }
       }
     } else {
       int nb = 0;
-      launch_pair2b(cd.p2, first, last, P->cv_off, P->cv_j, P->cv_s, d_pos, d_Z, lat, es, want_grad ? 1 : 0, d_le,
+      launch_pair2b(cd.p2, first, last, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, es, want_grad ? 1 : 0, d_le,
                     want_grad ? d_force : nullptr, want_grad ? P->b_vir.as<double>() + 9 * slot : nullptr, want_grad ? d_lv : nullptr, st, &launches,
                     &nb);
       if (want_grad) slot += nb;
@@ -701,9 +770,11 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   }
   // totals
   P->b_fin.ensure(sizeof(double) * 10 * FIN_BLOCKS);
-  k_finalize<<<FIN_BLOCKS, FIN_THREADS, 0, st>>>(d_Zc, N, first, last, P->d_e0, es, d_le, want_grad ? P->b_vir.as<double>() : nullptr,
+  const size_t fin_work = std::max<size_t>((size_t)N, want_grad ? slot : 0);
+  const int fin_blocks = (int)std::min<size_t>(FIN_BLOCKS, std::max<size_t>(1, (fin_work + FIN_THREADS - 1) / FIN_THREADS));
+  k_finalize<<<fin_blocks, FIN_THREADS, 0, st>>>(d_Zc, N, first, last, P->d_e0, es, d_le, want_grad ? P->b_vir.as<double>() : nullptr,
                                                 want_grad ? (int)slot : 0, P->b_fin.as<double>(), P->d_fin_counter, d_packed,
-                                                P->pending_check ? P->b_off.as<int>() + N : nullptr, P->pending_cap);
+                                                P->pending_check ? P->b_off.as<int>() + N + 2 : nullptr, P->pending_cap);
   P->launches += 1;
   mark(P, st, ST_OTHER);
   CUDA_OK(cudaGetLastError());
@@ -767,7 +838,7 @@ void gap_potential_finalise(gap_potential* P) {
   cudaFree(P->d_e0);
   cudaFree(P->d_fin_counter);
   if (P->h_pin) cudaFreeHost(P->h_pin);
-  DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_ccount, &P->b_cstart, &P->b_spos, &P->b_smshift,
+  DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_cstart, &P->b_end, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
                     &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke};
@@ -1138,7 +1209,6 @@ int gap_descriptor_calc(gap_potential* P, int i_coord, int N, const double* pos,
     if (d_out) *d_out = cd.h.d;
     if (!x) return;
     build_connect(P, N, 0, N, P->b_pos.as<double>(), lattice, pbc, cd.h.cutoff, false, false, st);
-    P->cv_off = P->b_off.as<int>(); P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
     Lattice9 lat;
     for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
     soap_forward_stage(P, cd, n_ub, P->b_pos.as<double>(), P->b_Z.as<int>(), lat, st);
@@ -1171,7 +1241,7 @@ int gap_gp_predict(gap_potential* P, int i_coord, int n, const double* x, double
     CUDA_OK(cudaMemsetAsync(P->b_le.p, 0, sizeof(double) * (size_t)(n + 1), st));
     covariance_stage(P, cd, n, nullptr, grad != nullptr, false, st);
     int launches = 1;
-    launch_energy_rows(P->b_epart.as<double>(), cd.M_pad / COV_BN1, P->b_centres.as<int>(), nullptr, n, 1.0, P->b_le.as<double>(), st, &launches);
+    launch_energy_rows(P->b_epart.as<double>(), P->g_tiles_n, P->b_centres.as<int>(), nullptr, n, 1.0, P->b_le.as<double>(), st, &launches);
     P->launches += launches;
     if (e) CUDA_OK(cudaMemcpyAsync(e, P->b_le.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     if (grad)

@@ -501,7 +501,7 @@ __device__ __forceinline__ void forward_flush(double* X, const int XS, const int
 template <int CN, int CL, int CNS>
 __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
                                                         const int* __restrict__ n_centres_dev,
-                                                        const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
+                                                        const int* __restrict__ nbr_off, const int* __restrict__ nbr_end, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
                                                         const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
                                                         double* __restrict__ xlm, double* __restrict__ pnorm) {
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
   for (int k = threadIdx.x; k < g.XR * g.XS; k += NT) s.X[k] = 0.0;
   __syncthreads();
 
-  const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
+  const int pbeg = nbr_off[i], pend = nbr_end[i];
   for (int pb = pbeg; pb < pend; pb += NBCAP) {
     int nv = gather_neighbours(sp, s, ns, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
     for (int t0 = 0; t0 < nv; t0 += TNF) {
@@ -758,7 +758,7 @@ __device__ __forceinline__ Smem view_of(const WSmem& w) {
 template <int CN, int CL, int CNS>
 __global__ void __launch_bounds__(NT, (CN > 8 ? 2 : 4)) k_soap_forward_w(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
                                                                          const int* __restrict__ n_centres_dev,
-                                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
+                                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_end, const int* __restrict__ nbr_j,
                                                                          const int* __restrict__ nbr_s, const double* __restrict__ pos,
                                                                          const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
                                                                          double* __restrict__ xlm, double* __restrict__ pnorm) {
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(NT, (CN > 8 ? 2 : 4)) k_soap_forward_w(const S
       for (int nt = 0; nt < NTN; nt++) acc[t][nt][0] = acc[t][nt][1] = 0.0;
   };
   zero_acc();
-  const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
+  const int pbeg = nbr_off[i], pend = nbr_end[i];
   int fill = 0;
   for (int p0 = pbeg; p0 < pend; p0 += 32) {
     fill = gather_chunk_w<false>(sp, w, fill, i, p0, pend, nbr_j, nbr_s, pos, Z, lat, lane);
@@ -1080,7 +1080,7 @@ __device__ __forceinline__ void adjoint_tile(const Smem& s, const Geo& g, const 
 template <int CN, int CL, int CNS>
 __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
                                                         const int* __restrict__ n_centres_dev,
-                                                        const int* __restrict__ nbr_off, const int* __restrict__ nbr_j,
+                                                        const int* __restrict__ nbr_off, const int* __restrict__ nbr_end, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
                                                         const int* __restrict__ Z, Lattice9 lat, const double* __restrict__ x,
                                                         const double* __restrict__ xlm, const double* __restrict__ pnorm,
@@ -1210,7 +1210,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
   if (fk == 0)
 #pragma unroll
     for (int k = 0; k < 12; k++) accs[k] = 0.0;
-  const int pbeg = nbr_off[i], pend = nbr_off[i + 1];
+  const int pbeg = nbr_off[i], pend = nbr_end[i];
   for (int pb = pbeg; pb < pend; pb += NBCAP) {
     gather_neighbours(sp, s, ns, i, pb, min(pb + NBCAP, pend), nbr_j, nbr_s, pos, Z, lat);
     int tbase = 0;
@@ -1271,7 +1271,7 @@ void launch_compact(const int* flags_scan, const int* flags, int first, int n, i
   *launches += 1;
 }
 
-void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off,
+void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, double* x, double* xlm, double* pnorm,
                          cudaStream_t st, int* launches) {
   const int n_centres = n_centres_ub;
@@ -1282,17 +1282,17 @@ void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres
   if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                  \
     const size_t smw = carve_w(make_geo(N, L, S), h.d_pad, false, 0, nullptr, nullptr);                                    \
     cudaFuncSetAttribute(k_soap_forward_w<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);                \
-    k_soap_forward_w<N, L, S><<<(n_centres + NW - 1) / NW, NT, smw, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, \
+    k_soap_forward_w<N, L, S><<<(n_centres + NW - 1) / NW, NT, smw, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, \
                                                                          xlm, pnorm);                                      \
     return;                                                                                                                \
   }
   SOAP_SPECIALISATIONS(GO)
 #undef GO
   cudaFuncSetAttribute(k_soap_forward<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_soap_forward<0, 0, 0><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
+  k_soap_forward<0, 0, 0><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
 }
 
-void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off,
+void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
                          const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
                          double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st,
@@ -1304,7 +1304,7 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
 #define GO(N, L, S)                                                                                                                          \
   if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                                     \
     cudaFuncSetAttribute(k_soap_adjoint<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                      \
-    k_soap_adjoint<N, L, S><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, \
+    k_soap_adjoint<N, L, S><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, \
                                                        g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part,         \
                                                        local_virial);                                                                         \
     return;                                                                                                                                   \
@@ -1312,7 +1312,7 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
   SOAP_SPECIALISATIONS(GO)
 #undef GO
   cudaFuncSetAttribute(k_soap_adjoint<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_soap_adjoint<0, 0, 0><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
+  k_soap_adjoint<0, 0, 0><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
                                                      g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);
 }
 
