@@ -418,18 +418,30 @@ class ShardedPotential:
                 self.calc_resident(N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad)
             cur.wait_stream(self.stream)
             return
-        # enqueue the evaluation AND the collective, synchronise once, then check the speculatively sized neighbour list
         for _ in range(2):
-            self.pot.calc_device_enqueue(N, d_pos.data_ptr(), d_Z.data_ptr(), lattice9, pbc3, d_packed.data_ptr(), want_grad=want_grad,
-                                         stream_ptr=cur.cuda_stream)
-            self.reduce_packed(d_packed)
-            # a rank whose list overflowed has poisoned its energy with NaN (k_finalize): after the reduction every rank sees it, so
-            # all ranks repeat together without an extra collective
-            self._h_e.copy_(d_packed[:1], non_blocking=True)
-            cur.synchronize()
-            ok = self.pot.calc_device_verify()
-            if ok and not bool(torch.isnan(self._h_e[0])):
+            self.calc_resident_enqueue(N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad)
+            if self.calc_resident_finish():
                 break
+
+    def calc_resident_enqueue(self, N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad=True):
+        """First half of :meth:`calc_resident`: enqueue the evaluation, the collective and the read-back of the energy word
+        on torch's current (non-default) stream and return without waiting."""
+        cur = self.torch.cuda.current_stream(self.device)
+        if cur.cuda_stream == 0:
+            raise RuntimeError("calc_resident_enqueue needs a real current stream (torch.cuda.set_stream(sp.stream))")
+        self.pot.calc_device_enqueue(N, d_pos.data_ptr(), d_Z.data_ptr(), lattice9, pbc3, d_packed.data_ptr(), want_grad=want_grad,
+                                     stream_ptr=cur.cuda_stream)
+        self.reduce_packed(d_packed)
+        # a rank whose list overflowed has poisoned its energy with NaN (k_finalize): after the reduction every rank sees it, so
+        # all ranks repeat together without an extra collective
+        self._h_e.copy_(d_packed[:1], non_blocking=True)
+
+    def calc_resident_finish(self):
+        """Second half: synchronise once, then check the speculatively sized neighbour list.  False = enqueue again (the
+        repeat sizes the list exactly)."""
+        self.torch.cuda.current_stream(self.device).synchronize()
+        ok = self.pot.calc_device_verify()
+        return bool(ok and not bool(self.torch.isnan(self._h_e[0])))
 
     def calc(self, atoms, force=True, virial=True):
         """Host in, host out: H2D of (pos, Z) from pinned memory, evaluation of this rank's block, all-reduce, D2H."""
