@@ -58,6 +58,25 @@ int gap_potential_calc(gap_potential* pot, int N, const double* pos, const int* 
                        const char* args_str, double* energy, double* local_e, double* force, double* virial,
                        double* local_virial);
 
+/* ---- optional inputs / outputs of IPModel_GAP_Calc that the reference passes through the Atoms object and the calc
+ * args string (src/Potentials/IPModel_GAP.f95:324-337, 344-346, 462-488, 558-573).  They are requested with the SAME
+ * keys in args_str and fetched after the calc:
+ *   atom_mask_name=NAME            only atoms with mask != 0 are centres of descriptors and receive e0; the mask itself (the
+ *                                  logical Atoms property NAME in the reference) is supplied with gap_potential_set_atom_mask.
+ *                                  As in the reference it cannot be combined with an active partition (:375-378).
+ *   energy_per_coordinate=NAME     -> gap_potential_get_energy_per_coordinate: sum of e_i * covariance_cutoff per GP
+ *                                  coordinate (:462), before e0 and E_scale
+ *   local_gap_variance=NAME [gap_variance_regularisation=0.001]
+ *                                  -> gap_potential_get_local_gap_variance: per-atom predictive variance (:464-469; the sparse
+ *                                  covariance k_mm is factorised on first use, gp_predict.f95:3970-4085, cuSOLVER) and, when
+ *                                  forces or virials were requested, its gradient gap_variance_gradient(3,N) (:484-487).
+ *                                  A negative variance is an error, as in gp_predict.f95:3877.
+ * With a partition active the fetched arrays are this rank's partial sums (the reference's sum_in_place, :545-549). */
+int gap_potential_set_atom_mask(gap_potential* pot, int N, const int* mask /* N logicals; NULL = no mask */);
+int gap_potential_get_energy_per_coordinate(gap_potential* pot, double* energy_per_coordinate /* n_coordinate */);
+int gap_potential_get_local_gap_variance(gap_potential* pot, int N, double* local_gap_variance /* N */,
+                                         double* gap_variance_gradient /* 3*N or NULL */);
+
 /* Same, GPU-resident: d_pos/d_Z are DEVICE pointers, results stay on the device.
  *   d_packed  : device double[10 + 3*N] = [ E | virial(9) | F(3,N) ]  (the buffer the host all-reduces when the
  *               partition is active: one collective instead of the reference's five); never NULL

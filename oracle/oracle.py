@@ -61,6 +61,7 @@ def lib():
         L.orc_model_free.argtypes = [C.c_void_p]
         L.orc_model_set_e0.argtypes = [C.c_void_p, c_dp, C.c_int]
         L.orc_model_set_E_scale.argtypes = [C.c_void_p, C.c_double]
+        L.orc_model_n_coord.argtypes = [C.c_void_p]
         L.orc_model_cutoff.restype = C.c_double
         L.orc_model_cutoff.argtypes = [C.c_void_p]
         L.orc_model_add_soap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, c_dp, C.c_double, C.c_double]
@@ -68,6 +69,7 @@ def lib():
                                                 c_dp, c_dp, C.c_double, C.c_double, C.c_double]
         L.orc_model_calc.argtypes = [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_double, C.c_int, C.c_int, C.c_int,
                                      c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+        L.orc_model_set_extras.argtypes = [C.c_void_p, c_ip, c_dp, c_dp, c_dp, C.c_double]
         L.orc_model_predict.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp]
         _LIB = L
     return _LIB
@@ -388,10 +390,19 @@ class Model:
         return lib().orc_model_cutoff(self.h)
 
     def calc(self, atoms, energy=True, force=True, virial=True, local_energy=False, local_virial=False,
-             connect_cutoff=None, first=0, last=None, nthreads=0):
+             connect_cutoff=None, first=0, last=None, nthreads=0, atom_mask=None, energy_per_coordinate=False,
+             local_gap_variance=False, gap_variance_regularisation=0.001):
+        """atom_mask / energy_per_coordinate / local_gap_variance: the optional calc args of IPModel_GAP_Calc
+        (IPModel_GAP.f95:324-337); the variance gradient is returned when forces or virials are requested (:560-564)."""
         pos, Z, lat, pbc = _geom(atoms)
         N = len(Z)
         last = N if last is None else last
+        mask = None if atom_mask is None else np.ascontiguousarray(np.asarray(atom_mask, dtype=bool).astype(np.int32))
+        epc = np.zeros(lib().orc_model_n_coord(self.h)) if energy_per_coordinate else None
+        lgv = np.zeros(N) if local_gap_variance else None
+        gvg = np.zeros((N, 3)) if (local_gap_variance and (force or virial or local_virial)) else None
+        if mask is not None or epc is not None or lgv is not None:
+            lib().orc_model_set_extras(self.h, _ip(mask), _dp(epc), _dp(lgv), _dp(gvg), float(gap_variance_regularisation))
         e = np.zeros(1)
         f = np.zeros((N, 3)) if force else None
         v = np.zeros((3, 3), order="F") if virial else None
@@ -402,8 +413,14 @@ class Model:
                                   float(connect_cutoff if connect_cutoff is not None else self.cutoff), first, last,
                                   nthreads, _dp(e), _dp(le), _dp(f), _dp(v), _dp(lv), _dp(t))
         if rc:
-            raise RuntimeError("orc_model_calc failed")
+            raise RuntimeError("orc_model_calc failed (rc=%d)" % rc)
         out = {"energy": float(e[0]), "timings": t}
+        if epc is not None:
+            out["energy_per_coordinate"] = epc
+        if lgv is not None:
+            out["local_gap_variance"] = lgv
+        if gvg is not None:
+            out["gap_variance_gradient"] = gvg
         if force:
             out["force"] = f
         if virial:

@@ -153,8 +153,22 @@ struct Pair2bDev {
   const double* scut;     // [M]
 };
 void launch_pair2b(Pair2bDev p, int first, int last, const int* nbr_off, const int* nbr_end, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z,
-                   Lattice9 lat, double e_scale, int do_grad, double* local_e, double* force, double* vir_part, double* local_virial,
+                   const int* Zc /* < 0: not a centre */, int scatter /* 1: atom mask active, scatter to the pair partner */, Lattice9 lat, double e_scale, int do_grad, double* local_e, double* force, double* vir_part, double* local_virial,
                    cudaStream_t st, int* launches, int* n_blocks_out);
+
+// ---- variance.cu (optional local_gap_variance output; cuBLAS / cuSOLVER loaded on first use) -----------------
+}  // namespace gapb200
+#include <string>
+namespace gapb200 {
+void launch_var_kmm_finish(const double* G, int ldg, int M, CovParams cp, double f02, double reg2, double* K, cudaStream_t st, int* launches);
+int var_factorise(double* K, int M, cudaStream_t st, std::string* err);
+int var_solve(const double* Lf, int M, double* Q, int ldq, int rows, cudaStream_t st, std::string* err);
+void launch_var_prepare(const double* Cm, int ld, int rows, int M, const double* scut, CovParams cp, double* Q, cudaStream_t st, int* launches);
+void launch_var_finish(double* Cm, const double* Q, int ld, int rows, int row0, const int* n_rows_dev, int M, const double* scut, CovParams cp,
+                       double diag, const int* centres, double* lgv, int want_grad, int* neg_flag, cudaStream_t st, int* launches);
+void launch_pair2b_var(Pair2bDev p, const double* kinv, double diag, int first, int last, const int* Zc, const int* nbr_off, const int* nbr_end,
+                       const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, double* lgv, double* gvg, int* neg_flag,
+                       cudaStream_t st, int* launches);
 
 // ---- finalize (potential.cu) ----------------------------------------------------------------
 void launch_finalize(const int* Z, int N, int first, int last, const double* e0_dev, double e_scale, double* local_e, const double* vir_part,

@@ -26,7 +26,8 @@ __device__ __forceinline__ double wsum(double v) {
 
 __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int last, const int* __restrict__ nbr_off, const int* __restrict__ nbr_end,
                                                      const int* __restrict__ nbr_j, const int* __restrict__ nbr_s,
-                                                     const double* __restrict__ pos, const int* __restrict__ Z, Lattice9 lat, double e_scale,
+                                                     const double* __restrict__ pos, const int* __restrict__ Z, const int* __restrict__ Zc,
+                                                     int scatter, Lattice9 lat, double e_scale,
                                                      int do_grad, double* __restrict__ local_e, double* __restrict__ force,
                                                      double* __restrict__ vir_part, double* __restrict__ local_virial) {
   __shared__ double sX[64], sA[64], sC[64];
@@ -40,7 +41,11 @@ __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = first + blockIdx.x * WPB + w;
   double e_acc = 0, f0 = 0, f1 = 0, f2 = 0, v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (i < last) {
+  // scatter = 0: every atom of the configuration is a centre somewhere (whole system, or a partition whose partial
+  //   results are summed): the instance (j,i) mirrors (i,j), so atom i takes both halves and nothing is scattered.
+  // scatter = 1 (atom mask, IPModel_GAP.f95:344-346): only masked atoms are centres; each instance (i,j) gives atom j its own
+  //   half of the energy, the opposite force and the virial row, exactly as the reference's scatter loop (:454-491).
+  if (i < last && Zc[i] >= 0) {
     const int Zi = Z[i];
     const bool Zi1 = (p.Z1 == 0) || (Zi == p.Z1), Zi2 = (p.Z2 == 0) || (Zi == p.Z2);
     if (Zi1 || Zi2) {
@@ -70,12 +75,29 @@ __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int
           fc = 0.5 * (cn + 1.0);
           dfc = -0.5 * PI_D * sn / p.ctw;
         } else { fc = 1.0; dfc = 0.0; }
-        e_acc += e * fc;
+        if (scatter) {
+          e_acc += 0.5 * e * fc;
+          if (local_e) atomicAdd(&local_e[j], 0.5 * e_scale * e * fc);
+        } else {
+          e_acc += e * fc;
+        }
         if (do_grad) {
           double phi = (g * fc + e * dfc) * e_scale, rinv = 1.0 / r;
           double u0 = dd[0] * rinv, u1 = dd[1] * rinv, u2 = dd[2] * rinv;
-          f0 += 2.0 * phi * u0; f1 += 2.0 * phi * u1; f2 += 2.0 * phi * u2;
           double wv[9] = {dd[0] * u0, dd[1] * u0, dd[2] * u0, dd[0] * u1, dd[1] * u1, dd[2] * u1, dd[0] * u2, dd[1] * u2, dd[2] * u2};
+          if (scatter) {
+            f0 += phi * u0; f1 += phi * u1; f2 += phi * u2;
+            if (force) {
+              atomicAdd(&force[3 * (size_t)j + 0], -phi * u0);
+              atomicAdd(&force[3 * (size_t)j + 1], -phi * u1);
+              atomicAdd(&force[3 * (size_t)j + 2], -phi * u2);
+            }
+            if (local_virial)
+#pragma unroll
+              for (int k = 0; k < 9; k++) atomicAdd(&local_virial[9 * (size_t)j + k], -phi * wv[k]);
+          } else {
+            f0 += 2.0 * phi * u0; f1 += 2.0 * phi * u1; f2 += 2.0 * phi * u2;
+          }
 #pragma unroll
           for (int k = 0; k < 9; k++) v[k] -= phi * wv[k];
         }
@@ -90,15 +112,23 @@ __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int
   }
   if (lane == 0) {
     if (i < last) {
-      if (local_e) local_e[i] += e_scale * e_acc;
-      if (do_grad && force) {
-        // other kernels scatter into force[] with atomics on the same stream; plain RMW is safe because kernels
-        // of one calc are stream-ordered and this kernel owns row i exclusively
-        force[3 * (size_t)i + 0] += f0; force[3 * (size_t)i + 1] += f1; force[3 * (size_t)i + 2] += f2;
-      }
-      if (do_grad && local_virial)
+      if (scatter) {  // other warps scatter into row i concurrently
+        if (local_e) atomicAdd(&local_e[i], e_scale * e_acc);
+        if (do_grad && force) {
+          atomicAdd(&force[3 * (size_t)i + 0], f0); atomicAdd(&force[3 * (size_t)i + 1], f1); atomicAdd(&force[3 * (size_t)i + 2], f2);
+        }
+        // the virial of an instance belongs to its row n = 1 (atom j, scattered above); row n = 0 has zero displacement
+      } else {
+        if (local_e) local_e[i] += e_scale * e_acc;
+        if (do_grad && force) {
+          // other kernels scatter into force[] with atomics on the same stream; plain RMW is safe because kernels
+          // of one calc are stream-ordered and this kernel owns row i exclusively
+          force[3 * (size_t)i + 0] += f0; force[3 * (size_t)i + 1] += f1; force[3 * (size_t)i + 2] += f2;
+        }
+        if (do_grad && local_virial)
 #pragma unroll
-        for (int k = 0; k < 9; k++) local_virial[9 * (size_t)i + k] += v[k];
+          for (int k = 0; k < 9; k++) local_virial[9 * (size_t)i + k] += v[k];
+      }
     }
 #pragma unroll
     for (int k = 0; k < 9; k++) svir[w][k] = (i < last && do_grad) ? v[k] : 0.0;
@@ -112,13 +142,13 @@ __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int
 }  // namespace
 
 void launch_pair2b(Pair2bDev p, int first, int last, const int* nbr_off, const int* nbr_end, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z,
-                   Lattice9 lat, double e_scale, int do_grad, double* local_e, double* force, double* vir_part, double* local_virial,
+                   const int* Zc, int scatter, Lattice9 lat, double e_scale, int do_grad, double* local_e, double* force, double* vir_part, double* local_virial,
                    cudaStream_t st, int* launches, int* n_blocks_out) {
   int n = last - first;
   int nb = (n + WPB - 1) / WPB;
   *n_blocks_out = nb;
   if (nb <= 0) return;
-  k_pair2b<<<nb, WPB * 32, 0, st>>>(p, first, last, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, e_scale, do_grad, local_e, force, vir_part,
+  k_pair2b<<<nb, WPB * 32, 0, st>>>(p, first, last, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, Zc, scatter, lat, e_scale, do_grad, local_e, force, vir_part,
                                     local_virial);
   *launches += 1;
 }

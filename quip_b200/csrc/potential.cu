@@ -71,6 +71,10 @@ struct CoordDev {
   // distance_2b
   Pair2bDev p2;
   double *x2 = nullptr, *a2 = nullptr, *c2 = nullptr;
+  // variance estimate (built on first use for a given regularisation): soap = lower Cholesky factor of k_mm (M x M,
+  // column-major), distance_2b = explicit inverse of k_mm (M x M)
+  double* var_mat = nullptr;
+  double var_reg = -1.0, f0 = 0.0, delta = 0.0;
 };
 
 }  // namespace
@@ -100,6 +104,15 @@ struct gap_potential {
   DevBuf b_xoff, b_xj, b_xs, b_zc;  // device copies of an external list and of the centre mask
   long launches = 0;
   double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // optional inputs / outputs of the last calc (IPModel_GAP.f95:324-337)
+  DevBuf b_mask;               // atom mask (ints) set with gap_potential_set_atom_mask
+  int mask_N = -1;
+  DevBuf b_epc;                // running sums of local_e after each coordinate -> energy_per_coordinate
+  bool epc_valid = false;
+  DevBuf b_lgv, b_gvg, b_varflag, b_vc, b_vq, b_vk;  // local_gap_variance[N], gap_variance_gradient[3N], negative-variance flag, work
+  int var_N = -1;
+  bool var_grad = false;
+  cudaStream_t last_stream = nullptr;
 
   // neighbour list state
   NeighbourWork nw;
@@ -177,6 +190,28 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict_
   }
 }
 
+// fixed-order sum of local_e (one block): the running total after each GP coordinate gives energy_per_coordinate
+__global__ void __launch_bounds__(1024) k_sum_range(const double* __restrict__ v, int n, double* __restrict__ out) {
+  __shared__ double ws[32];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) t += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    t = ws[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) *out = t;
+  }
+}
+// atomic numbers as the centre selection sees them: -1 for atoms outside the mask (atom_mask_name, IPModel_GAP.f95:344-346)
+__global__ void k_apply_mask(const int* __restrict__ Z, const int* __restrict__ mask, int N, int* __restrict__ Zc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) Zc[i] = mask[i] ? Z[i] : -1;
+}
+
 // zero the outputs of a calc in one launch: packed [E | virial | F], local_e, local_virial (may be NULL)
 __global__ void k_zero_outputs(double* __restrict__ a, size_t na, double* __restrict__ b, size_t nb, double* __restrict__ c, size_t nc) {
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,7 +238,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_compact_block(const int*
       if (t < n) {
         const int Zi = Z[first + t];
         for (int q = 0; q < nZ; q++)
-          if (sp->centre_Z[q] == Zi || sp->centre_Z[q] == 0) f[k] = 1;
+          if (Zi >= 0 && (sp->centre_Z[q] == Zi || sp->centre_Z[q] == 0)) f[k] = 1;
       }
     }
     BS(tmp).ExclusiveSum(f, pos, total);
@@ -491,6 +526,8 @@ void upload_model(gap_potential* P) {
   for (const Coordinate& c : P->model.coord) {
     CoordDev cd;
     cd.kind = c.kind;
+    cd.delta = c.delta;
+    cd.f0 = c.f0;
     if (c.kind == DESC_SOAP) {
       const SoapSpec& s = c.soap;
       if (s.n_max > SOAP_NMAX_CAP) throw GapError("soap n_max > " + std::to_string(SOAP_NMAX_CAP) + " is not supported by the B200 path");
@@ -590,6 +627,8 @@ gap_potential* create_potential(const std::string& args, const std::string& xml,
 
 struct CalcArgs {
   int only_descriptor = 0;  // 1-based, 0 = all
+  bool use_mask = false, do_epc = false, do_var = false;
+  double var_reg = 0.001;   // gap_variance_regularisation (IPModel_GAP.f95:332)
 };
 CalcArgs parse_calc_args(const gap_potential* P, const char* args_str) {
   CalcArgs a;
@@ -597,11 +636,20 @@ CalcArgs parse_calc_args(const gap_potential* P, const char* args_str) {
   ArgDict d(args_str);
   if (d.has("r_scale") || d.has("E_scale"))  // IPModel_GAP.f95:348-350
     throw GapError("IPModel_GAP_Calc: rescaling of potential at the calc() stage with r_scale and E_scale not yet implemented!");
-  if (d.has("atom_mask_name") && d.str("atom_mask_name", "NONE") != "NONE")
-    throw GapError("IPModel_GAP_Calc: atom_mask_name is not supported by the B200 path (use gap_potential_set_partition)");
-  if (!d.str("local_gap_variance", "").empty() || d.logical("print_gap_variance", false))
-    throw GapError("IPModel_GAP_Calc: GAP variance estimates are not supported by the B200 path");
-  if (!d.str("energy_per_coordinate", "").empty()) throw GapError("IPModel_GAP_Calc: energy_per_coordinate is not supported by the B200 path");
+  if (d.has("atom_mask_name") && d.str("atom_mask_name", "NONE") != "NONE") {
+    if (P->mask_N < 0)  // :345-346
+      throw GapError("IPModel_GAP_Calc did not find " + d.str("atom_mask_name", "") + " property in the atoms object (supply it with gap_potential_set_atom_mask)");
+    if (P->n_ranks > 1)  // :375-378
+      throw GapError("IPModel_GAP: atom_mask_name " + d.str("atom_mask_name", "") + " present while running the partitioned (MPI) version");
+    a.use_mask = true;
+  }
+  if (d.logical("print_gap_variance", false))
+    throw GapError("IPModel_GAP_Calc: print_gap_variance is not supported by the B200 path (use local_gap_variance)");
+  a.do_var = !d.str("local_gap_variance", "").empty();
+  a.var_reg = d.real("gap_variance_regularisation", 0.001);
+  if (a.do_var && a.var_reg < 0.0)  // gp_predict.f95:4002-4003
+    throw GapError("gpCoordinates_initialise_variance_estimate: regularisation (" + std::to_string(a.var_reg) + ") is negative.");
+  a.do_epc = !d.str("energy_per_coordinate", "").empty();
   if (d.has("only_descriptor")) {
     a.only_descriptor = (int)d.integer("only_descriptor", 0);
     if (P->model.coord.size() <= 1) a.only_descriptor = 0;  // :399
@@ -683,6 +731,118 @@ void covariance_stage(gap_potential* P, const CoordDev& cd, int nc, const int* r
   P->launches += launches;
 }
 
+// ---- predictive variance (optional output; variance.cu) -------------------------------------------------------------
+// k_mm of a coordinate, factorised (soap) or inverted (distance_2b), for this regularisation
+// (gpCoordinates_initialise_variance_estimate, gp_predict.f95:3970-4085)
+void ensure_variance_model(gap_potential* P, size_t ic, double reg, cudaStream_t st) {
+  CoordDev& cd = P->cd[ic];
+  const Coordinate& c = P->model.coord[ic];
+  if (cd.var_mat && cd.var_reg == reg) return;  // :3990-3996
+  if (cd.var_mat) { cudaFree(cd.var_mat); cd.var_mat = nullptr; }
+  const int M = c.M;
+  if (M <= 0) return;
+  int launches = 0;
+  if (cd.kind == DESC_SOAP) {
+    const int n_rows_pad = round_up(M, COV_BM), dnp = round_up(M, 128);
+    P->b_vc.ensure(sizeof(double) * (size_t)n_rows_pad * dnp);
+    launch_cov_gemm2(cd.sp_rows, cd.d_pad, cd.sp_rows, cd.d_pad, n_rows_pad, 0, nullptr, dnp, 128, 1, round_up(cd.h.d, 4), P->b_vc.as<double>(), dnp,
+                     0, st, &launches);
+    CUDA_OK(cudaMalloc(&cd.var_mat, sizeof(double) * (size_t)M * M));
+    launch_var_kmm_finish(P->b_vc.as<double>(), dnp, M, cd.cp, c.f0 * c.f0, reg * reg, cd.var_mat, st, &launches);
+    std::string err;
+    const int info = var_factorise(cd.var_mat, M, st, &err);
+    if (info != 0) {
+      cudaFree(cd.var_mat);
+      cd.var_mat = nullptr;
+      if (info == -1000) throw GapError("gpCoordinates_initialise_variance_estimate: " + err);
+      throw GapError("gpCoordinates_initialise_variance_estimate: k_mm is not positive definite (dpotrf info = " + std::to_string(info) + ")");
+    }
+  } else {
+    if (M > 64) throw GapError("GAP variance for distance_2b coordinates with more than 64 sparse points is not supported by the B200 path");
+    // ARD_SE, one permutation (:4034-4039), normalisation (:4055-4068), delta^2, f0^2, regularisation (:4070-4075); host, M <= 64
+    std::vector<double> K((size_t)M * M), Kinv((size_t)M * M, 0.0);
+    const double th = c.theta[0];
+    for (int i = 0; i < M; i++)
+      for (int j = 0; j < M; j++) {
+        double t = (c.sparseX[i] - c.sparseX[j]) / th, v = std::exp(-0.5 * t * t);
+        v = (i == j) ? c.sparseCutoff[i] * c.sparseCutoff[i] : v * c.sparseCutoff[i] * c.sparseCutoff[j];  // k_mm(i,i) = 1 before normalisation
+        K[(size_t)i * M + j] = v * c.delta * c.delta + c.f0 * c.f0 + (i == j ? reg * reg : 0.0);
+      }
+    for (int j = 0; j < M; j++) {  // lower Cholesky in place (row-major; the matrix is symmetric)
+      double sdiag = K[(size_t)j * M + j];
+      for (int k = 0; k < j; k++) sdiag -= K[(size_t)j * M + k] * K[(size_t)j * M + k];
+      if (!(sdiag > 0.0)) throw GapError("gpCoordinates_initialise_variance_estimate: k_mm is not positive definite");
+      const double ljj = std::sqrt(sdiag);
+      K[(size_t)j * M + j] = ljj;
+      for (int i = j + 1; i < M; i++) {
+        double t = K[(size_t)i * M + j];
+        for (int k = 0; k < j; k++) t -= K[(size_t)i * M + k] * K[(size_t)j * M + k];
+        K[(size_t)i * M + j] = t / ljj;
+      }
+    }
+    std::vector<double> y(M);
+    for (int col = 0; col < M; col++) {  // k_mm^-1 e_col
+      for (int i = 0; i < M; i++) {
+        double t = (i == col) ? 1.0 : 0.0;
+        for (int k = 0; k < i; k++) t -= K[(size_t)i * M + k] * y[k];
+        y[i] = t / K[(size_t)i * M + i];
+      }
+      for (int i = M - 1; i >= 0; i--) {
+        double t = y[i];
+        for (int k = i + 1; k < M; k++) t -= K[(size_t)k * M + i] * y[k];
+        y[i] = t / K[(size_t)i * M + i];
+      }
+      for (int i = 0; i < M; i++) Kinv[(size_t)i * M + col] = y[i];
+    }
+    CUDA_OK(cudaMalloc(&cd.var_mat, sizeof(double) * (size_t)M * M));
+    CUDA_OK(cudaMemcpyAsync(cd.var_mat, Kinv.data(), sizeof(double) * (size_t)M * M, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+  cd.var_reg = reg;
+  P->launches += launches;
+}
+
+// variance of every centre of SOAP coordinate ic (b_x rows [0, nc)) and, if want_grad, its gradient scattered to atoms
+void variance_soap(gap_potential* P, size_t ic, int nc, const int* ncd, bool want_grad, const double* d_pos, const int* d_Z, const Lattice9& lat,
+                   double reg, cudaStream_t st) {
+  const CoordDev& cd = P->cd[ic];
+  const int M = cd.M;
+  if (M <= 0 || nc <= 0) return;
+  int launches = 0;
+  const int ld = cd.M_pad, nc_pad = round_up(nc, COV_BM);
+  const size_t budget = (size_t)512 << 20;
+  int chunk = (int)(budget / ((size_t)ld * sizeof(double)) / COV_BM) * COV_BM;
+  if (chunk < COV_BM) chunk = COV_BM;
+  if (chunk > nc_pad) chunk = nc_pad;
+  P->b_vk.ensure(sizeof(double) * (size_t)chunk * ld);
+  P->b_vq.ensure(sizeof(double) * (size_t)chunk * ld);
+  const int ksplit = want_grad ? cov_gemm2_ksplit(chunk, cd.dn_pad, cd.bn2, P->n_sm) : 1;
+  const size_t split_stride = (size_t)nc_pad * cd.dn_pad;
+  if (want_grad) P->b_gvec.ensure(sizeof(double) * split_stride * ksplit);
+  const double diag = cd.delta * cd.delta + cd.f0 * cd.f0 + reg * reg;  // gp_predict.f95:3874
+  double* Cm = P->b_vk.as<double>();
+  double* Q = P->b_vq.as<double>();
+  for (int r0 = 0; r0 < nc_pad; r0 += chunk) {
+    const int rows = std::min(chunk, nc_pad - r0);
+    launch_cov_gemm2(P->b_x.as<double>() + (size_t)r0 * cd.d_pad, cd.d_pad, cd.sp_rows, cd.d_pad, rows, r0, ncd, round_up(M, 128), 128, 1,
+                     round_up(cd.h.d, 4), Cm, ld, 0, st, &launches);
+    launch_var_prepare(Cm, ld, rows, M, cd.scut, cd.cp, Q, st, &launches);
+    std::string err;
+    if (var_solve(cd.var_mat, M, Q, ld, rows, st, &err)) throw GapError("gpCoordinates_Predict (variance): " + err);
+    launches += 2;
+    launch_var_finish(Cm, Q, ld, rows, r0, ncd, M, cd.scut, cd.cp, diag, P->b_centres.as<int>(), P->b_lgv.as<double>(), want_grad ? 1 : 0,
+                      P->b_varflag.as<int>(), st, &launches);
+    if (want_grad)
+      launch_cov_gemm2(Cm, ld, cd.st_rows, cd.M_pad, rows, r0, ncd, cd.dn_pad, cd.bn2, ksplit, round_up(M, 4),
+                       P->b_gvec.as<double>() + (size_t)r0 * cd.dn_pad, cd.dn_pad, split_stride, st, &launches);
+  }
+  if (want_grad)  // pull-back through the descriptor: gap_variance_gradient(:,j) += grad_variance . grad_data(:,:,n)  (IPModel_GAP.f95:485-486)
+    launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_x.as<double>(),
+                        P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, ksplit, split_stride, nullptr, 0, nullptr,
+                        -1.0 /* the kernel scatters force = -e_scale f_gp */, P->b_gvg.as<double>(), nullptr, nullptr, st, &launches);
+  P->launches += launches;
+}
+
 // An externally supplied neighbour list (quip_lammps_wrapper): CSR over all N = nlocal + nghost atoms with zero shifts
 // (periodic images are explicit ghost atoms), and d_Zc = Z for the atoms that are centres, -1 for the others
 // (the reference's atom_mask_name=local, quip_lammps_wrapper.f95:97-147).
@@ -700,7 +860,31 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   int first = (int)((long long)P->rank * N / P->n_ranks), last = (int)((long long)(P->rank + 1) * N / P->n_ranks);
   const int* d_Zc = d_Z;  // atomic numbers as seen by the centre selection and the e0 sum
   P->ev_used = 0;
+  P->last_stream = st;
   mark(P, st, -1);
+  if (ca.use_mask) {
+    if (ext) throw GapError("IPModel_GAP_Calc: atom_mask_name cannot be combined with an external neighbour list");
+    if (P->mask_N != N) throw GapError("IPModel_GAP_Calc: the atom mask has " + std::to_string(P->mask_N) + " entries, the configuration " + std::to_string(N) + " atoms");
+    P->b_zc.ensure(sizeof(int) * (size_t)(N + 1));
+    if (N > 0) k_apply_mask<<<(N + 255) / 256, 256, 0, st>>>(d_Z, P->b_mask.as<int>(), N, P->b_zc.as<int>());
+    P->launches += 1;
+    d_Zc = P->b_zc.as<int>();
+  }
+  const size_t n_coord = P->cd.size();
+  P->epc_valid = false;
+  if (ca.do_epc) P->b_epc.ensure(sizeof(double) * (n_coord + 1));
+  P->var_N = -1;
+  if (ca.do_var) {
+    P->b_lgv.ensure(sizeof(double) * (size_t)(N + 1));
+    P->b_varflag.ensure(sizeof(int));
+    CUDA_OK(cudaMemsetAsync(P->b_lgv.p, 0, sizeof(double) * (size_t)(N + 1), st));
+    CUDA_OK(cudaMemsetAsync(P->b_varflag.p, 0, sizeof(int), st));
+    if (want_grad) {
+      P->b_gvg.ensure(sizeof(double) * 3 * (size_t)(N + 1));
+      CUDA_OK(cudaMemsetAsync(P->b_gvg.p, 0, sizeof(double) * 3 * (size_t)(N + 1), st));
+    }
+    for (size_t ic = 0; ic < n_coord; ic++) ensure_variance_model(P, ic, ca.var_reg, st);  // IPModel_GAP.f95:412-414
+  }
   if (ext) {
     first = 0;
     last = ext->nlocal;
@@ -735,10 +919,11 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   size_t slot = 0;
 
   for (size_t ic = 0; ic < P->cd.size(); ic++) {
-    if (ca.only_descriptor && (int)ic + 1 != ca.only_descriptor) continue;
     const CoordDev& cd = P->cd[ic];
     int launches = 0;
-    if (cd.kind == DESC_SOAP) {
+    if (ca.only_descriptor && (int)ic + 1 != ca.only_descriptor) {
+      // skipped coordinate (:399-401): its energy_per_coordinate entry is zero
+    } else if (cd.kind == DESC_SOAP) {
       int nc = select_centres(P, cd, d_Zc, first, last, st);  // upper bound; the count itself stays on the device
       mark(P, st, ST_OTHER);
       if (nc > 0) {
@@ -757,17 +942,31 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
           launch_energy_rows(P->b_epart.as<double>(), P->g_tiles_n, P->b_centres.as<int>(), ncd, nc, es, d_le, st, &launches);
           mark(P, st, ST_OTHER);
         }
+        if (ca.do_var) {
+          variance_soap(P, ic, nc, ncd, want_grad, d_pos, d_Z, lat, ca.var_reg, st);
+          mark(P, st, ST_OTHER);
+        }
       }
     } else {
       int nb = 0;
-      launch_pair2b(cd.p2, first, last, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, es, want_grad ? 1 : 0, d_le,
-                    want_grad ? d_force : nullptr, want_grad ? P->b_vir.as<double>() + 9 * slot : nullptr, want_grad ? d_lv : nullptr, st, &launches,
-                    &nb);
+      launch_pair2b(cd.p2, first, last, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, d_Zc, ca.use_mask ? 1 : 0, lat, es, want_grad ? 1 : 0,
+                    d_le, want_grad ? d_force : nullptr, want_grad ? P->b_vir.as<double>() + 9 * slot : nullptr, want_grad ? d_lv : nullptr, st,
+                    &launches, &nb);
       if (want_grad) slot += nb;
+      if (ca.do_var && cd.var_mat)
+        launch_pair2b_var(cd.p2, cd.var_mat, cd.delta * cd.delta + cd.f0 * cd.f0 + ca.var_reg * ca.var_reg, first, last, d_Zc, P->cv_off, P->cv_end,
+                          P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_lgv.as<double>(), want_grad ? P->b_gvg.as<double>() : nullptr,
+                          P->b_varflag.as<int>(), st, &launches);
       mark(P, st, ST_PAIR2B);
+    }
+    if (ca.do_epc) {  // running total of local_e (e0 not yet added): the increments are energy_per_coordinate * E_scale (:462)
+      k_sum_range<<<1, 1024, 0, st>>>(d_le, N, P->b_epc.as<double>() + ic);
+      launches += 1;
     }
     P->launches += launches;
   }
+  if (ca.do_epc) P->epc_valid = true;
+  if (ca.do_var) { P->var_N = N; P->var_grad = want_grad; }
   // totals
   P->b_fin.ensure(sizeof(double) * 10 * FIN_BLOCKS);
   const size_t fin_work = std::max<size_t>((size_t)N, want_grad ? slot : 0);
@@ -833,12 +1032,12 @@ void gap_potential_finalise(gap_potential* P) {
   if (P->stream) cudaStreamSynchronize(P->stream);
   for (CoordDev& cd : P->cd) {
     cudaFree(cd.d_sp); cudaFree(cd.sp_rows); cudaFree(cd.st_rows); cudaFree(cd.alpha); cudaFree(cd.scut);
-    cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2);
+    cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2); cudaFree(cd.var_mat);
   }
   cudaFree(P->d_e0);
   cudaFree(P->d_fin_counter);
   if (P->h_pin) cudaFreeHost(P->h_pin);
-  DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_cstart, &P->b_end, &P->b_spos, &P->b_smshift,
+  DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_cstart, &P->b_end, &P->b_mask, &P->b_epc, &P->b_lgv, &P->b_gvg, &P->b_varflag, &P->b_vc, &P->b_vq, &P->b_vk, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
                     &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke};
@@ -879,6 +1078,48 @@ int gap_potential_set_partition(gap_potential* P, int rank, int n_ranks) {
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw GapError("gap_potential_set_partition: need 0 <= rank < n_ranks");
     P->rank = rank;
     P->n_ranks = n_ranks;
+  });
+}
+
+int gap_potential_set_atom_mask(gap_potential* P, int N, const int* mask) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_set_atom_mask: pot is NULL");
+    if (!mask) { P->mask_N = -1; return; }
+    if (N < 0) throw GapError("gap_potential_set_atom_mask: N < 0");
+    CUDA_OK(cudaSetDevice(P->device));
+    P->b_mask.ensure(sizeof(int) * (size_t)(N + 1));
+    if (N > 0) CUDA_OK(cudaMemcpy(P->b_mask.p, mask, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice));
+    P->mask_N = N;
+  });
+}
+
+int gap_potential_get_energy_per_coordinate(gap_potential* P, double* out) {
+  return guard([&] {
+    if (!P || !out) throw GapError("gap_potential_get_energy_per_coordinate: bad arguments");
+    if (!P->epc_valid) throw GapError("gap_potential_get_energy_per_coordinate: the last calc was not asked for energy_per_coordinate=NAME");
+    CUDA_OK(cudaSetDevice(P->device));
+    const size_t n = P->cd.size();
+    std::vector<double> run(n);
+    CUDA_OK(cudaStreamSynchronize(P->last_stream));
+    if (n) CUDA_OK(cudaMemcpy(run.data(), P->b_epc.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    const double es = P->model.E_scale;
+    for (size_t k = 0; k < n; k++) out[k] = es != 0.0 ? (run[k] - (k ? run[k - 1] : 0.0)) / es : 0.0;
+  });
+}
+
+int gap_potential_get_local_gap_variance(gap_potential* P, int N, double* local_gap_variance, double* gap_variance_gradient) {
+  return guard([&] {
+    if (!P || !local_gap_variance) throw GapError("gap_potential_get_local_gap_variance: bad arguments");
+    if (P->var_N < 0 || P->var_N != N) throw GapError("gap_potential_get_local_gap_variance: the last calc was not asked for local_gap_variance=NAME (or N differs)");
+    if (gap_variance_gradient && !P->var_grad)
+      throw GapError("gap_potential_get_local_gap_variance: gap_variance_gradient needs a calc with forces or virials (IPModel_GAP.f95:560-564)");
+    CUDA_OK(cudaSetDevice(P->device));
+    CUDA_OK(cudaStreamSynchronize(P->last_stream));
+    int flag = 0;
+    CUDA_OK(cudaMemcpy(&flag, P->b_varflag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) throw GapError("gpCoordinates_Predict: variance_estimate: negative variance predicted");  // gp_predict.f95:3877
+    if (N > 0) CUDA_OK(cudaMemcpy(local_gap_variance, P->b_lgv.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+    if (gap_variance_gradient && N > 0) CUDA_OK(cudaMemcpy(gap_variance_gradient, P->b_gvg.p, sizeof(double) * 3 * (size_t)N, cudaMemcpyDeviceToHost));
   });
 }
 

@@ -1243,7 +1243,7 @@ __global__ void k_select_centres(const int* __restrict__ Z, int first, int last,
   if (t < last - first) {
     int Zi = Z[first + t];
     for (int k = 0; k < sp->n_Z; k++)
-      if (sp->centre_Z[k] == Zi || sp->centre_Z[k] == 0) f = 1;  // descriptors.f95:7962
+      if (Zi >= 0 && (sp->centre_Z[k] == Zi || sp->centre_Z[k] == 0)) f = 1;  // descriptors.f95:7962 ; Zi < 0: outside the atom mask
   }
   flags[t] = f;
 }

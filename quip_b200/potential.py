@@ -33,6 +33,9 @@ ABI = {
     "gap_potential_print": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "gap_potential_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "gap_potential_calc": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "gap_potential_set_atom_mask": (C.c_int, [C.c_void_p, C.c_int, c_ip]),
+    "gap_potential_get_energy_per_coordinate": (C.c_int, [C.c_void_p, c_dp]),
+    "gap_potential_get_local_gap_variance": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp]),
     "gap_potential_calc_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_dp, c_ip, C.c_char_p, C.c_int,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gap_md_run": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_ip, C.c_double, C.c_int, C.c_char_p, c_dp, c_dp]),
@@ -116,6 +119,16 @@ def key_val_dict_to_str(d):
     return " ".join("%s=%s" % (k, v) if v is not None else str(k) for k, v in d.items())
 
 
+def _calc_options(args_str):
+    """key=value pairs of a calc args string (ParamReader grammar, no quoting needed for the keys used here)"""
+    out = {}
+    for tok in (args_str or "").split():
+        if "=" in tok:
+            k, v = tok.split("=", 1)
+            out[k] = v.strip("{}'\"")
+    return out
+
+
 def _geometry(atoms):
     pos = np.ascontiguousarray(atoms.get_positions(), dtype=np.float64)
     Z = np.ascontiguousarray(atoms.get_atomic_numbers(), dtype=np.int32)
@@ -176,9 +189,29 @@ class Potential:
         le = np.zeros(N) if local_energy else None
         lv = np.zeros((N, 9)) if local_virial else None
         full_args = (self.calc_args + " " + (args_str or "")).strip()
-        _check(load_library().gap_potential_calc(self._h, N, _dp(pos), _ip(Z), _dp(lat), _ip(pbc), full_args.encode(), _dp(e),
-                                                 _dp(le), _dp(f), _dp(v), _dp(lv)))
+        opts = _calc_options(full_args)
+        lib = load_library()
+        if "atom_mask_name" in opts and opts["atom_mask_name"] != "NONE":
+            # the reference reads the logical Atoms property of that name (IPModel_GAP.f95:344-346)
+            arrays = getattr(atoms, "arrays", {})
+            if opts["atom_mask_name"] not in arrays:
+                raise RuntimeError("IPModel_GAP_Calc did not find %s property in the atoms object." % opts["atom_mask_name"])
+            mask = np.ascontiguousarray(np.asarray(arrays[opts["atom_mask_name"]]).astype(bool).astype(np.int32))
+            _check(lib.gap_potential_set_atom_mask(self._h, N, _ip(mask)))
+        _check(lib.gap_potential_calc(self._h, N, _dp(pos), _ip(Z), _dp(lat), _ip(pbc), full_args.encode(), _dp(e),
+                                      _dp(le), _dp(f), _dp(v), _dp(lv)))
         out = {"energy": float(e[0])}
+        if opts.get("energy_per_coordinate"):  # returned inside the Atoms object by the reference (:573)
+            epc = np.zeros(self.n_coordinate)
+            _check(lib.gap_potential_get_energy_per_coordinate(self._h, _dp(epc)))
+            out[opts["energy_per_coordinate"]] = epc
+        if opts.get("local_gap_variance"):  # (:558-571)
+            lgv = np.zeros(N)
+            gvg = np.zeros((N, 3)) if (force or virial or local_virial) else None
+            _check(lib.gap_potential_get_local_gap_variance(self._h, N, _dp(lgv), _dp(gvg)))
+            out[opts["local_gap_variance"]] = lgv
+            if gvg is not None:
+                out["gap_variance_gradient"] = gvg
         if force:
             out["force"] = f
         if virial:

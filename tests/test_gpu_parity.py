@@ -585,3 +585,63 @@ def test_lammps_pair_style_quip_abi(si_model, si_frames):
     letot = le[:N].copy()
     np.add.at(letot, gorig, le[N:])
     assert np.abs(letot - ref["local_energy"]).max() < 1e-8
+
+
+# ----------------------------------------------------------------------------------------------------
+# optional inputs / outputs of IPModel_GAP_Calc (IPModel_GAP.f95:324-337): atom mask, energy per coordinate, GAP variance
+# ----------------------------------------------------------------------------------------------------
+def test_atom_mask_matches_oracle(si_model, si_frames):
+    pot, om, _ = si_model
+    for a in (si_frames[4], si_frames[8]):
+        N = len(a)
+        mask = np.zeros(N, dtype=bool)
+        mask[::3] = True
+        am = Atoms(a.numbers, a.positions, a.cell, True, arrays={"sel": mask})
+        r = pot.calc(am, force=True, virial=True, local_energy=True, local_virial=True, args_str="atom_mask_name=sel")
+        o = om.calc(a, atom_mask=mask, local_energy=True, local_virial=True)
+        assert abs(r["energy"] - o["energy"]) / N < TOL_E_PER_ATOM
+        assert np.abs(r["local_energy"] - o["local_energy"]).max() < 1e-8   # the split between pair partners is the reference's
+        assert np.abs(r["force"] - o["force"]).max() < TOL_F
+        assert np.abs(r["virial"] - o["virial"]).max() < TOL_V
+        assert np.abs(r["local_virial"] - o["local_virial"]).max() < TOL_V
+        # complementary masks add up to the unmasked result
+        am2 = Atoms(a.numbers, a.positions, a.cell, True, arrays={"sel": ~mask})
+        r2 = pot.calc(am2, force=True, virial=True, args_str="atom_mask_name=sel")
+        full = pot.calc(a, force=True, virial=True)
+        assert abs(r["energy"] + r2["energy"] - full["energy"]) < 1e-8 * N
+        assert np.abs(r["force"] + r2["force"] - full["force"]).max() < 1e-9
+    with pytest.raises(RuntimeError, match="did not find"):
+        pot.calc(si_frames[4], args_str="atom_mask_name=nope")
+
+
+def test_energy_per_coordinate(si_model, si_frames):
+    pot, om, _ = si_model
+    a = si_frames[8]
+    r = pot.calc(a, force=True, args_str="energy_per_coordinate=epc")
+    o = om.calc(a, energy_per_coordinate=True)
+    assert r["epc"].shape == (2,)
+    assert np.abs(r["epc"] - o["energy_per_coordinate"]).max() < 1e-8 * len(a)
+    e0 = len(a) * (-158.54496821 + 2.0)
+    assert abs(r["epc"].sum() + e0 - r["energy"]) < 1e-8 * len(a)
+    r1 = pot.calc(a, args_str="energy_per_coordinate=epc only_descriptor=2")
+    assert r1["epc"][0] == 0.0 and abs(r1["epc"][1] - r["epc"][1]) < 1e-9 * len(a)
+
+
+def test_local_gap_variance_and_gradient(si_model, si_frames):
+    pot, om, _ = si_model
+    for a, reg in ((si_frames[4], 0.001), (si_frames[8], 0.01)):
+        args = "local_gap_variance=var gap_variance_regularisation=%g" % reg
+        r = pot.calc(a, force=True, args_str=args)
+        o = om.calc(a, local_gap_variance=True, gap_variance_regularisation=reg)
+        scale = np.abs(o["local_gap_variance"]).max()
+        # k_mm has a condition number ~ delta^2 / regularisation^2: the two Cholesky solves agree to ~1e-16 * cond
+        tol = 1e-9 * scale * (0.001 / reg) ** 2 * 1e3
+        assert np.abs(r["var"] - o["local_gap_variance"]).max() < tol, np.abs(r["var"] - o["local_gap_variance"]).max()
+        gs = np.abs(o["gap_variance_gradient"]).max()
+        assert np.abs(r["gap_variance_gradient"] - o["gap_variance_gradient"]).max() < 1e-6 * max(gs, 1.0)
+        # energies and forces are untouched by the request
+        plain = pot.calc(a, force=True)
+        assert r["energy"] == plain["energy"] and np.abs(r["force"] - plain["force"]).max() < 1e-11  # (forces are scattered with atomics)
+        # energy only: variance without gradient
+        r0 = pot.calc(a, args_str=args)
+        assert "gap_variance_gradient" not in r0 and np.abs(r0["var"] - r["var"]).max() < 1e-12 * scale
