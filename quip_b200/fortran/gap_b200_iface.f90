@@ -11,6 +11,7 @@ module gap_b200_iface
   private
   public :: gap_potential_initialise, gap_potential_filename_initialise, gap_potential_finalise, gap_potential_cutoff
   public :: gap_potential_calc, gap_potential_set_partition, gap_last_error, gap_b200_error_string
+  public :: gap_potential_set_atom_mask, gap_potential_get_energy_per_coordinate, gap_potential_get_local_gap_variance
 
   interface
      ! int gap_potential_initialise(gap_potential** pot, const char* args_str, const char* param_str, const char* base_dir, int device)
@@ -42,6 +43,28 @@ module gap_b200_iface
        import :: c_ptr, c_int
        type(c_ptr), value :: pot
        integer(c_int), value :: rank, n_ranks
+       integer(c_int) :: ierr
+     end function
+     ! optional inputs / outputs the reference keeps in the Atoms object (IPModel_GAP.f95:324-337, 558-573)
+     function gap_potential_set_atom_mask(pot, n, mask) bind(C, name="gap_potential_set_atom_mask") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: pot, mask        ! mask: c_loc of integer(c_int) mask(n), or c_null_ptr to clear it
+       integer(c_int), value :: n
+       integer(c_int) :: ierr
+     end function
+     function gap_potential_get_energy_per_coordinate(pot, energy_per_coordinate) &
+          bind(C, name="gap_potential_get_energy_per_coordinate") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: pot
+       real(c_double), intent(out) :: energy_per_coordinate(*)
+       integer(c_int) :: ierr
+     end function
+     function gap_potential_get_local_gap_variance(pot, n, local_gap_variance, gap_variance_gradient) &
+          bind(C, name="gap_potential_get_local_gap_variance") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: pot, gap_variance_gradient   ! c_loc of real(dp) (3,n), or c_null_ptr
+       integer(c_int), value :: n
+       real(c_double), intent(out) :: local_gap_variance(*)
        integer(c_int) :: ierr
      end function
      ! absent optional outputs are passed as C_NULL_PTR, hence type(c_ptr), value for every output
@@ -130,9 +153,22 @@ end module gap_b200_iface
 !   if (present(mpi)) then                                    ! the reference's atom mask (descriptors.f95:1036-1051)
 !      if (mpi%active) ierr = gap_potential_set_partition(this%b200, mpi%my_proc, mpi%n_procs)
 !   end if
+!   if (has_atom_mask_name) then                              ! :344-346: the logical property becomes an integer mask
+!      imask = merge(1_c_int, 0_c_int, atom_mask_pointer)
+!      ierr = gap_potential_set_atom_mask(this%b200, at%N, c_loc(imask))
+!   end if
 !   ierr = gap_potential_calc(this%b200, at%N, at%pos, at%Z, at%lattice, pbc, trim(args_str)//c_null_char, pe, ple, pf, pv, plv)
 !   if (ierr /= 0) then
 !      RAISE_ERROR("IPModel_GAP_Calc: "//gap_b200_error_string(), error)
+!   end if
+!   if (do_energy_per_coordinate) then                        ! :573 (sum_in_place over mpi first, :549)
+!      ierr = gap_potential_get_energy_per_coordinate(this%b200, energy_per_coordinate)
+!      call set_param_value(at, trim(calc_energy_per_coordinate), energy_per_coordinate)
+!   end if
+!   if (do_local_gap_variance) then                           ! :558-571 (sum_in_place over mpi first, :545-548)
+!      call add_property(at, trim(calc_local_gap_variance), 0.0_dp, ptr=local_gap_variance_pointer)
+!      call add_property(at, "gap_variance_gradient", 0.0_dp, n_cols=3, ptr2=gap_variance_gradient_pointer)
+!      ierr = gap_potential_get_local_gap_variance(this%b200, at%N, local_gap_variance_pointer, c_loc(gap_variance_gradient_pointer))
 !   end if
 !   if (present(mpi)) then                                    ! IPModel_GAP.f95:538-556, unchanged
 !      if (mpi%active) then
