@@ -136,13 +136,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
   const unsigned sA0 = (unsigned)__cvta_generic_to_shared(As + lrow * LDS_ROW + lcc);
   const unsigned sB0 = (unsigned)__cvta_generic_to_shared(Bs + lrow * LDS_ROW + lcc);
   constexpr unsigned A_STAGE = BM * LDS_ROW * 8, B_STAGE = BN * LDS_ROW * 8;
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; s++) {
-    if (s < KT) load_stage<BN>(sA0 + s * A_STAGE, sB0 + s * B_STAGE, gA + s * BK, gB + s * BK, lda16, ldb16);
-    cp_async_commit();
-  }
   if constexpr (!std::is_same<Epi, EpiStore>::value) {
-    // the tile's GP weights ride along with the first slabs (read in the epilogue)
+    // the tile's GP weights ride along ahead of the first slabs (read in the epilogue)
     double* wsm = Bs + (size_t)STAGES * BN * LDS_ROW;
     if (threadIdx.x < BN / 2) {
       unsigned sw = (unsigned)__cvta_generic_to_shared(wsm + 2 * threadIdx.x);
@@ -150,32 +145,50 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
     }
     cp_async_commit();
   }
+  // Software pipeline, two levels.  Global -> shared: all STAGES slabs are requested up front; slab kt + STAGES is requested as
+  // soon as every warp has taken its last fragments of slab kt.  Shared -> registers: the fragments of k-step kk+1 (of the next
+  // slab when kk is the last step) are loaded into the OTHER fragment buffer before the DMMAs of step kk are issued, so a load
+  // never waits for the tensor pipe to release the registers it overwrites and the pipe never waits for a load.
+#pragma unroll
+  for (int s = 0; s < STAGES; s++) {
+    if (s < KT) load_stage<BN>(sA0 + s * A_STAGE, sB0 + s * B_STAGE, gA + s * BK, gB + s * BK, lda16, ldb16);
+    cp_async_commit();
+  }
+  cp_async_wait<STAGES - 1>();  // slab 0 (and the weights) have landed
+  __syncthreads();
+  double af[2][MT], bf[2][NTL];
+  auto load_frag = [&](int buf, int stage, int kk) {
+    const double* as = As + (size_t)stage * BM * LDS_ROW + (wm * WTM + fr) * LDS_ROW + fk + kk * 4;
+    const double* bs = Bs + (size_t)stage * BN * LDS_ROW + (wn * WTN + fr) * LDS_ROW + fk + kk * 4;
+#pragma unroll
+    for (int i = 0; i < MT; i++) af[buf][i] = as[i * 8 * LDS_ROW];
+#pragma unroll
+    for (int j = 0; j < NTL; j++) bf[buf][j] = bs[j * 8 * LDS_ROW];
+  };
+  if (KT > 0) load_frag(0, 0, 0);
   for (int kt = 0; kt < KT; kt++) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {  // prefetch slab kt+STAGES-1 into the stage that was consumed in iteration kt-1
-      int kn = kt + STAGES - 1;
-      if (kn < KT) {
-        int s = kn % STAGES;
-        load_stage<BN>(sA0 + s * A_STAGE, sB0 + s * B_STAGE, gA + (size_t)kn * BK, gB + (size_t)kn * BK, lda16, ldb16);
-      }
-      cp_async_commit();
-    }
-    const double* as = As + (size_t)(kt % STAGES) * BM * LDS_ROW + (wm * WTM + fr) * LDS_ROW + fk;
-    const double* bs = Bs + (size_t)(kt % STAGES) * BN * LDS_ROW + (wn * WTN + fr) * LDS_ROW + fk;
     const int nk = (kt_beg + kt == KT_all - 1) ? nk_last : BK / 4;
+    const bool has_next = kt + 1 < KT;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; kk++) {
       if (kk >= nk) break;
-      double af[MT], bf[NTL];
-#pragma unroll
-      for (int i = 0; i < MT; i++) af[i] = as[i * 8 * LDS_ROW + kk * 4];
-#pragma unroll
-      for (int j = 0; j < NTL; j++) bf[j] = bs[j * 8 * LDS_ROW + kk * 4];
+      if (kk + 1 < nk) {
+        load_frag((kk + 1) & 1, kt % STAGES, kk + 1);
+      } else if (has_next) {
+        cp_async_wait<STAGES - 2>();  // slab kt+1 has landed ...
+        __syncthreads();              // ... for everybody, and everybody holds its last fragments of slab kt: its stage is free
+        const int kn = kt + STAGES;
+        if (kn < KT) {
+          const int st = kt % STAGES;
+          load_stage<BN>(sA0 + st * A_STAGE, sB0 + st * B_STAGE, gA + (size_t)kn * BK, gB + (size_t)kn * BK, lda16, ldb16);
+        }
+        cp_async_commit();
+        load_frag((kk + 1) & 1, (kt + 1) % STAGES, 0);
+      }
 #pragma unroll
       for (int i = 0; i < MT; i++)
 #pragma unroll
-        for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], af[kk & 1][i], bf[kk & 1][j]);
     }
   }
   cp_async_wait<0>();
