@@ -101,6 +101,18 @@ int gap_potential_calc_device(gap_potential* pot, int N, const double* d_pos, co
 int gap_md_run(gap_potential* pot, int N, double* pos, double* velo, const int* Z, const double* mass, const double* lattice, const int* pbc,
                double dt, int n_steps, const char* args_str, double* epot, double* ekin);
 
+/* Same dynamics on DEVICE-resident state, for runs partitioned over several GPUs (BASELINE config C: MD with per-step
+ * neighbour-list rebuild at 1/2/4/8 GPUs).  Every rank holds the whole state (d_pos, d_velo, d_mass, d_Z: device pointers,
+ * updated in place) and evaluates its block of centres (gap_potential_set_partition); after each evaluation has been
+ * enqueued the library calls reduce(reduce_ctx, stream), which must enqueue ON THAT STREAM the sum of d_packed[10 + 3*N]
+ * over the ranks (the reference's sum_in_place calls, IPModel_GAP.f95:538-556; quip_b200.ShardedPotential passes an NCCL
+ * all-reduce).  All ranks then integrate all atoms with identical forces, so the replicas stay bit-identical and no
+ * position exchange is needed.  reduce may be NULL on a single rank. */
+typedef void (*gap_reduce_fn)(void* reduce_ctx, void* stream);
+int gap_md_run_device(gap_potential* pot, int N, double* d_pos, double* d_velo, const int* d_Z, const double* d_mass, const double* lattice,
+                      const int* pbc, double dt, int n_steps, const char* args_str, double* d_packed, gap_reduce_fn reduce, void* reduce_ctx,
+                      double* epot, double* ekin, void* stream);
+
 /* ---- LAMMPS `pair_style quip` ABI: the three bind(c) symbols of src/Potentials/quip_lammps_wrapper.f95 (:24, :30-56,
  * :158-168) with identical names and argument lists (all by reference), so that LAMMPS' pair_quip.cpp links against
  * libgapb200.so instead of libquip.  The neighbour list is the caller's (full list of the local atoms, 1-based neighbour

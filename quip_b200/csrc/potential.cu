@@ -1193,68 +1193,104 @@ int gap_potential_calc(gap_potential* P, int N, const double* pos, const int* Z,
   });
 }
 
+namespace {
+// DynamicalSystem_run core on device-resident state.  reduce (may be NULL) is called after every force evaluation has been
+// enqueued and must enqueue, on the same stream, the reduction of d_packed over the ranks of a partitioned run.
+void md_run_impl(gap_potential* P, int N, double* d_pos, double* d_velo, const int* d_Z, const double* d_mass, const double* lattice, const int* pbc,
+                 double dt, int n_steps, const char* args_str, double* d_packed, gap_reduce_fn reduce, void* reduce_ctx, double* epot, double* ekin,
+                 cudaStream_t st) {
+  const size_t n3 = 3 * (size_t)N;
+  P->b_velo2.ensure(sizeof(double) * n3);
+  P->b_acc.ensure(sizeof(double) * n3);
+  P->b_ke.ensure(sizeof(double) * 128);
+  P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
+  double* velo_cur = d_velo;
+  double* velo_new = P->b_velo2.as<double>();
+  const int nb = (int)((n3 + 255) / 256);
+  double ke_part[128];
+  auto evaluate = [&](int step) {  // calc(pot, atoms, "energy force") with the per-step neighbour-list rebuild (Potential.f95:2340-2365)
+    for (int attempt = 0; attempt < 2; attempt++) {
+      calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, true, d_packed, P->b_le.as<double>(), nullptr, st);
+      if (reduce) reduce(reduce_ctx, (void*)st);  // partial [E | virial | F] -> totals on every rank (IPModel_GAP.f95:538-556)
+      // the new velocities go to a second buffer: if the speculatively sized neighbour list overflowed, the evaluation is simply repeated
+      k_verlet2<<<nb, 256, 0, st>>>(N, dt, d_packed + 10, d_mass, velo_cur, velo_new, P->b_acc.as<double>(), step > 0 ? 1 : 0);
+      P->launches += 1;
+      if (ekin) {
+        k_kinetic<<<128, 256, 0, st>>>(N, d_mass, velo_new, P->b_ke.as<double>());
+        P->launches += 1;
+        CUDA_OK(cudaMemcpyAsync(ke_part, P->b_ke.p, sizeof(ke_part), cudaMemcpyDeviceToHost, st));
+      }
+      double e = 0.0;
+      CUDA_OK(cudaMemcpyAsync(&e, d_packed, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      // a rank whose neighbour rows overflowed has NaN-poisoned its energy word (k_finalize): after the reduction every rank sees
+      // it, so all ranks repeat together (the local verification also refreshes the row-capacity hint)
+      const bool ok_local = verify_connect(P);
+      if (!ok_local || e != e) {
+        if (attempt == 1) throw GapError("gap_md_run: the neighbour list overflowed twice (non-finite positions or energies?)");
+        if (ok_local) P->row_hint = -1;  // another rank overflowed: take the exact path together with it
+        continue;
+      }
+      std::swap(velo_cur, velo_new);
+      if (epot) epot[step] = e;
+      if (ekin) {
+        double t = 0.0;
+        for (int k = 0; k < 128; k++) t += ke_part[k];
+        ekin[step] = t;
+      }
+      break;
+    }
+  };
+  evaluate(0);  // initial forces -> accelerations (Potential.f95:2348-2351)
+  for (int n = 1; n <= n_steps; n++) {
+    k_verlet1<<<nb, 256, 0, st>>>(N, dt, d_pos, velo_cur, P->b_acc.as<double>());
+    P->launches += 1;
+    evaluate(n);
+  }
+  if (velo_cur != d_velo) CUDA_OK(cudaMemcpyAsync(d_velo, velo_cur, sizeof(double) * n3, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+}
+}  // namespace
+
 int gap_md_run(gap_potential* P, int N, double* pos, double* velo, const int* Z, const double* mass, const double* lattice, const int* pbc,
                double dt, int n_steps, const char* args_str, double* epot, double* ekin) {
   return guard([&] {
     if (!P) throw GapError("gap_md_run: pot is NULL");
     if (N <= 0 || !pos || !velo || !Z || !mass) throw GapError("gap_md_run: N, pos, velo, Z and mass are required");
     if (n_steps < 0) throw GapError("gap_md_run: n_steps < 0");
-    if (P->n_ranks != 1) throw GapError("gap_md_run: the MD driver runs on one GPU (use calc_device + your own integrator for sharded runs)");
+    if (P->n_ranks != 1) throw GapError("gap_md_run: a partitioned run needs the reduction hook of gap_md_run_device");
     CUDA_OK(cudaSetDevice(P->device));
     cudaStream_t st = P->stream;
     const size_t n3 = 3 * (size_t)N;
     P->b_pos.ensure(sizeof(double) * (n3 + 3));
     P->b_Z.ensure(sizeof(int) * (size_t)(N + 1));
     P->b_velo.ensure(sizeof(double) * n3);
-    P->b_velo2.ensure(sizeof(double) * n3);
-    P->b_acc.ensure(sizeof(double) * n3);
     P->b_mass.ensure(sizeof(double) * (size_t)N);
-    P->b_ke.ensure(sizeof(double) * 128);
     P->b_packed.ensure(sizeof(double) * (10 + n3));
-    P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
     CUDA_OK(cudaMemcpyAsync(P->b_pos.p, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(P->b_velo.p, velo, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(P->b_Z.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(P->b_mass.p, mass, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
-    const int nb = (int)((n3 + 255) / 256);
-    double ke_part[128];
-    auto evaluate = [&](int step) {  // calc(pot, atoms, "energy force") with the per-step neighbour-list rebuild (Potential.f95:2340-2365)
-      for (int attempt = 0; attempt < 2; attempt++) {
-        calc_device_impl(P, N, P->b_pos.as<double>(), P->b_Z.as<int>(), lattice, pbc, args_str, true, P->b_packed.as<double>(), P->b_le.as<double>(),
-                         nullptr, st);
-        // the new velocities go to a second buffer: if the speculatively sized neighbour list overflowed, the evaluation is simply repeated
-        k_verlet2<<<nb, 256, 0, st>>>(N, dt, P->b_packed.as<double>() + 10, P->b_mass.as<double>(), P->b_velo.as<double>(), P->b_velo2.as<double>(),
-                                      P->b_acc.as<double>(), step > 0 ? 1 : 0);
-        P->launches += 1;
-        if (ekin) {
-          k_kinetic<<<128, 256, 0, st>>>(N, P->b_mass.as<double>(), P->b_velo2.as<double>(), P->b_ke.as<double>());
-          P->launches += 1;
-          CUDA_OK(cudaMemcpyAsync(ke_part, P->b_ke.p, sizeof(ke_part), cudaMemcpyDeviceToHost, st));
-        }
-        double e = 0.0;
-        CUDA_OK(cudaMemcpyAsync(&e, P->b_packed.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-        CUDA_OK(cudaStreamSynchronize(st));
-        if (!verify_connect(P)) continue;  // repeat with the exact list size
-        std::swap(P->b_velo, P->b_velo2);
-        if (epot) epot[step] = e;
-        if (ekin) {
-          double t = 0.0;
-          for (int k = 0; k < 128; k++) t += ke_part[k];
-          ekin[step] = t;
-        }
-        break;
-      }
-    };
-    evaluate(0);  // initial forces -> accelerations (Potential.f95:2348-2351)
-    for (int n = 1; n <= n_steps; n++) {
-      k_verlet1<<<nb, 256, 0, st>>>(N, dt, P->b_pos.as<double>(), P->b_velo.as<double>(), P->b_acc.as<double>());
-      P->launches += 1;
-      evaluate(n);
-    }
+    md_run_impl(P, N, P->b_pos.as<double>(), P->b_velo.as<double>(), P->b_Z.as<int>(), P->b_mass.as<double>(), lattice, pbc, dt, n_steps, args_str,
+                P->b_packed.as<double>(), nullptr, nullptr, epot, ekin, st);
     CUDA_OK(cudaMemcpyAsync(pos, P->b_pos.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaMemcpyAsync(velo, P->b_velo.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    CUDA_OK(cudaGetLastError());
+  });
+}
+
+int gap_md_run_device(gap_potential* P, int N, double* d_pos, double* d_velo, const int* d_Z, const double* d_mass, const double* lattice,
+                      const int* pbc, double dt, int n_steps, const char* args_str, double* d_packed, gap_reduce_fn reduce, void* reduce_ctx,
+                      double* epot, double* ekin, void* stream) {
+  return guard([&] {
+    if (!P) throw GapError("gap_md_run_device: pot is NULL");
+    if (N <= 0 || !d_pos || !d_velo || !d_Z || !d_mass || !d_packed) throw GapError("gap_md_run_device: N, d_pos, d_velo, d_Z, d_mass and d_packed are required");
+    if (n_steps < 0) throw GapError("gap_md_run_device: n_steps < 0");
+    if (P->n_ranks != 1 && !reduce) throw GapError("gap_md_run_device: a partitioned run needs the reduction hook");
+    CUDA_OK(cudaSetDevice(P->device));
+    md_run_impl(P, N, d_pos, d_velo, d_Z, d_mass, lattice, pbc, dt, n_steps, args_str, d_packed, reduce, reduce_ctx, epot, ekin,
+                stream ? (cudaStream_t)stream : P->stream);
   });
 }
 

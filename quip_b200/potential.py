@@ -39,6 +39,8 @@ ABI = {
     "gap_potential_calc_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_dp, c_ip, C.c_char_p, C.c_int,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gap_md_run": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_ip, C.c_double, C.c_int, C.c_char_p, c_dp, c_dp]),
+    "gap_md_run_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_dp, c_ip, C.c_double, C.c_int,
+                                    C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, c_dp, c_dp, C.c_void_p]),
     "quip_lammps_api_version": (C.c_int, []),
     "quip_lammps_potential_initialise": (None, [c_ip, c_ip, c_dp, C.c_char_p, c_ip, C.c_char_p, c_ip]),
     "quip_lammps_wrapper": (None, [c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_dp, c_ip, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
@@ -439,6 +441,42 @@ class ShardedPotential:
         """The path's one collective: sum of the per-rank partial [E | virial | F] buffers."""
         if self.world_size > 1:
             reduce_packed(d_packed, self.group)
+
+    def run(self, atoms, velocities, dt=1.0, n_steps=10, masses=None, args_str=""):
+        """Sharded ``DynamicalSystem_run`` (Potential.f95:2304; BASELINE config C): NVE velocity Verlet with the neighbour list
+        rebuilt on the device every step.  Every rank keeps the whole state resident on its GPU and evaluates its block of
+        centres; the library calls back after each evaluation to enqueue the all-reduce of ``[E | virial | F]``, then all ranks
+        integrate all atoms with the same forces.  Updates ``atoms.positions``; returns (velocities, epot, ekin)."""
+        torch = self.torch
+        pos, Z, lat, pbc = _geometry(atoms)
+        N = len(Z)
+        m = np.ascontiguousarray(element_masses(Z) if masses is None else masses, dtype=np.float64)
+        dev = self.device
+        d_pos = torch.tensor(pos, dtype=torch.float64, device=dev)
+        d_vel = torch.tensor(np.ascontiguousarray(velocities, dtype=np.float64), device=dev)
+        d_Z = torch.tensor(Z, dtype=torch.int32, device=dev)
+        d_m = torch.tensor(m, dtype=torch.float64, device=dev)
+        d_packed = torch.zeros(10 + 3 * N, dtype=torch.float64, device=dev)
+        ep, ek = np.zeros(n_steps + 1), np.zeros(n_steps + 1)
+        errors = []
+
+        def _reduce(_ctx, _stream):  # called from inside gap_md_run_device on this thread; enqueues on self.stream
+            try:
+                with torch.cuda.stream(self.stream):
+                    self.reduce_packed(d_packed)
+            except Exception as exc:  # an exception cannot cross the C frame
+                errors.append(exc)
+
+        cb = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)(_reduce)
+        torch.cuda.current_stream(dev).synchronize()
+        _check(load_library().gap_md_run_device(self.pot._h, N, d_pos.data_ptr(), d_vel.data_ptr(), d_Z.data_ptr(), d_m.data_ptr(), _dp(lat),
+                                                _ip(pbc), float(dt), int(n_steps), (self.pot.calc_args + " " + args_str).strip().encode(),
+                                                d_packed.data_ptr(), C.cast(cb, C.c_void_p) if self.world_size > 1 else None, None,
+                                                _dp(ep), _dp(ek), self.stream.cuda_stream))
+        if errors:
+            raise errors[0]
+        atoms.positions[...] = d_pos.cpu().numpy()
+        return d_vel.cpu().numpy(), ep, ek
 
     def calc_resident(self, N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad=True):
         """Inputs and outputs are device tensors; work is enqueued on torch's current stream (on ``self.stream``, ordered

@@ -500,6 +500,25 @@ def test_md_energy_conservation_config_A_shape(tmp_path):
     assert abs(epot[-1] - epot[0]) > 1e-6  # and something actually moved
 
 
+def test_sharded_md_driver_single_rank_matches_md_run(si_model, si_frames):
+    # gap_md_run_device (device-resident state + reduction hook; the hook is exercised at world size 2 by
+    # tools/md_sharded_check.py under torchrun) against gap_md_run on the same trajectory
+    from quip_b200 import ShardedPotential
+
+    pot, om, xml = si_model
+    a = si_frames[8]
+    rng = np.random.default_rng(5)
+    v0 = rng.normal(scale=0.01, size=a.positions.shape)
+    at1 = Atoms(a.numbers, a.positions.copy(), a.cell, True)
+    v1, ep1, ek1 = pot.run(at1, v0, dt=1.0, n_steps=5)
+    sp = ShardedPotential("IP GAP", param_filename=xml, rank=0, world_size=1)
+    at2 = Atoms(a.numbers, a.positions.copy(), a.cell, True)
+    v2, ep2, ek2 = sp.run(at2, v0, dt=1.0, n_steps=5)
+    assert np.abs(at1.positions - at2.positions).max() < 1e-10
+    assert np.abs(v1 - v2).max() < 1e-10
+    assert np.abs(ep1 - ep2).max() < 1e-9 and np.abs(ek1 - ek2).max() < 1e-9
+
+
 def test_quip_cli_known_answer(golden):
     # `quip atoms_filename=gap_sample.xyz param_filename=GAP.xml E F V` (quip.f95:135-235, 698-821)
     import io
