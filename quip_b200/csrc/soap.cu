@@ -1096,10 +1096,11 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
   }
   const int i = centres[c];
   // E_i = sum over the column tiles of GEMM-1 (fixed order) ; local_e(centre) += E_i  (IPModel_GAP.f95:454-459, cc = 1, |ci| = 1)
-  if (epart && threadIdx.x == 0) {
+  if (epart && threadIdx.x < 32) {  // warp 0: the column-tile partials in parallel, shuffle tree (fixed order)
     double t = 0.0;
-    for (int k = 0; k < n_tiles_n; k++) t += epart[(size_t)c * n_tiles_n + k];
-    local_e[i] += e_scale * t;
+    for (int k = threadIdx.x; k < n_tiles_n; k += 32) t += epart[(size_t)c * n_tiles_n + k];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) local_e[i] += e_scale * t;
   }
   const Geo g = make_geo(CN ? CN : sp->n_max, CN ? CL : sp->l_max, CN ? CNS : sp->n_species);
   const int n = g.n, L = g.L, L1 = g.L1, nlm = g.nlm, K1 = g.K1, d = sp->d, ns = g.ns;
