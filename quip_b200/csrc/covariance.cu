@@ -11,13 +11,21 @@
 // The reference streams sparseX twice per atom; here sparseX is read once per 128 atoms and stays L2 resident.
 //
 // Both GEMMs are the same "NT" kernel (A[m][k], B[n][k], K contiguous in both), built on the FP64 tensor-core
-// instruction mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- tcgen05 has no FP64 kind), fed by a 3-stage
-// cp.async pipeline.  CTA tile 64 x BN x 16 (BN = 128 or 112), 4 warps as 2(M) x 2(N), warp tile 32 x BN/2 =
+// instruction mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4 -- tcgen05 has no FP64 kind).  The operand slabs (16 doubles =
+// 128 bytes per row) are brought in by the TMA engine (cp.async.bulk.tensor.2d, SASS UTMALDG) into a 4-stage ring of dense,
+// 128B-swizzled stages; one thread arms the stage's mbarrier and issues the two copies, everybody waits on the mbarrier.
+// (Per-thread cp.async copies were the one part of the old main loop that cost DMMA issue slots: tools/dmma_loop_probe.cu.)
+// Lane (fr, fk) of a DMMA fragment owns k = 4 fk .. 4 fk + 3 of every slab -- a permutation of k common to both operands -- so
+// its operands are two LDS.128 per row and slab, conflict-free under the swizzle (16-byte chunk (2 fk + h) ^ fr); the K tail
+// (K is a multiple of 4, not of 16; the TMA zero-fills beyond K) runs its last slab in the plain k order with LDS.64.  CTA tile 64 x BN x 16 (BN = 128 or 112), 4 warps as 2(M) x 2(N), warp tile 32 x BN/2 =
 // 4 x (8 or 7) DMMA tiles, TWO CTAs resident per SM so that one CTA's epilogue (the kernel non-linearity and the
 // 64 x BN store) overlaps the other's main loop and the tail is balanced at half-tile granularity.  GEMM-2 can be
 // split along K (= the sparse-point index) into `ksplit` partial outputs when it has too few tiles to fill 148 SMs;
-// the consumer (the SOAP adjoint kernel) adds the partials in a fixed order.  Shared-memory rows are padded to
-// 20 doubles so that the (8 rows x 4 k) fragment loads of a half-warp hit 16 distinct 8-byte banks.
+// the consumer (the SOAP adjoint kernel) adds the partials in a fixed order.
+#include <cuda.h>
+
+#include <stdexcept>
+#include <string>
 #include <type_traits>
 
 #include "gap_device.cuh"
@@ -30,39 +38,39 @@ constexpr int BM = COV_BM, BK = COV_BK;
 constexpr int WARPS_M = 2, WARPS_N = 2, NTHREADS = WARPS_M * WARPS_N * 32;
 constexpr int WTM = BM / WARPS_M;   // 32
 constexpr int MT = WTM / 8;         // 4 DMMA tiles along M per warp
-constexpr int LDS_ROW = BK + 4;     // padded row (doubles)
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
+constexpr unsigned ROW_BYTES = BK * sizeof(double);  // 128: one swizzle span
+static_assert(ROW_BYTES == 128, "a slab row is one 128-byte swizzle span");
 template <int BN>
-constexpr size_t gemm_smem() { return ((size_t)STAGES * (BM + BN) * LDS_ROW + BN) * sizeof(double); }  // + the tile's GP weights
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+constexpr size_t gemm_smem() {  // 1 KiB alignment slack + stages + GP weights of the tile + epilogue row sums + mbarriers
+  return 1024 + (size_t)STAGES * (BM + BN) * ROW_BYTES + (BN + WARPS_N * BM) * sizeof(double) + STAGES * 8;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-
-// One K-slab (BK columns) of the A and B tiles -> a pipeline stage.  With BK/2 = 8 sixteen-byte chunks per row and 128
-// threads, thread t always copies column chunk (t % 8) of rows t/8, t/8 + 16, t/8 + 32, ...: the global pointers and the
-// shared addresses are computed ONCE per tile (gA/gB/sA/sB below) and only advance by constants afterwards -- the
-// index arithmetic of the first version cost more issue slots than the DMMAs of a slab.
-constexpr int CPR = BK / 2;                       // 16-byte chunks per row
-constexpr int ROWS_PER_PASS = NTHREADS / CPR;     // 16
-static_assert(BM % ROWS_PER_PASS == 0, "tile rows must be a multiple of the rows copied per pass");
-template <int BN>
-__device__ __forceinline__ void load_stage(unsigned sA, unsigned sB, const double* gA, const double* gB, size_t lda16, size_t ldb16) {
-  static_assert(BN % ROWS_PER_PASS == 0, "tile rows must be a multiple of the rows copied per pass");
-#pragma unroll
-  for (int it = 0; it < BM / ROWS_PER_PASS; it++)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sA + it * ROWS_PER_PASS * LDS_ROW * 8), "l"(gA + it * lda16));
-#pragma unroll
-  for (int it = 0; it < BN / ROWS_PER_PASS; it++)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sB + it * ROWS_PER_PASS * LDS_ROW * 8), "l"(gB + it * ldb16));
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// one box (16 k x box rows) of a row-major FP64 matrix -> a dense, 128B-swizzled stage; completion is signalled on the mbarrier
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int k0, int row0, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst), "l"(map),
+               "r"(bar), "r"(k0), "r"(row0)
+               : "memory");
 }
 
 // c^(zeta-1).  ZI = compile-time integer zeta (1..4, the usual GAP settings; fast_pow_1d multiplies repeatedly,
@@ -103,17 +111,48 @@ struct EpiStore {  // GEMM-2 epilogue
 };
 
 template <int BN, class Epi>
-__global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, int K,
+__global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K,
                                                           int row0, const int* __restrict__ n_rows_dev, Epi epi) {
   constexpr int WTN = BN / WARPS_N, NTL = WTN / 8;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* As = (double*)smem_raw;                  // [STAGES][BM][LDS_ROW]
-  double* Bs = As + (size_t)STAGES * BM * LDS_ROW;  // [STAGES][BN][LDS_ROW]
+  constexpr bool COV = !std::is_same<Epi, EpiStore>::value;
+  constexpr unsigned A_BYTES = BM * ROW_BYTES, B_BYTES = BN * ROW_BYTES, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ unsigned char smem_raw[];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (n_rows_dev && row0 + m0 >= *n_rows_dev) return;  // row tile beyond the (device-side) number of centres
+  unsigned char* const sbase = smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);  // swizzled stages: 1 KiB aligned
+  const unsigned base = (unsigned)__cvta_generic_to_shared(sbase);
+  double* const wsm = (double*)(sbase + STAGES * STAGE_BYTES);  // [BN] GP weights of this tile's columns
+  double* const red = wsm + BN;                                 // [WARPS_N][BM] row sums of the epilogue
+  const unsigned bars = base + STAGES * STAGE_BYTES + (BN + WARPS_N * BM) * sizeof(double);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
-  const int fr = lane >> 2, fk = lane & 3;  // fragment row (0..7) and k (0..3)
+  const int fr = lane >> 2, fk = lane & 3;  // fragment row (0..7) and k group (0..3)
+
+  // K range of this split (blockIdx.z of gridDim.z), in BK slabs.  K is a multiple of 4 (one DMMA k-step), not of BK.
+  const int KT_all = (K + BK - 1) / BK;
+  const int nk_last = ((K - 1) % BK) / 4 + 1;
+  const int kt_beg = (int)((long long)KT_all * blockIdx.z / gridDim.z), kt_end = (int)((long long)KT_all * (blockIdx.z + 1) / gridDim.z);
+  const int KT = kt_end - kt_beg;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  if constexpr (COV) {
+    if (threadIdx.x < BN) wsm[threadIdx.x] = epi.w[n0 + threadIdx.x];  // read in the epilogue, many barriers from here
+  }
+  __syncthreads();
+  auto issue = [&](int kt) {  // thread 0: slab kt -> stage kt % STAGES
+    const int s = kt % STAGES;
+    const unsigned bar = bars + 8 * s, sa = base + s * STAGE_BYTES;
+    mbar_expect_tx(bar, STAGE_BYTES);
+    tma_load_2d(sa, &tmA, (kt_beg + kt) * BK, m0, bar);
+    tma_load_2d(sa + A_BYTES, &tmB, (kt_beg + kt) * BK, n0, bar);
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < STAGES - 1 && s < KT; s++) issue(s);
 
   double acc[MT][NTL][2];
 #pragma unroll
@@ -121,84 +160,54 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
 #pragma unroll
     for (int j = 0; j < NTL; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  // K range of this split (blockIdx.z of gridDim.z), in BK slabs.  K is a multiple of 4 (one DMMA k-step), not of BK:
-  // the last slab is loaded whole (both operands are zero-padded to a multiple of BK) but only its first
-  // nk_last k-steps are multiplied.
-  const int KT_all = (K + BK - 1) / BK;
-  const int nk_last = ((K - 1) % BK) / 4 + 1;
-  const int kt_beg = (int)((long long)KT_all * blockIdx.z / gridDim.z), kt_end = (int)((long long)KT_all * (blockIdx.z + 1) / gridDim.z);
-  const int KT = kt_end - kt_beg;
-  // per-thread copy addresses (see load_stage)
-  const int lrow = threadIdx.x / CPR, lcc = (threadIdx.x % CPR) * 2;
-  const double* gA = A + (size_t)(m0 + lrow) * lda + (size_t)kt_beg * BK + lcc;
-  const double* gB = B + (size_t)(n0 + lrow) * ldb + (size_t)kt_beg * BK + lcc;
-  const size_t lda16 = (size_t)ROWS_PER_PASS * lda, ldb16 = (size_t)ROWS_PER_PASS * ldb;
-  const unsigned sA0 = (unsigned)__cvta_generic_to_shared(As + lrow * LDS_ROW + lcc);
-  const unsigned sB0 = (unsigned)__cvta_generic_to_shared(Bs + lrow * LDS_ROW + lcc);
-  constexpr unsigned A_STAGE = BM * LDS_ROW * 8, B_STAGE = BN * LDS_ROW * 8;
-  if constexpr (!std::is_same<Epi, EpiStore>::value) {
-    // the tile's GP weights ride along ahead of the first slabs (read in the epilogue)
-    double* wsm = Bs + (size_t)STAGES * BN * LDS_ROW;
-    if (threadIdx.x < BN / 2) {
-      unsigned sw = (unsigned)__cvta_generic_to_shared(wsm + 2 * threadIdx.x);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sw), "l"(epi.w + n0 + 2 * threadIdx.x));
-    }
-    cp_async_commit();
-  }
-  // Software pipeline, two levels.  Global -> shared: all STAGES slabs are requested up front; slab kt + STAGES is requested as
-  // soon as every warp has taken its last fragments of slab kt.  Shared -> registers: the fragments of k-step kk+1 (of the next
-  // slab when kk is the last step) are loaded into the OTHER fragment buffer before the DMMAs of step kk are issued, so a load
-  // never waits for the tensor pipe to release the registers it overwrites and the pipe never waits for a load.
-#pragma unroll
-  for (int s = 0; s < STAGES; s++) {
-    if (s < KT) load_stage<BN>(sA0 + s * A_STAGE, sB0 + s * B_STAGE, gA + s * BK, gB + s * BK, lda16, ldb16);
-    cp_async_commit();
-  }
-  cp_async_wait<STAGES - 1>();  // slab 0 (and the weights) have landed
-  __syncthreads();
-  double af[2][MT], bf[2][NTL];
-  auto load_frag = [&](int buf, int stage, int kk) {
-    const double* as = As + (size_t)stage * BM * LDS_ROW + (wm * WTM + fr) * LDS_ROW + fk + kk * 4;
-    const double* bs = Bs + (size_t)stage * BN * LDS_ROW + (wn * WTN + fr) * LDS_ROW + fk + kk * 4;
-#pragma unroll
-    for (int i = 0; i < MT; i++) af[buf][i] = as[i * 8 * LDS_ROW];
-#pragma unroll
-    for (int j = 0; j < NTL; j++) bf[buf][j] = bs[j * 8 * LDS_ROW];
-  };
-  if (KT > 0) load_frag(0, 0, 0);
+  // this lane's fragment rows inside a stage; element (row, k) sits at row * 128 + (((k >> 1) ^ (row & 7)) << 4) + (k & 1) * 8
+  const unsigned offA = (wm * WTM + fr) * ROW_BYTES, offB = A_BYTES + (wn * WTN + fr) * ROW_BYTES;
+  const unsigned ch0 = ((2 * fk) ^ fr) << 4, ch1 = ((2 * fk + 1) ^ fr) << 4;
   for (int kt = 0; kt < KT; kt++) {
-    const int nk = (kt_beg + kt == KT_all - 1) ? nk_last : BK / 4;
-    const bool has_next = kt + 1 < KT;
+    const int s = kt % STAGES;
+    mbar_wait(bars + 8 * s, (kt / STAGES) & 1);
+    __syncthreads();  // everybody has finished slab kt-1: its stage may be refilled
+    if (threadIdx.x == 0 && kt + STAGES - 1 < KT) issue(kt + STAGES - 1);
+    const unsigned st = base + s * STAGE_BYTES;
+    if (kt_beg + kt == KT_all - 1 && nk_last < BK / 4) {
+      // K tail: plain k order (k = 4 kk + fk), only the k-steps that hold data (two-way bank conflicts, once per tile)
+      for (int kk = 0; kk < nk_last; kk++) {
+        const int k = 4 * kk + fk;
+        const unsigned ch = ((unsigned)((k >> 1) ^ fr) << 4) + (k & 1) * 8;
+        double af[MT], bf[NTL];
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; kk++) {
-      if (kk >= nk) break;
-      if (kk + 1 < nk) {
-        load_frag((kk + 1) & 1, kt % STAGES, kk + 1);
-      } else if (has_next) {
-        cp_async_wait<STAGES - 2>();  // slab kt+1 has landed ...
-        __syncthreads();              // ... for everybody, and everybody holds its last fragments of slab kt: its stage is free
-        const int kn = kt + STAGES;
-        if (kn < KT) {
-          const int st = kt % STAGES;
-          load_stage<BN>(sA0 + st * A_STAGE, sB0 + st * B_STAGE, gA + (size_t)kn * BK, gB + (size_t)kn * BK, lda16, ldb16);
-        }
-        cp_async_commit();
-        load_frag((kk + 1) & 1, (kt + 1) % STAGES, 0);
+        for (int i = 0; i < MT; i++) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(af[i]) : "r"(st + offA + i * 8 * ROW_BYTES + ch));
+#pragma unroll
+        for (int j = 0; j < NTL; j++) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(bf[j]) : "r"(st + offB + j * 8 * ROW_BYTES + ch));
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+          for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
+    } else {
 #pragma unroll
-      for (int i = 0; i < MT; i++)
+      for (int h = 0; h < 2; h++) {
+        const unsigned ch = h ? ch1 : ch0;
+        double a0[MT], a1[MT], b0[NTL], b1[NTL];  // k = 4 fk + 2 h and 4 fk + 2 h + 1
 #pragma unroll
-        for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], af[kk & 1][i], bf[kk & 1][j]);
+        for (int i = 0; i < MT; i++) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(a0[i]), "=d"(a1[i]) : "r"(st + offA + i * 8 * ROW_BYTES + ch));
+#pragma unroll
+        for (int j = 0; j < NTL; j++) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(b0[j]), "=d"(b1[j]) : "r"(st + offB + j * 8 * ROW_BYTES + ch));
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+          for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], a0[i], b0[j]);
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+          for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], a1[i], b1[j]);
+      }
     }
   }
-  cp_async_wait<0>();
-  __syncthreads();
 
   // ---- epilogue: thread holds C[row = fr][col = 2*fk, 2*fk+1] of every 8x8 tile ----
-  if constexpr (!std::is_same<Epi, EpiStore>::value) {
+  if constexpr (COV) {
     const Epi& e = epi;
-    double* red = (double*)smem_raw;  // [WARPS_N][BM] (the pipeline stages are drained)
-    const double* wsm = Bs + (size_t)STAGES * BN * LDS_ROW;
     const double zeta = e.cp.zeta;
     const bool zeta0 = e.cp.zeta_int == 0;
     double wv[NTL][2];
@@ -208,7 +217,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const double* __restri
       wv[j][0] = t.x;
       wv[j][1] = t.y;
     }
-    __syncthreads();  // everyone has its weights: the stage area may now be reused for the row sums
 #pragma unroll
     for (int i = 0; i < MT; i++) {
       int row = m0 + wm * WTM + i * 8 + fr;
@@ -258,6 +266,36 @@ __global__ void k_energy_rows(const double* __restrict__ epart, int n_tiles_n, c
   local_e[centres[c]] += e_scale * t;
 }
 
+
+
+// ---- TMA descriptors (host) ----
+// cuTensorMapEncodeTiled comes from the driver; it is looked up once through the runtime, so the library does not link libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  if (!fn) throw std::runtime_error("cuTensorMapEncodeTiled is not available from this CUDA driver (the covariance GEMM needs TMA)");
+  return fn;
+}
+// row-major FP64 matrix [rows][ld] of which the first K columns are valid (the TMA zero-fills beyond K and beyond rows);
+// box = one slab (16 k) x box_rows rows, written to shared memory with the 128-byte swizzle
+CUtensorMap operand_map(const double* ptr, long rows, int K, int ld, int box_rows) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return m;
+}
+
 }  // namespace
 
 // Column tile of GEMM-1 for n_rows_pad rows and M sparse points.  All tiles of one launch cost the same, so the launch
@@ -285,8 +323,9 @@ void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, 
     constexpr int BN = decltype(bn_tag)::value;
     using E = decltype(e);
     dim3 grid((M + BN - 1) / BN, n_rows_pad / BM, 1);
+    const CUtensorMap tmA = operand_map(x, n_rows_pad, K, ldx, BM), tmB = operand_map(sp_rows, (long)grid.x * BN, K, lds, BN);
     cudaFuncSetAttribute(k_dgemm_nt<BN, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<BN>());
-    k_dgemm_nt<BN, E><<<grid, NTHREADS, gemm_smem<BN>(), st>>>(x, ldx, sp_rows, lds, K, row0, n_rows_dev, e);
+    k_dgemm_nt<BN, E><<<grid, NTHREADS, gemm_smem<BN>(), st>>>(tmA, tmB, K, row0, n_rows_dev, e);
   };
   auto by_zeta = [&](auto bn_tag) {
     switch (cp.zeta_int) {
@@ -327,12 +366,13 @@ void launch_cov_gemm2(const double* acoef, int lda, const double* st_rows, int l
                       int bn, int ksplit, int K, double* gvec, int ldg, size_t split_stride, cudaStream_t st, int* launches) {
   EpiStore e{gvec, ldg, split_stride};
   dim3 grid(dn_pad / bn, n_rows_pad / BM, ksplit);
+  const CUtensorMap tmA = operand_map(acoef, n_rows_pad, K, lda, BM), tmB = operand_map(st_rows, dn_pad, K, ldst, bn == 112 ? 112 : 128);
   if (bn == 112) {
     cudaFuncSetAttribute(k_dgemm_nt<112, EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<112>());
-    k_dgemm_nt<112, EpiStore><<<grid, NTHREADS, gemm_smem<112>(), st>>>(acoef, lda, st_rows, ldst, K, row0, n_rows_dev, e);
+    k_dgemm_nt<112, EpiStore><<<grid, NTHREADS, gemm_smem<112>(), st>>>(tmA, tmB, K, row0, n_rows_dev, e);
   } else {
     cudaFuncSetAttribute(k_dgemm_nt<128, EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128>());
-    k_dgemm_nt<128, EpiStore><<<grid, NTHREADS, gemm_smem<128>(), st>>>(acoef, lda, st_rows, ldst, K, row0, n_rows_dev, e);
+    k_dgemm_nt<128, EpiStore><<<grid, NTHREADS, gemm_smem<128>(), st>>>(tmA, tmB, K, row0, n_rows_dev, e);
   }
   *launches += 1;
 }
