@@ -658,13 +658,16 @@ struct WSmem {
   double *X, *acc, *nbd, *nbr, *nbf, *nbdf, *p;  // per warp
   int *nbj, *nbs, *ord;
 };
+constexpr int NBWA = 32;  // adjoint: every 32-entry chunk of the neighbour row is worked off at once
 __host__ __device__ __forceinline__ size_t carve_w(const Geo& g, int d_pad, bool adjoint, int warp, WSmem* w, unsigned char* base) {
+  const int NBW = adjoint ? NBWA : gapb200::NBW;
   size_t o = 0;
   auto take = [&](size_t cnt) { size_t r = o; o += ((cnt + 1) & ~(size_t)1) * sizeof(double); return r; };
   const size_t oT = take((size_t)g.n8 * g.TS), orb = take(g.n), oyn = take((size_t)g.L1 * (g.L1 + 1) / 2), oinv = take(16), odbl = take(20);
   const size_t tables = o;
   o = 0;
-  const size_t oX = take((size_t)g.XR * g.XS), oacc = take(adjoint ? 96 : 0);
+  // adjoint: 8 x 12 centre force / virial slots, then an 8 x XS scratch tile (Lambda between its two tensor-core products)
+  const size_t oX = take((size_t)g.XR * g.XS), oacc = take(adjoint ? 96 + 8 * g.XS : 0);
   const size_t oreg = o;
   const size_t onbd = take(3 * NBW), onbr = take(NBW), onbf = take(NBW), onbdf = take(adjoint ? NBW : 0);
   const size_t oint = o;
@@ -910,7 +913,7 @@ __global__ void __launch_bounds__(NT, (CN > 8 ? 2 : 4)) k_soap_forward_w(const S
 template <int CN, int CL>
 __device__ __forceinline__ void adjoint_tile(const Smem& s, const Geo& g, const double alpha, const int sk, const int q0, const int tn, const int fr,
                                              const int fk, const double e_scale, double* __restrict__ force,
-                                             double* __restrict__ local_virial, double* accs) {
+                                             double* __restrict__ local_virial, double* accs, const int* ord = nullptr) {
   constexpr bool SPEC = CN != 0;
   constexpr int KS = SPEC ? (CN + 3) / 4 : (SOAP_NMAX_CAP + 3) / 4;   // DMMA k steps over the radial channels of one species
   constexpr int NG = SPEC ? (CL >= 8 ? 2 : 1) : 2;                    // groups of 8 orders |m|
@@ -918,7 +921,9 @@ __device__ __forceinline__ void adjoint_tile(const Smem& s, const Geo& g, const 
   constexpr int NMJ = 2 + NJ1;
   const int n = g.n, L = SPEC ? CL : g.L, XS = g.XS;
   const bool vq = fr < tn;
-  const int q = q0 + (vq ? fr : 0);  // padding rows reuse the tile's first neighbour with f = f' = 0: their A fragments vanish
+  // padding rows reuse the tile's first neighbour with f = f' = 0: their A fragments vanish; ord (may be NULL) lists the
+  // buffer entries of the tile's species
+  const int q = ord ? ord[q0 + (vq ? fr : 0)] : q0 + (vq ? fr : 0);
   const double r = s.nbr[q], rinv = 1.0 / r;
   const double dx = s.nbd[3 * q], dy = s.nbd[3 * q + 1], dz = s.nbd[3 * q + 2];
   const double f = vq ? s.nbf[q] : 0.0, df = vq ? s.nbdf[q] : 0.0;
@@ -1237,6 +1242,181 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// adjoint, one WARP per centre (specialised shapes): as k_soap_forward_w, a warp owns its centre from the first load to the
+// last atomic, so nothing needs a block barrier (the four warps of a CTA only share the read-only tables) and the load
+// latencies of sixteen independent centres per SM overlap.  Per-warp shared memory: X (-> Lambda~ in place, one l-aligned
+// 8-row tile at a time through a scratch tile), the 8 x 12 centre force / virial slots, and ONE region that first holds
+// u = dE/dp and then, when u is dead, the compacted neighbour chunk.
+// ------------------------------------------------------------------------------------------------
+template <int CN, int CL, int CNS>
+__global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restrict__ sp, const int* __restrict__ centres,
+                                                          const int* __restrict__ n_centres_dev, int n_centres_ub,
+                                                          const int* __restrict__ nbr_off, const int* __restrict__ nbr_end,
+                                                          const int* __restrict__ nbr_j, const int* __restrict__ nbr_s,
+                                                          const double* __restrict__ pos, const int* __restrict__ Z, Lattice9 lat,
+                                                          const double* __restrict__ x, const double* __restrict__ xlm,
+                                                          const double* __restrict__ pnorm, const double* __restrict__ gvec, int ldg, int g_splits,
+                                                          size_t g_split_stride, const double* __restrict__ epart, int n_tiles_n,
+                                                          double* __restrict__ local_e, double e_scale, double* __restrict__ force,
+                                                          double* __restrict__ vir_part, double* __restrict__ local_virial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Geo g = make_geo(CN, CL, CNS);
+  constexpr int n = CN, L1 = CL + 1, nlm = (CL + 1) * (CL + 1), K1 = CN * CNS, ns = CNS;
+  constexpr int K18 = (K1 + 7) & ~7, NTN = K18 / 8, n_nt = (CN + 7) / 8, n_ks = (CN + 3) / 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int d = sp->d, d_pad = sp->d_pad;
+  WSmem w;
+  carve_w(g, d_pad, true, warp, &w, smem_raw);
+  load_tables_w(sp, g, w);
+  __syncthreads();  // the only block barrier: the tables
+  const int c = blockIdx.x * NW + warp;
+  if (c >= n_centres_ub) return;
+  if (c >= *n_centres_dev) {
+    if (vir_part && lane < 9) vir_part[9 * (size_t)c + lane] = 0.0;  // unused slot of the upper-bound grid
+    return;
+  }
+  const int i = centres[c];
+  const double alpha = sp->alpha;
+  const int XS = g.XS;
+  // E_i = sum over the column tiles of GEMM-1 (shuffle tree, fixed order) ; local_e(centre) += E_i  (IPModel_GAP.f95:454-459)
+  if (epart) {
+    double t = 0.0;
+    for (int k = lane; k < n_tiles_n; k += 32) t += epart[(size_t)c * n_tiles_n + k];
+    t = warp_sum(t);
+    if (lane == 0) local_e[i] += e_scale * t;
+  }
+  // X_lm -> shared (asynchronous), zero padding; u = dE/dp from the K-split partials of gradPredict, pulled back through x = p/|p|
+  for (int k = lane; k < nlm * K1; k += 32) {
+    const int lm = k / K1, ic = k - lm * K1;
+    cp_async8(w.X + lm * XS + ic, xlm + (size_t)c * nlm * K1 + k);
+  }
+  cp_async_commit();
+  for (int k = lane; k < g.XR * XS; k += 32) {
+    const int lm = k / XS, ic = k - lm * XS;
+    if (lm >= nlm || ic >= K1) w.X[k] = 0.0;
+  }
+  const double* xr = x + (size_t)c * d_pad;
+  const double* gr = gvec + (size_t)c * ldg;
+  const double nrm = pnorm[c];
+  double loc = 0.0;
+  for (int q0 = 0; q0 < d - 1; q0 += 4 * 32) {
+    double xv[4], gv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int q = q0 + u * 32 + lane;
+      xv[u] = q < d - 1 ? xr[q] : 0.0;
+      gv[u] = q < d - 1 ? gr[q] : 0.0;
+    }
+    for (int k = 1; k < g_splits; k++)
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = q0 + u * 32 + lane;
+        if (q < d - 1) gv[u] += gr[(size_t)k * g_split_stride + q];
+      }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int q = q0 + u * 32 + lane;
+      if (q < d - 1) w.p[q] = gv[u];
+      loc += xv[u] * gv[u];
+    }
+  }
+  const double sdot = warp_sum(loc);
+  __syncwarp();
+  if (sp->normalise)
+    for (int q = lane; q < d - 1; q += 32) w.p[q] = (w.p[q] - xr[q] * sdot) / nrm;
+  cp_async_wait_all();
+  __syncwarp();
+
+  // ---- Lambda = dE/dX_lm and Lambda~ = Lambda . T^T on the tensor cores, one l-aligned tile of 8 lm rows at a time, in place:
+  //      Lambda[lm][ia] = sum_jb X[lm][jb] U~_l(jb, ia) / sqrt(2l+1),  U~_l(ia,jb) = 2 u (ia == jb) or sqrt(2) u (ia != jb) ----
+  double* const scr = w.acc + 96;  // 8 x XS
+#pragma unroll 1
+  for (int l = 0; l <= CL; l++) {
+    const double sc = sp->tlpo[l];
+    const int lm_end = (l + 1) * (l + 1);
+#pragma unroll 1
+    for (int lm0 = l * l; lm0 < lm_end; lm0 += 8) {
+#pragma unroll
+      for (int nt = 0; nt < NTN; nt++) {
+        const int ia = nt * 8 + fr;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < K18; k0 += 4) {
+          const int jb = k0 + fk;
+          const double a = w.X[(lm0 + fr) * XS + jb];
+          double b = 0.0;
+          if (ia < K1 && jb < K1) {
+            const int hi = ia > jb ? ia : jb, lo = ia > jb ? jb : ia;
+            const double u = w.p[l + L1 * (hi * (hi + 1) / 2 + lo)];
+            b = ia == jb ? 2.0 * u : 1.41421356237309504880 * u;
+          }
+          dmma(c0, c1, a, b);
+        }
+        scr[fr * XS + nt * 8 + 2 * fk] = c0 * sc;
+        scr[fr * XS + nt * 8 + 2 * fk + 1] = c1 * sc;
+      }
+      __syncwarp();
+      const bool row_ok = lm0 + fr < lm_end;  // rows beyond this l belong to the next tile's l: left alone
+#pragma unroll
+      for (int sk = 0; sk < ns; sk++) {
+        double ta[n_nt][2];
+#pragma unroll
+        for (int nt = 0; nt < n_nt; nt++) ta[nt][0] = ta[nt][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < n_ks; ks++) {
+          const int ap = ks * 4 + fk;  // k index = a'
+          const double a = ap < n ? scr[fr * XS + sk * n + ap] : 0.0;
+#pragma unroll
+          for (int nt = 0; nt < n_nt; nt++) dmma(ta[nt][0], ta[nt][1], a, w.Tp[(nt * 8 + fr) * g.TS + ap]);  // B[k=a'][col=a] = T(a,a')
+        }
+#pragma unroll
+        for (int nt = 0; nt < n_nt; nt++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const int a = nt * 8 + 2 * fk + j;
+            if (a < n && row_ok) w.X[(lm0 + fr) * XS + sk * n + a] = ta[nt][j];
+          }
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- neighbour phase: the u region now takes the compacted neighbours, 32 CSR entries at a time ----
+  double* accs = w.acc + fr * 12;  // centre force (3) and virial (9) partials of fragment row fr, lane fk == 0
+  if (fk == 0)
+#pragma unroll
+    for (int k = 0; k < 12; k++) accs[k] = 0.0;
+  __syncwarp();
+  const Smem s = view_of(w);
+  const int pbeg = nbr_off[i], pend = nbr_end[i];
+  for (int p0 = pbeg; p0 < pend; p0 += 32) {
+    const int fill = gather_chunk_w<true>(sp, w, 0, i, p0, pend, nbr_j, nbr_s, pos, Z, lat, lane);
+    __syncwarp();
+    int seg[CNS + 1];
+    if (CNS == 1) { seg[0] = 0; seg[CNS] = fill; }
+    else sort_species_w<CNS>(w, fill, lane, seg);
+#pragma unroll
+    for (int sk = 0; sk < CNS; sk++) {
+      const int cnt = seg[sk + 1] - seg[sk];
+      for (int t0 = 0; t0 < cnt; t0 += 8)
+        adjoint_tile<CN, CL>(s, g, alpha, sk, seg[sk] + t0, min(8, cnt - t0), fr, fk, e_scale, force, local_virial, accs, CNS == 1 ? nullptr : w.ord);
+    }
+    __syncwarp();
+  }
+  // centre force / virial: the 8 slots are added in a fixed order
+  __syncwarp();
+  if (lane < 12) {
+    double t = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < 8; sl++) t += w.acc[sl * 12 + lane];
+    if (lane < 3) {
+      if (force) atomicAdd(&force[3 * (size_t)i + lane], t);
+    } else if (vir_part) vir_part[9 * (size_t)c + (lane - 3)] = t;
+  }
+}
+
 __global__ void k_select_centres(const int* __restrict__ Z, int first, int last, const SoapDev* __restrict__ sp, int* __restrict__ flags) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > last - first) return;
@@ -1260,6 +1440,7 @@ size_t soap_adjoint_smem(const SoapDev& h) { return carve(make_geo(h.n_max, h.l_
 
 // (n_max, l_max, n_species) combinations with a fully specialised instantiation; everything else runs the generic one
 #define SOAP_SPECIALISATIONS(X) X(8, 8, 1) X(12, 8, 1) X(10, 6, 2)
+#define SOAP_ADJOINT_W(X) X(8, 8, 1)
 
 void launch_select_centres(const int* Z, int first, int last, const SoapDev* sp, int* flags, cudaStream_t st, int* launches) {
   int n = last - first + 1;
@@ -1302,6 +1483,18 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
   if (n_centres <= 0) return;
   size_t sm = soap_adjoint_smem(h);
   *launches += 1;
+  // shapes whose per-warp state leaves room for 16 warps per SM run the warp-per-centre kernel
+#define GOW(N, L, S)                                                                                                                         \
+  if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                                     \
+    const size_t smw = carve_w(make_geo(N, L, S), h.d_pad, true, 0, nullptr, nullptr);                                                       \
+    cudaFuncSetAttribute(k_soap_adjoint_w<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);                                   \
+    k_soap_adjoint_w<N, L, S><<<(n_centres + NW - 1) / NW, NT, smw, st>>>(sp, centres, n_centres_dev, n_centres, nbr_off, nbr_end, nbr_j, nbr_s, pos, \
+                                                                         Z, lat, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride, epart,    \
+                                                                         n_tiles_n, local_e, e_scale, force, vir_part, local_virial);          \
+    return;                                                                                                                                   \
+  }
+  SOAP_ADJOINT_W(GOW)
+#undef GOW
 #define GO(N, L, S)                                                                                                                          \
   if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                                     \
     cudaFuncSetAttribute(k_soap_adjoint<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                      \
