@@ -241,11 +241,14 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    emulate = args.emulate_world if world == 1 else 0  # profiling aid: rank 0's share of a W-rank step on one GPU, no collective
+    if emulate:
+        world = emulate
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not emulate:
         # the bench prints ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) out of it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
@@ -267,6 +270,8 @@ def run_b200(args):
     bp.finalise()
     N = len(atoms)
     sp = ShardedPotential("", param_filename=xml, device=local, rank=rank, world_size=world)
+    if emulate:
+        sp.world_size = world = 1  # partition stays [0, N/W); the reduction is skipped
     pot = sp.pot
     lat = atoms.lattice_fortran
     pbc = atoms.pbc
@@ -419,6 +424,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-world", type=int, default=0, help="profiling aid (1 GPU): run rank 0's share of a W-rank weak-scaling step, no collective")
     ap.add_argument("--config", default="A", choices=["A", "B", "C", "D"], help="A = the bench line; B/C/D = the other BASELINE shapes (exploration)")
     args = ap.parse_args()
     global CONFIG

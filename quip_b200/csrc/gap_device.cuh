@@ -77,6 +77,7 @@ struct NeighbourWork {  // device scratch owned by the potential handle; sized f
   int* sort_idx = nullptr;     // [N] atom ids sorted by cell (stable)
   int* iota = nullptr;         // [N]
   int* keys_tmp = nullptr;     // [N]
+  int* cell_count = nullptr;   // [ncell+1] counting-sort path only
   int* cell_start = nullptr;   // [ncell+1]
   double* spos = nullptr;      // [N][3] positions in sorted order
   int* smshift = nullptr;      // [N]

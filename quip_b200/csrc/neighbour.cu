@@ -63,8 +63,9 @@ __global__ void k_minmax_final(const double* __restrict__ part, int nb, double* 
 
 // err_flag: set when an atom lies more than MAX_MAP_SHIFT periodic images away from the cell (shifts are carried as int8)
 constexpr int MAX_MAP_SHIFT = 60;
+// cell_count != NULL: also count the atoms of every cell (counting-sort path)
 __global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int* __restrict__ cell_of, int* __restrict__ mshift,
-                      int* __restrict__ iota, int* __restrict__ err_flag) {
+                      int* __restrict__ iota, int* __restrict__ err_flag, int* __restrict__ cell_count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double t[3];
@@ -89,6 +90,35 @@ __global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int*
   cell_of[i] = cell;
   mshift[i] = pack_shift(ms[0], ms[1], ms[2]);
   iota[i] = i;
+  if (cell_count) atomicAdd(&cell_count[cell], 1);
+}
+
+// counting sort, step 2: every atom takes a slot of its cell's range (in arbitrary order; the counts are consumed)
+__global__ void k_place(const int* __restrict__ cell_of, int N, const int* __restrict__ cell_start, int* __restrict__ cell_count,
+                        int* __restrict__ slots) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int c = cell_of[i];
+  slots[cell_start[c] + atomicSub(&cell_count[c], 1) - 1] = i;
+}
+// step 3: one thread per slot: the atom's place inside its cell is its rank by atom index (what the stable radix sort delivers, so
+// both paths give the same arrays); positions are gathered on the way
+__global__ void k_cell_sort_gather(const double* __restrict__ pos, const int* __restrict__ mshift, const int* __restrict__ cell_of,
+                                   const int* __restrict__ slots, int N, const int* __restrict__ cell_start, int* __restrict__ sort_idx,
+                                   int* __restrict__ sort_keys, double* __restrict__ spos, int* __restrict__ smshift) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N) return;
+  const int i = slots[t], c = cell_of[i];
+  const int b = cell_start[c], e = cell_start[c + 1];
+  int rank = 0;
+  for (int q = b; q < e; q++) rank += slots[q] < i;  // a cell holds a handful of atoms
+  const int p = b + rank;
+  sort_idx[p] = i;
+  sort_keys[p] = c;
+  spos[3 * (size_t)p + 0] = pos[3 * (size_t)i + 0];
+  spos[3 * (size_t)p + 1] = pos[3 * (size_t)i + 1];
+  spos[3 * (size_t)p + 2] = pos[3 * (size_t)i + 2];
+  smshift[p] = mshift[i];
 }
 
 // positions in cell-sorted order, and the cell ranges from the sorted keys: cell_start[c] = first sorted slot whose
@@ -228,11 +258,12 @@ __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, in
 }  // namespace
 
 size_t neighbour_cub_bytes(int N, int ncell) {
-  (void)ncell;
-  size_t a = 0, c = 0;
+  size_t a = 0, b = 0, c = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, a, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, N);
+  cub::DeviceScan::ExclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, ncell + 1);
   cub::DeviceScan::ExclusiveSum(nullptr, c, (int*)nullptr, (int*)nullptr, N + 1);
-  return (a > c ? a : c) + 256;
+  size_t m = a > b ? a : b;
+  return (m > c ? m : c) + 256;
 }
 
 void launch_frac_minmax(const double* pos, int N, const double*, const CellGrid& grid, double* minmax6, cudaStream_t st, int* launches) {
@@ -245,9 +276,23 @@ void launch_frac_minmax(const double* pos, int N, const double*, const CellGrid&
   *launches += 2;
 }
 
+// up to this many atoms cub sorts in ONE single-tile kernel; beyond it its multi-kernel radix sort costs more than a counting sort
+constexpr int SINGLE_TILE_SORT_MAX = 4864;
+
 void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell, NeighbourWork& w, cudaStream_t st, int* launches) {
   int nb = (N + 255) / 256;
-  k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.iota, w.err_flag);
+  if (N > SINGLE_TILE_SORT_MAX) {
+    // counting sort by cell: count (atomics), exclusive scan, place, then every atom finds its rank by index inside its cell
+    cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (ncell + 1), st);
+    k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.iota, w.err_flag, w.cell_count);
+    size_t bytes = w.cub_bytes;
+    cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.cell_count, w.cell_start, ncell + 1, st);
+    k_place<<<nb, 256, 0, st>>>(w.cell_of, N, w.cell_start, w.cell_count, w.iota);
+    k_cell_sort_gather<<<nb, 256, 0, st>>>(pos, w.mshift, w.cell_of, w.iota, N, w.cell_start, w.sort_idx, w.sort_keys, w.spos, w.smshift);
+    *launches += 4;
+    return;
+  }
+  k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.iota, w.err_flag, nullptr);
   int bits = 1;
   while ((1 << bits) < ncell && bits < 31) bits++;
   size_t bytes = w.cub_bytes;

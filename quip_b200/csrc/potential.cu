@@ -116,7 +116,7 @@ struct gap_potential {
 
   // neighbour list state
   NeighbourWork nw;
-  DevBuf b_cell_of, b_mshift, b_keys, b_idx, b_iota, b_cstart, b_spos, b_smshift, b_nn, b_cub, b_minmax;
+  DevBuf b_cell_of, b_mshift, b_keys, b_idx, b_iota, b_cstart, b_ccount, b_spos, b_smshift, b_nn, b_cub, b_minmax;
   DevBuf b_off, b_end, b_j, b_s, b_d;
   int conn_N = 0, conn_nnz = 0;
   // inputs / outputs owned for the host-pointer API
@@ -450,6 +450,7 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   P->b_idx.ensure(sizeof(int) * N); w.sort_idx = P->b_idx.as<int>();
   P->b_iota.ensure(sizeof(int) * N); w.iota = P->b_iota.as<int>();
   P->b_cstart.ensure(sizeof(int) * (ncell + 2)); w.cell_start = P->b_cstart.as<int>();
+  P->b_ccount.ensure(sizeof(int) * (ncell + 2)); w.cell_count = P->b_ccount.as<int>();
   P->b_spos.ensure(sizeof(double) * 3 * N); w.spos = P->b_spos.as<double>();
   P->b_smshift.ensure(sizeof(int) * N); w.smshift = P->b_smshift.as<int>();
   P->b_nn.ensure(sizeof(int) * (N + 2)); w.nn = P->b_nn.as<int>();
@@ -1037,7 +1038,7 @@ void gap_potential_finalise(gap_potential* P) {
   cudaFree(P->d_e0);
   cudaFree(P->d_fin_counter);
   if (P->h_pin) cudaFreeHost(P->h_pin);
-  DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_cstart, &P->b_end, &P->b_mask, &P->b_epc, &P->b_lgv, &P->b_gvg, &P->b_varflag, &P->b_vc, &P->b_vq, &P->b_vk, &P->b_spos, &P->b_smshift,
+  DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_cstart, &P->b_ccount, &P->b_end, &P->b_mask, &P->b_epc, &P->b_lgv, &P->b_gvg, &P->b_varflag, &P->b_vc, &P->b_vq, &P->b_vk, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
                     &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke};
