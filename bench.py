@@ -157,9 +157,17 @@ def workload_name(n_gpus):
 # ------------------------------------------------------------------------------------------------------------------
 # CPU baseline (oracle = restatement of the reference's algorithm; the reference itself is Fortran and cannot be built here)
 # ------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """All host cores this process may use.  (torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not inherit that.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(om, atoms, n_centres):
     t = time.perf_counter()
-    om.calc(atoms, force=True, virial=True, first=0, last=n_centres)
+    om.calc(atoms, force=True, virial=True, first=0, last=n_centres, nthreads=host_threads())
     return time.perf_counter() - t
 
 
@@ -168,7 +176,7 @@ def cpu_baseline_leg(xml, atoms, budget_s=12.0):
     from oracle import oracle as orc
 
     om = orc.Model(xml)
-    cores = int(orc.lib().orc_num_threads())
+    cores = host_threads()
     n = min(len(atoms), 256)
     rate = n / cpu_sample(om, atoms, n)
     per_pass = int(min(len(atoms), max(n, rate * budget_s)))
@@ -191,7 +199,7 @@ def run_reference(args):
     with tempfile.TemporaryDirectory() as tmp:
         atoms, xml = build_workload(tmp, n_gpus, lambda desc, at: orc.soap_descriptor(desc, at)["data"])
         om = orc.Model(xml)
-        cores = int(orc.lib().orc_num_threads())
+        cores = host_threads()
         n = min(len(atoms), 128)
         rate = n / cpu_sample(om, atoms, n)
         # each step = a bounded sample of centres sized so that warmup + steps take about two minutes at most
