@@ -222,11 +222,21 @@ __global__ void k_zero_outputs(double* __restrict__ a, size_t na, double* __rest
 
 // Centre selection of a SOAP coordinate for small partitions, ONE block: flag (descriptors.f95:7962), block scan and ordered
 // compaction, 4 atoms per thread and 4,096 per round; the count goes where the multi-kernel path leaves it (scan[n]).
-constexpr int SEL_THREADS = 1024, SEL_ITEMS = 4, SEL_MAX_N = 16384;
+// Blocks 1.. of the grid (if any) zero the outputs of the calc instead (one launch for both jobs at the start of a step).
+constexpr int SEL_THREADS = 1024, SEL_ITEMS = 4, SEL_MAX_N = 16384, SEL_ZERO_BLOCKS = 8;
 __global__ void __launch_bounds__(SEL_THREADS) k_select_compact_block(const int* __restrict__ Z, int first, int last, const SoapDev* __restrict__ sp,
-                                                                       int* __restrict__ centres, int* __restrict__ count_out) {
+                                                                       int* __restrict__ centres, int* __restrict__ count_out,
+                                                                       double* __restrict__ za, size_t nza, double* __restrict__ zb, size_t nzb,
+                                                                       double* __restrict__ zc, size_t nzc) {
   typedef cub::BlockScan<int, SEL_THREADS> BS;
   __shared__ typename BS::TempStorage tmp;
+  if (blockIdx.x > 0) {
+    const size_t stride = (size_t)(gridDim.x - 1) * SEL_THREADS, t0 = (size_t)(blockIdx.x - 1) * SEL_THREADS + threadIdx.x;
+    for (size_t t = t0; t < nza; t += stride) za[t] = 0.0;
+    for (size_t t = t0; t < nzb; t += stride) zb[t] = 0.0;
+    for (size_t t = t0; t < nzc; t += stride) zc[t] = 0.0;
+    return;
+  }
   const int n = last - first, nZ = sp->n_Z;
   int base = 0;
   for (int t0 = 0; t0 < n; t0 += SEL_THREADS * SEL_ITEMS) {
@@ -664,15 +674,21 @@ struct SoapRun {
 
 // select + compact the centres of SOAP coordinate cd among atoms [first,last).  The number of centres stays on the
 // device (P->b_scan[n], see nc_dev()); the host sizes grids and buffers with the upper bound n = last - first.
-int select_centres(gap_potential* P, const CoordDev& cd, const int* d_Z, int first, int last, cudaStream_t st) {
+// zero_* (optional): output buffers cleared by the same launch when the one-block path is taken; *zeroed tells whether it was.
+int select_centres(gap_potential* P, const CoordDev& cd, const int* d_Z, int first, int last, cudaStream_t st, double* za = nullptr,
+                   size_t nza = 0, double* zb = nullptr, size_t nzb = 0, double* zc = nullptr, size_t nzc = 0, bool* zeroed = nullptr) {
   int n = last - first;
+  if (zeroed) *zeroed = false;
   if (n <= 0) return 0;
   int launches = 0;
   P->b_flags.ensure(sizeof(int) * (n + 1));
   P->b_scan.ensure(sizeof(int) * (n + 1));
   P->b_centres.ensure(sizeof(int) * (n + 1));
   if (n <= SEL_MAX_N) {
-    k_select_compact_block<<<1, SEL_THREADS, 0, st>>>(d_Z, first, last, cd.d_sp, P->b_centres.as<int>(), P->b_scan.as<int>() + n);
+    const bool fuse = za != nullptr;
+    k_select_compact_block<<<fuse ? 1 + SEL_ZERO_BLOCKS : 1, SEL_THREADS, 0, st>>>(d_Z, first, last, cd.d_sp, P->b_centres.as<int>(),
+                                                                                  P->b_scan.as<int>() + n, za, nza, zb, nzb, zc, nzc);
+    if (zeroed) *zeroed = fuse;
     P->launches += 1;
     return n;
   }
@@ -886,30 +902,38 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
     }
     for (size_t ic = 0; ic < n_coord; ic++) ensure_variance_model(P, ic, ca.var_reg, st);  // IPModel_GAP.f95:412-414
   }
+  double* d_le = d_le_user;
+  if (!d_le) {
+    P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
+    d_le = P->b_le.as<double>();
+  }
+  const size_t nz_packed = 10 + 3 * (size_t)N, nz_le = (size_t)N + (d_le_user ? 0 : 1), nz_lv = d_lv ? 9 * (size_t)N : 0;
   if (ext) {
     first = 0;
     last = ext->nlocal;
     d_Zc = ext->Zc;
     P->cv_off = ext->off; P->cv_end = ext->off + 1; P->cv_j = ext->j; P->cv_s = ext->s;
     P->pending_check = false;
-  } else {
-    build_connect(P, N, first, last, d_pos, lattice, pbc, P->model.cutoff, false, true, st);
   }
+  // The centre selection of the first SOAP coordinate needs Z only: it is launched ahead of the neighbour-list build and, for small
+  // partitions, the same launch zeroes the outputs (one launch instead of two at the head of the step).
+  int hoisted_ic = -1, hoisted_nc = 0;
+  bool zeroed = false;
+  for (size_t ic = 0; ic < n_coord && hoisted_ic < 0; ic++)
+    if (P->cd[ic].kind == DESC_SOAP && !(ca.only_descriptor && (int)ic + 1 != ca.only_descriptor)) hoisted_ic = (int)ic;
+  if (hoisted_ic >= 0) hoisted_nc = select_centres(P, P->cd[hoisted_ic], d_Zc, first, last, st, d_packed, nz_packed, d_le, nz_le, d_lv, nz_lv, &zeroed);
+  if (!zeroed) {
+    const size_t nz = (d_lv ? 9 : 3) * (size_t)N + 10;
+    int zb = (int)std::min<size_t>((nz + 255) / 256, 2048);
+    k_zero_outputs<<<zb, 256, 0, st>>>(d_packed, nz_packed, d_le, nz_le, d_lv, nz_lv);
+    P->launches += 1;
+  }
+  mark(P, st, ST_OTHER);
+  if (!ext) build_connect(P, N, first, last, d_pos, lattice, pbc, P->model.cutoff, false, true, st);
   mark(P, st, ST_CONNECT);
   Lattice9 lat;
   for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
 
-  double* d_le = d_le_user;
-  if (!d_le) {
-    P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
-    d_le = P->b_le.as<double>();
-  }
-  {
-    const size_t nz = (d_lv ? 9 : 3) * (size_t)N + 10;
-    int zb = (int)std::min<size_t>((nz + 255) / 256, 2048);
-    k_zero_outputs<<<zb, 256, 0, st>>>(d_packed, 10 + 3 * (size_t)N, d_le, (size_t)N + (d_le_user ? 0 : 1), d_lv, d_lv ? 9 * (size_t)N : 0);
-    P->launches += 1;
-  }
   double* d_force = d_packed + 10;
   const double es = P->model.E_scale;
 
@@ -925,7 +949,8 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
     if (ca.only_descriptor && (int)ic + 1 != ca.only_descriptor) {
       // skipped coordinate (:399-401): its energy_per_coordinate entry is zero
     } else if (cd.kind == DESC_SOAP) {
-      int nc = select_centres(P, cd, d_Zc, first, last, st);  // upper bound; the count itself stays on the device
+      // upper bound; the count itself stays on the device
+      int nc = (int)ic == hoisted_ic ? hoisted_nc : select_centres(P, cd, d_Zc, first, last, st);
       mark(P, st, ST_OTHER);
       if (nc > 0) {
         const int* ncd = nc_dev(P, nc);

@@ -525,7 +525,10 @@ class ShardedPotential:
             self.h_Z.numpy()[...] = Z
             self.d_pos.copy_(self.h_pos, non_blocking=True)
             self.d_Z.copy_(self.h_Z, non_blocking=True)
-            self.calc_resident(N, self.d_pos, self.d_Z, lat, pbc, self.d_packed, want_grad=force or virial)
-            self.h_packed.copy_(self.d_packed, non_blocking=True)
-            self.stream.synchronize()
+            for _ in range(2):
+                # evaluation, collective and the read-back of the results are all enqueued before the ONE synchronisation of the call
+                self.calc_resident_enqueue(N, self.d_pos, self.d_Z, lat, pbc, self.d_packed, want_grad=force or virial)
+                self.h_packed.copy_(self.d_packed, non_blocking=True)
+                if self.calc_resident_finish():
+                    break
         return unpack_results(self.h_packed.numpy(), N)
