@@ -301,6 +301,7 @@ def run_b200(args):
     # ---- value: HBM-resident inputs, CUDA events per step, L2 flushed between steps ----
     # everything below is enqueued on sp.stream (a real stream; events are recorded on the stream the kernels run on)
     torch.cuda.set_stream(sp.stream)
+    pot.set_timing(True)  # per-stage events for the roofline of this leg
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
@@ -334,6 +335,7 @@ def run_b200(args):
     result = d_packed[:10].cpu().numpy()
 
     # ---- e2e: host-pointer API, pinned host buffers, H2D + D2H inside the timed region, wall clock ----
+    pot.set_timing(False)  # the stage events are instrumentation of the leg above
     for _ in range(3):
         r = sp.calc(atoms, force=True, virial=True)
     barrier()

@@ -62,6 +62,8 @@ def main(argv=None, out=sys.stdout):
     if not (cfg["E"] or cfg["F"] or cfg["V"] or cfg["local"]):
         raise RuntimeError("Nothing to be calculated")  # quip.f95:819
     pot = Potential(cfg["init_args"], param_filename=cfg["param_filename"], calc_args=cfg["calc_args"])
+    if cfg["timing"]:
+        pot.set_timing(True)
     frames = read_xyz(cfg["atoms_filename"])
     for at in frames:
         t0 = time.perf_counter()

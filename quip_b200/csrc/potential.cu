@@ -124,6 +124,7 @@ struct gap_potential {
   // per-coordinate workspaces
   DevBuf b_velo, b_velo2, b_acc, b_mass, b_ke;  // MD driver state
   DevBuf b_flags, b_scan, b_centres, b_x, b_xlm, b_pnorm, b_acoef, b_gvec, b_epart, b_vir, b_fin;
+  bool timing = false;         // record per-stage CUDA events (gap_potential_set_timing)
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_stage;
   size_t ev_used = 0;
@@ -300,6 +301,7 @@ __global__ void k_iota(int* p, int n) {
 enum { ST_CONNECT = 0, ST_SOAP_FWD = 1, ST_COV_GEMM1 = 2, ST_COV_GEMM2 = 3, ST_SOAP_ADJ = 4, ST_PAIR2B = 5, ST_OTHER = 6, ST_TOTAL = 7 };
 
 void mark(gap_potential* P, cudaStream_t st, int stage) {
+  if (!P->timing) return;  // stage timing is instrumentation: off unless gap_potential_set_timing asked for it
   if (P->ev_used == P->ev.size()) {
     cudaEvent_t e;
     CUDA_OK(cudaEventCreate(&e));
@@ -1430,6 +1432,14 @@ void quip_lammps_wrapper(int* nlocal, int* nghost, int* atomic_numbers, int* lmp
     fprintf(stderr, "SYSTEM ABORT: %s\n", gap_last_error());
     abort();
   }
+}
+
+int gap_potential_set_timing(gap_potential* P, int on) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_set_timing: pot is NULL");
+    P->timing = on != 0;
+    P->ev_used = 0;
+  });
 }
 
 int gap_potential_last_timings(gap_potential* P, double* ms8) {

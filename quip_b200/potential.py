@@ -55,6 +55,7 @@ ABI = {
     "gap_potential_n_coordinate": (C.c_int, [C.c_void_p]),
     "gap_potential_launch_count": (C.c_long, [C.c_void_p]),
     "gap_potential_last_timings": (C.c_int, [C.c_void_p, c_dp]),
+    "gap_potential_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "gap_model_describe": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     "gap_last_error": (C.c_char_p, []),
 }
@@ -353,6 +354,10 @@ class Potential:
     def launch_count(self):
         return load_library().gap_potential_launch_count(self._h)
 
+    def set_timing(self, on=True):
+        """Record per-stage CUDA events during calc (off by default; see last_timings)."""
+        _check(load_library().gap_potential_set_timing(self._h, 1 if on else 0))
+
     def last_timings(self):
         t = np.zeros(8)
         load_library().gap_potential_last_timings(self._h, _dp(t))
@@ -430,11 +435,16 @@ class ShardedPotential:
         if N == self._N:
             return
         self._N = N
-        self.h_pos = torch.empty((N, 3), dtype=torch.float64, pin_memory=True)
-        self.h_Z = torch.empty((N,), dtype=torch.int32, pin_memory=True)
+        # positions and atomic numbers travel in ONE pinned staging buffer / one H2D copy: [pos (3N f64) | Z (N i32)]
+        nb = 24 * N + 4 * N
+        self.h_in = torch.empty((nb,), dtype=torch.uint8, pin_memory=True)
+        self.d_in = torch.empty((nb,), dtype=torch.uint8, device=self.device)
+        self.h_pos = self.h_in[:24 * N].view(torch.float64).view(N, 3)
+        self.h_Z = self.h_in[24 * N:].view(torch.int32)
+        self.d_pos = self.d_in[:24 * N].view(torch.float64).view(N, 3)
+        self.d_Z = self.d_in[24 * N:].view(torch.int32)
+        self.h_pos_np, self.h_Z_np = self.h_pos.numpy(), self.h_Z.numpy()
         self.h_packed = torch.empty((10 + 3 * N,), dtype=torch.float64, pin_memory=True)
-        self.d_pos = torch.empty((N, 3), dtype=torch.float64, device=self.device)
-        self.d_Z = torch.empty((N,), dtype=torch.int32, device=self.device)
         self.d_packed = torch.empty((10 + 3 * N,), dtype=torch.float64, device=self.device)
 
     def reduce_packed(self, d_packed):
@@ -494,7 +504,7 @@ class ShardedPotential:
             if self.calc_resident_finish():
                 break
 
-    def calc_resident_enqueue(self, N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad=True):
+    def calc_resident_enqueue(self, N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad=True, read_energy=True):
         """First half of :meth:`calc_resident`: enqueue the evaluation, the collective and the read-back of the energy word
         on torch's current (non-default) stream and return without waiting."""
         cur = self.torch.cuda.current_stream(self.device)
@@ -505,14 +515,17 @@ class ShardedPotential:
         self.reduce_packed(d_packed)
         # a rank whose list overflowed has poisoned its energy with NaN (k_finalize): after the reduction every rank sees it, so
         # all ranks repeat together without an extra collective
-        self._h_e.copy_(d_packed[:1], non_blocking=True)
+        if read_energy:
+            self._h_e.copy_(d_packed[:1], non_blocking=True)
 
-    def calc_resident_finish(self):
+    def calc_resident_finish(self, h_energy=None):
         """Second half: synchronise once, then check the speculatively sized neighbour list.  False = enqueue again (the
-        repeat sizes the list exactly)."""
+        repeat sizes the list exactly).  h_energy: pinned host tensor whose first word received the reduced energy (default:
+        the word calc_resident_enqueue read back)."""
         self.torch.cuda.current_stream(self.device).synchronize()
         ok = self.pot.calc_device_verify()
-        return bool(ok and not bool(self.torch.isnan(self._h_e[0])))
+        e = float((self._h_e if h_energy is None else h_energy)[0])
+        return bool(ok and e == e)
 
     def calc(self, atoms, force=True, virial=True):
         """Host in, host out: H2D of (pos, Z) from pinned memory, evaluation of this rank's block, all-reduce, D2H."""
@@ -521,14 +534,14 @@ class ShardedPotential:
         N = len(Z)
         self._ensure(N)
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            self.h_pos.numpy()[...] = pos
-            self.h_Z.numpy()[...] = Z
-            self.d_pos.copy_(self.h_pos, non_blocking=True)
-            self.d_Z.copy_(self.h_Z, non_blocking=True)
+            self.h_pos_np[...] = pos
+            self.h_Z_np[...] = Z
+            self.d_in.copy_(self.h_in, non_blocking=True)
             for _ in range(2):
                 # evaluation, collective and the read-back of the results are all enqueued before the ONE synchronisation of the call
-                self.calc_resident_enqueue(N, self.d_pos, self.d_Z, lat, pbc, self.d_packed, want_grad=force or virial)
+                # (the energy word of h_packed doubles as the overflow signal)
+                self.calc_resident_enqueue(N, self.d_pos, self.d_Z, lat, pbc, self.d_packed, want_grad=force or virial, read_energy=False)
                 self.h_packed.copy_(self.d_packed, non_blocking=True)
-                if self.calc_resident_finish():
+                if self.calc_resident_finish(self.h_packed):
                     break
         return unpack_results(self.h_packed.numpy(), N)
