@@ -92,6 +92,8 @@ struct gap_potential {
   size_t g_split_stride = 0;
   // speculative neighbour-list sizing: the entry count of the previous call sizes the buffers of the next one, the
   // real count comes back asynchronously (pinned) and is verified after the final synchronisation of the call
+  unsigned char* h_stage = nullptr;  // pinned staging buffer of the host-pointer entry point (inputs in, results out)
+  size_t h_stage_cap = 0;
   int* h_pin = nullptr;        // pinned [3]: entry count (exact layout only), error flag, largest row
   int row_hint = -1;           // largest neighbour row of the previous call with the same (N, first, last)
   int hint_N = -1, hint_first = -1, hint_last = -1;
@@ -1065,6 +1067,7 @@ void gap_potential_finalise(gap_potential* P) {
   cudaFree(P->d_e0);
   cudaFree(P->d_fin_counter);
   if (P->h_pin) cudaFreeHost(P->h_pin);
+  if (P->h_stage) cudaFreeHost(P->h_stage);
   DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_cstart, &P->b_ccount, &P->b_end, &P->b_mask, &P->b_epc, &P->b_lgv, &P->b_gvg, &P->b_varflag, &P->b_vc, &P->b_vq, &P->b_vk, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
@@ -1193,26 +1196,50 @@ int gap_potential_calc(gap_potential* P, int N, const double* pos, const int* Z,
     if (N > 0 && (!pos || !Z)) throw GapError("gap_potential_calc: pos/Z are NULL");
     CUDA_OK(cudaSetDevice(P->device));
     cudaStream_t st = P->stream;
-    P->b_pos.ensure(sizeof(double) * 3 * (size_t)(N + 1));
-    P->b_Z.ensure(sizeof(int) * (size_t)(N + 1));
-    P->b_packed.ensure(sizeof(double) * (10 + 3 * (size_t)N));
+    const size_t n3 = 3 * (size_t)N;
+    // inputs: pos and Z staged through ONE pinned buffer into one device buffer [pos (3N f64) | Z (N i32)], one H2D copy;
+    // results: [E | virial | F] (+ local_e, local_virial) come back through one pinned buffer, one synchronisation per call
+    const size_t in_bytes = sizeof(double) * n3 + sizeof(int) * (size_t)N;
+    const size_t out_doubles = 10 + n3 + (local_e ? (size_t)N : 0) + (local_virial ? 9 * (size_t)N : 0);
+    P->b_pos.ensure(in_bytes + 64);
+    P->b_packed.ensure(sizeof(double) * (10 + n3));
     P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
     if (local_virial) P->b_lv.ensure(sizeof(double) * 9 * (size_t)(N + 1));
+    if (P->h_stage_cap < std::max(in_bytes, sizeof(double) * out_doubles) + 64) {
+      if (P->h_stage) cudaFreeHost(P->h_stage);
+      P->h_stage = nullptr;
+      P->h_stage_cap = 2 * std::max(in_bytes, sizeof(double) * out_doubles) + 4096;
+      CUDA_OK(cudaHostAlloc((void**)&P->h_stage, P->h_stage_cap, cudaHostAllocDefault));
+    }
+    double* d_pos = P->b_pos.as<double>();
+    int* d_Z = (int*)(P->b_pos.as<char>() + sizeof(double) * n3);
     if (N > 0) {
-      CUDA_OK(cudaMemcpyAsync(P->b_pos.p, pos, sizeof(double) * 3 * (size_t)N, cudaMemcpyHostToDevice, st));
-      CUDA_OK(cudaMemcpyAsync(P->b_Z.p, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+      memcpy(P->h_stage, pos, sizeof(double) * n3);
+      memcpy(P->h_stage + sizeof(double) * n3, Z, sizeof(int) * (size_t)N);
+      CUDA_OK(cudaMemcpyAsync(P->b_pos.p, P->h_stage, in_bytes, cudaMemcpyHostToDevice, st));
     }
     bool want_grad = force || virial || local_virial;  // IPModel_GAP.f95:416-424
-    double head[10];
+    double* h_out = (double*)P->h_stage;
     for (int attempt = 0; attempt < 2; attempt++) {
-      calc_device_impl(P, N, P->b_pos.as<double>(), P->b_Z.as<int>(), lattice, pbc, args_str, want_grad, P->b_packed.as<double>(),
-                       P->b_le.as<double>(), local_virial ? P->b_lv.as<double>() : nullptr, st);
-      CUDA_OK(cudaMemcpyAsync(head, P->b_packed.p, sizeof(head), cudaMemcpyDeviceToHost, st));
-      if (force && N > 0) CUDA_OK(cudaMemcpyAsync(force, P->b_packed.as<double>() + 10, sizeof(double) * 3 * (size_t)N, cudaMemcpyDeviceToHost, st));
-      if (local_e && N > 0) CUDA_OK(cudaMemcpyAsync(local_e, P->b_le.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
-      if (local_virial && N > 0) CUDA_OK(cudaMemcpyAsync(local_virial, P->b_lv.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, st));
+      if (attempt == 1 && N > 0) CUDA_OK(cudaStreamSynchronize(st));  // (the staging buffer is shared by both directions)
+      calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad, P->b_packed.as<double>(), P->b_le.as<double>(),
+                       local_virial ? P->b_lv.as<double>() : nullptr, st);
+      size_t o = 0;
+      CUDA_OK(cudaMemcpyAsync(h_out, P->b_packed.p, sizeof(double) * (force ? 10 + n3 : 10), cudaMemcpyDeviceToHost, st));
+      o += 10 + n3;
+      if (local_e && N > 0) { CUDA_OK(cudaMemcpyAsync(h_out + o, P->b_le.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st)); o += N; }
+      if (local_virial && N > 0) CUDA_OK(cudaMemcpyAsync(h_out + o, P->b_lv.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
       if (verify_connect(P)) break;  // false: the speculatively sized neighbour list overflowed; repeat with the exact size
+    }
+    double head[10];
+    memcpy(head, h_out, sizeof(head));
+    {
+      size_t o = 10;
+      if (force && N > 0) memcpy(force, h_out + o, sizeof(double) * n3);
+      o += n3;
+      if (local_e && N > 0) { memcpy(local_e, h_out + o, sizeof(double) * (size_t)N); o += N; }
+      if (local_virial && N > 0) memcpy(local_virial, h_out + o, sizeof(double) * 9 * (size_t)N);
     }
     if (energy) *energy = head[0];
     if (virial)

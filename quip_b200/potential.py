@@ -530,6 +530,9 @@ class ShardedPotential:
     def calc(self, atoms, force=True, virial=True):
         """Host in, host out: H2D of (pos, Z) from pinned memory, evaluation of this rank's block, all-reduce, D2H."""
         torch = self.torch
+        if self.world_size == 1:
+            # one rank: the plain host-pointer entry point of the C ABI (gap_potential_calc), exactly what a Fortran host calls
+            return self.pot.calc(atoms, force=force, virial=virial)
         pos, Z, lat, pbc = _geometry(atoms)
         N = len(Z)
         self._ensure(N)
