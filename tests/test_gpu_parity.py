@@ -103,6 +103,29 @@ def test_neighbour_list_config_A_size(gap_xml_pot):
     assert_same_list(gap_xml_pot, Atoms(slab.numbers, slab.positions, slab.cell, [1, 1, 0]), 5.0)
 
 
+def test_neighbour_list_counting_sort_path(gap_xml_pot):
+    # above cub's single-tile sort limit (4,864 atoms) the cells are filled by a counting sort; the list must not notice
+    a = syn.si_diamond(9, 9, 9)  # 5,832 atoms
+    n = assert_same_list(gap_xml_pot, a, 5.0)
+    assert 27.5 < n / len(a) < 28.5
+    rng = np.random.default_rng(11)
+    L = 40.0
+    gas = Atoms(np.full(6000, 6), rng.uniform(0, L, size=(6000, 3)), np.eye(3) * L, [1, 0, 1])  # uneven cells, mixed pbc
+    assert_same_list(gap_xml_pot, gas, 4.0)
+
+
+def test_stage_timing_is_opt_in(si_model, si_frames):
+    pot, _, xml = si_model
+    p = Potential("IP GAP", param_filename=xml)
+    p.calc(si_frames[8], force=True)
+    assert all(v == 0.0 for v in p.last_timings().values())
+    p.set_timing(True)
+    p.calc(si_frames[8], force=True)
+    t = p.last_timings()
+    assert t["total"] > 0.0 and t["connect"] > 0.0
+    p.set_timing(False)
+
+
 # ----------------------------------------------------------------------------------------------------
 # SOAP descriptor
 # ----------------------------------------------------------------------------------------------------
