@@ -398,7 +398,7 @@ def run_b200(args):
     cpu = cpu_baseline_leg(xml, atoms) if (world == 1 and not args.no_cpu_baseline) else None
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if CONFIG == "A" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n_gpus), "atoms": N, "atoms_per_gpu": N // world, "sparse_points": SHAPES[CONFIG][3], "descriptor_dim": d,
                        "parallelism": "centre-block x%d, positions replicated, one all-reduce of [E|virial|F]" % world,
                        "l2": "flushed between timed steps (512 MiB memset)", "timing": "CUDA events per step on the launching stream around the enqueued step (kernels + collective + energy read-back); one host synchronise + neighbour-list verification per step follows the closing event; max over ranks"},
