@@ -12,6 +12,7 @@ module gap_b200_iface
   public :: gap_potential_initialise, gap_potential_filename_initialise, gap_potential_finalise, gap_potential_cutoff
   public :: gap_potential_calc, gap_potential_set_partition, gap_last_error, gap_b200_error_string
   public :: gap_potential_set_atom_mask, gap_potential_get_energy_per_coordinate, gap_potential_get_local_gap_variance
+  public :: gap_potential_set_timing, gap_potential_last_timings, gap_md_run
 
   interface
      ! int gap_potential_initialise(gap_potential** pot, const char* args_str, const char* param_str, const char* base_dir, int device)
@@ -65,6 +66,31 @@ module gap_b200_iface
        type(c_ptr), value :: pot, gap_variance_gradient   ! c_loc of real(dp) (3,n), or c_null_ptr
        integer(c_int), value :: n
        real(c_double), intent(out) :: local_gap_variance(*)
+       integer(c_int) :: ierr
+     end function
+     ! system_timer analogue: per-stage device milliseconds of the last calc (recorded only after set_timing(pot, 1))
+     function gap_potential_set_timing(pot, on) bind(C, name="gap_potential_set_timing") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: pot
+       integer(c_int), value :: on
+       integer(c_int) :: ierr
+     end function
+     function gap_potential_last_timings(pot, ms8) bind(C, name="gap_potential_last_timings") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: pot
+       real(c_double), intent(out) :: ms8(8)
+       integer(c_int) :: ierr
+     end function
+     ! DynamicalSystem_run (Potential.f95:2304) for plain NVE dynamics, state resident on the GPU for the whole run
+     function gap_md_run(pot, n, pos, velo, z, mass, lattice, pbc, dt, n_steps, args_str, epot, ekin) bind(C, name="gap_md_run") result(ierr)
+       import :: c_ptr, c_char, c_int, c_double
+       type(c_ptr), value :: pot, epot, ekin              ! epot/ekin: c_loc of real(dp)(0:n_steps) or c_null_ptr
+       integer(c_int), value :: n, n_steps
+       real(c_double), intent(inout) :: pos(3, *), velo(3, *)
+       integer(c_int), intent(in) :: z(*), pbc(3)
+       real(c_double), intent(in) :: mass(*), lattice(3, 3)
+       real(c_double), value :: dt
+       character(kind=c_char), dimension(*), intent(in) :: args_str
        integer(c_int) :: ierr
      end function
      ! absent optional outputs are passed as C_NULL_PTR, hence type(c_ptr), value for every output
