@@ -133,8 +133,9 @@ def _calc_options(args_str):
 
 
 def _geometry(atoms):
-    pos = np.ascontiguousarray(atoms.get_positions(), dtype=np.float64)
-    Z = np.ascontiguousarray(atoms.get_atomic_numbers(), dtype=np.int32)
+    # the arrays are only read: use the Atoms object's own arrays when it exposes them (get_positions() returns a copy)
+    pos = np.ascontiguousarray(atoms.positions if hasattr(atoms, "positions") else atoms.get_positions(), dtype=np.float64)
+    Z = np.ascontiguousarray(atoms.numbers if hasattr(atoms, "numbers") else atoms.get_atomic_numbers(), dtype=np.int32)
     lat = np.ascontiguousarray(np.asarray(atoms.get_cell(), dtype=np.float64).reshape(9))  # rows = vectors = Fortran columns
     pbc = np.ascontiguousarray(np.asarray(atoms.get_pbc(), dtype=bool).astype(np.int32))
     return pos, Z, lat, pbc
