@@ -301,7 +301,7 @@ def run_b200(args):
     # ---- value: HBM-resident inputs, CUDA events per step, L2 flushed between steps ----
     # everything below is enqueued on sp.stream (a real stream; events are recorded on the stream the kernels run on)
     torch.cuda.set_stream(sp.stream)
-    pot.set_timing(True)  # per-stage events for the roofline of this leg
+    pot.set_timing(2)  # timed region: only the events that bracket the covariance GEMMs (the roofline kernel)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
@@ -334,8 +334,22 @@ def run_b200(args):
     value = N / (ms_per_step * 1e-3)
     result = d_packed[:10].cpu().numpy()
 
+    # ---- the other stages' times, for the record: a separate instrumented pass (every stage event adds ~1 us to the step) ----
+    pot.set_timing(1)
+    stage_diag = {}
+    for k in range(args.steps):
+        flush.zero_()
+        sp.calc_resident_enqueue(N, d_pos, d_Z, lat, pbc, d_packed, want_grad=True)
+        assert sp.calc_resident_finish()
+        for name, ms in pot.last_timings().items():
+            stage_diag[name] = stage_diag.get(name, 0.0) + ms
+    for name in stage_diag:
+        if name not in ("cov_gemm1", "cov_gemm2"):
+            stage_sum[name] = stage_diag[name]
+    barrier()
+
     # ---- e2e: host-pointer API, pinned host buffers, H2D + D2H inside the timed region, wall clock ----
-    pot.set_timing(False)  # the stage events are instrumentation of the leg above
+    pot.set_timing(False)  # the stage events are instrumentation of the legs above
     for _ in range(3):
         r = sp.calc(atoms, force=True, virial=True)
     barrier()
@@ -392,7 +406,9 @@ def run_b200(args):
     roofline = {"kernel": dom + (" (GEMM-1 + GEMM-2 launches of the covariance stage)" if dom == "k_dgemm_nt" else ""), "bound": kd["bound"],
                 "achieved": achieved, "peak": peak, "unit": kd["unit"], "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "ms_per_launch": st[dom] / kd.get("launches", 1),
-                "stage_ms": {k: round(v, 4) for k, v in st.items()}, "fp64_dgemm_tflops_measured": fp64_peak,
+                "stage_ms": {k: round(v, 4) for k, v in st.items()},
+                "stage_ms_note": "cov_gemm1 / cov_gemm2 / k_dgemm_nt: CUDA events inside the timed region; the other stages: a separate fully instrumented pass of the same steps",
+                "fp64_dgemm_tflops_measured": fp64_peak,
                 "cov_pair_tflops": 4.0 * d * M_SPARSE * nc / ((st["cov_gemm1"] + st["cov_gemm2"]) * 1e-3) / 1e12}
 
     cpu = cpu_baseline_leg(xml, atoms) if (world == 1 and not args.no_cpu_baseline) else None

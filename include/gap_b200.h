@@ -164,7 +164,8 @@ long gap_potential_launch_count(const gap_potential* pot);
  * totals) [7] whole calc.  CUDA events on the stream the calc was enqueued on; waits for the last calc. */
 int gap_potential_last_timings(gap_potential* pot, double* ms8);
 /* The per-stage events are instrumentation (system_timer in the reference, e.g. IPModel_GAP.f95:428): recorded only after
- * gap_potential_set_timing(pot, 1); off by default, gap_potential_last_timings then returns zeros. */
+ * gap_potential_set_timing(pot, 1); off by default, gap_potential_last_timings then returns zeros.  on = 2 records only the
+ * three events that bracket the two covariance GEMMs (slots [2] and [3]; the other slots stay zero). */
 int gap_potential_set_timing(gap_potential* pot, int on);
 
 /* Host-only: parse a model exactly as initialise would (XML + descriptor strings + SOAP radial-basis set-up) and

@@ -126,7 +126,7 @@ struct gap_potential {
   // per-coordinate workspaces
   DevBuf b_velo, b_velo2, b_acc, b_mass, b_ke;  // MD driver state
   DevBuf b_flags, b_scan, b_centres, b_x, b_xlm, b_pnorm, b_acoef, b_gvec, b_epart, b_vir, b_fin;
-  bool timing = false;         // record per-stage CUDA events (gap_potential_set_timing)
+  int timing = 0;              // 0: no events; 1: per-stage CUDA events; 2: only around the covariance GEMMs (gap_potential_set_timing)
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_stage;
   size_t ev_used = 0;
@@ -304,6 +304,8 @@ enum { ST_CONNECT = 0, ST_SOAP_FWD = 1, ST_COV_GEMM1 = 2, ST_COV_GEMM2 = 3, ST_S
 
 void mark(gap_potential* P, cudaStream_t st, int stage) {
   if (!P->timing) return;  // stage timing is instrumentation: off unless gap_potential_set_timing asked for it
+  // level 2: only the events that bracket the covariance GEMMs (end of the SOAP forward stage, end of GEMM-1, end of GEMM-2)
+  if (P->timing == 2 && stage != ST_SOAP_FWD && stage != ST_COV_GEMM1 && stage != ST_COV_GEMM2) return;
   if (P->ev_used == P->ev.size()) {
     cudaEvent_t e;
     CUDA_OK(cudaEventCreate(&e));
@@ -321,6 +323,7 @@ void collect_timings(gap_potential* P) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, P->ev[k - 1], P->ev[k]) == cudaSuccess) {
       int st = P->ev_stage[k];
+      if (P->timing == 2 && st != ST_COV_GEMM1 && st != ST_COV_GEMM2) continue;  // intervals between the brackets are not stages
       if (st >= 0 && st < 7) P->last_ms[st] += ms;
     }
   }
@@ -1464,7 +1467,7 @@ void quip_lammps_wrapper(int* nlocal, int* nghost, int* atomic_numbers, int* lmp
 int gap_potential_set_timing(gap_potential* P, int on) {
   return guard([&] {
     if (!P) throw GapError("gap_potential_set_timing: pot is NULL");
-    P->timing = on != 0;
+    P->timing = on == 2 ? 2 : (on != 0 ? 1 : 0);
     P->ev_used = 0;
   });
 }

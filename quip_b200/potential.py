@@ -356,8 +356,9 @@ class Potential:
         return load_library().gap_potential_launch_count(self._h)
 
     def set_timing(self, on=True):
-        """Record per-stage CUDA events during calc (off by default; see last_timings)."""
-        _check(load_library().gap_potential_set_timing(self._h, 1 if on else 0))
+        """Record per-stage CUDA events during calc (off by default; see last_timings).  on=2: only the events around the two
+        covariance GEMMs."""
+        _check(load_library().gap_potential_set_timing(self._h, 2 if on == 2 else (1 if on else 0)))
 
     def last_timings(self):
         t = np.zeros(8)
