@@ -17,11 +17,11 @@
 // (Per-thread cp.async copies were the one part of the old main loop that cost DMMA issue slots: tools/dmma_loop_probe.cu.)
 // Lane (fr, fk) of a DMMA fragment owns k = 4 fk .. 4 fk + 3 of every slab -- a permutation of k common to both operands -- so
 // its operands are two LDS.128 per row and slab, conflict-free under the swizzle (16-byte chunk (2 fk + h) ^ fr); the K tail
-// (K is a multiple of 4, not of 16; the TMA zero-fills beyond K) runs its last slab in the plain k order with LDS.64.  CTA tile 64 x BN x 16 (BN = 128 or 112), 4 warps as 2(M) x 2(N), warp tile 32 x BN/2 =
-// 4 x (8 or 7) DMMA tiles, TWO CTAs resident per SM so that one CTA's epilogue (the kernel non-linearity and the
-// 64 x BN store) overlaps the other's main loop and the tail is balanced at half-tile granularity.  GEMM-2 can be
-// split along K (= the sparse-point index) into `ksplit` partial outputs when it has too few tiles to fill 148 SMs;
-// the consumer (the SOAP adjoint kernel) adds the partials in a fixed order.
+// (K is a multiple of 4, not of 16; the TMA zero-fills beyond K) runs its last slab in the plain k order with LDS.64.
+// CTA tile 64 x BN x 16 (BN = 128, 112, 96 or 80: GEMM-1 picks the one that fills the last round of CTA slots), 4 warps as
+// 2(M) x 2(N), warp tile 32 x BN/2 = 4 x (8 .. 5) DMMA tiles, TWO CTAs resident per SM.  GEMM-2 can be split along K
+// (= the sparse-point index) into `ksplit` partial outputs when it has too few tiles to fill 2 x 148 CTA slots; the
+// consumer (the SOAP adjoint kernel) adds the partials in a fixed order.
 #include <cuda.h>
 
 #include <stdexcept>
