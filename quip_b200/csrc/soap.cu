@@ -24,11 +24,15 @@
 //  * The transform_basis product is hoisted out of the neighbour loop (it is linear): X = Xt.T once per centre and
 //    Lambda~ = Lambda.T^T once per centre, instead of the reference's per-neighbour matmul (descriptors.f95:8261-8263).
 //
-// One CTA (128 threads = 4 warps) per centre, several CTAs resident per SM.  Per tile of neighbours the threads first
-// evaluate per-neighbour items -- (neighbour, radial basis point) -> Phi_l / R_l by the reference's upward recursion,
-// (neighbour, m) -> Y_{l,+-m} (and gradient) by recursion in l -- into shared memory, then the warps run the tensor-core
-// contractions over output tiles.  All reductions are fixed-order (deterministic) except the final force scatter,
-// which uses FP64 atomics on HBM.
+// Two kernel families.  Specialised shapes (n_max, l_max, n_species) run WARP-per-centre kernels (k_soap_forward_w,
+// k_soap_adjoint_w): a warp owns its centre from the first load to the last store, the radial and harmonic recursions feed
+// the DMMA fragments directly from registers, and nothing needs a block barrier (ncu showed a fifth of the block kernels'
+// stall samples at barriers).  Every other shape -- and the adjoint of shapes whose per-warp state would leave fewer than
+// 12 warps per SM -- runs the generic kernels: one CTA (128 threads = 4 warps) per centre, several CTAs resident per SM; per
+// tile of neighbours the threads first evaluate per-neighbour items -- (neighbour, radial basis point) -> Phi_l / R_l by the
+// reference's upward recursion, (neighbour, m) -> Y_{l,+-m} (and gradient) by recursion in l -- into shared memory, then
+// the warps run the tensor-core contractions over output tiles.  All reductions are fixed-order (deterministic) except the
+// final force scatter, which uses FP64 atomics on HBM.
 #include "gap_device.cuh"
 
 namespace gapb200 {
