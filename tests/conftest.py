@@ -14,6 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """Build the CUDA library and the oracle if the tree is fresh (nvcc cross-compiles without a GPU); an existing build is kept."""
+    lib = os.path.join(ROOT, "quip_b200", "libgapb200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+
+        __graft_entry__.build()
+
+
 @pytest.fixture(scope="session")
 def golden():
     return GOLDEN
