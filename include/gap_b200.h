@@ -51,9 +51,27 @@ int gap_potential_print(const gap_potential* pot, char* buf, size_t n);
  * Outputs are then PARTIAL sums; the host reduces them (the reference's sum_in_place calls, IPModel_GAP.f95:538-556). */
 int gap_potential_set_partition(gap_potential* pot, int rank, int n_ranks);
 
+/* ---- the reduction over ranks, inside the library (replaces the reference's MPI_context + the five sum_in_place calls,
+ * src/libAtoms/MPI_context.f95:668-694, src/Potentials/IPModel_GAP.f95:538-556; the mpi argument of IPModel_GAP_Calc).
+ * One process per GPU.  Rank 0 calls gap_comm_get_unique_id and the HOST distributes the 128 bytes to the other ranks
+ * (MPI_Bcast in a Fortran / LAMMPS host, torch.distributed in quip_b200.ShardedPotential); every rank then calls
+ * gap_potential_set_comm (collective: NCCL communicator over NVLink / NVSwitch).  It also sets the partition (rank, n_ranks).
+ * From then on gap_potential_calc, gap_potential_calc_device[_enqueue], gap_md_run and gap_md_run_device return TOTALS on every
+ * rank: the packed [E | virial | F(3,N)] partials (and local_e / local_virial when requested) are summed on the evaluation's
+ * stream by ncclAllReduce or, for latency-bound sizes, by a one-shot peer-memory kernel over NVLink P2P (csrc/comm.cu;
+ * GAP_B200_P2P=0 forces NCCL).  n_ranks = 1 removes the communicator. */
+#define GAP_COMM_ID_BYTES 128
+int gap_comm_get_unique_id(char* id /* GAP_COMM_ID_BYTES */);
+int gap_potential_set_comm(gap_potential* pot, const char* id /* GAP_COMM_ID_BYTES */, int rank, int n_ranks);
+/* rank / n_ranks of the handle and the transport of its last reduction ("nccl", "p2p" or "none") */
+int gap_potential_comm_info(const gap_potential* pot, int* rank, int* n_ranks, char* transport, size_t n);
+
 /* calc(pot, at, energy, force, virial, local_energy, local_virial, args_str) (Potential.f95:803 ->
  * IPModel_GAP_Calc, IPModel_GAP.f95:233), including the neighbour-list build the reference does in
- * potential_calc (:844-859 -> calc_connect, src/libAtoms/Connection.f95:1035).  All pointers are HOST pointers. */
+ * potential_calc (:844-859 -> calc_connect, src/libAtoms/Connection.f95:1035).  All pointers are HOST pointers; arrays the
+ * caller has page-locked (cudaHostAlloc / cudaHostRegister) are transferred in place, pageable ones through a staging buffer.
+ * With a communicator every rank passes the whole configuration and receives the totals; a rank that does not need an
+ * array (e.g. the forces on ranks other than 0) passes NULL and skips that device-to-host copy. */
 int gap_potential_calc(gap_potential* pot, int N, const double* pos, const int* Z, const double* lattice, const int* pbc,
                        const char* args_str, double* energy, double* local_e, double* force, double* virial,
                        double* local_virial);

@@ -1,0 +1,318 @@
+// comm.cu -- the reduction of the per-rank partials [E | virial | F] over the GPUs of one node (see gap_comm.h).
+//
+// Reference semantics: sum_in_place(mpi, f) etc. = MPI_Allreduce(MPI_IN_PLACE, ..., MPI_SUM) (src/libAtoms/MPI_context.f95:668-694),
+// issued five times at the end of IPModel_GAP_Calc (src/Potentials/IPModel_GAP.f95:538-556).  Here: ONE reduction of one packed
+// buffer, enqueued on the evaluation's stream, by NCCL or -- for latency-bound sizes -- by one kernel that reads the partials
+// of all ranks through NVLink peer mappings.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gap_comm.h"
+#include "gap_model.h"
+
+namespace gapb200 {
+
+namespace {
+
+#define CUDA_OK(expr)                                                                                               \
+  do {                                                                                                              \
+    cudaError_t _e = (expr);                                                                                        \
+    if (_e != cudaSuccess)                                                                                          \
+      throw GapError(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+// ---- libnccl, loaded on first use.  A process that already carries an NCCL (PyTorch bundles one) gets THAT copy: glibc
+//      resolves the soname against the objects already loaded.  GAP_B200_NCCL_LIB overrides the name.
+struct Nccl {
+  void* lib = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+Nccl& nccl() {
+  static Nccl n = [] {
+    Nccl t;
+    const char* env = getenv("GAP_B200_NCCL_LIB");
+    const char* names[] = {env && *env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      t.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (t.lib) break;
+    }
+    if (!t.lib) return t;
+    auto sym = [&](const char* s) { return dlsym(t.lib, s); };
+    t.GetVersion = (decltype(t.GetVersion))sym("ncclGetVersion");
+    t.GetUniqueId = (decltype(t.GetUniqueId))sym("ncclGetUniqueId");
+    t.CommInitRank = (decltype(t.CommInitRank))sym("ncclCommInitRank");
+    t.CommDestroy = (decltype(t.CommDestroy))sym("ncclCommDestroy");
+    t.AllReduce = (decltype(t.AllReduce))sym("ncclAllReduce");
+    t.AllGather = (decltype(t.AllGather))sym("ncclAllGather");
+    t.GetErrorString = (decltype(t.GetErrorString))sym("ncclGetErrorString");
+    return t;
+  }();
+  if (!n.lib || !n.GetUniqueId || !n.CommInitRank || !n.AllReduce || !n.AllGather || !n.CommDestroy)
+    throw GapError("gap_comm: libnccl.so.2 could not be loaded (set GAP_B200_NCCL_LIB); a multi-GPU run needs NCCL");
+  return n;
+}
+void nccl_ok(ncclResult_t r, const char* what) {
+  if (r == ncclSuccess) return;
+  const char* s = nccl().GetErrorString ? nccl().GetErrorString(r) : "?";
+  throw GapError(std::string("NCCL error in ") + what + ": " + s);
+}
+
+constexpr int P2P_MAX_RANKS = 16;
+constexpr size_t P2P_FLAG_BYTES = 256;                // [n_ranks] step counters, one 256-byte line
+constexpr unsigned long long P2P_TIMEOUT_NS = 4000000000ull;
+
+struct PeerPtrs {
+  char* base[P2P_MAX_RANKS];  // base[r]: rank r's block (flags | buffer 0 | buffer 1) as mapped into THIS process
+};
+
+// One-shot all-reduce out of peer memory.  Every rank runs this kernel on its own GPU:
+//   1. block 0 tells every rank (itself included) that this rank's partial of step `step` is complete: the partial was written
+//      by earlier kernels of the same stream, so it is globally visible when this kernel starts;
+//   2. every block waits until all G ranks have said so (flags live in the waiter's own memory: local polling);
+//   3. the blocks sum the G partials element-wise in RANK order (bit-identical on every rank) reading peers over NVLink with
+//      L1-bypassing 16-byte loads, all G loads of an element in flight at once, and store the totals to the local result.
+// The partial buffers alternate between steps, so a fast rank can start writing step s+1 while a slow one still reads step s;
+// it cannot reach step s+2 (same buffer again) before every rank has signalled s+1, i.e. has left the kernel of step s.
+__global__ void __launch_bounds__(256) k_peer_allreduce(PeerPtrs peers, int rank, int n, unsigned step, size_t buf_off, size_t count,
+                                                        double* __restrict__ result, int* __restrict__ err) {
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < n) {
+    unsigned* f = reinterpret_cast<unsigned*>(peers.base[threadIdx.x]) + rank;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(f), "r"(step) : "memory");
+  }
+  if (threadIdx.x < n) {
+    const unsigned* f = reinterpret_cast<const unsigned*>(peers.base[rank]) + threadIdx.x;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - step) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+      if (t1 - t0 > P2P_TIMEOUT_NS) { timed_out = 1; break; }
+    }
+  }
+  __syncthreads();
+  if (timed_out) {
+    if (threadIdx.x == 0) atomicExch(err, 1);
+    return;
+  }
+  const size_t n2 = count >> 1, stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t idx = t; idx < n2; idx += stride) {
+    double sx = 0.0, sy = 0.0;
+    for (int r0 = 0; r0 < n; r0 += 8) {
+      double vx[8], vy[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        vx[k] = vy[k] = 0.0;
+        if (r0 + k < n) {
+          const char* p = peers.base[r0 + k] + buf_off + 16 * idx;
+          asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];\n" : "=d"(vx[k]), "=d"(vy[k]) : "l"(p));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (r0 + k < n) { sx += vx[k]; sy += vy[k]; }
+    }
+    *reinterpret_cast<double2*>(result + 2 * idx) = make_double2(sx, sy);
+  }
+  if ((count & 1) && t == 0) {  // odd tail element
+    double s = 0.0;
+    for (int r = 0; r < n; r++) s += __ldcg(reinterpret_cast<const double*>(peers.base[r] + buf_off) + (count - 1));
+    result[count - 1] = s;
+  }
+}
+
+}  // namespace
+
+struct GapComm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, n = 1, device = 0, n_sm = 148;
+  // peer-memory transport
+  bool p2p_enabled = true;          // GAP_B200_P2P=0 turns it off; a failed handle exchange turns it off for good
+  size_t p2p_limit_bytes = 8u << 20;  // largest partial buffer reduced out of peer memory (beyond it NCCL's bandwidth algorithms win)
+  char* block = nullptr;            // local: [flags | buffer 0 | buffer 1]
+  size_t cap = 0;                   // doubles per buffer
+  void* peer_base[P2P_MAX_RANKS] = {nullptr};
+  unsigned step = 0;
+  bool partial_is_peer = false;     // the partial of the step in flight lives in block (else: in the result buffer)
+  int* d_err = nullptr;
+  int* h_err = nullptr;             // pinned
+  char* d_handles = nullptr;        // [n + 1] x 64 bytes (slot n: this rank's handle, the send buffer)
+  int* d_okflag = nullptr;
+  const char* last = "none";
+  long launches = 0;
+};
+
+void comm_get_unique_id(char* id128) {
+  static_assert(sizeof(ncclUniqueId) == COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  nccl_ok(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+  memcpy(id128, &id, sizeof(id));
+}
+
+GapComm* comm_create(const char* id128, int rank, int n_ranks, int device) {
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw GapError("gap_potential_set_comm: need 0 <= rank < n_ranks");
+  CUDA_OK(cudaSetDevice(device));
+  GapComm* c = new GapComm();
+  c->rank = rank; c->n = n_ranks; c->device = device;
+  try {
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    nccl_ok(nccl().CommInitRank(&c->comm, n_ranks, id, rank), "ncclCommInitRank");
+    const char* e = getenv("GAP_B200_P2P");
+    if ((e && *e == '0') || n_ranks > P2P_MAX_RANKS || n_ranks < 2) c->p2p_enabled = false;
+    const char* lim = getenv("GAP_B200_P2P_MAX_BYTES");
+    if (lim && *lim) c->p2p_limit_bytes = (size_t)strtoull(lim, nullptr, 10);
+    CUDA_OK(cudaMalloc(&c->d_err, sizeof(int)));
+    CUDA_OK(cudaMemset(c->d_err, 0, sizeof(int)));
+    CUDA_OK(cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocDefault));
+    *c->h_err = 0;
+    CUDA_OK(cudaMalloc(&c->d_handles, (size_t)(n_ranks + 1) * sizeof(cudaIpcMemHandle_t)));
+    CUDA_OK(cudaMalloc(&c->d_okflag, sizeof(int)));
+  } catch (...) {
+    comm_destroy(c);
+    throw;
+  }
+  return c;
+}
+
+static void p2p_release(GapComm* c) {
+  for (int r = 0; r < c->n && r < P2P_MAX_RANKS; r++) {
+    if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    c->peer_base[r] = nullptr;
+  }
+  if (c->block) cudaFree(c->block);
+  c->block = nullptr;
+  c->cap = 0;
+}
+
+void comm_destroy(GapComm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  p2p_release(c);
+  if (c->comm) nccl().CommDestroy(c->comm);
+  cudaFree(c->d_err);
+  cudaFree(c->d_handles);
+  cudaFree(c->d_okflag);
+  if (c->h_err) cudaFreeHost(c->h_err);
+  delete c;
+}
+
+int comm_rank(const GapComm* c) { return c ? c->rank : 0; }
+int comm_size(const GapComm* c) { return c ? c->n : 1; }
+const char* comm_last_transport(const GapComm* c) { return c ? c->last : "none"; }
+long comm_launch_count(const GapComm* c) { return c ? c->launches : 0; }
+
+// (Re)allocate the peer-visible block for `count` doubles per buffer and map every other rank's block.  Collective.
+static void p2p_setup(GapComm* c, size_t count, cudaStream_t st) {
+  const size_t want = ((count + count / 4 + 1024) + 1) & ~(size_t)1;
+  CUDA_OK(cudaStreamSynchronize(st));
+  char* nb = nullptr;
+  const size_t bytes = P2P_FLAG_BYTES + 2 * want * sizeof(double);
+  bool ok = cudaMalloc(&nb, bytes) == cudaSuccess;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) ok = cudaMemset(nb, 0, P2P_FLAG_BYTES) == cudaSuccess && cudaIpcGetMemHandle(&mine, nb) == cudaSuccess;
+  cudaGetLastError();
+  // every rank takes part in the exchange even if its own allocation failed (the verdict below is collective)
+  CUDA_OK(cudaMemcpyAsync(c->d_handles + (size_t)c->n * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  nccl_ok(nccl().AllGather(c->d_handles + (size_t)c->n * sizeof(mine), c->d_handles, sizeof(mine), ncclChar, c->comm, st), "ncclAllGather (peer handles)");
+  std::vector<cudaIpcMemHandle_t> all(c->n);
+  CUDA_OK(cudaMemcpyAsync(all.data(), c->d_handles, (size_t)c->n * sizeof(mine), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));  // also: every rank has left the kernels that used the old block
+  p2p_release(c);
+  void* opened[P2P_MAX_RANKS] = {nullptr};
+  for (int r = 0; r < c->n && ok; r++) {
+    if (r == c->rank) { opened[r] = nb; continue; }
+    if (cudaIpcOpenMemHandle(&opened[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened[r] = nullptr; ok = false; }
+  }
+  cudaGetLastError();
+  int bad = ok ? 0 : 1;
+  CUDA_OK(cudaMemcpyAsync(c->d_okflag, &bad, sizeof(int), cudaMemcpyHostToDevice, st));
+  nccl_ok(nccl().AllReduce(c->d_okflag, c->d_okflag, 1, ncclInt32, ncclSum, c->comm, st), "ncclAllReduce (peer mapping verdict)");
+  CUDA_OK(cudaMemcpyAsync(&bad, c->d_okflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (bad) {  // some rank could not map its peers: everybody stays on NCCL
+    for (int r = 0; r < c->n; r++)
+      if (r != c->rank && opened[r]) cudaIpcCloseMemHandle(opened[r]);
+    if (nb) cudaFree(nb);
+    cudaGetLastError();
+    c->p2p_enabled = false;
+    return;
+  }
+  c->block = nb;
+  c->cap = want;
+  for (int r = 0; r < c->n; r++) c->peer_base[r] = opened[r];
+}
+
+double* comm_partial_buffer(GapComm* c, size_t count, double* result, cudaStream_t st) {
+  if (!c || c->n < 2) return result;
+  c->partial_is_peer = false;
+  if (c->p2p_enabled && count * sizeof(double) <= c->p2p_limit_bytes) {
+    if (count > c->cap) p2p_setup(c, count, st);
+    if (c->p2p_enabled && count <= c->cap) {
+      // the step counter advances when the reduction is enqueued (comm_allreduce_packed): an evaluation that throws in between
+      // leaves this rank's counter where its peers expect it
+      c->partial_is_peer = true;
+      return reinterpret_cast<double*>(c->block + P2P_FLAG_BYTES) + (size_t)((c->step + 1u) & 1u) * c->cap;
+    }
+  }
+  return result;
+}
+
+void comm_allreduce_packed(GapComm* c, size_t count, double* result, cudaStream_t st) {
+  if (!c || c->n < 2 || count == 0) return;
+  if (c->partial_is_peer) {
+    c->step++;
+    PeerPtrs pp;
+    for (int r = 0; r < P2P_MAX_RANKS; r++) pp.base[r] = r < c->n ? (char*)c->peer_base[r] : nullptr;
+    const size_t buf_off = P2P_FLAG_BYTES + (size_t)(c->step & 1u) * c->cap * sizeof(double);
+    int blocks = (int)((count / 2 + 255) / 256);
+    if (blocks > 2 * c->n_sm) blocks = 2 * c->n_sm;
+    if (blocks < 1) blocks = 1;
+    k_peer_allreduce<<<blocks, 256, 0, st>>>(pp, c->rank, c->n, c->step, buf_off, count, result, c->d_err);
+    CUDA_OK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    c->last = "p2p";
+  } else {
+    nccl_ok(nccl().AllReduce(result, result, count, ncclFloat64, ncclSum, c->comm, st), "ncclAllReduce");
+    c->last = "nccl";
+  }
+  c->launches++;
+}
+
+void comm_allreduce_inplace(GapComm* c, double* buf, size_t count, cudaStream_t st) {
+  if (!c || c->n < 2 || count == 0) return;
+  nccl_ok(nccl().AllReduce(buf, buf, count, ncclFloat64, ncclSum, c->comm, st), "ncclAllReduce");
+  c->launches++;
+}
+
+void comm_check(GapComm* c) {
+  if (!c || !c->h_err) return;
+  if (*c->h_err) {
+    *c->h_err = 0;
+    cudaMemset(c->d_err, 0, sizeof(int));
+    throw GapError("gap_comm: the peer-memory reduction timed out waiting for another rank (did a rank fail before its evaluation?)");
+  }
+}
+
+}  // namespace gapb200

@@ -421,6 +421,11 @@ GapModel load_gap_model(const std::string& args_str_in, const std::string& param
     throw GapError("Potential_initialise: only simple 'IP GAP' potentials are supported by the B200 path, got '" + args_str + "'");
   if (!(args.has("IP") && args.has("GAP")))
     throw GapError("Potential_initialise: init args must be 'IP GAP [label=...]', got '" + args_str + "'");
+  // Potential-level rescaling (Potential.f95:568-746: r_scale / E_scale wrapped around calc, target_vol / target_B fitted at
+  // initialise) is not part of the GAP path: refuse it rather than return unscaled results
+  for (const char* k : {"do_rescale_r", "do_rescale_E", "r_scale", "target_vol", "target_B", "minimise_bulk"})
+    if (args.has(k))
+      throw GapError(std::string("Potential_initialise: ") + k + " (rescaling of the potential, Potential.f95:568-746) is not supported by the B200 path");
 
   GapModel m;
   for (double& v : m.e0) v = 0.0;

@@ -61,8 +61,10 @@ __global__ void k_minmax_final(const double* __restrict__ part, int nb, double* 
   out6[r] = v;
 }
 
-// err_flag: set when an atom lies more than MAX_MAP_SHIFT periodic images away from the cell (shifts are carried as int8)
-constexpr int MAX_MAP_SHIFT = 60;
+// err_flag: set when an atom lies more than MAX_MAP_SHIFT periodic images away from the cell.  Shifts are carried as int8: with
+// |map_shift| <= 30 and at most 60 cell images (build_connect) every intermediate s - map_shift(i) (<= 90) and every total shift
+// s - map_shift(i) + map_shift(j) (<= 120) fits.
+constexpr int MAX_MAP_SHIFT = 30;
 // cell_count != NULL: also count the atoms of every cell (counting-sort path)
 __global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int* __restrict__ cell_of, int* __restrict__ mshift,
                       int* __restrict__ iota, int* __restrict__ err_flag, int* __restrict__ cell_count) {

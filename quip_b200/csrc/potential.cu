@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <fstream>
@@ -18,6 +19,7 @@
 #include <vector>
 
 #include "../../include/gap_b200.h"
+#include "gap_comm.h"
 #include "gap_device.cuh"
 #include "gap_model.h"
 
@@ -86,6 +88,7 @@ struct gap_potential {
   std::vector<CoordDev> cd;
   double* d_e0 = nullptr;
   int rank = 0, n_ranks = 1;
+  GapComm* comm = nullptr;     // set by gap_potential_set_comm: the reduction over ranks happens inside the library
   int n_sm = 148;
   int g_splits = 1;            // K splits of the last GEMM-2 (partial gvec buffers)
   int g_tiles_n = 1;           // column tiles of the last GEMM-1 (partial energies per row in epart)
@@ -452,7 +455,7 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
     if (grid.pbc[k]) {
       grid.R[k] = (int)std::ceil(cutoff / width[k] + 1e-9);
       if (grid.R[k] < 1) grid.R[k] = 1;
-      if ((grid.R[k] + grid.n[k] - 1) / grid.n[k] + 2 > 120) throw GapError("calc_connect: cutoff is too large for this cell (more than 120 images)");
+      if ((grid.R[k] + grid.n[k] - 1) / grid.n[k] + 2 > 60) throw GapError("calc_connect: cutoff is too large for this cell (more than 60 images)");
     } else {
       grid.R[k] = grid.n[k] > 1 ? (int)std::ceil(cutoff / width[k] + 1e-9) : 0;
       if (grid.R[k] > grid.n[k] - 1) grid.R[k] = grid.n[k] - 1;
@@ -500,7 +503,7 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   CUDA_OK(cudaMemcpyAsync(P->h_pin, stat, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   const int nnz = P->h_pin[0];
-  if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 60 periodic images away from the cell; wrap the positions first");
+  if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 30 periodic images away from the cell; wrap the positions first");
   if (nnz < 0) throw GapError("calc_connect: neighbour list exceeds 2^31 entries");
   P->conn_nnz = nnz;
   P->row_hint = P->h_pin[2]; P->hint_N = N; P->hint_first = first; P->hint_last = last;
@@ -518,7 +521,7 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
 bool verify_connect(gap_potential* P) {
   if (!P->pending_check) return true;
   P->pending_check = false;
-  if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 60 periodic images away from the cell; wrap the positions first");
+  if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 30 periodic images away from the cell; wrap the positions first");
   const int max_row = P->h_pin[2];
   const bool ok = max_row <= P->pending_cap;
   P->row_hint = ok ? max_row : -1;  // overflow: the repeat takes the exact (synchronising) path
@@ -1012,6 +1015,30 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   CUDA_OK(cudaGetLastError());
 }
 
+// This rank's block of centres and, when a communicator is set, the sum of the partials over the ranks (IPModel_GAP.f95:538-556):
+// d_packed (and d_le_user / d_lv if given) hold the TOTALS on every rank once the stream has drained.
+void calc_reduced(gap_potential* P, int N, const double* d_pos, const int* d_Z, const double* lattice, const int* pbc, const char* args_str,
+                  bool want_grad, double* d_packed, double* d_le_user, double* d_lv, cudaStream_t st) {
+  if (!P->comm || comm_size(P->comm) < 2) {
+    calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad, d_packed, d_le_user, d_lv, st);
+    return;
+  }
+  const size_t count = 10 + 3 * (size_t)N;
+  double* partial = comm_partial_buffer(P->comm, count, d_packed, st);
+  calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad, partial, d_le_user, d_lv, st);
+  comm_allreduce_packed(P->comm, count, d_packed, st);
+  if (d_le_user) comm_allreduce_inplace(P->comm, d_le_user, (size_t)N, st);
+  if (d_lv) comm_allreduce_inplace(P->comm, d_lv, 9 * (size_t)N, st);
+  mark(P, st, ST_OTHER);
+}
+
+bool host_pointer_is_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int guard(const std::function<void()>& fn) {
   try {
     fn();
@@ -1063,6 +1090,8 @@ void gap_potential_finalise(gap_potential* P) {
   if (!P) return;
   cudaSetDevice(P->device);
   if (P->stream) cudaStreamSynchronize(P->stream);
+  if (P->comm) comm_destroy(P->comm);
+  P->comm = nullptr;
   for (CoordDev& cd : P->cd) {
     cudaFree(cd.d_sp); cudaFree(cd.sp_rows); cudaFree(cd.st_rows); cudaFree(cd.alpha); cudaFree(cd.scut);
     cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2); cudaFree(cd.var_mat);
@@ -1115,6 +1144,39 @@ int gap_potential_set_partition(gap_potential* P, int rank, int n_ranks) {
   });
 }
 
+int gap_comm_get_unique_id(char* id) {
+  return guard([&] {
+    if (!id) throw GapError("gap_comm_get_unique_id: id is NULL");
+    comm_get_unique_id(id);
+  });
+}
+
+int gap_potential_set_comm(gap_potential* P, const char* id, int rank, int n_ranks) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_set_comm: pot is NULL");
+    if (P->comm) { comm_destroy(P->comm); P->comm = nullptr; }
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw GapError("gap_potential_set_comm: need 0 <= rank < n_ranks");
+    if (n_ranks > 1) {
+      if (!id) throw GapError("gap_potential_set_comm: id is NULL");
+      P->comm = comm_create(id, rank, n_ranks, P->device);
+    }
+    P->rank = rank;
+    P->n_ranks = n_ranks;
+  });
+}
+
+int gap_potential_comm_info(const gap_potential* P, int* rank, int* n_ranks, char* transport, size_t n) {
+  if (!P) return 1;
+  if (rank) *rank = P->rank;
+  if (n_ranks) *n_ranks = P->n_ranks;
+  if (transport && n) {
+    const char* t = P->comm ? comm_last_transport(P->comm) : "none";
+    strncpy(transport, t, n - 1);
+    transport[n - 1] = 0;
+  }
+  return 0;
+}
+
 int gap_potential_set_atom_mask(gap_potential* P, int N, const int* mask) {
   return guard([&] {
     if (!P) throw GapError("gap_potential_set_atom_mask: pot is NULL");
@@ -1164,11 +1226,19 @@ int gap_potential_calc_device(gap_potential* P, int N, const double* d_pos, cons
     if (N < 0) throw GapError("gap_potential_calc_device: N < 0");
     if (!d_packed) throw GapError("gap_potential_calc_device: d_packed is NULL");
     cudaStream_t st = stream ? (cudaStream_t)stream : P->stream;
+    const bool sharded = P->comm && comm_size(P->comm) > 1;
     for (int attempt = 0; attempt < 2; attempt++) {
-      calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad != 0 || d_local_virial != nullptr, d_packed, d_local_e, d_local_virial, st);
-      if (!P->pending_check) break;  // exact list: nothing to verify, the work is simply enqueued
+      calc_reduced(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad != 0 || d_local_virial != nullptr, d_packed, d_local_e, d_local_virial, st);
+      if (!sharded && !P->pending_check) break;  // exact list on one rank: nothing to verify, the work is simply enqueued
+      // a rank whose neighbour rows overflowed NaN-poisons its energy (k_finalize): after the reduction every rank sees it and all
+      // ranks repeat together
+      double e = 0.0;
+      if (sharded) CUDA_OK(cudaMemcpyAsync(&e, d_packed, sizeof(double), cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
-      if (verify_connect(P)) break;  // otherwise the speculatively sized neighbour list overflowed: repeat with the exact size
+      comm_check(P->comm);
+      const bool ok_local = verify_connect(P);
+      if (ok_local && e == e) break;
+      if (ok_local) P->row_hint = -1;  // another rank overflowed: take the exact path together with it
     }
   });
 }
@@ -1180,13 +1250,14 @@ int gap_potential_calc_device_enqueue(gap_potential* P, int N, const double* d_p
     if (N < 0) throw GapError("gap_potential_calc_device_enqueue: N < 0");
     if (!d_packed) throw GapError("gap_potential_calc_device_enqueue: d_packed is NULL");
     cudaStream_t st = stream ? (cudaStream_t)stream : P->stream;
-    calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad != 0 || d_local_virial != nullptr, d_packed, d_local_e, d_local_virial, st);
+    calc_reduced(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad != 0 || d_local_virial != nullptr, d_packed, d_local_e, d_local_virial, st);
   });
 }
 
 int gap_potential_calc_device_verify(gap_potential* P, int* repeat) {
   return guard([&] {
     if (!P || !repeat) throw GapError("gap_potential_calc_device_verify: bad arguments");
+    comm_check(P->comm);
     *repeat = verify_connect(P) ? 0 : 1;
   });
 }
@@ -1200,10 +1271,11 @@ int gap_potential_calc(gap_potential* P, int N, const double* pos, const int* Z,
     CUDA_OK(cudaSetDevice(P->device));
     cudaStream_t st = P->stream;
     const size_t n3 = 3 * (size_t)N;
-    // inputs: pos and Z staged through ONE pinned buffer into one device buffer [pos (3N f64) | Z (N i32)], one H2D copy;
-    // results: [E | virial | F] (+ local_e, local_virial) come back through one pinned buffer, one synchronisation per call
+    // inputs: pos and Z go into one device buffer [pos (3N f64) | Z (N i32)].  Host arrays that are already page-locked (cudaHostAlloc /
+    // cudaHostRegister by the caller) are copied from where they lie; pageable ones are staged through ONE pinned buffer and one H2D
+    // copy.  Results: [E | virial | F] (+ local_e, local_virial) come back the same way; one synchronisation per call.
     const size_t in_bytes = sizeof(double) * n3 + sizeof(int) * (size_t)N;
-    const size_t out_doubles = 10 + n3 + (local_e ? (size_t)N : 0) + (local_virial ? 9 * (size_t)N : 0);
+    const size_t out_doubles = 16 + n3 + (local_e ? (size_t)N : 0) + (local_virial ? 9 * (size_t)N : 0);
     P->b_pos.ensure(in_bytes + 64);
     P->b_packed.ensure(sizeof(double) * (10 + n3));
     P->b_le.ensure(sizeof(double) * (size_t)(N + 1));
@@ -1216,30 +1288,45 @@ int gap_potential_calc(gap_potential* P, int N, const double* pos, const int* Z,
     }
     double* d_pos = P->b_pos.as<double>();
     int* d_Z = (int*)(P->b_pos.as<char>() + sizeof(double) * n3);
+    const bool pinned_in = N > 0 && host_pointer_is_pinned(pos) && host_pointer_is_pinned(Z);
     if (N > 0) {
-      memcpy(P->h_stage, pos, sizeof(double) * n3);
-      memcpy(P->h_stage + sizeof(double) * n3, Z, sizeof(int) * (size_t)N);
-      CUDA_OK(cudaMemcpyAsync(P->b_pos.p, P->h_stage, in_bytes, cudaMemcpyHostToDevice, st));
+      if (pinned_in) {
+        CUDA_OK(cudaMemcpyAsync(d_pos, pos, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaMemcpyAsync(d_Z, Z, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+      } else {
+        memcpy(P->h_stage, pos, sizeof(double) * n3);
+        memcpy(P->h_stage + sizeof(double) * n3, Z, sizeof(int) * (size_t)N);
+        CUDA_OK(cudaMemcpyAsync(P->b_pos.p, P->h_stage, in_bytes, cudaMemcpyHostToDevice, st));
+      }
     }
     bool want_grad = force || virial || local_virial;  // IPModel_GAP.f95:416-424
-    double* h_out = (double*)P->h_stage;
+    const bool sharded = P->comm && comm_size(P->comm) > 1;
+    const bool pinned_f = force && N > 0 && host_pointer_is_pinned(force);
+    double* h_out = (double*)P->h_stage;  // [head (16) | F (3N) | local_e (N) | local_virial (9N)]
     for (int attempt = 0; attempt < 2; attempt++) {
-      if (attempt == 1 && N > 0) CUDA_OK(cudaStreamSynchronize(st));  // (the staging buffer is shared by both directions)
-      calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad, P->b_packed.as<double>(), P->b_le.as<double>(),
-                       local_virial ? P->b_lv.as<double>() : nullptr, st);
-      size_t o = 0;
-      CUDA_OK(cudaMemcpyAsync(h_out, P->b_packed.p, sizeof(double) * (force ? 10 + n3 : 10), cudaMemcpyDeviceToHost, st));
-      o += 10 + n3;
+      if (attempt == 1 && N > 0 && !pinned_in) CUDA_OK(cudaStreamSynchronize(st));  // (the staging buffer is shared by both directions)
+      // with a communicator the totals arrive on every rank; local_e / local_virial are reduced only when the caller wants them
+      calc_reduced(P, N, d_pos, d_Z, lattice, pbc, args_str, want_grad, P->b_packed.as<double>(), (!sharded || local_e) ? P->b_le.as<double>() : nullptr,
+                   local_virial ? P->b_lv.as<double>() : nullptr, st);
+      size_t o = 16;
+      CUDA_OK(cudaMemcpyAsync(h_out, P->b_packed.p, sizeof(double) * 10, cudaMemcpyDeviceToHost, st));
+      if (force && N > 0) CUDA_OK(cudaMemcpyAsync(pinned_f ? force : h_out + o, P->b_packed.as<double>() + 10, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
+      o += n3;
       if (local_e && N > 0) { CUDA_OK(cudaMemcpyAsync(h_out + o, P->b_le.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st)); o += N; }
       if (local_virial && N > 0) CUDA_OK(cudaMemcpyAsync(h_out + o, P->b_lv.p, sizeof(double) * 9 * (size_t)N, cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
-      if (verify_connect(P)) break;  // false: the speculatively sized neighbour list overflowed; repeat with the exact size
+      comm_check(P->comm);
+      // false: the speculatively sized neighbour list overflowed; repeat with the exact size.  A rank whose rows overflowed has
+      // NaN-poisoned its energy (k_finalize), so after the reduction every rank of a sharded run sees it and all repeat together.
+      const bool ok_local = verify_connect(P);
+      if (ok_local && (!sharded || h_out[0] == h_out[0])) break;
+      if (ok_local) P->row_hint = -1;
     }
     double head[10];
     memcpy(head, h_out, sizeof(head));
     {
-      size_t o = 10;
-      if (force && N > 0) memcpy(force, h_out + o, sizeof(double) * n3);
+      size_t o = 16;
+      if (force && N > 0 && !pinned_f) memcpy(force, h_out + o, sizeof(double) * n3);
       o += n3;
       if (local_e && N > 0) { memcpy(local_e, h_out + o, sizeof(double) * (size_t)N); o += N; }
       if (local_virial && N > 0) memcpy(local_virial, h_out + o, sizeof(double) * 9 * (size_t)N);
@@ -1268,8 +1355,14 @@ void md_run_impl(gap_potential* P, int N, double* d_pos, double* d_velo, const i
   double ke_part[128];
   auto evaluate = [&](int step) {  // calc(pot, atoms, "energy force") with the per-step neighbour-list rebuild (Potential.f95:2340-2365)
     for (int attempt = 0; attempt < 2; attempt++) {
-      calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, true, d_packed, P->b_le.as<double>(), nullptr, st);
-      if (reduce) reduce(reduce_ctx, (void*)st);  // partial [E | virial | F] -> totals on every rank (IPModel_GAP.f95:538-556)
+      // partial [E | virial | F] -> totals on every rank (IPModel_GAP.f95:538-556): by the caller's hook if one is given, else by the
+      // handle's communicator (gap_potential_set_comm)
+      if (reduce) {
+        calc_device_impl(P, N, d_pos, d_Z, lattice, pbc, args_str, true, d_packed, nullptr, nullptr, st);
+        reduce(reduce_ctx, (void*)st);
+      } else {
+        calc_reduced(P, N, d_pos, d_Z, lattice, pbc, args_str, true, d_packed, nullptr, nullptr, st);
+      }
       // the new velocities go to a second buffer: if the speculatively sized neighbour list overflowed, the evaluation is simply repeated
       k_verlet2<<<nb, 256, 0, st>>>(N, dt, d_packed + 10, d_mass, velo_cur, velo_new, P->b_acc.as<double>(), step > 0 ? 1 : 0);
       P->launches += 1;
@@ -1281,6 +1374,7 @@ void md_run_impl(gap_potential* P, int N, double* d_pos, double* d_velo, const i
       double e = 0.0;
       CUDA_OK(cudaMemcpyAsync(&e, d_packed, sizeof(double), cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
+      comm_check(P->comm);
       // a rank whose neighbour rows overflowed has NaN-poisoned its energy word (k_finalize): after the reduction every rank sees
       // it, so all ranks repeat together (the local verification also refreshes the row-capacity hint)
       const bool ok_local = verify_connect(P);
@@ -1317,7 +1411,7 @@ int gap_md_run(gap_potential* P, int N, double* pos, double* velo, const int* Z,
     if (!P) throw GapError("gap_md_run: pot is NULL");
     if (N <= 0 || !pos || !velo || !Z || !mass) throw GapError("gap_md_run: N, pos, velo, Z and mass are required");
     if (n_steps < 0) throw GapError("gap_md_run: n_steps < 0");
-    if (P->n_ranks != 1) throw GapError("gap_md_run: a partitioned run needs the reduction hook of gap_md_run_device");
+    if (P->n_ranks != 1 && !P->comm) throw GapError("gap_md_run: a partitioned run needs a communicator (gap_potential_set_comm) or the reduction hook of gap_md_run_device");
     CUDA_OK(cudaSetDevice(P->device));
     cudaStream_t st = P->stream;
     const size_t n3 = 3 * (size_t)N;
@@ -1345,7 +1439,7 @@ int gap_md_run_device(gap_potential* P, int N, double* d_pos, double* d_velo, co
     if (!P) throw GapError("gap_md_run_device: pot is NULL");
     if (N <= 0 || !d_pos || !d_velo || !d_Z || !d_mass || !d_packed) throw GapError("gap_md_run_device: N, d_pos, d_velo, d_Z, d_mass and d_packed are required");
     if (n_steps < 0) throw GapError("gap_md_run_device: n_steps < 0");
-    if (P->n_ranks != 1 && !reduce) throw GapError("gap_md_run_device: a partitioned run needs the reduction hook");
+    if (P->n_ranks != 1 && !reduce && !P->comm) throw GapError("gap_md_run_device: a partitioned run needs a communicator (gap_potential_set_comm) or the reduction hook");
     CUDA_OK(cudaSetDevice(P->device));
     md_run_impl(P, N, d_pos, d_velo, d_Z, d_mass, lattice, pbc, dt, n_steps, args_str, d_packed, reduce, reduce_ctx, epot, ekin,
                 stream ? (cudaStream_t)stream : P->stream);
@@ -1360,6 +1454,22 @@ int quip_lammps_api_version(void) { return 1; }  // quip_lammps_wrapper.f95:24-2
 
 static gap_potential* g_lammps_pot = nullptr;  // the reference keeps ONE saved Potential as well (:171)
 
+// CUDA device of a LAMMPS rank: GAP_B200_DEVICE if set, else the node-local MPI rank (Open MPI / MVAPICH / Slurm) modulo the
+// number of visible devices, so that the ranks of a multi-GPU node do not all land on device 0
+static int lammps_device() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return 0;
+  for (const char* k : {"GAP_B200_DEVICE", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID", "LOCAL_RANK"}) {
+    const char* v = getenv(k);
+    if (v && *v) {
+      char* end = nullptr;
+      long r = strtol(v, &end, 10);
+      if (end != v && r >= 0) return (int)(r % ndev);
+    }
+  }
+  return 0;
+}
+
 void quip_lammps_potential_initialise(int* quip_potential, int* n_quip_potential, double* quip_cutoff, char* quip_file, int* n_quip_file,
                                       char* quip_string, int* n_quip_string) {
   // two-call protocol (:176-192): first call (n == 0) builds the potential and returns the handle size in ints, the second
@@ -1369,7 +1479,7 @@ void quip_lammps_potential_initialise(int* quip_potential, int* n_quip_potential
     std::string file(quip_file, (size_t)*n_quip_file), args(quip_string, (size_t)*n_quip_string);
     if (g_lammps_pot) gap_potential_finalise(g_lammps_pot);
     g_lammps_pot = nullptr;
-    if (gap_potential_filename_initialise(&g_lammps_pot, args.c_str(), file.c_str(), 0) != 0) {
+    if (gap_potential_filename_initialise(&g_lammps_pot, args.c_str(), file.c_str(), lammps_device()) != 0) {
       fprintf(stderr, "SYSTEM ABORT: quip_lammps_potential_initialise: %s\n", gap_last_error());  // the reference system_aborts here
       abort();
     }

@@ -32,6 +32,9 @@ ABI = {
     "gap_potential_cutoff": (C.c_double, [C.c_void_p]),
     "gap_potential_print": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "gap_potential_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "gap_comm_get_unique_id": (C.c_int, [C.c_char_p]),
+    "gap_potential_set_comm": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "gap_potential_comm_info": (C.c_int, [C.c_void_p, c_ip, c_ip, C.c_char_p, C.c_size_t]),
     "gap_potential_calc": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "gap_potential_set_atom_mask": (C.c_int, [C.c_void_p, C.c_int, c_ip]),
     "gap_potential_get_energy_per_coordinate": (C.c_int, [C.c_void_p, c_dp]),
@@ -182,13 +185,31 @@ class Potential:
     def set_partition(self, rank, n_ranks):
         _check(load_library().gap_potential_set_partition(self._h, int(rank), int(n_ranks)))
 
-    def calc(self, atoms, energy=True, force=False, virial=False, local_energy=False, local_virial=False, args_str=""):
+    def set_comm(self, comm_id, rank, n_ranks):
+        """Collective: join the communicator ``comm_id`` (128 bytes from :func:`comm_unique_id` on one rank, distributed by the
+        host); from then on every calc returns the totals over the ranks (``IPModel_GAP.f95:538-556`` inside the library)."""
+        _check(load_library().gap_potential_set_comm(self._h, comm_id, int(rank), int(n_ranks)))
+
+    def comm_info(self):
+        r, n = C.c_int(0), C.c_int(1)
+        buf = C.create_string_buffer(16)
+        load_library().gap_potential_comm_info(self._h, C.byref(r), C.byref(n), buf, len(buf))
+        return {"rank": r.value, "n_ranks": n.value, "transport": buf.value.decode()}
+
+    def calc(self, atoms, energy=True, force=False, virial=False, local_energy=False, local_virial=False, args_str="", out_force=None):
         """``calc(pot, at, energy, force, virial, local_energy, local_virial, args_str)`` (Potential.f95:803).
-        Returns a dict with the requested quantities; ``force`` is (N,3), ``virial`` (3,3), ``local_virial`` (N,9)."""
+        Returns a dict with the requested quantities; ``force`` is (N,3), ``virial`` (3,3), ``local_virial`` (N,9).
+        ``out_force``: a caller-owned C-contiguous float64 (N,3) array the forces are written into (the Fortran caller owns its
+        output arrays too); page-locked arrays -- inputs and this one -- are transferred without a staging copy."""
         pos, Z, lat, pbc = _geometry(atoms)
         N = len(Z)
         e = np.zeros(1)
-        f = np.zeros((N, 3)) if force else None
+        if force and out_force is not None:
+            if out_force.shape != (N, 3) or out_force.dtype != np.float64 or not out_force.flags.c_contiguous:
+                raise RuntimeError("calc: out_force must be a C-contiguous float64 array of shape (N, 3)")
+            f = out_force
+        else:
+            f = np.zeros((N, 3)) if force else None
         v = np.zeros((3, 3), order="F") if virial else None
         le = np.zeros(N) if local_energy else None
         lv = np.zeros((N, 9)) if local_virial else None
@@ -394,7 +415,8 @@ def unpack_results(packed, N):
 
 
 def reduce_packed(t, group=None):
-    """Sum of the per-rank partial packed buffers (torch tensor, in place): NCCL for CUDA tensors, gloo for CPU ones."""
+    """Sum of per-rank partial packed buffers held in a torch tensor (in place): the host-side stand-in the CPU (gloo) test of the
+    partition logic uses.  The product path reduces inside libgapb200.so (``gap_potential_set_comm``)."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -402,63 +424,71 @@ def reduce_packed(t, group=None):
     return t
 
 
+def comm_unique_id():
+    """``gap_comm_get_unique_id``: 128 bytes that identify a new communicator; call on ONE rank and distribute."""
+    buf = C.create_string_buffer(128)
+    _check(load_library().gap_comm_get_unique_id(buf))
+    return buf.raw
+
+
+def broadcast_comm_id(group=None, src=0):
+    """The host's share of the communicator set-up: rank ``src`` creates the id, ``torch.distributed`` (NCCL or gloo; a Fortran host
+    would use MPI_Bcast) hands it to everybody."""
+    import torch.distributed as dist
+
+    box = [comm_unique_id() if dist.get_rank(group) == src else None]
+    dist.broadcast_object_list(box, src=src, group=group)
+    return box[0]
+
+
+def pinned_copy(a):
+    """A page-locked copy of a numpy array (what a host that wants zero staging copies hands to ``calc``)."""
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(a)).clone().pin_memory()
+    return t.numpy()
+
+
 class ShardedPotential:
     """One process per GPU: the reference's MPI-parallel ``calc`` (atom mask + ``sum_in_place``,
-    src/GAP/descriptors.f95:1036-1051, src/Potentials/IPModel_GAP.f95:538-556) over ``torch.distributed``.
+    src/GAP/descriptors.f95:1036-1051, src/Potentials/IPModel_GAP.f95:538-556).
 
-    Every rank holds the whole configuration (positions replicated) and evaluates the centres of its contiguous
-    block; the ONLY collective is one all-reduce of the packed ``[E | virial(9) | F(3,N)]`` device buffer (NCCL on
-    GPUs; the reference issues five MPI_Allreduce calls).  torch is plumbing here (device memory, streams, the
-    process group); all arithmetic is in libgapb200.so.
+    Every rank holds the whole configuration (positions replicated) and evaluates the centres of its contiguous block; the
+    ONLY exchange is the sum of the packed ``[E | virial(9) | F(3,N)]`` partials, and it happens INSIDE libgapb200.so on the
+    evaluation's stream (``gap_potential_set_comm``: ncclAllReduce, or the one-shot NVLink peer-memory kernel for latency-bound
+    sizes).  torch.distributed is used once, to hand the 128-byte communicator id to every rank; torch is plumbing here
+    (device memory, streams, the process group), all arithmetic and the collective are in the library.
     """
 
-    def __init__(self, args_str="", param_filename=None, param_str=None, device=0, group=None, rank=None, world_size=None):
+    def __init__(self, args_str="", param_filename=None, param_str=None, device=0, group=None, rank=None, world_size=None, comm_id=None):
         import torch
 
         self.torch = torch
         self.group = group
-        if rank is None or world_size is None:
-            import torch.distributed as dist
+        import torch.distributed as dist
 
-            if dist.is_available() and dist.is_initialized():
-                rank, world_size = dist.get_rank(group), dist.get_world_size(group)
-            else:
-                rank, world_size = 0, 1
+        live = dist.is_available() and dist.is_initialized()
+        if rank is None or world_size is None:
+            rank, world_size = (dist.get_rank(group), dist.get_world_size(group)) if live else (0, 1)
         self.rank, self.world_size = int(rank), int(world_size)
         self.pot = Potential(args_str, param_filename=param_filename, param_str=param_str, device=device)
-        self.pot.set_partition(self.rank, self.world_size)
         self.device = torch.device("cuda", device)
+        if self.world_size > 1 and (comm_id is not None or (live and dist.get_world_size(group) == self.world_size)):
+            with torch.cuda.device(self.device):
+                self.pot.set_comm(comm_id if comm_id is not None else broadcast_comm_id(group), self.rank, self.world_size)
+            self.reduces = True
+        else:
+            # no process group: this handle evaluates ONE block of a partitioned run and returns partial sums (profiling aid, tests)
+            self.pot.set_partition(self.rank, self.world_size)
+            self.reduces = False
         self.stream = torch.cuda.Stream(self.device)  # a real stream: the C ABI reads stream 0 / NULL as "the handle's own"
         self._h_e = torch.zeros(1, dtype=torch.float64, pin_memory=True)
-        self._N = -1
-
-    def _ensure(self, N):
-        torch = self.torch
-        if N == self._N:
-            return
-        self._N = N
-        # positions and atomic numbers travel in ONE pinned staging buffer / one H2D copy: [pos (3N f64) | Z (N i32)]
-        nb = 24 * N + 4 * N
-        self.h_in = torch.empty((nb,), dtype=torch.uint8, pin_memory=True)
-        self.d_in = torch.empty((nb,), dtype=torch.uint8, device=self.device)
-        self.h_pos = self.h_in[:24 * N].view(torch.float64).view(N, 3)
-        self.h_Z = self.h_in[24 * N:].view(torch.int32)
-        self.d_pos = self.d_in[:24 * N].view(torch.float64).view(N, 3)
-        self.d_Z = self.d_in[24 * N:].view(torch.int32)
-        self.h_pos_np, self.h_Z_np = self.h_pos.numpy(), self.h_Z.numpy()
-        self.h_packed = torch.empty((10 + 3 * N,), dtype=torch.float64, pin_memory=True)
-        self.d_packed = torch.empty((10 + 3 * N,), dtype=torch.float64, device=self.device)
-
-    def reduce_packed(self, d_packed):
-        """The path's one collective: sum of the per-rank partial [E | virial | F] buffers."""
-        if self.world_size > 1:
-            reduce_packed(d_packed, self.group)
 
     def run(self, atoms, velocities, dt=1.0, n_steps=10, masses=None, args_str=""):
         """Sharded ``DynamicalSystem_run`` (Potential.f95:2304; BASELINE config C): NVE velocity Verlet with the neighbour list
         rebuilt on the device every step.  Every rank keeps the whole state resident on its GPU and evaluates its block of
-        centres; the library calls back after each evaluation to enqueue the all-reduce of ``[E | virial | F]``, then all ranks
-        integrate all atoms with the same forces.  Updates ``atoms.positions``; returns (velocities, epot, ekin)."""
+        centres; the library sums ``[E | virial | F]`` over the ranks after each evaluation, then all ranks integrate all atoms
+        with the same forces.  Updates ``atoms.positions``; returns (velocities, epot, ekin)."""
         torch = self.torch
         pos, Z, lat, pbc = _geometry(atoms)
         N = len(Z)
@@ -470,23 +500,10 @@ class ShardedPotential:
         d_m = torch.tensor(m, dtype=torch.float64, device=dev)
         d_packed = torch.zeros(10 + 3 * N, dtype=torch.float64, device=dev)
         ep, ek = np.zeros(n_steps + 1), np.zeros(n_steps + 1)
-        errors = []
-
-        def _reduce(_ctx, _stream):  # called from inside gap_md_run_device on this thread; enqueues on self.stream
-            try:
-                with torch.cuda.stream(self.stream):
-                    self.reduce_packed(d_packed)
-            except Exception as exc:  # an exception cannot cross the C frame
-                errors.append(exc)
-
-        cb = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)(_reduce)
         torch.cuda.current_stream(dev).synchronize()
         _check(load_library().gap_md_run_device(self.pot._h, N, d_pos.data_ptr(), d_vel.data_ptr(), d_Z.data_ptr(), d_m.data_ptr(), _dp(lat),
                                                 _ip(pbc), float(dt), int(n_steps), (self.pot.calc_args + " " + args_str).strip().encode(),
-                                                d_packed.data_ptr(), C.cast(cb, C.c_void_p) if self.world_size > 1 else None, None,
-                                                _dp(ep), _dp(ek), self.stream.cuda_stream))
-        if errors:
-            raise errors[0]
+                                                d_packed.data_ptr(), None, None, _dp(ep), _dp(ek), self.stream.cuda_stream))
         atoms.positions[...] = d_pos.cpu().numpy()
         return d_vel.cpu().numpy(), ep, ek
 
@@ -507,14 +524,13 @@ class ShardedPotential:
                 break
 
     def calc_resident_enqueue(self, N, d_pos, d_Z, lattice9, pbc3, d_packed, want_grad=True, read_energy=True):
-        """First half of :meth:`calc_resident`: enqueue the evaluation, the collective and the read-back of the energy word
-        on torch's current (non-default) stream and return without waiting."""
+        """First half of :meth:`calc_resident`: enqueue the evaluation, the reduction over ranks (inside the library) and the
+        read-back of the energy word on torch's current (non-default) stream and return without waiting."""
         cur = self.torch.cuda.current_stream(self.device)
         if cur.cuda_stream == 0:
             raise RuntimeError("calc_resident_enqueue needs a real current stream (torch.cuda.set_stream(sp.stream))")
         self.pot.calc_device_enqueue(N, d_pos.data_ptr(), d_Z.data_ptr(), lattice9, pbc3, d_packed.data_ptr(), want_grad=want_grad,
                                      stream_ptr=cur.cuda_stream)
-        self.reduce_packed(d_packed)
         # a rank whose list overflowed has poisoned its energy with NaN (k_finalize): after the reduction every rank sees it, so
         # all ranks repeat together without an extra collective
         if read_energy:
@@ -529,24 +545,8 @@ class ShardedPotential:
         e = float((self._h_e if h_energy is None else h_energy)[0])
         return bool(ok and e == e)
 
-    def calc(self, atoms, force=True, virial=True):
-        """Host in, host out: H2D of (pos, Z) from pinned memory, evaluation of this rank's block, all-reduce, D2H."""
-        torch = self.torch
-        if self.world_size == 1:
-            # one rank: the plain host-pointer entry point of the C ABI (gap_potential_calc), exactly what a Fortran host calls
-            return self.pot.calc(atoms, force=force, virial=virial)
-        pos, Z, lat, pbc = _geometry(atoms)
-        N = len(Z)
-        self._ensure(N)
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            self.h_pos_np[...] = pos
-            self.h_Z_np[...] = Z
-            self.d_in.copy_(self.h_in, non_blocking=True)
-            for _ in range(2):
-                # evaluation, collective and the read-back of the results are all enqueued before the ONE synchronisation of the call
-                # (the energy word of h_packed doubles as the overflow signal)
-                self.calc_resident_enqueue(N, self.d_pos, self.d_Z, lat, pbc, self.d_packed, want_grad=force or virial, read_energy=False)
-                self.h_packed.copy_(self.d_packed, non_blocking=True)
-                if self.calc_resident_finish(self.h_packed):
-                    break
-        return unpack_results(self.h_packed.numpy(), N)
+    def calc(self, atoms, force=True, virial=True, out_force=None):
+        """Host in, host out, on every rank: the plain host-pointer entry point of the C ABI (``gap_potential_calc``) -- exactly what a
+        Fortran host calls.  H2D of (pos, Z), evaluation of this rank's block, reduction over the ranks, D2H of what THIS rank
+        asked for (a rank that passes ``force=False`` skips the force read-back)."""
+        return self.pot.calc(atoms, force=force, virial=virial, out_force=out_force)

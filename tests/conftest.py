@@ -15,9 +15,13 @@ def pytest_configure(config):
 
 
 def pytest_sessionstart(session):
-    """Build the CUDA library and the oracle if the tree is fresh (nvcc cross-compiles without a GPU); an existing build is kept."""
+    """Build the CUDA library and the oracle (nvcc cross-compiles without a GPU).  make is incremental, so an up-to-date tree costs
+    nothing and a stale binary can never pass for the edited sources.  Without a compiler (a box that only received the built
+    files) the existing build is used."""
+    import shutil
+
     lib = os.path.join(ROOT, "quip_b200", "libgapb200.so")
-    if not os.path.exists(lib):
+    if shutil.which("make") and (os.path.exists("/usr/local/cuda/bin/nvcc") or not os.path.exists(lib)):
         import __graft_entry__
 
         __graft_entry__.build()

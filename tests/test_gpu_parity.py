@@ -298,13 +298,17 @@ def test_device_resident_entry_point(si_model, si_frames):
 # ----------------------------------------------------------------------------------------------------
 # full-size config A: size-independent properties
 # ----------------------------------------------------------------------------------------------------
-def test_config_A_full_size_properties(tmp_path):
+def test_config_A_full_size_vs_oracle(tmp_path):
+    """BASELINE configs[1] at FULL size (4,096 atoms, 2,000 sparse points): neighbour list bit-exact, E/F/virial/local_e/local_virial
+    against the oracle's whole evaluation (0.3 s of CPU), then the size-independent properties."""
     boot = syn.bootstrap_xml(str(tmp_path / "boot.xml"), [(syn.SOAP_A, syn.soap_dimension(8, 8))])
     bp = Potential("", param_filename=boot)
     atoms, xml = syn.build_config_A(str(tmp_path), lambda desc, at: bp.descriptor_calc(at, 0)[0], n_cells=8, M=2000, seed=1)
     assert len(atoms) == 4096
-    pot = Potential("", param_filename=xml)
-    r = pot.calc(atoms, force=True, virial=True, local_energy=True, local_virial=True)
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    assert_same_list(pot, atoms, pot.cutoff())
+    r, o = check_efv(pot, om, atoms)
+    assert np.abs(r["force"]).max() > 1e-2
     assert abs(r["local_energy"].sum() - r["energy"]) < 1e-7
     assert np.abs(r["force"].sum(axis=0)).max() < 1e-8          # translation invariance
     assert np.abs(r["virial"] - r["virial"].T).max() < 1e-7     # rotation invariance
@@ -327,14 +331,49 @@ def test_config_A_full_size_properties(tmp_path):
         ep = pot.calc(Atoms(atoms.numbers, atoms.positions @ F.T, atoms.cell @ F.T, True))["energy"]
         em = pot.calc(Atoms(atoms.numbers, atoms.positions @ Fm.T, atoms.cell @ Fm.T, True))["energy"]
         assert abs((ep - em) / (2 * eps) + r["virial"][aa, bb]) < 1e-5
-    # oracle on a bounded sample of centres of the SAME configuration: partial sums must agree
-    om = orc.Model(xml)
-    first, last = 1000, 1064
-    o = om.calc(atoms, first=first, last=last, local_energy=True)
-    p = Potential("", param_filename=xml)
-    # the library partitions in equal blocks: 4096/64 = 64 atoms per block -> block index 1000/64 is not integral;
-    # compare local energies of the sample instead (they only depend on the centre)
-    assert np.abs(r["local_energy"][first:last] - o["local_energy"][first:last]).max() < 1e-8
+
+
+def test_si_fit_reproduces_dft_energies(si_model, si_frames):
+    # end-to-end pin of a SOAP dot-product GAP on the GPU: the fitted model reproduces the frames' dft_energy to fit accuracy
+    # (tests/test_gapfit.py:82-100; see tests/test_oracle_golden.py::test_si_fit_reproduces_dft_energies)
+    pot, om, _ = si_model
+    n_checked = 0
+    for a in si_frames:
+        if "dft_energy" not in a.info:
+            continue
+        err = abs(pot.calc(a)["energy"] - a.info["dft_energy"]) / len(a)
+        assert err < (0.01 if len(a) <= 2 else 2e-3), (a.info.get("config_type"), len(a), err)
+        n_checked += 1
+    assert n_checked == 16
+
+
+def test_wrapper_simple_and_print(si_model, si_frames, golden):
+    # quip_wrapper_simple_ (quip_unified_wrapper.f95:311-332): one-shot F77-style call, pbc T T T; IPModel_GAP_Print (IPModel_GAP.f95:952)
+    import ctypes as C
+
+    from quip_b200 import load_library
+
+    pot, om, xml = si_model
+    a = si_frames[8]
+    ref = pot.calc(a, force=True, virial=True)
+    lib = load_library()
+    N = len(a)
+    pos = np.ascontiguousarray(a.positions, dtype=np.float64)
+    Z = np.ascontiguousarray(a.numbers, dtype=np.int32)
+    lat = np.ascontiguousarray(a.cell.reshape(9))
+    e, f, v = C.c_double(0.0), np.zeros((N, 3)), np.zeros(9)
+    dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+    rc = lib.gap_b200_wrapper_simple(xml.encode(), C.byref(C.c_int(N)), dp(lat), Z.ctypes.data_as(C.POINTER(C.c_int)), dp(pos), C.byref(e), dp(f), dp(v))
+    assert rc == 0, lib.gap_last_error()
+    assert abs(e.value - ref["energy"]) < 1e-9 * abs(ref["energy"])
+    assert np.abs(f - ref["force"]).max() < 1e-10
+    assert np.abs(v.reshape(3, 3, order="F") - ref["virial"]).max() < 1e-9
+    assert lib.gap_b200_wrapper_simple(b"/nonexistent.xml", C.byref(C.c_int(N)), dp(lat), Z.ctypes.data_as(C.POINTER(C.c_int)), dp(pos), C.byref(e), dp(f), dp(v)) != 0
+    txt = pot.print_()
+    assert "IPModel_GAP : label = GAP_Si_two_descriptors" in txt and "cutoff = 6" in txt
+    assert txt.count("coordinate ") == 2 and "n_sparseX=100" in txt and "zeta=4" in txt
+    small = C.create_string_buffer(16)
+    assert lib.gap_potential_print(pot._h, small, len(small)) == 0 and len(small.value) == 15  # truncated, NUL terminated
 
 
 def test_error_reporting(golden):

