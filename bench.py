@@ -192,17 +192,18 @@ def host_threads():
 
 
 def cpu_sample(om, atoms, n_centres):
-    """One oracle pass over centres [0, n_centres): returns (wall seconds, the three phase times calc_connect / descriptor / gp_predict+scatter)."""
+    """One oracle pass over centres [0, n_centres): returns (wall seconds of the pass, wall seconds of its serial calc_connect).  (The
+    oracle's descriptor / gp_predict timers are summed over the OpenMP threads; the per-centre share is taken from the wall clock.)"""
     t = time.perf_counter()
     o = om.calc(atoms, force=True, virial=True, first=0, last=n_centres, nthreads=host_threads())
-    return time.perf_counter() - t, np.array(o["timings"], dtype=np.float64)
+    return time.perf_counter() - t, float(o["timings"][0])
 
 
-def whole_step_seconds(N, n_centres, phases):
+def whole_step_seconds(N, n_centres, wall, t_connect):
     """Seconds of ONE whole evaluation of N atoms implied by a pass over n_centres of its centres: the serial neighbour list of all
     atoms is paid once (calc_connect, Connection.f95:1060), the per-centre phases (soap_calc, descriptors.f95:7757; gp_predict +
     scatter, IPModel_GAP.f95:428) scale with the number of centres."""
-    return float(phases[0] + (phases[1] + phases[2]) * (N / float(n_centres)))
+    return float(t_connect + (wall - t_connect) * (N / float(n_centres)))
 
 
 def cpu_baseline_leg(xml, atoms, budget_s=12.0):
@@ -218,9 +219,9 @@ def cpu_baseline_leg(xml, atoms, budget_s=12.0):
     passes = int(max(1, min(64, round(rate * budget_s / per_pass))))
     tot, secs = 0.0, 0.0
     for _ in range(passes):
-        t, ph = cpu_sample(om, atoms, per_pass)
+        t, tc = cpu_sample(om, atoms, per_pass)
         tot += t
-        secs += whole_step_seconds(N, per_pass, ph)
+        secs += whole_step_seconds(N, per_pass, t, tc)
     return {"value": N * passes / secs, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d pass(es) over %d of %d centres of the same configuration, %.1f s in total; a whole step = serial neighbour list of all atoms "
                       "(as calc_connect) + per-centre phases scaled to all centres; OpenMP over atoms with %d threads; oracle/gap_oracle.c "
@@ -248,7 +249,7 @@ def run_reference(args):
         per_step = int(max(64, min(N, rate * 120.0 / max(1, args.steps + args.warmup))))
         for _ in range(args.warmup):
             cpu_sample(om, atoms, per_step)
-        secs = [whole_step_seconds(N, per_step, cpu_sample(om, atoms, per_step)[1]) for _ in range(args.steps)]
+        secs = [whole_step_seconds(N, per_step, *cpu_sample(om, atoms, per_step)) for _ in range(args.steps)]
     tot = float(np.sum(secs))
     value = N * args.steps / tot
     sample = ("%d of %d centres per step; step time = calc_connect of all atoms (serial) + (soap_calc + gp_predict/scatter of the sample) x %d/%d; "
