@@ -52,6 +52,7 @@ def lib():
         L.orc_soap_new.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                    C.c_double, C.c_int, C.c_int, c_ip, C.c_int, c_ip, C.c_int, C.c_int, C.c_double,
                                    C.c_double, C.c_double]
+        L.orc_soap_set_general.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, C.c_int, c_dp, C.c_int, c_dp, C.c_int, c_ip, c_ip, c_dp]
         L.orc_soap_free.argtypes = [C.c_void_p]
         L.orc_soap_dim.argtypes = [C.c_void_p]
         L.orc_soap_get_basis.argtypes = [C.c_void_p, c_dp, c_dp, c_dp]
@@ -175,16 +176,225 @@ def soap_params(desc_str, calc_xml_version=None):
     if not has_cras and p["n_species"] == 1:
         p["central_reference_all_species"] = True
     p["Z"] = _ilist(a.get("Z", "0")) if p["n_Z"] > 1 else [int(str(a.get("Z", "0")).split()[0])]
-    for key in ("average", "diagonal_radial", "Z_mix", "R_mix", "sym_mix"):
-        if _b(a.get(key, "F")):
-            raise NotImplementedError("soap option %s is outside the oracle's scope" % key)
-    if a.get("radial_basis", "EQUISPACED_GAUSS") not in ("", "EQUISPACED_GAUSS"):
-        raise NotImplementedError("radial_basis")
-    if int(a.get("nu_R", 2)) != 2 or int(a.get("nu_S", 2)) != 2 or not _b(a.get("coupling", "T")):
-        raise NotImplementedError("nu_R/nu_S/coupling")
+    if _b(a.get("average", "F")):
+        raise NotImplementedError("soap average=T (one global descriptor per configuration) is outside the oracle's scope")
+    # ---- compression modes and radial bases (descriptors.f95:2529-2537): handled by the general path ----
+    p["diagonal_radial"] = _b(a.get("diagonal_radial", "F"))
+    p["Z_mix"], p["R_mix"], p["sym_mix"] = _b(a.get("Z_mix", "F")), _b(a.get("R_mix", "F")), _b(a.get("sym_mix", "F"))
+    p["coupling"] = _b(a.get("coupling", "T"))
+    p["nu_R"], p["nu_S"] = int(a.get("nu_R", 2)), int(a.get("nu_S", 2))
+    p["K"], p["mix_shift"] = int(a.get("K", 0)), int(a.get("mix_shift", 0))
+    p["Z_map"] = a.get("Z_map", "").strip()
+    p["radial_basis"] = a.get("radial_basis", "") or "EQUISPACED_GAUSS"
+    if p["radial_basis"] not in ("EQUISPACED_GAUSS", "GTO", "POLY"):
+        raise ValueError("soap_initialise: radial_basis not recognised: EQUISPACED_GAUSS, POLY or GTO")
+    p["general"] = (p["diagonal_radial"] or p["Z_mix"] or p["R_mix"] or p["sym_mix"] or not p["coupling"] or p["nu_R"] != 2 or p["nu_S"] != 2
+                    or bool(p["Z_map"]) or p["radial_basis"] != "EQUISPACED_GAUSS")
     cv = 1423143769 if calc_xml_version is None else calc_xml_version
     p["do_two_l_plus_one"] = cv >= 1423143769
     return p
+
+
+# ---- QUIP's own random numbers (src/libAtoms/System.f95:2458-2489, 2659-2701): the channel-mixing weights are drawn from them ----
+class QuipRNG:
+    A, M, Q, R = 16807, 2147483647, 127773, 2836  # Park-Miller minimal standard (System.f95:142-145)
+
+    def __init__(self, seed):  # system_reseed_rng -> system_set_random_seeds: idum = seed, then 100 draws are discarded (:2474, :2484-2488)
+        self.idum = int(seed)
+        for _ in range(100):
+            self.ran()
+
+    def ran(self):  # :2659-2675
+        k = self.idum // self.Q
+        self.idum = self.A * (self.idum - k * self.Q) - self.R * k
+        if self.idum < 0:
+            self.idum += self.M
+        return self.idum
+
+    def uniform(self):  # :2678-2689 (RAN_MAX = huge(1))
+        while True:
+            u = self.ran() / 2147483647.0
+            if u <= 1.0:
+                return u
+
+    def normal(self):  # :2692-2701
+        while True:
+            v1, v2 = 2.0 * self.uniform() - 1.0, 2.0 * self.uniform() - 1.0
+            r = v1 * v1 + v2 * v2
+            if r <= 1.0:
+                return v1 * np.sqrt(-2.0 * np.log(r) / r)
+
+
+def soap_mixing(p):
+    """form_W (descriptors.f95:7618-7670) -> W(1), W(2), sym_desc, and the list of power-spectrum elements (ia, jb, factor) the
+    unpacking loops produce (:8402-8416 for coupling=T, form_coupling_inds :7274-7350 for coupling=F)."""
+    n, ns, K = p["n_max"], p["n_species"], p["K"]
+    K1 = n * ns
+    mixing = p["R_mix"] or p["Z_mix"] or p["sym_mix"]
+    if (p["nu_R"] != 2 or p["nu_S"] != 2) and (mixing or p["diagonal_radial"] or p["Z_map"]):
+        raise ValueError("(nu_R, nu_S) = (2,2) required to use channel mixing / diagonal radial / Zmap")
+    if mixing and p["Z_map"]:
+        raise ValueError("cant' using mixing and Zmap at the same time")
+    if mixing:  # form_mix_W :7430-7533
+        sym_desc = p["sym_mix"]
+        W = []
+        for j in (1, 2):
+            if sym_desc and j == 2:
+                W.append(W[0].copy())
+                continue
+            if p["R_mix"] and p["Z_mix"]:
+                w = np.zeros((K1, K))
+                for i_s in range(ns):
+                    rng = QuipRNG(p["species_Z"][i_s] + p["mix_shift"] + j * 200)
+                    for r in range(i_s * n, (i_s + 1) * n):
+                        for c in range(K):
+                            w[r, c] = rng.normal()
+            elif p["Z_mix"]:
+                w = np.zeros((K1, K * n))
+                R = np.zeros((ns, K))
+                for i_s in range(ns):
+                    rng = QuipRNG(p["species_Z"][i_s] + p["mix_shift"] + j * 200)
+                    for c in range(K):
+                        R[i_s, c] = rng.normal()
+                for i_s in range(ns):
+                    for a in range(n):
+                        for k in range(K):
+                            w[i_s * n + a, k * n + a] = R[i_s, k]
+            elif p["R_mix"]:
+                w = np.zeros((K1, K * ns))
+                rng = QuipRNG(n + p["mix_shift"] + j * 200)
+                R = np.zeros((n, K))
+                for r in range(n):
+                    for c in range(K):
+                        R[r, c] = rng.normal()
+                for i_s in range(ns):
+                    for a in range(n):
+                        for k in range(K):
+                            w[i_s * n + a, i_s * K + k] = R[a, k]
+            else:
+                raise ValueError("form_mix_W: not mixing anything")
+            W.append(w)
+    elif p["Z_map"]:  # form_Zmap_W :7536-7616
+        zs = p["Z_map"]
+        n_groups, dens = [1, 1], 0
+        for ch in zs:
+            if ch == ",":
+                n_groups[dens] += 1
+            if ch == ":":
+                dens += 1
+        two = dens == 1
+        sym_desc = not two
+        W = [np.zeros((K1, n * n_groups[0])), np.zeros((K1, n * (n_groups[1] if two else n_groups[0])))]
+        i_group, i_density, tok = 0, 0, ""
+        for ch in zs + " ":
+            if ch.isdigit():
+                tok += ch
+                continue
+            if tok:
+                i_sp = p["species_Z"].index(int(tok))
+                for a in range(n):
+                    W[i_density][i_sp * n + a, i_group * n + a] = 1.0
+                tok = ""
+            if ch == ",":
+                i_group += 1
+            if ch == ":":
+                i_density += 1
+                i_group = 0
+        if sym_desc:
+            W[1] = W[0].copy()
+    else:  # form_nu_W :7352-7424
+        sym_desc = not (p["nu_R"] == 1 or p["nu_S"] == 1)
+        nu_R, nu_S = p["nu_R"], p["nu_S"]
+        if not (0 <= nu_R <= 2 and 0 <= nu_S <= 2):
+            raise ValueError("nu_R / nu_S outside allowed range of 0-2")
+        W = []
+        for _ in (1, 2):
+            dn = ds = 0
+            n2_max = s2_max = 1
+            if nu_R > 0:
+                nu_R -= 1
+                dn, n2_max = 1, n
+            if nu_S > 0:
+                nu_S -= 1
+                ds, s2_max = 1, ns
+            w = np.zeros((K1, n2_max * s2_max))
+            for s_ in range(1, ns + 1):
+                for a in range(1, n + 1):
+                    ic = 0
+                    for s2 in range(1, s2_max + 1):
+                        for n2 in range(1, n2_max + 1):
+                            if ds * s_ == ds * s2 and dn * a == dn * n2:
+                                w[(s_ - 1) * n + a - 1, ic] = 1.0
+                            ic += 1
+            W.append(w)
+    Ka, Kb = W[0].shape[1], W[1].shape[1]
+    original = p["coupling"] and p["nu_R"] == 2 and p["nu_S"] == 2 and not mixing and not p["Z_map"]
+    pairs = []
+    if p["coupling"]:
+        if p["diagonal_radial"] and not original:
+            raise ValueError("soap_dimensions: can't combine diagonal radial with any other compression strategies")
+        for ia in range(Ka):
+            for jb in range(ia + 1 if sym_desc else Kb):
+                if p["diagonal_radial"] and (ia % n) != (jb % n):  # rs_index(1, .) = radial index of the channel
+                    continue
+                pairs.append((ia, jb, np.sqrt(2.0) if (sym_desc and ia != jb) else 1.0))
+    else:  # form_coupling_inds; sym_facs is declared `real` (single precision, :7283): its SQRT_TWO is rounded to float32
+        sqrt2_f32 = float(np.float32(np.sqrt(2.0)))
+        if Ka != Kb:
+            raise ValueError("require K1=K2 to use elementwise coupling")
+        if p["Z_mix"] and not p["R_mix"]:
+            for k in range(K):
+                for a in range(n):
+                    for b in range(a + 1 if p["sym_mix"] else n):
+                        pairs.append((k * n + a, k * n + b, sqrt2_f32 if (a != b and p["sym_mix"]) else 1.0))
+        elif p["R_mix"] and not p["Z_mix"]:
+            for i_s in range(ns):
+                for j_s in range(i_s + 1 if p["sym_mix"] else ns):
+                    for k in range(K):
+                        pairs.append((i_s * K + k, j_s * K + k, sqrt2_f32 if (i_s != j_s and p["sym_mix"]) else 1.0))
+        else:
+            pairs = [(i, i, 1.0) for i in range(Ka)]
+    return W[0], W[1], sym_desc, pairs
+
+
+def soap_radial(p):
+    """Radial points and the linear map radial_fun(l, :) -> radial_coefficient(l, :), per l, plus the central atom's coefficients.
+    EQUISPACED_GAUSS: r_basis and transform_basis (descriptors.f95:2603-2642).  GTO / POLY (:2643-2770): a grid of 3 n_max points, the
+    functions of the basis tabulated on it (B), orthonormalised with the Cholesky factor of their overlap, and the coefficients
+    found by the least-squares (QR) solve  B (L^T)^-1 c = radial_fun  (:8264-8278), i.e. c = pinv(B L^-T) radial_fun."""
+    from scipy.special import gamma, gammaincc
+
+    n, L = p["n_max"], p["l_max"]
+    alpha = 0.5 / p["atom_sigma"] ** 2
+    cutoff_basis = p["cutoff"] + p["atom_sigma"] * np.sqrt(2.0 * p["basis_error_exponent"] * np.log(10.0))
+    if p["radial_basis"] == "EQUISPACED_GAUSS":
+        r, t, ch = soap_basis(p)
+        return r, np.repeat(t[None, :, :], L + 1, axis=0), ch[0, :].copy()
+    ng = 3 * n
+    r = np.arange(ng) * (cutoff_basis / ng)
+    P = np.zeros((L + 1, ng, n))
+    l_ub = 0 if p["radial_basis"] == "POLY" else L
+    for l in range(l_ub + 1):
+        if p["radial_basis"] == "POLY":
+            idx = np.arange(1, n + 1, dtype=np.float64)
+            N_a = np.sqrt(cutoff_basis ** (2 * idx + 7) / ((idx + 3) * (2 * idx + 5) * (2 * idx + 7)))
+            i, j = np.meshgrid(idx, idx, indexing="ij")
+            S = 2 * cutoff_basis ** (i + j + 7) / ((5 + i + j) * (6 + i + j) * (7 + i + j)) / np.outer(N_a, N_a)
+            B = (cutoff_basis - r[:, None]) ** (idx[None, :] + 2) / N_a[None, :]
+        else:
+            Rg = (cutoff_basis / n) * np.arange(1, n + 1)
+            a_ln = -Rg ** (-2.0) * (np.log(0.001) - l * np.log(Rg))
+            ag = a_ln[:, None] + a_ln[None, :]
+            u, t = ag * cutoff_basis ** 2, l + 1.5
+            S = 0.5 * cutoff_basis ** (2 * t) * u ** (-t) * (gamma(t) - gammaincc(t, u) * gamma(t))
+            B = r[:, None] ** l * np.exp(-a_ln[None, :] * r[:, None] ** 2)
+        Lc = np.linalg.cholesky(S)
+        A = B @ np.linalg.inv(Lc.T)
+        P[l] = np.linalg.pinv(A).T
+    for l in range(l_ub + 1, L + 1):
+        P[l] = P[0]
+    c0 = np.exp(-alpha * r ** 2) @ P[0]
+    return r, P, c0
 
 
 def new_soap(p):
@@ -196,11 +406,19 @@ def new_soap(p):
                            p["cutoff_dexp"], p["cutoff_scale"], p["cutoff_rate"], p["basis_error_exponent"])
     if not h:
         raise RuntimeError("orc_soap_new failed")
+    if p.get("general"):
+        W1, W2, _, pairs = soap_mixing(p)
+        r, P, c0 = soap_radial(p)
+        W1, W2, P, r, c0 = (np.ascontiguousarray(x, dtype=np.float64) for x in (W1, W2, P, r, c0))
+        ia = np.array([q[0] for q in pairs], dtype=np.int32)
+        jb = np.array([q[1] for q in pairs], dtype=np.int32)
+        fac = np.array([q[2] for q in pairs], dtype=np.float64)
+        lib().orc_soap_set_general(h, len(r), _dp(r), _dp(P), _dp(c0), W1.shape[1], _dp(W1), W2.shape[1], _dp(W2), len(pairs), _ip(ia), _ip(jb), _dp(fac))
     return h
 
 
 def soap_basis(p):
-    h = new_soap(p)
+    h = new_soap({**p, "general": False})
     n = p["n_max"]
     r, t, ch = np.zeros(n), np.zeros((n, n), order="F"), np.zeros((n, n), order="F")
     lib().orc_soap_get_basis(h, _dp(r), _dp(t), _dp(ch))

@@ -152,3 +152,34 @@ def test_si_fit_reproduces_dft_energies(golden, tmp_path):
         assert err < (0.01 if len(a) <= 2 else 2e-3), (a.info.get("config_type"), len(a), err)
         n_checked += 1
     assert n_checked == 16
+
+
+def _soap_all_cases(golden):
+    meta = json.load(open(os.path.join(golden, "soap_reference_all.json")))
+    z = np.load(os.path.join(golden, "soap_reference_all.npz"))
+    S = json.load(open(os.path.join(golden, "soap_reference_cases.json")))["datasets"]
+    ds = {name: [Atoms(d["numbers"], np.array(d["scaled_positions"]) @ np.array(d["cell"]), d["cell"], False) for d in S[name]] for name in S}
+    return meta, z, ds
+
+
+def test_soap_reference_data_all_variants(golden):
+    """tests/test_SOAP.py:36-77 over tests/SOAP_reference_data.json: every case with average=F (66 of 122) -- Z_mix / R_mix / sym_mix with
+    QUIP's own random mixing weights, coupling=F, Z_map, nu_R / nu_S, diagonal_radial, GTO and POLY radial bases -- X, the gradient
+    index table and grad_data (np.allclose there; 1e-9 here).  average=T (one descriptor per configuration) is out of scope."""
+    meta, z, ds = _soap_all_cases(golden)
+    n = 0
+    for i, m in enumerate(meta):
+        qs = m["quippy_str"]
+        if "average=T" in qs:
+            with pytest.raises(NotImplementedError):
+                orc.soap_params(qs)
+            continue
+        outs = [orc.soap_descriptor(qs, a, grad=True) for a in ds[m["dataset_name"]]]
+        X = np.concatenate([o["data"] for o in outs])[z["perm_%d" % i]]
+        assert X.shape == z["X_%d" % i].shape, (i, qs)
+        assert np.abs(X - z["X_%d" % i]).max() < 1e-9, (i, qs)
+        gp = z["gperm_%d" % i]
+        assert np.array_equal(outs[0]["grad_index_0based"][gp], z["GI_%d" % i]), (i, qs)
+        assert np.abs(outs[0]["grad_data"][gp] - z["G_%d" % i]).max() < 1e-9, (i, qs)
+        n += 1
+    assert n == 66

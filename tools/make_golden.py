@@ -15,6 +15,7 @@ suite, cited per item.
          alphas (tests/test_gapfit.py:75-80,231-239)
   tests/SOAP_reference_data.json cases 112/114/116/119 (+ structures embedded in
       tests/test_SOAP.py:38) -> SOAP X and grad_data on the default path
+  tests/SOAP_reference_data.json, all 122 cases -> soap_reference_all.{json,npz}
   tests/test_descriptor.py:63-226 -> C2H cell gradient index table + 2 gradient blocks
 """
 import ast
@@ -62,6 +63,19 @@ def main():
         cases[str(i)] = {k: e[k] for k in ("quippy_str", "perm", "X", "grad_data", "grad_index_0based", "grad_perm",
                                            "dataset_name")}
     json.dump({"datasets": dataset_info, "cases": cases}, open(os.path.join(OUT, "soap_reference_cases.json"), "w"))
+
+    # --- SOAP_reference_data.json, ALL 122 cases (compression modes, nu_R/nu_S, Z_map, diagonal_radial, GTO / POLY bases, average):
+    #     descriptor strings as JSON, the numbers as one compressed npz (tests/test_SOAP.py:36-77 compares X and grad_data) ----------
+    arrays, meta = {}, []
+    for i, e in enumerate(ref):
+        meta.append({"quippy_str": e["quippy_str"], "dataset_name": e["dataset_name"]})
+        arrays["X_%d" % i] = np.array(e["X"], dtype=np.float64)
+        arrays["G_%d" % i] = np.array(e["grad_data"], dtype=np.float64)
+        arrays["GI_%d" % i] = np.array(e["grad_index_0based"], dtype=np.int32)
+        arrays["perm_%d" % i] = np.array(e["perm"], dtype=np.int32)
+        arrays["gperm_%d" % i] = np.array(e["grad_perm"], dtype=np.int32)
+    json.dump(meta, open(os.path.join(OUT, "soap_reference_all.json"), "w"))
+    np.savez_compressed(os.path.join(OUT, "soap_reference_all.npz"), **arrays)
 
     # --- test_descriptor.py C2H --------------------------------------------
     src = open(os.path.join(REF, "test_descriptor.py")).read()
