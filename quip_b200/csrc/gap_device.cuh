@@ -117,6 +117,28 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
                          double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st,
                          int* launches);
 
+// ---- soap_general.cu: compression modes and GTO / POLY radial bases (tables built by gap_model.cpp soap_general_setup) ----
+struct SoapGenDev {
+  int n_grid, Ka, Kb, n_pairs;
+  const double* r_grid;    // [n_grid]
+  const double* P;         // [l_max+1][n_grid][n_max]
+  const double* c0;        // [n_max]
+  const double* W1;        // [K1][Ka]
+  const double* W2;        // [K1][Kb]
+  const int* pair_ia;      // [n_pairs]
+  const int* pair_jb;
+  const double* pair_fac;
+};
+size_t soap_general_smem(const SoapDev& h, const SoapGenDev& g);
+void launch_soap_forward_general(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* centres, const int* n_centres_dev, int n_centres_ub,
+                                 const int* nbr_off, const int* nbr_end, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat,
+                                 double* x, double* xlm, double* pnorm, cudaStream_t st, int* launches);
+void launch_soap_adjoint_general(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* centres, const int* n_centres_dev, int n_centres_ub,
+                                 const int* nbr_off, const int* nbr_end, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat,
+                                 const double* x, const double* xlm, const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride,
+                                 const double* epart, int n_tiles_n, double* local_e, double e_scale, double* force, double* vir_part,
+                                 double* local_virial, cudaStream_t st, int* launches);
+
 // ---- covariance.cu -------------------------------------------------------------------------
 struct CovParams {
   double delta2;   // delta^2

@@ -168,6 +168,318 @@ static void chol_lower(std::vector<double>& a, int n, const char* what) {
   }
 }
 
+
+// ======================================================================================
+// general SOAP set-up: mixing matrices, power-spectrum element list, GTO / POLY radial maps
+// ======================================================================================
+namespace {
+// QUIP's random numbers (src/libAtoms/System.f95): Park-Miller minimal standard generator (:142-145, 2659-2675), seeded by
+// system_reseed_rng -> idum = seed, 100 draws discarded (:2474, 2484-2488); ran_uniform = ran / huge(1) (:2678-2689); ran_normal by the
+// polar method (:2692-2701).  The channel-mixing weights of form_mix_W are drawn from it, so a model fitted with QUIP needs these numbers.
+struct QuipRng {
+  long idum;
+  explicit QuipRng(long seed) : idum(seed) {
+    if (idum == 0) throw GapError("function ran(): linear-congruential random number generators fail with seed idum=0");
+    for (int i = 0; i < 100; i++) ran();
+  }
+  long ran() {
+    const long k = idum / 127773;
+    idum = 16807 * (idum - k * 127773) - 2836 * k;
+    if (idum < 0) idum += 2147483647;
+    return idum;
+  }
+  double uniform() {
+    double u = 1.1;
+    while (u > 1.0) u = (double)ran() / 2147483647.0;
+    return u;
+  }
+  double normal() {
+    double r = 2.0, v1 = 0.0, v2 = 0.0;
+    while (r > 1.0) {
+      v1 = 2.0 * uniform() - 1.0;
+      v2 = 2.0 * uniform() - 1.0;
+      r = v1 * v1 + v2 * v2;
+    }
+    return v1 * std::sqrt(-2.0 * std::log(r) / r);
+  }
+};
+
+// upper incomplete gamma function Gamma(a, x) = Q(a, x) Gamma(a) (gamma_incomplete_upper, src/libAtoms/gamma_functions.f95:43-63:
+// series for x < a + 1, continued fraction otherwise)
+double gamma_incomplete_upper(double a, double x) {
+  if (x < 0.0 || a <= 0.0) throw GapError("bad arguments in gamma_incomplete_upper");
+  const double gln = std::lgamma(a);
+  double q;
+  if (x < a + 1.0) {
+    double p = 0.0;
+    if (x > 0.0) {
+      double ap = a, sum = 1.0 / a, del = sum;
+      for (int i = 0; i < 100000; i++) {
+        ap += 1.0;
+        del *= x / ap;
+        sum += del;
+        if (std::fabs(del) < std::fabs(sum) * 1e-17) break;
+      }
+      p = sum * std::exp(-x + a * std::log(x) - gln);
+    }
+    q = 1.0 - p;
+  } else {
+    const double tiny = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    for (int i = 1; i < 100000; i++) {
+      const double an = -i * (i - a);
+      b += 2.0;
+      d = an * d + b;
+      if (std::fabs(d) < tiny) d = tiny;
+      c = b + an / c;
+      if (std::fabs(c) < tiny) c = tiny;
+      d = 1.0 / d;
+      const double del = d * c;
+      h *= del;
+      if (std::fabs(del - 1.0) < 1e-16) break;
+    }
+    q = std::exp(-x + a * std::log(x) - gln) * h;
+  }
+  return q * std::exp(gln);
+}
+
+// least-squares solution operator of the m x n (m >= n, full rank) column-major matrix A by Householder QR (LA_Matrix_QR_Factorise +
+// Matrix_QR_Solve, linearalgebra.f95): returns Pinv[n][m] with x = Pinv b
+std::vector<double> pinv_qr(std::vector<double> A, int m, int n) {
+  std::vector<double> Q((size_t)m * m, 0.0);  // accumulate Q^T as a dense m x m matrix (m <= 48)
+  for (int i = 0; i < m; i++) Q[i + (size_t)m * i] = 1.0;
+  for (int k = 0; k < n; k++) {
+    double nrm = 0.0;
+    for (int i = k; i < m; i++) nrm += A[i + (size_t)m * k] * A[i + (size_t)m * k];
+    nrm = std::sqrt(nrm);
+    if (nrm == 0.0) throw GapError("LA_Matrix_QR_Factorise: rank-deficient radial basis");
+    const double alpha = A[k + (size_t)m * k] > 0 ? -nrm : nrm;
+    std::vector<double> v(m, 0.0);
+    for (int i = k; i < m; i++) v[i] = A[i + (size_t)m * k];
+    v[k] -= alpha;
+    double vn = 0.0;
+    for (int i = k; i < m; i++) vn += v[i] * v[i];
+    if (vn == 0.0) continue;
+    for (int j = 0; j < n; j++) {  // A <- H A
+      double t = 0.0;
+      for (int i = k; i < m; i++) t += v[i] * A[i + (size_t)m * j];
+      t *= 2.0 / vn;
+      for (int i = k; i < m; i++) A[i + (size_t)m * j] -= t * v[i];
+    }
+    for (int j = 0; j < m; j++) {  // Qt <- H Qt
+      double t = 0.0;
+      for (int i = k; i < m; i++) t += v[i] * Q[i + (size_t)m * j];
+      t *= 2.0 / vn;
+      for (int i = k; i < m; i++) Q[i + (size_t)m * j] -= t * v[i];
+    }
+  }
+  // x = R^-1 (Q^T b)[0:n]  ->  Pinv = R^-1 Qt[0:n, :]
+  std::vector<double> Pinv((size_t)n * m, 0.0);
+  for (int col = 0; col < m; col++)
+    for (int i = n - 1; i >= 0; i--) {
+      double t = Q[i + (size_t)m * col];
+      for (int k = i + 1; k < n; k++) t -= A[i + (size_t)m * k] * Pinv[(size_t)k * m + col];
+      Pinv[(size_t)i * m + col] = t / A[i + (size_t)m * i];
+    }
+  return Pinv;
+}
+
+void soap_general_setup(SoapSpec& s, bool diagonal_radial, bool Z_mix, bool R_mix, bool sym_mix, bool coupling, int nu_R, int nu_S, int K, int mix_shift,
+                        const std::string& Z_map, double cutoff_basis) {
+  const int n = s.n_max, ns = s.n_species, L = s.l_max, K1 = n * ns;
+  const bool mixing = R_mix || Z_mix || sym_mix, using_Zmap = !Z_map.empty();
+  // form_W :7618-7670
+  if ((nu_R != 2 || nu_S != 2) && mixing) throw GapError("(nu_R, nu_S) = (2,2) required to use channel mixing");
+  if ((nu_R != 2 || nu_S != 2) && diagonal_radial) throw GapError("(nu_R, nu_S) = (2,2) required to use diagonal radial");
+  if ((nu_R != 2 || nu_S != 2) && using_Zmap) throw GapError("(nu_R, nu_S) = (2,2) required to use Zmap");
+  if (mixing && using_Zmap) throw GapError("cant' using mixing and Zmap at the same time");
+  bool sym_desc;
+  std::vector<double> W[2];
+  int Kw[2] = {0, 0};
+  if (mixing) {  // form_mix_W :7430-7533
+    sym_desc = sym_mix;
+    if (K < 1) throw GapError("form_mix_W: K (number of mixing channels) must be positive");
+    for (int j = 1; j <= 2; j++) {
+      std::vector<double>& w = W[j - 1];
+      if (sym_desc && j == 2) { w = W[0]; Kw[1] = Kw[0]; continue; }
+      if (R_mix && Z_mix) {
+        Kw[j - 1] = K;
+        w.assign((size_t)K1 * K, 0.0);
+        for (int is = 0; is < ns; is++) {
+          QuipRng rng(s.species_Z[is] + mix_shift + j * 200);
+          for (int r = is * n; r < (is + 1) * n; r++)
+            for (int c = 0; c < K; c++) w[(size_t)r * K + c] = rng.normal();
+        }
+      } else if (Z_mix) {
+        Kw[j - 1] = K * n;
+        w.assign((size_t)K1 * K * n, 0.0);
+        for (int is = 0; is < ns; is++) {
+          QuipRng rng(s.species_Z[is] + mix_shift + j * 200);
+          for (int k = 0; k < K; k++) {
+            const double rv = rng.normal();
+            for (int a = 0; a < n; a++) w[(size_t)(is * n + a) * (K * n) + k * n + a] = rv;
+          }
+        }
+      } else if (R_mix) {
+        Kw[j - 1] = K * ns;
+        w.assign((size_t)K1 * K * ns, 0.0);
+        QuipRng rng(n + mix_shift + j * 200);
+        std::vector<double> R((size_t)n * K);
+        for (int r = 0; r < n; r++)
+          for (int c = 0; c < K; c++) R[(size_t)r * K + c] = rng.normal();
+        for (int is = 0; is < ns; is++)
+          for (int a = 0; a < n; a++)
+            for (int k = 0; k < K; k++) w[(size_t)(is * n + a) * (K * ns) + is * K + k] = R[(size_t)a * K + k];
+      } else {
+        throw GapError("form_mix_W: not mixing anything");
+      }
+    }
+  } else if (using_Zmap) {  // form_Zmap_W :7536-7616
+    int n_groups[2] = {1, 1}, dens = 0;
+    for (char ch : Z_map) {
+      if (ch == ',') n_groups[dens < 2 ? dens : 1]++;
+      if (ch == ':') dens++;
+    }
+    if (dens > 1) throw GapError("form_Zmap_W: at most one ':' in Z_map");
+    sym_desc = dens == 0;
+    Kw[0] = n * n_groups[0];
+    Kw[1] = n * (dens == 1 ? n_groups[1] : n_groups[0]);
+    W[0].assign((size_t)K1 * Kw[0], 0.0);
+    W[1].assign((size_t)K1 * Kw[1], 0.0);
+    int i_group = 0, i_density = 0;
+    std::string tok;
+    for (size_t q = 0; q <= Z_map.size(); q++) {
+      const char ch = q < Z_map.size() ? Z_map[q] : ' ';
+      if (isdigit((unsigned char)ch)) { tok.push_back(ch); continue; }
+      if (!tok.empty()) {
+        const int Zv = atoi(tok.c_str());
+        int isp = -1;
+        for (int k = 0; k < ns; k++)
+          if (s.species_Z[k] == Zv) isp = k;
+        if (isp < 0) throw GapError("form_Zmap_W: Z_map names Z=" + tok + " which is not in species_Z");
+        for (int a = 0; a < n; a++) W[i_density][(size_t)(isp * n + a) * Kw[i_density] + i_group * n + a] = 1.0;
+        tok.clear();
+      }
+      if (ch == ',') i_group++;
+      if (ch == ':') { i_density++; i_group = 0; }
+    }
+    if (sym_desc) W[1] = W[0];
+  } else {  // form_nu_W :7352-7424
+    if (nu_R < 0 || nu_R > 2) throw GapError("nu_R outside allowed range of 0-2");
+    if (nu_S < 0 || nu_S > 2) throw GapError("nu_S outside allowed range of 0-2");
+    sym_desc = !(nu_R == 1 || nu_S == 1);
+    int r = nu_R, sp = nu_S;
+    for (int i = 0; i < 2; i++) {
+      int dn = 0, ds = 0, n2_max = 1, s2_max = 1;
+      if (r > 0) { r--; dn = 1; n2_max = n; }
+      if (sp > 0) { sp--; ds = 1; s2_max = ns; }
+      Kw[i] = n2_max * s2_max;
+      W[i].assign((size_t)K1 * Kw[i], 0.0);
+      for (int s1 = 1; s1 <= ns; s1++)
+        for (int a = 1; a <= n; a++) {
+          int ic = 0;
+          for (int s2 = 1; s2 <= s2_max; s2++)
+            for (int n2 = 1; n2 <= n2_max; n2++, ic++)
+              if (ds * s1 == ds * s2 && dn * a == dn * n2) W[i][(size_t)((s1 - 1) * n + a - 1) * Kw[i] + ic] = 1.0;
+        }
+    }
+  }
+  s.Ka = Kw[0]; s.Kb = Kw[1];
+  s.W1 = W[0]; s.W2 = W[1];
+  // the power-spectrum elements, in the order the unpacking loops write them (:8402-8416; form_coupling_inds :7274-7350)
+  const bool original = coupling && nu_R == 2 && nu_S == 2 && !mixing && !using_Zmap;
+  const double sqrt2 = std::sqrt(2.0);
+  s.pair_ia.clear(); s.pair_jb.clear(); s.pair_fac.clear();
+  auto push = [&](int ia, int jb, double f) { s.pair_ia.push_back(ia); s.pair_jb.push_back(jb); s.pair_fac.push_back(f); };
+  if (coupling) {
+    if (diagonal_radial && !original) throw GapError("soap_dimensions: can't combine diagonal radial with any other compression strategies");
+    for (int ia = 0; ia < s.Ka; ia++)
+      for (int jb = 0; jb < (sym_desc ? ia + 1 : s.Kb); jb++) {
+        if (diagonal_radial && (ia % n) != (jb % n)) continue;
+        push(ia, jb, (sym_desc && ia != jb) ? sqrt2 : 1.0);
+      }
+  } else {
+    if (s.Ka != s.Kb) throw GapError("require K1=K2 to use elementwise coupling");
+    const double sqrt2_f32 = (double)(float)sqrt2;  // sym_facs is declared `real` (single precision, :7283)
+    if (Z_mix && !R_mix) {
+      for (int k = 0; k < K; k++)
+        for (int a = 0; a < n; a++)
+          for (int b = 0; b < (sym_mix ? a + 1 : n); b++) push(k * n + a, k * n + b, (a != b && sym_mix) ? sqrt2_f32 : 1.0);
+    } else if (R_mix && !Z_mix) {
+      for (int is = 0; is < ns; is++)
+        for (int js = 0; js < (sym_mix ? is + 1 : ns); js++)
+          for (int k = 0; k < K; k++) push(is * K + k, js * K + k, (is != js && sym_mix) ? sqrt2_f32 : 1.0);
+    } else {
+      for (int i = 0; i < s.Ka; i++) push(i, i, 1.0);
+    }
+  }
+  s.d = (L + 1) * (int)s.pair_ia.size() + 1;  // soap_dimensions :10929-10967
+
+  // radial map per l
+  if (s.radial_basis == "EQUISPACED_GAUSS") {
+    s.n_grid = n;
+    s.r_grid = s.r_basis;
+    s.P.assign((size_t)(L + 1) * n * n, 0.0);
+    for (int l = 0; l <= L; l++)
+      for (int g = 0; g < n; g++)
+        for (int a = 0; a < n; a++) s.P[((size_t)l * n + g) * n + a] = s.transform_basis[g + n * a];
+    s.c0.assign(n, 0.0);
+    for (int a = 0; a < n; a++) s.c0[a] = s.cholesky_overlap[0 + n * a];  // radial_fun(0,:) = e_1 times the Cholesky factor :8151-8154
+    return;
+  }
+  const int ng = 3 * n;  // :2644-2651
+  s.n_grid = ng;
+  s.r_grid.assign(ng, 0.0);
+  for (int i = 1; i < ng; i++) s.r_grid[i] = s.r_grid[i - 1] + cutoff_basis / ng;
+  s.P.assign((size_t)(L + 1) * ng * n, 0.0);
+  const int l_ub = s.radial_basis == "POLY" ? 0 : L;
+  for (int l = 0; l <= l_ub; l++) {
+    std::vector<double> S((size_t)n * n), B((size_t)ng * n);  // overlap (n x n) and the basis functions on the grid (ng x n), column-major
+    if (s.radial_basis == "POLY") {  // :2661-2678
+      auto Nn = [&](int i) { return std::sqrt(std::pow(cutoff_basis, 2 * i + 7) / ((i + 3.0) * (2 * i + 5.0) * (2 * i + 7.0))); };
+      for (int i = 1; i <= n; i++)
+        for (int j = 1; j <= n; j++)
+          S[(j - 1) + (size_t)n * (i - 1)] = 2.0 * std::pow(cutoff_basis, i + j + 7) / ((5.0 + i + j) * (6.0 + i + j) * (7.0 + i + j)) / (Nn(i) * Nn(j));
+      for (int i = 1; i <= n; i++)
+        for (int g = 0; g < ng; g++) B[g + (size_t)ng * (i - 1)] = std::pow(cutoff_basis - s.r_grid[g], i + 2) / Nn(i);
+    } else {  // GTO :2680-2712
+      std::vector<double> aln(n);
+      for (int k = 1; k <= n; k++) {
+        const double Rg = (cutoff_basis / n) * k;
+        aln[k - 1] = -std::pow(Rg, -2.0) * (std::log(0.001) - l * std::log(Rg));
+      }
+      const double t = l + 1.5;
+      for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+          const double u = (aln[i] + aln[j]) * cutoff_basis * cutoff_basis;
+          S[i + (size_t)n * j] = 0.5 * std::pow(cutoff_basis, 2.0 * t) * std::pow(u, -t) * (std::tgamma(t) - gamma_incomplete_upper(t, u));
+        }
+      for (int i = 0; i < n; i++)
+        for (int g = 0; g < ng; g++) B[g + (size_t)ng * i] = std::pow(s.r_grid[g], l) * std::exp(-aln[i] * s.r_grid[g] * s.r_grid[g]);
+    }
+    chol_lower(S, n, "overlap_basis");  // :2724-2731 (lower factor Lc, S = Lc Lc^T)
+    // A = B (Lc^T)^-1 :2733-2739 : solve A Lc^T = B column by column (Lc^T upper triangular)
+    std::vector<double> A((size_t)ng * n, 0.0);
+    for (int g = 0; g < ng; g++)
+      for (int j = 0; j < n; j++) {
+        double v = B[g + (size_t)ng * j];
+        for (int k = 0; k < j; k++) v -= A[g + (size_t)ng * k] * S[j + (size_t)n * k];  // (Lc^T)(k, j) = Lc(j, k)
+        A[g + (size_t)ng * j] = v / S[j + (size_t)n * j];
+      }
+    const std::vector<double> Pinv = pinv_qr(A, ng, n);  // [a][g]
+    for (int g = 0; g < ng; g++)
+      for (int a = 0; a < n; a++) s.P[((size_t)l * ng + g) * n + a] = Pinv[(size_t)a * ng + g];
+  }
+  for (int l = l_ub + 1; l <= L; l++)  // POLY: the l = 0 factors serve every l (:2751-2756)
+    for (size_t k = 0; k < (size_t)ng * n; k++) s.P[(size_t)l * ng * n + k] = s.P[k];
+  s.c0.assign(n, 0.0);  // central atom: radial_fun(0, g) = exp(-alpha r_g^2) through the l = 0 map (:8156-8165)
+  for (int g = 0; g < ng; g++) {
+    const double rf = std::exp(-s.alpha * s.r_grid[g] * s.r_grid[g]);
+    for (int a = 0; a < n; a++) s.c0[a] += rf * s.P[(size_t)g * n + a];
+  }
+}
+}  // namespace
+
 SoapSpec soap_from_string(const std::string& desc, long calc_xml_version) {
   ArgDict a(desc);
   SoapSpec s;
@@ -195,14 +507,17 @@ SoapSpec soap_from_string(const std::string& desc, long calc_xml_version) {
   bool has_n_species = a.has("n_species");
   s.n_species = (int)a.integer("n_species", 1);
   long xml_version = a.integer("xml_version", 1426512068L);
-  // options outside the hot-path scope: refuse loudly rather than mis-evaluate
-  for (const char* k : {"average", "diagonal_radial", "Z_mix", "R_mix", "sym_mix"})
-    if (a.logical(k, false)) throw GapError(std::string("soap option ") + k + "=T is not supported by the B200 path");
-  if (a.integer("nu_R", 2) != 2 || a.integer("nu_S", 2) != 2 || !a.logical("coupling", true))
-    throw GapError("soap nu_R/nu_S/coupling variants are not supported by the B200 path");
-  std::string rb = a.str("radial_basis", "");
-  if (!rb.empty() && rb != "EQUISPACED_GAUSS") throw GapError("soap radial_basis=" + rb + " is not supported by the B200 path");
-  if (!a.str("Z_map", "").empty()) throw GapError("soap Z_map is not supported by the B200 path");
+  // average=T is ONE descriptor per configuration (global SOAP), not a per-atom environment: outside the hot path, refused loudly
+  if (a.logical("average", false)) throw GapError("soap option average=T (global SOAP) is not supported by the B200 path");
+  const bool diagonal_radial = a.logical("diagonal_radial", false), Z_mix = a.logical("Z_mix", false), R_mix = a.logical("R_mix", false),
+             sym_mix = a.logical("sym_mix", false), coupling = a.logical("coupling", true);
+  const int nu_R = (int)a.integer("nu_R", 2), nu_S = (int)a.integer("nu_S", 2), K_mix = (int)a.integer("K", 0), mix_shift = (int)a.integer("mix_shift", 0);
+  const std::string Z_map = a.str("Z_map", "");
+  s.radial_basis = a.str("radial_basis", "");
+  if (s.radial_basis.empty()) s.radial_basis = "EQUISPACED_GAUSS";  // :2548-2551
+  if (s.radial_basis != "EQUISPACED_GAUSS" && s.radial_basis != "GTO" && s.radial_basis != "POLY")
+    throw GapError("soap_initialise: radial_basis not recognised: EQUISPACED_GAUSS, POLY or GTO");
+  s.general = diagonal_radial || Z_mix || R_mix || sym_mix || !coupling || nu_R != 2 || nu_S != 2 || !Z_map.empty() || s.radial_basis != "EQUISPACED_GAUSS";
   if (s.cutoff_dexp < 0) throw GapError("soap_initialise: cutoff_dexp may not be less than 0");
   if (s.cutoff_scale <= 0.0) throw GapError("soap_initialise: cutoff_scale must be greater than 0");
   if (s.cutoff_rate < 0.0) throw GapError("soap_initialise: cutoff_rate may not be less than 0");
@@ -267,6 +582,7 @@ SoapSpec soap_from_string(const std::string& desc, long calc_xml_version) {
   }
   int K1 = s.K1();
   s.d = (s.l_max + 1) * K1 * (K1 + 1) / 2 + 1;  // soap_dimensions :10953-10958
+  if (s.general) soap_general_setup(s, diagonal_radial, Z_mix, R_mix, sym_mix, coupling, nu_R, nu_S, K_mix, mix_shift, Z_map, cutoff_basis);
   return s;
 }
 

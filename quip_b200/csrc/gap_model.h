@@ -47,6 +47,19 @@ struct SoapSpec {
   std::vector<double> cholesky_overlap; // n_max x n_max, column-major, lower
   int d = 0;
   int K1() const { return n_species * n_max; }
+  // ---- general path: compression modes (Z_mix / R_mix / sym_mix / coupling / nu_R, nu_S / Z_map / diagonal_radial,
+  //      descriptors.f95:7274-7670) and the GTO / POLY radial bases (:2643-2770, :8264-8278); general == false is the reference's
+  //      "original" power spectrum (:7772-7775) on EQUISPACED_GAUSS
+  bool general = false;
+  std::string radial_basis = "EQUISPACED_GAUSS";
+  int n_grid = 0;               // radial points: n_max, or 3 n_max for GTO / POLY
+  std::vector<double> r_grid;   // n_grid
+  std::vector<double> P;        // [l][g][a]: radial_coefficient(l, a) = sum_g radial_fun(l, g) P[l][g][a]
+  std::vector<double> c0;       // n_max: radial coefficients of the central atom's own Gaussian
+  int Ka = 0, Kb = 0;           // columns of the mixing matrices W(1), W(2)
+  std::vector<double> W1, W2;   // [K1][Ka], [K1][Kb] row-major
+  std::vector<int> pair_ia, pair_jb;  // power-spectrum elements per l: tlpo_l * fac * sum_m Y1_lm(ia) Y2_lm(jb), index l + (l_max+1) k
+  std::vector<double> pair_fac;
 };
 struct Distance2bSpec {
   double cutoff = 0, cutoff_transition_width = 0.5;

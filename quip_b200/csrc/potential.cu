@@ -67,6 +67,9 @@ struct CoordDev {
   // soap
   SoapDev h;
   SoapDev* d_sp = nullptr;
+  bool general = false;        // compression modes / GTO / POLY: soap_general.cu kernels
+  SoapGenDev gen;
+  void* gen_blob = nullptr;    // one device allocation behind the pointers of gen
   double *sp_rows = nullptr, *st_rows = nullptr, *alpha = nullptr, *scut = nullptr;
   int M = 0, M_pad = 0, d_pad = 0, dn_pad = 0, bn2 = 128;
   CovParams cp;
@@ -576,10 +579,32 @@ void upload_model(gap_potential* P) {
       cudaDeviceProp prop;
       CUDA_OK(cudaGetDeviceProperties(&prop, P->device));
       P->n_sm = prop.multiProcessorCount;
-      if (soap_adjoint_smem(h) > prop.sharedMemPerBlockOptin || soap_forward_smem(h) > prop.sharedMemPerBlockOptin)
+      if (!s.general && (soap_adjoint_smem(h) > prop.sharedMemPerBlockOptin || soap_forward_smem(h) > prop.sharedMemPerBlockOptin))
         throw GapError("soap descriptor too large for the shared memory of this device");
       CUDA_OK(cudaMalloc(&cd.d_sp, sizeof(SoapDev)));
       CUDA_OK(cudaMemcpy(cd.d_sp, &h, sizeof(SoapDev), cudaMemcpyHostToDevice));
+      memset(&cd.gen, 0, sizeof(cd.gen));
+      cd.general = s.general;
+      if (s.general) {  // tables of the general path, packed into one allocation (doubles first, then the two int lists)
+        const size_t np = s.pair_ia.size();
+        std::vector<double> blob;
+        auto put = [&](const std::vector<double>& v) { size_t o = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); if (blob.size() & 1) blob.push_back(0.0); return o; };
+        const size_t o_r = put(s.r_grid), o_P = put(s.P), o_c0 = put(s.c0), o_W1 = put(s.W1), o_W2 = put(s.W2), o_f = put(s.pair_fac), o_int = blob.size();
+        const size_t bytes = blob.size() * sizeof(double) + 2 * np * sizeof(int);
+        CUDA_OK(cudaMalloc(&cd.gen_blob, bytes + 16));
+        CUDA_OK(cudaMemcpy(cd.gen_blob, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
+        int* d_int = (int*)((double*)cd.gen_blob + o_int);
+        if (np) {
+          CUDA_OK(cudaMemcpy(d_int, s.pair_ia.data(), np * sizeof(int), cudaMemcpyHostToDevice));
+          CUDA_OK(cudaMemcpy(d_int + np, s.pair_jb.data(), np * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        const double* b = (const double*)cd.gen_blob;
+        cd.gen.n_grid = s.n_grid; cd.gen.Ka = s.Ka; cd.gen.Kb = s.Kb; cd.gen.n_pairs = (int)np;
+        cd.gen.r_grid = b + o_r; cd.gen.P = b + o_P; cd.gen.c0 = b + o_c0; cd.gen.W1 = b + o_W1; cd.gen.W2 = b + o_W2; cd.gen.pair_fac = b + o_f;
+        cd.gen.pair_ia = d_int; cd.gen.pair_jb = d_int + np;
+        if (soap_general_smem(h, cd.gen) > prop.sharedMemPerBlockOptin)
+          throw GapError("soap descriptor (general path) too large for the shared memory of this device");
+      }
       cd.M = c.M;
       cd.M_pad = round_up(c.M > 0 ? c.M : 1, COV_BK) + COV_BN1_MAX;  // any GEMM-1 column tiling (cov_gemm1_bn) stays in bounds
       cd.d_pad = h.d_pad;
@@ -678,9 +703,18 @@ CalcArgs parse_calc_args(const gap_potential* P, const char* args_str) {
   return a;
 }
 
-struct SoapRun {
-  int nc = 0, nc_pad = 0;
-};
+// SOAP adjoint + scatter of a coordinate: the DMMA kernels of soap.cu, or the general path of soap_general.cu
+void soap_adjoint_any(const CoordDev& cd, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
+                      const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
+                      const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
+                      double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st, int* launches) {
+  if (cd.general)
+    launch_soap_adjoint_general(cd.d_sp, cd.h, cd.gen, centres, n_centres_dev, n_centres_ub, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec,
+                                ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, st, launches);
+  else
+    launch_soap_adjoint(cd.d_sp, cd.h, centres, n_centres_dev, n_centres_ub, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
+                        g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, st, launches);
+}
 
 // select + compact the centres of SOAP coordinate cd among atoms [first,last).  The number of centres stays on the
 // device (P->b_scan[n], see nc_dev()); the host sizes grids and buffers with the upper bound n = last - first.
@@ -721,8 +755,12 @@ void soap_forward_stage(gap_potential* P, const CoordDev& cd, int n_ub, const do
   P->b_x.ensure(sizeof(double) * (size_t)nc_pad * cd.d_pad);
   P->b_xlm.ensure(sizeof(double) * (size_t)(n_ub > 0 ? n_ub : 1) * cd.h.nlm * cd.h.K1);
   P->b_pnorm.ensure(sizeof(double) * (size_t)nc_pad);
-  launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
-                      P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
+  if (cd.general)
+    launch_soap_forward_general(cd.d_sp, cd.h, cd.gen, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z,
+                                lat, P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
+  else
+    launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
+                        P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
   P->launches += launches;
 }
 
@@ -864,9 +902,9 @@ void variance_soap(gap_potential* P, size_t ic, int nc, const int* ncd, bool wan
                        P->b_gvec.as<double>() + (size_t)r0 * cd.dn_pad, cd.dn_pad, split_stride, st, &launches);
   }
   if (want_grad)  // pull-back through the descriptor: gap_variance_gradient(:,j) += grad_variance . grad_data(:,:,n)  (IPModel_GAP.f95:485-486)
-    launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_x.as<double>(),
-                        P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, ksplit, split_stride, nullptr, 0, nullptr,
-                        -1.0 /* the kernel scatters force = -e_scale f_gp */, P->b_gvg.as<double>(), nullptr, nullptr, st, &launches);
+    soap_adjoint_any(cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_x.as<double>(),
+                     P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, ksplit, split_stride, nullptr, 0, nullptr,
+                     -1.0 /* the kernel scatters force = -e_scale f_gp */, P->b_gvg.as<double>(), nullptr, nullptr, st, &launches);
   P->launches += launches;
 }
 
@@ -968,10 +1006,10 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
         mark(P, st, ST_SOAP_FWD);
         covariance_stage(P, cd, nc, ncd, want_grad, true, st);
         if (want_grad) {
-          launch_soap_adjoint(cd.d_sp, cd.h, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
-                              P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, P->g_splits,
-                              P->g_split_stride, P->b_epart.as<double>(), P->g_tiles_n, d_le, es, d_force,
-                              P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches);
+          soap_adjoint_any(cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
+                           P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, P->g_splits,
+                           P->g_split_stride, P->b_epart.as<double>(), P->g_tiles_n, d_le, es, d_force,
+                           P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches);
           slot += nc;
           mark(P, st, ST_SOAP_ADJ);
         } else {
@@ -1093,6 +1131,7 @@ void gap_potential_finalise(gap_potential* P) {
   if (P->comm) comm_destroy(P->comm);
   P->comm = nullptr;
   for (CoordDev& cd : P->cd) {
+    cudaFree(cd.gen_blob);
     cudaFree(cd.d_sp); cudaFree(cd.sp_rows); cudaFree(cd.st_rows); cudaFree(cd.alpha); cudaFree(cd.scut);
     cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2); cudaFree(cd.var_mat);
   }
@@ -1741,6 +1780,22 @@ int gap_model_describe(const char* args_str, const char* param_str, const char* 
         os << "\ncholesky_overlap";
         for (double v : s.cholesky_overlap) os << " " << v;
         os << "\n";
+        if (s.general) {  // the general path's derived tables (compression modes, GTO / POLY radial maps)
+          os << "soap_general " << i << " radial_basis " << s.radial_basis << " n_grid " << s.n_grid << " Ka " << s.Ka << " Kb " << s.Kb << " n_pairs "
+             << s.pair_ia.size() << "\nr_grid";
+          for (double v : s.r_grid) os << " " << v;
+          os << "\nP";
+          for (double v : s.P) os << " " << v;
+          os << "\nc0";
+          for (double v : s.c0) os << " " << v;
+          os << "\nW1";
+          for (double v : s.W1) os << " " << v;
+          os << "\nW2";
+          for (double v : s.W2) os << " " << v;
+          os << "\npairs";
+          for (size_t k = 0; k < s.pair_ia.size(); k++) os << " " << s.pair_ia[k] << ":" << s.pair_jb[k] << ":" << s.pair_fac[k];
+          os << "\n";
+        }
       } else {
         os << "distance_2b " << i << " Z1 " << c.d2b.Z1 << " Z2 " << c.d2b.Z2 << " ctw " << c.d2b.cutoff_transition_width << "\n";
       }

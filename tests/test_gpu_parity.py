@@ -726,3 +726,54 @@ def test_local_gap_variance_and_gradient(si_model, si_frames):
         # energy only: variance without gradient
         r0 = pot.calc(a, args_str=args)
         assert "gap_variance_gradient" not in r0 and np.abs(r0["var"] - r["var"]).max() < 1e-12 * scale
+
+
+# ----------------------------------------------------------------------------------------------------
+# SOAP variants: compression modes, nu_R / nu_S, Z_map, diagonal_radial, GTO / POLY radial bases -- the general
+# path of soap_general.cu against the reference's own golden vectors and, for the gradients, E/F/V against the oracle
+# ----------------------------------------------------------------------------------------------------
+def _variant_cases(golden):
+    meta = json.load(open(os.path.join(golden, "soap_reference_all.json")))
+    z = np.load(os.path.join(golden, "soap_reference_all.npz"))
+    S = json.load(open(os.path.join(golden, "soap_reference_cases.json")))["datasets"]
+    return meta, z, S
+
+
+def test_soap_reference_data_all_variants_gpu(golden, tmp_path):
+    """tests/test_SOAP.py:36-77 on the GPU: gap_descriptor_calc reproduces X of every average=F case of SOAP_reference_data.json
+    (66 of 122: mixing with QUIP's random weights, coupling=F, Z_map, nu_R / nu_S, diagonal_radial, GTO, POLY, and the default path)."""
+    meta, z, S = _variant_cases(golden)
+    n = 0
+    for i, m in enumerate(meta):
+        qs = m["quippy_str"]
+        if "average=T" in qs:
+            continue
+        d = z["X_%d" % i].shape[1]
+        coord = {"descriptor": qs, "covariance_type": 2, "delta": 1.0, "zeta": 2.0, "sparseX": np.zeros((1, d)), "alpha": np.zeros(1)}
+        pot = Potential("", param_filename=write_gap_xml(str(tmp_path / ("v%d.xml" % i)), [coord], separate_files=False))
+        ds = [Atoms(dd["numbers"], np.array(dd["scaled_positions"]) @ np.array(dd["cell"]), dd["cell"], False) for dd in S[m["dataset_name"]]]
+        X = np.concatenate([pot.descriptor_calc(a, 0)[0] for a in ds])[z["perm_%d" % i]]
+        assert X.shape == z["X_%d" % i].shape, (i, qs)
+        assert np.abs(X - z["X_%d" % i]).max() < 1e-9, (i, qs, np.abs(X - z["X_%d" % i]).max())
+        pot.finalise()
+        n += 1
+    assert n == 66
+
+
+VARIANT_EFV = [0, 2, 6, 12, 18, 22, 30, 38, 48, 53, 55, 60, 69, 73, 75, 101, 113, 115, 117, 118, 120, 121]
+
+
+@pytest.mark.parametrize("case", VARIANT_EFV)
+def test_soap_variants_efv_vs_oracle(golden, tmp_path, case):
+    """Gradients of the general path: a GAP built on the variant descriptor (random sparse points drawn from the oracle's descriptors,
+    non-trivial alphas and sparseCutoff), energy / force / virial / local quantities against the oracle, whose forward-mode grad_data
+    for the same strings is pinned to the reference's golden vectors (tests/test_oracle_golden.py)."""
+    meta, z, S = _variant_cases(golden)
+    qs = meta[case]["quippy_str"]
+    for pbc in (False, True):
+        ds = [Atoms(dd["numbers"], np.array(dd["scaled_positions"]) @ np.array(dd["cell"]), dd["cell"], pbc) for dd in S[meta[case]["dataset_name"]]]
+        xml = multi_species_model(str(tmp_path), qs, ds, 9, seed=100 + case + int(pbc), zeta=3.0 if case % 2 else 2.0)
+        pot, om = Potential("", param_filename=xml), orc.Model(xml)
+        for a in ds:
+            check_efv(pot, om, a)
+        pot.finalise()

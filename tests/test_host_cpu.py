@@ -145,3 +145,44 @@ def test_cli_argument_grammar():
 
     with pytest.raises(RuntimeError, match="outside the GAP evaluation path"):
         cli.parse_cli(["relax=T"])
+
+
+def test_general_soap_setup_matches_oracle(golden, tmp_path):
+    """The C++ loader's general-SOAP tables (mixing matrices with QUIP's random weights, power-spectrum element list, GTO / POLY
+    radial maps; gap_model.cpp soap_general_setup) against the oracle's independent numpy derivation, for every average=F descriptor
+    string of the reference's SOAP_reference_data.json that takes the general path."""
+    import json
+
+    meta = json.load(open(os.path.join(golden, "soap_reference_all.json")))
+    n_general = 0
+    for m in meta:
+        qs = m["quippy_str"]
+        if "average=T" in qs:
+            continue
+        p = orc.soap_params(qs)
+        W1, W2, _, pairs = orc.soap_mixing(p)
+        d = (p["l_max"] + 1) * len(pairs) + 1
+        coord = {"descriptor": qs, "covariance_type": 2, "delta": 1.0, "zeta": 2.0, "sparseX": np.zeros((1, d)), "alpha": np.zeros(1)}
+        xml = write_gap_xml(str(tmp_path / "g.xml"), [coord], separate_files=False)
+        text = P.model_describe(param_filename=xml)
+        if not p["general"]:
+            assert "soap_general" not in text
+            continue
+        n_general += 1
+        rows = {ln.split()[0]: ln.split()[1:] for ln in text.splitlines() if ln.split()[0] in ("soap_general", "r_grid", "P", "c0", "W1", "W2", "pairs")}
+        hdr = dict(zip(rows["soap_general"][1::2], rows["soap_general"][2::2]))
+        assert int(hdr["Ka"]) == W1.shape[1] and int(hdr["Kb"]) == W2.shape[1] and int(hdr["n_pairs"]) == len(pairs), qs
+        assert np.abs(np.array(rows["W1"], dtype=float).reshape(W1.shape) - W1).max() < 1e-14, qs
+        assert np.abs(np.array(rows["W2"], dtype=float).reshape(W2.shape) - W2).max() < 1e-14, qs
+        got = [tuple(float(v) for v in t.split(":")) for t in rows["pairs"]]
+        assert all(g[0] == q[0] and g[1] == q[1] and abs(g[2] - q[2]) < 1e-15 for g, q in zip(got, pairs)), qs
+        r, Pm, c0 = orc.soap_radial(p)
+        assert int(hdr["n_grid"]) == len(r)
+        assert np.abs(np.array(rows["r_grid"], dtype=float) - r).max() < 1e-13
+        Pc = np.array(rows["P"], dtype=float).reshape(Pm.shape)
+        assert np.abs(Pc - Pm).max() < 1e-9 * max(1.0, np.abs(Pm).max()), (qs, np.abs(Pc - Pm).max(), np.abs(Pm).max())
+        assert np.abs(np.array(rows["c0"], dtype=float) - c0).max() < 1e-9 * max(1.0, np.abs(c0).max()), qs
+    assert n_general >= 55
+    with pytest.raises(RuntimeError, match="average=T"):
+        coord = {"descriptor": meta[1]["quippy_str"], "covariance_type": 2, "delta": 1.0, "zeta": 2.0, "sparseX": np.zeros((1, 5)), "alpha": np.zeros(1)}
+        P.model_describe(param_filename=write_gap_xml(str(tmp_path / "avg.xml"), [coord], separate_files=False))
