@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "gap_comm.h"
+#include "gap_device.cuh"
 #include "gap_model.h"
 
 namespace gapb200 {
@@ -88,7 +89,9 @@ struct PeerPtrs {
 __global__ void __launch_bounds__(256) k_peer_allreduce(PeerPtrs peers, int rank, int n, unsigned step, size_t buf_off, size_t count,
                                                         double* __restrict__ result, int* __restrict__ err) {
   __shared__ int timed_out;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) timed_out = 0;
+  pdl_wait();  // this rank's partial is complete and visible
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x < n) {
     unsigned* f = reinterpret_cast<unsigned*>(peers.base[threadIdx.x]) + rank;
@@ -109,7 +112,10 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerPtrs peers, int rank
   }
   __syncthreads();
   if (timed_out) {
-    if (threadIdx.x == 0) atomicExch(err, 1);
+    if (threadIdx.x == 0) {  // err lives in mapped host memory: the host reads it after its synchronisation
+      *(volatile int*)err = 1;
+      __threadfence_system();
+    }
     return;
   }
   const size_t n2 = count >> 1, stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,8 +157,8 @@ struct GapComm {
   void* peer_base[P2P_MAX_RANKS] = {nullptr};
   unsigned step = 0;
   bool partial_is_peer = false;     // the partial of the step in flight lives in block (else: in the result buffer)
-  int* d_err = nullptr;
-  int* h_err = nullptr;             // pinned
+  int* d_err = nullptr;             // device address of h_err
+  int* h_err = nullptr;             // pinned + mapped: set by the peer kernel if it timed out
   char* d_handles = nullptr;        // [n + 1] x 64 bytes (slot n: this rank's handle, the send buffer)
   int* d_okflag = nullptr;
   const char* last = "none";
@@ -182,10 +188,9 @@ GapComm* comm_create(const char* id128, int rank, int n_ranks, int device) {
     if ((e && *e == '0') || n_ranks > P2P_MAX_RANKS || n_ranks < 2) c->p2p_enabled = false;
     const char* lim = getenv("GAP_B200_P2P_MAX_BYTES");
     if (lim && *lim) c->p2p_limit_bytes = (size_t)strtoull(lim, nullptr, 10);
-    CUDA_OK(cudaMalloc(&c->d_err, sizeof(int)));
-    CUDA_OK(cudaMemset(c->d_err, 0, sizeof(int)));
-    CUDA_OK(cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocDefault));
+    CUDA_OK(cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocMapped));
     *c->h_err = 0;
+    CUDA_OK(cudaHostGetDevicePointer((void**)&c->d_err, c->h_err, 0));
     CUDA_OK(cudaMalloc(&c->d_handles, (size_t)(n_ranks + 1) * sizeof(cudaIpcMemHandle_t)));
     CUDA_OK(cudaMalloc(&c->d_okflag, sizeof(int)));
   } catch (...) {
@@ -211,7 +216,6 @@ void comm_destroy(GapComm* c) {
   cudaDeviceSynchronize();
   p2p_release(c);
   if (c->comm) nccl().CommDestroy(c->comm);
-  cudaFree(c->d_err);
   cudaFree(c->d_handles);
   cudaFree(c->d_okflag);
   if (c->h_err) cudaFreeHost(c->h_err);
@@ -290,8 +294,7 @@ void comm_allreduce_packed(GapComm* c, size_t count, double* result, cudaStream_
     int blocks = (int)((count / 2 + 255) / 256);
     if (blocks > 2 * c->n_sm) blocks = 2 * c->n_sm;
     if (blocks < 1) blocks = 1;
-    k_peer_allreduce<<<blocks, 256, 0, st>>>(pp, c->rank, c->n, c->step, buf_off, count, result, c->d_err);
-    CUDA_OK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    launch_pdl(k_peer_allreduce, dim3(blocks), dim3(256), 0, st, pp, c->rank, c->n, c->step, buf_off, count, result, c->d_err);
     c->last = "p2p";
   } else {
     nccl_ok(nccl().AllReduce(result, result, count, ncclFloat64, ncclSum, c->comm, st), "ncclAllReduce");
@@ -310,7 +313,6 @@ void comm_check(GapComm* c) {
   if (!c || !c->h_err) return;
   if (*c->h_err) {
     *c->h_err = 0;
-    cudaMemset(c->d_err, 0, sizeof(int));
     throw GapError("gap_comm: the peer-memory reduction timed out waiting for another rank (did a rank fail before its evaluation?)");
   }
 }

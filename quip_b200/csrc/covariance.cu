@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const __grid_constant_
   constexpr unsigned A_BYTES = BM * ROW_BYTES, B_BYTES = BN * ROW_BYTES, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ unsigned char smem_raw[];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  if (n_rows_dev && row0 + m0 >= *n_rows_dev) return;  // row tile beyond the (device-side) number of centres
+  pdl_launch_dependents();
   unsigned char* const sbase = smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);  // swizzled stages: 1 KiB aligned
   const unsigned base = (unsigned)__cvta_generic_to_shared(sbase);
   double* const wsm = (double*)(sbase + STAGES * STAGE_BYTES);  // [BN] GP weights of this tile's columns
@@ -141,8 +141,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_dgemm_nt(const __grid_constant_
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
   if constexpr (COV) {
-    if (threadIdx.x < BN) wsm[threadIdx.x] = epi.w[n0 + threadIdx.x];  // read in the epilogue, many barriers from here
+    if (threadIdx.x < BN) wsm[threadIdx.x] = epi.w[n0 + threadIdx.x];  // read in the epilogue, many barriers from here (model constants)
   }
+  pdl_wait();  // everything above is independent of the preceding kernels; the operands (and the centre count) are not
+  if (n_rows_dev && row0 + m0 >= *n_rows_dev) return;  // row tile beyond the (device-side) number of centres
   __syncthreads();
   auto issue = [&](int kt) {  // thread 0: slab kt -> stage kt % STAGES
     const int s = kt % STAGES;
@@ -325,7 +327,7 @@ void launch_cov_gemm1(const double* x, int ldx, const double* sp_rows, int lds, 
     dim3 grid((M + BN - 1) / BN, n_rows_pad / BM, 1);
     const CUtensorMap tmA = operand_map(x, n_rows_pad, K, ldx, BM), tmB = operand_map(sp_rows, (long)grid.x * BN, K, lds, BN);
     cudaFuncSetAttribute(k_dgemm_nt<BN, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<BN>());
-    k_dgemm_nt<BN, E><<<grid, NTHREADS, gemm_smem<BN>(), st>>>(tmA, tmB, K, row0, n_rows_dev, e);
+    launch_pdl(k_dgemm_nt<BN, E>, grid, dim3(NTHREADS), gemm_smem<BN>(), st, tmA, tmB, K, row0, n_rows_dev, e);
   };
   auto by_zeta = [&](auto bn_tag) {
     switch (cp.zeta_int) {
@@ -369,10 +371,10 @@ void launch_cov_gemm2(const double* acoef, int lda, const double* st_rows, int l
   const CUtensorMap tmA = operand_map(acoef, n_rows_pad, K, lda, BM), tmB = operand_map(st_rows, dn_pad, K, ldst, bn == 112 ? 112 : 128);
   if (bn == 112) {
     cudaFuncSetAttribute(k_dgemm_nt<112, EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<112>());
-    k_dgemm_nt<112, EpiStore><<<grid, NTHREADS, gemm_smem<112>(), st>>>(tmA, tmB, K, row0, n_rows_dev, e);
+    launch_pdl(k_dgemm_nt<112, EpiStore>, grid, dim3(NTHREADS), gemm_smem<112>(), st, tmA, tmB, K, row0, n_rows_dev, e);
   } else {
     cudaFuncSetAttribute(k_dgemm_nt<128, EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem<128>());
-    k_dgemm_nt<128, EpiStore><<<grid, NTHREADS, gemm_smem<128>(), st>>>(tmA, tmB, K, row0, n_rows_dev, e);
+    launch_pdl(k_dgemm_nt<128, EpiStore>, grid, dim3(NTHREADS), gemm_smem<128>(), st, tmA, tmB, K, row0, n_rows_dev, e);
   }
   *launches += 1;
 }

@@ -12,7 +12,36 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <utility>
+
 namespace gapb200 {
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------------
+// The kernels of one evaluation form a chain on one stream.  Launched with the programmatic-stream-serialization attribute, a
+// kernel's CTAs may become resident while its predecessor drains (its last round of CTAs), so the launch latency and the ramp-up
+// disappear from the critical path.  Contract: such a kernel calls pdl_wait() before it touches anything a predecessor wrote
+// (griddepcontrol.wait returns when the prerequisite grids have completed and their writes are visible), and pdl_launch_dependents()
+// as early as possible.  Both are no-ops in a kernel launched the ordinary way.  GAP_B200_PDL=0 turns the attribute off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("GAP_B200_PDL"); return !(e && *e == '0'); }();
+  return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 constexpr int SOAP_NMAX_CAP = 16;   // n_max
 constexpr int SOAP_LMAX_CAP = 12;   // l_max

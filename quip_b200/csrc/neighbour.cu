@@ -68,6 +68,8 @@ constexpr int MAX_MAP_SHIFT = 30;
 // cell_count != NULL: also count the atoms of every cell (counting-sort path)
 __global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int* __restrict__ cell_of, int* __restrict__ mshift,
                       int* __restrict__ iota, int* __restrict__ err_flag, int* __restrict__ cell_count) {
+  pdl_launch_dependents();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double t[3];
@@ -98,6 +100,8 @@ __global__ void k_bin(const double* __restrict__ pos, int N, CellGrid grid, int*
 // counting sort, step 2: every atom takes a slot of its cell's range (in arbitrary order; the counts are consumed)
 __global__ void k_place(const int* __restrict__ cell_of, int N, const int* __restrict__ cell_start, int* __restrict__ cell_count,
                         int* __restrict__ slots) {
+  pdl_launch_dependents();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const int c = cell_of[i];
@@ -108,6 +112,8 @@ __global__ void k_place(const int* __restrict__ cell_of, int N, const int* __res
 __global__ void k_cell_sort_gather(const double* __restrict__ pos, const int* __restrict__ mshift, const int* __restrict__ cell_of,
                                    const int* __restrict__ slots, int N, const int* __restrict__ cell_start, int* __restrict__ sort_idx,
                                    int* __restrict__ sort_keys, double* __restrict__ spos, int* __restrict__ smshift) {
+  pdl_launch_dependents();
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= N) return;
   const int i = slots[t], c = cell_of[i];
@@ -128,6 +134,8 @@ __global__ void k_cell_sort_gather(const double* __restrict__ pos, const int* __
 __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __restrict__ mshift, const int* __restrict__ sort_idx,
                                 const int* __restrict__ sort_keys, int N, int ncell, double* __restrict__ spos, int* __restrict__ smshift,
                                 int* __restrict__ cell_start) {
+  pdl_launch_dependents();
+  pdl_wait();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
   const int key = sort_keys[p], prev = p > 0 ? sort_keys[p - 1] : -1;
@@ -161,6 +169,8 @@ __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, in
                                                             int* __restrict__ nbr_j, int* __restrict__ nbr_s, double* __restrict__ nbr_d, int cap,
                                                             int row_cap, int* __restrict__ max_row) {
   constexpr bool FILL = MODE != NEIGH_COUNT;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * NEIGH_WARPS + (threadIdx.x >> 5);
   if (p >= N) return;
@@ -286,20 +296,22 @@ void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell,
   if (N > SINGLE_TILE_SORT_MAX) {
     // counting sort by cell: count (atomics), exclusive scan, place, then every atom finds its rank by index inside its cell
     cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (ncell + 1), st);
-    k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.iota, w.err_flag, w.cell_count);
+    launch_pdl(k_bin, dim3(nb), dim3(256), 0, st, pos, N, grid, w.cell_of, w.mshift, w.iota, w.err_flag, w.cell_count);
     size_t bytes = w.cub_bytes;
     cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.cell_count, w.cell_start, ncell + 1, st);
-    k_place<<<nb, 256, 0, st>>>(w.cell_of, N, w.cell_start, w.cell_count, w.iota);
-    k_cell_sort_gather<<<nb, 256, 0, st>>>(pos, w.mshift, w.cell_of, w.iota, N, w.cell_start, w.sort_idx, w.sort_keys, w.spos, w.smshift);
+    launch_pdl(k_place, dim3(nb), dim3(256), 0, st, (const int*)w.cell_of, N, (const int*)w.cell_start, w.cell_count, w.iota);
+    launch_pdl(k_cell_sort_gather, dim3(nb), dim3(256), 0, st, pos, (const int*)w.mshift, (const int*)w.cell_of, (const int*)w.iota, N, (const int*)w.cell_start,
+               w.sort_idx, w.sort_keys, w.spos, w.smshift);
     *launches += 4;
     return;
   }
-  k_bin<<<nb, 256, 0, st>>>(pos, N, grid, w.cell_of, w.mshift, w.iota, w.err_flag, nullptr);
+  launch_pdl(k_bin, dim3(nb), dim3(256), 0, st, pos, N, grid, w.cell_of, w.mshift, w.iota, w.err_flag, (int*)nullptr);
   int bits = 1;
   while ((1 << bits) < ncell && bits < 31) bits++;
   size_t bytes = w.cub_bytes;
   cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.cell_of, w.sort_keys, w.iota, w.sort_idx, N, 0, bits, st);
-  k_gather_sorted<<<nb, 256, 0, st>>>(pos, w.mshift, w.sort_idx, w.sort_keys, N, ncell, w.spos, w.smshift, w.cell_start);
+  launch_pdl(k_gather_sorted, dim3(nb), dim3(256), 0, st, pos, (const int*)w.mshift, (const int*)w.sort_idx, (const int*)w.sort_keys, N, ncell, w.spos,
+             w.smshift, w.cell_start);
   *launches += 3;
 }
 
@@ -328,8 +340,8 @@ void launch_neigh_onepass(const double* pos, int N, int first, int last, const C
                           int* nbr_j, int* nbr_s, int row_cap, int* max_row, cudaStream_t st, int* launches) {
   (void)pos;
   int nb = (N + NEIGH_WARPS - 1) / NEIGH_WARPS;
-  k_neigh<NEIGH_ONEPASS><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn,
-                                                          nbr_off, nbr_end, nbr_j, nbr_s, nullptr, 0, row_cap, max_row);
+  launch_pdl(k_neigh<NEIGH_ONEPASS>, dim3(nb), dim3(NEIGH_WARPS * 32), 0, st, N, first, last, grid, (const int*)w.sort_idx, (const int*)w.sort_keys,
+             (const double*)w.spos, (const int*)w.smshift, (const int*)w.cell_start, w.nn, nbr_off, nbr_end, nbr_j, nbr_s, (double*)nullptr, 0, row_cap, max_row);
   *launches += 1;
 }
 

@@ -100,7 +100,9 @@ struct gap_potential {
   // real count comes back asynchronously (pinned) and is verified after the final synchronisation of the call
   unsigned char* h_stage = nullptr;  // pinned staging buffer of the host-pointer entry point (inputs in, results out)
   size_t h_stage_cap = 0;
-  int* h_pin = nullptr;        // pinned [3]: entry count (exact layout only), error flag, largest row
+  int* h_pin = nullptr;        // pinned + mapped [3]: entry count (exact layout only), error flag, largest row
+  int* d_hpin = nullptr;       // device address of h_pin (k_finalize writes the status there: no copy node in the stream)
+  bool stat_clean = false;     // the device status words were reset by the last k_finalize (speculative build needs no memset)
   int row_hint = -1;           // largest neighbour row of the previous call with the same (N, first, last)
   int hint_N = -1, hint_first = -1, hint_last = -1;
   bool pending_check = false;
@@ -151,9 +153,12 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict_
                                                           double e_scale, double* __restrict__ local_e, const double* __restrict__ vir_part,
                                                           int n_slots, double* __restrict__ part /* [gridDim][10] */,
                                                           unsigned int* __restrict__ counter, double* __restrict__ packed,
-                                                          const int* __restrict__ max_row_dev, long cap) {
+                                                          int* __restrict__ stat_dev /* [entry count, error flag, largest row] or NULL */, long cap,
+                                                          int* __restrict__ stat_host /* the same three words in mapped host memory */) {
   __shared__ double wsum[FIN_THREADS / 32][10];
   __shared__ bool is_last;
+  pdl_launch_dependents();
+  pdl_wait();
   const int stride = gridDim.x * FIN_THREADS;
   double v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = blockIdx.x * FIN_THREADS + threadIdx.x; i < N; i += stride) {
@@ -187,15 +192,28 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict_
   __syncthreads();
   if (is_last) {
     __threadfence();
+    // the partials of all blocks are fetched in parallel (a chain of dependent L2 loads costs ~0.3 us each), then added in block order
+    __shared__ double sp[FIN_BLOCKS * 10];
+    for (int k = threadIdx.x; k < 10 * (int)gridDim.x; k += FIN_THREADS) sp[k] = __ldcg(&part[k]);
+    __syncthreads();
     if (threadIdx.x < 10) {
       double t = 0.0;
-      for (int b = 0; b < (int)gridDim.x; b++) t += __ldcg(&part[10 * b + threadIdx.x]);
+      for (int b = 0; b < (int)gridDim.x; b++) t += sp[10 * b + threadIdx.x];
       // a speculatively sized neighbour list that overflowed poisons the energy: after the all-reduce EVERY rank sees the NaN
       // and repeats the evaluation, with no extra collective
-      if (threadIdx.x == 0 && max_row_dev && (long)*max_row_dev > cap) t = __longlong_as_double(0x7ff8000000000000LL);
+      if (threadIdx.x == 0 && stat_dev && (long)stat_dev[2] > cap) t = __longlong_as_double(0x7ff8000000000000LL);
       packed[threadIdx.x] = t;
     }
-    if (threadIdx.x == 0) *counter = 0u;
+    if (threadIdx.x == 0) {
+      *counter = 0u;
+      if (stat_dev) {  // the host reads the list's status from mapped memory after its synchronisation (no copy node in the stream);
+                       // the device words are left clean for the next speculative build
+        stat_host[1] = stat_dev[1];
+        stat_host[2] = stat_dev[2];
+        __threadfence_system();
+        stat_dev[0] = stat_dev[1] = stat_dev[2] = 0;
+      }
+    }
   }
 }
 
@@ -239,6 +257,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_compact_block(const int*
                                                                        double* __restrict__ zc, size_t nzc) {
   typedef cub::BlockScan<int, SEL_THREADS> BS;
   __shared__ typename BS::TempStorage tmp;
+  pdl_launch_dependents();
+  pdl_wait();
   if (blockIdx.x > 0) {
     const size_t stride = (size_t)(gridDim.x - 1) * SEL_THREADS, t0 = (size_t)(blockIdx.x - 1) * SEL_THREADS + threadIdx.x;
     for (size_t t = t0; t < nza; t += stride) za[t] = 0.0;
@@ -482,9 +502,11 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
 
   int* const stat = P->b_off.as<int>() + N;  // [0] entry count (written by the scan of the exact layout) [1] error flag [2] largest row
   w.err_flag = stat + 1;
-  CUDA_OK(cudaMemsetAsync(stat, 0, 3 * sizeof(int), st));
+  const bool spec = speculative && !want_dist && P->row_hint >= 0 && P->hint_N == N && P->hint_first == first && P->hint_last == last;
+  if (!(spec && P->stat_clean)) CUDA_OK(cudaMemsetAsync(stat, 0, 3 * sizeof(int), st));  // (k_finalize of the previous evaluation left them clean)
+  P->stat_clean = false;
   launch_bin_atoms(d_pos, N, grid, ncell, w, st, &launches);
-  if (speculative && !want_dist && P->row_hint >= 0 && P->hint_N == N && P->hint_first == first && P->hint_last == last) {
+  if (spec) {
     const int row_cap = round_up(P->row_hint + P->row_hint / 4 + 8, 4);
     const long cap = (long)row_cap * (last - first);
     if (cap <= 2147483000L) {
@@ -493,8 +515,7 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
       P->b_s.ensure(sizeof(int) * (size_t)(cap + 1));
       launch_neigh_onepass(d_pos, N, first, last, grid, w, P->b_off.as<int>(), P->b_end.as<int>(), P->b_j.as<int>(), P->b_s.as<int>(), row_cap,
                            stat + 2, st, &launches);
-      CUDA_OK(cudaMemcpyAsync(P->h_pin, stat, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
-      P->pending_check = true;
+      P->pending_check = true;  // the status words reach the host through k_finalize (mapped memory), see verify_connect
       P->pending_cap = row_cap;
       P->cv_end = P->b_end.as<int>(); P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
       P->launches += launches;
@@ -544,7 +565,9 @@ void upload_model(gap_potential* P) {
   const double pi = 3.14159265358979323846264338327950288;
   CUDA_OK(cudaMalloc(&P->d_fin_counter, sizeof(unsigned int)));
   CUDA_OK(cudaMemset(P->d_fin_counter, 0, sizeof(unsigned int)));
-  CUDA_OK(cudaHostAlloc((void**)&P->h_pin, 4 * sizeof(int), cudaHostAllocDefault));
+  CUDA_OK(cudaHostAlloc((void**)&P->h_pin, 4 * sizeof(int), cudaHostAllocMapped));
+  CUDA_OK(cudaHostGetDevicePointer((void**)&P->d_hpin, P->h_pin, 0));
+  P->h_pin[0] = P->h_pin[1] = P->h_pin[2] = P->h_pin[3] = 0;
   CUDA_OK(cudaMalloc(&P->d_e0, sizeof(double) * 128));
   CUDA_OK(cudaMemcpy(P->d_e0, P->model.e0, sizeof(double) * 128, cudaMemcpyHostToDevice));
   for (const Coordinate& c : P->model.coord) {
@@ -730,8 +753,8 @@ int select_centres(gap_potential* P, const CoordDev& cd, const int* d_Z, int fir
   P->b_centres.ensure(sizeof(int) * (n + 1));
   if (n <= SEL_MAX_N) {
     const bool fuse = za != nullptr;
-    k_select_compact_block<<<fuse ? 1 + SEL_ZERO_BLOCKS : 1, SEL_THREADS, 0, st>>>(d_Z, first, last, cd.d_sp, P->b_centres.as<int>(),
-                                                                                  P->b_scan.as<int>() + n, za, nza, zb, nzb, zc, nzc);
+    launch_pdl(k_select_compact_block, dim3(fuse ? 1 + SEL_ZERO_BLOCKS : 1), dim3(SEL_THREADS), 0, st, d_Z, first, last, (const SoapDev*)cd.d_sp,
+               P->b_centres.as<int>(), P->b_scan.as<int>() + n, za, nza, zb, nzb, zc, nzc);
     if (zeroed) *zeroed = fuse;
     P->launches += 1;
     return n;
@@ -1045,9 +1068,10 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   P->b_fin.ensure(sizeof(double) * 10 * FIN_BLOCKS);
   const size_t fin_work = std::max<size_t>((size_t)N, want_grad ? slot : 0);
   const int fin_blocks = (int)std::min<size_t>(FIN_BLOCKS, std::max<size_t>(1, (fin_work + FIN_THREADS - 1) / FIN_THREADS));
-  k_finalize<<<fin_blocks, FIN_THREADS, 0, st>>>(d_Zc, N, first, last, P->d_e0, es, d_le, want_grad ? P->b_vir.as<double>() : nullptr,
-                                                want_grad ? (int)slot : 0, P->b_fin.as<double>(), P->d_fin_counter, d_packed,
-                                                P->pending_check ? P->b_off.as<int>() + N + 2 : nullptr, P->pending_cap);
+  launch_pdl(k_finalize, dim3(fin_blocks), dim3(FIN_THREADS), 0, st, d_Zc, N, first, last, (const double*)P->d_e0, es, d_le,
+             (const double*)(want_grad ? P->b_vir.as<double>() : nullptr), want_grad ? (int)slot : 0, P->b_fin.as<double>(), P->d_fin_counter, d_packed,
+             P->pending_check ? P->b_off.as<int>() + N : (int*)nullptr, P->pending_cap, P->d_hpin);
+  if (P->pending_check) P->stat_clean = true;
   P->launches += 1;
   mark(P, st, ST_OTHER);
   CUDA_OK(cudaGetLastError());

@@ -363,6 +363,8 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
                                                         const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
                                                         double* __restrict__ xlm, double* __restrict__ pnorm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x;
   if (c >= *n_centres_dev) return;  // the grid is sized by an upper bound; the centre count never leaves the device
   const Geo g = make_geo(CN ? CN : sp->n_max, CN ? CL : sp->l_max, CN ? CNS : sp->n_species);
@@ -631,7 +633,9 @@ __global__ void __launch_bounds__(NT, (CN > 8 ? 2 : 4)) k_soap_forward_w(const S
   const int d = sp->d, d_pad = sp->d_pad;
   WSmem w;
   carve_w(g, d_pad, false, warp, &w, smem_raw);
-  load_tables_w(sp, g, w);
+  pdl_launch_dependents();
+  load_tables_w(sp, g, w);  // model constants: independent of the preceding kernels
+  pdl_wait();
   __syncthreads();  // the only block barrier: the tables
   const int c = blockIdx.x * NW + warp;
   if (c >= *n_centres_dev) return;
@@ -951,6 +955,8 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
                                                         double e_scale, double* __restrict__ force, double* __restrict__ vir_part,
                                                         double* __restrict__ local_virial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x;
   if (c >= *n_centres_dev) {
     if (vir_part && threadIdx.x < 9) vir_part[9 * (size_t)c + threadIdx.x] = 0.0;  // unused slot of the upper-bound grid
@@ -1126,7 +1132,9 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restr
   const int d = sp->d, d_pad = sp->d_pad;
   WSmem w;
   carve_w(g, d_pad, true, warp, &w, smem_raw);
-  load_tables_w(sp, g, w);
+  pdl_launch_dependents();
+  load_tables_w(sp, g, w);  // model constants: independent of the preceding kernels
+  pdl_wait();
   __syncthreads();  // the only block barrier: the tables
   const int c = blockIdx.x * NW + warp;
   if (c >= n_centres_ub) return;
@@ -1321,14 +1329,14 @@ void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres
   if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                  \
     const size_t smw = carve_w(make_geo(N, L, S), h.d_pad, false, 0, nullptr, nullptr);                                    \
     cudaFuncSetAttribute(k_soap_forward_w<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);                \
-    k_soap_forward_w<N, L, S><<<(n_centres + NW - 1) / NW, NT, smw, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, \
-                                                                         xlm, pnorm);                                      \
+    launch_pdl(k_soap_forward_w<N, L, S>, dim3((n_centres + NW - 1) / NW), dim3(NT), smw, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, \
+               pos, Z, lat, x, xlm, pnorm);                                                                                \
     return;                                                                                                                \
   }
   SOAP_SPECIALISATIONS(GO)
 #undef GO
   cudaFuncSetAttribute(k_soap_forward<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_soap_forward<0, 0, 0><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
+  launch_pdl(k_soap_forward<0, 0, 0>, dim3(n_centres), dim3(NT), sm, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
 }
 
 void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
@@ -1345,9 +1353,9 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
   if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                                     \
     const size_t smw = carve_w(make_geo(N, L, S), h.d_pad, true, 0, nullptr, nullptr);                                                       \
     cudaFuncSetAttribute(k_soap_adjoint_w<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);                                   \
-    k_soap_adjoint_w<N, L, S><<<(n_centres + NW - 1) / NW, NT, smw, st>>>(sp, centres, n_centres_dev, n_centres, nbr_off, nbr_end, nbr_j, nbr_s, pos, \
-                                                                         Z, lat, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride, epart,    \
-                                                                         n_tiles_n, local_e, e_scale, force, vir_part, local_virial);          \
+    launch_pdl(k_soap_adjoint_w<N, L, S>, dim3((n_centres + NW - 1) / NW), dim3(NT), smw, st, sp, centres, n_centres_dev, n_centres, nbr_off, nbr_end,  \
+               nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part,  \
+               local_virial);                                                                                                                \
     return;                                                                                                                                   \
   }
   SOAP_ADJOINT_W(GOW)
@@ -1355,16 +1363,15 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
 #define GO(N, L, S)                                                                                                                          \
   if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                                     \
     cudaFuncSetAttribute(k_soap_adjoint<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                      \
-    k_soap_adjoint<N, L, S><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, \
-                                                       g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part,         \
-                                                       local_virial);                                                                         \
+    launch_pdl(k_soap_adjoint<N, L, S>, dim3(n_centres), dim3(NT), sm, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, \
+               pnorm, gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);                \
     return;                                                                                                                                   \
   }
   SOAP_SPECIALISATIONS(GO)
 #undef GO
   cudaFuncSetAttribute(k_soap_adjoint<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_soap_adjoint<0, 0, 0><<<n_centres, NT, sm, st>>>(sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
-                                                     g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);
+  launch_pdl(k_soap_adjoint<0, 0, 0>, dim3(n_centres), dim3(NT), sm, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm,
+             gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);
 }
 
 }  // namespace gapb200
