@@ -76,6 +76,14 @@ int gap_potential_calc(gap_potential* pot, int N, const double* pos, const int* 
                        const char* args_str, double* energy, double* local_e, double* force, double* virial,
                        double* local_virial);
 
+/* at%cutoff_skin (calc_connect's skin, src/libAtoms/Connection.f95:1085-1128; the quip CLI's cutoff_skin=0.5 default, src/Programs/quip.f95:217,
+ * 343-345): with skin > 0 the neighbour list of gap_potential_calc / _calc_device / gap_md_run* is built out to cutoff + skin and REUSED
+ * while no atom has moved more than skin / 2 since the build (same N, partition, lattice, pbc); pairs beyond a descriptor's own cutoff
+ * are dropped by the descriptor kernels, which recompute every distance from the current positions (the reference's calc_dists).
+ * Results are identical to a rebuild at every call.  skin = 0 (default): rebuild every call.  _connect_stats counts both outcomes. */
+int gap_potential_set_cutoff_skin(gap_potential* pot, double cutoff_skin);
+int gap_potential_connect_stats(const gap_potential* pot, long* n_rebuilds, long* n_reuses);
+
 /* ---- optional inputs / outputs of IPModel_GAP_Calc that the reference passes through the Atoms object and the calc
  * args string (src/Potentials/IPModel_GAP.f95:324-337, 344-346, 462-488, 558-573).  They are requested with the SAME
  * keys in args_str and fetched after the calc:

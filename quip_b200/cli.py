@@ -64,6 +64,7 @@ def main(argv=None, out=sys.stdout):
     pot = Potential(cfg["init_args"], param_filename=cfg["param_filename"], calc_args=cfg["calc_args"])
     if cfg["timing"]:
         pot.set_timing(True)
+    pot.set_cutoff_skin(float(cfg.get("cutoff_skin", 0.5)))  # quip.f95:217, 343-345: at%cutoff_skin, default 0.5 A
     frames = read_xyz(cfg["atoms_filename"])
     for at in frames:
         t0 = time.perf_counter()

@@ -104,6 +104,7 @@ struct NeighbourWork {  // device scratch owned by the potential handle; sized f
   int* mshift = nullptr;       // [N] packed map_shift
   int* sort_keys = nullptr;    // [N]
   int* sort_idx = nullptr;     // [N] atom ids sorted by cell (stable)
+  int* slot_of = nullptr;      // [N] inverse: sorted slot of atom i
   int* iota = nullptr;         // [N]
   int* keys_tmp = nullptr;     // [N]
   int* cell_count = nullptr;   // [ncell+1] counting-sort path only

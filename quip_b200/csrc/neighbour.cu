@@ -111,7 +111,7 @@ __global__ void k_place(const int* __restrict__ cell_of, int N, const int* __res
 // both paths give the same arrays); positions are gathered on the way
 __global__ void k_cell_sort_gather(const double* __restrict__ pos, const int* __restrict__ mshift, const int* __restrict__ cell_of,
                                    const int* __restrict__ slots, int N, const int* __restrict__ cell_start, int* __restrict__ sort_idx,
-                                   int* __restrict__ sort_keys, double* __restrict__ spos, int* __restrict__ smshift) {
+                                   int* __restrict__ sort_keys, double* __restrict__ spos, int* __restrict__ smshift, int* __restrict__ slot_of) {
   pdl_launch_dependents();
   pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,6 +122,7 @@ __global__ void k_cell_sort_gather(const double* __restrict__ pos, const int* __
   for (int q = b; q < e; q++) rank += slots[q] < i;  // a cell holds a handful of atoms
   const int p = b + rank;
   sort_idx[p] = i;
+  slot_of[i] = p;
   sort_keys[p] = c;
   spos[3 * (size_t)p + 0] = pos[3 * (size_t)i + 0];
   spos[3 * (size_t)p + 1] = pos[3 * (size_t)i + 1];
@@ -133,7 +134,7 @@ __global__ void k_cell_sort_gather(const double* __restrict__ pos, const int* __
 // key is >= c (every thread fills the cells between its predecessor's key and its own; cell_start[ncell] = N)
 __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __restrict__ mshift, const int* __restrict__ sort_idx,
                                 const int* __restrict__ sort_keys, int N, int ncell, double* __restrict__ spos, int* __restrict__ smshift,
-                                int* __restrict__ cell_start) {
+                                int* __restrict__ cell_start, int* __restrict__ slot_of) {
   pdl_launch_dependents();
   pdl_wait();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,6 +144,7 @@ __global__ void k_gather_sorted(const double* __restrict__ pos, const int* __res
   if (p == N - 1)
     for (int c = key + 1; c <= ncell; c++) cell_start[c] = N;
   int i = sort_idx[p];
+  slot_of[i] = p;
   spos[3 * (size_t)p + 0] = pos[3 * (size_t)i + 0];
   spos[3 * (size_t)p + 1] = pos[3 * (size_t)i + 1];
   spos[3 * (size_t)p + 2] = pos[3 * (size_t)i + 2];
@@ -163,7 +165,7 @@ enum { NEIGH_COUNT = 0, NEIGH_FILL = 1, NEIGH_ONEPASS = 2 };
 
 template <int MODE>
 __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, int last, CellGrid grid, const int* __restrict__ sort_idx,
-                                                            const int* __restrict__ sort_keys, const double* __restrict__ spos,
+                                                            const int* __restrict__ slot_of, const int* __restrict__ sort_keys, const double* __restrict__ spos,
                                                             const int* __restrict__ smshift, const int* __restrict__ cell_start,
                                                             int* __restrict__ nn, int* __restrict__ nbr_off, int* __restrict__ nbr_end,
                                                             int* __restrict__ nbr_j, int* __restrict__ nbr_s, double* __restrict__ nbr_d, int cap,
@@ -172,14 +174,11 @@ __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, in
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int p = blockIdx.x * NEIGH_WARPS + (threadIdx.x >> 5);
-  if (p >= N) return;
-  const int i = sort_idx[p];
-  if (i < first || i >= last) {  // not a centre of this partition (descriptor_atomic_MPI_setup mask): empty row
-    if (MODE == NEIGH_COUNT && lane == 0) nn[i] = 0;
-    if (MODE == NEIGH_ONEPASS && lane == 0) nbr_off[i] = nbr_end[i] = 0;
-    return;
-  }
+  // one warp per CENTRE of this partition (descriptor_atomic_MPI_setup mask: atoms [first, last)); the rows of the other atoms are
+  // never read (the descriptor kernels only visit centres of the partition), except by the count / scan of the exact layout
+  const int i = first + blockIdx.x * NEIGH_WARPS + (threadIdx.x >> 5);
+  if (i >= last) return;
+  const int p = slot_of[i];
   const int cell = sort_keys[p];
   const int c0 = cell % grid.n[0], c1 = (cell / grid.n[0]) % grid.n[1], c2 = cell / (grid.n[0] * grid.n[1]);
   const double pi[3] = {spos[3 * (size_t)p], spos[3 * (size_t)p + 1], spos[3 * (size_t)p + 2]};
@@ -295,13 +294,13 @@ void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell,
   int nb = (N + 255) / 256;
   if (N > SINGLE_TILE_SORT_MAX) {
     // counting sort by cell: count (atomics), exclusive scan, place, then every atom finds its rank by index inside its cell
-    cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (ncell + 1), st);
+    // k_place hands every count back (atomicSub down to zero): the array is zeroed once, when it is allocated (potential.cu)
     launch_pdl(k_bin, dim3(nb), dim3(256), 0, st, pos, N, grid, w.cell_of, w.mshift, w.iota, w.err_flag, w.cell_count);
     size_t bytes = w.cub_bytes;
     cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.cell_count, w.cell_start, ncell + 1, st);
     launch_pdl(k_place, dim3(nb), dim3(256), 0, st, (const int*)w.cell_of, N, (const int*)w.cell_start, w.cell_count, w.iota);
     launch_pdl(k_cell_sort_gather, dim3(nb), dim3(256), 0, st, pos, (const int*)w.mshift, (const int*)w.cell_of, (const int*)w.iota, N, (const int*)w.cell_start,
-               w.sort_idx, w.sort_keys, w.spos, w.smshift);
+               w.sort_idx, w.sort_keys, w.spos, w.smshift, w.slot_of);
     *launches += 4;
     return;
   }
@@ -311,17 +310,18 @@ void launch_bin_atoms(const double* pos, int N, const CellGrid& grid, int ncell,
   size_t bytes = w.cub_bytes;
   cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, w.cell_of, w.sort_keys, w.iota, w.sort_idx, N, 0, bits, st);
   launch_pdl(k_gather_sorted, dim3(nb), dim3(256), 0, st, pos, (const int*)w.mshift, (const int*)w.sort_idx, (const int*)w.sort_keys, N, ncell, w.spos,
-             w.smshift, w.cell_start);
+             w.smshift, w.cell_start, w.slot_of);
   *launches += 3;
 }
 
 void launch_neigh_count(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, int* max_row,
                         cudaStream_t st, int* launches) {
   (void)pos;
-  int nb = (N + NEIGH_WARPS - 1) / NEIGH_WARPS;
-  k_neigh<NEIGH_COUNT><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nullptr,
-                                                        nullptr, nullptr, nullptr, nullptr, 0, 0, max_row);
-  cudaMemsetAsync(w.nn + N, 0, sizeof(int), st);
+  int nb = (last - first + NEIGH_WARPS - 1) / NEIGH_WARPS;
+  cudaMemsetAsync(w.nn, 0, sizeof(int) * (N + 1), st);  // rows of atoms outside the partition are empty
+  if (nb > 0)
+    k_neigh<NEIGH_COUNT><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.slot_of, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn,
+                                                          nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, max_row);
   size_t bytes = w.cub_bytes;
   cub::DeviceScan::ExclusiveSum(w.cub_tmp, bytes, w.nn, nbr_off, N + 1, st);
   *launches += 2;
@@ -330,18 +330,21 @@ void launch_neigh_count(const double* pos, int N, int first, int last, const Cel
 void launch_neigh_fill(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, int* nbr_j,
                        int* nbr_s, double* nbr_d, int cap, cudaStream_t st, int* launches) {
   (void)pos;
-  int nb = (N + NEIGH_WARPS - 1) / NEIGH_WARPS;
-  k_neigh<NEIGH_FILL><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn, nbr_off,
-                                                       nullptr, nbr_j, nbr_s, nbr_d, cap, 0, nullptr);
+  int nb = (last - first + NEIGH_WARPS - 1) / NEIGH_WARPS;
+  if (nb > 0)
+    k_neigh<NEIGH_FILL><<<nb, NEIGH_WARPS * 32, 0, st>>>(N, first, last, grid, w.sort_idx, w.slot_of, w.sort_keys, w.spos, w.smshift, w.cell_start, w.nn,
+                                                         nbr_off, nullptr, nbr_j, nbr_s, nbr_d, cap, 0, nullptr);
   *launches += 1;
 }
 
 void launch_neigh_onepass(const double* pos, int N, int first, int last, const CellGrid& grid, NeighbourWork& w, int* nbr_off, int* nbr_end,
                           int* nbr_j, int* nbr_s, int row_cap, int* max_row, cudaStream_t st, int* launches) {
   (void)pos;
-  int nb = (N + NEIGH_WARPS - 1) / NEIGH_WARPS;
-  launch_pdl(k_neigh<NEIGH_ONEPASS>, dim3(nb), dim3(NEIGH_WARPS * 32), 0, st, N, first, last, grid, (const int*)w.sort_idx, (const int*)w.sort_keys,
-             (const double*)w.spos, (const int*)w.smshift, (const int*)w.cell_start, w.nn, nbr_off, nbr_end, nbr_j, nbr_s, (double*)nullptr, 0, row_cap, max_row);
+  int nb = (last - first + NEIGH_WARPS - 1) / NEIGH_WARPS;
+  if (nb > 0)
+    launch_pdl(k_neigh<NEIGH_ONEPASS>, dim3(nb), dim3(NEIGH_WARPS * 32), 0, st, N, first, last, grid, (const int*)w.sort_idx, (const int*)w.slot_of,
+               (const int*)w.sort_keys, (const double*)w.spos, (const int*)w.smshift, (const int*)w.cell_start, w.nn, nbr_off, nbr_end, nbr_j, nbr_s,
+               (double*)nullptr, 0, row_cap, max_row);
   *launches += 1;
 }
 

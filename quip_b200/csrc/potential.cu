@@ -124,9 +124,17 @@ struct gap_potential {
   bool var_grad = false;
   cudaStream_t last_stream = nullptr;
 
+  // skin-based reuse of the neighbour list (calc_connect with cutoff_skin, Connection.f95:1085-1128)
+  double cutoff_skin = 0.0;
+  bool list_valid = false;     // cv_* describe a list built with last_cut for the geometry remembered below
+  DevBuf b_lastpos, b_disp;    // positions at the last build; per-block maxima of the squared displacement
+  double last_lat[9] = {0}, last_cut = 0.0;
+  int last_pbc[3] = {0, 0, 0}, last_N = -1, last_first = -1, last_last = -1;
+  long n_rebuilds = 0, n_reuses = 0;
+  double* h_disp = nullptr;    // pinned [DISP_BLOCKS]
   // neighbour list state
   NeighbourWork nw;
-  DevBuf b_cell_of, b_mshift, b_keys, b_idx, b_iota, b_cstart, b_ccount, b_spos, b_smshift, b_nn, b_cub, b_minmax;
+  DevBuf b_cell_of, b_mshift, b_keys, b_idx, b_slot, b_iota, b_cstart, b_ccount, b_spos, b_smshift, b_nn, b_cub, b_minmax;
   DevBuf b_off, b_end, b_j, b_s, b_d;
   int conn_N = 0, conn_nnz = 0;
   // inputs / outputs owned for the host-pointer API
@@ -320,6 +328,21 @@ __global__ void __launch_bounds__(256) k_kinetic(int N, const double* __restrict
   if (threadIdx.x == 0) part[blockIdx.x] = t;
 }
 
+// largest squared displacement since the last list build, per block (the host takes the maximum of the block values)
+constexpr int DISP_BLOCKS = 256;
+__global__ void __launch_bounds__(256) k_max_disp2(const double* __restrict__ pos, const double* __restrict__ last, int N, double* __restrict__ part) {
+  typedef cub::BlockReduce<double, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  double m = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < N; i += gridDim.x * 256) {
+    const double dx = pos[3 * (size_t)i] - last[3 * (size_t)i], dy = pos[3 * (size_t)i + 1] - last[3 * (size_t)i + 1], dz = pos[3 * (size_t)i + 2] - last[3 * (size_t)i + 2];
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    m = (d2 > m || d2 != d2) ? d2 : m;  // a NaN position forces the rebuild (and its error reporting)
+  }
+  m = BR(tmp).Reduce(m, [](double a, double b) { return (a != a || a > b) ? a : b; });
+  if (threadIdx.x == 0) part[blockIdx.x] = m;
+}
+
 __global__ void k_iota(int* p, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = i;
@@ -377,6 +400,18 @@ void inv3(const double* a, double* g) {  // column-major both
   g[2 + 3 * 2] = (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0)) / det;
 }
 
+// the geometry a list was built for (this%last_connect_pos / last_connect_lattice / last_connect_cutoff, Connection.f95:1122-1124)
+void remember_build(gap_potential* P, int N, int first, int last, const double* d_pos, const double* lattice, const int* pbc, double cutoff_used,
+                    cudaStream_t st) {
+  P->b_lastpos.ensure(sizeof(double) * 3 * (size_t)N);
+  CUDA_OK(cudaMemcpyAsync(P->b_lastpos.p, d_pos, sizeof(double) * 3 * (size_t)N, cudaMemcpyDeviceToDevice, st));
+  for (int k = 0; k < 9; k++) P->last_lat[k] = lattice[k];
+  for (int k = 0; k < 3; k++) P->last_pbc[k] = pbc[k] ? 1 : 0;
+  P->last_N = N; P->last_first = first; P->last_last = last; P->last_cut = cutoff_used;
+  P->list_valid = true;
+  P->n_rebuilds++;
+}
+
 // speculative = true: if the previous call had the same (N, first, last), build the list in ONE pass into rows of fixed
 // capacity (largest row of that call + 25 %) and do NOT wait for anything: the largest row of this call arrives in
 // P->h_pin and verify_connect() checks it after the caller's final synchronisation.  Otherwise: exact packed CSR rows
@@ -386,6 +421,32 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   P->pending_check = false;
   if (N < 0) throw GapError("calc_connect: negative number of atoms");
   if (cutoff < 0.0) throw GapError("calc_connect: Negative cutoff radius " + std::to_string(cutoff));  // Connection.f95:1069
+  // calc_connect with cutoff_skin (Connection.f95:1085-1128): the list is built out to cutoff + skin and kept while no atom has moved
+  // more than skin / 2 since the build (same N, partition, lattice and pbc); the descriptor kernels recompute every distance from the
+  // current positions and drop pairs beyond their own cutoff (descriptors.f95:8190, 4729), as calc_dists + the reference's filters do
+  const bool use_skin = speculative && !want_dist && P->cutoff_skin > 0.0 && N > 0 && cutoff > 0.0;
+  if (use_skin) {
+    cutoff += P->cutoff_skin;
+    bool same = P->list_valid && P->last_N == N && P->last_first == first && P->last_last == last && cutoff <= P->last_cut;
+    for (int k = 0; k < 9 && same; k++) same = P->last_lat[k] == lattice[k];
+    for (int k = 0; k < 3 && same; k++) same = P->last_pbc[k] == (pbc[k] ? 1 : 0);
+    if (same) {
+      P->b_disp.ensure(sizeof(double) * DISP_BLOCKS);
+      if (!P->h_disp) CUDA_OK(cudaHostAlloc((void**)&P->h_disp, sizeof(double) * DISP_BLOCKS, cudaHostAllocDefault));
+      const int nb = std::min(DISP_BLOCKS, (N + 255) / 256);
+      k_max_disp2<<<nb, 256, 0, st>>>(d_pos, P->b_lastpos.as<double>(), N, P->b_disp.as<double>());
+      P->launches += 1;
+      CUDA_OK(cudaMemcpyAsync(P->h_disp, P->b_disp.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      double m = 0.0;
+      for (int k = 0; k < nb; k++) m = (P->h_disp[k] != P->h_disp[k] || P->h_disp[k] > m) ? P->h_disp[k] : m;
+      if (m == m && std::sqrt(m) < 0.5 * P->cutoff_skin) {  // :1110-1116: reuse (cv_* still describe the list)
+        P->n_reuses++;
+        return;
+      }
+    }
+    P->list_valid = false;
+  }
   P->conn_N = N;
   P->conn_nnz = 0;
   P->b_off.ensure(sizeof(int) * (N + 4));  // [0..N] row offsets, then: [N+1] error flag, [N+2] largest row
@@ -491,9 +552,15 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   P->b_mshift.ensure(sizeof(int) * N); w.mshift = P->b_mshift.as<int>();
   P->b_keys.ensure(sizeof(int) * N); w.sort_keys = P->b_keys.as<int>();
   P->b_idx.ensure(sizeof(int) * N); w.sort_idx = P->b_idx.as<int>();
+  P->b_slot.ensure(sizeof(int) * N); w.slot_of = P->b_slot.as<int>();
   P->b_iota.ensure(sizeof(int) * N); w.iota = P->b_iota.as<int>();
   P->b_cstart.ensure(sizeof(int) * (ncell + 2)); w.cell_start = P->b_cstart.as<int>();
-  P->b_ccount.ensure(sizeof(int) * (ncell + 2)); w.cell_count = P->b_ccount.as<int>();
+  {  // cell counts of the counting sort: zeroed when (re)allocated; every build hands them back zeroed (k_place)
+    const void* before = P->b_ccount.p;
+    P->b_ccount.ensure(sizeof(int) * (ncell + 2));
+    if (P->b_ccount.p != before) CUDA_OK(cudaMemsetAsync(P->b_ccount.p, 0, P->b_ccount.cap, st));
+    w.cell_count = P->b_ccount.as<int>();
+  }
   P->b_spos.ensure(sizeof(double) * 3 * N); w.spos = P->b_spos.as<double>();
   P->b_smshift.ensure(sizeof(int) * N); w.smshift = P->b_smshift.as<int>();
   P->b_nn.ensure(sizeof(int) * (N + 2)); w.nn = P->b_nn.as<int>();
@@ -519,6 +586,7 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
       P->pending_cap = row_cap;
       P->cv_end = P->b_end.as<int>(); P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
       P->launches += launches;
+      if (use_skin) remember_build(P, N, first, last, d_pos, lattice, pbc, cutoff, st);
       CUDA_OK(cudaGetLastError());
       return;
     }
@@ -538,6 +606,7 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
                     nnz, st, &launches);
   P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
   P->launches += launches;
+  if (use_skin) remember_build(P, N, first, last, d_pos, lattice, pbc, cutoff, st);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -549,6 +618,7 @@ bool verify_connect(gap_potential* P) {
   const int max_row = P->h_pin[2];
   const bool ok = max_row <= P->pending_cap;
   P->row_hint = ok ? max_row : -1;  // overflow: the repeat takes the exact (synchronising) path
+  if (!ok) P->list_valid = false;   // (and never reuses the truncated list)
   return ok;
 }
 
@@ -985,6 +1055,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
     d_Zc = ext->Zc;
     P->cv_off = ext->off; P->cv_end = ext->off + 1; P->cv_j = ext->j; P->cv_s = ext->s;
     P->pending_check = false;
+    P->list_valid = false;
   }
   // The centre selection of the first SOAP coordinate needs Z only: it is launched ahead of the neighbour-list build and, for small
   // partitions, the same launch zeroes the outputs (one launch instead of two at the head of the step).
@@ -1163,10 +1234,11 @@ void gap_potential_finalise(gap_potential* P) {
   cudaFree(P->d_fin_counter);
   if (P->h_pin) cudaFreeHost(P->h_pin);
   if (P->h_stage) cudaFreeHost(P->h_stage);
-  DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_iota, &P->b_cstart, &P->b_ccount, &P->b_end, &P->b_mask, &P->b_epc, &P->b_lgv, &P->b_gvg, &P->b_varflag, &P->b_vc, &P->b_vq, &P->b_vk, &P->b_spos, &P->b_smshift,
+  if (P->h_disp) cudaFreeHost(P->h_disp);
+  DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_slot, &P->b_iota, &P->b_cstart, &P->b_ccount, &P->b_end, &P->b_mask, &P->b_epc, &P->b_lgv, &P->b_gvg, &P->b_varflag, &P->b_vc, &P->b_vq, &P->b_vk, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
-                    &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke};
+                    &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke, &P->b_lastpos, &P->b_disp};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : P->ev) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);
@@ -1237,6 +1309,22 @@ int gap_potential_comm_info(const gap_potential* P, int* rank, int* n_ranks, cha
     strncpy(transport, t, n - 1);
     transport[n - 1] = 0;
   }
+  return 0;
+}
+
+int gap_potential_set_cutoff_skin(gap_potential* P, double cutoff_skin) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_set_cutoff_skin: pot is NULL");
+    if (!(cutoff_skin >= 0.0)) throw GapError("gap_potential_set_cutoff_skin: cutoff_skin must be >= 0");
+    P->cutoff_skin = cutoff_skin;
+    P->list_valid = false;
+  });
+}
+
+int gap_potential_connect_stats(const gap_potential* P, long* n_rebuilds, long* n_reuses) {
+  if (!P) return 1;
+  if (n_rebuilds) *n_rebuilds = P->n_rebuilds;
+  if (n_reuses) *n_reuses = P->n_reuses;
   return 0;
 }
 

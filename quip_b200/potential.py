@@ -35,6 +35,8 @@ ABI = {
     "gap_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "gap_potential_set_comm": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "gap_potential_comm_info": (C.c_int, [C.c_void_p, c_ip, c_ip, C.c_char_p, C.c_size_t]),
+    "gap_potential_set_cutoff_skin": (C.c_int, [C.c_void_p, C.c_double]),
+    "gap_potential_connect_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "gap_potential_calc": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "gap_potential_set_atom_mask": (C.c_int, [C.c_void_p, C.c_int, c_ip]),
     "gap_potential_get_energy_per_coordinate": (C.c_int, [C.c_void_p, c_dp]),
@@ -184,6 +186,16 @@ class Potential:
 
     def set_partition(self, rank, n_ranks):
         _check(load_library().gap_potential_set_partition(self._h, int(rank), int(n_ranks)))
+
+    def set_cutoff_skin(self, cutoff_skin):
+        """``at%cutoff_skin`` (Connection.f95:1085-1128): build the neighbour list out to cutoff + skin and reuse it while no atom has moved
+        more than skin / 2."""
+        _check(load_library().gap_potential_set_cutoff_skin(self._h, float(cutoff_skin)))
+
+    def connect_stats(self):
+        a, b = C.c_long(0), C.c_long(0)
+        load_library().gap_potential_connect_stats(self._h, C.byref(a), C.byref(b))
+        return {"rebuilds": a.value, "reuses": b.value}
 
     def set_comm(self, comm_id, rank, n_ranks):
         """Collective: join the communicator ``comm_id`` (128 bytes from :func:`comm_unique_id` on one rank, distributed by the

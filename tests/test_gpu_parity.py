@@ -777,3 +777,58 @@ def test_soap_variants_efv_vs_oracle(golden, tmp_path, case):
         for a in ds:
             check_efv(pot, om, a)
         pot.finalise()
+
+
+# ----------------------------------------------------------------------------------------------------
+# skin-based neighbour-list reuse (calc_connect with cutoff_skin, Connection.f95:1085-1128)
+# ----------------------------------------------------------------------------------------------------
+def test_cutoff_skin_reuses_list_with_identical_results(si_model, si_frames, tmp_path):
+    pot, om, xml = si_model
+    a = si_frames[8]
+    rng = np.random.default_rng(21)
+    skin_pot = Potential("IP GAP", param_filename=xml)
+    skin_pot.set_cutoff_skin(0.5)
+    pos = a.positions.copy()
+    for step in range(6):
+        # steps 1-3 move atoms by < skin / 2 in total (reuse), step 4 jumps one atom by 0.6 A (rebuild), step 5 is small again (reuse)
+        if step in (1, 2, 3, 5):
+            pos = pos + rng.uniform(-0.04, 0.04, size=pos.shape)
+        if step == 4:
+            pos = pos.copy()
+            pos[3] += np.array([0.6, 0.0, 0.0])
+        at = Atoms(a.numbers, pos, a.cell, True)
+        r = skin_pot.calc(at, force=True, virial=True, local_energy=True, local_virial=True)
+        o = om.calc(at, local_energy=True, local_virial=True)
+        assert abs(r["energy"] - o["energy"]) / len(a) < TOL_E_PER_ATOM
+        assert np.abs(r["force"] - o["force"]).max() < TOL_F
+        assert np.abs(r["virial"] - o["virial"]).max() < TOL_V
+        assert np.abs(r["local_energy"] - o["local_energy"]).max() < 1e-8
+        assert np.abs(r["local_virial"] - o["local_virial"]).max() < TOL_V
+    st = skin_pot.connect_stats()
+    assert st == {"rebuilds": 2, "reuses": 4}, st
+    # a changed lattice forces the rebuild (:1093-1096)
+    at = Atoms(a.numbers, pos * 1.001, a.cell * 1.001, True)
+    r = skin_pot.calc(at, force=True)
+    assert abs(r["energy"] - om.calc(at)["energy"]) / len(a) < TOL_E_PER_ATOM
+    assert skin_pot.connect_stats()["rebuilds"] == 3
+
+
+def test_md_with_skin_matches_rebuild_every_step(tmp_path):
+    # DynamicalSystem_run with cutoff_skin (the quip / md programs' default): same trajectory as rebuilding every step, fewer list builds
+    from quip_b200.potential import element_masses
+
+    atoms, xml = syn.build_config_A(str(tmp_path), _oracle_desc, n_cells=3, M=100, seed=1)
+    rng = np.random.default_rng(7)
+    m = element_masses(atoms.numbers)
+    v0 = rng.normal(size=atoms.positions.shape) * np.sqrt(8.617385e-5 * 300.0 / m)[:, None]
+    a1 = Atoms(atoms.numbers, atoms.positions.copy(), atoms.cell, True)
+    a2 = Atoms(atoms.numbers, atoms.positions.copy(), atoms.cell, True)
+    p1 = Potential("", param_filename=xml)
+    p2 = Potential("", param_filename=xml)
+    p2.set_cutoff_skin(0.5)
+    v1, ep1, ek1 = p1.run(a1, v0, dt=1.0, n_steps=30)
+    v2, ep2, ek2 = p2.run(a2, v0, dt=1.0, n_steps=30)
+    assert np.abs(a1.positions - a2.positions).max() < 1e-9
+    assert np.abs(ep1 - ep2).max() < 1e-8 * len(atoms)
+    st = p2.connect_stats()
+    assert st["reuses"] > 20 and st["rebuilds"] >= 1 and st["rebuilds"] + st["reuses"] == 31, st
