@@ -213,19 +213,29 @@ def cpu_baseline_leg(xml, atoms, budget_s=12.0):
     om = orc.Model(xml)
     cores = host_threads()
     N = len(atoms)
-    n = min(N, 256)
-    rate = n / cpu_sample(om, atoms, n)[0]
-    per_pass = int(min(N, max(n, rate * budget_s)))
-    passes = int(max(1, min(64, round(rate * budget_s / per_pass))))
-    tot, secs = 0.0, 0.0
-    for _ in range(passes):
-        t, tc = cpu_sample(om, atoms, per_pass)
-        tot += t
-        secs += whole_step_seconds(N, per_pass, t, tc)
-    return {"value": N * passes / secs, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d pass(es) over %d of %d centres of the same configuration, %.1f s in total; a whole step = serial neighbour list of all atoms "
-                      "(as calc_connect) + per-centre phases scaled to all centres; OpenMP over atoms with %d threads; oracle/gap_oracle.c "
-                      "(hand loops at -march=x86-64-v3, not the gfortran + BLAS binary)" % (passes, per_pass, N, tot, cores)}
+    flavours, tot_all = {}, 0.0
+    for name in ("loops", "openblas_dgemv"):  # the two per-atom products of gp_predict as vectorised loops / as dgemv from scipy's OpenBLAS
+        if name == "openblas_dgemv" and not orc.use_openblas(True):
+            continue
+        n = min(N, 256)
+        rate = n / cpu_sample(om, atoms, n)[0]
+        per_pass = int(min(N, max(n, rate * budget_s / 2)))
+        passes = int(max(1, min(64, round(rate * budget_s / 2 / per_pass))))
+        tot, secs = 0.0, 0.0
+        for _ in range(passes):
+            t, tc = cpu_sample(om, atoms, per_pass)
+            tot += t
+            secs += whole_step_seconds(N, per_pass, t, tc)
+        flavours[name] = {"value": N * passes / secs, "passes": passes, "centres_per_pass": per_pass}
+        tot_all += tot
+    orc.use_openblas(False)
+    best = max(flavours, key=lambda k: flavours[k]["value"])
+    return {"value": flavours[best]["value"], "unit": UNIT, "cores": cores, "kind": "port", "flavour": best,
+            "flavours": {k: v["value"] for k, v in flavours.items()},
+            "sample": "%d pass(es) over %d of %d centres of the same configuration per flavour, %.1f s in total; a whole step = serial neighbour list of "
+                      "all atoms (as calc_connect) + per-centre phases scaled to all centres; OpenMP over atoms with %d threads; oracle/gap_oracle.c "
+                      "with the gp_predict products as vectorised loops and as OpenBLAS dgemv (the faster one is `value`); not the gfortran binary"
+                      % (flavours[best]["passes"], flavours[best]["centres_per_pass"], N, tot_all, cores)}
 
 
 def run_reference(args):
@@ -244,6 +254,14 @@ def run_reference(args):
         N = len(atoms)
         n = min(N, 128)
         rate = n / cpu_sample(om, atoms, n)[0]
+        flavour = "loops"
+        if orc.use_openblas(True):  # gp_predict's two products as dgemv from scipy's OpenBLAS: keep whichever flavour is faster here
+            cpu_sample(om, atoms, n)
+            rate_blas = n / cpu_sample(om, atoms, n)[0]
+            if rate_blas > rate:
+                rate, flavour = rate_blas, "openblas_dgemv"
+            else:
+                orc.use_openblas(False)
         # each step = a bounded sample of centres sized so that warmup + steps take about two minutes at most; a step that covers
         # every centre is a whole evaluation, a smaller one is scaled to the whole evaluation phase by phase (the list is paid once)
         per_step = int(max(64, min(N, rate * 120.0 / max(1, args.steps + args.warmup))))
@@ -253,7 +271,7 @@ def run_reference(args):
     tot = float(np.sum(secs))
     value = N * args.steps / tot
     sample = ("%d of %d centres per step; step time = calc_connect of all atoms (serial) + (soap_calc + gp_predict/scatter of the sample) x %d/%d; "
-              "%d OpenMP threads" % (per_step, N, N, per_step, cores))
+              "%d OpenMP threads; gp_predict products: %s" % (per_step, N, N, per_step, cores, flavour))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak" if CONFIG == "A" else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_dict(n_gpus, N),
@@ -285,6 +303,25 @@ def measure_fp64_peak(torch, dev):
         best = min(best, e0.elapsed_time(e1))
     del a, b
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def measure_cublas_same_shape(torch, dev, nc, d, M):
+    """cuBLAS DGEMM on the covariance stage's own shapes (C = X S^T: nc x M x d, G = A S: nc x d x M), best of 5 each: what the library
+    reaches on THIS problem size (without the fused kernel epilogue), next to the 4096^3 figure."""
+    X = torch.randn(nc, d, dtype=torch.float64, device=dev)
+    S = torch.randn(M, d, dtype=torch.float64, device=dev)
+    A = torch.randn(nc, M, dtype=torch.float64, device=dev)
+    best = [1e30, 1e30]
+    for k, fn in enumerate((lambda: torch.matmul(X, S.t()), lambda: torch.matmul(A, S))):
+        fn()
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            best[k] = min(best[k], e0.elapsed_time(e1))
+    return {"gemm1_ms": best[0], "gemm2_ms": best[1], "pair_tflops": 4.0 * nc * d * M / ((best[0] + best[1]) * 1e-3) / 1e12}
 
 
 DMMA_PROBE_TFLOPS = 37.1  # register-only DMMA loop on a B200 (tools/fp64_pipes.cu, profiles/r01e_fp64_pipes.txt): the pipe's own ceiling
@@ -543,6 +580,12 @@ def leg_static(ctx, args, config, atoms, xml, steps, warmup, with_cpu, full_pari
     if os.path.exists(tpath) and config == "A" and world == 1:
         traffic = json.load(open(tpath)).get("k_dgemm_nt")
     roofline = roofline_block(st, N // world, N, world, SHAPES[config], ctx.fp64_peak, traffic)
+    n_max, l_max, n_spec, M_sp, _ = SHAPES[config]
+    from quip_b200 import synthetic as syn
+    if N // world <= 65536:
+        same = measure_cublas_same_shape(torch, dev, N // world // n_spec, syn.soap_dimension(n_max, l_max, n_spec), M_sp)
+        roofline["cublas_same_shape"] = same
+        roofline["frac_of_cublas_same_shape"] = roofline["cov_pair_tflops"] / same["pair_tflops"]
     roofline["stage_ms_note"] = ("cov_gemm1 / cov_gemm2 / k_dgemm_nt: CUDA events inside the timed region; the other stages: a separate fully "
                                  "instrumented pass of the same steps")
     cpu = cpu_baseline_leg(xml, atoms) if with_cpu else None

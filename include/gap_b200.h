@@ -99,6 +99,9 @@ int gap_potential_connect_stats(const gap_potential* pot, long* n_rebuilds, long
  *                                  A negative variance is an error, as in gp_predict.f95:3877.
  * With a partition active the fetched arrays are this rank's partial sums (the reference's sum_in_place, :545-549). */
 int gap_potential_set_atom_mask(gap_potential* pot, int N, const int* mask /* N logicals; NULL = no mask */);
+/* residue ids of the atoms: the integer Atoms property a distance_2b descriptor names with resid_name= for only_intra / only_inter
+ * (src/GAP/descriptors.f95:1771-1790, 4660-4668, 4735-4738) */
+int gap_potential_set_resid(gap_potential* pot, int N, const int* resid /* N ints; NULL = none */);
 int gap_potential_get_energy_per_coordinate(gap_potential* pot, double* energy_per_coordinate /* n_coordinate */);
 int gap_potential_get_local_gap_variance(gap_potential* pot, int N, double* local_gap_variance /* N */,
                                          double* gap_variance_gradient /* 3*N or NULL */);

@@ -67,13 +67,32 @@ def lib():
         L.orc_model_cutoff.argtypes = [C.c_void_p]
         L.orc_model_add_soap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, c_dp, C.c_double, C.c_double]
         L.orc_model_add_distance_2b.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp,
-                                                c_dp, c_dp, C.c_double, C.c_double, C.c_double]
+                                                c_dp, c_dp, C.c_double, C.c_double, C.c_int, c_dp, c_dp, C.c_int, C.c_double, C.c_int]
+        L.orc_model_set_resid.argtypes = [C.c_void_p, c_ip]
         L.orc_model_calc.argtypes = [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_double, C.c_int, C.c_int, C.c_int,
                                      c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
         L.orc_model_set_extras.argtypes = [C.c_void_p, c_ip, c_dp, c_dp, c_dp, C.c_double]
         L.orc_model_predict.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp]
+        L.orc_set_blas.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
         _LIB = L
     return _LIB
+
+
+def use_openblas(on=True):
+    """Switch the two per-atom products of gp_predict between the oracle's vectorised loops and dgemv from scipy's bundled OpenBLAS
+    (``scipy_dgemv_``; BASELINE.md section 3: the reference links a BLAS).  Returns True when the BLAS flavour is active."""
+    if not on:
+        lib().orc_set_blas(b"", b"", b"")
+        return False
+    import glob
+
+    import scipy
+
+    cands = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))
+    for path in cands:
+        if lib().orc_set_blas(path.encode(), b"scipy_dgemv_", b"scipy_openblas_set_num_threads") == 0:
+            return True
+    return False
 
 
 def _dp(a):
@@ -572,6 +591,7 @@ class Model:
 
     def __init__(self, path=None, xml_string=None, label=None, E_scale=1.0, model=None):
         self.spec = model if model is not None else load_gap_xml(path, xml_string, label)
+        self.resid_names = []  # the resid_name properties the distance_2b coordinates with only_intra / only_inter read
         L = lib()
         self.h = L.orc_model_new()
         e0 = np.ascontiguousarray(self.spec["e0"], dtype=np.float64)
@@ -592,14 +612,29 @@ class Model:
                 assert L.orc_soap_dim(hs) == co["d"], (L.orc_soap_dim(hs), co["d"])
                 L.orc_model_add_soap(self.h, hs, co["M"], _dp(X), _dp(al), _dp(cu), co["delta"], co["zeta"])
             elif kind == "distance_2b":
-                if co["covariance_type"] != 1 or co["n_permutations"] != 1 or co["d"] != 1:
+                a = parse_args(desc)  # distance_2b_initialise, descriptors.f95:1757-1815
+                if co["covariance_type"] != 1 or co["n_permutations"] != 1:
                     raise NotImplementedError("distance_2b variant")
-                a = parse_args(desc)
-                if int(a.get("n_exponents", 1)) != 1 or _f(a.get("exponents", 1)) != 1.0 or int(a.get("tail_exponent", 0)) != 0:
-                    raise NotImplementedError("distance_2b exponents/tail")
+                n_exp = int(a.get("n_exponents", 1))
+                if co["d"] != n_exp or n_exp > 8:
+                    raise NotImplementedError("distance_2b dimensions")
+                if "exponents" in a:
+                    expo = [_f(t) for t in str(a["exponents"]).replace(",", " ").split()]
+                else:
+                    expo = [1.0] if n_exp == 1 else [-float(i) for i in range(1, n_exp + 1)]  # :1808-1812
+                assert len(expo) == n_exp
+                intra, inter = _b(a.get("only_intra", "F")), _b(a.get("only_inter", "F"))
+                if intra and inter:
+                    raise ValueError("distance_2b_initialise: cannot specify both only_inter AND only_intra")
+                if (intra or inter) and "resid_name" not in a:
+                    raise ValueError("distance_2b_initialise: only_intra and only_inter require resid_name to be given as well")
+                self.resid_names.append(a.get("resid_name")) if (intra or inter) else None
+                th = np.ascontiguousarray(co["theta"], dtype=np.float64)
+                ex = np.ascontiguousarray(expo, dtype=np.float64)
                 L.orc_model_add_distance_2b(self.h, _f(a.get("cutoff", 0.0)), _f(a.get("cutoff_transition_width", 0.5)),
                                             int(a.get("Z1", 0)), int(a.get("Z2", 0)), co["M"], _dp(X), _dp(al), _dp(cu),
-                                            co["delta"], co["f0"], float(co["theta"][0]))
+                                            co["delta"], co["f0"], n_exp, _dp(th), _dp(ex), int(a.get("tail_exponent", 0)),
+                                            _f(a.get("tail_range", 1.0)), 1 if intra else (2 if inter else 0))
             else:
                 raise NotImplementedError("descriptor %s" % kind)
 
@@ -621,6 +656,13 @@ class Model:
         gvg = np.zeros((N, 3)) if (local_gap_variance and (force or virial or local_virial)) else None
         if mask is not None or epc is not None or lgv is not None:
             lib().orc_model_set_extras(self.h, _ip(mask), _dp(epc), _dp(lgv), _dp(gvg), float(gap_variance_regularisation))
+        resid = None
+        if self.resid_names:  # (one residue property serves all coordinates here; the reference reads each coordinate's own)
+            arrays = getattr(atoms, "arrays", {})
+            if self.resid_names[0] not in arrays:
+                raise RuntimeError("distance_2b_calc did not find %s property (residue id) in the atoms object." % self.resid_names[0])
+            resid = np.ascontiguousarray(arrays[self.resid_names[0]], dtype=np.int32)
+        lib().orc_model_set_resid(self.h, _ip(resid))
         e = np.zeros(1)
         f = np.zeros((N, 3)) if force else None
         v = np.zeros((3, 3), order="F") if virial else None

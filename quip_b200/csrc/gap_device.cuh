@@ -198,10 +198,18 @@ void launch_energy_rows(const double* epart, int n_tiles_n, const int* centres, 
                         double* local_e, cudaStream_t st, int* launches);
 
 // ---- pair2b.cu -----------------------------------------------------------------------------
+constexpr int PAIR2B_MAX_EXP = 4;
 struct Pair2bDev {
-  double cutoff, ctw, delta2, f02, inv_theta;
+  double cutoff, ctw, delta2, f02;
+  double inv_theta[PAIR2B_MAX_EXP];   // 1 / theta_k
+  double exponents[PAIR2B_MAX_EXP];   // data_k = r^exponents_k (descriptors.f95:4750)
+  int n_exp;
+  int tail_exponent;                  // covariance_cutoff *= (erf(tail_range r) / r)^tail_exponent (:4743-4747)
+  double tail_range;
+  int intra_mode;                     // 0: all pairs, 1: only_intra, 2: only_inter (residue ids, :4735-4738)
+  const int* resid;                   // [N] or NULL
   int Z1, Z2, M;
-  const double* sparseX;  // [M]
+  const double* sparseX;  // [M][n_exp]
   const double* alpha;    // [M]
   const double* scut;     // [M]
 };

@@ -593,12 +593,26 @@ Distance2bSpec distance_2b_from_string(const std::string& desc) {
   s.cutoff_transition_width = a.real("cutoff_transition_width", 0.5);
   s.Z1 = (int)a.integer("Z1", 0);
   s.Z2 = (int)a.integer("Z2", 0);
-  if (a.logical("only_intra", false) || a.logical("only_inter", false))
-    throw GapError("distance_2b only_intra/only_inter are not supported by the B200 path");
-  if (a.integer("n_exponents", 1) != 1 || a.real("exponents", 1.0) != 1.0)
-    throw GapError("distance_2b exponents other than 1 are not supported by the B200 path");
-  if (a.has("tail_exponent") && a.integer("tail_exponent", 0) != 0)
-    throw GapError("distance_2b tail_exponent is not supported by the B200 path");
+  const bool intra = a.logical("only_intra", false), inter = a.logical("only_inter", false);
+  if (intra && inter) throw GapError("distance_2b_initialise: cannot specify both only_inter AND only_intra");
+  if ((intra || inter) && !a.has("resid_name")) throw GapError("distance_2b_initialise: only_intra and only_inter require resid_name to be given as well");
+  s.intra_mode = intra ? 1 : (inter ? 2 : 0);
+  s.resid_name = a.str("resid_name", "");
+  const int n_exp = (int)a.integer("n_exponents", 1);
+  if (n_exp < 1 || n_exp > 4) throw GapError("distance_2b: n_exponents must be 1..4 on the B200 path");
+  if (a.has("exponents")) {
+    std::string t = a.str("exponents", "");
+    for (char& ch : t)
+      if (ch == ',') ch = ' ';
+    s.exponents = parse_reals(t);
+    if ((int)s.exponents.size() != n_exp) throw GapError("distance_2b_initialise: exponents must list n_exponents values");
+  } else if (n_exp == 1) {
+    s.exponents.assign(1, 1.0);
+  } else {  // :1808-1812
+    for (int i = 1; i <= n_exp; i++) s.exponents.push_back(-(double)i);
+  }
+  s.tail_exponent = a.has("tail_exponent") ? (int)a.integer("tail_exponent", 0) : 0;
+  s.tail_range = a.real("tail_range", 1.0);
   return s;
 }
 
@@ -961,10 +975,13 @@ GapModel load_gap_model(const std::string& args_str_in, const std::string& param
     } else if (f[0] == "distance_2b") {
       c.kind = DESC_DISTANCE_2B;
       c.d2b = distance_2b_from_string(desc);
-      if (c.d != 1) throw GapError("distance_2b with dimensions != 1 is not supported by the B200 path");
+      if (c.d != (int)c.d2b.exponents.size())
+        throw GapError("gpCoordinates dimensions=" + std::to_string(c.d) + " does not match distance_2b n_exponents=" + std::to_string(c.d2b.exponents.size()));
       if (c.covariance_type != COVARIANCE_ARD_SE || c.n_permutations != 1)
         throw GapError("distance_2b is supported with covariance_type=ard_se and n_permutations=1 only");
-      if (c.theta[0] == 0.0) throw GapError("gpCoordinates: ard_se covariance with theta = 0");
+      if ((int)c.theta.size() < c.d) throw GapError("gpCoordinates: ard_se covariance needs one theta per dimension");
+      for (int k = 0; k < c.d; k++)
+        if (c.theta[k] == 0.0) throw GapError("gpCoordinates: ard_se covariance with theta = 0");
     } else {
       throw GapError("descriptor '" + f[0] + "' is not supported by the B200 path (soap and distance_2b only)");
     }

@@ -64,6 +64,13 @@ struct SoapSpec {
 struct Distance2bSpec {
   double cutoff = 0, cutoff_transition_width = 0.5;
   int Z1 = 0, Z2 = 0;
+  // descriptors.f95:1771-1815: data = r^exponents (one component per exponent), covariance_cutoff *= (erf(tail_range r) / r)^tail_exponent,
+  // only_intra / only_inter against the residue ids of the atoms (the integer property resid_name)
+  std::vector<double> exponents;  // n_exponents entries
+  int tail_exponent = 0;
+  double tail_range = 1.0;
+  int intra_mode = 0;             // 0: all pairs, 1: only_intra, 2: only_inter
+  std::string resid_name;
 };
 // soap_initialise; calc_xml_version = the xml_version soap_calc would see (<0: descriptor-only default)
 SoapSpec soap_from_string(const std::string& desc, long calc_xml_version);

@@ -30,10 +30,11 @@ __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int
                                                      int scatter, Lattice9 lat, double e_scale,
                                                      int do_grad, double* __restrict__ local_e, double* __restrict__ force,
                                                      double* __restrict__ vir_part, double* __restrict__ local_virial) {
-  __shared__ double sX[64], sA[64], sC[64];
+  __shared__ double sX[64 * PAIR2B_MAX_EXP], sA[64], sC[64];
   __shared__ double svir[WPB][9];
+  const int ne = p.n_exp;
   for (int k = threadIdx.x; k < p.M && k < 64; k += blockDim.x) {
-    sX[k] = p.sparseX[k];
+    for (int q = 0; q < ne; q++) sX[k * ne + q] = p.sparseX[(size_t)k * ne + q];
     sA[k] = p.alpha[k];
     sC[k] = p.scut[k];
   }
@@ -59,14 +60,35 @@ __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int
         int Zj = Z[j];
         bool Zj1 = (p.Z1 == 0) || (Zj == p.Z1), Zj2 = (p.Z2 == 0) || (Zj == p.Z2);
         if (!((Zi1 && Zj2) || (Zi2 && Zj1))) continue;  // :4733
-        // ARD_SE with d = 1 (gp_predict.f95:3795-3816)
+        if (p.intra_mode && p.resid) {  // :4735-4738
+          const bool same = p.resid[i] == p.resid[j];
+          if ((p.intra_mode == 1 && !same) || (p.intra_mode == 2 && same)) continue;
+        }
+        // descriptor data_k = r^exponents_k and d data_k / dr (:4750, 4768); ARD_SE over the n_exp components (gp_predict.f95:3795-3816)
+        double xk[PAIR2B_MAX_EXP], dxk[PAIR2B_MAX_EXP];
+#pragma unroll
+        for (int q = 0; q < PAIR2B_MAX_EXP; q++) {
+          xk[q] = dxk[q] = 0.0;
+          if (q < ne) {
+            if (p.exponents[q] == 1.0) { xk[q] = r; dxk[q] = 1.0; }
+            else { xk[q] = pow(r, p.exponents[q]); dxk[q] = p.exponents[q] * pow(r, p.exponents[q] - 1.0); }
+          }
+        }
         double e = 0.0, g = 0.0;
         for (int s = 0; s < p.M; s++) {
-          double xs = s < 64 ? sX[s] : p.sparseX[s], as = s < 64 ? sA[s] : p.alpha[s], cs = s < 64 ? sC[s] : p.scut[s];
-          double t = (xs - r) * p.inv_theta;
-          double ce = p.delta2 * exp(-0.5 * t * t);
+          const double as = s < 64 ? sA[s] : p.alpha[s], cs = s < 64 ? sC[s] : p.scut[s];
+          double r2 = 0.0, gs = 0.0;
+#pragma unroll
+          for (int q = 0; q < PAIR2B_MAX_EXP; q++)
+            if (q < ne) {
+              const double xs = s < 64 ? sX[s * ne + q] : p.sparseX[(size_t)s * ne + q];
+              const double t = (xs - xk[q]) * p.inv_theta[q];
+              r2 += t * t;
+              gs += t * p.inv_theta[q] * dxk[q];
+            }
+          const double ce = p.delta2 * exp(-0.5 * r2);
           e += as * (ce + p.f02) * cs;
-          g += as * ce * t * p.inv_theta * cs;
+          g += as * ce * gs * cs;
         }
         double fc, dfc;  // coordination_function, linearalgebra.f95:7488-7516
         if (r > p.cutoff - p.ctw) {
@@ -75,6 +97,13 @@ __global__ void __launch_bounds__(WPB * 32) k_pair2b(Pair2bDev p, int first, int
           fc = 0.5 * (cn + 1.0);
           dfc = -0.5 * PI_D * sn / p.ctw;
         } else { fc = 1.0; dfc = 0.0; }
+        if (p.tail_exponent != 0) {  // covariance_cutoff = f_cut tail (:4743-4747, 4759-4764)
+          const double ef = erf(p.tail_range * r);
+          const double tail = pow(ef / r, (double)p.tail_exponent);
+          const double dtail = tail * p.tail_exponent * (2.0 * p.tail_range * exp(-p.tail_range * p.tail_range * r * r) / sqrt(PI_D) / ef - 1.0 / r);
+          dfc = dfc * tail + fc * dtail;
+          fc = fc * tail;
+        }
         if (scatter) {
           e_acc += 0.5 * e * fc;
           if (local_e) atomicAdd(&local_e[j], 0.5 * e_scale * e * fc);

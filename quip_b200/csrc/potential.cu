@@ -117,6 +117,8 @@ struct gap_potential {
   // optional inputs / outputs of the last calc (IPModel_GAP.f95:324-337)
   DevBuf b_mask;               // atom mask (ints) set with gap_potential_set_atom_mask
   int mask_N = -1;
+  DevBuf b_resid;              // residue ids (ints) set with gap_potential_set_resid (distance_2b only_intra / only_inter)
+  int resid_N = -1;
   DevBuf b_epc;                // running sums of local_e after each coordinate -> energy_per_coordinate
   bool epc_valid = false;
   DevBuf b_lgv, b_gvg, b_varflag, b_vc, b_vq, b_vk;  // local_gap_variance[N], gap_variance_gradient[3N], negative-variance flag, work
@@ -727,16 +729,24 @@ void upload_model(gap_potential* P) {
       double zi = std::nearbyint(c.zeta);
       cd.cp.zeta_int = (std::fabs(c.zeta - zi) < 1e-12 * std::fmax(1.0, std::fabs(c.zeta)) && zi >= 0 && zi <= 64) ? (int)zi : -1;
     } else {
-      std::vector<double> xs(c.M > 0 ? c.M : 1, 0.0), al(xs.size(), 0.0), cu(xs.size(), 0.0);
-      for (int m = 0; m < c.M; m++) { xs[m] = c.sparseX[m]; al[m] = c.alpha[m]; cu[m] = c.sparseCutoff[m]; }
+      const int ne = (int)c.d2b.exponents.size();
+      std::vector<double> xs((size_t)(c.M > 0 ? c.M : 1) * ne, 0.0), al(c.M > 0 ? c.M : 1, 0.0), cu(al.size(), 0.0);
+      for (int m = 0; m < c.M; m++) {
+        for (int q = 0; q < ne; q++) xs[(size_t)m * ne + q] = c.sparseX[(size_t)m * ne + q];
+        al[m] = c.alpha[m]; cu[m] = c.sparseCutoff[m];
+      }
       CUDA_OK(cudaMalloc(&cd.x2, xs.size() * sizeof(double)));
-      CUDA_OK(cudaMalloc(&cd.a2, xs.size() * sizeof(double)));
-      CUDA_OK(cudaMalloc(&cd.c2, xs.size() * sizeof(double)));
+      CUDA_OK(cudaMalloc(&cd.a2, al.size() * sizeof(double)));
+      CUDA_OK(cudaMalloc(&cd.c2, al.size() * sizeof(double)));
       CUDA_OK(cudaMemcpy(cd.x2, xs.data(), xs.size() * sizeof(double), cudaMemcpyHostToDevice));
-      CUDA_OK(cudaMemcpy(cd.a2, al.data(), xs.size() * sizeof(double), cudaMemcpyHostToDevice));
-      CUDA_OK(cudaMemcpy(cd.c2, cu.data(), xs.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(cd.a2, al.data(), al.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(cd.c2, cu.data(), al.size() * sizeof(double), cudaMemcpyHostToDevice));
+      memset(&cd.p2, 0, sizeof(cd.p2));
       cd.p2.cutoff = c.d2b.cutoff; cd.p2.ctw = c.d2b.cutoff_transition_width; cd.p2.delta2 = c.delta * c.delta; cd.p2.f02 = c.f0 * c.f0;
-      cd.p2.inv_theta = 1.0 / c.theta[0]; cd.p2.Z1 = c.d2b.Z1; cd.p2.Z2 = c.d2b.Z2; cd.p2.M = c.M;
+      cd.p2.n_exp = ne;
+      for (int q = 0; q < ne; q++) { cd.p2.inv_theta[q] = 1.0 / c.theta[q]; cd.p2.exponents[q] = c.d2b.exponents[q]; }
+      cd.p2.tail_exponent = c.d2b.tail_exponent; cd.p2.tail_range = c.d2b.tail_range; cd.p2.intra_mode = c.d2b.intra_mode; cd.p2.resid = nullptr;
+      cd.p2.Z1 = c.d2b.Z1; cd.p2.Z2 = c.d2b.Z2; cd.p2.M = c.M;
       cd.p2.sparseX = cd.x2; cd.p2.alpha = cd.a2; cd.p2.scut = cd.c2;
     }
     P->cd.push_back(cd);
@@ -917,6 +927,8 @@ void ensure_variance_model(gap_potential* P, size_t ic, double reg, cudaStream_t
     }
   } else {
     if (M > 64) throw GapError("GAP variance for distance_2b coordinates with more than 64 sparse points is not supported by the B200 path");
+    if (c.d2b.exponents.size() != 1 || c.d2b.exponents[0] != 1.0 || c.d2b.tail_exponent != 0 || c.d2b.intra_mode != 0)
+      throw GapError("GAP variance for distance_2b coordinates with exponents / tail / residue options is not supported by the B200 path");
     // ARD_SE, one permutation (:4034-4039), normalisation (:4055-4068), delta^2, f0^2, regularisation (:4070-4075); host, M <= 64
     std::vector<double> K((size_t)M * M), Kinv((size_t)M * M, 0.0);
     const double th = c.theta[0];
@@ -1117,7 +1129,12 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
       }
     } else {
       int nb = 0;
-      launch_pair2b(cd.p2, first, last, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, d_Zc, ca.use_mask ? 1 : 0, lat, es, want_grad ? 1 : 0,
+      Pair2bDev p2 = cd.p2;
+      if (p2.intra_mode) {  // the residue ids are an Atoms property in the reference (resid_name): supplied with gap_potential_set_resid
+        if (P->resid_N != N) throw GapError("distance_2b_calc did not find " + P->model.coord[ic].d2b.resid_name + " property (residue id) in the atoms object (supply it with gap_potential_set_resid)");
+        p2.resid = P->b_resid.as<int>();
+      }
+      launch_pair2b(p2, first, last, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, d_Zc, ca.use_mask ? 1 : 0, lat, es, want_grad ? 1 : 0,
                     d_le, want_grad ? d_force : nullptr, want_grad ? P->b_vir.as<double>() + 9 * slot : nullptr, want_grad ? d_lv : nullptr, st,
                     &launches, &nb);
       if (want_grad) slot += nb;
@@ -1238,7 +1255,7 @@ void gap_potential_finalise(gap_potential* P) {
   DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_slot, &P->b_iota, &P->b_cstart, &P->b_ccount, &P->b_end, &P->b_mask, &P->b_epc, &P->b_lgv, &P->b_gvg, &P->b_varflag, &P->b_vc, &P->b_vq, &P->b_vk, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
-                    &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke, &P->b_lastpos, &P->b_disp};
+                    &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke, &P->b_lastpos, &P->b_disp, &P->b_resid};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : P->ev) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);
@@ -1337,6 +1354,18 @@ int gap_potential_set_atom_mask(gap_potential* P, int N, const int* mask) {
     P->b_mask.ensure(sizeof(int) * (size_t)(N + 1));
     if (N > 0) CUDA_OK(cudaMemcpy(P->b_mask.p, mask, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice));
     P->mask_N = N;
+  });
+}
+
+int gap_potential_set_resid(gap_potential* P, int N, const int* resid) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_set_resid: pot is NULL");
+    if (!resid) { P->resid_N = -1; return; }
+    if (N < 0) throw GapError("gap_potential_set_resid: N < 0");
+    CUDA_OK(cudaSetDevice(P->device));
+    P->b_resid.ensure(sizeof(int) * (size_t)(N + 1));
+    if (N > 0) CUDA_OK(cudaMemcpy(P->b_resid.p, resid, sizeof(int) * (size_t)N, cudaMemcpyHostToDevice));
+    P->resid_N = N;
   });
 }
 

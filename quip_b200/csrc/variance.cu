@@ -110,10 +110,10 @@ __global__ void __launch_bounds__(128) k_pair2b_var(Pair2bDev p, const double* _
     const bool Zj1 = (p.Z1 == 0) || (Zj == p.Z1), Zj2 = (p.Z2 == 0) || (Zj == p.Z2);
     if (!((Zi1 && Zj2) || (Zi2 && Zj1))) continue;  // :4733
     // k_s and grad_k_s (gp_predict.f95:3795-3816)
-    double t0 = (x0 - r) * p.inv_theta, t1 = (x1 - r) * p.inv_theta;
+    double t0 = (x0 - r) * p.inv_theta[0], t1 = (x1 - r) * p.inv_theta[0];
     double e0 = p.delta2 * exp(-0.5 * t0 * t0), e1 = p.delta2 * exp(-0.5 * t1 * t1);
     double k0 = s0i < M ? (e0 + p.f02) * c0 : 0.0, k1 = s1i < M ? (e1 + p.f02) * c1 : 0.0;
-    double g0 = s0i < M ? e0 * t0 * p.inv_theta * c0 : 0.0, g1 = s1i < M ? e1 * t1 * p.inv_theta * c1 : 0.0;
+    double g0 = s0i < M ? e0 * t0 * p.inv_theta[0] * c0 : 0.0, g1 = s1i < M ? e1 * t1 * p.inv_theta[0] * c1 : 0.0;
     double q0 = 0.0, q1 = 0.0;  // (k_mm^-1 k)_s
     for (int t = 0; t < M; t++) {
       const double kt = __shfl_sync(0xffffffffu, t < 32 ? k0 : k1, t & 31);

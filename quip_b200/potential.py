@@ -39,6 +39,7 @@ ABI = {
     "gap_potential_connect_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "gap_potential_calc": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "gap_potential_set_atom_mask": (C.c_int, [C.c_void_p, C.c_int, c_ip]),
+    "gap_potential_set_resid": (C.c_int, [C.c_void_p, C.c_int, c_ip]),
     "gap_potential_get_energy_per_coordinate": (C.c_int, [C.c_void_p, c_dp]),
     "gap_potential_get_local_gap_variance": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp]),
     "gap_potential_calc_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, c_dp, c_ip, C.c_char_p, C.c_int,
@@ -235,6 +236,10 @@ class Potential:
                 raise RuntimeError("IPModel_GAP_Calc did not find %s property in the atoms object." % opts["atom_mask_name"])
             mask = np.ascontiguousarray(np.asarray(arrays[opts["atom_mask_name"]]).astype(bool).astype(np.int32))
             _check(lib.gap_potential_set_atom_mask(self._h, N, _ip(mask)))
+        arrays = getattr(atoms, "arrays", None)
+        if arrays and "resid" in arrays:  # residue ids for distance_2b only_intra / only_inter (the property the descriptor's resid_name names)
+            rid = np.ascontiguousarray(arrays["resid"], dtype=np.int32)
+            _check(lib.gap_potential_set_resid(self._h, N, _ip(rid)))
         _check(lib.gap_potential_calc(self._h, N, _dp(pos), _ip(Z), _dp(lat), _ip(pbc), full_args.encode(), _dp(e),
                                       _dp(le), _dp(f), _dp(v), _dp(lv)))
         out = {"energy": float(e[0])}

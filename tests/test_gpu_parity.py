@@ -832,3 +832,33 @@ def test_md_with_skin_matches_rebuild_every_step(tmp_path):
     assert np.abs(ep1 - ep2).max() < 1e-8 * len(atoms)
     st = p2.connect_stats()
     assert st["reuses"] > 20 and st["rebuilds"] >= 1 and st["rebuilds"] + st["reuses"] == 31, st
+
+
+# ----------------------------------------------------------------------------------------------------
+# distance_2b options (descriptors.f95:1757-1815, 4735-4764): exponents, tail, only_intra / only_inter
+# ----------------------------------------------------------------------------------------------------
+def _d2b_variant_model(tmpdir, seed=5):
+    rng = np.random.default_rng(seed)
+    def coord(desc, d, M=9):
+        return {"descriptor": desc, "covariance_type": 1, "delta": 0.7, "f0": 0.05, "theta": list(rng.uniform(0.3, 1.2, size=d)),
+                "sparseX": rng.uniform(0.05, 1.0, size=(M, d)) if d > 1 else np.linspace(1.2, 4.5, M).reshape(M, 1),
+                "alpha": rng.normal(0.0, 0.2, size=M), "sparseCutoff": rng.uniform(0.6, 1.0, size=M)}
+    coords = [coord("distance_2b cutoff=4.5 cutoff_transition_width=0.8 Z1=23 Z2=41 n_exponents=3 exponents={-1 -2 -4}", 3),
+              coord("distance_2b cutoff=5.0 Z1=42 Z2=0 tail_exponent=2 tail_range=0.7", 1),
+              coord("distance_2b cutoff=4.0 Z1=0 Z2=0 n_exponents=2 tail_exponent=1 tail_range=1.3 only_inter resid_name=resid", 2),
+              coord("distance_2b cutoff=4.0 Z1=0 Z2=0 only_intra resid_name=resid", 1)]
+    return write_gap_xml(os.path.join(tmpdir, "d2b_variants.xml"), coords, e0={23: 0.1, 41: -0.2, 42: 0.3, 73: 0.4})
+
+
+def test_distance_2b_options_vs_oracle(golden, tmp_path):
+    xml = _d2b_variant_model(str(tmp_path))
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    for pbc in (True, False):
+        for a in quad_datasets(golden, pbc):
+            resid = np.arange(len(a)) // 2
+            am = Atoms(a.numbers, a.positions, a.cell, pbc, arrays={"resid": resid})
+            check_efv(pot, om, am)
+    # the residue property is mandatory for only_intra / only_inter (:4660-4668)
+    fresh = Potential("", param_filename=xml)
+    with pytest.raises(RuntimeError, match="residue id"):
+        fresh.calc(quad_datasets(golden, True)[0])

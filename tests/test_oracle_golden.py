@@ -183,3 +183,36 @@ def test_soap_reference_data_all_variants(golden):
         assert np.abs(outs[0]["grad_data"][gp] - z["G_%d" % i]).max() < 1e-9, (i, qs)
         n += 1
     assert n == 66
+
+
+def test_distance_2b_options_finite_difference(golden, tmp_path):
+    """distance_2b exponents / tail / only_intra / only_inter (descriptors.f95:1757-1815, 4735-4764) have no golden numbers in the
+    reference tree (parity unpinned at that level): the restatement is checked by central finite differences of its own energy, and
+    against the plain distance_2b path (pinned by tests/GAP.xml) in the limit exponents = 1, no tail."""
+    from quip_b200.gap_xml import write_gap_xml
+    rng = np.random.default_rng(3)
+    S = json.load(open(os.path.join(golden, "soap_reference_cases.json")))["datasets"]["quad_3"][0]
+    a = Atoms(S["numbers"], np.array(S["scaled_positions"]) @ np.array(S["cell"]), S["cell"], True, arrays={"resid": np.arange(6) // 2})
+    def coord(desc, d, M=7):
+        return {"descriptor": desc, "covariance_type": 1, "delta": 0.7, "f0": 0.05, "theta": list(rng.uniform(0.3, 1.2, size=d)),
+                "sparseX": rng.uniform(0.05, 1.0, size=(M, d)), "alpha": rng.normal(0.0, 0.2, size=M), "sparseCutoff": np.ones(M)}
+    xml = write_gap_xml(str(tmp_path / "v.xml"), [coord("distance_2b cutoff=4.5 Z1=0 Z2=0 n_exponents=2 exponents={-1 -3} tail_exponent=2 tail_range=0.8", 2),
+                                                   coord("distance_2b cutoff=4.0 Z1=0 Z2=0 only_inter resid_name=resid", 1)])
+    om = orc.Model(xml)
+    r = om.calc(a)
+    h = 1e-5
+    for j, k in ((0, 0), (3, 2), (5, 1)):
+        e = []
+        for sgn in (1, -1):
+            p = a.positions.copy()
+            p[j, k] += sgn * h
+            e.append(om.calc(Atoms(a.numbers, p, a.cell, True, arrays=a.arrays), force=False, virial=False)["energy"])
+        assert abs((e[0] - e[1]) / (2 * h) + r["force"][j, k]) < 1e-7 * max(1.0, np.abs(r["force"]).max())
+    # only_inter + only_intra with the same parameters add up to the unrestricted coordinate
+    base = coord("distance_2b cutoff=4.0 Z1=0 Z2=0", 1)
+    parts = []
+    for extra in ("", " only_intra resid_name=resid", " only_inter resid_name=resid"):
+        c = dict(base, descriptor=base["descriptor"] + extra)
+        parts.append(orc.Model(write_gap_xml(str(tmp_path / "p.xml"), [c])).calc(a))
+    assert abs(parts[1]["energy"] + parts[2]["energy"] - parts[0]["energy"]) < 1e-10
+    assert np.abs(parts[1]["force"] + parts[2]["force"] - parts[0]["force"]).max() < 1e-11
