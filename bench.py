@@ -527,12 +527,17 @@ def leg_static(ctx, args, config, atoms, xml, steps, warmup, with_cpu, full_pari
     # ---- the other stages' times, for the record: a separate instrumented pass (every stage event adds ~1 us to the step) ----
     pot.set_timing(1)
     stage_diag = {}
+    red_wait, red_sum = [], []
     for k in range(steps):
         flush.zero_()
         sp.calc_resident_enqueue(N, d_pos, d_Z, lat, pbc, d_packed, want_grad=True)
         assert sp.calc_resident_finish()
         for name, ms in pot.last_timings().items():
             stage_diag[name] = stage_diag.get(name, 0.0) + ms
+        if world > 1 and not ctx.real_world == 1:
+            ci = pot.comm_info()  # %globaltimer stamps of this step's peer reduction: wait for the other ranks' partials / sum phase
+            red_wait.append(ci["last_wait_us"])
+            red_sum.append(ci["last_sum_us"])
     for name in stage_diag:
         if name not in ("cov_gemm1", "cov_gemm2"):
             stage_sum[name] = stage_diag[name]
@@ -555,6 +560,12 @@ def leg_static(ctx, args, config, atoms, xml, steps, warmup, with_cpu, full_pari
     e2e_value = N * steps / ctx.max_over_ranks(time.perf_counter() - t0)
     assert abs(r["energy"] - resident[0]) <= 1e-9 * abs(resident[0]), (r["energy"], resident[0])
     transport = pot.comm_info()["transport"]
+    reduction = {"transport": transport}
+    if red_wait:
+        reduction.update(wait_us_mean_over_steps_max_over_ranks=ctx.max_over_ranks(float(np.mean(red_wait))),
+                         sum_phase_us_mean_over_steps_max_over_ranks=ctx.max_over_ranks(float(np.mean(red_sum))),
+                         note="peer-memory kernel, %globaltimer: wait = time between this rank's partial being ready and the last rank's "
+                              "(the skew of the ranks' evaluations, not transfer time); sum = reading the partials of all ranks over NVLink")
 
     # ---- parity of the benchmarked configuration (rank 0; the other ranks wait) ----
     parity = None
@@ -593,7 +604,7 @@ def leg_static(ctx, args, config, atoms, xml, steps, warmup, with_cpu, full_pari
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 28 * N, "d2h_bytes_per_step": 8 * (10 + 3 * N),
                    "note": "per rank: H2D of all positions + Z from page-locked memory; D2H of E + virial on every rank, of all forces on rank 0"},
            "gpu_launches": int(launches), "roofline": roofline, "wall_s_timed_region": t_wall, "energy_eV": float(resident[0]),
-           "reduction_transport": transport}
+           "reduction_transport": transport, "reduction": reduction}
     if parity is not None:
         out["parity"] = parity
     if cpu is not None:
@@ -725,7 +736,7 @@ def run_b200(args):
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak" if CONFIG == "A" else "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config_dict(n_gpus, N), "clocks": head["clocks"], "e2e": head["e2e"],
                 "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "wall_s_timed_region": head["wall_s_timed_region"],
-                "energy_eV": head["energy_eV"], "reduction_transport": head["reduction_transport"]}
+                "energy_eV": head["energy_eV"], "reduction_transport": head["reduction_transport"], "reduction": head["reduction"]}
         for k in ("parity", "cpu_baseline"):
             if k in head:
                 line[k] = head[k]

@@ -87,11 +87,12 @@ struct PeerPtrs {
 // The partial buffers alternate between steps, so a fast rank can start writing step s+1 while a slow one still reads step s;
 // it cannot reach step s+2 (same buffer again) before every rank has signalled s+1, i.e. has left the kernel of step s.
 __global__ void __launch_bounds__(256) k_peer_allreduce(PeerPtrs peers, int rank, int n, unsigned step, size_t buf_off, size_t count,
-                                                        double* __restrict__ result, int* __restrict__ err) {
+                                                        double* __restrict__ result, int* __restrict__ err, unsigned long long* __restrict__ stamps) {
   __shared__ int timed_out;
   pdl_launch_dependents();
   if (threadIdx.x == 0) timed_out = 0;
   pdl_wait();  // this rank's partial is complete and visible
+  if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(stamps[0]));  // partial ready (ns)
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x < n) {
     unsigned* f = reinterpret_cast<unsigned*>(peers.base[threadIdx.x]) + rank;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerPtrs peers, int rank
     }
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(stamps[1]));  // every rank's partial ready
   if (timed_out) {
     if (threadIdx.x == 0) {  // err lives in mapped host memory: the host reads it after its synchronisation
       *(volatile int*)err = 1;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerPtrs peers, int rank
     for (int r = 0; r < n; r++) s += __ldcg(reinterpret_cast<const double*>(peers.base[r] + buf_off) + (count - 1));
     result[count - 1] = s;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(stamps[2]));  // block 0 done (a sample of the sum phase)
 }
 
 }  // namespace
@@ -159,6 +162,7 @@ struct GapComm {
   bool partial_is_peer = false;     // the partial of the step in flight lives in block (else: in the result buffer)
   int* d_err = nullptr;             // device address of h_err
   int* h_err = nullptr;             // pinned + mapped: set by the peer kernel if it timed out
+  unsigned long long* d_stamps = nullptr;  // [3] globaltimer of the last peer reduction: own partial ready, all partials ready, done
   char* d_handles = nullptr;        // [n + 1] x 64 bytes (slot n: this rank's handle, the send buffer)
   int* d_okflag = nullptr;
   const char* last = "none";
@@ -193,6 +197,8 @@ GapComm* comm_create(const char* id128, int rank, int n_ranks, int device) {
     CUDA_OK(cudaHostGetDevicePointer((void**)&c->d_err, c->h_err, 0));
     CUDA_OK(cudaMalloc(&c->d_handles, (size_t)(n_ranks + 1) * sizeof(cudaIpcMemHandle_t)));
     CUDA_OK(cudaMalloc(&c->d_okflag, sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->d_stamps, 3 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemset(c->d_stamps, 0, 3 * sizeof(unsigned long long)));
   } catch (...) {
     comm_destroy(c);
     throw;
@@ -218,6 +224,7 @@ void comm_destroy(GapComm* c) {
   if (c->comm) nccl().CommDestroy(c->comm);
   cudaFree(c->d_handles);
   cudaFree(c->d_okflag);
+  cudaFree(c->d_stamps);
   if (c->h_err) cudaFreeHost(c->h_err);
   delete c;
 }
@@ -225,6 +232,14 @@ void comm_destroy(GapComm* c) {
 int comm_rank(const GapComm* c) { return c ? c->rank : 0; }
 int comm_size(const GapComm* c) { return c ? c->n : 1; }
 const char* comm_last_transport(const GapComm* c) { return c ? c->last : "none"; }
+void comm_last_stamps(const GapComm* c, double* wait_us, double* sum_us) {
+  *wait_us = *sum_us = 0.0;
+  if (!c || !c->d_stamps) return;
+  unsigned long long t[3] = {0, 0, 0};
+  if (cudaMemcpy(t, c->d_stamps, sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  if (t[1] >= t[0]) *wait_us = (double)(t[1] - t[0]) * 1e-3;
+  if (t[2] >= t[1]) *sum_us = (double)(t[2] - t[1]) * 1e-3;
+}
 long comm_launch_count(const GapComm* c) { return c ? c->launches : 0; }
 
 // (Re)allocate the peer-visible block for `count` doubles per buffer and map every other rank's block.  Collective.
@@ -294,7 +309,7 @@ void comm_allreduce_packed(GapComm* c, size_t count, double* result, cudaStream_
     int blocks = (int)((count / 2 + 255) / 256);
     if (blocks > 2 * c->n_sm) blocks = 2 * c->n_sm;
     if (blocks < 1) blocks = 1;
-    launch_pdl(k_peer_allreduce, dim3(blocks), dim3(256), 0, st, pp, c->rank, c->n, c->step, buf_off, count, result, c->d_err);
+    launch_pdl(k_peer_allreduce, dim3(blocks), dim3(256), 0, st, pp, c->rank, c->n, c->step, buf_off, count, result, c->d_err, c->d_stamps);
     c->last = "p2p";
   } else {
     nccl_ok(nccl().AllReduce(result, result, count, ncclFloat64, ncclSum, c->comm, st), "ncclAllReduce");

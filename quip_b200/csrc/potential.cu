@@ -1317,6 +1317,13 @@ int gap_potential_set_comm(gap_potential* P, const char* id, int rank, int n_ran
   });
 }
 
+int gap_potential_comm_timing(const gap_potential* P, double* wait_us, double* sum_us) {
+  if (!P || !wait_us || !sum_us) return 1;
+  cudaSetDevice(P->device);
+  comm_last_stamps(P->comm, wait_us, sum_us);
+  return 0;
+}
+
 int gap_potential_comm_info(const gap_potential* P, int* rank, int* n_ranks, char* transport, size_t n) {
   if (!P) return 1;
   if (rank) *rank = P->rank;

@@ -13,6 +13,9 @@ module gap_b200_iface
   public :: gap_potential_calc, gap_potential_set_partition, gap_last_error, gap_b200_error_string
   public :: gap_potential_set_atom_mask, gap_potential_get_energy_per_coordinate, gap_potential_get_local_gap_variance
   public :: gap_potential_set_timing, gap_potential_last_timings, gap_md_run
+  public :: gap_comm_get_unique_id, gap_potential_set_comm, gap_potential_set_cutoff_skin, gap_potential_set_resid, GAP_COMM_ID_BYTES
+
+  integer, parameter :: GAP_COMM_ID_BYTES = 128
 
   interface
      ! int gap_potential_initialise(gap_potential** pot, const char* args_str, const char* param_str, const char* base_dir, int device)
@@ -44,6 +47,34 @@ module gap_b200_iface
        import :: c_ptr, c_int
        type(c_ptr), value :: pot
        integer(c_int), value :: rank, n_ranks
+       integer(c_int) :: ierr
+     end function
+     ! the reduction over ranks inside the library (replaces sum_in_place, IPModel_GAP.f95:538-556): rank 0 creates the id, the host
+     ! broadcasts its 128 bytes (MPI_Bcast), every rank joins; from then on calc returns totals on every rank
+     function gap_comm_get_unique_id(id) bind(C, name="gap_comm_get_unique_id") result(ierr)
+       import :: c_char, c_int
+       character(kind=c_char), intent(out) :: id(128)
+       integer(c_int) :: ierr
+     end function
+     function gap_potential_set_comm(pot, id, rank, n_ranks) bind(C, name="gap_potential_set_comm") result(ierr)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr), value :: pot
+       character(kind=c_char), intent(in) :: id(128)
+       integer(c_int), value :: rank, n_ranks
+       integer(c_int) :: ierr
+     end function
+     ! at%cutoff_skin (Connection.f95:1085-1128): neighbour list built to cutoff + skin, reused while max displacement < skin / 2
+     function gap_potential_set_cutoff_skin(pot, cutoff_skin) bind(C, name="gap_potential_set_cutoff_skin") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: pot
+       real(c_double), value :: cutoff_skin
+       integer(c_int) :: ierr
+     end function
+     ! residue ids for distance_2b only_intra / only_inter (the integer property named by resid_name, descriptors.f95:4660-4668)
+     function gap_potential_set_resid(pot, n, resid) bind(C, name="gap_potential_set_resid") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: pot, resid       ! resid: c_loc of integer(c_int) resid(n), or c_null_ptr
+       integer(c_int), value :: n
        integer(c_int) :: ierr
      end function
      ! optional inputs / outputs the reference keeps in the Atoms object (IPModel_GAP.f95:324-337, 558-573)
@@ -176,9 +207,15 @@ end module gap_b200_iface
 !      call check_size('Local_virial', local_virial, (/9, at%N/), 'IPModel_GAP_Calc', error); plv = c_loc(local_virial)
 !   end if
 !   pbc = merge(1, 0, at%is_periodic)
-!   if (present(mpi)) then                                    ! the reference's atom mask (descriptors.f95:1036-1051)
-!      if (mpi%active) ierr = gap_potential_set_partition(this%b200, mpi%my_proc, mpi%n_procs)
+!   if (present(mpi)) then                                    ! the reference's atom mask (descriptors.f95:1036-1051) + its reduction
+!      if (mpi%active .and. .not. this%b200_comm_set) then    ! once per potential: NCCL communicator over the ranks' GPUs
+!         if (mpi%my_proc == 0) ierr = gap_comm_get_unique_id(comm_id)
+!         call bcast(mpi, comm_id)                            ! MPI_Bcast of the 128 bytes (MPI_context.f95)
+!         ierr = gap_potential_set_comm(this%b200, comm_id, mpi%my_proc, mpi%n_procs)
+!         this%b200_comm_set = .true.
+!      end if
 !   end if
+!   ierr = gap_potential_set_cutoff_skin(this%b200, at%cutoff_skin)
 !   if (has_atom_mask_name) then                              ! :344-346: the logical property becomes an integer mask
 !      imask = merge(1_c_int, 0_c_int, atom_mask_pointer)
 !      ierr = gap_potential_set_atom_mask(this%b200, at%N, c_loc(imask))
@@ -196,13 +233,8 @@ end module gap_b200_iface
 !      call add_property(at, "gap_variance_gradient", 0.0_dp, n_cols=3, ptr2=gap_variance_gradient_pointer)
 !      ierr = gap_potential_get_local_gap_variance(this%b200, at%N, local_gap_variance_pointer, c_loc(gap_variance_gradient_pointer))
 !   end if
-!   if (present(mpi)) then                                    ! IPModel_GAP.f95:538-556, unchanged
-!      if (mpi%active) then
-!         if (present(f)) call sum_in_place(mpi, f)
-!         if (present(virial)) call sum_in_place(mpi, virial)
-!         if (present(local_virial)) call sum_in_place(mpi, local_virial)
-!         if (present(e)) e = sum(mpi, e)
-!         if (present(local_e)) call sum_in_place(mpi, local_e)
-!      end if
-!   end if
+!   ! IPModel_GAP.f95:538-556 (sum_in_place(mpi, f / virial / local_virial / local_e), e = sum(mpi, e)) is GONE: with the communicator
+!   ! set, e, f, virial, local_e and local_virial come back from gap_potential_calc already summed over the ranks (one reduction of
+!   ! the packed [E | virial | F] buffer on the GPUs, over NVLink).  Only the optional energy_per_coordinate / local_gap_variance
+!   ! arrays are still per-rank partial sums and keep their sum_in_place calls (:545-549).
 ! end subroutine

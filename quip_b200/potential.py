@@ -35,6 +35,7 @@ ABI = {
     "gap_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "gap_potential_set_comm": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "gap_potential_comm_info": (C.c_int, [C.c_void_p, c_ip, c_ip, C.c_char_p, C.c_size_t]),
+    "gap_potential_comm_timing": (C.c_int, [C.c_void_p, c_dp, c_dp]),
     "gap_potential_set_cutoff_skin": (C.c_int, [C.c_void_p, C.c_double]),
     "gap_potential_connect_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "gap_potential_calc": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
@@ -207,7 +208,9 @@ class Potential:
         r, n = C.c_int(0), C.c_int(1)
         buf = C.create_string_buffer(16)
         load_library().gap_potential_comm_info(self._h, C.byref(r), C.byref(n), buf, len(buf))
-        return {"rank": r.value, "n_ranks": n.value, "transport": buf.value.decode()}
+        w, t = C.c_double(0.0), C.c_double(0.0)
+        load_library().gap_potential_comm_timing(self._h, C.byref(w), C.byref(t))
+        return {"rank": r.value, "n_ranks": n.value, "transport": buf.value.decode(), "last_wait_us": w.value, "last_sum_us": t.value}
 
     def calc(self, atoms, energy=True, force=False, virial=False, local_energy=False, local_virial=False, args_str="", out_force=None):
         """``calc(pot, at, energy, force, virial, local_energy, local_virial, args_str)`` (Potential.f95:803).

@@ -15,6 +15,8 @@ for path in sys.argv[1:]:
     if "roofline" in j:
         r = j["roofline"]
         print("  stage_ms", r["stage_ms"], "frac %.4f of cuBLAS %.2f TF, %.4f of DMMA probe" % (r["frac"], r["fp64_dgemm_tflops_measured"], r.get("frac_of_dmma_probe", 0)))
+    if "reduction" in j:
+        print("  reduction", {k: v for k, v in j["reduction"].items() if k != "note"})
     if "parity" in j:
         print("  parity", j["parity"])
     if "cpu_baseline" in j:
