@@ -18,7 +18,8 @@ parity  : the GPU result of the benchmarked configuration against the oracle's w
           against the oracle's, and at N > 1 the reduced result against an unpartitioned evaluation on rank 0's GPU.  The run FAILS
           if the north-star tolerances are exceeded (1e-8 eV/atom, 1e-6 eV/A, 1e-6 eV).
 named_configs: BASELINE configs[3] (C: 262,144-atom amorphous carbon, MD with the list rebuilt every step, strong scaling) at every
-          N and configs[4] (D: 1,048,576-atom Si slab, E/F/V sharded) at N = 1 and 8, measured in the same process.
+          N, configs[4] (D: 1,048,576-atom Si slab, E/F/V sharded) at N = 1 and 8, configs[2] (B: SiC, distance_2b + SOAP) at N = 1,
+          measured in the same process.
 cpu_baseline / --impl reference: the CPU restatement of QUIP's algorithm (oracle/, OpenMP over atoms) on the host cores.
 """
 import argparse
@@ -397,7 +398,7 @@ def pinned_atoms(atoms):
     return Atoms(pinned_copy(np.asarray(atoms.numbers, dtype=np.int32)), pinned_copy(np.asarray(atoms.positions, dtype=np.float64)), atoms.cell, atoms.pbc)
 
 
-def parity_block(atoms, xml, reduced, device, world, check_list=True, sample=None):
+def parity_block(atoms, xml, reduced, device, world, check_list=True, sample=None, soap_only=False):
     """Rank 0: the benchmarked configuration against the oracle (whole evaluation, or `sample` centres' local energies when the whole
     one is out of reach), the neighbour list against the oracle's, and the reduced N-rank result against an unpartitioned evaluation."""
     from oracle import oracle as orc
@@ -406,7 +407,13 @@ def parity_block(atoms, xml, reduced, device, world, check_list=True, sample=Non
     N = len(atoms)
     out = {}
     t0 = time.perf_counter()
-    om = orc.Model(xml)
+    if soap_only:  # distance_2b splits each pair's energy between both ends, so its partial local energies are not comparable centre by
+        # centre when the oracle only visits a sample of centres: compare the SOAP coordinates' share (the GPU side sums only_descriptor runs)
+        spec = orc.load_gap_xml(xml)
+        spec["coordinates"] = [c for c in spec["coordinates"] if c["descriptor"].split()[0] == "soap"]
+        om = orc.Model(model=spec)
+    else:
+        om = orc.Model(xml)
     if sample is None:
         o = om.calc(atoms, force=True, virial=True, nthreads=host_threads())
         out.update(dE_per_atom=abs(reduced["energy"] - o["energy"]) / N, max_dF=float(np.abs(reduced["force"] - o["force"]).max()),
@@ -440,6 +447,14 @@ def parity_block(atoms, xml, reduced, device, world, check_list=True, sample=Non
     out["ok"] = bool(ok)
     out["seconds"] = round(time.perf_counter() - t0, 2)
     return out
+
+
+def _e0_of(atoms, xml):
+    """per-atom e0 of the model (every only_descriptor run adds it once)"""
+    from oracle import oracle as orc
+
+    e0 = orc.load_gap_xml(xml)["e0"]
+    return np.array([e0[int(z)] for z in atoms.numbers])
 
 
 def roofline_block(st, nc, N, world, shape, fp64_peak, traffic=None):
@@ -574,10 +589,16 @@ def leg_static(ctx, args, config, atoms, xml, steps, warmup, with_cpu, full_pari
             if rank == 0:
                 parity = parity_block(atoms, xml, r, ctx.local, world)
         else:  # sample of centres: local energies, reduced over the ranks inside the library (collective call on every rank)
-            rl = pot.calc(hat, local_energy=True)
+            soap_only = config == "B"
+            if soap_only:  # SOAP coordinates only (see parity_block): sum of the only_descriptor runs; every run adds e0 once
+                ks = [k + 1 for k in range(pot.n_coordinate) if k >= 3]
+                runs = [pot.calc(hat, local_energy=True, args_str="only_descriptor=%d" % k)["local_energy"] for k in ks]
+                rl = {"local_energy": sum(runs) - (len(runs) - 1) * _e0_of(atoms, xml)}
+            else:
+                rl = pot.calc(hat, local_energy=True)
             if rank == 0:
-                first = min(N - 8, 70000)
-                parity = parity_block(atoms, xml, rl, ctx.local, world, check_list=False, sample=(first, first + 8))
+                first = min(N - 8, 70000 if config == "D" else 5000)
+                parity = parity_block(atoms, xml, rl, ctx.local, world, check_list=False, sample=(first, first + 8), soap_only=soap_only)
         ctx.barrier()
     sp.pot.finalise()
     del d_pos, d_Z, d_packed
@@ -715,10 +736,20 @@ def run_b200(args):
         want = "none"
     do_C = want in ("C", "all") or want == "auto"
     do_D = want in ("D", "all") or (want == "auto" and n_gpus in (1, 8))
+    do_B = want in ("B", "all") or (want == "auto" and n_gpus == 1)
     if do_C:
         buildC = descriptor_builder(local, "C")
         atomsC, xmlC = ctx.build_shared("named_C", lambda d: buildC(d, n_gpus))
         named["C_md"] = leg_md(ctx, atomsC, xmlC, args.md_steps)
+    if do_B:  # BASELINE configs[2]: SiC, 2 species, 3 x distance_2b + one SOAP (n_max=10 l_max=6, 4,000 sparse points) per centre species
+        buildB = descriptor_builder(local, "B")
+        atomsB, xmlB = ctx.build_shared("named_B", lambda d: buildB(d, n_gpus))
+        b_leg = leg_static(ctx, args, "B", atomsB, xmlB, 5, 3, with_cpu=False, full_parity=False)
+        if rank == 0:
+            named["B"] = {"workload": workload_name(n_gpus, "B"), "n_gpus": n_gpus, "atoms": len(atomsB), "steps": 5,
+                          "ms_per_step": b_leg["ms_per_step"], "atoms_per_s": b_leg["value"], "e2e_atoms_per_s": b_leg["e2e"]["value"],
+                          "roofline": b_leg["roofline"], "reduction_transport": b_leg["reduction_transport"], "parity": b_leg.get("parity"),
+                          "gpu_launches": b_leg["gpu_launches"]}
     if do_D:
         buildD = descriptor_builder(local, "D")
         atomsD, xmlD = ctx.build_shared("named_D", lambda d: buildD(d, n_gpus))
@@ -778,8 +809,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the benchmarked configuration (profiling runs)")
-    ap.add_argument("--named-configs", default="auto", choices=["auto", "none", "C", "D", "all"],
-                    help="auto: config C MD at every N, config D at N = 1 and 8; none: headline only")
+    ap.add_argument("--named-configs", default="auto", choices=["auto", "none", "B", "C", "D", "all"],
+                    help="auto: config C MD at every N, config D at N = 1 and 8, config B at N = 1; none: headline only")
     ap.add_argument("--md-steps", type=int, default=12, help="MD steps of the config C leg")
     ap.add_argument("--emulate-world", type=int, default=0, help="profiling aid (1 GPU): run rank 0's share of a W-rank weak-scaling step, no reduction")
     ap.add_argument("--config", default="A", choices=["A", "B", "C", "D"], help="A = the bench line; B/C/D = the other BASELINE shapes (exploration)")

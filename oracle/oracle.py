@@ -53,6 +53,9 @@ def lib():
                                    C.c_double, C.c_int, C.c_int, c_ip, C.c_int, c_ip, C.c_int, C.c_int, C.c_double,
                                    C.c_double, C.c_double]
         L.orc_soap_set_general.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, C.c_int, c_dp, C.c_int, c_dp, C.c_int, c_ip, c_ip, c_dp]
+        L.orc_soap_set_global.argtypes = [C.c_void_p, C.c_int]
+        L.orc_soap_is_global.argtypes = [C.c_void_p]
+        L.orc_soap_calc_global.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_int, c_ip, c_dp, c_ip, c_dp, c_ip, c_dp, c_ip]
         L.orc_soap_free.argtypes = [C.c_void_p]
         L.orc_soap_dim.argtypes = [C.c_void_p]
         L.orc_soap_get_basis.argtypes = [C.c_void_p, c_dp, c_dp, c_dp]
@@ -195,8 +198,7 @@ def soap_params(desc_str, calc_xml_version=None):
     if not has_cras and p["n_species"] == 1:
         p["central_reference_all_species"] = True
     p["Z"] = _ilist(a.get("Z", "0")) if p["n_Z"] > 1 else [int(str(a.get("Z", "0")).split()[0])]
-    if _b(a.get("average", "F")):
-        raise NotImplementedError("soap average=T (one global descriptor per configuration) is outside the oracle's scope")
+    p["global"] = _b(a.get("average", "F"))  # average=T: ONE descriptor per configuration from the summed density expansions (:2516)
     # ---- compression modes and radial bases (descriptors.f95:2529-2537): handled by the general path ----
     p["diagonal_radial"] = _b(a.get("diagonal_radial", "F"))
     p["Z_mix"], p["R_mix"], p["sym_mix"] = _b(a.get("Z_mix", "F")), _b(a.get("R_mix", "F")), _b(a.get("sym_mix", "F"))
@@ -207,7 +209,7 @@ def soap_params(desc_str, calc_xml_version=None):
     p["radial_basis"] = a.get("radial_basis", "") or "EQUISPACED_GAUSS"
     if p["radial_basis"] not in ("EQUISPACED_GAUSS", "GTO", "POLY"):
         raise ValueError("soap_initialise: radial_basis not recognised: EQUISPACED_GAUSS, POLY or GTO")
-    p["general"] = (p["diagonal_radial"] or p["Z_mix"] or p["R_mix"] or p["sym_mix"] or not p["coupling"] or p["nu_R"] != 2 or p["nu_S"] != 2
+    p["general"] = (p["global"] or p["diagonal_radial"] or p["Z_mix"] or p["R_mix"] or p["sym_mix"] or not p["coupling"] or p["nu_R"] != 2 or p["nu_S"] != 2
                     or bool(p["Z_map"]) or p["radial_basis"] != "EQUISPACED_GAUSS")
     cv = 1423143769 if calc_xml_version is None else calc_xml_version
     p["do_two_l_plus_one"] = cv >= 1423143769
@@ -433,6 +435,7 @@ def new_soap(p):
         jb = np.array([q[1] for q in pairs], dtype=np.int32)
         fac = np.array([q[2] for q in pairs], dtype=np.float64)
         lib().orc_soap_set_general(h, len(r), _dp(r), _dp(P), _dp(c0), W1.shape[1], _dp(W1), W2.shape[1], _dp(W2), len(pairs), _ip(ia), _ip(jb), _dp(fac))
+        lib().orc_soap_set_global(h, int(bool(p.get("global"))))
     return h
 
 
@@ -490,6 +493,21 @@ def soap_descriptor(desc_str, atoms, grad=False, cutoff=None):
     con = Connect(atoms, p["cutoff"] + 1.0 if cutoff is None else cutoff)
     d = lib().orc_soap_dim(hs)
     nrows = C.c_int(0)
+    if p.get("global"):  # one descriptor per configuration; grad rows: (centre i, then its neighbours) for every centre
+        nc = lib().orc_soap_calc_global(hs, con.h, con.N, _dp(con.pos), _ip(con.Z), _dp(con.lat), None, int(grad), C.byref(nrows), None, None,
+                                        None, None, None, None)
+        rows = nrows.value
+        x, ci = np.zeros((1, d)), np.zeros(max(nc, 1), dtype=np.int32)
+        g = np.zeros((max(rows, 1), 3, d)) if grad else None
+        ii, gpos, hg = np.zeros(max(rows, 1), dtype=np.int32), np.zeros((max(rows, 1), 3)), np.zeros(max(rows, 1), dtype=np.int32)
+        lib().orc_soap_calc_global(hs, con.h, con.N, _dp(con.pos), _ip(con.Z), _dp(con.lat), None, int(grad), C.byref(nrows), _dp(x), _ip(ci),
+                                   _dp(g), _ip(ii), _dp(gpos), _ip(hg))
+        lib().orc_soap_free(hs)
+        out = {"data": x, "ci": ci[:nc], "row_off": np.array([0, rows], dtype=np.int32)}
+        if grad:
+            out.update(grad_data=g[:rows], ii=ii[:rows], pos=gpos[:rows], has_grad_data=hg[:rows].astype(bool),
+                       grad_index_0based=np.stack([np.zeros(rows, dtype=np.int32), ii[:rows]], axis=1))
+        return out
     nd = lib().orc_soap_calc(hs, con.h, con.N, _dp(con.pos), _ip(con.Z), _dp(con.lat), int(grad), C.byref(nrows),
                              None, None, None, None, None, None, None)
     rows = nrows.value

@@ -163,17 +163,14 @@ def _soap_all_cases(golden):
 
 
 def test_soap_reference_data_all_variants(golden):
-    """tests/test_SOAP.py:36-77 over tests/SOAP_reference_data.json: every case with average=F (66 of 122) -- Z_mix / R_mix / sym_mix with
-    QUIP's own random mixing weights, coupling=F, Z_map, nu_R / nu_S, diagonal_radial, GTO and POLY radial bases -- X, the gradient
-    index table and grad_data (np.allclose there; 1e-9 here).  average=T (one descriptor per configuration) is out of scope."""
+    """tests/test_SOAP.py:36-77 over tests/SOAP_reference_data.json, ALL 122 cases: Z_mix / R_mix / sym_mix with QUIP's own random mixing
+    weights, coupling=F, Z_map, nu_R / nu_S, diagonal_radial, GTO and POLY radial bases, the default path, each with average=F (one
+    descriptor per atom) and average=T (one per configuration) -- X, the gradient index table and grad_data (np.allclose there; 1e-9
+    here)."""
     meta, z, ds = _soap_all_cases(golden)
-    n = 0
+    n_avg = 0
     for i, m in enumerate(meta):
         qs = m["quippy_str"]
-        if "average=T" in qs:
-            with pytest.raises(NotImplementedError):
-                orc.soap_params(qs)
-            continue
         outs = [orc.soap_descriptor(qs, a, grad=True) for a in ds[m["dataset_name"]]]
         X = np.concatenate([o["data"] for o in outs])[z["perm_%d" % i]]
         assert X.shape == z["X_%d" % i].shape, (i, qs)
@@ -181,8 +178,42 @@ def test_soap_reference_data_all_variants(golden):
         gp = z["gperm_%d" % i]
         assert np.array_equal(outs[0]["grad_index_0based"][gp], z["GI_%d" % i]), (i, qs)
         assert np.abs(outs[0]["grad_data"][gp] - z["G_%d" % i]).max() < 1e-9, (i, qs)
-        n += 1
-    assert n == 66
+        n_avg += "average=T" in qs
+    assert len(meta) == 122 and n_avg == 56
+
+
+def test_global_soap_model_finite_difference(golden, tmp_path):
+    """A GAP on an average=T (global) SOAP descriptor: one descriptor instance per configuration, its energy shared by all centres
+    (descriptors.f95:8014-8028, IPModel_GAP.f95:454-459).  No golden E/F/V exists in the reference tree (the descriptor and its grad_data
+    are pinned above): forces and virial of the restatement are checked by central finite differences of its own energy."""
+    from quip_b200.gap_xml import write_gap_xml
+    meta, z, ds = _soap_all_cases(golden)
+    qs = meta[3]["quippy_str"]  # Z_mix, coupling=T, average=T
+    frames = [Atoms(a.numbers, a.positions, a.cell, True) for a in ds["quad_3"]]
+    X = np.concatenate([orc.soap_descriptor(qs, a)["data"] for a in frames])
+    rng = np.random.default_rng(9)
+    coord = {"descriptor": qs, "covariance_type": 2, "delta": 1.1, "zeta": 2.0, "sparseX": X, "alpha": rng.normal(size=len(X)),
+             "sparseCutoff": np.ones(len(X))}
+    om = orc.Model(write_gap_xml(str(tmp_path / "g.xml"), [coord], e0={23: 0.1, 41: -0.2, 42: 0.3, 73: 0.4}))
+    a = Atoms(frames[0].numbers, frames[0].positions + rng.normal(scale=0.05, size=frames[0].positions.shape), frames[0].cell, True)
+    r = om.calc(a, local_energy=True)
+    assert abs(r["local_energy"].sum() - r["energy"]) < 1e-10
+    h = 1e-5
+    for j, k in ((0, 0), (2, 1), (5, 2)):
+        e = []
+        for sgn in (1, -1):
+            p = a.positions.copy()
+            p[j, k] += sgn * h
+            e.append(om.calc(Atoms(a.numbers, p, a.cell, True), force=False, virial=False)["energy"])
+        assert abs((e[0] - e[1]) / (2 * h) + r["force"][j, k]) < 1e-7 * max(1.0, np.abs(r["force"]).max())
+    eps = 1e-6
+    for (aa, bb) in ((0, 0), (1, 2)):
+        F, Fm = np.eye(3), np.eye(3)
+        F[aa, bb] += eps
+        Fm[aa, bb] -= eps
+        ep = om.calc(Atoms(a.numbers, a.positions @ F.T, a.cell @ F.T, True), force=False, virial=False)["energy"]
+        em = om.calc(Atoms(a.numbers, a.positions @ Fm.T, a.cell @ Fm.T, True), force=False, virial=False)["energy"]
+        assert abs((ep - em) / (2 * eps) + r["virial"][aa, bb]) < 1e-6 * max(1.0, np.abs(r["virial"]).max())
 
 
 def test_distance_2b_options_finite_difference(golden, tmp_path):

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from oracle import oracle as orc
 from quip_b200 import read_xyz
-from quip_b200.potential import pack_results, partition_bounds, reduce_packed, unpack_results
+from quip_b200.potential import broadcast_comm_id, pack_results, partition_bounds, reduce_packed, unpack_results
 from tests.models import GOLDEN, si_two_descriptor_model
 
 
@@ -33,6 +33,10 @@ def _worker(rank, world, port, xml, out_dir):
     o = orc.Model(xml).calc(a, first=first, last=last, nthreads=1)
     t = torch.from_numpy(pack_results(o["energy"], o["virial"], o["force"]))
     reduce_packed(t)
+    # the host's share of the in-library reduction: rank 0 creates the 128-byte communicator id, torch.distributed hands it to every rank
+    cid = broadcast_comm_id()
+    assert isinstance(cid, bytes) and len(cid) == 128
+    np.save(os.path.join(out_dir, "id%d.npy" % rank), np.frombuffer(cid, dtype=np.uint8))
     np.save(os.path.join(out_dir, "r%d.npy" % rank), t.numpy())
     dist.barrier()
     dist.destroy_process_group()
@@ -54,7 +58,9 @@ def test_two_rank_gloo_allreduce_matches_single_rank():
         mp.spawn(_worker, args=(2, _free_port(), xml, tmp), nprocs=2, join=True)
         r0 = np.load(os.path.join(tmp, "r0.npy"))
         r1 = np.load(os.path.join(tmp, "r1.npy"))
+        id0, id1 = np.load(os.path.join(tmp, "id0.npy")), np.load(os.path.join(tmp, "id1.npy"))
     assert np.array_equal(r0, r1)
+    assert np.array_equal(id0, id1) and id0.any()  # both ranks hold the same, non-trivial communicator id
     u = unpack_results(r0, len(a))
     assert abs(u["energy"] - full["energy"]) < 1e-9 * abs(full["energy"])
     assert np.abs(u["force"] - full["force"]).max() < 1e-10
