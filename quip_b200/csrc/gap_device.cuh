@@ -150,6 +150,9 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
 // ---- soap_general.cu: compression modes and GTO / POLY radial bases (tables built by gap_model.cpp soap_general_setup) ----
 struct SoapGenDev {
   int n_grid, Ka, Kb, n_pairs;
+  int global_mode;         // average=T: one descriptor per configuration (sum of the centres' density expansions)
+  double* Xg;              // global_mode: [nlm][K1] summed density expansion
+  double* Lt;              // global_mode: [nlm][n_species * n_grid] dE/dX on the radial grid, shared by all centres
   const double* r_grid;    // [n_grid]
   const double* P;         // [l_max+1][n_grid][n_max]
   const double* c0;        // [n_max]

@@ -507,8 +507,7 @@ SoapSpec soap_from_string(const std::string& desc, long calc_xml_version) {
   bool has_n_species = a.has("n_species");
   s.n_species = (int)a.integer("n_species", 1);
   long xml_version = a.integer("xml_version", 1426512068L);
-  // average=T is ONE descriptor per configuration (global SOAP), not a per-atom environment: outside the hot path, refused loudly
-  if (a.logical("average", false)) throw GapError("soap option average=T (global SOAP) is not supported by the B200 path");
+  s.global = a.logical("average", false);  // ONE descriptor per configuration (global SOAP): the general path's element list on the summed X
   const bool diagonal_radial = a.logical("diagonal_radial", false), Z_mix = a.logical("Z_mix", false), R_mix = a.logical("R_mix", false),
              sym_mix = a.logical("sym_mix", false), coupling = a.logical("coupling", true);
   const int nu_R = (int)a.integer("nu_R", 2), nu_S = (int)a.integer("nu_S", 2), K_mix = (int)a.integer("K", 0), mix_shift = (int)a.integer("mix_shift", 0);
@@ -517,7 +516,7 @@ SoapSpec soap_from_string(const std::string& desc, long calc_xml_version) {
   if (s.radial_basis.empty()) s.radial_basis = "EQUISPACED_GAUSS";  // :2548-2551
   if (s.radial_basis != "EQUISPACED_GAUSS" && s.radial_basis != "GTO" && s.radial_basis != "POLY")
     throw GapError("soap_initialise: radial_basis not recognised: EQUISPACED_GAUSS, POLY or GTO");
-  s.general = diagonal_radial || Z_mix || R_mix || sym_mix || !coupling || nu_R != 2 || nu_S != 2 || !Z_map.empty() || s.radial_basis != "EQUISPACED_GAUSS";
+  s.general = s.global || diagonal_radial || Z_mix || R_mix || sym_mix || !coupling || nu_R != 2 || nu_S != 2 || !Z_map.empty() || s.radial_basis != "EQUISPACED_GAUSS";
   if (s.cutoff_dexp < 0) throw GapError("soap_initialise: cutoff_dexp may not be less than 0");
   if (s.cutoff_scale <= 0.0) throw GapError("soap_initialise: cutoff_scale must be greater than 0");
   if (s.cutoff_rate < 0.0) throw GapError("soap_initialise: cutoff_rate may not be less than 0");

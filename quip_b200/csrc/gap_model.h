@@ -51,6 +51,7 @@ struct SoapSpec {
   //      descriptors.f95:7274-7670) and the GTO / POLY radial bases (:2643-2770, :8264-8278); general == false is the reference's
   //      "original" power spectrum (:7772-7775) on EQUISPACED_GAUSS
   bool general = false;
+  bool global = false;          // average=T: ONE descriptor per configuration (descriptors.f95:2516, 8357-8367, 8738-9008)
   std::string radial_basis = "EQUISPACED_GAUSS";
   int n_grid = 0;               // radial points: n_max, or 3 n_max for GTO / POLY
   std::vector<double> r_grid;   // n_grid

@@ -70,6 +70,7 @@ struct CoordDev {
   bool general = false;        // compression modes / GTO / POLY: soap_general.cu kernels
   SoapGenDev gen;
   void* gen_blob = nullptr;    // one device allocation behind the pointers of gen
+  double* gen_global = nullptr; // average=T: [Xg | Lt] (see SoapGenDev)
   double *sp_rows = nullptr, *st_rows = nullptr, *alpha = nullptr, *scut = nullptr;
   int M = 0, M_pad = 0, d_pad = 0, dn_pad = 0, bn2 = 128;
   CovParams cp;
@@ -697,6 +698,12 @@ void upload_model(gap_potential* P) {
         cd.gen.n_grid = s.n_grid; cd.gen.Ka = s.Ka; cd.gen.Kb = s.Kb; cd.gen.n_pairs = (int)np;
         cd.gen.r_grid = b + o_r; cd.gen.P = b + o_P; cd.gen.c0 = b + o_c0; cd.gen.W1 = b + o_W1; cd.gen.W2 = b + o_W2; cd.gen.pair_fac = b + o_f;
         cd.gen.pair_ia = d_int; cd.gen.pair_jb = d_int + np;
+        cd.gen.global_mode = s.global ? 1 : 0;
+        if (s.global) {  // average=T: the summed density expansion and the shared dE/dX on the radial grid
+          CUDA_OK(cudaMalloc(&cd.gen_global, sizeof(double) * (size_t)h.nlm * (h.K1 + s.n_species * s.n_grid)));
+          cd.gen.Xg = cd.gen_global;
+          cd.gen.Lt = cd.gen_global + (size_t)h.nlm * h.K1;
+        }
         if (soap_general_smem(h, cd.gen) > prop.sharedMemPerBlockOptin)
           throw GapError("soap descriptor (general path) too large for the shared memory of this device");
       }
@@ -1108,9 +1115,13 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
       mark(P, st, ST_OTHER);
       if (nc > 0) {
         const int* ncd = nc_dev(P, nc);
+        const bool glob = cd.general && cd.gen.global_mode;
+        if (glob && (first != 0 || last != N))  // (the reference sums the centres' expansions of the whole configuration, :8357-8367)
+          throw GapError("soap average=T (one descriptor per configuration) cannot be evaluated on a partition of the centres");
         soap_forward_stage(P, cd, nc, d_pos, d_Z, lat, st);
         mark(P, st, ST_SOAP_FWD);
-        covariance_stage(P, cd, nc, ncd, want_grad, true, st);
+        // average=T: ONE descriptor (row 0 of x) whatever the number of centres
+        covariance_stage(P, cd, glob ? 1 : nc, glob ? nullptr : ncd, want_grad, true, st);
         if (want_grad) {
           soap_adjoint_any(cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
                            P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, P->g_splits,
@@ -1118,10 +1129,16 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
                            P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches);
           slot += nc;
           mark(P, st, ST_SOAP_ADJ);
+        } else if (glob) {  // energy only: e_i shared by all centres (IPModel_GAP.f95:454-459)
+          soap_adjoint_any(cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_x.as<double>(),
+                           P->b_xlm.as<double>(), P->b_pnorm.as<double>(), nullptr, 0, 0, 0, P->b_epart.as<double>(), P->g_tiles_n, d_le, es, nullptr,
+                           nullptr, nullptr, st, &launches);
+          mark(P, st, ST_OTHER);
         } else {
           launch_energy_rows(P->b_epart.as<double>(), P->g_tiles_n, P->b_centres.as<int>(), ncd, nc, es, d_le, st, &launches);
           mark(P, st, ST_OTHER);
         }
+        if (ca.do_var && glob) throw GapError("local_gap_variance is not supported for soap average=T coordinates on the B200 path");
         if (ca.do_var) {
           variance_soap(P, ic, nc, ncd, want_grad, d_pos, d_Z, lat, ca.var_reg, st);
           mark(P, st, ST_OTHER);
@@ -1244,6 +1261,7 @@ void gap_potential_finalise(gap_potential* P) {
   P->comm = nullptr;
   for (CoordDev& cd : P->cd) {
     cudaFree(cd.gen_blob);
+    cudaFree(cd.gen_global);
     cudaFree(cd.d_sp); cudaFree(cd.sp_rows); cudaFree(cd.st_rows); cudaFree(cd.alpha); cudaFree(cd.scut);
     cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2); cudaFree(cd.var_mat);
   }
@@ -1845,7 +1863,8 @@ int gap_descriptor_calc(gap_potential* P, int i_coord, int N, const double* pos,
       CUDA_OK(cudaMemcpyAsync(&nc, nc_dev(P, n_ub), sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
     }
-    if (n_desc) *n_desc = nc;
+    const bool glob = cd.general && cd.gen.global_mode;
+    if (n_desc) *n_desc = glob ? (nc > 0 ? 1 : 0) : nc;  // average=T: one descriptor per configuration (ci returns its first centre)
     if (d_out) *d_out = cd.h.d;
     if (!x) return;
     build_connect(P, N, 0, N, P->b_pos.as<double>(), lattice, pbc, cd.h.cutoff, false, false, st);
@@ -1853,8 +1872,9 @@ int gap_descriptor_calc(gap_potential* P, int i_coord, int N, const double* pos,
     for (int k = 0; k < 9; k++) lat.v[k] = lattice[k];
     soap_forward_stage(P, cd, n_ub, P->b_pos.as<double>(), P->b_Z.as<int>(), lat, st);
     if (nc > 0) {
-      CUDA_OK(cudaMemcpy2DAsync(x, sizeof(double) * cd.h.d, P->b_x.p, sizeof(double) * cd.d_pad, sizeof(double) * cd.h.d, nc, cudaMemcpyDeviceToHost, st));
-      if (ci) CUDA_OK(cudaMemcpyAsync(ci, P->b_centres.p, sizeof(int) * nc, cudaMemcpyDeviceToHost, st));
+      const int nrow = glob ? 1 : nc;
+      CUDA_OK(cudaMemcpy2DAsync(x, sizeof(double) * cd.h.d, P->b_x.p, sizeof(double) * cd.d_pad, sizeof(double) * cd.h.d, nrow, cudaMemcpyDeviceToHost, st));
+      if (ci) CUDA_OK(cudaMemcpyAsync(ci, P->b_centres.p, sizeof(int) * nrow, cudaMemcpyDeviceToHost, st));
     }
     CUDA_OK(cudaStreamSynchronize(st));
   });

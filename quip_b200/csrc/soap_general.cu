@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(NT) k_soap_forward_gen(const SoapDev* __restri
                                                          const int* __restrict__ n_centres_dev, const int* __restrict__ nbr_off,
                                                          const int* __restrict__ nbr_end, const int* __restrict__ nbr_j, const int* __restrict__ nbr_s,
                                                          const double* __restrict__ pos, const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
-                                                         double* __restrict__ xlm, double* __restrict__ pnorm) {
+                                                         double* __restrict__ xlm, double* __restrict__ pnorm, int global_mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x;
   if (c >= *n_centres_dev) return;
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(NT) k_soap_forward_gen(const SoapDev* __restri
   }
   __syncthreads();
   for (int k = threadIdx.x; k < nlm * K1; k += NT) xlm[(size_t)c * nlm * K1 + k] = s.X[k];
+  if (global_mode) return;  // average=T: the power spectrum is taken of the SUM over the centres (k_soap_global_power)
   g_mix(s, g, nlm, K1);
   __syncthreads();
   double loc = 0.0;
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(NT) k_soap_adjoint_gen(const SoapDev* __restri
                                                          const double* __restrict__ x, const double* __restrict__ xlm, const double* __restrict__ pnorm,
                                                          const double* __restrict__ gvec, int ldg, int g_splits, size_t g_split_stride,
                                                          const double* __restrict__ epart, int n_tiles_n, double* __restrict__ local_e, double e_scale,
-                                                         double* __restrict__ force, double* __restrict__ vir_part, double* __restrict__ local_virial) {
+                                                         double* __restrict__ force, double* __restrict__ vir_part, double* __restrict__ local_virial,
+                                                         const double* __restrict__ Lt_global) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x;
   if (c >= *n_centres_dev) {
@@ -192,6 +194,10 @@ __global__ void __launch_bounds__(NT) k_soap_adjoint_gen(const SoapDev* __restri
     if (threadIdx.x == 0) local_e[i] += e_scale * t;
   }
   g_tables(sp, s, L, nlm);
+  if (Lt_global) {  // average=T: dE/dX on the radial grid is the same for every centre (k_soap_global_lambda)
+    for (int k = threadIdx.x; k < nlm * Kg; k += NT) s.Xt[k] = Lt_global[k];
+    __syncthreads();
+  } else {
   for (int k = threadIdx.x; k < nlm * K1; k += NT) s.X[k] = xlm[(size_t)c * nlm * K1 + k];
   for (int k = threadIdx.x; k < nlm * g.Ka; k += NT) s.dY1[k] = 0.0;
   for (int k = threadIdx.x; k < nlm * g.Kb; k += NT) s.dY2[k] = 0.0;
@@ -238,6 +244,7 @@ __global__ void __launch_bounds__(NT) k_soap_adjoint_gen(const SoapDev* __restri
     s.Xt[idx] = acc;
   }
   __syncthreads();
+  }  // !Lt_global
   // neighbour phase: f_gp,k = sum_lm sum_g Lambda~_lm(s, g) d/dr_k [ f Phi_l(g) Y_lm ]   (IPModel_GAP.f95:479 without grad_data)
   double acc12[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // thread 0: centre force (3), virial (9)
   const int pbeg = nbr_off[i], pend = nbr_end[i];
@@ -307,6 +314,103 @@ __global__ void __launch_bounds__(NT) k_soap_adjoint_gen(const SoapDev* __restri
   }
 }
 
+// ---- average=T (global SOAP, descriptors.f95:8357-8367, 8738-9008): ONE descriptor per configuration from the sum of the density
+//      expansions of all centres.  One CTA each: the sum + power spectrum, and the pull-back dE/dx -> Lambda~ shared by all centres.
+__global__ void __launch_bounds__(NT) k_soap_global_power(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ n_centres_dev,
+                                                          const double* __restrict__ xlm, double* __restrict__ Xg, double* __restrict__ x,
+                                                          double* __restrict__ pnorm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int L = sp->l_max, n = sp->n_max, ns = sp->n_species, K1 = ns * n, nlm = (L + 1) * (L + 1), d = sp->d, d_pad = sp->d_pad, L1 = L + 1,
+            np = g.n_pairs, nc = *n_centres_dev;
+  GSmem s;
+  gcarve(L, n, ns, d_pad, g, false, &s, smem_raw);
+  g_tables(sp, s, L, nlm);
+  for (int k = threadIdx.x; k < nlm * K1; k += NT) {  // fixed order over the centres: deterministic
+    double acc = 0.0;
+    for (int c = 0; c < nc; c++) acc += xlm[(size_t)c * nlm * K1 + k];
+    s.X[k] = acc;
+    Xg[k] = acc;
+  }
+  __syncthreads();
+  g_mix(s, g, nlm, K1);
+  __syncthreads();
+  double loc = 0.0;
+  for (int idx = threadIdx.x; idx < L1 * np; idx += NT) {
+    const int k = idx / L1, l = idx - k * L1, ia = g.pair_ia[k], jb = g.pair_jb[k];
+    double acc = 0.0;
+    for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) acc += s.Y1[lm * g.Ka + ia] * s.Y2[lm * g.Kb + jb];
+    const double v = acc * s.tlpo[l] * g.pair_fac[k];
+    s.p[idx] = v;
+    loc += v * v;
+  }
+  double nrm = sqrt(block_sum(loc, s.red));
+  if (nrm == 0.0) nrm = 2.2250738585072014e-308;  // tiny(1.0_dp), :8842
+  const double inv = sp->normalise ? 1.0 / nrm : 1.0;
+  for (int q = threadIdx.x; q < d_pad; q += NT) x[q] = q < d - 1 ? s.p[q] * inv : (q == d - 1 ? sp->sigma0 : 0.0);
+  if (threadIdx.x == 0) pnorm[0] = nrm;
+}
+
+__global__ void __launch_bounds__(NT) k_soap_global_lambda(const SoapDev* __restrict__ sp, SoapGenDev g, const double* __restrict__ Xg,
+                                                           const double* __restrict__ x, const double* __restrict__ pnorm,
+                                                           const double* __restrict__ gvec, int g_splits, size_t g_split_stride,
+                                                           double* __restrict__ Lt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int L = sp->l_max, n = sp->n_max, ns = sp->n_species, K1 = ns * n, nlm = (L + 1) * (L + 1), ng = g.n_grid, Kg = ns * ng, d = sp->d,
+            d_pad = sp->d_pad, L1 = L + 1, np = g.n_pairs;
+  GSmem s;
+  gcarve(L, n, ns, d_pad, g, true, &s, smem_raw);
+  g_tables(sp, s, L, nlm);
+  for (int k = threadIdx.x; k < nlm * K1; k += NT) s.X[k] = Xg[k];
+  for (int k = threadIdx.x; k < nlm * g.Ka; k += NT) s.dY1[k] = 0.0;
+  for (int k = threadIdx.x; k < nlm * g.Kb; k += NT) s.dY2[k] = 0.0;
+  const double nrm = pnorm[0];
+  double loc = 0.0;
+  for (int q = threadIdx.x; q < d - 1; q += NT) {
+    double gv = gvec[q];
+    for (int k = 1; k < g_splits; k++) gv += gvec[(size_t)k * g_split_stride + q];
+    s.p[q] = gv;
+    loc += x[q] * gv;
+  }
+  const double sdot = block_sum(loc, s.red);
+  if (sp->normalise)
+    for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = (s.p[q] - x[q] * sdot) / nrm;
+  g_mix(s, g, nlm, K1);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < L1 * np; idx += NT) {
+    const int k = idx / L1, l = idx - k * L1, ia = g.pair_ia[k], jb = g.pair_jb[k];
+    const double w = s.p[idx] * s.tlpo[l] * g.pair_fac[k];
+    for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) {
+      atomicAdd(&s.dY1[lm * g.Ka + ia], w * s.Y2[lm * g.Kb + jb]);
+      atomicAdd(&s.dY2[lm * g.Kb + jb], w * s.Y1[lm * g.Ka + ia]);
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nlm * K1; idx += NT) {
+    const int lm = idx / K1, ic = idx - lm * K1;
+    double acc = 0.0;
+    for (int k = 0; k < g.Ka; k++) acc += s.dY1[lm * g.Ka + k] * g.W1[(size_t)ic * g.Ka + k];
+    for (int k = 0; k < g.Kb; k++) acc += s.dY2[lm * g.Kb + k] * g.W2[(size_t)ic * g.Kb + k];
+    s.X[idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nlm * Kg; idx += NT) {
+    const int lm = idx / Kg, t = idx - lm * Kg, sk = t / ng, gg = t - sk * ng, l = s.l_of[lm];
+    double acc = 0.0;
+    for (int a = 0; a < n; a++) acc += s.X[lm * K1 + sk * n + a] * g.P[((size_t)l * ng + gg) * n + a];
+    Lt[idx] = acc;
+  }
+}
+
+// local_e(ci(n)) += e_i / size(ci) for every centre (IPModel_GAP.f95:454-459 with the global descriptor's ci = all centres)
+__global__ void k_global_energy(const double* __restrict__ epart, int n_tiles_n, const int* __restrict__ centres, const int* __restrict__ n_centres_dev,
+                                double e_scale, double* __restrict__ local_e) {
+  const int nc = *n_centres_dev, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double t = 0.0;
+  for (int k = 0; k < n_tiles_n; k++) t += epart[k];
+  local_e[centres[c]] += e_scale * t / (double)nc;
+}
+
 }  // namespace
 
 size_t soap_general_smem(const SoapDev& h, const SoapGenDev& g) { return gcarve(h.l_max, h.n_max, h.n_species, h.d_pad, g, true, nullptr, nullptr); }
@@ -317,8 +421,15 @@ void launch_soap_forward_general(const SoapDev* sp, const SoapDev& h, const Soap
   if (n_centres_ub <= 0) return;
   const size_t sm = gcarve(h.l_max, h.n_max, h.n_species, h.d_pad, g, false, nullptr, nullptr);
   cudaFuncSetAttribute(k_soap_forward_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_soap_forward_gen<<<n_centres_ub, NT, sm, st>>>(sp, g, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
+  k_soap_forward_gen<<<n_centres_ub, NT, sm, st>>>(sp, g, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm,
+                                                   g.global_mode);
   *launches += 1;
+  if (g.global_mode) {
+    const size_t sm2 = soap_general_smem(h, g);
+    cudaFuncSetAttribute(k_soap_global_power, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    k_soap_global_power<<<1, NT, sm2, st>>>(sp, g, n_centres_dev, xlm, g.Xg, x, pnorm);
+    *launches += 1;
+  }
 }
 
 void launch_soap_adjoint_general(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* centres, const int* n_centres_dev, int n_centres_ub,
@@ -329,8 +440,22 @@ void launch_soap_adjoint_general(const SoapDev* sp, const SoapDev& h, const Soap
   if (n_centres_ub <= 0) return;
   const size_t sm = soap_general_smem(h, g);
   cudaFuncSetAttribute(k_soap_adjoint_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (g.global_mode) {  // one descriptor: its energy is shared by all centres, its dE/dX by all neighbour phases
+    if (epart) {
+      k_global_energy<<<(n_centres_ub + 255) / 256, 256, 0, st>>>(epart, n_tiles_n, centres, n_centres_dev, e_scale, local_e);
+      *launches += 1;
+    }
+    if (!gvec) return;  // energy only
+    cudaFuncSetAttribute(k_soap_global_lambda, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    k_soap_global_lambda<<<1, NT, sm, st>>>(sp, g, g.Xg, x, pnorm, gvec, g_splits, g_split_stride, g.Lt);
+    *launches += 1;
+    k_soap_adjoint_gen<<<n_centres_ub, NT, sm, st>>>(sp, g, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
+                                                     g_splits, g_split_stride, nullptr, 0, local_e, e_scale, force, vir_part, local_virial, g.Lt);
+    *launches += 1;
+    return;
+  }
   k_soap_adjoint_gen<<<n_centres_ub, NT, sm, st>>>(sp, g, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
-                                                   g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);
+                                                   g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, nullptr);
   *launches += 1;
 }
 

@@ -740,14 +740,11 @@ def _variant_cases(golden):
 
 
 def test_soap_reference_data_all_variants_gpu(golden, tmp_path):
-    """tests/test_SOAP.py:36-77 on the GPU: gap_descriptor_calc reproduces X of every average=F case of SOAP_reference_data.json
-    (66 of 122: mixing with QUIP's random weights, coupling=F, Z_map, nu_R / nu_S, diagonal_radial, GTO, POLY, and the default path)."""
+    """tests/test_SOAP.py:36-77 on the GPU: gap_descriptor_calc reproduces X of ALL 122 cases of SOAP_reference_data.json (mixing with
+    QUIP's random weights, coupling=F, Z_map, nu_R / nu_S, diagonal_radial, GTO, POLY, the default path; average=F and average=T)."""
     meta, z, S = _variant_cases(golden)
-    n = 0
     for i, m in enumerate(meta):
         qs = m["quippy_str"]
-        if "average=T" in qs:
-            continue
         d = z["X_%d" % i].shape[1]
         coord = {"descriptor": qs, "covariance_type": 2, "delta": 1.0, "zeta": 2.0, "sparseX": np.zeros((1, d)), "alpha": np.zeros(1)}
         pot = Potential("", param_filename=write_gap_xml(str(tmp_path / ("v%d.xml" % i)), [coord], separate_files=False))
@@ -756,11 +753,11 @@ def test_soap_reference_data_all_variants_gpu(golden, tmp_path):
         assert X.shape == z["X_%d" % i].shape, (i, qs)
         assert np.abs(X - z["X_%d" % i]).max() < 1e-9, (i, qs, np.abs(X - z["X_%d" % i]).max())
         pot.finalise()
-        n += 1
-    assert n == 66
+    assert len(meta) == 122
 
 
-VARIANT_EFV = [0, 2, 6, 12, 18, 22, 30, 38, 48, 53, 55, 60, 69, 73, 75, 101, 113, 115, 117, 118, 120, 121]
+VARIANT_EFV = [0, 2, 6, 12, 18, 22, 30, 38, 48, 53, 55, 60, 69, 73, 75, 101, 113, 115, 117, 118, 120, 121,
+               1, 3, 15, 23, 29, 57, 59, 79, 82, 109]  # second row: average=T (one descriptor per configuration)
 
 
 @pytest.mark.parametrize("case", VARIANT_EFV)

@@ -149,16 +149,14 @@ def test_cli_argument_grammar():
 
 def test_general_soap_setup_matches_oracle(golden, tmp_path):
     """The C++ loader's general-SOAP tables (mixing matrices with QUIP's random weights, power-spectrum element list, GTO / POLY
-    radial maps; gap_model.cpp soap_general_setup) against the oracle's independent numpy derivation, for every average=F descriptor
-    string of the reference's SOAP_reference_data.json that takes the general path."""
+    radial maps; gap_model.cpp soap_general_setup) against the oracle's independent numpy derivation, for every descriptor string of
+    the reference's SOAP_reference_data.json that takes the general path (average=T strings included)."""
     import json
 
     meta = json.load(open(os.path.join(golden, "soap_reference_all.json")))
     n_general = 0
     for m in meta:
         qs = m["quippy_str"]
-        if "average=T" in qs:
-            continue
         p = orc.soap_params(qs)
         W1, W2, _, pairs = orc.soap_mixing(p)
         d = (p["l_max"] + 1) * len(pairs) + 1
@@ -182,7 +180,4 @@ def test_general_soap_setup_matches_oracle(golden, tmp_path):
         Pc = np.array(rows["P"], dtype=float).reshape(Pm.shape)
         assert np.abs(Pc - Pm).max() < 1e-9 * max(1.0, np.abs(Pm).max()), (qs, np.abs(Pc - Pm).max(), np.abs(Pm).max())
         assert np.abs(np.array(rows["c0"], dtype=float) - c0).max() < 1e-9 * max(1.0, np.abs(c0).max()), qs
-    assert n_general >= 55
-    with pytest.raises(RuntimeError, match="average=T"):
-        coord = {"descriptor": meta[1]["quippy_str"], "covariance_type": 2, "delta": 1.0, "zeta": 2.0, "sparseX": np.zeros((1, 5)), "alpha": np.zeros(1)}
-        P.model_describe(param_filename=write_gap_xml(str(tmp_path / "avg.xml"), [coord], separate_files=False))
+    assert n_general >= 110
