@@ -215,29 +215,46 @@ __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, in
       if (lane >= o) pre += v;
     }
     const int total = __shfl_sync(0xffffffffu, pre, 31);
-    for (int base = 0; base < total; base += 32) {
+    // candidate t of the flattened index space -> (sorted slot q, image shift) by a shuffle-based binary search; the loads of a
+    // candidate (its shift word, position and atom id) are issued one batch AHEAD of their use, so two batches are in flight
+    struct Cand { int q, sh, ms, j; double x, y, z; bool in; };
+    auto fetch = [&](int base) {
+      Cand c;
       const int t = base + lane;
-      // smallest k with pre_k > t
-      int k = 0;
+      int k = 0;  // smallest k with pre_k > t
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         int v = __shfl_sync(0xffffffffu, pre, k + o - 1);
         if (v <= t) k += o;
       }
-      const int pk = __shfl_sync(0xffffffffu, pre, k), ck_cnt = __shfl_sync(0xffffffffu, cnt, k), kqb = __shfl_sync(0xffffffffu, qb, k),
-                ksh = __shfl_sync(0xffffffffu, sh, k);
+      const int pk = __shfl_sync(0xffffffffu, pre, k), ck_cnt = __shfl_sync(0xffffffffu, cnt, k), kqb = __shfl_sync(0xffffffffu, qb, k);
+      c.sh = __shfl_sync(0xffffffffu, sh, k);
+      c.in = t < total;
+      c.q = c.in ? kqb + (t - (pk - ck_cnt)) : 0;
+      c.ms = 0; c.j = 0; c.x = c.y = c.z = 0.0;
+      if (c.in) {
+        c.ms = smshift[c.q];
+        c.x = spos[3 * (size_t)c.q]; c.y = spos[3 * (size_t)c.q + 1]; c.z = spos[3 * (size_t)c.q + 2];
+        if (FILL) c.j = sort_idx[c.q];
+      }
+      return c;
+    };
+    Cand nxt = fetch(0);
+    for (int base = 0; base < total; base += 32) {
+      const Cand cur = nxt;
+      if (base + 32 < total) nxt = fetch(base + 32);
       bool acc = false;
-      int q = 0, t0 = 0, t1 = 0, t2 = 0;
+      int t0 = 0, t1 = 0, t2 = 0;
       double d = 0.0;
-      if (t < total) {
-        q = kqb + (t - (pk - ck_cnt));
+      if (cur.in) {
         int mj0, mj1, mj2, b0, b1, b2;
-        unpack_shift(smshift[q], mj0, mj1, mj2);
-        unpack_shift(ksh, b0, b1, b2);
+        unpack_shift(cur.ms, mj0, mj1, mj2);
+        unpack_shift(cur.sh, b0, b1, b2);
         t0 = b0 + mj0; t1 = b1 + mj1; t2 = b2 + mj2;
-        if (!(q == p && t0 == 0 && t1 == 0 && t2 == 0)) {  // self, zero shift (:1266-1272)
+        if (!(cur.q == p && t0 == 0 && t1 == 0 && t2 == 0)) {  // self, zero shift (:1266-1272)
+          const double pj[3] = {cur.x, cur.y, cur.z};
           double dd[3];
-          image_diff(pi, spos + 3 * (size_t)q, grid.lat, t0, t1, t2, dd);
+          image_diff(pi, pj, grid.lat, t0, t1, t2, dd);
           d = norm_nofma(dd);
           acc = d < cutoff;  // strict, Connection.f95:517
         }
@@ -246,7 +263,7 @@ __global__ void __launch_bounds__(NEIGH_WARPS * 32) k_neigh(int N, int first, in
       if (FILL && acc) {
         int w = wpos + __popc(bal & ((1u << lane) - 1u));
         if (w < cap) {  // only a speculatively sized row can overflow; the host then repeats the call with the exact layout
-          nbr_j[w] = sort_idx[q];
+          nbr_j[w] = cur.j;
           nbr_s[w] = pack_shift(t0, t1, t2);
           if (nbr_d) nbr_d[w] = d;
         }

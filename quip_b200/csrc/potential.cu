@@ -219,9 +219,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const int* __restrict_
       *counter = 0u;
       if (stat_dev) {  // the host reads the list's status from mapped memory after its synchronisation (no copy node in the stream);
                        // the device words are left clean for the next speculative build
-        stat_host[1] = stat_dev[1];
+        stat_host[1] = stat_dev[1];  // (visible to the host once the kernel has completed: no fence needed)
         stat_host[2] = stat_dev[2];
-        __threadfence_system();
         stat_dev[0] = stat_dev[1] = stat_dev[2] = 0;
       }
     }
@@ -262,7 +261,11 @@ __global__ void k_zero_outputs(double* __restrict__ a, size_t na, double* __rest
 // compaction, 4 atoms per thread and 4,096 per round; the count goes where the multi-kernel path leaves it (scan[n]).
 // Blocks 1.. of the grid (if any) zero the outputs of the calc instead (one launch for both jobs at the start of a step).
 constexpr int SEL_THREADS = 1024, SEL_ITEMS = 4, SEL_MAX_N = 16384, SEL_ZERO_BLOCKS = 8;
-__global__ void __launch_bounds__(SEL_THREADS) k_select_compact_block(const int* __restrict__ Z, int first, int last, const SoapDev* __restrict__ sp,
+struct CentreZ {  // Z(:) of a soap descriptor (descriptors.f95:7962), by value: no dependent loads at the head of the step
+  int n_Z;
+  int Z[SOAP_SPECIES_CAP];
+};
+__global__ void __launch_bounds__(SEL_THREADS) k_select_compact_block(const int* __restrict__ Z, int first, int last, CentreZ cz,
                                                                        int* __restrict__ centres, int* __restrict__ count_out,
                                                                        double* __restrict__ za, size_t nza, double* __restrict__ zb, size_t nzb,
                                                                        double* __restrict__ zc, size_t nzc) {
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_compact_block(const int*
     for (size_t t = t0; t < nzc; t += stride) zc[t] = 0.0;
     return;
   }
-  const int n = last - first, nZ = sp->n_Z;
+  const int n = last - first, nZ = cz.n_Z;
   int base = 0;
   for (int t0 = 0; t0 < n; t0 += SEL_THREADS * SEL_ITEMS) {
     int f[SEL_ITEMS], pos[SEL_ITEMS], total;
@@ -287,8 +290,9 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_compact_block(const int*
       f[k] = 0;
       if (t < n) {
         const int Zi = Z[first + t];
-        for (int q = 0; q < nZ; q++)
-          if (Zi >= 0 && (sp->centre_Z[q] == Zi || sp->centre_Z[q] == 0)) f[k] = 1;
+#pragma unroll
+        for (int q = 0; q < SOAP_SPECIES_CAP; q++)
+          if (q < nZ && Zi >= 0 && (cz.Z[q] == Zi || cz.Z[q] == 0)) f[k] = 1;
       }
     }
     BS(tmp).ExclusiveSum(f, pos, total);
@@ -840,8 +844,11 @@ int select_centres(gap_potential* P, const CoordDev& cd, const int* d_Z, int fir
   P->b_centres.ensure(sizeof(int) * (n + 1));
   if (n <= SEL_MAX_N) {
     const bool fuse = za != nullptr;
-    launch_pdl(k_select_compact_block, dim3(fuse ? 1 + SEL_ZERO_BLOCKS : 1), dim3(SEL_THREADS), 0, st, d_Z, first, last, (const SoapDev*)cd.d_sp,
-               P->b_centres.as<int>(), P->b_scan.as<int>() + n, za, nza, zb, nzb, zc, nzc);
+    CentreZ cz;
+    cz.n_Z = cd.h.n_Z;
+    for (int q = 0; q < SOAP_SPECIES_CAP; q++) cz.Z[q] = cd.h.centre_Z[q];
+    launch_pdl(k_select_compact_block, dim3(fuse ? 1 + SEL_ZERO_BLOCKS : 1), dim3(SEL_THREADS), 0, st, d_Z, first, last, cz, P->b_centres.as<int>(),
+               P->b_scan.as<int>() + n, za, nza, zb, nzb, zc, nzc);
     if (zeroed) *zeroed = fuse;
     P->launches += 1;
     return n;

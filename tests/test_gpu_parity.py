@@ -859,3 +859,42 @@ def test_distance_2b_options_vs_oracle(golden, tmp_path):
     fresh = Potential("", param_filename=xml)
     with pytest.raises(RuntimeError, match="residue id"):
         fresh.calc(quad_datasets(golden, True)[0])
+
+
+def test_md_run_device_reduce_hook_is_called(si_model, si_frames):
+    # gap_md_run_device's reduction hook (a host without the library's communicator, e.g. one that reduces with MPI-aware CUDA): called once
+    # after every force evaluation, on the evaluation's stream; the trajectory equals gap_md_run's
+    import ctypes as C
+
+    import torch
+
+    from quip_b200 import load_library
+    from quip_b200.potential import element_masses
+
+    pot, om, xml = si_model
+    a = si_frames[8]
+    N = len(a)
+    rng = np.random.default_rng(5)
+    v0 = rng.normal(scale=0.01, size=a.positions.shape)
+    at1 = Atoms(a.numbers, a.positions.copy(), a.cell, True)
+    v1, ep1, ek1 = pot.run(at1, v0, dt=1.0, n_steps=4)
+    calls = []
+    hook = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)(lambda ctx, stream: calls.append(stream))
+    dev = torch.device("cuda", 0)
+    d_pos = torch.tensor(a.positions, dtype=torch.float64, device=dev)
+    d_vel = torch.tensor(v0, dtype=torch.float64, device=dev)
+    d_Z = torch.tensor(a.numbers, dtype=torch.int32, device=dev)
+    d_m = torch.tensor(element_masses(a.numbers), dtype=torch.float64, device=dev)
+    d_packed = torch.zeros(10 + 3 * N, dtype=torch.float64, device=dev)
+    ep, ek = np.zeros(5), np.zeros(5)
+    lat = np.ascontiguousarray(a.cell.reshape(9))
+    pbc = np.ones(3, dtype=np.int32)
+    torch.cuda.synchronize()
+    p2 = Potential("IP GAP", param_filename=xml)
+    rc = load_library().gap_md_run_device(p2._h, N, d_pos.data_ptr(), d_vel.data_ptr(), d_Z.data_ptr(), d_m.data_ptr(), lat.ctypes.data_as(C.POINTER(C.c_double)),
+                                          pbc.ctypes.data_as(C.POINTER(C.c_int)), 1.0, 4, b"", d_packed.data_ptr(), C.cast(hook, C.c_void_p), None,
+                                          ep.ctypes.data_as(C.POINTER(C.c_double)), ek.ctypes.data_as(C.POINTER(C.c_double)), None)
+    assert rc == 0, load_library().gap_last_error()
+    assert len(calls) == 5 and all(s == calls[0] for s in calls)  # initial evaluation + 4 steps, always the same stream
+    assert np.abs(d_pos.cpu().numpy() - at1.positions).max() < 1e-10
+    assert np.abs(ep - ep1).max() < 1e-9
