@@ -87,6 +87,13 @@ int gap_potential_calc(gap_potential* pot, int N, const double* pos, const int* 
 int gap_potential_set_cutoff_skin(gap_potential* pot, double cutoff_skin);
 int gap_potential_connect_stats(const gap_potential* pot, long* n_rebuilds, long* n_reuses);
 
+/* Run-to-run reproducible forces.  By default the SOAP force scatter (IPModel_GAP.f95:482, f(:, ii(n)) -= f_gp) adds with FP64 atomics: the
+ * summation order, hence the last bits of the forces, varies between runs (as it does between the threads of the reference's OpenMP
+ * reduction).  on = 1: every pair force is stored at the slot of its neighbour-list entry and the slots are summed per receiving atom in
+ * slot order with a fixed reduction tree (one stable radix sort of the slots per list build): bitwise identical forces for identical
+ * inputs.  Energies and virials are reduced in a fixed order in both modes; local_virial and the atom-mask scatter keep atomics. */
+int gap_potential_set_deterministic(gap_potential* pot, int on);
+
 /* ---- optional inputs / outputs of IPModel_GAP_Calc that the reference passes through the Atoms object and the calc
  * args string (src/Potentials/IPModel_GAP.f95:324-337, 344-346, 462-488, 558-573).  They are requested with the SAME
  * keys in args_str and fetched after the calc:

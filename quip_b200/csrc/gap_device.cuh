@@ -144,8 +144,11 @@ void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres
 void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
                          const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
-                         double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st,
+                         double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, double* fpair, cudaStream_t st,
                          int* launches);
+// fpair != NULL selects the DETERMINISTIC scatter: the force on neighbour j of a pair goes to fpair[3 * slot] (slot = position of the
+// entry in the neighbour list), the centre's own sum to force[3 * i] by a plain store (force = a zeroed per-atom scratch buffer); the
+// caller then adds both per atom in a fixed order (potential.cu k_det_gather).  fpair == NULL: FP64 atomics on force[].
 
 // ---- soap_general.cu: compression modes and GTO / POLY radial bases (tables built by gap_model.cpp soap_general_setup) ----
 struct SoapGenDev {
@@ -170,7 +173,7 @@ void launch_soap_adjoint_general(const SoapDev* sp, const SoapDev& h, const Soap
                                  const int* nbr_off, const int* nbr_end, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat,
                                  const double* x, const double* xlm, const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride,
                                  const double* epart, int n_tiles_n, double* local_e, double e_scale, double* force, double* vir_part,
-                                 double* local_virial, cudaStream_t st, int* launches);
+                                 double* local_virial, double* fpair, cudaStream_t st, int* launches);
 
 // ---- covariance.cu -------------------------------------------------------------------------
 struct CovParams {

@@ -127,6 +127,14 @@ struct gap_potential {
   bool var_grad = false;
   cudaStream_t last_stream = nullptr;
 
+  // deterministic force scatter (gap_potential_set_deterministic): pair forces stored per list slot, summed per atom in a fixed order
+  bool deterministic = false;
+  bool list_reused = false;    // the last build_connect kept the previous list (the reverse index of the slots is still valid)
+  long ext_nnz = 0;            // entries of an external (LAMMPS) list
+  long det_slots = 0;          // slots covered by the reverse index
+  int list_row_cap = 0;        // layout of the handle's own list: fixed-capacity rows of this many slots, or 0 = packed CSR
+  long list_slots = 0;         // slots of the handle's own list (row_cap * centres, or the entry count)
+  DevBuf b_fpair, b_fself, b_dkeys, b_dkeys2, b_dvals, b_dvals2, b_joff, b_dcub;
   // skin-based reuse of the neighbour list (calc_connect with cutoff_skin, Connection.f95:1085-1128)
   double cutoff_skin = 0.0;
   bool list_valid = false;     // cv_* describe a list built with last_cut for the geometry remembered below
@@ -335,6 +343,50 @@ __global__ void __launch_bounds__(256) k_kinetic(int N, const double* __restrict
   if (threadIdx.x == 0) part[blockIdx.x] = t;
 }
 
+// ---- deterministic force scatter -----------------------------------------------------------------------------------------
+// The SOAP adjoint kernels store the force a pair exerts on its neighbour at the SLOT of that list entry (fpair) instead of adding
+// it to force[j] with an FP64 atomic; here the slots are indexed by receiving atom (stable radix sort of (j, slot)), and one warp per
+// atom adds its contributions in slot order with a fixed reduction tree, plus the atom's own sum as a centre (fself).
+__global__ void k_det_keys(long n_slots, int row_cap, int first, const int* __restrict__ nbr_end, const int* __restrict__ nbr_j, int N,
+                           int* __restrict__ keys, int* __restrict__ vals) {
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_slots) return;
+  bool valid = true;
+  if (row_cap > 0) valid = p < (long)nbr_end[first + (int)(p / row_cap)];  // fixed-capacity rows: slots beyond the row's fill are empty
+  keys[p] = valid ? nbr_j[p] : N;
+  vals[p] = (int)p;
+}
+__global__ void k_det_joff(const int* __restrict__ keys_sorted, long n_slots, int N, int* __restrict__ joff /* [N + 2] */) {
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_slots) return;
+  const int key = keys_sorted[p], prev = p > 0 ? keys_sorted[p - 1] : -1;
+  for (int c = prev + 1; c <= key; c++) joff[c] = (int)p;
+  if (p == n_slots - 1)
+    for (int c = key + 1; c <= N + 1; c++) joff[c] = (int)n_slots;
+}
+__global__ void __launch_bounds__(128) k_det_gather(int N, const int* __restrict__ joff, const int* __restrict__ slot_of_entry,
+                                                    const double* __restrict__ fpair, double* __restrict__ fself, double* __restrict__ force) {
+  const int lane = threadIdx.x & 31, j = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (j >= N) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int e = joff[j] + lane; e < joff[j + 1]; e += 32) {
+    const size_t p = (size_t)slot_of_entry[e];
+    a0 += fpair[3 * p]; a1 += fpair[3 * p + 1]; a2 += fpair[3 * p + 2];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (lane == 0) {
+    force[3 * (size_t)j] += a0 + fself[3 * (size_t)j];
+    force[3 * (size_t)j + 1] += a1 + fself[3 * (size_t)j + 1];
+    force[3 * (size_t)j + 2] += a2 + fself[3 * (size_t)j + 2];
+    fself[3 * (size_t)j] = fself[3 * (size_t)j + 1] = fself[3 * (size_t)j + 2] = 0.0;  // clean for the next coordinate
+  }
+}
+
 // largest squared displacement since the last list build, per block (the host takes the maximum of the block values)
 constexpr int DISP_BLOCKS = 256;
 __global__ void __launch_bounds__(256) k_max_disp2(const double* __restrict__ pos, const double* __restrict__ last, int N, double* __restrict__ part) {
@@ -426,6 +478,7 @@ void remember_build(gap_potential* P, int N, int first, int last, const double* 
 void build_connect(gap_potential* P, int N, int first, int last, const double* d_pos, const double* lattice, const int* pbc, double cutoff,
                    bool want_dist, bool speculative, cudaStream_t st) {
   P->pending_check = false;
+  P->list_reused = false;
   if (N < 0) throw GapError("calc_connect: negative number of atoms");
   if (cutoff < 0.0) throw GapError("calc_connect: Negative cutoff radius " + std::to_string(cutoff));  // Connection.f95:1069
   // calc_connect with cutoff_skin (Connection.f95:1085-1128): the list is built out to cutoff + skin and kept while no atom has moved
@@ -449,6 +502,7 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
       for (int k = 0; k < nb; k++) m = (P->h_disp[k] != P->h_disp[k] || P->h_disp[k] > m) ? P->h_disp[k] : m;
       if (m == m && std::sqrt(m) < 0.5 * P->cutoff_skin) {  // :1110-1116: reuse (cv_* still describe the list)
         P->n_reuses++;
+        P->list_reused = true;
         return;
       }
     }
@@ -459,6 +513,8 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   P->b_off.ensure(sizeof(int) * (N + 4));  // [0..N] row offsets, then: [N+1] error flag, [N+2] largest row
   P->cv_off = P->b_off.as<int>(); P->cv_end = P->b_off.as<int>() + 1; P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
   if (N == 0 || cutoff == 0.0) {  // cutoff == 0: "don't compute neighbours" (:1079)
+    P->list_row_cap = 0;
+    P->list_slots = 0;
     CUDA_OK(cudaMemsetAsync(P->b_off.p, 0, sizeof(int) * (N + 4), st));
     return;
   }
@@ -591,6 +647,8 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
                            stat + 2, st, &launches);
       P->pending_check = true;  // the status words reach the host through k_finalize (mapped memory), see verify_connect
       P->pending_cap = row_cap;
+      P->list_row_cap = row_cap;
+      P->list_slots = cap;
       P->cv_end = P->b_end.as<int>(); P->cv_j = P->b_j.as<int>(); P->cv_s = P->b_s.as<int>();
       P->launches += launches;
       if (use_skin) remember_build(P, N, first, last, d_pos, lattice, pbc, cutoff, st);
@@ -605,6 +663,8 @@ void build_connect(gap_potential* P, int N, int first, int last, const double* d
   if (P->h_pin[1]) throw GapError("calc_connect: an atom lies more than 30 periodic images away from the cell; wrap the positions first");
   if (nnz < 0) throw GapError("calc_connect: neighbour list exceeds 2^31 entries");
   P->conn_nnz = nnz;
+  P->list_row_cap = 0;
+  P->list_slots = nnz;
   P->row_hint = P->h_pin[2]; P->hint_N = N; P->hint_first = first; P->hint_last = last;
   P->b_j.ensure(sizeof(int) * (size_t)(nnz + 1));
   P->b_s.ensure(sizeof(int) * (size_t)(nnz + 1));
@@ -817,17 +877,53 @@ CalcArgs parse_calc_args(const gap_potential* P, const char* args_str) {
   return a;
 }
 
-// SOAP adjoint + scatter of a coordinate: the DMMA kernels of soap.cu, or the general path of soap_general.cu
+// SOAP adjoint + scatter of a coordinate: the DMMA kernels of soap.cu, or the general path of soap_general.cu.  fpair != NULL: deterministic
+// scatter (force = the per-atom scratch of the centres' own sums, see gap_device.cuh)
 void soap_adjoint_any(const CoordDev& cd, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                       const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
                       const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
-                      double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st, int* launches) {
+                      double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st, int* launches,
+                      double* fpair = nullptr) {
   if (cd.general)
     launch_soap_adjoint_general(cd.d_sp, cd.h, cd.gen, centres, n_centres_dev, n_centres_ub, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec,
-                                ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, st, launches);
+                                ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair, st, launches);
   else
     launch_soap_adjoint(cd.d_sp, cd.h, centres, n_centres_dev, n_centres_ub, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
-                        g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, st, launches);
+                        g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair, st, launches);
+}
+
+// reverse index of the neighbour-list slots by receiving atom, for the deterministic scatter; returns the number of slots
+long det_build_index(gap_potential* P, int N, int first, int last, bool ext, cudaStream_t st) {
+  const int row_cap = ext ? 0 : P->list_row_cap;  // fixed-capacity rows (speculative layout) or packed CSR
+  const long n_slots = ext ? P->ext_nnz : P->list_slots;
+  (void)last;
+  P->b_joff.ensure(sizeof(int) * (size_t)(N + 2));
+  if (P->b_fself.cap < sizeof(double) * 3 * (size_t)(N + 1)) {
+    P->b_fself.ensure(sizeof(double) * 3 * (size_t)(N + 1));
+    CUDA_OK(cudaMemsetAsync(P->b_fself.p, 0, P->b_fself.cap, st));
+  }
+  P->b_fpair.ensure(sizeof(double) * 3 * (size_t)(n_slots + 1));
+  if (P->list_reused && P->det_slots == n_slots) return n_slots;  // same list as in the previous call: the index still holds
+  P->det_slots = n_slots;
+  if (n_slots == 0) {
+    CUDA_OK(cudaMemsetAsync(P->b_joff.p, 0, sizeof(int) * (size_t)(N + 2), st));
+    return 0;
+  }
+  if (n_slots > 2147483000L) throw GapError("deterministic scatter: neighbour list too large");
+  for (DevBuf* b : {&P->b_dkeys, &P->b_dkeys2, &P->b_dvals, &P->b_dvals2}) b->ensure(sizeof(int) * (size_t)n_slots);
+  const int nb = (int)((n_slots + 255) / 256);
+  k_det_keys<<<nb, 256, 0, st>>>(n_slots, row_cap, first, P->cv_end, P->cv_j, N, P->b_dkeys.as<int>(), P->b_dvals.as<int>());
+  int bits = 1;
+  while ((1L << bits) <= N && bits < 31) bits++;
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int)n_slots, 0, bits, st);
+  P->b_dcub.ensure(bytes + 256);
+  bytes = P->b_dcub.cap;
+  cub::DeviceRadixSort::SortPairs(P->b_dcub.p, bytes, P->b_dkeys.as<int>(), P->b_dkeys2.as<int>(), P->b_dvals.as<int>(), P->b_dvals2.as<int>(), (int)n_slots, 0,
+                                  bits, st);
+  k_det_joff<<<nb, 256, 0, st>>>(P->b_dkeys2.as<int>(), n_slots, N, P->b_joff.as<int>());
+  P->launches += 3;
+  return n_slots;
 }
 
 // select + compact the centres of SOAP coordinate cd among atoms [first,last).  The number of centres stays on the
@@ -1033,6 +1129,7 @@ void variance_soap(gap_potential* P, size_t ic, int nc, const int* ncd, bool wan
 struct ExtList {
   const int *off, *j, *s, *Zc;
   int nlocal;
+  long nnz;
 };
 
 void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d_Z, const double* lattice, const int* pbc,
@@ -1082,6 +1179,8 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
     P->cv_off = ext->off; P->cv_end = ext->off + 1; P->cv_j = ext->j; P->cv_s = ext->s;
     P->pending_check = false;
     P->list_valid = false;
+    P->list_reused = false;
+    P->ext_nnz = ext->nnz;
   }
   // The centre selection of the first SOAP coordinate needs Z only: it is launched ahead of the neighbour-list build and, for small
   // partitions, the same launch zeroes the outputs (one launch instead of two at the head of the step).
@@ -1104,6 +1203,14 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
 
   double* d_force = d_packed + 10;
   const double es = P->model.E_scale;
+  // deterministic force scatter: index the list slots by receiving atom once per list
+  const bool det = P->deterministic && want_grad;
+  long det_slots = 0;
+  if (det) {
+    bool any_soap = false;
+    for (const CoordDev& cdv : P->cd) any_soap = any_soap || cdv.kind == DESC_SOAP;
+    if (any_soap) det_slots = det_build_index(P, N, first, last, ext != nullptr, st);
+  }
 
   // virial partial slots
   size_t slots_cap = 0;
@@ -1130,10 +1237,15 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
         // average=T: ONE descriptor (row 0 of x) whatever the number of centres
         covariance_stage(P, cd, glob ? 1 : nc, glob ? nullptr : ncd, want_grad, true, st);
         if (want_grad) {
+          if (det && det_slots > 0) CUDA_OK(cudaMemsetAsync(P->b_fpair.p, 0, sizeof(double) * 3 * (size_t)det_slots, st));  // (unvisited slots)
           soap_adjoint_any(cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
                            P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, P->g_splits,
-                           P->g_split_stride, P->b_epart.as<double>(), P->g_tiles_n, d_le, es, d_force,
-                           P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches);
+                           P->g_split_stride, P->b_epart.as<double>(), P->g_tiles_n, d_le, es, det ? P->b_fself.as<double>() : d_force,
+                           P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches, det ? P->b_fpair.as<double>() : nullptr);
+          if (det) {  // F_j += (pair forces on j, in slot order) + (j's own sum as a centre)
+            k_det_gather<<<(N + 3) / 4, 128, 0, st>>>(N, P->b_joff.as<int>(), P->b_dvals2.as<int>(), P->b_fpair.as<double>(), P->b_fself.as<double>(), d_force);
+            launches += 1;
+          }
           slot += nc;
           mark(P, st, ST_SOAP_ADJ);
         } else if (glob) {  // energy only: e_i shared by all centres (IPModel_GAP.f95:454-459)
@@ -1280,7 +1392,8 @@ void gap_potential_finalise(gap_potential* P) {
   DevBuf* bufs[] = {&P->b_cell_of, &P->b_mshift, &P->b_keys, &P->b_idx, &P->b_slot, &P->b_iota, &P->b_cstart, &P->b_ccount, &P->b_end, &P->b_mask, &P->b_epc, &P->b_lgv, &P->b_gvg, &P->b_varflag, &P->b_vc, &P->b_vq, &P->b_vk, &P->b_spos, &P->b_smshift,
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
-                    &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke, &P->b_lastpos, &P->b_disp, &P->b_resid};
+                    &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke, &P->b_lastpos, &P->b_disp, &P->b_resid,
+                    &P->b_fpair, &P->b_fself, &P->b_dkeys, &P->b_dkeys2, &P->b_dvals, &P->b_dvals2, &P->b_joff, &P->b_dcub};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : P->ev) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);
@@ -1359,6 +1472,13 @@ int gap_potential_comm_info(const gap_potential* P, int* rank, int* n_ranks, cha
     transport[n - 1] = 0;
   }
   return 0;
+}
+
+int gap_potential_set_deterministic(gap_potential* P, int on) {
+  return guard([&] {
+    if (!P) throw GapError("gap_potential_set_deterministic: pot is NULL");
+    P->deterministic = on != 0;
+  });
 }
 
 int gap_potential_set_cutoff_skin(gap_potential* P, double cutoff_skin) {
@@ -1759,7 +1879,7 @@ void quip_lammps_wrapper(int* nlocal, int* nghost, int* atomic_numbers, int* lmp
     CUDA_OK(cudaMemcpyAsync(P->b_xoff.p, off.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, st));
     if (nnz) CUDA_OK(cudaMemcpyAsync(P->b_xj.p, nj.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(P->b_xs.p, 0, sizeof(int) * (nnz + 1), st));
-    ExtList ext{P->b_xoff.as<int>(), P->b_xj.as<int>(), P->b_xs.as<int>(), P->b_zc.as<int>(), *nlocal};
+    ExtList ext{P->b_xoff.as<int>(), P->b_xj.as<int>(), P->b_xs.as<int>(), P->b_zc.as<int>(), *nlocal, (long)nnz};
     const int pbc[3] = {0, 0, 0};
     const int save_rank = P->rank, save_n = P->n_ranks;
     P->rank = 0; P->n_ranks = 1;

@@ -96,6 +96,7 @@ struct Smem {
   double* p;       // d_pad : forward power spectrum (aliases the staging area) ; adjoint u = dE/dp (own region)
   int* nbs;        // NBCAP species
   int* nbj;        // NBCAP neighbour atom
+  int* nbp;        // NBCAP slot of the entry in the neighbour list (deterministic scatter: the pair force is stored per slot)
   int* mt_lm0;     // NTM first row of the lm tile
   int* mt_l;       // NTM its l
   int* col_s;      // K18 species of channel (-1: padding)
@@ -122,7 +123,7 @@ __host__ __device__ __forceinline__ size_t carve(const Geo& g, int d_pad, bool a
     if ((size_t)d_pad * sizeof(double) > stage_bytes) o = ostage + (size_t)d_pad * sizeof(double);
   }
   size_t oi = o;
-  o += sizeof(int) * (NBCAP * 2 + 2 * g.NTM + 2 * g.K18 + NW * SOAP_SPECIES_CAP + SOAP_SPECIES_CAP + 2);
+  o += sizeof(int) * (NBCAP * 3 + 2 * g.NTM + 2 * g.K18 + NW * SOAP_SPECIES_CAP + SOAP_SPECIES_CAP + 2);
   o = (o + 15) & ~(size_t)15;
   if (s) {
     s->Tp = (double*)(base + oT); s->rb = (double*)(base + orb); s->ynorm = (double*)(base + oyn); s->invint = (double*)(base + oinv);
@@ -130,7 +131,7 @@ __host__ __device__ __forceinline__ size_t carve(const Geo& g, int d_pad, bool a
     s->nbd = (double*)(base + onbd); s->nbr = (double*)(base + onbr); s->nbf = (double*)(base + onbf); s->nbdf = (double*)(base + onbdf);
     s->red = (double*)(base + ored); s->rf = (double*)(base + orf); s->Y = (double*)(base + oY); s->acc = (double*)(base + oacc);
     s->p = (double*)(base + op);
-    s->nbs = (int*)(base + oi); s->nbj = s->nbs + NBCAP; s->mt_lm0 = s->nbj + NBCAP; s->mt_l = s->mt_lm0 + g.NTM; s->col_s = s->mt_l + g.NTM;
+    s->nbs = (int*)(base + oi); s->nbj = s->nbs + NBCAP; s->nbp = s->nbj + NBCAP; s->mt_lm0 = s->nbp + NBCAP; s->mt_l = s->mt_lm0 + g.NTM; s->col_s = s->mt_l + g.NTM;
     s->col_a = s->col_s + g.K18; s->wcount = s->col_a + g.K18; s->seg = s->wcount + NW * SOAP_SPECIES_CAP;
   }
   return o;
@@ -221,6 +222,7 @@ __device__ __forceinline__ int gather_neighbours(const SoapDev* sp, const Smem& 
     s.nbdf[q] = df;
     s.nbs[q] = spc;
     s.nbj[q] = j;
+    s.nbp[q] = p;
   }
   __syncthreads();
   return total;
@@ -515,7 +517,7 @@ constexpr int NBW = 64;  // compacted neighbours buffered per warp; longer rows 
 struct WSmem {
   double *Tp, *rb, *ynorm, *invint, *dblf;  // block-shared tables
   double *X, *acc, *nbd, *nbr, *nbf, *nbdf, *p;  // per warp
-  int *nbj, *nbs, *ord;
+  int *nbj, *nbs, *ord, *nbp;
 };
 constexpr int NBWA = 32;  // adjoint: every 32-entry chunk of the neighbour row is worked off at once
 __host__ __device__ __forceinline__ size_t carve_w(const Geo& g, int d_pad, bool adjoint, int warp, WSmem* w, unsigned char* base) {
@@ -530,7 +532,7 @@ __host__ __device__ __forceinline__ size_t carve_w(const Geo& g, int d_pad, bool
   const size_t oreg = o;
   const size_t onbd = take(3 * NBW), onbr = take(NBW), onbf = take(NBW), onbdf = take(adjoint ? NBW : 0);
   const size_t oint = o;
-  o += sizeof(int) * 3 * NBW;
+  o += sizeof(int) * 4 * NBW;
   if (o - oreg < (size_t)d_pad * sizeof(double)) o = oreg + (size_t)d_pad * sizeof(double);
   o = (o + 15) & ~(size_t)15;
   const size_t per_warp = o;
@@ -540,7 +542,7 @@ __host__ __device__ __forceinline__ size_t carve_w(const Geo& g, int d_pad, bool
     unsigned char* wb = base + tables + (size_t)warp * per_warp;
     w->X = (double*)(wb + oX); w->acc = (double*)(wb + oacc); w->nbd = (double*)(wb + onbd); w->nbr = (double*)(wb + onbr);
     w->nbf = (double*)(wb + onbf); w->nbdf = (double*)(wb + onbdf); w->p = (double*)(wb + oreg);
-    w->nbj = (int*)(wb + oint); w->nbs = w->nbj + NBW; w->ord = w->nbs + NBW;
+    w->nbj = (int*)(wb + oint); w->nbs = w->nbj + NBW; w->ord = w->nbs + NBW; w->nbp = w->ord + NBW;
   }
   return tables + (size_t)NW * per_warp;
 }
@@ -583,7 +585,7 @@ __device__ __forceinline__ int gather_chunk_w(const SoapDev* sp, const WSmem& w,
     w.nbd[3 * q + 2] = dd[2];
     w.nbr[q] = r;
     w.nbf[q] = f;
-    if (ADJ) { w.nbdf[q] = df; w.nbj[q] = j; }
+    if (ADJ) { w.nbdf[q] = df; w.nbj[q] = j; w.nbp[q] = p; }
     w.nbs[q] = spc;
   }
   return fill + __popc(bal);
@@ -611,7 +613,7 @@ __device__ __forceinline__ void sort_species_w(const WSmem& w, int fill, int lan
 __device__ __forceinline__ Smem view_of(const WSmem& w) {
   Smem s;
   s.Tp = w.Tp; s.rb = w.rb; s.ynorm = w.ynorm; s.invint = w.invint; s.dblf = w.dblf; s.X = w.X; s.nbd = w.nbd; s.nbr = w.nbr; s.nbf = w.nbf;
-  s.nbdf = w.nbdf; s.nbj = w.nbj; s.nbs = w.nbs; s.p = w.p; s.acc = w.acc;
+  s.nbdf = w.nbdf; s.nbj = w.nbj; s.nbp = w.nbp; s.nbs = w.nbs; s.p = w.p; s.acc = w.acc;
   s.X2 = nullptr; s.red = nullptr; s.rf = nullptr; s.Y = nullptr; s.mt_lm0 = nullptr; s.mt_l = nullptr; s.col_s = nullptr; s.col_a = nullptr;
   s.wcount = nullptr; s.seg = nullptr;
   return s;
@@ -773,7 +775,7 @@ __global__ void __launch_bounds__(NT, (CN > 8 ? 2 : 4)) k_soap_forward_w(const S
 // +m and -m of a thread share the Legendre recursion.  Four shuffles finish the sum over m; lane fk == 0 scatters.
 template <int CN, int CL>
 __device__ __forceinline__ void adjoint_tile(const Smem& s, const Geo& g, const double alpha, const int sk, const int q0, const int tn, const int fr,
-                                             const int fk, const double e_scale, double* __restrict__ force,
+                                             const int fk, const double e_scale, double* __restrict__ force, double* __restrict__ fpair,
                                              double* __restrict__ local_virial, double* accs, const int* ord = nullptr) {
   constexpr bool SPEC = CN != 0;
   constexpr int KS = SPEC ? (CN + 3) / 4 : (SOAP_NMAX_CAP + 3) / 4;   // DMMA k steps over the radial channels of one species
@@ -926,9 +928,14 @@ __device__ __forceinline__ void adjoint_tile(const Smem& s, const Geo& g, const 
     // IPModel_GAP.f95:479-491: F_j -= f_gp ; centre row is minus the sum ; W_j -= (pos_j - pos_i) (x) f_gp
     const int j = s.nbj[q];
     if (force) {
-      atomicAdd(&force[3 * (size_t)j + 0], -f0);
-      atomicAdd(&force[3 * (size_t)j + 1], -f1);
-      atomicAdd(&force[3 * (size_t)j + 2], -f2);
+      if (fpair) {  // deterministic scatter: the pair force goes to the slot of its list entry, summed per atom in a fixed order afterwards
+        const size_t pp = (size_t)s.nbp[q];
+        fpair[3 * pp + 0] = -f0; fpair[3 * pp + 1] = -f1; fpair[3 * pp + 2] = -f2;
+      } else {
+        atomicAdd(&force[3 * (size_t)j + 0], -f0);
+        atomicAdd(&force[3 * (size_t)j + 1], -f1);
+        atomicAdd(&force[3 * (size_t)j + 2], -f2);
+      }
       accs[0] += f0; accs[1] += f1; accs[2] += f2;
     }
     const double wv[9] = {dx * f0, dy * f0, dz * f0, dx * f1, dy * f1, dz * f1, dx * f2, dy * f2, dz * f2};  // column-major (a + 3b)
@@ -953,7 +960,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
                                                         const double* __restrict__ gvec, int ldg, int g_splits, size_t g_split_stride,
                                                         const double* __restrict__ epart, int n_tiles_n, double* __restrict__ local_e,
                                                         double e_scale, double* __restrict__ force, double* __restrict__ vir_part,
-                                                        double* __restrict__ local_virial) {
+                                                        double* __restrict__ local_virial, double* __restrict__ fpair) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_launch_dependents();
   pdl_wait();
@@ -1087,7 +1094,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
       const int sbeg = s.seg[sk], send = s.seg[sk + 1];
       const int ntile = (send - sbeg + 7) >> 3;
       for (int t = (warp + NW - (tbase & (NW - 1))) & (NW - 1); t < ntile; t += NW)
-        adjoint_tile<CN, CL>(s, g, alpha, sk, sbeg + 8 * t, min(8, send - sbeg - 8 * t), fr, fk, e_scale, force, local_virial, accs);
+        adjoint_tile<CN, CL>(s, g, alpha, sk, sbeg + 8 * t, min(8, send - sbeg - 8 * t), fr, fk, e_scale, force, fpair, local_virial, accs);
       tbase += ntile;
     }
     if (pb + NBCAP < pend) __syncthreads();  // the next pass overwrites the compacted list
@@ -1100,7 +1107,8 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
 #pragma unroll 8
     for (int sl = 0; sl < NW * 8; sl++) t += s.acc[sl * 12 + k];
     if (k < 3) {
-      if (force) atomicAdd(&force[3 * (size_t)i + k], t);
+      if (force && fpair) force[3 * (size_t)i + k] = t;  // deterministic scatter: `force` is the per-atom buffer of the centres' own sums
+      else if (force) atomicAdd(&force[3 * (size_t)i + k], t);
     } else if (vir_part) vir_part[9 * (size_t)c + (k - 3)] = t;
   }
 }
@@ -1122,7 +1130,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restr
                                                           const double* __restrict__ pnorm, const double* __restrict__ gvec, int ldg, int g_splits,
                                                           size_t g_split_stride, const double* __restrict__ epart, int n_tiles_n,
                                                           double* __restrict__ local_e, double e_scale, double* __restrict__ force,
-                                                          double* __restrict__ vir_part, double* __restrict__ local_virial) {
+                                                          double* __restrict__ vir_part, double* __restrict__ local_virial, double* __restrict__ fpair) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Geo g = make_geo(CN, CL, CNS);
   constexpr int n = CN, L1 = CL + 1, nlm = (CL + 1) * (CL + 1), K1 = CN * CNS, ns = CNS;
@@ -1266,7 +1274,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restr
     for (int sk = 0; sk < CNS; sk++) {
       const int cnt = seg[sk + 1] - seg[sk];
       for (int t0 = 0; t0 < cnt; t0 += 8)
-        adjoint_tile<CN, CL>(s, g, alpha, sk, seg[sk] + t0, min(8, cnt - t0), fr, fk, e_scale, force, local_virial, accs, CNS == 1 ? nullptr : w.ord);
+        adjoint_tile<CN, CL>(s, g, alpha, sk, seg[sk] + t0, min(8, cnt - t0), fr, fk, e_scale, force, fpair, local_virial, accs, CNS == 1 ? nullptr : w.ord);
     }
     __syncwarp();
   }
@@ -1277,7 +1285,8 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restr
 #pragma unroll
     for (int sl = 0; sl < 8; sl++) t += w.acc[sl * 12 + lane];
     if (lane < 3) {
-      if (force) atomicAdd(&force[3 * (size_t)i + lane], t);
+      if (force && fpair) force[3 * (size_t)i + lane] = t;
+      else if (force) atomicAdd(&force[3 * (size_t)i + lane], t);
     } else if (vir_part) vir_part[9 * (size_t)c + (lane - 3)] = t;
   }
 }
@@ -1342,7 +1351,7 @@ void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres
 void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
                          const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
-                         double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st,
+                         double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, double* fpair, cudaStream_t st,
                          int* launches) {
   const int n_centres = n_centres_ub;
   if (n_centres <= 0) return;
@@ -1355,7 +1364,7 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
     cudaFuncSetAttribute(k_soap_adjoint_w<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);                                   \
     launch_pdl(k_soap_adjoint_w<N, L, S>, dim3((n_centres + NW - 1) / NW), dim3(NT), smw, st, sp, centres, n_centres_dev, n_centres, nbr_off, nbr_end,  \
                nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part,  \
-               local_virial);                                                                                                                \
+               local_virial, fpair);                                                                                                         \
     return;                                                                                                                                   \
   }
   SOAP_ADJOINT_W(GOW)
@@ -1364,14 +1373,14 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
   if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                                     \
     cudaFuncSetAttribute(k_soap_adjoint<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                      \
     launch_pdl(k_soap_adjoint<N, L, S>, dim3(n_centres), dim3(NT), sm, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, \
-               pnorm, gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);                \
+               pnorm, gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair);         \
     return;                                                                                                                                   \
   }
   SOAP_SPECIALISATIONS(GO)
 #undef GO
   cudaFuncSetAttribute(k_soap_adjoint<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   launch_pdl(k_soap_adjoint<0, 0, 0>, dim3(n_centres), dim3(NT), sm, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm,
-             gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial);
+             gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair);
 }
 
 }  // namespace gapb200

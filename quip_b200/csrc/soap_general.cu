@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NT) k_soap_adjoint_gen(const SoapDev* __restri
                                                          const double* __restrict__ gvec, int ldg, int g_splits, size_t g_split_stride,
                                                          const double* __restrict__ epart, int n_tiles_n, double* __restrict__ local_e, double e_scale,
                                                          double* __restrict__ force, double* __restrict__ vir_part, double* __restrict__ local_virial,
-                                                         const double* __restrict__ Lt_global) {
+                                                         const double* __restrict__ Lt_global, double* __restrict__ fpair) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int c = blockIdx.x;
   if (c >= *n_centres_dev) {
@@ -291,9 +291,14 @@ __global__ void __launch_bounds__(NT) k_soap_adjoint_gen(const SoapDev* __restri
         const double f2 = (SA * uz + (G2 - uz * ug) * rinv) * e_scale;
         const int j = s.nbj[q];
         if (force) {  // IPModel_GAP.f95:479-491: F_j -= f_gp ; the centre row is minus the sum ; W_j -= (pos_j - pos_i) (x) f_gp
-          atomicAdd(&force[3 * (size_t)j + 0], -f0);
-          atomicAdd(&force[3 * (size_t)j + 1], -f1);
-          atomicAdd(&force[3 * (size_t)j + 2], -f2);
+          if (fpair) {  // deterministic scatter (see gap_device.cuh): slot = position of the entry in the neighbour list
+            const size_t pp = (size_t)(pb + q);
+            fpair[3 * pp + 0] = -f0; fpair[3 * pp + 1] = -f1; fpair[3 * pp + 2] = -f2;
+          } else {
+            atomicAdd(&force[3 * (size_t)j + 0], -f0);
+            atomicAdd(&force[3 * (size_t)j + 1], -f1);
+            atomicAdd(&force[3 * (size_t)j + 2], -f2);
+          }
           acc12[0] += f0; acc12[1] += f1; acc12[2] += f2;
         }
         const double wv[9] = {dx * f0, dy * f0, dz * f0, dx * f1, dy * f1, dz * f1, dx * f2, dy * f2, dz * f2};  // column-major (a + 3b)
@@ -307,7 +312,9 @@ __global__ void __launch_bounds__(NT) k_soap_adjoint_gen(const SoapDev* __restri
     __syncthreads();  // the next chunk overwrites the neighbour arrays
   }
   if (threadIdx.x == 0) {
-    if (force)
+    if (force && fpair)
+      for (int k = 0; k < 3; k++) force[3 * (size_t)i + k] = acc12[k];
+    else if (force)
       for (int k = 0; k < 3; k++) atomicAdd(&force[3 * (size_t)i + k], acc12[k]);
     if (vir_part)
       for (int k = 0; k < 9; k++) vir_part[9 * (size_t)c + k] = acc12[3 + k];
@@ -436,7 +443,7 @@ void launch_soap_adjoint_general(const SoapDev* sp, const SoapDev& h, const Soap
                                  const int* nbr_off, const int* nbr_end, const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat,
                                  const double* x, const double* xlm, const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride,
                                  const double* epart, int n_tiles_n, double* local_e, double e_scale, double* force, double* vir_part,
-                                 double* local_virial, cudaStream_t st, int* launches) {
+                                 double* local_virial, double* fpair, cudaStream_t st, int* launches) {
   if (n_centres_ub <= 0) return;
   const size_t sm = soap_general_smem(h, g);
   cudaFuncSetAttribute(k_soap_adjoint_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -450,12 +457,12 @@ void launch_soap_adjoint_general(const SoapDev* sp, const SoapDev& h, const Soap
     k_soap_global_lambda<<<1, NT, sm, st>>>(sp, g, g.Xg, x, pnorm, gvec, g_splits, g_split_stride, g.Lt);
     *launches += 1;
     k_soap_adjoint_gen<<<n_centres_ub, NT, sm, st>>>(sp, g, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
-                                                     g_splits, g_split_stride, nullptr, 0, local_e, e_scale, force, vir_part, local_virial, g.Lt);
+                                                     g_splits, g_split_stride, nullptr, 0, local_e, e_scale, force, vir_part, local_virial, g.Lt, fpair);
     *launches += 1;
     return;
   }
   k_soap_adjoint_gen<<<n_centres_ub, NT, sm, st>>>(sp, g, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
-                                                   g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, nullptr);
+                                                   g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, nullptr, fpair);
   *launches += 1;
 }
 

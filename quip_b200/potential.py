@@ -36,6 +36,7 @@ ABI = {
     "gap_potential_set_comm": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "gap_potential_comm_info": (C.c_int, [C.c_void_p, c_ip, c_ip, C.c_char_p, C.c_size_t]),
     "gap_potential_comm_timing": (C.c_int, [C.c_void_p, c_dp, c_dp]),
+    "gap_potential_set_deterministic": (C.c_int, [C.c_void_p, C.c_int]),
     "gap_potential_set_cutoff_skin": (C.c_int, [C.c_void_p, C.c_double]),
     "gap_potential_connect_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "gap_potential_calc": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
@@ -188,6 +189,10 @@ class Potential:
 
     def set_partition(self, rank, n_ranks):
         _check(load_library().gap_potential_set_partition(self._h, int(rank), int(n_ranks)))
+
+    def set_deterministic(self, on=True):
+        """Bitwise reproducible forces: pair forces are summed per receiving atom in a fixed order instead of with FP64 atomics."""
+        _check(load_library().gap_potential_set_deterministic(self._h, int(bool(on))))
 
     def set_cutoff_skin(self, cutoff_skin):
         """``at%cutoff_skin`` (Connection.f95:1085-1128): build the neighbour list out to cutoff + skin and reuse it while no atom has moved

@@ -898,3 +898,49 @@ def test_md_run_device_reduce_hook_is_called(si_model, si_frames):
     assert len(calls) == 5 and all(s == calls[0] for s in calls)  # initial evaluation + 4 steps, always the same stream
     assert np.abs(d_pos.cpu().numpy() - at1.positions).max() < 1e-10
     assert np.abs(ep - ep1).max() < 1e-9
+
+
+def test_deterministic_scatter_is_bitwise_reproducible(tmp_path, si_model, si_frames, golden):
+    # gap_potential_set_deterministic: forces identical to the last bit between runs and between handles, equal to the atomic path within
+    # rounding and to the oracle within the usual bar; also with skin-based list reuse, multi-species (general path) and the LAMMPS entry
+    atoms, xml = syn.build_config_A(str(tmp_path), _oracle_desc, n_cells=4, M=120, seed=1)
+    om = orc.Model(xml)
+    o = om.calc(atoms)
+    ref = Potential("", param_filename=xml).calc(atoms, force=True, virial=True)
+    runs = []
+    for k in range(3):
+        p = Potential("", param_filename=xml)
+        p.set_deterministic(True)
+        for _ in range(2 + k):  # different call histories: exact list on the first call, speculative rows afterwards
+            r = p.calc(atoms, force=True, virial=True)
+        runs.append(r["force"].copy())
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    assert np.abs(runs[0] - ref["force"]).max() < 1e-12
+    assert np.abs(runs[0] - o["force"]).max() < TOL_F
+    # skin reuse + deterministic
+    p = Potential("", param_filename=xml)
+    p.set_deterministic(True)
+    p.set_cutoff_skin(0.4)
+    rng = np.random.default_rng(2)
+    pos = atoms.positions + rng.uniform(-0.03, 0.03, size=atoms.positions.shape)
+    p.calc(atoms, force=True)
+    r1 = p.calc(Atoms(atoms.numbers, pos, atoms.cell, True), force=True)
+    assert p.connect_stats()["reuses"] == 1
+    o1 = om.calc(Atoms(atoms.numbers, pos, atoms.cell, True))
+    assert np.abs(r1["force"] - o1["force"]).max() < TOL_F
+    # two-descriptor model (distance_2b + SOAP) and a general-path multi-species model
+    pot, om2, xml2 = si_model
+    q = Potential("IP GAP", param_filename=xml2)
+    q.set_deterministic(True)
+    a = si_frames[8]
+    f1, f2 = q.calc(a, force=True)["force"], q.calc(a, force=True)["force"]
+    assert np.array_equal(f1, f2) and np.abs(f1 - om2.calc(a)["force"]).max() < TOL_F
+    desc = "soap n_Z=2 n_species=4 Z={23 42} species_Z={23 41 42 73} n_max=4 l_max=3 cutoff=4.5 atom_sigma=0.45 Z_mix=T K=3 coupling=F"
+    ds = quad_datasets(golden, True)
+    xml3 = multi_species_model(str(tmp_path), desc, ds, 8, seed=31, zeta=2.0)
+    g = Potential("", param_filename=xml3)
+    g.set_deterministic(True)
+    om3 = orc.Model(xml3)
+    for b in ds:
+        f1, f2 = g.calc(b, force=True)["force"], g.calc(b, force=True)["force"]
+        assert np.array_equal(f1, f2) and np.abs(f1 - om3.calc(b)["force"]).max() < TOL_F
