@@ -95,6 +95,25 @@ __device__ __forceinline__ void g_mix(const GSmem& s, const SoapGenDev& g, int n
   }
 }
 
+// dE/dY1(lm, ia) = sum over the elements k with ia_k = ia of  w_k Y2(lm, jb_k),  dE/dY2(lm, jb) likewise with Y1,  w_k = tlpo_l fac_k dE/dp(l, k):
+// one thread per output, the elements visited in list order (deterministic; no shared-memory atomics)
+__device__ __forceinline__ void g_dY(const GSmem& s, const SoapGenDev& g, int nlm, int L1, int np) {
+  for (int idx = threadIdx.x; idx < nlm * (g.Ka + g.Kb); idx += NT) {
+    const bool second = idx >= nlm * g.Ka;
+    const int t = second ? idx - nlm * g.Ka : idx, Kw = second ? g.Kb : g.Ka;
+    const int lm = t / Kw, k = t - lm * Kw, l = s.l_of[lm];
+    const double tl = s.tlpo[l];
+    double acc = 0.0;
+    for (int e = 0; e < np; e++) {
+      const int ia = g.pair_ia[e], jb = g.pair_jb[e];
+      if ((second ? jb : ia) != k) continue;
+      const double w = s.p[l + L1 * e] * tl * g.pair_fac[e];
+      acc += w * (second ? s.Y1[lm * g.Ka + ia] : s.Y2[lm * g.Kb + jb]);
+    }
+    (second ? s.dY2 : s.dY1)[t] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(NT) k_soap_forward_gen(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ centres,
                                                          const int* __restrict__ n_centres_dev, const int* __restrict__ nbr_off,
                                                          const int* __restrict__ nbr_end, const int* __restrict__ nbr_j, const int* __restrict__ nbr_s,
@@ -217,15 +236,7 @@ __global__ void __launch_bounds__(NT) k_soap_adjoint_gen(const SoapDev* __restri
     for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = (s.p[q] - xr[q] * sdot) / nrm;
   g_mix(s, g, nlm, K1);
   __syncthreads();
-  // dE/dY1(ia) += w Y2(jb), dE/dY2(jb) += w Y1(ia), w = tlpo fac dE/dp   (product rule on the element list)
-  for (int idx = threadIdx.x; idx < L1 * np; idx += NT) {
-    const int k = idx / L1, l = idx - k * L1, ia = g.pair_ia[k], jb = g.pair_jb[k];
-    const double w = s.p[idx] * s.tlpo[l] * g.pair_fac[k];
-    for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) {
-      atomicAdd(&s.dY1[lm * g.Ka + ia], w * s.Y2[lm * g.Kb + jb]);
-      atomicAdd(&s.dY2[lm * g.Kb + jb], w * s.Y1[lm * g.Ka + ia]);
-    }
-  }
+  g_dY(s, g, nlm, L1, np);  // dE/dY1, dE/dY2 (product rule on the element list)
   __syncthreads();
   // Lambda = dE/dX = dE/dY1 W1^T + dE/dY2 W2^T  (into X)
   for (int idx = threadIdx.x; idx < nlm * K1; idx += NT) {
@@ -383,14 +394,7 @@ __global__ void __launch_bounds__(NT) k_soap_global_lambda(const SoapDev* __rest
     for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = (s.p[q] - x[q] * sdot) / nrm;
   g_mix(s, g, nlm, K1);
   __syncthreads();
-  for (int idx = threadIdx.x; idx < L1 * np; idx += NT) {
-    const int k = idx / L1, l = idx - k * L1, ia = g.pair_ia[k], jb = g.pair_jb[k];
-    const double w = s.p[idx] * s.tlpo[l] * g.pair_fac[k];
-    for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) {
-      atomicAdd(&s.dY1[lm * g.Ka + ia], w * s.Y2[lm * g.Kb + jb]);
-      atomicAdd(&s.dY2[lm * g.Kb + jb], w * s.Y1[lm * g.Ka + ia]);
-    }
-  }
+  g_dY(s, g, nlm, L1, np);
   __syncthreads();
   for (int idx = threadIdx.x; idx < nlm * K1; idx += NT) {
     const int lm = idx / K1, ic = idx - lm * K1;
