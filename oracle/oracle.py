@@ -71,6 +71,8 @@ def lib():
         L.orc_model_add_soap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_dp, c_dp, c_dp, C.c_double, C.c_double]
         L.orc_model_add_distance_2b.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp,
                                                 c_dp, c_dp, C.c_double, C.c_double, C.c_int, c_dp, c_dp, C.c_int, C.c_double, C.c_int]
+        L.orc_model_add_angle_3b.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp,
+                                             C.c_double, C.c_double, c_dp]
         L.orc_model_set_resid.argtypes = [C.c_void_p, c_ip]
         L.orc_model_calc.argtypes = [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_ip, C.c_double, C.c_int, C.c_int, C.c_int,
                                      c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
@@ -653,6 +655,14 @@ class Model:
                                             int(a.get("Z1", 0)), int(a.get("Z2", 0)), co["M"], _dp(X), _dp(al), _dp(cu),
                                             co["delta"], co["f0"], n_exp, _dp(th), _dp(ex), int(a.get("tail_exponent", 0)),
                                             _f(a.get("tail_range", 1.0)), 1 if intra else (2 if inter else 0))
+            elif kind == "angle_3b":
+                a = parse_args(desc)  # angle_3b_initialise, descriptors.f95:1886-1911 (Z_center has the alternative key Z)
+                if co["covariance_type"] != 1 or co["n_permutations"] != 1 or co["d"] != 3:
+                    raise NotImplementedError("angle_3b variant")
+                th = np.ascontiguousarray(co["theta"], dtype=np.float64)
+                L.orc_model_add_angle_3b(self.h, _f(a.get("cutoff", 0.0)), _f(a.get("cutoff_transition_width", 0.5)),
+                                         int(a.get("Z_center", a.get("Z", 0))), int(a.get("Z1", 0)), int(a.get("Z2", 0)), co["M"],
+                                         _dp(X), _dp(al), _dp(cu), co["delta"], co["f0"], _dp(th))
             else:
                 raise NotImplementedError("descriptor %s" % kind)
 

@@ -223,6 +223,20 @@ void launch_pair2b(Pair2bDev p, int first, int last, const int* nbr_off, const i
                    const int* Zc /* < 0: not a centre */, int scatter /* 1: atom mask active, scatter to the pair partner */, Lattice9 lat, double e_scale, int do_grad, double* local_e, double* force, double* vir_part, double* local_virial,
                    cudaStream_t st, int* launches, int* n_blocks_out);
 
+// ---- angle3b.cu ----------------------------------------------------------------------------
+struct Angle3bDev {
+  double cutoff, ctw;
+  double inv_theta[3];
+  double e_f0;            // f0^2 sum_s alpha_s sparseCutoff_s: the constant part of every instance's energy (gp_predict.f95:3812)
+  int Zc, Z1, Z2, M;
+  const double* table;    // [M][4]: sparseX_s / theta (3), alpha_s sparseCutoff_s delta^2
+};
+// cidx: int scratch parallel to the list slots (compacted in-cutoff entries of each row).  fpair != NULL: deterministic mode (pair forces per
+// list slot, `force` = the per-atom buffer of the centres' own sums)
+void launch_angle3b(Angle3bDev p, int first, int last, const int* nbr_off, const int* nbr_end, const int* nbr_j, const int* nbr_s, const double* pos,
+                    const int* Z, const int* Zc /* < 0: not a centre */, Lattice9 lat, double e_scale, int do_grad, double* local_e, double* force,
+                    double* fpair, double* vir_part, double* local_virial, int* cidx, cudaStream_t st, int* launches, int* n_blocks_out);
+
 // ---- variance.cu (optional local_gap_variance output; cuBLAS / cuSOLVER loaded on first use) -----------------
 }  // namespace gapb200
 #include <string>

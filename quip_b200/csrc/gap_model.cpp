@@ -615,6 +615,17 @@ Distance2bSpec distance_2b_from_string(const std::string& desc) {
   return s;
 }
 
+Angle3bSpec angle_3b_from_string(const std::string& desc) {
+  ArgDict a(desc);
+  Angle3bSpec s;
+  s.cutoff = a.real("cutoff", 0.0);
+  s.cutoff_transition_width = a.real("cutoff_transition_width", 0.5);
+  s.Zc = (int)a.integer("Z_center", a.integer("Z", 0));
+  s.Z1 = (int)a.integer("Z1", 0);
+  s.Z2 = (int)a.integer("Z2", 0);
+  return s;
+}
+
 // ======================================================================================
 // minimal SAX-style XML scanner (stands in for FoX, src/fox)
 // ======================================================================================
@@ -981,8 +992,17 @@ GapModel load_gap_model(const std::string& args_str_in, const std::string& param
       if ((int)c.theta.size() < c.d) throw GapError("gpCoordinates: ard_se covariance needs one theta per dimension");
       for (int k = 0; k < c.d; k++)
         if (c.theta[k] == 0.0) throw GapError("gpCoordinates: ard_se covariance with theta = 0");
+    } else if (f[0] == "angle_3b") {
+      c.kind = DESC_ANGLE_3B;
+      c.a3b = angle_3b_from_string(desc);
+      if (c.d != 3) throw GapError("gpCoordinates dimensions=" + std::to_string(c.d) + " does not match angle_3b (3)");
+      if (c.covariance_type != COVARIANCE_ARD_SE || c.n_permutations != 1)
+        throw GapError("angle_3b is supported with covariance_type=ard_se and n_permutations=1 only");
+      if ((int)c.theta.size() < c.d) throw GapError("gpCoordinates: ard_se covariance needs one theta per dimension");
+      for (int k = 0; k < c.d; k++)
+        if (c.theta[k] == 0.0) throw GapError("gpCoordinates: ard_se covariance with theta = 0");
     } else {
-      throw GapError("descriptor '" + f[0] + "' is not supported by the B200 path (soap and distance_2b only)");
+      throw GapError("descriptor '" + f[0] + "' is not supported by the B200 path (soap, distance_2b and angle_3b only)");
     }
     if (c.cutoff() > m.cutoff) m.cutoff = c.cutoff();
     m.coord.push_back(std::move(c));

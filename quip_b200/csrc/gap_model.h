@@ -8,6 +8,7 @@
 //   param_read_line grammar         src/libAtoms/ParamReader.f95:393-518
 //   soap_initialise                 src/GAP/descriptors.f95:2476-2642
 //   distance_2b_initialise          src/GAP/descriptors.f95:1757-1818
+//   angle_3b_initialise             src/GAP/descriptors.f95:1886-1911
 #pragma once
 #include <map>
 #include <stdexcept>
@@ -73,13 +74,18 @@ struct Distance2bSpec {
   int intra_mode = 0;             // 0: all pairs, 1: only_intra, 2: only_inter
   std::string resid_name;
 };
+struct Angle3bSpec {  // angle_3b_initialise, descriptors.f95:1886-1911 (Z_center has the alternative key Z)
+  double cutoff = 0, cutoff_transition_width = 0.5;
+  int Zc = 0, Z1 = 0, Z2 = 0;
+};
 // soap_initialise; calc_xml_version = the xml_version soap_calc would see (<0: descriptor-only default)
 SoapSpec soap_from_string(const std::string& desc, long calc_xml_version);
 Distance2bSpec distance_2b_from_string(const std::string& desc);
+Angle3bSpec angle_3b_from_string(const std::string& desc);
 
 // ---- model --------------------------------------------------------------------------
 enum { COVARIANCE_ARD_SE = 1, COVARIANCE_DOT_PRODUCT = 2 };
-enum { DESC_DISTANCE_2B = 1, DESC_SOAP = 2 };
+enum { DESC_DISTANCE_2B = 1, DESC_SOAP = 2, DESC_ANGLE_3B = 3 };
 
 struct Coordinate {
   int kind = 0, covariance_type = 0, d = 0, M = 0, n_permutations = 1;
@@ -88,7 +94,8 @@ struct Coordinate {
   std::string label, descriptor_str;
   SoapSpec soap;
   Distance2bSpec d2b;
-  double cutoff() const { return kind == DESC_SOAP ? soap.cutoff : d2b.cutoff; }
+  Angle3bSpec a3b;
+  double cutoff() const { return kind == DESC_SOAP ? soap.cutoff : (kind == DESC_ANGLE_3B ? a3b.cutoff : d2b.cutoff); }
 };
 
 struct GapModel {

@@ -77,6 +77,9 @@ struct CoordDev {
   // distance_2b
   Pair2bDev p2;
   double *x2 = nullptr, *a2 = nullptr, *c2 = nullptr;
+  // angle_3b
+  Angle3bDev p3;
+  double* t3 = nullptr;
   // variance estimate (built on first use for a given regularisation): soap = lower Cholesky factor of k_mm (M x M,
   // column-major), distance_2b = explicit inverse of k_mm (M x M)
   double* var_mat = nullptr;
@@ -135,6 +138,7 @@ struct gap_potential {
   int list_row_cap = 0;        // layout of the handle's own list: fixed-capacity rows of this many slots, or 0 = packed CSR
   long list_slots = 0;         // slots of the handle's own list (row_cap * centres, or the entry count)
   DevBuf b_fpair, b_fself, b_dkeys, b_dkeys2, b_dvals, b_dvals2, b_joff, b_dcub;
+  DevBuf b_a3idx;              // angle_3b: compacted in-cutoff entries of each list row (int per slot)
   // skin-based reuse of the neighbour list (calc_connect with cutoff_skin, Connection.f95:1085-1128)
   double cutoff_skin = 0.0;
   bool list_valid = false;     // cv_* describe a list built with last_cut for the geometry remembered below
@@ -799,6 +803,22 @@ void upload_model(gap_potential* P) {
       cd.cp.zeta = c.zeta;
       double zi = std::nearbyint(c.zeta);
       cd.cp.zeta_int = (std::fabs(c.zeta - zi) < 1e-12 * std::fmax(1.0, std::fabs(c.zeta)) && zi >= 0 && zi <= 64) ? (int)zi : -1;
+    } else if (c.kind == DESC_ANGLE_3B) {
+      std::vector<double> tb((size_t)4 * (c.M > 0 ? c.M : 1), 0.0);
+      double ef0 = 0.0;
+      for (int m = 0; m < c.M; m++) {  // sparseX / theta as gpCoordinates_precalculate_sparse does (gp_predict.f95:3901-3923)
+        for (int q = 0; q < 3; q++) tb[(size_t)4 * m + q] = c.sparseX[(size_t)m * 3 + q] / c.theta[q];
+        tb[(size_t)4 * m + 3] = c.alpha[m] * c.sparseCutoff[m] * c.delta * c.delta;
+        ef0 += c.alpha[m] * c.sparseCutoff[m];
+      }
+      CUDA_OK(cudaMalloc(&cd.t3, tb.size() * sizeof(double)));
+      CUDA_OK(cudaMemcpy(cd.t3, tb.data(), tb.size() * sizeof(double), cudaMemcpyHostToDevice));
+      memset(&cd.p3, 0, sizeof(cd.p3));
+      cd.p3.cutoff = c.a3b.cutoff; cd.p3.ctw = c.a3b.cutoff_transition_width;
+      for (int q = 0; q < 3; q++) cd.p3.inv_theta[q] = 1.0 / c.theta[q];
+      cd.p3.e_f0 = c.f0 * c.f0 * ef0;
+      cd.p3.Zc = c.a3b.Zc; cd.p3.Z1 = c.a3b.Z1; cd.p3.Z2 = c.a3b.Z2; cd.p3.M = c.M;
+      cd.p3.table = cd.t3;
     } else {
       const int ne = (int)c.d2b.exponents.size();
       std::vector<double> xs((size_t)(c.M > 0 ? c.M : 1) * ne, 0.0), al(c.M > 0 ? c.M : 1, 0.0), cu(al.size(), 0.0);
@@ -1018,6 +1038,7 @@ void ensure_variance_model(gap_potential* P, size_t ic, double reg, cudaStream_t
   if (cd.var_mat && cd.var_reg == reg) return;  // :3990-3996
   if (cd.var_mat) { cudaFree(cd.var_mat); cd.var_mat = nullptr; }
   const int M = c.M;
+  if (c.kind == DESC_ANGLE_3B) throw GapError("GAP variance for angle_3b coordinates is not supported by the B200 path");
   if (M <= 0) return;
   int launches = 0;
   if (cd.kind == DESC_SOAP) {
@@ -1207,8 +1228,8 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
   const bool det = P->deterministic && want_grad;
   long det_slots = 0;
   if (det) {
-    bool any_soap = false;
-    for (const CoordDev& cdv : P->cd) any_soap = any_soap || cdv.kind == DESC_SOAP;
+    bool any_soap = false;  // (or angle_3b: the coordinates whose pair forces go through the slot index)
+    for (const CoordDev& cdv : P->cd) any_soap = any_soap || cdv.kind == DESC_SOAP || cdv.kind == DESC_ANGLE_3B;
     if (any_soap) det_slots = det_build_index(P, N, first, last, ext != nullptr, st);
   }
 
@@ -1263,6 +1284,22 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
           mark(P, st, ST_OTHER);
         }
       }
+    } else if (cd.kind == DESC_ANGLE_3B) {
+      int nb = 0;
+      if (ca.do_var) throw GapError("GAP variance for angle_3b coordinates is not supported by the B200 path");
+      const long n_slots = ext ? P->ext_nnz : P->list_slots;
+      P->b_a3idx.ensure(sizeof(int) * (size_t)(n_slots + 1));
+      const bool det3 = det && det_slots > 0;
+      if (det3) CUDA_OK(cudaMemsetAsync(P->b_fpair.p, 0, sizeof(double) * 3 * (size_t)det_slots, st));  // (slots outside this descriptor's cutoff)
+      launch_angle3b(cd.p3, first, last, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, d_Zc, lat, es, want_grad ? 1 : 0, d_le,
+                     want_grad ? (det3 ? P->b_fself.as<double>() : d_force) : nullptr, det3 ? P->b_fpair.as<double>() : nullptr,
+                     want_grad ? P->b_vir.as<double>() + 9 * slot : nullptr, want_grad ? d_lv : nullptr, P->b_a3idx.as<int>(), st, &launches, &nb);
+      if (det3) {
+        k_det_gather<<<(N + 3) / 4, 128, 0, st>>>(N, P->b_joff.as<int>(), P->b_dvals2.as<int>(), P->b_fpair.as<double>(), P->b_fself.as<double>(), d_force);
+        launches += 1;
+      }
+      if (want_grad) slot += nb;
+      mark(P, st, ST_PAIR2B);
     } else {
       int nb = 0;
       Pair2bDev p2 = cd.p2;
@@ -1382,7 +1419,7 @@ void gap_potential_finalise(gap_potential* P) {
     cudaFree(cd.gen_blob);
     cudaFree(cd.gen_global);
     cudaFree(cd.d_sp); cudaFree(cd.sp_rows); cudaFree(cd.st_rows); cudaFree(cd.alpha); cudaFree(cd.scut);
-    cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2); cudaFree(cd.var_mat);
+    cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2); cudaFree(cd.t3); cudaFree(cd.var_mat);
   }
   cudaFree(P->d_e0);
   cudaFree(P->d_fin_counter);
@@ -1393,7 +1430,7 @@ void gap_potential_finalise(gap_potential* P) {
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
                     &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke, &P->b_lastpos, &P->b_disp, &P->b_resid,
-                    &P->b_fpair, &P->b_fself, &P->b_dkeys, &P->b_dkeys2, &P->b_dvals, &P->b_dvals2, &P->b_joff, &P->b_dcub};
+                    &P->b_fpair, &P->b_fself, &P->b_dkeys, &P->b_dkeys2, &P->b_dvals, &P->b_dvals2, &P->b_joff, &P->b_dcub, &P->b_a3idx};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : P->ev) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);
@@ -2091,6 +2128,8 @@ int gap_model_describe(const char* args_str, const char* param_str, const char* 
           for (size_t k = 0; k < s.pair_ia.size(); k++) os << " " << s.pair_ia[k] << ":" << s.pair_jb[k] << ":" << s.pair_fac[k];
           os << "\n";
         }
+      } else if (c.kind == DESC_ANGLE_3B) {
+        os << "angle_3b " << i << " Z " << c.a3b.Zc << " Z1 " << c.a3b.Z1 << " Z2 " << c.a3b.Z2 << " ctw " << c.a3b.cutoff_transition_width << "\n";
       } else {
         os << "distance_2b " << i << " Z1 " << c.d2b.Z1 << " Z2 " << c.d2b.Z2 << " ctw " << c.d2b.cutoff_transition_width << "\n";
       }

@@ -861,6 +861,76 @@ def test_distance_2b_options_vs_oracle(golden, tmp_path):
         fresh.calc(quad_datasets(golden, True)[0])
 
 
+# ----------------------------------------------------------------------------------------------------
+# angle_3b (descriptors.f95:1886-1911, 4932-5112): three-body descriptor with ARD_SE covariance
+# ----------------------------------------------------------------------------------------------------
+def _angle_3b_model(tmpdir, seed=11, M=12, with_si=False):
+    rng = np.random.default_rng(seed)
+    def coord(desc, M=M):
+        X = np.column_stack([rng.uniform(3.0, 7.5, size=M), rng.uniform(0.0, 2.0, size=M), rng.uniform(1.5, 6.0, size=M)])
+        return {"descriptor": desc, "covariance_type": 1, "delta": 0.6, "f0": 0.02, "theta": list(rng.uniform(0.8, 2.0, size=3)),
+                "sparseX": X, "alpha": rng.normal(0.0, 0.3, size=M), "sparseCutoff": rng.uniform(0.7, 1.0, size=M)}
+    if with_si:
+        return write_gap_xml(os.path.join(tmpdir, "angle_3b_si.xml"), [coord("angle_3b cutoff=3.7 cutoff_transition_width=0.6 Z_center=14 Z1=14 Z2=14", M=40)],
+                             e0={14: -0.3})
+    coords = [coord("angle_3b cutoff=4.2 cutoff_transition_width=0.7 Z_center=0 Z1=0 Z2=0"),
+              coord("angle_3b cutoff=4.6 Z=23 Z1=41 Z2=42"),
+              coord("angle_3b cutoff=4.0 Z_center=41 Z1=23 Z2=23")]
+    return write_gap_xml(os.path.join(tmpdir, "angle_3b.xml"), coords, e0={23: 0.1, 41: -0.2, 42: 0.3, 73: 0.4})
+
+
+def test_angle_3b_vs_oracle(golden, tmp_path):
+    xml = _angle_3b_model(str(tmp_path))
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    assert pot.cutoff() == 4.6 and pot.n_coordinate == 3
+    for pbc in (True, False):
+        for a in quad_datasets(golden, pbc):
+            check_efv(pot, om, a)
+    a = quad_datasets(golden, True)[1]
+    # atom mask: only masked atoms are centres, their neighbours still take forces (IPModel_GAP.f95:344-346, 472-491)
+    mask = np.arange(len(a)) % 2 == 0
+    am = Atoms(a.numbers, a.positions, a.cell, True, arrays={"sel": mask})
+    r = pot.calc(am, force=True, virial=True, local_energy=True, args_str="atom_mask_name=sel")
+    o = om.calc(a, local_energy=True, atom_mask=mask)
+    assert abs(r["energy"] - o["energy"]) < 1e-9 and np.abs(r["force"] - o["force"]).max() < TOL_F and np.abs(r["virial"] - o["virial"]).max() < TOL_V
+    # energy_per_coordinate and only_descriptor
+    r = pot.calc(a, args_str="energy_per_coordinate=epc")
+    o = om.calc(a, energy_per_coordinate=True, force=False, virial=False)
+    assert np.abs(r["epc"] - o["energy_per_coordinate"]).max() < 1e-9
+    r1 = pot.calc(a, args_str="only_descriptor=2")
+    assert abs(r1["energy"] - (o["energy_per_coordinate"][1] + sum({23: 0.1, 41: -0.2, 42: 0.3, 73: 0.4}[int(z)] for z in a.numbers))) < 1e-9
+    # the variance of an angle_3b coordinate is refused, not approximated
+    with pytest.raises(RuntimeError, match="angle_3b"):
+        pot.calc(a, args_str="local_gap_variance=var")
+
+
+def test_angle_3b_silicon_frames_partition_and_deterministic(si_frames, tmp_path):
+    # a Si three-body coordinate on the reference's Si.np1.xyz frames (up to 96 atoms, 30-odd neighbours inside 3.7 A pairs), whole and as
+    # the sum of three centre blocks; deterministic mode: two calls bit-identical and equal to the default within rounding
+    xml = _angle_3b_model(str(tmp_path), with_si=True)
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    for k in (3, 8, 16):
+        check_efv(pot, om, si_frames[k])
+    a = si_frames[16]
+    full = pot.calc(a, force=True, virial=True)
+    N = len(a)
+    acc = {"energy": 0.0, "force": np.zeros((N, 3)), "virial": np.zeros((3, 3))}
+    for r in range(3):
+        p = Potential("", param_filename=xml)
+        p.set_partition(r, 3)
+        part = p.calc(a, force=True, virial=True)
+        for key in acc:
+            acc[key] = acc[key] + part[key]
+    assert abs(acc["energy"] - full["energy"]) < 1e-9 * max(1.0, abs(full["energy"]))
+    assert np.abs(acc["force"] - full["force"]).max() < 1e-10 and np.abs(acc["virial"] - full["virial"]).max() < 1e-9
+    det = Potential("", param_filename=xml)
+    det.set_deterministic(True)
+    d1 = det.calc(a, force=True, virial=True)
+    d2 = det.calc(a, force=True, virial=True)
+    assert np.array_equal(d1["force"], d2["force"]) and d1["energy"] == d2["energy"]
+    assert np.abs(d1["force"] - full["force"]).max() < 1e-10 and np.abs(d1["virial"] - full["virial"]).max() < 1e-9
+
+
 def test_md_run_device_reduce_hook_is_called(si_model, si_frames):
     # gap_md_run_device's reduction hook (a host without the library's communicator, e.g. one that reduces with MPI-aware CUDA): called once
     # after every force evaluation, on the evaluation's stream; the trajectory equals gap_md_run's

@@ -121,7 +121,7 @@ def test_reference_error_conditions(golden, tmp_path):
     unfitted = xml.replace('n_coordinate="3"', 'n_coordinate="3" fitted="F"')
     with pytest.raises(RuntimeError, match="has not been fitted"):  # IPModel_GAP.f95:179
         P.model_describe(param_str=unfitted, base_dir=golden)
-    other = xml.replace("distance_2b cutoff=4.0", "angle_3b cutoff=4.0", 1)
+    other = xml.replace("distance_2b cutoff=4.0", "co_angle_3b cutoff=4.0", 1)
     with pytest.raises(RuntimeError, match="not supported"):
         P.model_describe(param_str=other, base_dir=golden)
 
