@@ -648,6 +648,14 @@ def leg_md(ctx, atoms, xml, n_steps):
     sp = ShardedPotential("", param_filename=xml, device=ctx.local, rank=rank, world_size=world)
     copy = lambda: Atoms(atoms.numbers, atoms.positions.copy(), atoms.cell, atoms.pbc)
     sp.run(copy(), v0, dt=1.0, n_steps=1)  # warm-up: buffers, communicator, peer mappings
+    # a run of 0 steps = the state's trip to the GPU and back + the initial force evaluation: subtracted, so that the figure is the
+    # cost of an MD step itself (integrator + list rebuild + evaluation + reduction + one host synchronisation)
+    a0 = copy()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    sp.run(a0, v0, dt=1.0, n_steps=0)
+    torch.cuda.synchronize()
+    wall0 = ctx.max_over_ranks(time.perf_counter() - t0)
     a1 = copy()
     ctx.barrier()
     t0 = time.perf_counter()
@@ -686,11 +694,13 @@ def leg_md(ctx, atoms, xml, n_steps):
     if rank != 0:
         return None
     etot = ep + ek
-    evals = n_steps + 1
+    t_steps = max(wall - wall0, 1e-9)
     return {"workload": workload_name(world, "C") + ", NVE velocity Verlet dt = 1 fs from 300 K, neighbour list rebuilt every step", "n_gpus": world,
-            "atoms": N, "md_steps": n_steps, "ms_per_md_step": 1e3 * wall / evals, "atom_steps_per_s": N * evals / wall,
-            "timing": "wall clock of gap_md_run_device over %d steps + the initial force evaluation (= %d list rebuilds + evaluations + reductions, "
-                      "one host synchronisation per step), max over ranks" % (n_steps, evals),
+            "atoms": N, "md_steps": n_steps, "ms_per_md_step": 1e3 * t_steps / n_steps, "atom_steps_per_s": N * n_steps / t_steps,
+            "run_wall_s": wall, "run_of_0_steps_wall_s": wall0,
+            "timing": "wall clock (max over ranks) of a %d-step run minus that of a 0-step run through the same call (ShardedPotential.run -> "
+                      "gap_md_run_device): %d x (integrator + list rebuild + evaluation + reduction, one host synchronisation per step); the 0-step "
+                      "run is the state's transfer to the GPU and back plus the initial force evaluation" % (n_steps, n_steps),
             "energy_drift_eV": float(np.abs(etot - etot[0]).max()), "ekin0_eV": float(ek[0]), "replica_spread": spread,
             "roofline": roofline_block(st, N // world, N, world, SHAPES["C"], ctx.fp64_peak), "reduction_transport": transport, "parity": parity}
 
@@ -718,6 +728,8 @@ def run_b200(args):
     n_gpus = world
     if args.gpus != world and rank == 0:
         print("bench.py: --gpus %d but WORLD_SIZE=%d; using %d" % (args.gpus, world, world), file=sys.stderr)
+    t_start = time.perf_counter()
+    leg_s = {}
     ctx = Ctx(torch, dist, world, rank, local, dev, real_world)
     ctx.fp64_peak = measure_fp64_peak(torch, dev) if rank == 0 else 0.0
 
@@ -729,6 +741,7 @@ def run_b200(args):
     head = leg_static(ctx, args, CONFIG, atoms, xml, steps, warmup, with_cpu=(real_world == 1 and not args.no_cpu_baseline and not emulate),
                       full_parity=(None if (args.no_parity or emulate) else (N <= 65536)))
 
+    leg_s["headline"] = round(time.perf_counter() - t_start, 1)
     # ---- the other named configurations of BASELINE.json, in the same process ----
     named = {}
     want = args.named_configs
@@ -740,8 +753,11 @@ def run_b200(args):
     if do_C:
         buildC = descriptor_builder(local, "C")
         atomsC, xmlC = ctx.build_shared("named_C", lambda d: buildC(d, n_gpus))
+        t_leg = time.perf_counter()
         named["C_md"] = leg_md(ctx, atomsC, xmlC, args.md_steps)
+        leg_s["C_md"] = round(time.perf_counter() - t_leg, 1)
     if do_B:  # BASELINE configs[2]: SiC, 2 species, 3 x distance_2b + one SOAP (n_max=10 l_max=6, 4,000 sparse points) per centre species
+        t_leg = time.perf_counter()
         buildB = descriptor_builder(local, "B")
         atomsB, xmlB = ctx.build_shared("named_B", lambda d: buildB(d, n_gpus))
         b_leg = leg_static(ctx, args, "B", atomsB, xmlB, 5, 3, with_cpu=False, full_parity=False)
@@ -750,7 +766,9 @@ def run_b200(args):
                           "ms_per_step": b_leg["ms_per_step"], "atoms_per_s": b_leg["value"], "e2e_atoms_per_s": b_leg["e2e"]["value"],
                           "roofline": b_leg["roofline"], "reduction_transport": b_leg["reduction_transport"], "parity": b_leg.get("parity"),
                           "gpu_launches": b_leg["gpu_launches"]}
+        leg_s["B"] = round(time.perf_counter() - t_leg, 1)
     if do_D:
+        t_leg = time.perf_counter()
         buildD = descriptor_builder(local, "D")
         atomsD, xmlD = ctx.build_shared("named_D", lambda d: buildD(d, n_gpus))
         saved = CONFIG
@@ -761,6 +779,7 @@ def run_b200(args):
                           "roofline": d_leg["roofline"], "reduction_transport": d_leg["reduction_transport"], "parity": d_leg.get("parity"),
                           "gpu_launches": d_leg["gpu_launches"]}
         assert saved == CONFIG
+        leg_s["D"] = round(time.perf_counter() - t_leg, 1)
 
     if rank == 0:
         line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
@@ -773,6 +792,8 @@ def run_b200(args):
                 line[k] = head[k]
         if named:
             line["named_configs"] = named
+        # wall clock of the whole run by leg (model building, warm-up, oracle comparisons and the CPU leg included), seconds
+        line["wall_s_by_leg"] = dict(leg_s, total=round(time.perf_counter() - t_start, 1))
         emit(json.dumps(line))
         bad = [k for k, p in [("headline", head.get("parity"))] + [(k, v.get("parity")) for k, v in named.items() if v] if p is not None and not p["ok"]]
         if ctx.share:
