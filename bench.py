@@ -177,7 +177,8 @@ def config_dict(n_gpus, n_atoms):
                            "reference arm: OpenMP over atoms on the host cores" % n_gpus,
             "l2": "B200 arm: flushed between timed steps (512 MiB memset); reference arm: n/a (CPU)",
             "timing": "B200 arm: CUDA events per step on the launching stream around the enqueued step (kernels + reduction + energy read-back), one "
-                      "host synchronise + neighbour-list verification per step follows the closing event, max over ranks; reference arm: wall "
+                      "host synchronise + neighbour-list verification per step follows the closing event, max over ranks (at N > 1 the ranks are aligned by a "
+                      "one-element all-reduce on the stream between the L2 flush and the opening event); reference arm: wall "
                       "clock of calc_connect + soap_calc + gp_predict/scatter (omp_get_wtime around the phases the reference times)"}
 
 
@@ -521,10 +522,15 @@ def leg_static(ctx, args, config, atoms, xml, steps, warmup, with_cpu, full_pari
     launches0 = pot.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     stage_sum = {}
+    # N > 1: the ranks are aligned on the device after the L2 flush and before the step's opening event (a one-element all-reduce on the same
+    # stream), as consecutive MD steps are by the previous step's reduction; without it a step would also time the other ranks' flushes
+    align = torch.zeros(1, device=dev) if ctx.real_world > 1 else None
     ctx.barrier()
     t_wall = time.perf_counter()
     for k in range(steps):
         flush.zero_()
+        if align is not None:
+            ctx.dist.all_reduce(align)
         ev[k][0].record()
         sp.calc_resident_enqueue(N, d_pos, d_Z, lat, pbc, d_packed, want_grad=True)  # evaluation + reduction + energy read-back
         ev[k][1].record()
@@ -545,6 +551,8 @@ def leg_static(ctx, args, config, atoms, xml, steps, warmup, with_cpu, full_pari
     red_wait, red_sum = [], []
     for k in range(steps):
         flush.zero_()
+        if align is not None:
+            ctx.dist.all_reduce(align)
         sp.calc_resident_enqueue(N, d_pos, d_Z, lat, pbc, d_packed, want_grad=True)
         assert sp.calc_resident_finish()
         for name, ms in pot.last_timings().items():

@@ -58,8 +58,10 @@ int gap_potential_set_partition(gap_potential* pot, int rank, int n_ranks);
  * gap_potential_set_comm (collective: NCCL communicator over NVLink / NVSwitch).  It also sets the partition (rank, n_ranks).
  * From then on gap_potential_calc, gap_potential_calc_device[_enqueue], gap_md_run and gap_md_run_device return TOTALS on every
  * rank: the packed [E | virial | F(3,N)] partials (and local_e / local_virial when requested) are summed on the evaluation's
- * stream by ncclAllReduce or, for latency-bound sizes, by a one-shot peer-memory kernel over NVLink P2P (csrc/comm.cu;
- * GAP_B200_P2P=0 forces NCCL).  n_ranks = 1 removes the communicator. */
+ * stream by ncclAllReduce or, for latency-bound sizes, by a peer-memory kernel over NVLink P2P (one-shot pull on 2-3 ranks, low-latency
+ * reduce-scatter + all-gather by push from 4 ranks on; csrc/comm.cu;
+ * GAP_B200_P2P=0 forces NCCL; GAP_B200_P2P_MAX_BYTES, default 8 MiB, is the largest buffer the peer kernel takes; a rank that waits longer
+ * than GAP_B200_P2P_TIMEOUT_S, default 60, for the others' partials reports an error instead of hanging).  n_ranks = 1 removes the communicator. */
 #define GAP_COMM_ID_BYTES 128
 int gap_comm_get_unique_id(char* id /* GAP_COMM_ID_BYTES */);
 int gap_potential_set_comm(gap_potential* pot, const char* id /* GAP_COMM_ID_BYTES */, int rank, int n_ranks);

@@ -72,7 +72,18 @@ void nccl_ok(ncclResult_t r, const char* what) {
 
 constexpr int P2P_MAX_RANKS = 16;
 constexpr size_t P2P_FLAG_BYTES = 256;                // [n_ranks] step counters, one 256-byte line
-constexpr unsigned long long P2P_TIMEOUT_NS = 4000000000ull;
+// a rank waits this long for the other ranks' partials before it reports an error (GAP_B200_P2P_TIMEOUT_S, default 60 s: ranks of an MPI host
+// may reach the evaluation seconds apart; an NCCL all-reduce would wait for ever)
+unsigned long long p2p_timeout_ns() {
+  static unsigned long long v = 0;
+  if (!v) {
+    const char* e = getenv("GAP_B200_P2P_TIMEOUT_S");
+    double sec = e && *e ? atof(e) : 60.0;
+    if (!(sec > 0.0)) sec = 60.0;
+    v = (unsigned long long)(sec * 1e9);
+  }
+  return v;
+}
 
 struct PeerPtrs {
   char* base[P2P_MAX_RANKS];  // base[r]: rank r's block (flags | buffer 0 | buffer 1) as mapped into THIS process
@@ -87,7 +98,8 @@ struct PeerPtrs {
 // The partial buffers alternate between steps, so a fast rank can start writing step s+1 while a slow one still reads step s;
 // it cannot reach step s+2 (same buffer again) before every rank has signalled s+1, i.e. has left the kernel of step s.
 __global__ void __launch_bounds__(256) k_peer_allreduce(PeerPtrs peers, int rank, int n, unsigned step, size_t buf_off, size_t count,
-                                                        double* __restrict__ result, int* __restrict__ err, unsigned long long* __restrict__ stamps) {
+                                                        double* __restrict__ result, int* __restrict__ err, unsigned long long* __restrict__ stamps,
+                                                        unsigned long long timeout_ns) {
   __shared__ int timed_out;
   pdl_launch_dependents();
   if (threadIdx.x == 0) timed_out = 0;
@@ -108,7 +120,7 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerPtrs peers, int rank
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
       if ((int)(v - step) >= 0) break;
       asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
-      if (t1 - t0 > P2P_TIMEOUT_NS) { timed_out = 1; break; }
+      if (t1 - t0 > timeout_ns) { timed_out = 1; break; }
     }
   }
   __syncthreads();
@@ -147,6 +159,89 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerPtrs peers, int rank
   if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(stamps[2]));  // block 0 done (a sample of the sum phase)
 }
 
+
+// LOW-LATENCY variant (reduce-scatter + all-gather by PUSH, no flag rounds, no fences, no grid barrier) for latency-bound payloads on 4 or
+// more ranks.  Every double travels in a 16-byte cell {low word, step, high word, step}: the two 8-byte halves validate themselves, so the
+// receiver simply polls its LOCAL memory until both step words match (the protocol NCCL calls LL).  One launch:
+//   1. every rank pushes element i of its partial into the cell (src = me, i) of the rank that owns i (contiguous slices),
+//   2. the owner polls its G - 1 incoming cells per element, adds the G values in rank order, stores the total to its own result and
+//      pushes it into cell i of every peer,
+//   3. every rank polls the cells of the elements it does not own and copies the totals to its result.
+// Remote traffic is 2 (G - 1) / G buffer volumes per rank in 16-byte posted WRITES (the one-shot kernel: G - 1 volumes of remote READS); the
+// critical path is two one-way NVLink latencies.  Cells alternate between two sets by step parity: a rank can be at most one step ahead of
+// a peer that still polls (it needs that peer's step-(s+1) data to finish step s+1), so a set is overwritten only after it has been read.
+// All ranks end with the same bits.  Blocks spin on data produced by other GPUs' blocks: the launcher keeps the grid co-resident.
+struct LLGeom {
+  size_t rs_off, ag_off;   // byte offsets of the two cell regions in a rank's block
+  unsigned slice_cap, cap; // cells per (parity, source) in the reduce-scatter region; cells per parity in the all-gather region
+};
+__device__ __forceinline__ void ll_store(char* p, double v, unsigned flag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+__device__ __forceinline__ bool ll_poll(const char* p, unsigned flag, double& v, unsigned long long timeout_ns) {
+  unsigned a, b, c, d;
+  unsigned long long t0 = 0, t1;
+  for (unsigned spin = 0;; spin++) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+    if (b == flag && d == flag) break;
+    if ((spin & 1023u) == 1023u) {
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      else if (t1 - t0 > timeout_ns) return false;
+    }
+  }
+  v = __hiloint2double((int)c, (int)a);
+  return true;
+}
+__global__ void __launch_bounds__(256) k_peer_allreduce_ll(PeerPtrs peers, int rank, int n, unsigned step, size_t buf_off, LLGeom g, unsigned count,
+                                                           double* __restrict__ result, int* __restrict__ err, unsigned long long* __restrict__ stamps,
+                                                           unsigned long long timeout_ns) {
+  pdl_launch_dependents();
+  pdl_wait();  // this rank's partial is complete
+  if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(stamps[0]));
+  const unsigned stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x, par = step & 1u;
+  const double* partial = reinterpret_cast<const double*>(peers.base[rank] + buf_off);
+  auto slice_lo = [&](unsigned sr) { return (unsigned)(((unsigned long long)count * sr) / (unsigned)n); };
+  const unsigned lo = slice_lo((unsigned)rank), hi = slice_lo((unsigned)rank + 1u);
+  // 1. push my contribution to the owners
+  for (unsigned idx = t; idx < count; idx += stride) {
+    if (idx >= lo && idx < hi) continue;
+    unsigned sr = (unsigned)(((unsigned long long)idx * (unsigned)n) / count);
+    while (idx >= slice_lo(sr + 1u)) sr++;
+    char* dst = peers.base[sr] + g.rs_off + ((size_t)(par * (unsigned)n + (unsigned)rank) * g.slice_cap + (idx - slice_lo(sr))) * 16;
+    ll_store(dst, partial[idx], step);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(stamps[1]));
+  // 2. my slice: sum in rank order, publish the totals
+  bool ok = true;
+  for (unsigned idx = lo + t; idx < hi && ok; idx += stride) {
+    double sum = 0.0;
+    for (int r = 0; r < n && ok; r++) {
+      double v;
+      if (r == rank) v = partial[idx];
+      else ok = ll_poll(peers.base[rank] + g.rs_off + ((size_t)(par * (unsigned)n + (unsigned)r) * g.slice_cap + (idx - lo)) * 16, step, v, timeout_ns);
+      sum += v;
+    }
+    if (!ok) break;
+    result[idx] = sum;
+    for (int r = 0; r < n; r++)
+      if (r != rank) ll_store(peers.base[r] + g.ag_off + ((size_t)par * g.cap + idx) * 16, sum, step);
+  }
+  // 3. the other slices' totals
+  for (unsigned idx = t; idx < count && ok; idx += stride) {
+    if (idx >= lo && idx < hi) continue;
+    double v;
+    ok = ll_poll(peers.base[rank] + g.ag_off + ((size_t)par * g.cap + idx) * 16, step, v, timeout_ns);
+    if (ok) result[idx] = v;
+  }
+  if (!ok) {
+    *(volatile int*)err = 1;
+    __threadfence_system();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(stamps[2]));
+}
+
 }  // namespace
 
 struct GapComm {
@@ -165,6 +260,9 @@ struct GapComm {
   unsigned long long* d_stamps = nullptr;  // [3] globaltimer of the last peer reduction: own partial ready, all partials ready, done
   char* d_handles = nullptr;        // [n + 1] x 64 bytes (slot n: this rank's handle, the send buffer)
   int* d_okflag = nullptr;
+  LLGeom ll{0, 0, 0, 0};            // cell regions of the low-latency kernel (cap = 0: not allocated for this block)
+  size_t ll_limit = 1u << 20;       // largest payload (doubles) the low-latency kernel takes (GAP_B200_P2P_LL_MAX_DOUBLES; 0 = never)
+  int ll_min_ranks = 4;
   const char* last = "none";
   long launches = 0;
 };
@@ -197,8 +295,12 @@ GapComm* comm_create(const char* id128, int rank, int n_ranks, int device) {
     CUDA_OK(cudaHostGetDevicePointer((void**)&c->d_err, c->h_err, 0));
     CUDA_OK(cudaMalloc(&c->d_handles, (size_t)(n_ranks + 1) * sizeof(cudaIpcMemHandle_t)));
     CUDA_OK(cudaMalloc(&c->d_okflag, sizeof(int)));
-    CUDA_OK(cudaMalloc(&c->d_stamps, 3 * sizeof(unsigned long long)));
-    CUDA_OK(cudaMemset(c->d_stamps, 0, 3 * sizeof(unsigned long long)));
+    const char* llm = getenv("GAP_B200_P2P_LL_MAX_DOUBLES");
+    if (llm && *llm) c->ll_limit = (size_t)strtoull(llm, nullptr, 10);
+    const char* llr = getenv("GAP_B200_P2P_LL_MIN_RANKS");
+    if (llr && *llr) c->ll_min_ranks = atoi(llr);
+    CUDA_OK(cudaMalloc(&c->d_stamps, 8 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemset(c->d_stamps, 0, 8 * sizeof(unsigned long long)));
   } catch (...) {
     comm_destroy(c);
     throw;
@@ -214,6 +316,7 @@ static void p2p_release(GapComm* c) {
   if (c->block) cudaFree(c->block);
   c->block = nullptr;
   c->cap = 0;
+  c->ll = LLGeom{0, 0, 0, 0};
 }
 
 void comm_destroy(GapComm* c) {
@@ -235,7 +338,7 @@ const char* comm_last_transport(const GapComm* c) { return c ? c->last : "none";
 void comm_last_stamps(const GapComm* c, double* wait_us, double* sum_us) {
   *wait_us = *sum_us = 0.0;
   if (!c || !c->d_stamps) return;
-  unsigned long long t[3] = {0, 0, 0};
+  unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cudaMemcpy(t, c->d_stamps, sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess) return;
   if (t[1] >= t[0]) *wait_us = (double)(t[1] - t[0]) * 1e-3;
   if (t[2] >= t[1]) *sum_us = (double)(t[2] - t[1]) * 1e-3;
@@ -247,11 +350,20 @@ static void p2p_setup(GapComm* c, size_t count, cudaStream_t st) {
   const size_t want = ((count + count / 4 + 1024) + 1) & ~(size_t)1;
   CUDA_OK(cudaStreamSynchronize(st));
   char* nb = nullptr;
-  const size_t bytes = P2P_FLAG_BYTES + 2 * want * sizeof(double);
+  size_t bytes = P2P_FLAG_BYTES + 2 * want * sizeof(double);  // flags | partial 0 | partial 1 | low-latency cells
+  LLGeom ll{0, 0, 0, 0};
+  if (c->n >= c->ll_min_ranks && count <= c->ll_limit && want < (1u << 30)) {
+    ll.cap = (unsigned)want;
+    ll.slice_cap = (unsigned)(want / (size_t)c->n + 2);
+    ll.rs_off = (bytes + 255) & ~(size_t)255;
+    ll.ag_off = ll.rs_off + (size_t)2 * c->n * ll.slice_cap * 16;
+    bytes = ll.ag_off + (size_t)2 * ll.cap * 16;
+  }
   bool ok = cudaMalloc(&nb, bytes) == cudaSuccess;
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
   if (ok) ok = cudaMemset(nb, 0, P2P_FLAG_BYTES) == cudaSuccess && cudaIpcGetMemHandle(&mine, nb) == cudaSuccess;
+  if (ok && ll.cap) ok = cudaMemset(nb + ll.rs_off, 0, bytes - ll.rs_off) == cudaSuccess;  // step words: 0 matches no step
   cudaGetLastError();
   // every rank takes part in the exchange even if its own allocation failed (the verdict below is collective)
   CUDA_OK(cudaMemcpyAsync(c->d_handles + (size_t)c->n * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
@@ -281,6 +393,7 @@ static void p2p_setup(GapComm* c, size_t count, cudaStream_t st) {
   }
   c->block = nb;
   c->cap = want;
+  c->ll = ll;
   for (int r = 0; r < c->n; r++) c->peer_base[r] = opened[r];
 }
 
@@ -309,8 +422,16 @@ void comm_allreduce_packed(GapComm* c, size_t count, double* result, cudaStream_
     int blocks = (int)((count / 2 + 255) / 256);
     if (blocks > 2 * c->n_sm) blocks = 2 * c->n_sm;
     if (blocks < 1) blocks = 1;
-    launch_pdl(k_peer_allreduce, dim3(blocks), dim3(256), 0, st, pp, c->rank, c->n, c->step, buf_off, count, result, c->d_err, c->d_stamps);
-    c->last = "p2p";
+    if (c->ll.cap && c->n >= c->ll_min_ranks && count <= c->ll_limit && count <= c->ll.cap && count >= (size_t)c->n) {
+      int lb = (int)((count + 255) / 256);
+      if (lb > 2 * c->n_sm) lb = 2 * c->n_sm;
+      launch_pdl(k_peer_allreduce_ll, dim3(lb), dim3(256), 0, st, pp, c->rank, c->n, c->step, buf_off, c->ll, (unsigned)count, result, c->d_err, c->d_stamps,
+                 p2p_timeout_ns());
+      c->last = "p2p-ll";
+    } else {
+      launch_pdl(k_peer_allreduce, dim3(blocks), dim3(256), 0, st, pp, c->rank, c->n, c->step, buf_off, count, result, c->d_err, c->d_stamps, p2p_timeout_ns());
+      c->last = "p2p";
+    }
   } else {
     nccl_ok(nccl().AllReduce(result, result, count, ncclFloat64, ncclSum, c->comm, st), "ncclAllReduce");
     c->last = "nccl";
