@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Print the essentials of bench.py JSON lines (one file per argument)."""
 import json
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 import sys
 
 for path in sys.argv[1:]:
