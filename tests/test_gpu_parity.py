@@ -931,6 +931,23 @@ def test_angle_3b_silicon_frames_partition_and_deterministic(si_frames, tmp_path
     assert np.abs(d1["force"] - full["force"]).max() < 1e-10 and np.abs(d1["virial"] - full["virial"]).max() < 1e-9
 
 
+def test_c_example_program_matches_python_binding(gap_xml_pot, golden, tmp_path):
+    # examples/wrapper_simple_example.c (the reference's quip_wrapper_simple_example_C.c against this library), compiled with gcc and run
+    import subprocess
+
+    from tests.test_host_cpu import _build_c_example
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe, os.path.join(golden, "GAP.xml")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = dict(line.split(" = ") for line in r.stdout.strip().splitlines())
+    a = Atoms([1, 1], [[-7.110371, -3.533572, 2.147261], [-7.933029, -3.234956, 2.573383]], np.eye(3) * 20.0, True)
+    ref = gap_xml_pot.calc(a, force=True, local_energy=True)
+    assert abs(float(out["Energy"]) - ref["energy"]) < 1e-10 and abs(float(out["Energy2"]) - ref["energy"]) < 1e-10
+    assert np.abs(np.array(out["Force0"].split(), dtype=float) - ref["force"][0]).max() < 1e-10
+    assert np.abs(np.array(out["LocalE"].split(), dtype=float) - ref["local_energy"]).max() < 1e-10
+    assert abs(float(out["Cutoff"]) - 4.0) < 1e-12
+
+
 def test_md_run_device_reduce_hook_is_called(si_model, si_frames):
     # gap_md_run_device's reduction hook (a host without the library's communicator, e.g. one that reduces with MPI-aware CUDA): called once
     # after every force evaluation, on the evaluation's stream; the trajectory equals gap_md_run's

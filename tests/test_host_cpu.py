@@ -181,3 +181,23 @@ def test_general_soap_setup_matches_oracle(golden, tmp_path):
         assert np.abs(Pc - Pm).max() < 1e-9 * max(1.0, np.abs(Pm).max()), (qs, np.abs(Pc - Pm).max(), np.abs(Pm).max())
         assert np.abs(np.array(rows["c0"], dtype=float) - c0).max() < 1e-9 * max(1.0, np.abs(c0).max()), qs
     assert n_general >= 110
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "wrapper_simple_example")
+    subprocess.run(["gcc", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "wrapper_simple_example.c"),
+                    "-L" + os.path.join(root, "quip_b200"), "-lgapb200", "-Wl,-rpath," + os.path.join(root, "quip_b200"), "-o", exe], check=True)
+    return exe
+
+
+def test_c_example_compiles_against_the_header_and_fails_loudly_without_a_gpu(golden, tmp_path):
+    # the C caller of INTEGRATION.md section 4 (the reference's quip_wrapper_simple_example_C.c): plain C, include/gap_b200.h, -lgapb200
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe, os.path.join(golden, "GAP.xml")], capture_output=True, text=True)
+    if r.returncode == 0:  # a CUDA device is present: the example ran
+        assert "Energy =" in r.stdout
+    else:
+        assert "no CPU fallback" in r.stderr
