@@ -153,6 +153,27 @@ def quad_datasets(golden, pbc):
     return [Atoms(d["numbers"], np.array(d["scaled_positions"]) @ np.array(d["cell"]), d["cell"], pbc) for d in S["datasets"]["quad_3"]]
 
 
+def test_descriptor_tutorial_outputs_of_the_reference_binary(golden, tmp_path):
+    """The stored outputs of src/GAP/doc_src/quippy-descriptor-tutorial.ipynb (printed by the real QUIP binary) on the GPU: SOAP vectors of the
+    2-atom diamond cell (one species; two species with an extra H atom) to the 9 printed digits, the 92 distance_2b instances (neighbour
+    list inside the cutoff) and the sum of their covariance_cutoff values as the energy of a GAP whose every instance has energy 1."""
+    from tests.test_oracle_golden import _count_model, _tutorial
+    T, a, ah = _tutorial(golden)
+    for key, at in (("soap_1", a), ("soap_2", ah)):
+        desc = T[key]["descriptor"]
+        X = np.array(T[key]["data"])
+        coord = {"descriptor": desc, "covariance_type": 2, "delta": 1.0, "zeta": 2.0, "sparseX": X, "alpha": np.ones(len(X)), "sparseCutoff": np.ones(len(X))}
+        pot = Potential("", param_filename=write_gap_xml(str(tmp_path / (key + ".xml")), [coord], e0={6: -1.0, 1: 0.5}))
+        x, ci = pot.descriptor_calc(at, 0)
+        assert np.array_equal(ci, np.arange(len(X)))
+        assert np.abs(x - X).max() < 1e-9
+    off, j, s, d = Potential("", param_filename=_count_model(tmp_path, T["distance_2b"]["descriptor"])).calc_connect(a, 4.0)
+    ref = T["distance_2b"]
+    assert len(d) == ref["count"] and np.abs(np.sort(d) - np.sort(ref["data"])).max() < 1e-8
+    e = Potential("", param_filename=_count_model(tmp_path, ref["descriptor"])).calc(a)["energy"]
+    assert abs(e - sum(ref["covariance_cutoff"])) < 2e-7
+
+
 def test_soap_multispecies_descriptor(golden, tmp_path):
     desc = "soap n_Z=4 n_species=4 Z={23 41 42 73} species_Z={23 41 42 73} n_max=4 l_max=2 cutoff=5 atom_sigma=0.4 cutoff_transition_width=0.5 central_weight=1"
     for pbc in (False, True):

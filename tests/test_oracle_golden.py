@@ -325,3 +325,38 @@ def test_angle_3b_against_direct_sum_and_finite_differences(golden, tmp_path):
         em = om.calc(Atoms(a.numbers, a.positions @ Fm.T, a.cell @ Fm.T, True), force=False, virial=False)["energy"]
         assert abs((ep - em) / (2 * eps) + r["virial"][aa, bb]) < 1e-6 * max(1.0, np.abs(r["virial"]).max())
     assert np.abs(r["force"].sum(axis=0)).max() < 1e-10
+
+
+def _tutorial(golden):
+    T = json.load(open(os.path.join(golden, "descriptor_tutorial.json")))
+    a = Atoms(T["numbers"], T["positions"], T["cell"], True)
+    ah = Atoms(T["numbers"] + [T["extra_atom"]["number"]], T["positions"] + [T["extra_atom"]["position"]], T["cell"], True)
+    return T, a, ah
+
+
+def _count_model(tmp_path, desc):
+    """A GAP whose every descriptor instance has energy 1 (delta = 0, f0 = 1, one sparse point with alpha = 1): E = sum of covariance_cutoff."""
+    from quip_b200.gap_xml import write_gap_xml
+    return write_gap_xml(str(tmp_path / "count.xml"), [{"descriptor": desc, "covariance_type": 1, "delta": 0.0, "f0": 1.0, "theta": [1.0],
+                                                        "sparseX": np.array([[2.0]]), "alpha": np.array([1.0]), "sparseCutoff": np.array([1.0])}])
+
+
+def test_descriptor_tutorial_outputs_of_the_reference_binary(golden, tmp_path):
+    """src/GAP/doc_src/quippy-descriptor-tutorial.ipynb stores what the real QUIP binary printed for the 2-atom diamond cell: SOAP vectors
+    (n_max = l_max = 4; one species, and two species after adding an H atom) to 9 digits, and the distance_2b instances (92 of them, their
+    distances and covariance_cutoff values)."""
+    T, a, ah = _tutorial(golden)
+    o1 = orc.soap_descriptor(T["soap_1"]["descriptor"], a, grad=True)
+    assert np.abs(o1["data"] - np.array(T["soap_1"]["data"])).max() < 1e-9
+    o2 = orc.soap_descriptor(T["soap_2"]["descriptor"], ah, grad=True)
+    assert np.abs(o2["data"] - np.array(T["soap_2"]["data"])).max() < 1e-9
+    # sizes() = (n_descriptors, n_cross): one gradient row per centre and per neighbour inside the cutoff
+    assert [len(o1["data"]), len(o1["ii"])] == T["soap_1"]["sizes"]
+    assert [len(o2["data"]), len(o2["ii"])] == T["soap_2"]["sizes"]
+    # distance_2b: the instances are the ordered pairs of the full neighbour list inside the cutoff
+    d = orc.Connect(a, 4.0).arrays()[3]
+    ref = T["distance_2b"]
+    assert len(d) == ref["count"] and 2 * len(d) == ref["n_cross"]
+    assert np.abs(np.sort(d) - np.sort(ref["data"])).max() < 1e-8
+    e = orc.Model(_count_model(tmp_path, ref["descriptor"])).calc(a)["energy"]
+    assert abs(e - sum(ref["covariance_cutoff"])) < 2e-7  # 92 values printed to 8 decimals

@@ -17,6 +17,9 @@ suite, cited per item.
       tests/test_SOAP.py:38) -> SOAP X and grad_data on the default path
   tests/SOAP_reference_data.json, all 122 cases -> soap_reference_all.{json,npz}
   tests/test_descriptor.py:63-226 -> C2H cell gradient index table + 2 gradient blocks
+  src/GAP/doc_src/quippy-descriptor-tutorial.ipynb, the STORED OUTPUTS of cells 19-22, 31, 38-41, 45-52 (a run of the real QUIP binary,
+      git f538cd9fe): distance_2b instances (count, distances, covariance_cutoff) and SOAP vectors (n_max=4, l_max=4; one species
+      2 x 51, two species 3 x 181) of the 2-atom diamond cell (+ one H) -> descriptor_tutorial.json
 """
 import ast
 import json
@@ -98,6 +101,28 @@ def main():
                "numbers": [1, 1],
                "ref_energies": [0.36747083829015637, 2.8715032700273735, 4.10632306979403, 5.518256035535996,
                                 5.885656871424537]}, open(os.path.join(OUT, "h2_cell_energies.json"), "w"))
+    # --- quippy-descriptor-tutorial.ipynb: outputs the reference binary printed -------------------------
+    nb = json.load(open("/root/reference/src/GAP/doc_src/quippy-descriptor-tutorial.ipynb"))
+
+    def cell_output(i):
+        txt = ""
+        for o in nb["cells"][i].get("outputs", []):
+            if "text" in o:
+                txt += "".join(o["text"])
+            elif "data" in o and "text/plain" in o["data"]:
+                txt += "".join(o["data"]["text/plain"])
+        return eval(txt, {"array": np.array, "int32": np.int32, "__builtins__": {}})  # numpy reprs of dicts of arrays
+
+    d2b, s1, s2 = cell_output(22), cell_output(41), cell_output(52)
+    json.dump({
+        "source": "src/GAP/doc_src/quippy-descriptor-tutorial.ipynb (stored cell outputs; structure: ase.build.bulk('C', 'diamond', 3.5), cells 5-7)",
+        "cell": [[0.0, 1.75, 1.75], [1.75, 0.0, 1.75], [1.75, 1.75, 0.0]], "positions": [[0.0, 0.0, 0.0], [0.875, 0.875, 0.875]], "numbers": [6, 6],
+        "extra_atom": {"number": 1, "position": [0.2, 0.2, 0.2]},
+        "distance_2b": {"descriptor": "distance_2b Z1=6 Z2=6 cutoff=4", "count": 92, "n_cross": 184,
+                        "data": [float(v) for v in d2b["data"][:, 0]], "covariance_cutoff": [float(v) for v in d2b["covariance_cutoff"]]},
+        "soap_1": {"descriptor": "soap cutoff=3 l_max=4 n_max=4 atom_sigma=0.5 n_Z=1 Z={6} ", "sizes": [2, 58], "data": s1["data"].tolist()},
+        "soap_2": {"descriptor": "soap cutoff=3 l_max=4 n_max=4 atom_sigma=0.5 n_Z=2 Z={1 6} n_species=2 species_Z={1 6}", "sizes": [3, 123],
+                   "data": s2["data"].tolist()}}, open(os.path.join(OUT, "descriptor_tutorial.json"), "w"))
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-50s %8d B" % (f, os.path.getsize(os.path.join(OUT, f))))
