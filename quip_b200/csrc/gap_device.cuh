@@ -164,6 +164,8 @@ struct SoapGenDev {
   const int* pair_ia;      // [n_pairs]
   const int* pair_jb;
   const double* pair_fac;
+  // the elements grouped by their first / second channel (for dE/dY1, dE/dY2): offsets [Ka + 1] / [Kb + 1] into element lists [n_pairs]
+  const int *by_ia_off, *by_ia, *by_jb_off, *by_jb;
 };
 size_t soap_general_smem(const SoapDev& h, const SoapGenDev& g);
 void launch_soap_forward_general(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* centres, const int* n_centres_dev, int n_centres_ub,

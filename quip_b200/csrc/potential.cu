@@ -754,18 +754,34 @@ void upload_model(gap_potential* P) {
         std::vector<double> blob;
         auto put = [&](const std::vector<double>& v) { size_t o = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); if (blob.size() & 1) blob.push_back(0.0); return o; };
         const size_t o_r = put(s.r_grid), o_P = put(s.P), o_c0 = put(s.c0), o_W1 = put(s.W1), o_W2 = put(s.W2), o_f = put(s.pair_fac), o_int = blob.size();
-        const size_t bytes = blob.size() * sizeof(double) + 2 * np * sizeof(int);
+        // int tables: ia | jb | elements grouped by ia (offsets, list) | elements grouped by jb (offsets, list), each group in element order
+        std::vector<int> ints;
+        ints.insert(ints.end(), s.pair_ia.begin(), s.pair_ia.end());
+        ints.insert(ints.end(), s.pair_jb.begin(), s.pair_jb.end());
+        size_t o_ia_off = 0, o_ia = 0, o_jb_off = 0, o_jb = 0;
+        for (int side = 0; side < 2; side++) {
+          const std::vector<int>& key = side ? s.pair_jb : s.pair_ia;
+          const int K = side ? s.Kb : s.Ka;
+          (side ? o_jb_off : o_ia_off) = ints.size();
+          std::vector<int> off((size_t)K + 1, 0);
+          for (size_t e = 0; e < np; e++) off[(size_t)key[e] + 1]++;
+          for (int k = 0; k < K; k++) off[(size_t)k + 1] += off[k];
+          ints.insert(ints.end(), off.begin(), off.end());
+          (side ? o_jb : o_ia) = ints.size();
+          std::vector<int> lst(np), fill(off.begin(), off.end() - 1);
+          for (size_t e = 0; e < np; e++) lst[(size_t)fill[key[e]]++] = (int)e;
+          ints.insert(ints.end(), lst.begin(), lst.end());
+        }
+        const size_t bytes = blob.size() * sizeof(double) + ints.size() * sizeof(int);
         CUDA_OK(cudaMalloc(&cd.gen_blob, bytes + 16));
         CUDA_OK(cudaMemcpy(cd.gen_blob, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
         int* d_int = (int*)((double*)cd.gen_blob + o_int);
-        if (np) {
-          CUDA_OK(cudaMemcpy(d_int, s.pair_ia.data(), np * sizeof(int), cudaMemcpyHostToDevice));
-          CUDA_OK(cudaMemcpy(d_int + np, s.pair_jb.data(), np * sizeof(int), cudaMemcpyHostToDevice));
-        }
+        CUDA_OK(cudaMemcpy(d_int, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice));
         const double* b = (const double*)cd.gen_blob;
         cd.gen.n_grid = s.n_grid; cd.gen.Ka = s.Ka; cd.gen.Kb = s.Kb; cd.gen.n_pairs = (int)np;
         cd.gen.r_grid = b + o_r; cd.gen.P = b + o_P; cd.gen.c0 = b + o_c0; cd.gen.W1 = b + o_W1; cd.gen.W2 = b + o_W2; cd.gen.pair_fac = b + o_f;
         cd.gen.pair_ia = d_int; cd.gen.pair_jb = d_int + np;
+        cd.gen.by_ia_off = d_int + o_ia_off; cd.gen.by_ia = d_int + o_ia; cd.gen.by_jb_off = d_int + o_jb_off; cd.gen.by_jb = d_int + o_jb;
         cd.gen.global_mode = s.global ? 1 : 0;
         if (s.global) {  // average=T: the summed density expansion and the shared dE/dX on the radial grid
           CUDA_OK(cudaMalloc(&cd.gen_global, sizeof(double) * (size_t)h.nlm * (h.K1 + s.n_species * s.n_grid)));
