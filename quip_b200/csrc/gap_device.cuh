@@ -139,13 +139,13 @@ size_t soap_adjoint_smem(const SoapDev& h);
 // n_centres_dev: device int holding the number of centres (the grid is sized by the host-side upper bound n_centres_ub)
 void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, double* x, double* xlm, double* pnorm,
-                         cudaStream_t st, int* launches);
+                         cudaStream_t st, int* launches, int skip_power = 0);
 // epart/n_tiles_n/local_e: if epart != NULL the kernel also folds the GEMM-1 row sums into local_e (E_i)
 void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
                          const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
                          double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, double* fpair, cudaStream_t st,
-                         int* launches);
+                         int* launches, const double* lambda_in = nullptr);
 // fpair != NULL selects the DETERMINISTIC scatter: the force on neighbour j of a pair goes to fpair[3 * slot] (slot = position of the
 // entry in the neighbour list), the centre's own sum to force[3 * i] by a plain store (force = a zeroed per-atom scratch buffer); the
 // caller then adds both per atom in a fixed order (potential.cu k_det_gather).  fpair == NULL: FP64 atomics on force[].
@@ -204,6 +204,14 @@ void launch_cov_gemm2(const double* acoef, int lda, const double* st_rows, int l
                       int* launches);
 void launch_energy_rows(const double* epart, int n_tiles_n, const int* centres, const int* n_centres_dev, int n_centres_ub, double e_scale,
                         double* local_e, cudaStream_t st, int* launches);
+
+// compression modes on the EQUISPACED_GAUSS basis ("hybrid"): soap.cu's kernels for the density expansion (skip_power) and the neighbour phase
+// (lambda_in), these two for the variant-specific middle: X_lm -> descriptor, dE/dx -> Lambda = dE/dX_lm [centre][nlm][K1]
+void launch_soap_power_general(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* n_centres_dev, int n_centres_ub, const double* xlm,
+                               double* x, double* pnorm, cudaStream_t st, int* launches);
+void launch_soap_lambda_general(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* n_centres_dev, int n_centres_ub, const double* x,
+                                const double* xlm, const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride,
+                                double* lambda_out, cudaStream_t st, int* launches);
 
 // ---- pair2b.cu -----------------------------------------------------------------------------
 constexpr int PAIR2B_MAX_EXP = 4;

@@ -68,6 +68,7 @@ struct CoordDev {
   SoapDev h;
   SoapDev* d_sp = nullptr;
   bool general = false;        // compression modes / GTO / POLY: soap_general.cu kernels
+  bool hybrid = false;         // general on the EQUISPACED_GAUSS basis: soap.cu's kernels for the density expansion and the neighbour phase
   SoapGenDev gen;
   void* gen_blob = nullptr;    // one device allocation behind the pointers of gen
   double* gen_global = nullptr; // average=T: [Xg | Lt] (see SoapGenDev)
@@ -139,6 +140,7 @@ struct gap_potential {
   long list_slots = 0;         // slots of the handle's own list (row_cap * centres, or the entry count)
   DevBuf b_fpair, b_fself, b_dkeys, b_dkeys2, b_dvals, b_dvals2, b_joff, b_dcub;
   DevBuf b_a3idx;              // angle_3b: compacted in-cutoff entries of each list row (int per slot)
+  DevBuf b_lambda;             // hybrid SOAP coordinates: Lambda = dE/dX_lm [centre][nlm][K1]
   // skin-based reuse of the neighbour list (calc_connect with cutoff_skin, Connection.f95:1085-1128)
   double cutoff_skin = 0.0;
   bool list_valid = false;     // cv_* describe a list built with last_cut for the geometry remembered below
@@ -743,12 +745,14 @@ void upload_model(gap_potential* P) {
       cudaDeviceProp prop;
       CUDA_OK(cudaGetDeviceProperties(&prop, P->device));
       P->n_sm = prop.multiProcessorCount;
-      if (!s.general && (soap_adjoint_smem(h) > prop.sharedMemPerBlockOptin || soap_forward_smem(h) > prop.sharedMemPerBlockOptin))
+      if ((!s.general || (!s.global && s.radial_basis == "EQUISPACED_GAUSS")) &&
+          (soap_adjoint_smem(h) > prop.sharedMemPerBlockOptin || soap_forward_smem(h) > prop.sharedMemPerBlockOptin))
         throw GapError("soap descriptor too large for the shared memory of this device");
       CUDA_OK(cudaMalloc(&cd.d_sp, sizeof(SoapDev)));
       CUDA_OK(cudaMemcpy(cd.d_sp, &h, sizeof(SoapDev), cudaMemcpyHostToDevice));
       memset(&cd.gen, 0, sizeof(cd.gen));
       cd.general = s.general;
+      cd.hybrid = s.general && !s.global && s.radial_basis == "EQUISPACED_GAUSS" && s.n_grid == s.n_max && getenv("GAP_B200_SOAP_HYBRID") == nullptr;
       if (s.general) {  // tables of the general path, packed into one allocation (doubles first, then the two int lists)
         const size_t np = s.pair_ia.size();
         std::vector<double> blob;
@@ -915,12 +919,19 @@ CalcArgs parse_calc_args(const gap_potential* P, const char* args_str) {
 
 // SOAP adjoint + scatter of a coordinate: the DMMA kernels of soap.cu, or the general path of soap_general.cu.  fpair != NULL: deterministic
 // scatter (force = the per-atom scratch of the centres' own sums, see gap_device.cuh)
-void soap_adjoint_any(const CoordDev& cd, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
+void soap_adjoint_any(gap_potential* P, const CoordDev& cd, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                       const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
                       const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
                       double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st, int* launches,
                       double* fpair = nullptr) {
-  if (cd.general)
+  if (cd.hybrid && gvec) {  // variant-specific pull-back dE/dx -> Lambda, then the default path's transform pull-back and neighbour phase
+    P->b_lambda.ensure(sizeof(double) * (size_t)(n_centres_ub > 0 ? n_centres_ub : 1) * cd.h.nlm * cd.h.K1);
+    launch_soap_lambda_general(cd.d_sp, cd.h, cd.gen, n_centres_dev, n_centres_ub, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride,
+                               P->b_lambda.as<double>(), st, launches);
+    launch_soap_adjoint(cd.d_sp, cd.h, centres, n_centres_dev, n_centres_ub, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
+                        g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair, st, launches,
+                        P->b_lambda.as<double>());
+  } else if (cd.general)
     launch_soap_adjoint_general(cd.d_sp, cd.h, cd.gen, centres, n_centres_dev, n_centres_ub, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec,
                                 ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair, st, launches);
   else
@@ -1004,7 +1015,12 @@ void soap_forward_stage(gap_potential* P, const CoordDev& cd, int n_ub, const do
   P->b_x.ensure(sizeof(double) * (size_t)nc_pad * cd.d_pad);
   P->b_xlm.ensure(sizeof(double) * (size_t)(n_ub > 0 ? n_ub : 1) * cd.h.nlm * cd.h.K1);
   P->b_pnorm.ensure(sizeof(double) * (size_t)nc_pad);
-  if (cd.general)
+  if (cd.hybrid) {  // density expansion on the default path's kernels, channel mixing + element list from the stored X_lm
+    launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
+                        P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches, 1);
+    launch_soap_power_general(cd.d_sp, cd.h, cd.gen, nc_dev(P, n_ub), n_ub, P->b_xlm.as<double>(), P->b_x.as<double>(), P->b_pnorm.as<double>(), st,
+                              &launches);
+  } else if (cd.general)
     launch_soap_forward_general(cd.d_sp, cd.h, cd.gen, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z,
                                 lat, P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
   else
@@ -1154,7 +1170,7 @@ void variance_soap(gap_potential* P, size_t ic, int nc, const int* ncd, bool wan
                        P->b_gvec.as<double>() + (size_t)r0 * cd.dn_pad, cd.dn_pad, split_stride, st, &launches);
   }
   if (want_grad)  // pull-back through the descriptor: gap_variance_gradient(:,j) += grad_variance . grad_data(:,:,n)  (IPModel_GAP.f95:485-486)
-    soap_adjoint_any(cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_x.as<double>(),
+    soap_adjoint_any(P, cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_x.as<double>(),
                      P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, ksplit, split_stride, nullptr, 0, nullptr,
                      -1.0 /* the kernel scatters force = -e_scale f_gp */, P->b_gvg.as<double>(), nullptr, nullptr, st, &launches);
   P->launches += launches;
@@ -1275,7 +1291,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
         covariance_stage(P, cd, glob ? 1 : nc, glob ? nullptr : ncd, want_grad, true, st);
         if (want_grad) {
           if (det && det_slots > 0) CUDA_OK(cudaMemsetAsync(P->b_fpair.p, 0, sizeof(double) * 3 * (size_t)det_slots, st));  // (unvisited slots)
-          soap_adjoint_any(cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
+          soap_adjoint_any(P, cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
                            P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, P->g_splits,
                            P->g_split_stride, P->b_epart.as<double>(), P->g_tiles_n, d_le, es, det ? P->b_fself.as<double>() : d_force,
                            P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches, det ? P->b_fpair.as<double>() : nullptr);
@@ -1286,7 +1302,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
           slot += nc;
           mark(P, st, ST_SOAP_ADJ);
         } else if (glob) {  // energy only: e_i shared by all centres (IPModel_GAP.f95:454-459)
-          soap_adjoint_any(cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_x.as<double>(),
+          soap_adjoint_any(P, cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_x.as<double>(),
                            P->b_xlm.as<double>(), P->b_pnorm.as<double>(), nullptr, 0, 0, 0, P->b_epart.as<double>(), P->g_tiles_n, d_le, es, nullptr,
                            nullptr, nullptr, st, &launches);
           mark(P, st, ST_OTHER);
@@ -1446,7 +1462,7 @@ void gap_potential_finalise(gap_potential* P) {
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
                     &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke, &P->b_lastpos, &P->b_disp, &P->b_resid,
-                    &P->b_fpair, &P->b_fself, &P->b_dkeys, &P->b_dkeys2, &P->b_dvals, &P->b_dvals2, &P->b_joff, &P->b_dcub, &P->b_a3idx};
+                    &P->b_fpair, &P->b_fself, &P->b_dkeys, &P->b_dkeys2, &P->b_dvals, &P->b_dvals2, &P->b_joff, &P->b_dcub, &P->b_a3idx, &P->b_lambda};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : P->ev) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);

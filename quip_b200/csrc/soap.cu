@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
                                                         const int* __restrict__ nbr_off, const int* __restrict__ nbr_end, const int* __restrict__ nbr_j,
                                                         const int* __restrict__ nbr_s, const double* __restrict__ pos,
                                                         const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
-                                                        double* __restrict__ xlm, double* __restrict__ pnorm) {
+                                                        double* __restrict__ xlm, double* __restrict__ pnorm, int skip_power) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_launch_dependents();
   pdl_wait();
@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_forward(const SoapDev* __restric
     int lm = k / K1, ic = k - lm * K1;
     xlm[(size_t)c * nlm * K1 + k] = s.X[lm * g.XS + ic];
   }
+  if (skip_power) return;  // compression modes: the power spectrum of the mixed channels is taken by soap_general.cu from xlm
   // ---- power spectrum on the tensor cores (descriptors.f95:8370-8418): p_l(ia,jb) = sum_m X_lm(ia) X_lm(jb) / sqrt(2l+1),
   //      element q = l + (l_max+1) * pair(ia, jb<=ia), off-diagonal pairs times sqrt(2); one warp per (l, tile pair) ----
   double loc = 0.0;
@@ -625,7 +626,7 @@ __global__ void __launch_bounds__(NT, (CN > 8 ? 2 : 4)) k_soap_forward_w(const S
                                                                          const int* __restrict__ nbr_off, const int* __restrict__ nbr_end, const int* __restrict__ nbr_j,
                                                                          const int* __restrict__ nbr_s, const double* __restrict__ pos,
                                                                          const int* __restrict__ Z, Lattice9 lat, double* __restrict__ x,
-                                                                         double* __restrict__ xlm, double* __restrict__ pnorm) {
+                                                                         double* __restrict__ xlm, double* __restrict__ pnorm, int skip_power) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Geo g = make_geo(CN, CL, CNS);
   constexpr int n = CN, L1 = CL + 1, nlm = (CL + 1) * (CL + 1), K1 = CN * CNS, ns = CNS;
@@ -720,6 +721,7 @@ __global__ void __launch_bounds__(NT, (CN > 8 ? 2 : 4)) k_soap_forward_w(const S
     const int lm = k / K1, ic = k - lm * K1;
     xlm[(size_t)c * nlm * K1 + k] = w.X[lm * g.XS + ic];
   }
+  if (skip_power) return;
   // ---- power spectrum on the tensor cores (descriptors.f95:8370-8418) ----
   double loc = 0.0;
   {
@@ -960,7 +962,8 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
                                                         const double* __restrict__ gvec, int ldg, int g_splits, size_t g_split_stride,
                                                         const double* __restrict__ epart, int n_tiles_n, double* __restrict__ local_e,
                                                         double e_scale, double* __restrict__ force, double* __restrict__ vir_part,
-                                                        double* __restrict__ local_virial, double* __restrict__ fpair) {
+                                                        double* __restrict__ local_virial, double* __restrict__ fpair,
+                                                        const double* __restrict__ lambda_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   pdl_launch_dependents();
   pdl_wait();
@@ -988,17 +991,21 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
   // u = dE/dp: pull gradPredict back through x = p/|p| (reference forward form: descriptors.f95:8595-8600)
   const double* xr = x + (size_t)c * sp->d_pad;
   const double* gr = gvec + (size_t)c * ldg;
+  // lambda_in != NULL (compression modes): Lambda = dE/dX_lm [centre][lm][K1] was formed by soap_general.cu from the element list and the
+  // mixing matrices; this kernel starts at the basis-transform pull-back
   // X_lm -> shared: asynchronous copies issued first so that their latency overlaps the gradPredict loads below
+  if (!lambda_in) {
   for (int k = threadIdx.x; k < nlm * K1; k += NT) {
     int lm = k / K1, ic = k - lm * K1;
     cp_async8(s.X + lm * g.XS + ic, xlm + (size_t)c * nlm * K1 + k);
   }
   cp_async_commit();
+  }
   // gradPredict arrives as g_splits partial sums (the K splits of GEMM-2), added here in a fixed order; four elements per
   // thread are in flight at a time
   double loc = 0.0;
-  const double nrm = pnorm[c];
-  for (int q0 = 0; q0 < d - 1; q0 += 4 * NT) {
+  const double nrm = lambda_in ? 1.0 : pnorm[c];
+  for (int q0 = 0; q0 < (lambda_in ? 0 : d - 1); q0 += 4 * NT) {
     double xv[4], gv[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
@@ -1026,13 +1033,19 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint(const SoapDev* __restric
     s.X2[k] = 0.0;
   }
   double sdot = block_sum(loc, s.red);
-  if (sp->normalise)
+  if (sp->normalise && !lambda_in)
     for (int q = threadIdx.x; q < d - 1; q += NT) s.p[q] = (s.p[q] - xr[q] * sdot) / nrm;
   cp_async_wait_all();
   __syncthreads();
+  if (lambda_in) {
+    for (int k = threadIdx.x; k < nlm * K1; k += NT) {
+      int lm = k / K1, ic = k - lm * K1;
+      s.X2[lm * g.XS + ic] = lambda_in[(size_t)c * nlm * K1 + k];
+    }
+  }
   // ---- Lambda = dE/dX_lm on the tensor cores: Lambda[lm][ia] = sum_jb X[lm][jb] U~_l(jb, ia) / sqrt(2l+1), with the symmetric
   //      U~_l(ia,jb) = 2 u (ia == jb) or sqrt(2) u (ia != jb), u = dE/dp at (l, pair(ia, jb)) ----
-  for (int t = warp; t < g.NTM * g.NTN; t += NW) {
+  for (int t = warp; t < (lambda_in ? 0 : g.NTM * g.NTN); t += NW) {
     const int mt = t / g.NTN, nt = t - mt * g.NTN;
     const int lm0 = s.mt_lm0[mt], l = s.mt_l[mt];
     const int ia = nt * 8 + fr;
@@ -1130,7 +1143,8 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restr
                                                           const double* __restrict__ pnorm, const double* __restrict__ gvec, int ldg, int g_splits,
                                                           size_t g_split_stride, const double* __restrict__ epart, int n_tiles_n,
                                                           double* __restrict__ local_e, double e_scale, double* __restrict__ force,
-                                                          double* __restrict__ vir_part, double* __restrict__ local_virial, double* __restrict__ fpair) {
+                                                          double* __restrict__ vir_part, double* __restrict__ local_virial, double* __restrict__ fpair,
+                                                          const double* __restrict__ lambda_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Geo g = make_geo(CN, CL, CNS);
   constexpr int n = CN, L1 = CL + 1, nlm = (CL + 1) * (CL + 1), K1 = CN * CNS, ns = CNS;
@@ -1161,20 +1175,22 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restr
     if (lane == 0) local_e[i] += e_scale * t;
   }
   // X_lm -> shared (asynchronous), zero padding; u = dE/dp from the K-split partials of gradPredict, pulled back through x = p/|p|
-  for (int k = lane; k < nlm * K1; k += 32) {
-    const int lm = k / K1, ic = k - lm * K1;
-    cp_async8(w.X + lm * XS + ic, xlm + (size_t)c * nlm * K1 + k);
+  if (!lambda_in) {
+    for (int k = lane; k < nlm * K1; k += 32) {
+      const int lm = k / K1, ic = k - lm * K1;
+      cp_async8(w.X + lm * XS + ic, xlm + (size_t)c * nlm * K1 + k);
+    }
+    cp_async_commit();
   }
-  cp_async_commit();
   for (int k = lane; k < g.XR * XS; k += 32) {
     const int lm = k / XS, ic = k - lm * XS;
     if (lm >= nlm || ic >= K1) w.X[k] = 0.0;
   }
   const double* xr = x + (size_t)c * d_pad;
   const double* gr = gvec + (size_t)c * ldg;
-  const double nrm = pnorm[c];
+  const double nrm = lambda_in ? 1.0 : pnorm[c];
   double loc = 0.0;
-  for (int q0 = 0; q0 < d - 1; q0 += 4 * 32) {
+  for (int q0 = 0; q0 < (lambda_in ? 0 : d - 1); q0 += 4 * 32) {
     double xv[4], gv[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
@@ -1197,7 +1213,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restr
   }
   const double sdot = warp_sum(loc);
   __syncwarp();
-  if (sp->normalise)
+  if (sp->normalise && !lambda_in)
     for (int q = lane; q < d - 1; q += 32) w.p[q] = (w.p[q] - xr[q] * sdot) / nrm;
   cp_async_wait_all();
   __syncwarp();
@@ -1211,6 +1227,12 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restr
     const int lm_end = (l + 1) * (l + 1);
 #pragma unroll 1
     for (int lm0 = l * l; lm0 < lm_end; lm0 += 8) {
+      if (lambda_in) {  // Lambda rows of this tile straight from the general path's pre-kernel (already scaled)
+        for (int k = lane; k < 8 * K18; k += 32) {
+          const int r = k / K18, col = k - r * K18;
+          scr[r * XS + col] = (lm0 + r < lm_end && col < K1) ? lambda_in[((size_t)c * nlm + lm0 + r) * K1 + col] : 0.0;
+        }
+      } else {
 #pragma unroll
       for (int nt = 0; nt < NTN; nt++) {
         const int ia = nt * 8 + fr;
@@ -1229,6 +1251,7 @@ __global__ void __launch_bounds__(NT, 4) k_soap_adjoint_w(const SoapDev* __restr
         }
         scr[fr * XS + nt * 8 + 2 * fk] = c0 * sc;
         scr[fr * XS + nt * 8 + 2 * fk + 1] = c1 * sc;
+      }
       }
       __syncwarp();
       const bool row_ok = lm0 + fr < lm_end;  // rows beyond this l belong to the next tile's l: left alone
@@ -1329,7 +1352,7 @@ void launch_compact(const int* flags_scan, const int* flags, int first, int n, i
 
 void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, double* x, double* xlm, double* pnorm,
-                         cudaStream_t st, int* launches) {
+                         cudaStream_t st, int* launches, int skip_power) {
   const int n_centres = n_centres_ub;
   if (n_centres <= 0) return;
   size_t sm = soap_forward_smem(h);
@@ -1339,20 +1362,21 @@ void launch_soap_forward(const SoapDev* sp, const SoapDev& h, const int* centres
     const size_t smw = carve_w(make_geo(N, L, S), h.d_pad, false, 0, nullptr, nullptr);                                    \
     cudaFuncSetAttribute(k_soap_forward_w<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);                \
     launch_pdl(k_soap_forward_w<N, L, S>, dim3((n_centres + NW - 1) / NW), dim3(NT), smw, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, \
-               pos, Z, lat, x, xlm, pnorm);                                                                                \
+               pos, Z, lat, x, xlm, pnorm, skip_power);                                                                    \
     return;                                                                                                                \
   }
   SOAP_SPECIALISATIONS(GO)
 #undef GO
   cudaFuncSetAttribute(k_soap_forward<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  launch_pdl(k_soap_forward<0, 0, 0>, dim3(n_centres), dim3(NT), sm, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm);
+  launch_pdl(k_soap_forward<0, 0, 0>, dim3(n_centres), dim3(NT), sm, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm,
+             skip_power);
 }
 
 void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                          const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
                          const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
                          double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, double* fpair, cudaStream_t st,
-                         int* launches) {
+                         int* launches, const double* lambda_in) {
   const int n_centres = n_centres_ub;
   if (n_centres <= 0) return;
   size_t sm = soap_adjoint_smem(h);
@@ -1364,7 +1388,7 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
     cudaFuncSetAttribute(k_soap_adjoint_w<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw);                                   \
     launch_pdl(k_soap_adjoint_w<N, L, S>, dim3((n_centres + NW - 1) / NW), dim3(NT), smw, st, sp, centres, n_centres_dev, n_centres, nbr_off, nbr_end,  \
                nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part,  \
-               local_virial, fpair);                                                                                                         \
+               local_virial, fpair, lambda_in);                                                                                              \
     return;                                                                                                                                   \
   }
   SOAP_ADJOINT_W(GOW)
@@ -1373,14 +1397,14 @@ void launch_soap_adjoint(const SoapDev* sp, const SoapDev& h, const int* centres
   if (h.n_max == N && h.l_max == L && h.n_species == S) {                                                                                     \
     cudaFuncSetAttribute(k_soap_adjoint<N, L, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                                      \
     launch_pdl(k_soap_adjoint<N, L, S>, dim3(n_centres), dim3(NT), sm, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, \
-               pnorm, gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair);         \
+               pnorm, gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair, lambda_in); \
     return;                                                                                                                                   \
   }
   SOAP_SPECIALISATIONS(GO)
 #undef GO
   cudaFuncSetAttribute(k_soap_adjoint<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   launch_pdl(k_soap_adjoint<0, 0, 0>, dim3(n_centres), dim3(NT), sm, st, sp, centres, n_centres_dev, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm,
-             gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair);
+             gvec, ldg, g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair, lambda_in);
 }
 
 }  // namespace gapb200

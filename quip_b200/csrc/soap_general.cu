@@ -171,6 +171,66 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// X (shared) -> Y1 = X W1, Y2 = X W2 -> the element list of the power spectrum -> normalised descriptor row c (descriptors.f95:8384-8451)
+__device__ __forceinline__ void g_power_tail(const SoapDev* __restrict__ sp, const SoapGenDev& g, const GSmem& s, int c, double* __restrict__ x,
+                                             double* __restrict__ pnorm) {
+  const int L = sp->l_max, nlm = (L + 1) * (L + 1), K1 = sp->n_species * sp->n_max, d = sp->d, d_pad = sp->d_pad, L1 = L + 1, np = g.n_pairs;
+  g_mix(s, g, nlm, K1);
+  __syncthreads();
+  double loc = 0.0;
+  for (int idx = threadIdx.x; idx < L1 * np; idx += GNT) {  // element l + (l_max+1) k (:8396-8447)
+    const int k = idx / L1, l = idx - k * L1, ia = g.pair_ia[k], jb = g.pair_jb[k];
+    double acc = 0.0;
+    for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) acc += s.Y1[lm * g.Ka + ia] * s.Y2[lm * g.Kb + jb];
+    const double v = acc * s.tlpo[l] * g.pair_fac[k];
+    s.p[idx] = v;
+    loc += v * v;
+  }
+  const double nrm = sqrt(gblock_sum(loc, s.red));  // :8450-8451
+  const double inv = sp->normalise ? 1.0 / nrm : 1.0;
+  double* xr = x + (size_t)c * d_pad;
+  for (int q = threadIdx.x; q < d_pad; q += GNT) xr[q] = q < d - 1 ? s.p[q] * inv : (q == d - 1 ? sp->sigma0 : 0.0);
+  if (threadIdx.x == 0) pnorm[c] = nrm;
+}
+
+// u = dE/dp from the K-split partials of gradPredict, pulled back through the normalisation, the element list and the mixing matrices:
+// leaves Lambda = dE/dX_lm [lm][K1] in s.X (synchronised)
+__device__ __forceinline__ void g_lambda_head(const SoapDev* __restrict__ sp, const SoapGenDev& g, const GSmem& s, int c, const double* __restrict__ x,
+                                              const double* __restrict__ xlm, const double* __restrict__ pnorm, const double* __restrict__ gvec, int ldg,
+                                              int g_splits, size_t g_split_stride) {
+  const int L = sp->l_max, nlm = (L + 1) * (L + 1), K1 = sp->n_species * sp->n_max, d = sp->d, d_pad = sp->d_pad, L1 = L + 1;
+  for (int k = threadIdx.x; k < nlm * K1; k += GNT) s.X[k] = xlm[(size_t)c * nlm * K1 + k];
+  for (int k = threadIdx.x; k < nlm * g.Ka; k += GNT) s.dY1[k] = 0.0;
+  for (int k = threadIdx.x; k < nlm * g.Kb; k += GNT) s.dY2[k] = 0.0;
+  // u = dE/dp: gradPredict (the K-split partials of GEMM-2 added in a fixed order) pulled back through x = p / |p| (:8595-8600)
+  const double* xr = x + (size_t)c * d_pad;
+  const double* gr = gvec + (size_t)c * ldg;
+  const double nrm = pnorm[c];
+  double loc = 0.0;
+  for (int q = threadIdx.x; q < d - 1; q += GNT) {
+    double gv = gr[q];
+    for (int k = 1; k < g_splits; k++) gv += gr[(size_t)k * g_split_stride + q];
+    s.p[q] = gv;
+    loc += xr[q] * gv;
+  }
+  const double sdot = gblock_sum(loc, s.red);  // (synchronises: X and the zeroed dY are visible afterwards)
+  if (sp->normalise)
+    for (int q = threadIdx.x; q < d - 1; q += GNT) s.p[q] = (s.p[q] - xr[q] * sdot) / nrm;
+  g_mix(s, g, nlm, K1);
+  __syncthreads();
+  g_dY(s, g, nlm, L1);  // dE/dY1, dE/dY2 (product rule on the element list)
+  __syncthreads();
+  // Lambda = dE/dX = dE/dY1 W1^T + dE/dY2 W2^T  (into X)
+  for (int idx = threadIdx.x; idx < nlm * K1; idx += GNT) {
+    const int lm = idx / K1, ic = idx - lm * K1;
+    double acc = 0.0;
+    for (int k = 0; k < g.Ka; k++) acc += s.dY1[lm * g.Ka + k] * g.W1[(size_t)ic * g.Ka + k];
+    for (int k = 0; k < g.Kb; k++) acc += s.dY2[lm * g.Kb + k] * g.W2[(size_t)ic * g.Kb + k];
+    s.X[idx] = acc;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(GNT) k_soap_forward_gen(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ centres,
                                                          const int* __restrict__ n_centres_dev, const int* __restrict__ nbr_off,
                                                          const int* __restrict__ nbr_end, const int* __restrict__ nbr_j, const int* __restrict__ nbr_s,
@@ -246,22 +306,7 @@ __global__ void __launch_bounds__(GNT) k_soap_forward_gen(const SoapDev* __restr
   __syncthreads();
   for (int k = threadIdx.x; k < nlm * K1; k += GNT) xlm[(size_t)c * nlm * K1 + k] = s.X[k];
   if (global_mode) return;  // average=T: the power spectrum is taken of the SUM over the centres (k_soap_global_power)
-  g_mix(s, g, nlm, K1);
-  __syncthreads();
-  double loc = 0.0;
-  for (int idx = threadIdx.x; idx < L1 * np; idx += GNT) {  // element l + (l_max+1) k (:8396-8447)
-    const int k = idx / L1, l = idx - k * L1, ia = g.pair_ia[k], jb = g.pair_jb[k];
-    double acc = 0.0;
-    for (int lm = l * l; lm < (l + 1) * (l + 1); lm++) acc += s.Y1[lm * g.Ka + ia] * s.Y2[lm * g.Kb + jb];
-    const double v = acc * s.tlpo[l] * g.pair_fac[k];
-    s.p[idx] = v;
-    loc += v * v;
-  }
-  const double nrm = sqrt(gblock_sum(loc, s.red));  // :8450-8451
-  const double inv = sp->normalise ? 1.0 / nrm : 1.0;
-  double* xr = x + (size_t)c * d_pad;
-  for (int q = threadIdx.x; q < d_pad; q += GNT) xr[q] = q < d - 1 ? s.p[q] * inv : (q == d - 1 ? sp->sigma0 : 0.0);
-  if (threadIdx.x == 0) pnorm[c] = nrm;
+  g_power_tail(sp, g, s, c, x, pnorm);
 }
 
 template <int NB>
@@ -300,36 +345,7 @@ __global__ void __launch_bounds__(GNT) k_soap_adjoint_gen(const SoapDev* __restr
     }
     __syncthreads();
   } else {
-  for (int k = threadIdx.x; k < nlm * K1; k += GNT) s.X[k] = xlm[(size_t)c * nlm * K1 + k];
-  for (int k = threadIdx.x; k < nlm * g.Ka; k += GNT) s.dY1[k] = 0.0;
-  for (int k = threadIdx.x; k < nlm * g.Kb; k += GNT) s.dY2[k] = 0.0;
-  // u = dE/dp: gradPredict (the K-split partials of GEMM-2 added in a fixed order) pulled back through x = p / |p| (:8595-8600)
-  const double* xr = x + (size_t)c * d_pad;
-  const double* gr = gvec + (size_t)c * ldg;
-  const double nrm = pnorm[c];
-  double loc = 0.0;
-  for (int q = threadIdx.x; q < d - 1; q += GNT) {
-    double gv = gr[q];
-    for (int k = 1; k < g_splits; k++) gv += gr[(size_t)k * g_split_stride + q];
-    s.p[q] = gv;
-    loc += xr[q] * gv;
-  }
-  const double sdot = gblock_sum(loc, s.red);  // (synchronises: X and the zeroed dY are visible afterwards)
-  if (sp->normalise)
-    for (int q = threadIdx.x; q < d - 1; q += GNT) s.p[q] = (s.p[q] - xr[q] * sdot) / nrm;
-  g_mix(s, g, nlm, K1);
-  __syncthreads();
-  g_dY(s, g, nlm, L1);  // dE/dY1, dE/dY2 (product rule on the element list)
-  __syncthreads();
-  // Lambda = dE/dX = dE/dY1 W1^T + dE/dY2 W2^T  (into X)
-  for (int idx = threadIdx.x; idx < nlm * K1; idx += GNT) {
-    const int lm = idx / K1, ic = idx - lm * K1;
-    double acc = 0.0;
-    for (int k = 0; k < g.Ka; k++) acc += s.dY1[lm * g.Ka + k] * g.W1[(size_t)ic * g.Ka + k];
-    for (int k = 0; k < g.Kb; k++) acc += s.dY2[lm * g.Kb + k] * g.W2[(size_t)ic * g.Kb + k];
-    s.X[idx] = acc;
-  }
-  __syncthreads();
+  g_lambda_head(sp, g, s, c, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride);
   // Lambda~ = Lambda P_l^T on the radial grid, stored as Xt[(s, g)][lm]: lm contiguous
   for (int idx = threadIdx.x; idx < nlm * Kg; idx += GNT) {
     const int lm = idx / Kg, t = idx - lm * Kg, sk = t / ng, gg = t - sk * ng, l = s.l_of[lm];
@@ -508,6 +524,38 @@ __global__ void __launch_bounds__(GNT) k_soap_adjoint_gen(const SoapDev* __restr
   }
 }
 
+// ---- compression modes on the EQUISPACED_GAUSS basis: the density expansion X_lm and the neighbour phase are those of the default power
+//      spectrum, so they run on soap.cu's DMMA kernels (forward with skip_power, adjoint with lambda_in); only the channel mixing and the
+//      element list are different, and these two small kernels supply them: X_lm -> descriptor, and dE/dx -> Lambda = dE/dX_lm.
+__global__ void __launch_bounds__(GNT) k_soap_power_gen(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ n_centres_dev,
+                                                        const double* __restrict__ xlm, double* __restrict__ x, double* __restrict__ pnorm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x;
+  if (c >= *n_centres_dev) return;
+  const int L = sp->l_max, nlm = (L + 1) * (L + 1), K1 = sp->n_species * sp->n_max;
+  GSmem s;
+  gcarve(L, sp->n_max, sp->n_species, sp->d_pad, g, false, 1, &s, smem_raw);
+  g_tables(sp, s, L, nlm);
+  for (int k = threadIdx.x; k < nlm * K1; k += GNT) s.X[k] = xlm[(size_t)c * nlm * K1 + k];
+  __syncthreads();
+  g_power_tail(sp, g, s, c, x, pnorm);
+}
+
+__global__ void __launch_bounds__(GNT) k_soap_lambda_gen(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ n_centres_dev,
+                                                         const double* __restrict__ x, const double* __restrict__ xlm, const double* __restrict__ pnorm,
+                                                         const double* __restrict__ gvec, int ldg, int g_splits, size_t g_split_stride,
+                                                         double* __restrict__ lambda_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x;
+  if (c >= *n_centres_dev) return;
+  const int L = sp->l_max, nlm = (L + 1) * (L + 1), K1 = sp->n_species * sp->n_max;
+  GSmem s;
+  gcarve(L, sp->n_max, sp->n_species, sp->d_pad, g, true, 1, &s, smem_raw);
+  g_tables(sp, s, L, nlm);
+  g_lambda_head(sp, g, s, c, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride);
+  for (int k = threadIdx.x; k < nlm * K1; k += GNT) lambda_out[(size_t)c * nlm * K1 + k] = s.X[k];
+}
+
 // ---- average=T (global SOAP, descriptors.f95:8357-8367, 8738-9008): ONE descriptor per configuration from the sum of the density
 //      expansions of all centres.  One CTA each: the sum + power spectrum, and the pull-back dE/dx -> Lambda~ shared by all centres.
 __global__ void __launch_bounds__(GNT) k_soap_global_power(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ n_centres_dev,
@@ -672,6 +720,25 @@ void launch_soap_adjoint_general(const SoapDev* sp, const SoapDev& h, const Soap
   else if (NB >= 2) GAP_ADJ_GEN(2);
   else GAP_ADJ_GEN(1);
 #undef GAP_ADJ_GEN
+  *launches += 1;
+}
+
+void launch_soap_power_general(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* n_centres_dev, int n_centres_ub, const double* xlm,
+                               double* x, double* pnorm, cudaStream_t st, int* launches) {
+  if (n_centres_ub <= 0) return;
+  const size_t sm = gcarve(h.l_max, h.n_max, h.n_species, h.d_pad, g, false, 1, nullptr, nullptr);
+  cudaFuncSetAttribute(k_soap_power_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_soap_power_gen<<<n_centres_ub, GNT, sm, st>>>(sp, g, n_centres_dev, xlm, x, pnorm);
+  *launches += 1;
+}
+
+void launch_soap_lambda_general(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* n_centres_dev, int n_centres_ub, const double* x,
+                                const double* xlm, const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride,
+                                double* lambda_out, cudaStream_t st, int* launches) {
+  if (n_centres_ub <= 0) return;
+  const size_t sm = soap_general_smem(h, g);
+  cudaFuncSetAttribute(k_soap_lambda_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_soap_lambda_gen<<<n_centres_ub, GNT, sm, st>>>(sp, g, n_centres_dev, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride, lambda_out);
   *launches += 1;
 }
 
