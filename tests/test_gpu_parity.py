@@ -797,6 +797,36 @@ def test_soap_variants_efv_vs_oracle(golden, tmp_path, case):
         pot.finalise()
 
 
+HYBRID_SHAPES = [
+    # (descriptor options on top of the shape, frames) -- shapes with warp-per-centre specialisations: (8,8,1) and (10,6,2)
+    ("soap cutoff=4.0 cutoff_transition_width=1.0 n_max=8 l_max=8 atom_sigma=0.5 central_weight=1.0 n_species=1 Z=14 species_Z={14} R_mix=T K=4", "si"),
+    ("soap cutoff=4.0 cutoff_transition_width=1.0 n_max=8 l_max=8 atom_sigma=0.5 central_weight=1.0 n_species=1 Z=14 species_Z={14} nu_R=1", "si"),
+    ("soap cutoff=4.0 cutoff_transition_width=1.0 n_max=8 l_max=8 atom_sigma=0.5 central_weight=1.0 n_species=1 Z=14 species_Z={14} diagonal_radial=T "
+     "normalise=F", "si"),
+    ("soap cutoff=4.5 n_max=10 l_max=6 atom_sigma=0.5 n_species=2 species_Z={23 41} n_Z=2 Z={23 41} Z_mix=T K=3 sym_mix=T", "quad"),
+    ("soap cutoff=4.5 n_max=10 l_max=6 atom_sigma=0.5 n_species=2 species_Z={23 41} n_Z=2 Z={23 41} coupling=F", "quad"),
+]
+
+
+@pytest.mark.parametrize("spec", range(len(HYBRID_SHAPES)))
+def test_compression_modes_on_specialised_shapes_vs_oracle(golden, si_frames, tmp_path, spec):
+    """Compression modes on the EQUISPACED_GAUSS basis borrow the default path's kernels (density expansion with skip_power, neighbour phase
+    with lambda_in): here on the shapes that have warp-per-centre specialisations, (8,8,1) and (10,6,2); E / F / V and the local
+    quantities against the oracle, plus the descriptor itself."""
+    desc, which = HYBRID_SHAPES[spec]
+    if which == "si":
+        frames = [si_frames[k] for k in (3, 8, 16)]
+    else:  # four-species cells: the two mapped species are centres and neighbours, the others are ignored (descriptors.f95:8194-8195)
+        frames = quad_datasets(golden, True)[:2] + quad_datasets(golden, False)[:1]
+    xml = multi_species_model(str(tmp_path), desc, frames, 12, seed=300 + spec, zeta=2.0 + (spec % 2))
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    for a in frames:
+        x, ci = pot.descriptor_calc(a, 0)
+        o = orc.soap_descriptor(desc, a)
+        assert np.array_equal(ci, o["ci"]) and np.abs(x - o["data"]).max() < 1e-12
+        check_efv(pot, om, a)
+
+
 # ----------------------------------------------------------------------------------------------------
 # skin-based neighbour-list reuse (calc_connect with cutoff_skin, Connection.f95:1085-1128)
 # ----------------------------------------------------------------------------------------------------
