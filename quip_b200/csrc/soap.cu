@@ -1336,8 +1336,8 @@ size_t soap_forward_smem(const SoapDev& h) { return carve(make_geo(h.n_max, h.l_
 size_t soap_adjoint_smem(const SoapDev& h) { return carve(make_geo(h.n_max, h.l_max, h.n_species), h.d_pad, true, nullptr, nullptr); }
 
 // (n_max, l_max, n_species) combinations with a fully specialised instantiation; everything else runs the generic one
-#define SOAP_SPECIALISATIONS(X) X(8, 8, 1) X(12, 8, 1) X(10, 6, 2)
-#define SOAP_ADJOINT_W(X) X(8, 8, 1)  // (12,8,1) and (10,6,2): per-warp state leaves < 12 warps per SM, measured slower than the block kernel
+#define SOAP_SPECIALISATIONS(X) X(8, 8, 1) X(12, 8, 1) X(10, 6, 2) X(12, 6, 1) X(10, 12, 1)
+#define SOAP_ADJOINT_W(X) X(8, 8, 1) X(12, 6, 1)  // (12,8,1) and (10,6,2): per-warp state leaves < 12 warps per SM, measured slower than the block kernel
 
 void launch_select_centres(const int* Z, int first, int last, const SoapDev* sp, int* flags, cudaStream_t st, int* launches) {
   int n = last - first + 1;

@@ -797,6 +797,22 @@ def test_soap_variants_efv_vs_oracle(golden, tmp_path, case):
         pot.finalise()
 
 
+@pytest.mark.parametrize("shape", [(12, 6), (12, 8), (10, 12), (6, 4)])
+def test_default_power_spectrum_shapes_vs_oracle(si_frames, tmp_path, shape):
+    """The default power spectrum at (n_max, l_max) = (12,6), (12,8), (10,12) (warp-per-centre / block specialisations) and (6,4) (run-time-shape
+    kernels): descriptor and E / F / V on Si frames against the oracle."""
+    n, l = shape
+    desc = "soap cutoff=4.0 cutoff_transition_width=1.0 n_max=%d l_max=%d atom_sigma=0.5 central_weight=1.0 n_species=1 Z=14 species_Z={14}" % (n, l)
+    frames = [si_frames[k] for k in (3, 8, 16)]
+    xml = multi_species_model(str(tmp_path), desc, frames, 12, seed=400 + n + l, zeta=4.0)
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    for a in frames:
+        x, ci = pot.descriptor_calc(a, 0)
+        o = orc.soap_descriptor(desc, a)
+        assert np.array_equal(ci, o["ci"]) and np.abs(x - o["data"]).max() < 1e-12
+        check_efv(pot, om, a)
+
+
 HYBRID_SHAPES = [
     # (descriptor options on top of the shape, frames) -- shapes with warp-per-centre specialisations: (8,8,1) and (10,6,2)
     ("soap cutoff=4.0 cutoff_transition_width=1.0 n_max=8 l_max=8 atom_sigma=0.5 central_weight=1.0 n_species=1 Z=14 species_Z={14} R_mix=T K=4", "si"),
