@@ -749,6 +749,26 @@ def test_local_gap_variance_and_gradient(si_model, si_frames):
         assert "gap_variance_gradient" not in r0 and np.abs(r0["var"] - r["var"]).max() < 1e-12 * scale
 
 
+@pytest.mark.parametrize("extra", [" R_mix=T K=3", " radial_basis=GTO"])
+def test_local_gap_variance_of_soap_variants(si_frames, tmp_path, extra):
+    # the predictive variance and its gradient through the compression-mode (borrowed default kernels) and GTO (general kernels) pull-backs
+    desc = "soap cutoff=4.0 cutoff_transition_width=1.0 n_max=6 l_max=4 atom_sigma=0.5 central_weight=1.0 n_species=1 Z=14 species_Z={14}" + extra
+    X = np.concatenate([orc.soap_descriptor(desc, si_frames[k])["data"] for k in (3, 8)])
+    rng = np.random.default_rng(77)
+    rows = rng.choice(len(X), size=10, replace=False)
+    coord = {"descriptor": desc, "covariance_type": 2, "delta": 1.3, "zeta": 2.0, "sparseX": X[rows], "alpha": rng.normal(size=10),
+             "sparseCutoff": np.ones(10)}  # (the variance estimate is only non-negative for unit sparse cutoffs, as gap_fit writes them)
+    xml = write_gap_xml(str(tmp_path / "var.xml"), [coord], e0={14: -1.0})
+    pot, om = Potential("", param_filename=xml), orc.Model(xml)
+    a = si_frames[8]
+    r = pot.calc(a, force=True, args_str="local_gap_variance=var gap_variance_regularisation=0.01")
+    o = om.calc(a, local_gap_variance=True, gap_variance_regularisation=0.01)
+    scale = np.abs(o["local_gap_variance"]).max()
+    assert np.abs(r["var"] - o["local_gap_variance"]).max() < 1e-7 * scale
+    assert np.abs(r["gap_variance_gradient"] - o["gap_variance_gradient"]).max() < 1e-6 * max(np.abs(o["gap_variance_gradient"]).max(), 1.0)
+    assert np.abs(r["force"] - o["force"]).max() < TOL_F
+
+
 # ----------------------------------------------------------------------------------------------------
 # SOAP variants: compression modes, nu_R / nu_S, Z_map, diagonal_radial, GTO / POLY radial bases -- the general
 # path of soap_general.cu against the reference's own golden vectors and, for the gradients, E/F/V against the oracle
