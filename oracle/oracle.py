@@ -701,7 +701,7 @@ class Model:
                                   float(connect_cutoff if connect_cutoff is not None else self.cutoff), first, last,
                                   nthreads, _dp(e), _dp(le), _dp(f), _dp(v), _dp(lv), _dp(t))
         if rc:
-            raise RuntimeError("orc_model_calc failed (rc=%d)" % rc)
+            raise RuntimeError("gpCoordinates_Predict: variance_estimate: negative variance predicted" if rc == 5 else "orc_model_calc failed (rc=%d)" % rc)
         out = {"energy": float(e[0]), "timings": t}
         if epc is not None:
             out["energy_per_coordinate"] = epc

@@ -767,6 +767,13 @@ def test_local_gap_variance_of_soap_variants(si_frames, tmp_path, extra):
     assert np.abs(r["var"] - o["local_gap_variance"]).max() < 1e-7 * scale
     assert np.abs(r["gap_variance_gradient"] - o["gap_variance_gradient"]).max() < 1e-6 * max(np.abs(o["gap_variance_gradient"]).max(), 1.0)
     assert np.abs(r["force"] - o["force"]).max() < TOL_F
+    # a negative variance is an error on both sides, as in gp_predict.f95:3876-3878 (sparse cutoffs below one make k_mm inconsistent with k)
+    bad = dict(coord, sparseCutoff=np.full(10, 0.6))
+    xml_bad = write_gap_xml(str(tmp_path / "var_bad.xml"), [bad], e0={14: -1.0})
+    with pytest.raises(RuntimeError, match="negative variance"):
+        Potential("", param_filename=xml_bad).calc(a, args_str="local_gap_variance=var gap_variance_regularisation=0.01")
+    with pytest.raises(RuntimeError, match="negative variance"):
+        orc.Model(xml_bad).calc(a, local_gap_variance=True, gap_variance_regularisation=0.01)
 
 
 # ----------------------------------------------------------------------------------------------------
