@@ -43,18 +43,21 @@ struct GSmem {
   double *ynorm, *Xt, *X, *Y1, *Y2, *dY1, *dY2, *p, *Phi, *Rr, *Yq, *Gq, *red, *part, *nbd, *nbr, *nbf, *nbdf, *tlpo;
   int *nbs, *nbj, *nbp, *l_of, *cnt;
 };
-// NB = neighbours per batch: Phi / Rr hold NB x (L+1) x n_grid radial values, Yq / Gq NB x nlm (x 3) harmonics
+// NB = neighbours per batch: Phi / Rr hold NB x (L+1) x n_grid radial values, Yq / Gq NB x nlm (x 3) harmonics.  NB = 0: no neighbour phase
+// (the kernels that only turn X_lm into the descriptor or dE/dx into Lambda): the radial-grid, batch and neighbour arrays are left out
 __host__ __device__ inline size_t gcarve(int L, int n, int ns, int d_pad, const SoapGenDev& g, bool adjoint, int NB, GSmem* s, unsigned char* base) {
   const int nlm = (L + 1) * (L + 1), K1 = ns * n, Kg = ns * g.n_grid;
+  const size_t nbn = NB > 0 ? GNT : 0;
   size_t o = 0;
   auto take = [&](size_t cnt) { size_t r = o; o += ((cnt + 1) & ~(size_t)1) * sizeof(double); return r; };
-  const size_t oyn = take((size_t)(L + 1) * (L + 2) / 2), oXt = take((size_t)nlm * Kg), oX = take((size_t)nlm * K1), oY1 = take((size_t)nlm * g.Ka),
-               oY2 = take((size_t)nlm * g.Kb), odY1 = take(adjoint ? (size_t)nlm * g.Ka : 0), odY2 = take(adjoint ? (size_t)nlm * g.Kb : 0),
-               op = take(d_pad), oPhi = take((size_t)NB * (L + 1) * g.n_grid), oRr = take(adjoint ? (size_t)NB * (L + 1) * g.n_grid : 0),
-               oYq = take((size_t)NB * nlm), oGq = take(adjoint ? 3 * (size_t)NB * nlm : 0), ored = take(64),
-               opart = take(adjoint ? (size_t)NB * GNW * 4 : 0), onbd = take(3 * GNT), onbr = take(GNT), onbf = take(GNT), onbdf = take(GNT), otl = take(L + 1);
+  const size_t oyn = take((size_t)(L + 1) * (L + 2) / 2), oXt = take(NB > 0 ? (size_t)nlm * Kg : 0), oX = take((size_t)nlm * K1),
+               oY1 = take((size_t)nlm * g.Ka), oY2 = take((size_t)nlm * g.Kb), odY1 = take(adjoint ? (size_t)nlm * g.Ka : 0),
+               odY2 = take(adjoint ? (size_t)nlm * g.Kb : 0), op = take(d_pad), oPhi = take((size_t)NB * (L + 1) * g.n_grid),
+               oRr = take(adjoint ? (size_t)NB * (L + 1) * g.n_grid : 0), oYq = take((size_t)NB * nlm), oGq = take(adjoint ? 3 * (size_t)NB * nlm : 0),
+               ored = take(64), opart = take(adjoint ? (size_t)NB * GNW * 4 : 0), onbd = take(3 * nbn), onbr = take(nbn), onbf = take(nbn),
+               onbdf = take(nbn), otl = take(L + 1);
   const size_t oi = o;
-  o += sizeof(int) * (3 * GNT + nlm + 8);
+  o += sizeof(int) * (3 * nbn + nlm + 8);
   o = (o + 15) & ~(size_t)15;
   if (s) {
     s->ynorm = (double*)(base + oyn); s->Xt = (double*)(base + oXt); s->X = (double*)(base + oX); s->Y1 = (double*)(base + oY1);
@@ -62,7 +65,7 @@ __host__ __device__ inline size_t gcarve(int L, int n, int ns, int d_pad, const 
     s->Phi = (double*)(base + oPhi); s->Rr = (double*)(base + oRr); s->Yq = (double*)(base + oYq); s->Gq = (double*)(base + oGq);
     s->red = (double*)(base + ored); s->part = (double*)(base + opart); s->nbd = (double*)(base + onbd); s->nbr = (double*)(base + onbr);
     s->nbf = (double*)(base + onbf); s->nbdf = (double*)(base + onbdf); s->tlpo = (double*)(base + otl);
-    s->nbs = (int*)(base + oi); s->nbj = s->nbs + GNT; s->nbp = s->nbj + GNT; s->l_of = s->nbp + GNT; s->cnt = s->l_of + nlm;
+    s->nbs = (int*)(base + oi); s->nbj = s->nbs + nbn; s->nbp = s->nbj + nbn; s->l_of = s->nbp + nbn; s->cnt = s->l_of + nlm;
   }
   return o;
 }
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(GNT) k_soap_power_gen(const SoapDev* __restric
   if (c >= *n_centres_dev) return;
   const int L = sp->l_max, nlm = (L + 1) * (L + 1), K1 = sp->n_species * sp->n_max;
   GSmem s;
-  gcarve(L, sp->n_max, sp->n_species, sp->d_pad, g, false, 1, &s, smem_raw);
+  gcarve(L, sp->n_max, sp->n_species, sp->d_pad, g, false, 0, &s, smem_raw);
   g_tables(sp, s, L, nlm);
   for (int k = threadIdx.x; k < nlm * K1; k += GNT) s.X[k] = xlm[(size_t)c * nlm * K1 + k];
   __syncthreads();
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(GNT) k_soap_lambda_gen(const SoapDev* __restri
   if (c >= *n_centres_dev) return;
   const int L = sp->l_max, nlm = (L + 1) * (L + 1), K1 = sp->n_species * sp->n_max;
   GSmem s;
-  gcarve(L, sp->n_max, sp->n_species, sp->d_pad, g, true, 1, &s, smem_raw);
+  gcarve(L, sp->n_max, sp->n_species, sp->d_pad, g, true, 0, &s, smem_raw);
   g_tables(sp, s, L, nlm);
   g_lambda_head(sp, g, s, c, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride);
   for (int k = threadIdx.x; k < nlm * K1; k += GNT) lambda_out[(size_t)c * nlm * K1 + k] = s.X[k];
@@ -726,7 +729,7 @@ void launch_soap_adjoint_general(const SoapDev* sp, const SoapDev& h, const Soap
 void launch_soap_power_general(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* n_centres_dev, int n_centres_ub, const double* xlm,
                                double* x, double* pnorm, cudaStream_t st, int* launches) {
   if (n_centres_ub <= 0) return;
-  const size_t sm = gcarve(h.l_max, h.n_max, h.n_species, h.d_pad, g, false, 1, nullptr, nullptr);
+  const size_t sm = gcarve(h.l_max, h.n_max, h.n_species, h.d_pad, g, false, 0, nullptr, nullptr);
   cudaFuncSetAttribute(k_soap_power_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   k_soap_power_gen<<<n_centres_ub, GNT, sm, st>>>(sp, g, n_centres_dev, xlm, x, pnorm);
   *launches += 1;
@@ -736,7 +739,7 @@ void launch_soap_lambda_general(const SoapDev* sp, const SoapDev& h, const SoapG
                                 const double* xlm, const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride,
                                 double* lambda_out, cudaStream_t st, int* launches) {
   if (n_centres_ub <= 0) return;
-  const size_t sm = soap_general_smem(h, g);
+  const size_t sm = gcarve(h.l_max, h.n_max, h.n_species, h.d_pad, g, true, 0, nullptr, nullptr);
   cudaFuncSetAttribute(k_soap_lambda_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   k_soap_lambda_gen<<<n_centres_ub, GNT, sm, st>>>(sp, g, n_centres_dev, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride, lambda_out);
   *launches += 1;

@@ -757,7 +757,7 @@ def test_local_gap_variance_of_soap_variants(si_frames, tmp_path, extra):
     rng = np.random.default_rng(77)
     rows = rng.choice(len(X), size=10, replace=False)
     coord = {"descriptor": desc, "covariance_type": 2, "delta": 1.3, "zeta": 2.0, "sparseX": X[rows], "alpha": rng.normal(size=10),
-             "sparseCutoff": np.ones(10)}  # (the variance estimate is only non-negative for unit sparse cutoffs, as gap_fit writes them)
+             "sparseCutoff": np.ones(10)}  # (unit sparse cutoffs, as gap_fit writes them: larger ones drive the estimate negative)
     xml = write_gap_xml(str(tmp_path / "var.xml"), [coord], e0={14: -1.0})
     pot, om = Potential("", param_filename=xml), orc.Model(xml)
     a = si_frames[8]
@@ -767,8 +767,8 @@ def test_local_gap_variance_of_soap_variants(si_frames, tmp_path, extra):
     assert np.abs(r["var"] - o["local_gap_variance"]).max() < 1e-7 * scale
     assert np.abs(r["gap_variance_gradient"] - o["gap_variance_gradient"]).max() < 1e-6 * max(np.abs(o["gap_variance_gradient"]).max(), 1.0)
     assert np.abs(r["force"] - o["force"]).max() < TOL_F
-    # a negative variance is an error on both sides, as in gp_predict.f95:3876-3878 (sparse cutoffs below one make k_mm inconsistent with k)
-    bad = dict(coord, sparseCutoff=np.full(10, 0.6))
+    # a negative variance is an error on both sides, as in gp_predict.f95:3876-3878 (k carries the sparse cutoffs, k_mm does not)
+    bad = dict(coord, sparseCutoff=np.full(10, 3.0))
     xml_bad = write_gap_xml(str(tmp_path / "var_bad.xml"), [bad], e0={14: -1.0})
     with pytest.raises(RuntimeError, match="negative variance"):
         Potential("", param_filename=xml_bad).calc(a, args_str="local_gap_variance=var gap_variance_regularisation=0.01")
