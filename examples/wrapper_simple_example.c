@@ -1,6 +1,6 @@
-/* The reference's C example (src/Programs/quip_wrapper_simple_example_C.c: two atoms in a 20 A box through quip_wrapper_simple_) against
- * libgapb200.so: the one-shot entry point gap_b200_wrapper_simple, then the handle interface (initialise / cutoff / calc / finalise) on the same
- * configuration.  Build and run (needs a B200; there is no CPU fallback):
+/* A C caller of libgapb200.so (the role src/Programs/quip_wrapper_simple_example_C.c plays for libquip): a hydrogen pair in a periodic box,
+ * first through the one-shot entry point gap_b200_wrapper_simple, then through the handle interface (initialise / cutoff / calc / finalise).
+ * Build and run (needs a B200; there is no CPU fallback):
  *   gcc -Iinclude examples/wrapper_simple_example.c -Lquip_b200 -lgapb200 -Wl,-rpath,$PWD/quip_b200 -o /tmp/wrapper_simple_example
  *   /tmp/wrapper_simple_example tests/golden/GAP.xml
  */
@@ -9,37 +9,36 @@
 
 #include "gap_b200.h"
 
+#define N_ATOMS 2
+
+static int fail(const char* where) {
+  fprintf(stderr, "%s: %s\n", where, gap_last_error());
+  return 1;
+}
+
 int main(int argc, char** argv) {
   const char* xml = argc > 1 ? argv[1] : "gp.xml";
-  int n = 2;
-  double lattice[3][3] = {{20.0, 0.0, 0.0}, {0.0, 20.0, 0.0}, {0.0, 0.0, 20.0}};
-  int Z[2] = {1, 1};
-  double coord[2][3] = {{-7.110371, -3.533572, 2.147261}, {-7.933029, -3.234956, 2.573383}};
-  double energy = 0.0, force[2][3], virial[3][3];
-  if (argc > 2) Z[0] = Z[1] = atoi(argv[2]);
+  const int species = argc > 2 ? atoi(argv[2]) : 1;
+  /* Fortran layouts: cell(3,3) column-major (columns = cell vectors), positions(3,N) */
+  const double cell[9] = {12.0, 0.0, 0.0, 0.0, 12.0, 0.0, 0.0, 0.0, 12.0};
+  const double positions[3 * N_ATOMS] = {1.50, 2.25, 3.00, 2.35, 2.75, 3.40};
+  const int numbers[N_ATOMS] = {species, species};
+  const int n = N_ATOMS, periodic[3] = {1, 1, 1};
+  double e_total = 0.0, forces[3 * N_ATOMS], stress_virial[9], e_atom[N_ATOMS], e_again = 0.0, forces_again[3 * N_ATOMS];
 
-  if (gap_b200_wrapper_simple(xml, &n, &lattice[0][0], Z, &coord[0][0], &energy, &force[0][0], &virial[0][0])) {
-    fprintf(stderr, "gap_b200_wrapper_simple: %s\n", gap_last_error());
-    return 1;
-  }
-  printf("Energy = %.12e\n", energy);
-  printf("Force0 = %.12e %.12e %.12e\n", force[0][0], force[0][1], force[0][2]);
+  if (gap_b200_wrapper_simple(xml, &n, cell, numbers, positions, &e_total, forces, stress_virial)) return fail("gap_b200_wrapper_simple");
+  printf("Energy = %.12e\n", e_total);
+  printf("Force0 = %.12e %.12e %.12e\n", forces[0], forces[1], forces[2]);
 
   gap_potential* pot = NULL;
-  if (gap_potential_filename_initialise(&pot, "IP GAP", xml, 0)) {
-    fprintf(stderr, "gap_potential_filename_initialise: %s\n", gap_last_error());
-    return 1;
-  }
-  int pbc[3] = {1, 1, 1};
-  double e2 = 0.0, f2[2][3], local_e[2];
+  if (gap_potential_filename_initialise(&pot, "IP GAP", xml, 0)) return fail("gap_potential_filename_initialise");
   printf("Cutoff = %.6f\n", gap_potential_cutoff(pot));
-  if (gap_potential_calc(pot, n, &coord[0][0], Z, &lattice[0][0], pbc, "", &e2, local_e, &f2[0][0], NULL, NULL)) {
-    fprintf(stderr, "gap_potential_calc: %s\n", gap_last_error());
+  if (gap_potential_calc(pot, n, positions, numbers, cell, periodic, "", &e_again, e_atom, forces_again, NULL, NULL)) {
     gap_potential_finalise(pot);
-    return 1;
+    return fail("gap_potential_calc");
   }
-  printf("Energy2 = %.12e\n", e2);
-  printf("LocalE = %.12e %.12e\n", local_e[0], local_e[1]);
+  printf("Energy2 = %.12e\n", e_again);
+  printf("LocalE = %.12e %.12e\n", e_atom[0], e_atom[1]);
   gap_potential_finalise(pot);
   return 0;
 }

@@ -1026,7 +1026,7 @@ def test_angle_3b_silicon_frames_partition_and_deterministic(si_frames, tmp_path
 
 
 def test_c_example_program_matches_python_binding(gap_xml_pot, golden, tmp_path):
-    # examples/wrapper_simple_example.c (the reference's quip_wrapper_simple_example_C.c against this library), compiled with gcc and run
+    # examples/wrapper_simple_example.c (a plain-C caller of the library, the role of the reference's quip_wrapper_simple_example_C.c), compiled with gcc and run
     import subprocess
 
     from tests.test_host_cpu import _build_c_example
@@ -1034,7 +1034,7 @@ def test_c_example_program_matches_python_binding(gap_xml_pot, golden, tmp_path)
     r = subprocess.run([exe, os.path.join(golden, "GAP.xml")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     out = dict(line.split(" = ") for line in r.stdout.strip().splitlines())
-    a = Atoms([1, 1], [[-7.110371, -3.533572, 2.147261], [-7.933029, -3.234956, 2.573383]], np.eye(3) * 20.0, True)
+    a = Atoms([1, 1], [[1.50, 2.25, 3.00], [2.35, 2.75, 3.40]], np.eye(3) * 12.0, True)
     ref = gap_xml_pot.calc(a, force=True, local_energy=True)
     assert abs(float(out["Energy"]) - ref["energy"]) < 1e-10 and abs(float(out["Energy2"]) - ref["energy"]) < 1e-10
     assert np.abs(np.array(out["Force0"].split(), dtype=float) - ref["force"][0]).max() < 1e-10
