@@ -68,8 +68,9 @@ int gap_comm_get_unique_id(char* id /* GAP_COMM_ID_BYTES */);
 int gap_potential_set_comm(gap_potential* pot, const char* id /* GAP_COMM_ID_BYTES */, int rank, int n_ranks);
 /* rank / n_ranks of the handle and the transport of its last reduction ("nccl", "p2p" or "none") */
 int gap_potential_comm_info(const gap_potential* pot, int* rank, int* n_ranks, char* transport, size_t n);
-/* the last peer-memory reduction on this rank, from %globaltimer inside the kernel: microseconds it waited for the other ranks'
- * partials (the skew between the ranks' evaluations) and microseconds of the sum phase itself */
+/* the last peer-memory reduction on this rank, from %globaltimer inside the kernel.  One-shot kernel: microseconds it waited for the other
+ * ranks' partials (the skew between the ranks' evaluations) and microseconds of the sum phase itself.  Low-latency kernel: microseconds of
+ * its push phase, and of everything after it (polling for the other ranks' data, summing, publishing and collecting the totals) */
 int gap_potential_comm_timing(const gap_potential* pot, double* wait_us, double* sum_us);
 
 /* calc(pot, at, energy, force, virial, local_energy, local_virial, args_str) (Potential.f95:803 ->

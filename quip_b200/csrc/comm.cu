@@ -2,8 +2,8 @@
 //
 // Reference semantics: sum_in_place(mpi, f) etc. = MPI_Allreduce(MPI_IN_PLACE, ..., MPI_SUM) (src/libAtoms/MPI_context.f95:668-694),
 // issued five times at the end of IPModel_GAP_Calc (src/Potentials/IPModel_GAP.f95:538-556).  Here: ONE reduction of one packed
-// buffer, enqueued on the evaluation's stream, by NCCL or -- for latency-bound sizes -- by one kernel that reads the partials
-// of all ranks through NVLink peer mappings.
+// buffer, enqueued on the evaluation's stream, by NCCL or -- for latency-bound sizes -- by one kernel over NVLink peer mappings: a one-shot
+// pull of all ranks' partials (2-3 ranks) or a reduce-scatter + all-gather by push in self-validating 16-byte cells (4 ranks and more).
 #include <dlfcn.h>
 #include <nccl.h>
 

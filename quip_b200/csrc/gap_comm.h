@@ -44,8 +44,8 @@ void comm_check(GapComm* c);
 // "nccl" / "p2p" transport of the last packed reduction, and the number of peer reductions / NCCL calls so far
 const char* comm_last_transport(const GapComm* c);
 long comm_launch_count(const GapComm* c);
-// last peer-memory reduction on this rank: microseconds spent waiting for the other ranks' partials (= the skew between the ranks) and
-// microseconds of the sum phase (block 0's share)
+// last peer-memory reduction on this rank (block 0's view): one-shot kernel -- microseconds spent waiting for the other ranks' partials (= the skew
+// between the ranks) and microseconds of the sum phase; low-latency kernel -- microseconds of the push phase and of everything after it
 void comm_last_stamps(const GapComm* c, double* wait_us, double* sum_us);
 
 }  // namespace gapb200
