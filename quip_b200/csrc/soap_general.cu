@@ -12,10 +12,14 @@
 // Gradients in REVERSE mode, as in soap.cu: dE/dp -> dE/dY1, dE/dY2 -> Lambda = dE/dX -> Lambda~ = Lambda P^T on the radial grid,
 // then per neighbour the 3-vector f_gp.  The reference's forward-mode dY / grad_data (:8311-8336, :8470-8555) never exists.
 //
-// One CTA per centre, plain FP64 FMAs.  The neighbours of a centre are compacted and processed in BATCHES: the radial recursions and the
-// harmonics of a whole batch run as independent items across the CTA's threads (one barrier per batch instead of two per neighbour), the
-// forward accumulation keeps its output element in a register across the batch, and the adjoint contracts Lambda~ (stored with the lm index
-// contiguous: conflict-free for lanes over lm) against every neighbour of the batch with one thread per lm and register accumulators.
+// Two ways through this file:
+//  * compression modes on the EQUISPACED_GAUSS basis: X_lm and the neighbour phase do not depend on the variant, so they run on soap.cu's
+//    kernels (forward with skip_power, adjoint with lambda_in); k_soap_power_gen (X_lm -> descriptor) and k_soap_lambda_gen (dE/dx ->
+//    Lambda) supply the variant-specific middle, one small CTA per centre;
+//  * GTO / POLY (radial grid of 3 n_max points, per-l maps) and average=T: k_soap_forward_gen / k_soap_adjoint_gen, one CTA per centre.
+//    The neighbours of a centre are compacted and processed in BATCHES: the radial recursions and the harmonics of a whole batch run as
+//    independent items across the CTA's threads (one barrier per batch instead of two per neighbour); the density accumulation and the
+//    adjoint contraction of Lambda~ (stored with the lm index contiguous) against the batch are small FP64 tensor-core GEMMs per l.
 // Fixed-order reductions throughout; only the final force scatter uses FP64 atomics (per-slot stores in deterministic mode).
 #include "gap_device.cuh"
 #include "soap_device.cuh"
