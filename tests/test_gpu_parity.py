@@ -64,6 +64,22 @@ def test_neighbour_list_bit_exact_fixtures(gap_xml_pot, golden, si_frames):
             assert_same_list(gap_xml_pot, a, rc)
 
 
+def test_left_handed_and_skewed_cells(si_model, si_frames):
+    # a left-handed lattice (two cell vectors exchanged: negative triple product) and a strongly sheared one: list bit-exact, E / F / V vs oracle
+    pot, om, _ = si_model
+    a = si_frames[8]
+    swapped = Atoms(a.numbers, a.positions, a.cell[[1, 0, 2]], True)
+    assert np.linalg.det(swapped.cell) * np.linalg.det(a.cell) < 0
+    shear = np.eye(3)
+    shear[0, 1], shear[1, 2] = 0.45, -0.35
+    sheared = Atoms(a.numbers, a.positions @ shear.T, a.cell @ shear.T, True)
+    for b in (swapped, sheared):
+        assert_same_list(pot, b, 6.0)
+        check_efv(pot, om, b)
+    # exchanging two cell vectors describes the same crystal
+    assert abs(pot.calc(swapped)["energy"] - pot.calc(a)["energy"]) < 1e-9
+
+
 def test_neighbour_list_pbc_variants_and_offsets(gap_xml_pot, si_frames):
     # tests/test_neighbour_list.py idea: every pbc combination, and invariance under lattice-vector offsets
     a = si_frames[8]
