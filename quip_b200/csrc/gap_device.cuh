@@ -213,6 +213,14 @@ void launch_soap_lambda_general(const SoapDev* sp, const SoapDev& h, const SoapG
                                 const double* xlm, const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride,
                                 double* lambda_out, cudaStream_t st, int* launches);
 
+// GTO / POLY in grid passes of gp <= 16 points through soap.cu's kernels (see soap_general.cu): pass buffers [pass][centre][nlm][n_species * gp]
+void launch_soap_power_grid(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* centres, const int* n_centres_dev, int n_centres_ub,
+                            const int* Z, const double* xt_pass, size_t pass_stride, int gp, double* x, double* xlm, double* pnorm, cudaStream_t st,
+                            int* launches);
+void launch_soap_lambda_grid(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* n_centres_dev, int n_centres_ub, const double* x,
+                             const double* xlm, const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, double* lam_pass,
+                             size_t pass_stride, int gp, cudaStream_t st, int* launches);
+
 // ---- pair2b.cu -----------------------------------------------------------------------------
 constexpr int PAIR2B_MAX_EXP = 4;
 struct Pair2bDev {

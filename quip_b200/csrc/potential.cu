@@ -69,6 +69,11 @@ struct CoordDev {
   SoapDev* d_sp = nullptr;
   bool general = false;        // compression modes / GTO / POLY: soap_general.cu kernels
   bool hybrid = false;         // general on the EQUISPACED_GAUSS basis: soap.cu's kernels for the density expansion and the neighbour phase
+  // GTO / POLY through soap.cu's kernels in passes over the radial grid (grid_passes slices of grid_gp <= 16 points; 0 = not used):
+  // h_grid / d_sp_grid = clones of the descriptor whose basis points are the slice, identity transform, no central term
+  int grid_passes = 0, grid_gp = 0;
+  SoapDev h_grid;
+  SoapDev* d_sp_grid[3] = {nullptr, nullptr, nullptr};
   SoapGenDev gen;
   void* gen_blob = nullptr;    // one device allocation behind the pointers of gen
   double* gen_global = nullptr; // average=T: [Xg | Lt] (see SoapGenDev)
@@ -141,6 +146,7 @@ struct gap_potential {
   DevBuf b_fpair, b_fself, b_dkeys, b_dkeys2, b_dvals, b_dvals2, b_joff, b_dcub;
   DevBuf b_a3idx;              // angle_3b: compacted in-cutoff entries of each list row (int per slot)
   DevBuf b_lambda;             // hybrid SOAP coordinates: Lambda = dE/dX_lm [centre][nlm][K1]
+  DevBuf b_xt_pass, b_lam_pass; // GTO / POLY grid passes: [pass][centre][nlm][n_species * gp]
   // skin-based reuse of the neighbour list (calc_connect with cutoff_skin, Connection.f95:1085-1128)
   double cutoff_skin = 0.0;
   bool list_valid = false;     // cv_* describe a list built with last_cut for the geometry remembered below
@@ -753,6 +759,25 @@ void upload_model(gap_potential* P) {
       memset(&cd.gen, 0, sizeof(cd.gen));
       cd.general = s.general;
       cd.hybrid = s.general && !s.global && s.radial_basis == "EQUISPACED_GAUSS" && s.n_grid == s.n_max && getenv("GAP_B200_SOAP_HYBRID") == nullptr;
+      if (s.general && !s.global && s.radial_basis != "EQUISPACED_GAUSS" && getenv("GAP_B200_SOAP_HYBRID") == nullptr) {
+        const int G = s.n_grid;  // = 3 n_max: always divisible by 3, and G / 3 = n_max <= 16
+        const int npass = G <= SOAP_NMAX_CAP ? 1 : ((G % 2 == 0 && G / 2 <= SOAP_NMAX_CAP) ? 2 : 3);
+        if (G % npass == 0 && G / npass <= SOAP_NMAX_CAP) {
+          SoapDev hg = h;
+          const int gp = G / npass;
+          hg.n_max = gp; hg.K1 = s.n_species * gp; hg.central_weight = 0.0; hg.chol00 = 0.0;
+          memset(hg.T, 0, sizeof(hg.T));
+          for (int a = 0; a < gp; a++) hg.T[a + gp * a] = 1.0;
+          if (soap_adjoint_smem(hg) <= prop.sharedMemPerBlockOptin && soap_forward_smem(hg) <= prop.sharedMemPerBlockOptin) {
+            cd.grid_passes = npass; cd.grid_gp = gp; cd.h_grid = hg;
+            for (int p = 0; p < npass; p++) {
+              for (int a = 0; a < gp; a++) hg.r_basis[a] = s.r_grid[(size_t)p * gp + a];
+              CUDA_OK(cudaMalloc(&cd.d_sp_grid[p], sizeof(SoapDev)));
+              CUDA_OK(cudaMemcpy(cd.d_sp_grid[p], &hg, sizeof(SoapDev), cudaMemcpyHostToDevice));
+            }
+          }
+        }
+      }
       if (s.general) {  // tables of the general path, packed into one allocation (doubles first, then the two int lists)
         const size_t np = s.pair_ia.size();
         std::vector<double> blob;
@@ -919,11 +944,23 @@ CalcArgs parse_calc_args(const gap_potential* P, const char* args_str) {
 
 // SOAP adjoint + scatter of a coordinate: the DMMA kernels of soap.cu, or the general path of soap_general.cu.  fpair != NULL: deterministic
 // scatter (force = the per-atom scratch of the centres' own sums, see gap_device.cuh)
-void soap_adjoint_any(gap_potential* P, const CoordDev& cd, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
+int soap_adjoint_any(gap_potential* P, const CoordDev& cd, const int* centres, const int* n_centres_dev, int n_centres_ub, const int* nbr_off, const int* nbr_end,
                       const int* nbr_j, const int* nbr_s, const double* pos, const int* Z, Lattice9 lat, const double* x, const double* xlm,
                       const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, const double* epart, int n_tiles_n,
                       double* local_e, double e_scale, double* force, double* vir_part, double* local_virial, cudaStream_t st, int* launches,
                       double* fpair = nullptr) {
+  if (cd.grid_passes && gvec && !fpair) {  // GTO / POLY: dE/dx -> Lambda~ on the radial grid, then one run of the default kernels per grid slice
+    const size_t stride = (size_t)(n_centres_ub > 0 ? n_centres_ub : 1) * cd.h.nlm * cd.h_grid.K1;
+    P->b_lam_pass.ensure(sizeof(double) * stride * cd.grid_passes);
+    launch_soap_lambda_grid(cd.d_sp, cd.h, cd.gen, n_centres_dev, n_centres_ub, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride,
+                            P->b_lam_pass.as<double>(), stride, cd.grid_gp, st, launches);
+    for (int p = 0; p < cd.grid_passes; p++)  // the energy fold (epart) belongs to one pass only; every pass has its own block of virial partials
+      launch_soap_adjoint(cd.d_sp_grid[p], cd.h_grid, centres, n_centres_dev, n_centres_ub, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec,
+                          ldg, g_splits, g_split_stride, p == 0 ? epart : nullptr, n_tiles_n, local_e, e_scale, force,
+                          vir_part ? vir_part + 9 * (size_t)n_centres_ub * p : nullptr, local_virial, nullptr, st, launches,
+                          P->b_lam_pass.as<double>() + stride * p);
+    return cd.grid_passes;
+  }
   if (cd.hybrid && gvec) {  // variant-specific pull-back dE/dx -> Lambda, then the default path's transform pull-back and neighbour phase
     P->b_lambda.ensure(sizeof(double) * (size_t)(n_centres_ub > 0 ? n_centres_ub : 1) * cd.h.nlm * cd.h.K1);
     launch_soap_lambda_general(cd.d_sp, cd.h, cd.gen, n_centres_dev, n_centres_ub, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride,
@@ -937,6 +974,7 @@ void soap_adjoint_any(gap_potential* P, const CoordDev& cd, const int* centres, 
   else
     launch_soap_adjoint(cd.d_sp, cd.h, centres, n_centres_dev, n_centres_ub, nbr_off, nbr_end, nbr_j, nbr_s, pos, Z, lat, x, xlm, pnorm, gvec, ldg,
                         g_splits, g_split_stride, epart, n_tiles_n, local_e, e_scale, force, vir_part, local_virial, fpair, st, launches);
+  return 1;  // blocks of n_centres_ub virial partials written
 }
 
 // reverse index of the neighbour-list slots by receiving atom, for the deterministic scatter; returns the number of slots
@@ -1015,7 +1053,15 @@ void soap_forward_stage(gap_potential* P, const CoordDev& cd, int n_ub, const do
   P->b_x.ensure(sizeof(double) * (size_t)nc_pad * cd.d_pad);
   P->b_xlm.ensure(sizeof(double) * (size_t)(n_ub > 0 ? n_ub : 1) * cd.h.nlm * cd.h.K1);
   P->b_pnorm.ensure(sizeof(double) * (size_t)nc_pad);
-  if (cd.hybrid) {  // density expansion on the default path's kernels, channel mixing + element list from the stored X_lm
+  if (cd.grid_passes) {  // GTO / POLY: the radial grid in slices through the default path's kernels, then the per-l map, mixing and element list
+    const size_t stride = (size_t)(n_ub > 0 ? n_ub : 1) * cd.h.nlm * cd.h_grid.K1;
+    P->b_xt_pass.ensure(sizeof(double) * stride * cd.grid_passes);
+    for (int p = 0; p < cd.grid_passes; p++)
+      launch_soap_forward(cd.d_sp_grid[p], cd.h_grid, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
+                          P->b_x.as<double>(), P->b_xt_pass.as<double>() + stride * p, P->b_pnorm.as<double>(), st, &launches, 1);
+    launch_soap_power_grid(cd.d_sp, cd.h, cd.gen, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, d_Z, P->b_xt_pass.as<double>(), stride, cd.grid_gp,
+                           P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches);
+  } else if (cd.hybrid) {  // density expansion on the default path's kernels, channel mixing + element list from the stored X_lm
     launch_soap_forward(cd.d_sp, cd.h, P->b_centres.as<int>(), nc_dev(P, n_ub), n_ub, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
                         P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), st, &launches, 1);
     launch_soap_power_general(cd.d_sp, cd.h, cd.gen, nc_dev(P, n_ub), n_ub, P->b_xlm.as<double>(), P->b_x.as<double>(), P->b_pnorm.as<double>(), st,
@@ -1267,7 +1313,8 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
 
   // virial partial slots
   size_t slots_cap = 0;
-  for (const CoordDev& cd : P->cd) slots_cap += cd.kind == DESC_SOAP ? (size_t)(last - first) : (size_t)((last - first + 3) / 4);
+  for (const CoordDev& cd : P->cd)
+    slots_cap += cd.kind == DESC_SOAP ? (size_t)(last - first) * (cd.grid_passes > 1 ? cd.grid_passes : 1) : (size_t)((last - first + 3) / 4);
   if (want_grad) P->b_vir.ensure(sizeof(double) * 9 * (slots_cap + 1));
   size_t slot = 0;
 
@@ -1291,7 +1338,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
         covariance_stage(P, cd, glob ? 1 : nc, glob ? nullptr : ncd, want_grad, true, st);
         if (want_grad) {
           if (det && det_slots > 0) CUDA_OK(cudaMemsetAsync(P->b_fpair.p, 0, sizeof(double) * 3 * (size_t)det_slots, st));  // (unvisited slots)
-          soap_adjoint_any(P, cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
+          const int vir_blocks = soap_adjoint_any(P, cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat,
                            P->b_x.as<double>(), P->b_xlm.as<double>(), P->b_pnorm.as<double>(), P->b_gvec.as<double>(), cd.dn_pad, P->g_splits,
                            P->g_split_stride, P->b_epart.as<double>(), P->g_tiles_n, d_le, es, det ? P->b_fself.as<double>() : d_force,
                            P->b_vir.as<double>() + 9 * slot, d_lv, st, &launches, det ? P->b_fpair.as<double>() : nullptr);
@@ -1299,7 +1346,7 @@ void calc_device_impl(gap_potential* P, int N, const double* d_pos, const int* d
             k_det_gather<<<(N + 3) / 4, 128, 0, st>>>(N, P->b_joff.as<int>(), P->b_dvals2.as<int>(), P->b_fpair.as<double>(), P->b_fself.as<double>(), d_force);
             launches += 1;
           }
-          slot += nc;
+          slot += (size_t)nc * vir_blocks;
           mark(P, st, ST_SOAP_ADJ);
         } else if (glob) {  // energy only: e_i shared by all centres (IPModel_GAP.f95:454-459)
           soap_adjoint_any(P, cd, P->b_centres.as<int>(), ncd, nc, P->cv_off, P->cv_end, P->cv_j, P->cv_s, d_pos, d_Z, lat, P->b_x.as<double>(),
@@ -1449,6 +1496,7 @@ void gap_potential_finalise(gap_potential* P) {
   P->comm = nullptr;
   for (CoordDev& cd : P->cd) {
     cudaFree(cd.gen_blob);
+    for (SoapDev* q : cd.d_sp_grid) cudaFree(q);
     cudaFree(cd.gen_global);
     cudaFree(cd.d_sp); cudaFree(cd.sp_rows); cudaFree(cd.st_rows); cudaFree(cd.alpha); cudaFree(cd.scut);
     cudaFree(cd.x2); cudaFree(cd.a2); cudaFree(cd.c2); cudaFree(cd.t3); cudaFree(cd.var_mat);
@@ -1462,7 +1510,7 @@ void gap_potential_finalise(gap_potential* P) {
                     &P->b_nn, &P->b_cub, &P->b_minmax, &P->b_off, &P->b_j, &P->b_s, &P->b_d, &P->b_pos, &P->b_Z, &P->b_packed, &P->b_le,
                     &P->b_lv, &P->b_flags, &P->b_scan, &P->b_centres, &P->b_x, &P->b_xlm, &P->b_pnorm, &P->b_acoef, &P->b_gvec, &P->b_epart,
                     &P->b_vir, &P->b_fin, &P->b_xoff, &P->b_xj, &P->b_xs, &P->b_zc, &P->b_velo, &P->b_velo2, &P->b_acc, &P->b_mass, &P->b_ke, &P->b_lastpos, &P->b_disp, &P->b_resid,
-                    &P->b_fpair, &P->b_fself, &P->b_dkeys, &P->b_dkeys2, &P->b_dvals, &P->b_dvals2, &P->b_joff, &P->b_dcub, &P->b_a3idx, &P->b_lambda};
+                    &P->b_fpair, &P->b_fself, &P->b_dkeys, &P->b_dkeys2, &P->b_dvals, &P->b_dvals2, &P->b_joff, &P->b_dcub, &P->b_a3idx, &P->b_lambda, &P->b_xt_pass, &P->b_lam_pass};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : P->ev) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);

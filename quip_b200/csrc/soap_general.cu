@@ -16,7 +16,9 @@
 //  * compression modes on the EQUISPACED_GAUSS basis: X_lm and the neighbour phase do not depend on the variant, so they run on soap.cu's
 //    kernels (forward with skip_power, adjoint with lambda_in); k_soap_power_gen (X_lm -> descriptor) and k_soap_lambda_gen (dE/dx ->
 //    Lambda) supply the variant-specific middle, one small CTA per centre;
-//  * GTO / POLY (radial grid of 3 n_max points, per-l maps) and average=T: k_soap_forward_gen / k_soap_adjoint_gen, one CTA per centre.
+//  * GTO / POLY (radial grid of 3 n_max points, per-l maps): the same, one run of soap.cu's kernels per slice of <= 16 grid points, with
+//    k_soap_power_grid / k_soap_lambda_grid in between;
+//  * average=T (and GTO / POLY in deterministic mode): k_soap_forward_gen / k_soap_adjoint_gen, one CTA per centre.
 //    The neighbours of a centre are compacted and processed in BATCHES: the radial recursions and the harmonics of a whole batch run as
 //    independent items across the CTA's threads (one barrier per batch instead of two per neighbour); the density accumulation and the
 //    adjoint contraction of Lambda~ (stored with the lm index contiguous) against the batch are small FP64 tensor-core GEMMs per l.
@@ -52,9 +54,11 @@ struct GSmem {
 __host__ __device__ inline size_t gcarve(int L, int n, int ns, int d_pad, const SoapGenDev& g, bool adjoint, int NB, GSmem* s, unsigned char* base) {
   const int nlm = (L + 1) * (L + 1), K1 = ns * n, Kg = ns * g.n_grid;
   const size_t nbn = NB > 0 ? GNT : 0;
+  const bool with_xt = NB != 0;  // NB = -1: the radial-grid array without the batch tables (k_soap_power_grid)
+  if (NB < 0) NB = 0;
   size_t o = 0;
   auto take = [&](size_t cnt) { size_t r = o; o += ((cnt + 1) & ~(size_t)1) * sizeof(double); return r; };
-  const size_t oyn = take((size_t)(L + 1) * (L + 2) / 2), oXt = take(NB > 0 ? (size_t)nlm * Kg : 0), oX = take((size_t)nlm * K1),
+  const size_t oyn = take((size_t)(L + 1) * (L + 2) / 2), oXt = take(with_xt ? (size_t)nlm * Kg : 0), oX = take((size_t)nlm * K1),
                oY1 = take((size_t)nlm * g.Ka), oY2 = take((size_t)nlm * g.Kb), odY1 = take(adjoint ? (size_t)nlm * g.Ka : 0),
                odY2 = take(adjoint ? (size_t)nlm * g.Kb : 0), op = take(d_pad), oPhi = take((size_t)NB * (L + 1) * g.n_grid),
                oRr = take(adjoint ? (size_t)NB * (L + 1) * g.n_grid : 0), oYq = take((size_t)NB * nlm), oGq = take(adjoint ? 3 * (size_t)NB * nlm : 0),
@@ -238,6 +242,28 @@ __device__ __forceinline__ void g_lambda_head(const SoapDev* __restrict__ sp, co
   __syncthreads();
 }
 
+// Xt (shared, radial functions on the grid) -> X = Xt . P_l + central term -> xlm (kept for the adjoint) -> descriptor row c
+__device__ __forceinline__ void g_forward_post(const SoapDev* __restrict__ sp, const SoapGenDev& g, const GSmem& s, int c, int i, const int* __restrict__ Z,
+                                               double* __restrict__ x, double* __restrict__ xlm, double* __restrict__ pnorm, int global_mode) {
+  const int L = sp->l_max, n = sp->n_max, ns = sp->n_species, K1 = ns * n, nlm = (L + 1) * (L + 1), ng = g.n_grid, Kg = ns * ng;
+  // radial_coefficient = radial_fun . P_l (:8261-8270); the map is linear, so it is applied once per centre
+  for (int idx = threadIdx.x; idx < nlm * K1; idx += GNT) {
+    const int lm = idx / K1, ic = idx - lm * K1, sk = ic / n, a = ic - sk * n, l = s.l_of[lm];
+    double acc = 0.0;
+    for (int gg = 0; gg < ng; gg++) acc += s.Xt[lm * Kg + sk * ng + gg] * g.P[((size_t)l * ng + gg) * n + a];
+    s.X[idx] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < K1) {  // central atom term (:8151-8182)
+    const int sk = threadIdx.x / n, a = threadIdx.x - sk * n;
+    if (sp->cras || sp->species_Z[sk] == Z[i] || sp->species_Z[sk] == 0) s.X[threadIdx.x] += sp->central_weight * g.c0[a] * 0.28209479177387814347;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nlm * K1; k += GNT) xlm[(size_t)c * nlm * K1 + k] = s.X[k];
+  if (global_mode) return;  // average=T: the power spectrum is taken of the SUM over the centres (k_soap_global_power)
+  g_power_tail(sp, g, s, c, x, pnorm);
+}
+
 __global__ void __launch_bounds__(GNT) k_soap_forward_gen(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ centres,
                                                          const int* __restrict__ n_centres_dev, const int* __restrict__ nbr_off,
                                                          const int* __restrict__ nbr_end, const int* __restrict__ nbr_j, const int* __restrict__ nbr_s,
@@ -298,22 +324,7 @@ __global__ void __launch_bounds__(GNT) k_soap_forward_gen(const SoapDev* __restr
       __syncthreads();
     }
   }
-  // radial_coefficient = radial_fun . P_l (:8261-8270); the map is linear, so it is applied once per centre
-  for (int idx = threadIdx.x; idx < nlm * K1; idx += GNT) {
-    const int lm = idx / K1, ic = idx - lm * K1, sk = ic / n, a = ic - sk * n, l = s.l_of[lm];
-    double acc = 0.0;
-    for (int gg = 0; gg < ng; gg++) acc += s.Xt[lm * Kg + sk * ng + gg] * g.P[((size_t)l * ng + gg) * n + a];
-    s.X[idx] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < K1) {  // central atom term (:8151-8182)
-    const int sk = threadIdx.x / n, a = threadIdx.x - sk * n;
-    if (sp->cras || sp->species_Z[sk] == Z[i] || sp->species_Z[sk] == 0) s.X[threadIdx.x] += sp->central_weight * g.c0[a] * 0.28209479177387814347;
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < nlm * K1; k += GNT) xlm[(size_t)c * nlm * K1 + k] = s.X[k];
-  if (global_mode) return;  // average=T: the power spectrum is taken of the SUM over the centres (k_soap_global_power)
-  g_power_tail(sp, g, s, c, x, pnorm);
+  g_forward_post(sp, g, s, c, i, Z, x, xlm, pnorm, global_mode);
 }
 
 template <int NB>
@@ -563,6 +574,51 @@ __global__ void __launch_bounds__(GNT) k_soap_lambda_gen(const SoapDev* __restri
   for (int k = threadIdx.x; k < nlm * K1; k += GNT) lambda_out[(size_t)c * nlm * K1 + k] = s.X[k];
 }
 
+// ---- GTO / POLY on the default path's kernels: the radial functions of these bases are the same Phi_l(r; r_g) on a grid of 3 n_max points,
+//      followed by a per-l map to n_max functions.  The grid is cut into passes of at most 16 points; each pass is a run of soap.cu's
+//      kernels on a clone of the descriptor whose "basis points" are that slice of the grid, with the identity as basis transform and no
+//      central term (forward with skip_power: xlm = Xt on the slice; adjoint with lambda_in = Lambda~ on the slice).  These two kernels
+//      sit in between: slices of Xt -> X = Xt . P_l + central term -> descriptor, and dE/dx -> Lambda -> Lambda~ = Lambda P_l^T in slices.
+//      Pass buffers: [pass][centre][lm][s * gp + a], pass_stride doubles apart.
+__global__ void __launch_bounds__(GNT) k_soap_power_grid(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ centres,
+                                                         const int* __restrict__ n_centres_dev, const int* __restrict__ Z,
+                                                         const double* __restrict__ xt_pass, size_t pass_stride, int gp, double* __restrict__ x,
+                                                         double* __restrict__ xlm, double* __restrict__ pnorm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x;
+  if (c >= *n_centres_dev) return;
+  const int L = sp->l_max, ns = sp->n_species, nlm = (L + 1) * (L + 1), ng = g.n_grid, Kg = ns * ng, K1p = ns * gp;
+  GSmem s;
+  gcarve(L, sp->n_max, ns, sp->d_pad, g, false, -1, &s, smem_raw);
+  g_tables(sp, s, L, nlm);
+  for (int k = threadIdx.x; k < nlm * Kg; k += GNT) {
+    const int lm = k / Kg, t = k - lm * Kg, sk = t / ng, gg = t - sk * ng, pass = gg / gp, a = gg - pass * gp;
+    s.Xt[k] = xt_pass[(size_t)pass * pass_stride + ((size_t)c * nlm + lm) * K1p + sk * gp + a];
+  }
+  __syncthreads();
+  g_forward_post(sp, g, s, c, centres[c], Z, x, xlm, pnorm, 0);
+}
+
+__global__ void __launch_bounds__(GNT) k_soap_lambda_grid(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ n_centres_dev,
+                                                          const double* __restrict__ x, const double* __restrict__ xlm, const double* __restrict__ pnorm,
+                                                          const double* __restrict__ gvec, int ldg, int g_splits, size_t g_split_stride,
+                                                          double* __restrict__ lam_pass, size_t pass_stride, int gp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int c = blockIdx.x;
+  if (c >= *n_centres_dev) return;
+  const int L = sp->l_max, n = sp->n_max, ns = sp->n_species, nlm = (L + 1) * (L + 1), K1 = ns * n, ng = g.n_grid, Kg = ns * ng, K1p = ns * gp;
+  GSmem s;
+  gcarve(L, n, ns, sp->d_pad, g, true, 0, &s, smem_raw);
+  g_tables(sp, s, L, nlm);
+  g_lambda_head(sp, g, s, c, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride);
+  for (int idx = threadIdx.x; idx < nlm * Kg; idx += GNT) {  // Lambda~ = Lambda P_l^T on the radial grid, written slice by slice
+    const int lm = idx / Kg, t = idx - lm * Kg, sk = t / ng, gg = t - sk * ng, l = s.l_of[lm], pass = gg / gp, a = gg - pass * gp;
+    double acc = 0.0;
+    for (int b = 0; b < n; b++) acc += s.X[lm * K1 + sk * n + b] * g.P[((size_t)l * ng + gg) * n + b];
+    lam_pass[(size_t)pass * pass_stride + ((size_t)c * nlm + lm) * K1p + sk * gp + a] = acc;
+  }
+}
+
 // ---- average=T (global SOAP, descriptors.f95:8357-8367, 8738-9008): ONE descriptor per configuration from the sum of the density
 //      expansions of all centres.  One CTA each: the sum + power spectrum, and the pull-back dE/dx -> Lambda~ shared by all centres.
 __global__ void __launch_bounds__(GNT) k_soap_global_power(const SoapDev* __restrict__ sp, SoapGenDev g, const int* __restrict__ n_centres_dev,
@@ -746,6 +802,26 @@ void launch_soap_lambda_general(const SoapDev* sp, const SoapDev& h, const SoapG
   const size_t sm = gcarve(h.l_max, h.n_max, h.n_species, h.d_pad, g, true, 0, nullptr, nullptr);
   cudaFuncSetAttribute(k_soap_lambda_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   k_soap_lambda_gen<<<n_centres_ub, GNT, sm, st>>>(sp, g, n_centres_dev, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride, lambda_out);
+  *launches += 1;
+}
+
+void launch_soap_power_grid(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* centres, const int* n_centres_dev, int n_centres_ub,
+                            const int* Z, const double* xt_pass, size_t pass_stride, int gp, double* x, double* xlm, double* pnorm, cudaStream_t st,
+                            int* launches) {
+  if (n_centres_ub <= 0) return;
+  const size_t sm = gcarve(h.l_max, h.n_max, h.n_species, h.d_pad, g, false, -1, nullptr, nullptr);
+  cudaFuncSetAttribute(k_soap_power_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_soap_power_grid<<<n_centres_ub, GNT, sm, st>>>(sp, g, centres, n_centres_dev, Z, xt_pass, pass_stride, gp, x, xlm, pnorm);
+  *launches += 1;
+}
+
+void launch_soap_lambda_grid(const SoapDev* sp, const SoapDev& h, const SoapGenDev& g, const int* n_centres_dev, int n_centres_ub, const double* x,
+                             const double* xlm, const double* pnorm, const double* gvec, int ldg, int g_splits, size_t g_split_stride, double* lam_pass,
+                             size_t pass_stride, int gp, cudaStream_t st, int* launches) {
+  if (n_centres_ub <= 0) return;
+  const size_t sm = gcarve(h.l_max, h.n_max, h.n_species, h.d_pad, g, true, 0, nullptr, nullptr);
+  cudaFuncSetAttribute(k_soap_lambda_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_soap_lambda_grid<<<n_centres_ub, GNT, sm, st>>>(sp, g, n_centres_dev, x, xlm, pnorm, gvec, ldg, g_splits, g_split_stride, lam_pass, pass_stride, gp);
   *launches += 1;
 }
 
