@@ -62,7 +62,9 @@ int gap_potential_set_partition(gap_potential* pot, int rank, int n_ranks);
  * reduce-scatter + all-gather by push from 4 ranks on; csrc/comm.cu;
  * GAP_B200_P2P=0 forces NCCL; GAP_B200_P2P_MAX_BYTES, default 8 MiB, is the largest buffer the peer kernel takes; a rank that waits longer
  * than GAP_B200_P2P_TIMEOUT_S, default 60, for the others' partials reports an error instead of hanging; GAP_B200_P2P_LL_MIN_RANKS, default 4,
- * and GAP_B200_P2P_LL_MAX_DOUBLES, default 2^20, bound the use of the low-latency variant).  n_ranks = 1 removes the communicator. */
+ * and GAP_B200_P2P_LL_MAX_DOUBLES, default 2^20, bound the use of the low-latency variant).  The peer kernels' blocks spin on data written by the
+ * other GPUs, so they assume that the ranks run the same sequence of evaluations and that each rank's GPU is not saturated by unrelated work.
+ * n_ranks = 1 removes the communicator. */
 #define GAP_COMM_ID_BYTES 128
 int gap_comm_get_unique_id(char* id /* GAP_COMM_ID_BYTES */);
 int gap_potential_set_comm(gap_potential* pot, const char* id /* GAP_COMM_ID_BYTES */, int rank, int n_ranks);
