@@ -201,3 +201,13 @@ def test_c_example_compiles_against_the_header_and_fails_loudly_without_a_gpu(go
         assert "Energy =" in r.stdout
     else:
         assert "no CPU fallback" in r.stderr
+
+
+def test_xml_with_comments_processing_instructions_and_embedded_training_data(golden):
+    # a GAP XML as gap_fit writes it with do_copy_at_file=T: prolog, comments, and the training set inside a CDATA block whose text contains
+    # angle brackets, quotes and ampersands (IPModel_GAP.f95:618-700 goes through FoX; the scanner here has to skip all of it)
+    xml = open(os.path.join(golden, "GAP.xml")).read()
+    wrapped = ('<?xml version="1.0"?>\n<!-- fitted by gap_fit <test> -->\n<GAP_wrapper>\n' + xml +
+               '\n<XYZ_data compression="none"><![CDATA[2\nLattice="10 0 0 0 10 0 0 0 10" Properties=species:S:1:pos:R:3 note="a<b>c & d"\n'
+               'H 0 0 0\nH 0 0 0.74\n]]></XYZ_data>\n</GAP_wrapper>\n')
+    assert P.model_describe(param_str=wrapped, base_dir=golden) == P.model_describe(param_str=xml, base_dir=golden)
